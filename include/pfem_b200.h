@@ -1,0 +1,162 @@
+/* =====================================================================================
+ * pfem_b200.h -- C ABI of the B200-native (sm_100a, fp64) PFEM3D finite-element hot path.
+ *
+ * Drop-in boundary for ImperatorS79/PFEM ("PFEM3D").  The reference has no plugin ABI; its
+ * seams are C++ virtuals:
+ *     virtual bool Equation::solve()                 srcs/simulation/Equation.hpp:68
+ *     MatrixBuilder<dim> get / set vocabulary      srcs/simulation/matricesBuilder/MatricesBuilder.hpp:54-85
+ *     the linear solver object m_solver              srcs/simulation/physics/IncompNewton/MomContEquationPSPG.inl:281-290
+ * Concrete equations are created only at the REGISTER_EQ sites
+ * (physics/IncompNewton/Solver.cpp:6-10,38-40; physics/WCompNewton/Solver.cpp:9-13,45-54).
+ * The functions below are what replacement Equation subclasses (shim/pfem_b200_equations.hpp)
+ * bind to; each one cites the reference code it replaces.  INTEGRATION.md shows the host patch.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every pointer is a HOST pointer owned by the caller and is
+ *    not retained after the call returns (device-pointer variants are suffixed _device);
+ *  - nodal vectors use the reference's flat layout q[n + s*nNodes]
+ *    (getQFromNodesStates, srcs/simulation/utility/StatesFromToQ.hpp:21-34);
+ *  - state order: incompressible [u,v,(w),p] (physics/IncompNewton/Problem.cpp:13-14),
+ *    weakly compressible [u,v,(w),p,rho,ax,ay,(az)] (physics/WCompNewton/Problem.cpp:17-18);
+ *  - global dof of the PSPG system: node + d*nNodes, pressure block last (PSPG.inl:71-86);
+ *  - all arithmetic is IEEE fp64; indices are int32 on the device;
+ *  - return value: 0 ok; >0 recoverable numerical outcome (the shim maps it to `return false`,
+ *    i.e. the reference's dt-halving path, IncompNewton/Solver.cpp:216-224); <0 fatal, message
+ *    in pfem_last_error().  Nothing throws across this boundary.
+ *  - a context is bound to one GPU, owns one CUDA stream and is not thread-safe; calls are
+ *    synchronous on return.  There is NO CPU fallback: without a CUDA device pfem_create fails.
+ * ===================================================================================== */
+#ifndef PFEM_B200_H
+#define PFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFEM_ABI_VERSION 1
+
+/* status codes */
+#define PFEM_OK 0
+#define PFEM_NOT_CONVERGED 1 /* Krylov / Picard hit maxIter (PicardAlgo.cpp:55-65) */
+#define PFEM_NAN 2           /* NaN residual (PicardAlgo.cpp:79-86) or NaN dt (WCompNewton/Solver.cpp:231-232) */
+#define PFEM_ERR_INVALID (-1)
+#define PFEM_ERR_CUDA (-2)
+#define PFEM_ERR_STATE (-3) /* call order: e.g. assemble before set_topology */
+#define PFEM_ERR_COMM (-4)
+
+/* node flag bits (Node.hpp:93-105; isFree == node belongs to no element, Node.inl:48-51) */
+#define PFEM_NODE_BOUND 1u
+#define PFEM_NODE_FREE 2u
+#define PFEM_NODE_FIXED 4u
+#define PFEM_NODE_FREE_SURFACE 8u
+
+typedef struct pfem_ctx pfem_ctx;
+
+/* material + solver scalars of MomContEqIncompNewton (MomContEquation.inl:28-30, 239-243; dt = Solver::getTimeStep) */
+typedef struct pfem_pspg_params {
+    double rho, mu, dt;
+    double bodyForce[3];
+} pfem_pspg_params;
+
+/* ContEqWCompNewton / MomEqWCompNewton scalars (ContEquation.inl:26-37; MomEquation.inl:28-29, 149-153);
+ * meduri != 0  <=>  stabilization == "Meduri" (ContEquation.inl:387-390) */
+typedef struct pfem_wc_params {
+    double mu, K0, K0p, rhoStar;
+    double bodyForce[3];
+    int32_t meduri;
+} pfem_wc_params;
+
+typedef struct pfem_info {
+    int32_t dim, device, nRanks, rank;
+    int64_t nNodes, nElems, nDof;
+    int64_t nnzBlocks;     /* (dim+1)x(dim+1) node blocks held on the device          */
+    int64_t nnzReference;  /* nnz of the reference's m_A (row masks + explicit zeros)  */
+    int64_t deviceBytes;   /* device memory owned by the context                       */
+    int32_t maxElemsPerNode, maxNeighbours;
+} pfem_info;
+
+/* ---- lifetime ------------------------------------------------------------------- */
+int pfem_abi_version(void);
+/* dim = Mesh::getDim() (2|3); device = CUDA ordinal.  Fails with PFEM_ERR_CUDA when no device is usable. */
+int pfem_create(pfem_ctx** ctx, int dim, int device);
+int pfem_destroy(pfem_ctx* ctx);
+const char* pfem_last_error(const pfem_ctx* ctx);
+/* Run on a caller-provided cudaStream_t (NULL: the context's own stream).  Lets a harness time with its own events. */
+int pfem_set_stream(pfem_ctx* ctx, void* cudaStream);
+int pfem_get_info(const pfem_ctx* ctx, pfem_info* info);
+
+/* ---- mesh: once per remesh (Mesh::remesh, Mesh.cpp:919-926 stays on the host) ------ */
+/* elemNodes: nElems x (dim+1) row-major, as Element::m_nodesIndexes (Element.hpp:121; Element.inl:18-21), positive
+ * orientation.  nodeFlags: PFEM_NODE_* per node.  Builds node->element incidence, the node-block sparsity pattern of
+ * m_A and (multi-GPU) the partition -- the device counterpart of the pattern work inside setFromTriplets (PSPG.inl:136). */
+int pfem_set_topology(pfem_ctx* ctx, int64_t nNodes, int64_t nElems, const uint64_t* elemNodes, const uint8_t* nodeFlags);
+/* Node::m_position (Node.hpp:93), layout x[n + d*nNodes] */
+int pfem_set_positions(pfem_ctx* ctx, const double* x);
+int pfem_get_positions(pfem_ctx* ctx, double* x);
+/* Mesh::saveNodesList / restoreNodesList (Mesh.cpp:1019-1053) -- positions only; states are caller-managed */
+int pfem_snapshot_positions(pfem_ctx* ctx);
+int pfem_restore_positions(pfem_ctx* ctx);
+/* Mesh::updateNodesPosition (fromSnapshot=0, Mesh.cpp:1101-1137) / updateNodesPositionFromSave (=1, :1238-1277):
+ * x = base + delta for nodes that are not isFixed; delta layout n + d*nNodes. */
+int pfem_move_positions(pfem_ctx* ctx, const double* delta, int fromSnapshot);
+/* setNodesStatesfromQ / getQFromNodesStates (StatesFromToQ.hpp:9-34): states [first, first+count) */
+int pfem_set_states(pfem_ctx* ctx, int first, int count, const double* q);
+int pfem_get_states(pfem_ctx* ctx, int first, int count, double* q);
+/* Host-evaluated Lua velocity BC: mask[n] != 0 <=> node.isBound() && getBcTagFlags(tag, flag 0); values[n + d*nNodes]
+ * = "<type>V"(pos, t+dt) (PSPG.inl:206-214; WCompNewton/MomEquation.inl:355-364). */
+int pfem_set_dirichlet(pfem_ctx* ctx, const uint8_t* mask, const double* values);
+
+/* ---- incompressible PSPG (MomContEqIncompNewton<dim>) ------------------------------- */
+/* m_buildAbPSPG + m_applyBCPSPG (PSPG.inl:7-146, 149-235) with gamma = 0.  qPrev: (dim+1)*nNodes. */
+int pfem_pspg_assemble(pfem_ctx* ctx, const pfem_pspg_params* p, const double* qPrev);
+/* The same split in two, so that a caller that keeps qPrev across Picard iterations (PSPG.inl:273, 298 pass the same
+ * qPrevVec[0]) uploads it once: set_qprev copies it to the device, assemble_resident assembles from device-resident data. */
+int pfem_pspg_set_qprev(pfem_ctx* ctx, const double* qPrev);
+int pfem_pspg_assemble_resident(pfem_ctx* ctx, const pfem_pspg_params* p);
+/* Replaces m_solver.analyzePattern/factorize/solve (PSPG.inl:281-290) by Jacobi-preconditioned BiCGSTAB on the device.
+ * q (out, (dim+1)*nNodes) may be NULL to leave the solution on the device.  relTol is on ||b - A q|| / ||b||.
+ * Returns PFEM_NOT_CONVERGED / PFEM_NAN like a failed factorisation would (PSPG.inl:304-312). */
+int pfem_pspg_solve(pfem_ctx* ctx, double relTol, int maxIter, double* q, int* iters, double* relRes);
+/* ||A q - b||_2 of the currently assembled system (Res::Ax_f, PSPG.inl:368).  q NULL: the last device solution. */
+int pfem_pspg_residual(pfem_ctx* ctx, const double* q, double* resAxf);
+/* One body of the Picard loop (PSPG.inl:278-313 + :366-370): solve -> node states <- q -> positions = snapshot + dt*v
+ * -> reassemble (+BC) -> res = ||A q - b||.  Requires pfem_snapshot_positions + pfem_pspg_assemble first (m_prepare,
+ * PSPG.inl:264-277).  q may be NULL. */
+int pfem_pspg_picard_iter(pfem_ctx* ctx, const pfem_pspg_params* p, const double* qPrev, double relTol, int maxIter,
+                          double* q, double* resAxf, int* iters);
+/* The assembled system in the reference's own format: column-major compressed m_A (MomContEquation.hpp:70) with the
+ * reference's pattern (row masks, identity rows, explicit zeros of eliminated Dirichlet columns) and m_b.
+ * Call with colPtr == NULL to obtain *nnz only.  colPtr: nDof+1. */
+int pfem_pspg_export_csc(pfem_ctx* ctx, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b);
+/* y = A x with the assembled matrix (the sparse*dense product of PSPG.inl:368), host vectors of nDof */
+int pfem_pspg_matvec(pfem_ctx* ctx, const double* x, double* y);
+
+/* ---- weakly compressible explicit step --------------------------------------------- */
+/* SolverWCompNewton::m_solveWCompNewtonNoT body up to the remesh (WCompNewton/Solver.cpp:236-263): half kick, move,
+ * ContEqWCompNewton::solve (CDS_dpdt, ContEquation.inl:123-148), MomEqWCompNewton::solve (MomEquation.inl:201-226).
+ * Operates on the device-resident states; nSteps > 1 repeats with the CFL time step recomputed on the device between
+ * steps (computeNextDT) when adaptDT != 0. */
+int pfem_wc_step(pfem_ctx* ctx, const pfem_wc_params* p, double dt);
+/* SolverWCompNewton::computeNextDT (WCompNewton/Solver.cpp:192-234) incl. Element::getRin (Element.cpp:226-294) */
+int pfem_wc_next_dt(pfem_ctx* ctx, const pfem_wc_params* p, double securityCoeff, double maxDT, double* dt);
+
+/* ---- multi-GPU (one context per rank/GPU; elements sharded by RCB) ---- */
+/* ncclUniqueId: the 128 opaque bytes of ncclGetUniqueId obtained by rank 0 (pfem_comm_unique_id) and broadcast by the
+ * launcher.  After this call pfem_set_topology expects the GLOBAL mesh on every rank and keeps only this rank's part. */
+int pfem_comm_unique_id(void* id128);
+int pfem_comm_init(pfem_ctx* ctx, int nRanks, int rank, const void* id128);
+
+/* ---- instrumentation (phase names = the reference's m_accumalatedTimes keys, PSPG.inl:19-369) ---- */
+int pfem_profile_enable(pfem_ctx* ctx, int on);
+int pfem_profile_reset(pfem_ctx* ctx);
+/* accumulated device milliseconds (CUDA events on the context's stream) and call count of one phase */
+int pfem_profile_get(pfem_ctx* ctx, const char* phase, double* ms, int64_t* calls);
+/* number of kernels this library has launched on the context since creation */
+int pfem_launch_count(const pfem_ctx* ctx, int64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFEM_B200_H */

@@ -1,0 +1,191 @@
+"""ctypes front-end of the CPU oracle (oracle/pfem_oracle.cpp) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
+import this module.  PARITY UNPINNED: see the header of pfem_oracle.cpp.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import scipy.sparse as sp
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "_build", "libpfem_oracle.so")
+_lib = None
+
+PHASES = ["Prepare matrix assembly", "Compute triplets", "Push back (n, n, 1)", "Assemble matrix",
+          "Assemble vector", "Apply boundary conditions"]  # timer names of PSPG.inl:19-145, 276
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "pfem_oracle.cpp")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            build()
+        L = C.CDLL(_SO)
+        dp, ip, bp, i64 = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.c_int64
+        L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.argtypes = [C.c_int]
+        L.oracle_pspg_elements.argtypes = [C.c_int, i64, i64, ip, dp, dp, dp, dp, dp, dp, dp]
+        L.oracle_pspg_build.restype = C.c_void_p
+        L.oracle_pspg_build.argtypes = [C.c_int, i64, i64, ip, dp, dp, dp, bp, dp, C.c_int, bp, dp, dp, dp]
+        L.oracle_csc_nnz.restype = i64
+        L.oracle_csc_nnz.argtypes = [C.c_void_p]
+        L.oracle_csc_copy.argtypes = [C.c_void_p, ip, C.POINTER(C.c_int32), dp]
+        L.oracle_csc_free.argtypes = [C.c_void_p]
+        L.oracle_move_positions.argtypes = [C.c_int, i64, bp, dp, dp, dp]
+        L.oracle_wc_step.argtypes = [C.c_int, i64, i64, ip, dp, bp, bp, dp, dp, dp, dp, dp, dp, C.c_double]
+        L.oracle_wc_next_dt.restype = C.c_double
+        L.oracle_wc_next_dt.argtypes = [C.c_int, i64, i64, ip, dp, dp, dp, dp, dp, C.c_double, C.c_double]
+        L.oracle_csc_matvec.argtypes = [i64, ip, C.POINTER(C.c_int32), dp, dp, dp]
+        L.oracle_bicgstab_csr.restype = C.c_int
+        L.oracle_bicgstab_csr.argtypes = [i64, ip, C.POINTER(C.c_int32), dp, dp, dp, C.c_double, C.c_int, dp]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _i(a):
+    assert a.dtype == np.int64 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def _i32(a):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _b(a):
+    assert a.dtype == np.uint8 and a.flags.c_contiguous
+    return a.ctypes.data_as(C.POINTER(C.c_uint8))
+
+
+def pspg_param_array(rho, mu, dt, body_force):
+    bf = np.zeros(3)
+    bf[: len(body_force)] = body_force
+    return np.array([rho, mu, dt, bf[0], bf[1], bf[2]], dtype=np.float64)
+
+
+def wc_param_array(mu, K0, K0p, rhoStar, body_force, meduri=True):
+    bf = np.zeros(3)
+    bf[: len(body_force)] = body_force
+    return np.array([mu, K0, K0p, rhoStar, bf[0], bf[1], bf[2], 1.0 if meduri else 0.0], dtype=np.float64)
+
+
+def pspg_elements(mesh, vcur, q_prev, params):
+    """Per-element (Ae, be, tau): MB.inl + PSPG.inl:26-53."""
+    nt = (mesh.dim + 1) ** 2
+    ne = mesh.n_elems
+    Ae = np.zeros((ne, nt, nt))
+    be = np.zeros((ne, nt))
+    tau = np.zeros(ne)
+    rc = lib().oracle_pspg_elements(mesh.dim, mesh.n_nodes, ne, _i(mesh.conn), _d(mesh.x), _d(vcur), _d(q_prev),
+                                    _d(params), _d(Ae), _d(be), _d(tau))
+    assert rc == 0
+    return Ae, be, tau
+
+
+def pspg_build(mesh, vcur, q_prev, params, apply_bc=True, x=None, phase_sec=None):
+    """m_buildAbPSPG (+ m_applyBCPSPG): returns (A as scipy CSC with explicit zeros kept, b)."""
+    L = lib()
+    n_dof = (mesh.dim + 1) * mesh.n_nodes
+    b = np.zeros(n_dof)
+    x = mesh.x if x is None else x
+    ph = np.zeros(6) if phase_sec is None else phase_sec
+    h = L.oracle_pspg_build(mesh.dim, mesh.n_nodes, mesh.n_elems, _i(mesh.conn), _d(x), _d(vcur), _d(q_prev),
+                            _b(mesh.flags), _d(params), 1 if apply_bc else 0, _b(mesh.dir_mask), _d(mesh.dir_val),
+                            _d(b), _d(ph))
+    assert h
+    nnz = L.oracle_csc_nnz(h)
+    col_ptr = np.zeros(n_dof + 1, dtype=np.int64)
+    row_idx = np.zeros(nnz, dtype=np.int32)
+    val = np.zeros(nnz)
+    L.oracle_csc_copy(h, _i(col_ptr), _i32(row_idx), _d(val))
+    L.oracle_csc_free(h)
+    A = sp.csc_matrix((val, row_idx, col_ptr), shape=(n_dof, n_dof))  # no sum_duplicates/eliminate_zeros
+    return A, b
+
+
+def move_positions(mesh, delta, base):
+    x = base.copy()
+    lib().oracle_move_positions(mesh.dim, mesh.n_nodes, _b(mesh.flags), _d(np.ascontiguousarray(delta)), _d(base), _d(x))
+    return x
+
+
+def wc_step(mesh, x, state, params, dt):
+    """One explicit step (WC/Solver.cpp:236-263).  Returns new (x, state) copies."""
+    x = x.copy()
+    st = {k: v.copy() for k, v in state.items()}
+    rc = lib().oracle_wc_step(mesh.dim, mesh.n_nodes, mesh.n_elems, _i(mesh.conn), _d(x), _b(mesh.flags),
+                              _b(mesh.dir_mask), _d(mesh.dir_val), _d(st["v"]), _d(st["acc"]), _d(st["p"]),
+                              _d(st["rho"]), _d(params), float(dt))
+    assert rc == 0
+    return x, st
+
+
+def wc_next_dt(mesh, x, state, params, security_coeff, max_dt):
+    return lib().oracle_wc_next_dt(mesh.dim, mesh.n_nodes, mesh.n_elems, _i(mesh.conn), _d(x), _d(state["v"]),
+                                   _d(state["p"]), _d(state["rho"]), _d(params), float(security_coeff), float(max_dt))
+
+
+def bicgstab(A_csr, b, tol=1e-12, max_iter=10000, x0=None):
+    A_csr = A_csr.tocsr()
+    n = A_csr.shape[0]
+    x = np.zeros(n) if x0 is None else x0.copy()
+    rr = np.zeros(1)
+    it = lib().oracle_bicgstab_csr(n, _i(A_csr.indptr.astype(np.int64)), _i32(A_csr.indices.astype(np.int32)),
+                                   _d(np.ascontiguousarray(A_csr.data)), _d(b), _d(x), tol, max_iter, _d(rr))
+    return x, it, float(rr[0])
+
+
+def num_threads():
+    return lib().oracle_num_threads()
+
+
+# --------------------------------------------------------------------------------------
+# Picard driver (PicardAlgo.cpp:31-94 + PSPG.inl:262-373) with scipy SuperLU standing in for
+# Eigen::SparseLU (COLAMD).  residual = "Ax_f" (absolute ||A q - b||_2, PSPG.inl:368).
+# --------------------------------------------------------------------------------------
+def pspg_picard(mesh, q_state, q_prev, params, max_iter=10, min_res=1e-6, direct_solve=None):
+    import scipy.sparse.linalg as spla
+
+    dim, nn = mesh.dim, mesh.n_nodes
+    dt = params[2]
+    if direct_solve is None:
+        def direct_solve(A, b):
+            return spla.splu(A.tocsc(), permc_spec="COLAMD").solve(b)
+    x_save = mesh.x.copy()                       # Mesh::saveNodesList
+    vcur = q_state[: dim * nn].copy()            # node states (used by tau)
+    A, b = pspg_build(mesh, vcur, q_prev, params, True, x=x_save)   # m_prepare
+    q = np.zeros_like(q_prev)
+    res = np.finfo(np.float64).max
+    it = 0
+    x = x_save
+    history = []
+    while res > min_res:
+        if it > max_iter:
+            return dict(ok=False, q=q, x=x_save, iters=it, res=res, history=history)
+        q = direct_solve(A, b)
+        vcur = q[: dim * nn].copy()              # setNodesStatesfromQ (PSPG.inl:293)
+        x = move_positions(mesh, q[: dim * nn] * dt, x_save)  # updateNodesPositionFromSave (PSPG.inl:294-295)
+        A, b = pspg_build(mesh, vcur, q_prev, params, True, x=x)
+        res = float(np.linalg.norm(A @ q - b))
+        history.append(res)
+        if np.isnan(res):
+            return dict(ok=False, q=q, x=x_save, iters=it, res=res, history=history)
+        it += 1
+    return dict(ok=True, q=q, x=x, iters=it, res=res, history=history, A=A, b=b)

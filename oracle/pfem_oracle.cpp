@@ -1,0 +1,991 @@
+// =====================================================================================
+// oracle/pfem_oracle.cpp  --  TEST INFRASTRUCTURE ONLY.  NOT PART OF THE PRODUCT PATH.
+//
+// CPU restatement (plain C++17 + OpenMP, no Eigen) of the per-time-step finite-element
+// hot path of PFEM3D (ImperatorS79/PFEM).  Every function cites the reference file:line
+// it restates (paths relative to /root/reference/).  The arithmetic deliberately follows
+// the reference's *literal* structure -- Gauss-point loops calling a factor functor,
+// dense B^T*ddev*B products, triplets -> duplicate-summing CSC compression, serial nodal
+// scatters -- and NOT the closed forms the CUDA kernels use, so that a CUDA-vs-oracle
+// comparison is a comparison of two independent derivations.
+//
+// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
+// (CMakeLists.txt:88 enable_testing() with zero add_test) and cannot be compiled in this
+// environment (needs Eigen, CGAL, gmsh, Lua/sol2 -- all absent, no network).  This file is
+// therefore pinned only by (i) a second, independent numpy restatement
+// (oracle/literal_numpy.py), (ii) algebraic invariants (tests/test_oracle_invariants.py)
+// and (iii) scipy SuperLU as the stand-in for Eigen::SparseLU.
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+// may load this library.
+// =====================================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------- node flag bits (ABI)
+constexpr uint8_t F_BOUND = 1, F_FREE = 2, F_FIXED = 4, F_FS = 8;
+
+// ------------------------------------------------------------------------------------
+// Quadrature tables.  srcs/mesh/Mesh.cpp:342-414 (points), :416-470 (weights),
+// :472-488 (reference size), :490-530 (shape functions); 2-D 3-point, 3-D 4-point rules
+// selected by MomContEquation.inl:12-23 / WCompNewton/MomEquation.inl:13-24.
+// ------------------------------------------------------------------------------------
+template <int DIM> struct Quad;
+template <> struct Quad<2> {
+    static constexpr int NGP = 3;
+    static void gp(double g[3][3]) {
+        const double p[3][3] = {{1.0 / 6.0, 1.0 / 6.0, 0.0}, {1.0 / 6.0, 2.0 / 3.0, 0.0}, {2.0 / 3.0, 1.0 / 6.0, 0.0}};
+        std::memcpy(g, p, sizeof(p));
+    }
+    static double w(int) { return 1.0 / 3.0; }
+    static double ref() { return 0.5; }
+};
+template <> struct Quad<3> {
+    static constexpr int NGP = 4;
+    static void gp(double g[4][3]) {
+        const double p[4][3] = {{0.585410196624968, 0.138196601125011, 0.138196601125011},
+                                {0.138196601125011, 0.585410196624968, 0.138196601125011},
+                                {0.138196601125011, 0.138196601125011, 0.585410196624968},
+                                {0.138196601125011, 0.138196601125011, 0.138196601125011}};
+        std::memcpy(g, p, sizeof(p));
+    }
+    static double w(int) { return 0.25; }
+    static double ref() { return 0.16666666666666666666666666666667; }
+};
+
+// ------------------------------------------------------------------------------------
+// Element geometry.  srcs/mesh/Element.cpp:15-69 (J), :71-86 (detJ, Sarrus), :88-135
+// (cofactor inverse, each entry divided by detJ).
+// ------------------------------------------------------------------------------------
+template <int DIM> struct Geo {
+    double J[3][3];
+    double invJ[3][3];
+    double detJ;
+};
+
+template <int DIM>
+void computeGeo(const double* x, int64_t nNodes, const int64_t* en, Geo<DIM>& G) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) G.J[i][j] = G.invJ[i][j] = 0.0;
+    auto X = [&](int node, int d) { return x[en[node] + (int64_t)d * nNodes]; };
+    for (int d = 0; d < DIM; ++d)
+        for (int k = 0; k < DIM; ++k) G.J[d][k] = X(k + 1, d) - X(0, d);
+    auto& J = G.J;
+    if constexpr (DIM == 2) {
+        G.detJ = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+        G.invJ[0][0] = J[1][1] / G.detJ;
+        G.invJ[0][1] = -J[0][1] / G.detJ;
+        G.invJ[1][0] = -J[1][0] / G.detJ;
+        G.invJ[1][1] = J[0][0] / G.detJ;
+    } else {
+        G.detJ = J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
+                 J[2][0] * J[1][1] * J[0][2] - J[2][1] * J[1][2] * J[0][0] - J[2][2] * J[1][0] * J[0][1];
+        const double d = G.detJ;
+        G.invJ[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / d;
+        G.invJ[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) / d;
+        G.invJ[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / d;
+        G.invJ[1][0] = (J[2][0] * J[1][2] - J[1][0] * J[2][2]) / d;
+        G.invJ[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) / d;
+        G.invJ[1][2] = (J[1][0] * J[0][2] - J[0][0] * J[1][2]) / d;
+        G.invJ[2][0] = (J[1][0] * J[2][1] - J[2][0] * J[1][1]) / d;
+        G.invJ[2][1] = (J[2][0] * J[0][1] - J[0][0] * J[2][1]) / d;
+        G.invJ[2][2] = (J[0][0] * J[1][1] - J[1][0] * J[0][1]) / d;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// MatrixBuilder restatement.  srcs/simulation/matricesBuilder/MatricesBuilder.inl.
+// NPE = dim+1 nodes, NS = Voigt size (3 | 6), ND = dim*NPE velocity dofs per element.
+// Factor functors take the shape-function row N_g, exactly where the reference calls its
+// std::function (MB.inl:223, 284, 300, 316, 332, 349, 380).
+// ------------------------------------------------------------------------------------
+template <int DIM> struct MB {
+    static constexpr int NPE = DIM + 1;
+    static constexpr int NS = DIM * DIM - 2 * DIM + 3;
+    static constexpr int ND = DIM * NPE;
+    static constexpr int NGP = Quad<DIM>::NGP;
+
+    double N[NGP][NPE];          // m_NHD        (MB.inl:26-45)
+    double NtN[NGP][NPE][NPE];   // m_NhdTNhd    (MB.inl:72-76)
+    double Nt[NGP][DIM][ND];     // m_NHDtilde   (MB.inl:28-42)
+    double w[NGP];
+    double ref;
+    double ddev[NS][NS];
+    double m[NS];
+
+    MB() {
+        double gp[NGP][3];
+        Quad<DIM>::gp(gp);
+        for (int g = 0; g < NGP; ++g) {
+            w[g] = Quad<DIM>::w(g);
+            // Mesh.cpp:509-519
+            double s = 1.0;
+            for (int d = 0; d < DIM; ++d) s -= gp[g][d];
+            N[g][0] = s;
+            for (int d = 0; d < DIM; ++d) N[g][d + 1] = gp[g][d];
+            for (int r = 0; r < DIM; ++r)
+                for (int c = 0; c < ND; ++c) Nt[g][r][c] = 0.0;
+            for (int r = 0; r < DIM; ++r)
+                for (int k = 0; k < NPE; ++k) Nt[g][r][r * NPE + k] = N[g][k];
+            for (int i = 0; i < NPE; ++i)
+                for (int j = 0; j < NPE; ++j) NtN[g][i][j] = N[g][i] * N[g][j];
+        }
+        ref = Quad<DIM>::ref();
+        for (int i = 0; i < NS; ++i) {
+            m[i] = 0;
+            for (int j = 0; j < NS; ++j) ddev[i][j] = 0;
+        }
+    }
+
+    // MB.inl:93-127
+    static void gradN(const Geo<DIM>& G, double g[DIM][NPE]) {
+        for (int d = 0; d < DIM; ++d) {
+            double s = -G.invJ[0][d];
+            for (int k = 1; k < DIM; ++k) s = s - G.invJ[k][d];
+            g[d][0] = s;
+            for (int k = 0; k < DIM; ++k) g[d][k + 1] = G.invJ[k][d];
+        }
+    }
+    // MB.inl:130-164
+    static void Bmat(const double g[DIM][NPE], double B[NS][ND]) {
+        for (int i = 0; i < NS; ++i)
+            for (int j = 0; j < ND; ++j) B[i][j] = 0.0;
+        if constexpr (DIM == 2) {
+            for (int k = 0; k < 3; ++k) {
+                B[0][k] = B[2][3 + k] = g[0][k];
+                B[1][3 + k] = B[2][k] = g[1][k];
+            }
+        } else {
+            for (int k = 0; k < 4; ++k) {
+                B[0][k] = B[3][4 + k] = B[4][8 + k] = g[0][k];
+                B[1][4 + k] = B[3][k] = B[5][8 + k] = g[1][k];
+                B[2][8 + k] = B[4][k] = B[5][4 + k] = g[2][k];
+            }
+        }
+    }
+    // MB.inl:217-229
+    template <class F> void getM(const Geo<DIM>& G, F&& f, double M[NPE][NPE]) const {
+        for (int i = 0; i < NPE; ++i)
+            for (int j = 0; j < NPE; ++j) M[i][j] = 0.0;
+        for (int g = 0; g < NGP; ++g) {
+            const double fg = f(N[g]);
+            for (int i = 0; i < NPE; ++i)
+                for (int j = 0; j < NPE; ++j) M[i][j] += fg * NtN[g][i][j] * w[g];
+        }
+        const double s = G.detJ * ref;
+        for (int i = 0; i < NPE; ++i)
+            for (int j = 0; j < NPE; ++j) M[i][j] *= s;
+    }
+    // MB.inl:277-290   K = detJ*ref*fact * B^T * ddev * B  (evaluated left to right)
+    template <class F> void getK(const Geo<DIM>& G, const double B[NS][ND], F&& f, double K[ND][ND]) const {
+        double fact = 0;
+        for (int g = 0; g < NGP; ++g) fact += f(N[g]) * w[g];
+        const double s = G.detJ * ref * fact;
+        double T1[ND][NS], T2[ND][NS];
+        for (int i = 0; i < ND; ++i)
+            for (int k = 0; k < NS; ++k) T1[i][k] = s * B[k][i];
+        for (int i = 0; i < ND; ++i)
+            for (int k = 0; k < NS; ++k) {
+                double a = 0;
+                for (int l = 0; l < NS; ++l) a += T1[i][l] * ddev[l][k];
+                T2[i][k] = a;
+            }
+        for (int i = 0; i < ND; ++i)
+            for (int j = 0; j < ND; ++j) {
+                double a = 0;
+                for (int l = 0; l < NS; ++l) a += T2[i][l] * B[l][j];
+                K[i][j] = a;
+            }
+    }
+    // MB.inl:293-306   D = detJ*ref * sumWNT * m^T * B
+    template <class F> void getD(const Geo<DIM>& G, const double B[NS][ND], F&& f, double D[NPE][ND]) const {
+        double sumWNT[NPE];
+        for (int i = 0; i < NPE; ++i) sumWNT[i] = 0;
+        for (int g = 0; g < NGP; ++g) {
+            const double fg = f(N[g]);
+            for (int i = 0; i < NPE; ++i) sumWNT[i] += fg * N[g][i] * w[g];
+        }
+        const double s = G.detJ * ref;
+        double mB[ND];
+        for (int j = 0; j < ND; ++j) {
+            double a = 0;
+            for (int l = 0; l < NS; ++l) a += m[l] * B[l][j];
+            mB[j] = a;
+        }
+        for (int i = 0; i < NPE; ++i)
+            for (int j = 0; j < ND; ++j) D[i][j] = (s * sumWNT[i]) * mB[j];
+    }
+    // MB.inl:309-322
+    template <class F> void getL(const Geo<DIM>& G, const double g[DIM][NPE], F&& f, double L[NPE][NPE]) const {
+        double fact = 0;
+        for (int q = 0; q < NGP; ++q) fact += f(N[q]) * w[q];
+        const double s = G.detJ * ref * fact;
+        for (int i = 0; i < NPE; ++i)
+            for (int j = 0; j < NPE; ++j) {
+                double a = 0;
+                for (int d = 0; d < DIM; ++d) a += (s * g[d][i]) * g[d][j];
+                L[i][j] = a;
+            }
+    }
+    // MB.inl:325-338
+    template <class F> void getC(const Geo<DIM>& G, const double g[DIM][NPE], F&& f, double C[NPE][ND]) const {
+        double sumNW[DIM][ND];
+        for (int r = 0; r < DIM; ++r)
+            for (int c = 0; c < ND; ++c) sumNW[r][c] = 0;
+        for (int q = 0; q < NGP; ++q) {
+            const double fg = f(N[q]);
+            for (int r = 0; r < DIM; ++r)
+                for (int c = 0; c < ND; ++c) sumNW[r][c] += fg * Nt[q][r][c] * w[q];
+        }
+        const double s = G.detJ * ref;
+        for (int i = 0; i < NPE; ++i)
+            for (int c = 0; c < ND; ++c) {
+                double a = 0;
+                for (int d = 0; d < DIM; ++d) a += (s * g[d][i]) * sumNW[d][c];
+                C[i][c] = a;
+            }
+    }
+    // MB.inl:341-355
+    template <class F> void getF(const Geo<DIM>& G, const double vec[DIM], F&& f, double Fv[ND]) const {
+        for (int c = 0; c < ND; ++c) Fv[c] = 0;
+        for (int q = 0; q < NGP; ++q) {
+            const double fg = f(N[q]);
+            for (int c = 0; c < ND; ++c) {
+                double a = 0;
+                for (int r = 0; r < DIM; ++r) a += (fg * Nt[q][r][c]) * vec[r];
+                Fv[c] += a * w[q];
+            }
+        }
+        const double s = G.detJ * ref;
+        for (int c = 0; c < ND; ++c) Fv[c] *= s;
+    }
+    // MB.inl:373-386
+    template <class F>
+    void getH(const Geo<DIM>& G, const double vec[DIM], const double g[DIM][NPE], F&& f, double H[NPE]) const {
+        for (int i = 0; i < NPE; ++i) H[i] = 0;
+        for (int q = 0; q < NGP; ++q) {
+            const double fg = f(N[q]);
+            for (int i = 0; i < NPE; ++i) {
+                double a = 0;
+                for (int d = 0; d < DIM; ++d) a += (fg * g[d][i]) * vec[d];
+                H[i] += a * w[q];
+            }
+        }
+        const double s = G.detJ * ref;
+        for (int i = 0; i < NPE; ++i) H[i] *= s;
+    }
+};
+
+// ddev / m of the incompressible equation.  MomContEquation.inl:73-95.
+template <int DIM> void setIncomp(MB<DIM>& mb) {
+    constexpr int NS = MB<DIM>::NS;
+    for (int i = 0; i < NS; ++i) {
+        mb.m[i] = (i < DIM) ? 1.0 : 0.0;
+        for (int j = 0; j < NS; ++j) mb.ddev[i][j] = (i == j) ? ((i < DIM) ? 2.0 : 1.0) : 0.0;
+    }
+}
+
+template <int DIM> double dotN(const double* N, const double* s) {
+    double a = 0;
+    for (int i = 0; i < DIM + 1; ++i) a += N[i] * s[i];
+    return a;
+}
+
+struct Triplet {
+    int32_t r, c;
+    double v;
+};  // Eigen::Triplet<double> default-constructs to (0,0,0.0)
+
+// ------------------------------------------------------------------------------------
+// Eigen::SparseMatrix::setFromTriplets semantics (PSPG.inl:136; Eigen 3.3.x, not in tree):
+// column-major result, inner (row) indices sorted, duplicates summed in triplet order,
+// explicit zeros kept.  Implemented as stable bucket-by-column + stable sort by row.
+// ------------------------------------------------------------------------------------
+void tripletsToCSC(int64_t n, const std::vector<Triplet>& T, std::vector<int64_t>& colPtr, std::vector<int32_t>& rowIdx,
+                   std::vector<double>& val) {
+    std::vector<int64_t> cnt(n + 1, 0);
+    for (const auto& t : T) cnt[t.c + 1]++;
+    for (int64_t c = 0; c < n; ++c) cnt[c + 1] += cnt[c];
+    std::vector<Triplet> S(T.size());
+    {
+        std::vector<int64_t> cur(cnt.begin(), cnt.end() - 1);
+        for (const auto& t : T) S[cur[t.c]++] = t;
+    }
+    std::vector<int64_t> nnzCol(n, 0);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t c = 0; c < n; ++c) {
+        auto b = S.begin() + cnt[c], e = S.begin() + cnt[c + 1];
+        std::stable_sort(b, e, [](const Triplet& a, const Triplet& bb) { return a.r < bb.r; });
+        int64_t k = 0;
+        int32_t last = -1;
+        for (auto it = b; it != e; ++it)
+            if (it->r != last) {
+                ++k;
+                last = it->r;
+            }
+        nnzCol[c] = k;
+    }
+    colPtr.assign(n + 1, 0);
+    for (int64_t c = 0; c < n; ++c) colPtr[c + 1] = colPtr[c] + nnzCol[c];
+    rowIdx.resize(colPtr[n]);
+    val.resize(colPtr[n]);
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t c = 0; c < n; ++c) {
+        int64_t o = colPtr[c] - 1;
+        int32_t last = -1;
+        for (int64_t k = cnt[c]; k < cnt[c + 1]; ++k) {
+            if (S[k].r != last) {
+                ++o;
+                last = S[k].r;
+                rowIdx[o] = S[k].r;
+                val[o] = S[k].v;
+            } else
+                val[o] += S[k].v;
+        }
+    }
+}
+
+struct PspgParams {
+    double rho, mu, dt, bodyForce[3];
+};
+
+// ------------------------------------------------------------------------------------
+// tau_PSPG.  MomContEquationPSPG.inl:238-259 (h uses the 2-D formula in 3-D as well;
+// U from the CURRENT node states, not qPrev).
+// ------------------------------------------------------------------------------------
+template <int DIM>
+double tauPSPG(const Geo<DIM>& G, const int64_t* en, const double* vcur, int64_t nNodes, const PspgParams& P) {
+    const double h = std::sqrt(Quad<DIM>::ref() * G.detJ / M_PI);
+    double U = 0;
+    for (int n = 0; n < DIM + 1; ++n) {
+        double nodeU = 0;
+        for (int d = 0; d < DIM; ++d) {
+            const double s = vcur[en[n] + (int64_t)d * nNodes];
+            nodeU += s * s;
+        }
+        U += std::sqrt(nodeU);
+    }
+    U /= (DIM + 1);
+    return 1 / std::sqrt((2 / P.dt) * (2 / P.dt) + (2 * U / h) * (2 * U / h) +
+                         9 * (4 * P.mu / (h * h * P.rho)) * (4 * P.mu / (h * h * P.rho)));
+}
+
+// ------------------------------------------------------------------------------------
+// Per-element PSPG system.  MomContEquationPSPG.inl:26-53; factors MomContEquation.inl:
+// 73-93 (ddev, m), :97-100 (M: rho), :123-128 (K: mu), :131-135 (D: 1), :139-149 (C: 1,
+// L: 1/rho), :203-207 (F: rho), :218-222 (H: 1).
+// ------------------------------------------------------------------------------------
+template <int DIM>
+void pspgElement(const MB<DIM>& mb, const double* x, const double* vcur, const double* qPrev, int64_t nNodes,
+                 const int64_t* en, const PspgParams& P, double* Ae /*[(DIM+1)*NPE]^2 row-major*/, double* be,
+                 double* tauOut) {
+    constexpr int NPE = DIM + 1, ND = DIM * NPE, NT = (DIM + 1) * NPE, NS = MB<DIM>::NS;
+    Geo<DIM> G;
+    computeGeo<DIM>(x, nNodes, en, G);
+    const double tau = tauPSPG<DIM>(G, en, vcur, nNodes, P);
+    if (tauOut) *tauOut = tau;
+    double g[DIM][NPE], B[NS][ND];
+    MB<DIM>::gradN(G, g);
+    MB<DIM>::Bmat(g, B);
+    double M[NPE][NPE], K[ND][ND], D[NPE][ND], C[NPE][ND], L[NPE][NPE], F[ND], H[NPE];
+    mb.getM(G, [&](const double*) { return P.rho; }, M);
+    for (int i = 0; i < NPE; ++i)
+        for (int j = 0; j < NPE; ++j) M[i][j] = (1 / P.dt) * M[i][j];
+    mb.getK(G, B, [&](const double*) { return P.mu; }, K);
+    mb.getD(G, B, [&](const double*) { return 1.0; }, D);
+    mb.getC(G, g, [&](const double*) { return 1.0; }, C);
+    for (int i = 0; i < NPE; ++i)
+        for (int j = 0; j < ND; ++j) C[i][j] = (tau / P.dt) * C[i][j];
+    mb.getL(G, g, [&](const double*) { return 1 / P.rho; }, L);
+    for (int i = 0; i < NPE; ++i)
+        for (int j = 0; j < NPE; ++j) L[i][j] = tau * L[i][j];
+    mb.getF(G, P.bodyForce, [&](const double*) { return P.rho; }, F);
+    mb.getH(G, P.bodyForce, g, [&](const double*) { return 1.0; }, H);
+    for (int i = 0; i < NPE; ++i) H[i] = tau * H[i];
+
+    auto A = [&](int r, int c) -> double& { return Ae[r * NT + c]; };
+    // Ae << Me_dt + Ke, -De^T, Ce_dt + De, Le   (PSPG.inl:42), Me_dt = diagBlock (MB.hpp:120-129)
+    for (int r = 0; r < ND; ++r)
+        for (int c = 0; c < ND; ++c) {
+            double mv = 0;
+            if (r / NPE == c / NPE) mv = M[r % NPE][c % NPE];
+            A(r, c) = mv + K[r][c];
+        }
+    for (int r = 0; r < ND; ++r)
+        for (int c = 0; c < NPE; ++c) A(r, ND + c) = -D[c][r];
+    for (int r = 0; r < NPE; ++r)
+        for (int c = 0; c < ND; ++c) A(ND + r, c) = C[r][c] + D[r][c];
+    for (int r = 0; r < NPE; ++r)
+        for (int c = 0; c < NPE; ++c) A(ND + r, ND + c) = L[r][c];
+
+    // vPrev: StatesFromToQ.hpp:136-170 ; be << Fe + Me_dt*vPrev, He + Ce_dt*vPrev (PSPG.inl:53)
+    double vPrev[ND];
+    for (int d = 0; d < DIM; ++d)
+        for (int k = 0; k < NPE; ++k) vPrev[d * NPE + k] = qPrev[en[k] + (int64_t)d * nNodes];
+    for (int r = 0; r < ND; ++r) {
+        double a = 0;
+        const int blk = r / NPE;
+        for (int k = 0; k < NPE; ++k) a += M[r % NPE][k] * vPrev[blk * NPE + k];
+        be[r] = F[r] + a;
+    }
+    for (int r = 0; r < NPE; ++r) {
+        double a = 0;
+        for (int c = 0; c < ND; ++c) a += C[r][c] * vPrev[c];
+        be[ND + r] = H[r] + a;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// m_buildAbPSPG.  MomContEquationPSPG.inl:7-146: omp element loop -> row-masked triplets
+// (default (0,0,0) triplets for masked slots), identity triplets appended in node order
+// (pressure first, then velocity components, :108-128), setFromTriplets, serial RHS.
+// ------------------------------------------------------------------------------------
+template <int DIM>
+void pspgBuild(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const double* vcur,
+               const double* qPrev, const uint8_t* flags, const PspgParams& P, std::vector<int64_t>& colPtr,
+               std::vector<int32_t>& rowIdx, std::vector<double>& val, double* b, double* phaseSec) {
+    constexpr int NPE = DIM + 1, NT = (DIM + 1) * NPE;
+    const int64_t tripletPerElm = (int64_t)NT * NT, doubletPerElm = NT;
+    MB<DIM> mb;
+    setIncomp<DIM>(mb);
+    double t0 = omp_get_wtime();
+    std::vector<Triplet> indexA(tripletPerElm * nElm, Triplet{0, 0, 0.0});
+    std::vector<std::pair<int64_t, double>> indexb(doubletPerElm * nElm);
+    const int64_t nDof = (DIM + 1) * nNodes;
+    for (int64_t i = 0; i < nDof; ++i) b[i] = 0;
+    double t1 = omp_get_wtime();
+    if (phaseSec) phaseSec[0] += t1 - t0;  // "Prepare matrix assembly"
+#pragma omp parallel for default(shared)
+    for (int64_t elm = 0; elm < nElm; ++elm) {
+        const int64_t* en = conn + elm * NPE;
+        double Ae[NT * NT], be[NT];
+        pspgElement<DIM>(mb, x, vcur, qPrev, nNodes, en, P, Ae, be, nullptr);
+        int64_t countA = 0, countb = 0;
+        for (int i = 0; i < NPE; ++i) {
+            const uint8_t fi = flags[en[i]];
+            const bool bound = fi & F_BOUND, free_ = fi & F_FREE;
+            for (int j = 0; j < NPE; ++j) {
+                for (int d1 = 0; d1 < DIM; ++d1)
+                    for (int d2 = 0; d2 <= DIM; ++d2) {
+                        if (!(bound || free_))
+                            indexA[tripletPerElm * elm + countA] =
+                                Triplet{(int32_t)(en[i] + d1 * nNodes), (int32_t)(en[j] + d2 * nNodes),
+                                        Ae[(i + d1 * NPE) * NT + (j + d2 * NPE)]};
+                        countA++;
+                    }
+                for (int d2 = 0; d2 <= DIM; ++d2) {
+                    if (!free_)
+                        indexA[tripletPerElm * elm + countA] =
+                            Triplet{(int32_t)(en[i] + DIM * nNodes), (int32_t)(en[j] + d2 * nNodes),
+                                    Ae[(i + DIM * NPE) * NT + (j + d2 * NPE)]};
+                    countA++;
+                }
+            }
+            for (int d = 0; d <= DIM; ++d) {
+                indexb[doubletPerElm * elm + countb] = std::make_pair(en[i] + d * nNodes, be[i + d * NPE]);
+                countb++;
+            }
+        }
+    }
+    double t2 = omp_get_wtime();
+    if (phaseSec) phaseSec[1] += t2 - t1;  // "Compute triplets"
+    for (int64_t n = 0; n < nNodes; ++n) {
+        const bool bound = flags[n] & F_BOUND, free_ = flags[n] & F_FREE;
+        if (free_) indexA.push_back(Triplet{(int32_t)(n + DIM * nNodes), (int32_t)(n + DIM * nNodes), 1.0});
+        if (bound || free_)
+            for (int d = 0; d < DIM; ++d)
+                indexA.push_back(Triplet{(int32_t)(n + d * nNodes), (int32_t)(n + d * nNodes), 1.0});
+    }
+    double t3 = omp_get_wtime();
+    if (phaseSec) phaseSec[2] += t3 - t2;  // "Push back (n, n, 1)"
+    tripletsToCSC(nDof, indexA, colPtr, rowIdx, val);
+    double t4 = omp_get_wtime();
+    if (phaseSec) phaseSec[3] += t4 - t3;  // "Assemble matrix"
+    for (const auto& d : indexb) b[d.first] += d.second;
+    double t5 = omp_get_wtime();
+    if (phaseSec) phaseSec[4] += t5 - t4;  // "Assemble vector"
+}
+
+// ------------------------------------------------------------------------------------
+// m_applyBCPSPG.  MomContEquationPSPG.inl:149-235 (gamma = 0: facet loop skipped, :157).
+// dirMask[n] != 0  <=>  node.isBound() && getBcTagFlags(tag, flag0) (:206-208);
+// dirVal[n + d*nNodes] = the Lua "<type>V" result (:211-214), host-evaluated.
+// Column walk + explicit zeros: :219-228.
+// ------------------------------------------------------------------------------------
+template <int DIM>
+void pspgApplyBC(int64_t nNodes, const uint8_t* flags, const uint8_t* dirMask, const double* dirVal,
+                 const double* qPrev, const PspgParams& P, const int64_t* colPtr, const int32_t* rowIdx, double* val,
+                 double* b) {
+    for (int64_t n = 0; n < nNodes; ++n) {
+        const bool bound = flags[n] & F_BOUND, free_ = flags[n] & F_FREE;
+        if (free_) {
+            b[n + DIM * nNodes] = 0;
+            if (!bound)
+                for (int d = 0; d < DIM; ++d) b[n + d * nNodes] = qPrev[n + d * nNodes] + P.dt * P.bodyForce[d];
+        }
+        if (bound && dirMask[n]) {
+            for (int d = 0; d < DIM; ++d) {
+                const int64_t col = n + d * nNodes;
+                const double r = dirVal[col];
+                b[col] = r;
+                for (int64_t k = colPtr[col]; k < colPtr[col + 1]; ++k) {
+                    const int64_t row = rowIdx[k];
+                    if (row == col) continue;
+                    const double v = val[k];
+                    b[row] -= v * r;
+                    val[k] = 0;
+                }
+            }
+        }
+    }
+}
+
+struct WcParams {
+    double mu, K0, K0p, rhoStar, bodyForce[3];
+    int meduri;
+};
+
+// ------------------------------------------------------------------------------------
+// Mesh::updateNodesPosition.  srcs/mesh/Mesh.cpp:1101-1137: x += delta unless m_isFixed.
+// (Jacobians are recomputed from coordinates on use in this restatement.)
+// ------------------------------------------------------------------------------------
+void movePositions(int dim, int64_t nNodes, const uint8_t* flags, const double* delta, const double* base, double* x) {
+#pragma omp parallel for
+    for (int64_t n = 0; n < nNodes; ++n)
+        if (!(flags[n] & F_FIXED))
+            for (int d = 0; d < dim; ++d) x[n + d * nNodes] = base[n + d * nNodes] + delta[n + d * nNodes];
+}
+
+// ------------------------------------------------------------------------------------
+// ContEqWCompNewton (CDS_dpdt).  WCompNewton/ContEquation.inl:353-413 (build), :334-350
+// (BC), :123-148 (solve), :319-331 (Tait-Murnaghan); factors :75-86.
+// ------------------------------------------------------------------------------------
+template <int DIM>
+void wcCont(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const uint8_t* flags, const double* v,
+            double* p, double* rho, const WcParams& P, double dt) {
+    constexpr int NPE = DIM + 1, ND = DIM * NPE, NS = MB<DIM>::NS;
+    MB<DIM> mb;
+    for (int i = 0; i < NS; ++i) mb.m[i] = (i < DIM) ? 1.0 : 0.0;
+    std::vector<double> MeL((size_t)nElm * NPE), F0e((size_t)nElm * NPE);
+#pragma omp parallel for default(shared)
+    for (int64_t elm = 0; elm < nElm; ++elm) {
+        const int64_t* en = conn + elm * NPE;
+        Geo<DIM> G;
+        computeGeo<DIM>(x, nNodes, en, G);
+        double Me[NPE][NPE];
+        mb.getM(G, [](const double*) { return 1.0; }, Me);
+        double lumped[NPE];  // lump2, MB.hpp:87-102
+        for (int i = 0; i < NPE; ++i) {
+            lumped[i] = 0;
+            for (int j = 0; j < NPE; ++j) lumped[i] += Me[i][j];
+        }
+        double Pe[NPE], V[ND];
+        for (int k = 0; k < NPE; ++k) Pe[k] = p[en[k]];
+        for (int d = 0; d < DIM; ++d)
+            for (int k = 0; k < NPE; ++k) V[d * NPE + k] = v[en[k] + (int64_t)d * nNodes];
+        double g[DIM][NPE], B[NS][ND], D[NPE][ND];
+        MB<DIM>::gradN(G, g);
+        MB<DIM>::Bmat(g, B);
+        mb.getD(G, B, [&](const double* N) { return P.K0 + P.K0p * dotN<DIM>(N, Pe); }, D);
+        for (int i = 0; i < NPE; ++i) {
+            double a = 0;
+            for (int c = 0; c < ND; ++c) a += (-dt * D[i][c]) * V[c];
+            double s = 0;
+            if (P.meduri)
+                for (int j = 0; j < NPE; ++j) s += Me[i][j] * Pe[j];
+            else
+                s = lumped[i] * Pe[i];
+            F0e[elm * NPE + i] = a + s;
+            MeL[elm * NPE + i] = lumped[i];
+        }
+    }
+    std::vector<double> invM(nNodes, 0.0), F0(nNodes, 0.0);
+    for (int64_t elm = 0; elm < nElm; ++elm)  // serial scatter, :398-408
+        for (int i = 0; i < NPE; ++i) {
+            invM[conn[elm * NPE + i]] += MeL[elm * NPE + i];
+            F0[conn[elm * NPE + i]] += F0e[elm * NPE + i];
+        }
+    for (int64_t n = 0; n < nNodes; ++n) invM[n] = 1 / invM[n];
+    for (int64_t n = 0; n < nNodes; ++n)
+        if (flags[n] & F_FREE) {
+            F0[n] = 0;
+            invM[n] = 1;
+        }
+    for (int64_t n = 0; n < nNodes; ++n) {
+        p[n] = invM[n] * F0[n];
+        rho[n] = std::pow((P.K0p / P.K0) * p[n] + 1, 1 / P.K0p) * P.rhoStar;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// MomEqWCompNewton.  WCompNewton/MomEquation.inl:229-302 (build), :305-374 (BC, gamma=0),
+// :201-226 (solve); factors :63-103, :135-139.  The "acceleration" of a Dirichlet node is
+// set to the Dirichlet *velocity* value (:361-369), reproduced as is.
+// ------------------------------------------------------------------------------------
+template <int DIM>
+void wcMom(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const uint8_t* flags,
+           const uint8_t* dirMask, const double* dirVal, double* v /*in: v_half, out: v*/, double* acc, const double* p,
+           const double* rho, const WcParams& P, double dt) {
+    constexpr int NPE = DIM + 1, ND = DIM * NPE, NS = MB<DIM>::NS;
+    MB<DIM> mb;
+    for (int i = 0; i < NS; ++i) mb.m[i] = (i < DIM) ? 1.0 : 0.0;
+    for (int i = 0; i < NS; ++i)
+        for (int j = 0; j < NS; ++j) {
+            if (i < DIM && j < DIM)
+                mb.ddev[i][j] = (i == j) ? 4.0 / 3 : -2.0 / 3;
+            else
+                mb.ddev[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    std::vector<double> Mdiag((size_t)nElm * ND), FTot((size_t)nElm * ND);
+#pragma omp parallel for default(shared)
+    for (int64_t elm = 0; elm < nElm; ++elm) {
+        const int64_t* en = conn + elm * NPE;
+        Geo<DIM> G;
+        computeGeo<DIM>(x, nNodes, en, G);
+        double V[ND], Pe[NPE], Re[NPE];
+        for (int d = 0; d < DIM; ++d)
+            for (int k = 0; k < NPE; ++k) V[d * NPE + k] = v[en[k] + (int64_t)d * nNodes];
+        for (int k = 0; k < NPE; ++k) {
+            Pe[k] = p[en[k]];
+            Re[k] = rho[en[k]];
+        }
+        double g[DIM][NPE], B[NS][ND];
+        MB<DIM>::gradN(G, g);
+        MB<DIM>::Bmat(g, B);
+        double Mt[NPE][NPE];
+        mb.getM(G, [&](const double* N) { return dotN<DIM>(N, Re); }, Mt);
+        // diagBlock then lump (MB.hpp:104-129): diagonal entry accumulates its row in column order
+        double Me[ND][ND];
+        for (int r = 0; r < ND; ++r)
+            for (int c = 0; c < ND; ++c) Me[r][c] = (r / NPE == c / NPE) ? Mt[r % NPE][c % NPE] : 0.0;
+        for (int i = 0; i < ND; ++i)
+            for (int j = 0; j < ND; ++j)
+                if (i != j) {
+                    Me[i][i] += Me[i][j];
+                    Me[i][j] = 0;
+                }
+        double K[ND][ND], D[NPE][ND], F[ND];
+        mb.getK(G, B, [&](const double*) { return P.mu; }, K);
+        mb.getD(G, B, [](const double*) { return 1.0; }, D);
+        mb.getF(G, P.bodyForce, [&](const double* N) { return dotN<DIM>(N, Re); }, F);
+        for (int r = 0; r < ND; ++r) {
+            double kv = 0;
+            for (int c = 0; c < ND; ++c) kv += (-K[r][c]) * V[c];
+            double dp = 0;
+            for (int k = 0; k < NPE; ++k) dp += D[k][r] * Pe[k];
+            FTot[elm * ND + r] = (kv + dp) + F[r];
+            Mdiag[elm * ND + r] = Me[r][r];
+        }
+    }
+    std::vector<double> invM((size_t)DIM * nNodes, 0.0), F((size_t)DIM * nNodes, 0.0);
+    for (int64_t elm = 0; elm < nElm; ++elm)  // serial scatter, :279-298
+        for (int i = 0; i < NPE; ++i)
+            for (int d = 0; d < DIM; ++d) {
+                invM[conn[elm * NPE + i] + (int64_t)d * nNodes] += Mdiag[elm * ND + i + d * NPE];
+                F[conn[elm * NPE + i] + (int64_t)d * nNodes] += FTot[elm * ND + i + d * NPE];
+            }
+    for (size_t i = 0; i < invM.size(); ++i) invM[i] = 1 / invM[i];
+    for (int64_t n = 0; n < nNodes; ++n) {
+        const bool bound = flags[n] & F_BOUND, free_ = flags[n] & F_FREE;
+        if (free_ && !bound) {
+            for (int d = 0; d < DIM; ++d) {
+                F[n + (int64_t)d * nNodes] = P.bodyForce[d];
+                invM[n + (int64_t)d * nNodes] = 1;
+            }
+        } else if (bound && dirMask[n]) {
+            for (int d = 0; d < DIM; ++d) {
+                F[n + (int64_t)d * nNodes] = dirVal[n + (int64_t)d * nNodes];
+                invM[n + (int64_t)d * nNodes] = 1;
+            }
+        }
+    }
+    for (int64_t i = 0; i < (int64_t)DIM * nNodes; ++i) {
+        const double a = invM[i] * F[i];
+        acc[i] = a;
+        v[i] = v[i] + 0.5 * dt * a;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Element::getRin (srcs/mesh/Element.cpp:226-294) and SolverWCompNewton::computeNextDT
+// (WCompNewton/Solver.cpp:192-234) with c^2 = (K0 + K0' p)/rho (ContEquation.inl:117-120),
+// u^2 (MomEquation.inl:184-192), alpha = mu/rho (:195-198).
+// ------------------------------------------------------------------------------------
+template <int DIM> double rin(const double* x, int64_t nNodes, const int64_t* en) {
+    Geo<DIM> G;
+    computeGeo<DIM>(x, nNodes, en, G);
+    const double size = G.detJ * Quad<DIM>::ref();
+    auto X = [&](int node, int d) { return x[en[node] + (int64_t)d * nNodes]; };
+    if constexpr (DIM == 2) {
+        auto dist = [&](int a, int b) {
+            // Node::distance (srcs/mesh/Node.cpp): Euclidean over the 3 stored coordinates (z = 0 in 2-D)
+            double s = 0;
+            for (int d = 0; d < 2; ++d) s += (X(a, d) - X(b, d)) * (X(a, d) - X(b, d));
+            return std::sqrt(s);
+        };
+        const double a = dist(0, 1), b = dist(1, 2), c = dist(0, 2);
+        const double s = (a + b + c) / 2;
+        return size / s;
+    } else {
+        const double x0 = X(0, 0), x1 = X(1, 0), x2 = X(2, 0), x3 = X(3, 0);
+        const double y0 = X(0, 1), y1 = X(1, 1), y2 = X(2, 1), y3 = X(3, 1);
+        const double z0 = X(0, 2), z1 = X(1, 2), z2 = X(2, 2), z3 = X(3, 2);
+        auto nrm = [](double a, double b, double c) { return std::sqrt(a * a + b * b + c * c); };
+        const double n1 = nrm((y1 - y0) * (z2 - z0) - (z1 - z0) * (y2 - y0), (z1 - z0) * (x2 - x0) - (x1 - x0) * (z2 - z0),
+                              (x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0));
+        const double n2 = nrm((y3 - y0) * (z2 - z0) - (z3 - z0) * (y2 - y0), (z3 - z0) * (x2 - x0) - (x3 - x0) * (z2 - z0),
+                              (x3 - x0) * (y2 - y0) - (y3 - y0) * (x2 - x0));
+        const double n3 = nrm((y1 - y0) * (z3 - z0) - (z1 - z0) * (y3 - y0), (z1 - z0) * (x3 - x0) - (x1 - x0) * (z3 - z0),
+                              (x1 - x0) * (y3 - y0) - (y1 - y0) * (x3 - x0));
+        const double n4 = nrm((y1 - y3) * (z2 - z3) - (z1 - z3) * (y2 - y3), (z1 - z3) * (x2 - x3) - (x1 - x3) * (z2 - z3),
+                              (x1 - x3) * (y2 - y3) - (y1 - y3) * (x2 - x3));
+        return 6 * size / (n1 + n2 + n3 + n4);
+    }
+}
+
+template <int DIM>
+double wcNextDt(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const double* v, const double* p,
+                const double* rho, const WcParams& P, double securityCoeff, double maxDT) {
+    double ts = std::numeric_limits<double>::max();
+#pragma omp parallel for reduction(min : ts)
+    for (int64_t elm = 0; elm < nElm; ++elm) {
+        const int64_t* en = conn + elm * (DIM + 1);
+        const double he = 2 * rin<DIM>(x, nNodes, en);
+        double mx = 0;
+        for (int n = 0; n < DIM + 1; ++n) {
+            const int64_t nd = en[n];
+            const double c2 = (P.K0 + P.K0p * p[nd]) / rho[nd];
+            double u2 = 0;
+            for (int d = 0; d < DIM; ++d) u2 += v[nd + (int64_t)d * nNodes] * v[nd + (int64_t)d * nNodes];
+            const double alpha = P.mu / rho[nd];
+            mx = std::max(std::max(u2, c2), mx);
+            mx = std::max(mx, 4 * alpha * alpha / (he * he));
+        }
+        ts = std::min(ts, securityCoeff * securityCoeff * he * he / mx);
+    }
+    return std::min(std::sqrt(ts), maxDT);
+}
+
+// handle for CSC results that outlive one call
+struct CscHandle {
+    std::vector<int64_t> colPtr;
+    std::vector<int32_t> rowIdx;
+    std::vector<double> val;
+};
+
+}  // namespace
+
+extern "C" {
+
+int oracle_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#endif
+}
+
+// Per-element Ae (row-major (dim+1)*npe square) / be / tau for every element: test hook for MB.inl + PSPG.inl:26-53.
+int oracle_pspg_elements(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x,
+                         const double* vcur, const double* qPrev, const double* params /*rho,mu,dt,b[3]*/, double* Ae,
+                         double* be, double* tau) {
+    PspgParams P{params[0], params[1], params[2], {params[3], params[4], params[5]}};
+    if (dim == 2) {
+        MB<2> mb;
+        setIncomp<2>(mb);
+        constexpr int NT = 9;
+#pragma omp parallel for
+        for (int64_t e = 0; e < nElm; ++e)
+            pspgElement<2>(mb, x, vcur, qPrev, nNodes, conn + e * 3, P, Ae + e * NT * NT, be + e * NT, tau + e);
+    } else if (dim == 3) {
+        MB<3> mb;
+        setIncomp<3>(mb);
+        constexpr int NT = 16;
+#pragma omp parallel for
+        for (int64_t e = 0; e < nElm; ++e)
+            pspgElement<3>(mb, x, vcur, qPrev, nNodes, conn + e * 4, P, Ae + e * NT * NT, be + e * NT, tau + e);
+    } else
+        return -1;
+    return 0;
+}
+
+// m_buildAbPSPG (+ optionally m_applyBCPSPG).  Returns a handle; query nnz, then copy out.
+// phaseSec[5]: Prepare / Compute triplets / Push back / Assemble matrix / Assemble vector; [5] = Apply BC.
+void* oracle_pspg_build(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x,
+                        const double* vcur, const double* qPrev, const uint8_t* flags, const double* params,
+                        int applyBC, const uint8_t* dirMask, const double* dirVal, double* b, double* phaseSec) {
+    PspgParams P{params[0], params[1], params[2], {params[3], params[4], params[5]}};
+    auto* H = new CscHandle;
+    if (dim == 2)
+        pspgBuild<2>(nNodes, nElm, conn, x, vcur, qPrev, flags, P, H->colPtr, H->rowIdx, H->val, b, phaseSec);
+    else if (dim == 3)
+        pspgBuild<3>(nNodes, nElm, conn, x, vcur, qPrev, flags, P, H->colPtr, H->rowIdx, H->val, b, phaseSec);
+    else {
+        delete H;
+        return nullptr;
+    }
+    if (applyBC) {
+        double t0 = omp_get_wtime();
+        if (dim == 2)
+            pspgApplyBC<2>(nNodes, flags, dirMask, dirVal, qPrev, P, H->colPtr.data(), H->rowIdx.data(), H->val.data(), b);
+        else
+            pspgApplyBC<3>(nNodes, flags, dirMask, dirVal, qPrev, P, H->colPtr.data(), H->rowIdx.data(), H->val.data(), b);
+        if (phaseSec) phaseSec[5] += omp_get_wtime() - t0;
+    }
+    return H;
+}
+int64_t oracle_csc_nnz(void* h) { return (int64_t) static_cast<CscHandle*>(h)->val.size(); }
+void oracle_csc_copy(void* h, int64_t* colPtr, int32_t* rowIdx, double* val) {
+    auto* H = static_cast<CscHandle*>(h);
+    std::copy(H->colPtr.begin(), H->colPtr.end(), colPtr);
+    std::copy(H->rowIdx.begin(), H->rowIdx.end(), rowIdx);
+    std::copy(H->val.begin(), H->val.end(), val);
+}
+void oracle_csc_free(void* h) { delete static_cast<CscHandle*>(h); }
+
+// Mesh::updateNodesPosition (base = x) / updateNodesPositionFromSave (base = saved), Mesh.cpp:1101-1137, 1238-1277
+void oracle_move_positions(int dim, int64_t nNodes, const uint8_t* flags, const double* delta, const double* base,
+                           double* x) {
+    movePositions(dim, nNodes, flags, delta, base, x);
+}
+
+// One explicit step: WCompNewton/Solver.cpp:236-263.  State arrays are SoA: v[dim*nNodes], acc[dim*nNodes], p, rho.
+// params: mu, K0, K0p, rhoStar, b[3], meduri
+int oracle_wc_step(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, double* x, const uint8_t* flags,
+                   const uint8_t* dirMask, const double* dirVal, double* v, double* acc, double* p, double* rho,
+                   const double* params, double dt) {
+    WcParams P{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}, (int)params[7]};
+    const int64_t nv = (int64_t)dim * nNodes;
+    std::vector<double> delta(nv);
+    // qV1half = qVPrev + 0.5*dt*qAccPrev ; states <- v_half ; x += v_half*dt   (Solver.cpp:249-253)
+    for (int64_t i = 0; i < nv; ++i) {
+        v[i] = v[i] + 0.5 * dt * acc[i];
+        delta[i] = v[i] * dt;
+    }
+    movePositions(dim, nNodes, flags, delta.data(), x, x);
+    if (dim == 2) {
+        wcCont<2>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt);
+        wcMom<2>(nNodes, nElm, conn, x, flags, dirMask, dirVal, v, acc, p, rho, P, dt);
+    } else if (dim == 3) {
+        wcCont<3>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt);
+        wcMom<3>(nNodes, nElm, conn, x, flags, dirMask, dirVal, v, acc, p, rho, P, dt);
+    } else
+        return -1;
+    return 0;
+}
+
+double oracle_wc_next_dt(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const double* v,
+                         const double* p, const double* rho, const double* params, double securityCoeff, double maxDT) {
+    WcParams P{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}, (int)params[7]};
+    if (dim == 2) return wcNextDt<2>(nNodes, nElm, conn, x, v, p, rho, P, securityCoeff, maxDT);
+    return wcNextDt<3>(nNodes, nElm, conn, x, v, p, rho, P, securityCoeff, maxDT);
+}
+
+// y = A x for a CSC matrix, serial column sweep (what Eigen 3.3 does for a column-major sparse * dense vector;
+// PSPG.inl:368).  ompRows != 0: transpose-free row-parallel variant is not possible on CSC, so the caller passes CSR.
+void oracle_csc_matvec(int64_t n, const int64_t* colPtr, const int32_t* rowIdx, const double* val, const double* xv,
+                       double* y) {
+    for (int64_t i = 0; i < n; ++i) y[i] = 0;
+    for (int64_t c = 0; c < n; ++c) {
+        const double xc = xv[c];
+        for (int64_t k = colPtr[c]; k < colPtr[c + 1]; ++k) y[rowIdx[k]] += val[k] * xc;
+    }
+}
+
+// Jacobi-preconditioned BiCGSTAB on CSR (omp row-parallel SpMV), Eigen 3.3 formulation (IterativeLinearSolvers/BiCGSTAB.h,
+// not in tree: restarts when |rho| < eps^2*|r0|^2, tol on ||r||/||b||).  CPU baseline for the Krylov solve only; the
+// reference itself uses SparseLU on this system (PSPG.inl:281-290).
+int oracle_bicgstab_csr(int64_t n, const int64_t* rowPtr, const int32_t* colIdx, const double* val, const double* b,
+                        double* xsol, double tol, int maxIter, double* relRes) {
+    std::vector<double> dinv(n), r(n), r0(n), p(n, 0.0), v(n, 0.0), s(n), t(n), y(n), z(n);
+    auto spmv = [&](const double* in, double* out) {
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            double a = 0;
+            for (int64_t k = rowPtr[i]; k < rowPtr[i + 1]; ++k) a += val[k] * in[colIdx[k]];
+            out[i] = a;
+        }
+    };
+    auto dot = [&](const double* a, const double* c) {
+        double sum = 0;
+#pragma omp parallel for reduction(+ : sum) schedule(static)
+        for (int64_t i = 0; i < n; ++i) sum += a[i] * c[i];
+        return sum;
+    };
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        double d = 0;
+        for (int64_t k = rowPtr[i]; k < rowPtr[i + 1]; ++k)
+            if (colIdx[k] == i) d = val[k];
+        dinv[i] = (d != 0) ? 1 / d : 1;
+    }
+    spmv(xsol, r.data());
+    for (int64_t i = 0; i < n; ++i) r0[i] = r[i] = b[i] - r[i];
+    const double r0sq = dot(r0.data(), r0.data()), rhsSq = dot(b, b);
+    if (rhsSq == 0) {
+        for (int64_t i = 0; i < n; ++i) xsol[i] = 0;
+        *relRes = 0;
+        return 0;
+    }
+    double rho = 1, alpha = 1, w = 1;
+    const double tol2 = tol * tol * rhsSq, eps2 = std::numeric_limits<double>::epsilon() * std::numeric_limits<double>::epsilon();
+    int it = 0, restarts = 0;
+    double rsq = r0sq;
+    while (rsq > tol2 && it < maxIter) {
+        const double rhoOld = rho;
+        rho = dot(r0.data(), r.data());
+        if (std::fabs(rho) < eps2 * r0sq) {
+            spmv(xsol, r.data());
+            for (int64_t i = 0; i < n; ++i) r0[i] = r[i] = b[i] - r[i];
+            rho = dot(r.data(), r.data());
+            if (restarts++ == 0) it = 0;
+        }
+        const double beta = (rho / rhoOld) * (alpha / w);
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            p[i] = r[i] + beta * (p[i] - w * v[i]);
+            y[i] = dinv[i] * p[i];
+        }
+        spmv(y.data(), v.data());
+        alpha = rho / dot(r0.data(), v.data());
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            s[i] = r[i] - alpha * v[i];
+            z[i] = dinv[i] * s[i];
+        }
+        spmv(z.data(), t.data());
+        const double tt = dot(t.data(), t.data());
+        w = (tt > 0) ? dot(t.data(), s.data()) / tt : 0;
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < n; ++i) {
+            xsol[i] += alpha * y[i] + w * z[i];
+            r[i] = s[i] - w * t[i];
+        }
+        rsq = dot(r.data(), r.data());
+        ++it;
+    }
+    *relRes = std::sqrt(rsq / rhsSq);
+    return it;
+}
+
+}  // extern "C"

@@ -1,0 +1,228 @@
+// common.cuh -- context, device buffers, launch/phase bookkeeping shared by the pfem_b200 translation units.
+// B200 (sm_100a) only; fp64 throughout.  Nothing in this library runs the physics on the CPU.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pfem_b200.h"
+
+#define PFEM_MAX_STATES 8  // 2*dim+2 for the weakly-compressible problem in 3-D
+
+// ---- error plumbing: every API entry point is `try { ... } catch (PfemFail&)`, nothing escapes the C ABI ----------
+struct PfemFail {
+    int code;
+    std::string msg;
+};
+[[noreturn]] inline void pfemThrow(int code, const std::string& m) { throw PfemFail{code, m}; }
+#define CUDA_CHECK(expr)                                                                                        \
+    do {                                                                                                        \
+        cudaError_t _e = (expr);                                                                                \
+        if (_e != cudaSuccess)                                                                                  \
+            pfemThrow(PFEM_ERR_CUDA, std::string(#expr) + " -> " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                                         std::to_string(__LINE__));                                             \
+    } while (0)
+#define PFEM_REQUIRE(cond, code, msg) \
+    do {                              \
+        if (!(cond)) pfemThrow((code), (msg)); \
+    } while (0)
+
+// ---- grow-only device buffer (remeshing every step must not cudaMalloc every step) --------------------------------
+template <class T> struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    size_t* accounting = nullptr;
+    void reserve(size_t n) {
+        if (n <= cap) return;
+        size_t want = n + n / 8 + 64;
+        release();
+        CUDA_CHECK(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+        if (accounting) *accounting += want * sizeof(T);
+    }
+    void release() {
+        if (p) {
+            cudaFree(p);
+            if (accounting) *accounting -= cap * sizeof(T);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+    ~DevBuf() { release(); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct PhaseAcc {
+    double ms = 0;
+    int64_t calls = 0;
+};
+struct PendingPhase {
+    std::string name;
+    cudaEvent_t e0, e1;
+};
+
+struct NcclApi;  // dlopen'ed NCCL entry points (comm.cu)
+
+// slots of the Krylov scalar bank kept on the device (krylov.cu)
+enum { SC_RHO0 = 0, SC_RHO1, SC_ALPHA, SC_OMEGA, SC_DONE, SC_ITERS, SC_RES2, SC_BNORM2, SC_TOL2, SC_BAD, SC_COUNT = 16 };
+// slots of the per-block partial-sum bank
+enum { PS_RHO = 0, PS_SIGMA, PS_TS, PS_TT, PS_RR, PS_AUX, PS_COUNT = 8 };
+
+struct pfem_ctx {
+    int dim = 0, device = 0, nRanks = 1, rank = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr, ownStream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    size_t deviceBytes = 0;
+
+    // ---- mesh (device) ----
+    int nNodes = 0, nElems = 0;
+    int64_t nBlocks = 0;       // node-block non-zeros
+    int64_t nnzReference = -1; // lazily counted
+    int maxE = 0, maxNb = 0;
+    bool haveTopology = false, havePositions = false, haveSnapshot = false, haveDirichlet = false;
+    bool haveQprev = false, haveSystem = false, haveSolution = false;
+    DevBuf<int> conn;          // nElems*(dim+1)
+    DevBuf<uint8_t> flags;     // PFEM_NODE_* ; FREE recomputed from the incidence (Node.inl:48-51)
+    DevBuf<uint8_t> dirMask;
+    DevBuf<double> dirVal4;    // 4 doubles per node
+    DevBuf<int> n2ePtr, n2e;   // node -> incident elements, ascending element index
+    DevBuf<int> nbrPtr, nbr;   // node -> sorted neighbour nodes (incl. itself) == block-row pattern
+    DevBuf<int> diagSlot;      // position of the node in its own neighbour list
+    DevBuf<int> scratchI;      // counters / cursors
+    DevBuf<int> scanScratch;   // tile sums of exclusiveScanInt
+    DevBuf<unsigned long long> stage64;
+    DevBuf<double> stageD;     // host<->device staging in ABI (SoA) layout
+    DevBuf<uint8_t> stageB;
+
+    // ---- nodal fields (device, 4 doubles per node, both dims) ----
+    DevBuf<double> X4;         // (x, y, z, p)
+    DevBuf<double> Xsave4;     // snapshot of X4 (saveNodesList)
+    DevBuf<double> V4;         // (u, v, w, rho)
+    DevBuf<double> A4;         // (ax, ay, az, -)
+    DevBuf<double> VP4;        // (u_prev, v_prev, w_prev, |v_cur|)  -- PSPG assembly input
+    DevBuf<double> X4b, V4b;   // ping-pong partners for the explicit step
+
+    // ---- PSPG system ----
+    DevBuf<double> Aval;       // nBlocks * BS*BS, block row-major
+    DevBuf<double> bvec;       // nNodes*BS, internal dof = node*BS + d
+    DevBuf<double> dinv;       // 1/diag
+    DevBuf<double> kx, kr, kr0, kp, kv, ks, kt, kph, ksh;  // Krylov vectors (internal dof order)
+    DevBuf<double> partial;    // PS_COUNT * reduceBlocks
+    DevBuf<double> scal;       // SC_COUNT
+    double* hScal = nullptr;   // pinned mirror
+    int reduceBlocks = 0;
+
+    // ---- export scratch ----
+    DevBuf<int> cscPtr;
+    DevBuf<int> cscRow;
+    DevBuf<double> cscVal;
+
+    // ---- explicit step ----
+    DevBuf<double> dtPartial;
+
+    // ---- multi-GPU ----
+    NcclApi* nccl = nullptr;
+    void* comm = nullptr;
+    DevBuf<int> ifaceIdx;      // local ids of interface nodes, ordered by global id
+    DevBuf<double> ifaceBuf;
+    int nIface = 0;
+    std::vector<int> l2gNodes; // local -> global node id (host)
+    int nNodesGlobal = 0, nElemsGlobal = 0;
+    DevBuf<int> ownedMask;
+
+    // ---- profiling ----
+    bool profiling = false;
+    std::map<std::string, PhaseAcc> phases;
+    std::vector<PendingPhase> pending;
+    std::vector<cudaEvent_t> eventPool;
+
+    pfem_ctx() {
+        for (auto* b : {&conn, &n2ePtr, &n2e, &nbrPtr, &nbr, &diagSlot, &scratchI, &scanScratch, &cscPtr, &cscRow, &ifaceIdx, &ownedMask})
+            b->accounting = &deviceBytes;
+        for (auto* b : {&flags, &dirMask, &stageB}) b->accounting = &deviceBytes;
+        for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &kx, &kr, &kr0,
+                        &kp, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &ifaceBuf})
+            b->accounting = &deviceBytes;
+        stage64.accounting = &deviceBytes;
+    }
+};
+
+// ---- phase timing (names mirror the reference's m_accumalatedTimes keys) ------------------------------------------
+struct PhaseScope {
+    pfem_ctx* c;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    std::string name;
+    PhaseScope(pfem_ctx* ctx, const char* n) : c(ctx), name(n) {
+        if (!c->profiling) return;
+        auto get = [&]() {
+            cudaEvent_t e;
+            if (!c->eventPool.empty()) {
+                e = c->eventPool.back();
+                c->eventPool.pop_back();
+            } else
+                cudaEventCreate(&e);
+            return e;
+        };
+        e0 = get();
+        e1 = get();
+        cudaEventRecord(e0, c->stream);
+    }
+    ~PhaseScope() {
+        if (!e0) return;
+        cudaEventRecord(e1, c->stream);
+        c->pending.push_back({name, e0, e1});
+    }
+};
+void pfemFlushPhases(pfem_ctx* c);
+
+inline void countLaunch(pfem_ctx* c, int n = 1) { c->launches += n; }
+#define LAUNCH_CHECK(c)                 \
+    do {                                \
+        countLaunch(c);                 \
+        CUDA_CHECK(cudaGetLastError()); \
+    } while (0)
+
+inline int divUp(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- per-module entry points (implemented in the .cu files) -------------------------------------------------------
+// topology.cu
+void topoBuild(pfem_ctx* c, int64_t nNodes, int64_t nElems, const uint64_t* elemNodes, const uint8_t* flags);
+void exclusiveScanInt(pfem_ctx* c, int* data, int n, int* totalOut /*device, may be null*/);
+// fields.cu
+void fieldsSetPositions(pfem_ctx* c, const double* x);
+void fieldsGetPositions(pfem_ctx* c, double* x);
+void fieldsSetStates(pfem_ctx* c, int first, int count, const double* q);
+void fieldsGetStates(pfem_ctx* c, int first, int count, double* q);
+void fieldsSetDirichlet(pfem_ctx* c, const uint8_t* mask, const double* values);
+void fieldsSnapshot(pfem_ctx* c);
+void fieldsRestore(pfem_ctx* c);
+void fieldsMove(pfem_ctx* c, const double* delta, int fromSnapshot);
+void fieldsSetQprev(pfem_ctx* c, const double* qPrev);
+// pspg.cu
+void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p);
+void pspgExportCsc(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b);
+void pspgPicardUpdate(pfem_ctx* c, double dt);  // states <- q ; X = Xsave + dt*v
+// krylov.cu
+int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* iters, double* relRes, bool warmStart);
+void krylovFetchSolution(pfem_ctx* c, double* q);
+void krylovLoadVector(pfem_ctx* c, const double* qHost, double* dst);  // ABI layout -> internal dof order
+void krylovStoreVector(pfem_ctx* c, const double* src, double* qHost);
+double krylovResidualNorm(pfem_ctx* c, const double* xInternal);
+void krylovMatvec(pfem_ctx* c, const double* xInternal, double* yInternal);
+// wc.cu
+void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt);
+int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dt);
+// comm.cu
+void commUniqueId(void* id128);
+void commInit(pfem_ctx* c, int nRanks, int rank, const void* id128);
+void commDestroy(pfem_ctx* c);
+void commAllReduceSumInterface(pfem_ctx* c, double* buf, int count);
+void commAllReduceMin(pfem_ctx* c, double* devScalar);

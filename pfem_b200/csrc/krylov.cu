@@ -1,0 +1,404 @@
+// krylov.cu -- Jacobi-preconditioned BiCGSTAB on the node-block matrix; replaces the Eigen::SparseLU
+// analyzePattern/factorize/solve of MomContEquationPSPG.inl:281-290 (a direct solver does not scale to the
+// 1.4 M-dof 3-D systems of the target configs).
+//
+// B200 design:
+//   * SpMV on (dim+1)x(dim+1) node blocks: one warp per block row, lane = (block, row): every lane streams one
+//     32-byte row of a 4x4 block (full sector), the warp 1 KB contiguous per step -> A is read at HBM speed with
+//     4 B of index per 128 B of values; x (11 MB at 2 M tets) stays L2-resident.
+//   * every dot product is fused into the kernel that produces its operand; block partial sums go to a small bank,
+//     and each consumer block re-reduces the bank in a fixed order -> no atomics, no extra launches, no host sync,
+//     bit-reproducible.  Scalars (rho, alpha, omega) live in a device bank with iteration-parity double buffering.
+//   * 5 kernels per iteration, the loop runs `checkEvery` iterations between convergence polls; a device-side DONE
+//     flag freezes the state once ||r|| <= tol ||b||.
+// Vectors use the internal dof order node*BS + d.
+#include "common.cuh"
+
+namespace {
+
+constexpr int RB_THREADS = 256;
+
+// ---- block reduction helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warpSum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int NV> __device__ __forceinline__ void blockSumStore(double (&v)[NV], double* partial, int stride, const int* slots) {
+    __shared__ double sh[NV][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const double s = warpSum(v[k]);
+        if (lane == 0) sh[k][w] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = lane < nw ? sh[k][lane] : 0.0;
+            s = warpSum(s);
+            if (lane == 0) partial[(size_t)slots[k] * stride + blockIdx.x] = s;
+        }
+    }
+}
+// every block reduces the bank entry `slot` identically (fixed order) -> same bits in every block
+__device__ __forceinline__ double bankSum(const double* __restrict__ partial, int stride, int slot, int nPart) {
+    __shared__ double sh[32];
+    __shared__ double result;
+    double s = 0;
+    for (int k = threadIdx.x; k < nPart; k += blockDim.x) s += partial[(size_t)slot * stride + k];
+    s = warpSum(s);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = s;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? sh[lane] : 0.0;
+        t = warpSum(t);
+        if (lane == 0) result = t;
+    }
+    __syncthreads();
+    return result;
+}
+
+// ---- SpMV y = A x with up to two fused dots  (y,w1) and (y,y) ------------------------------------------------------
+template <int BS>
+__global__ void __launch_bounds__(256) k_spmv(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+                                              const double* __restrict__ Aval, const double* __restrict__ x,
+                                              double* __restrict__ y, const double* __restrict__ w1, double* partial,
+                                              int stride, int slotYW, int slotYY, const double* __restrict__ scal) {
+    const int lane = threadIdx.x & 31, grp = lane >> 2, r = lane & 3;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nw = gridDim.x * warpsPerBlock;
+    double accYW = 0, accYY = 0;
+    const bool frozen = scal && scal[SC_DONE] != 0.0;
+    if (!frozen) {
+        for (int i = gw; i < nNodes; i += nw) {
+            const int b0 = nbrPtr[i], nb = nbrPtr[i + 1] - b0;
+            double acc = 0;
+            for (int s0 = 0; s0 < nb; s0 += 8) {
+                const int s = s0 + grp;
+                if (s < nb && r < BS) {
+                    const int col = nbr[b0 + s];
+                    const double* ap = Aval + ((size_t)(b0 + s) * BS + r) * BS;
+                    const double* xp = x + (size_t)col * BS;
+                    if constexpr (BS == 4) {
+                        const double2 a01 = *reinterpret_cast<const double2*>(ap);
+                        const double2 a23 = *reinterpret_cast<const double2*>(ap + 2);
+                        const double2 x01 = *reinterpret_cast<const double2*>(xp);
+                        const double2 x23 = *reinterpret_cast<const double2*>(xp + 2);
+                        acc += a01.x * x01.x + a01.y * x01.y + a23.x * x23.x + a23.y * x23.y;
+                    } else {
+#pragma unroll
+                        for (int cidx = 0; cidx < BS; ++cidx) acc += ap[cidx] * xp[cidx];
+                    }
+                }
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (grp == 0 && r < BS) {
+                const size_t o = (size_t)i * BS + r;
+                y[o] = acc;
+                if (slotYW >= 0) accYW += acc * w1[o];
+                if (slotYY >= 0) accYY += acc * acc;
+            }
+        }
+    }
+    if (slotYW >= 0 || slotYY >= 0) {
+        double v[2] = {accYW, accYY};
+        const int slots[2] = {slotYW >= 0 ? slotYW : PS_AUX, slotYY >= 0 ? slotYY : PS_AUX + 1};
+        blockSumStore<2>(v, partial, stride, slots);
+    }
+}
+
+// ---- vector kernels ---------------------------------------------------------------------------------------------------
+// r = b - y (y = A x0 precomputed, or nullptr for x0 = 0) ; r0 = r ; p = v = 0 ; partials rho=(r0,r)=||r||^2, ||b||^2
+__global__ void __launch_bounds__(RB_THREADS) k_init(int n, const double* __restrict__ b, const double* __restrict__ y,
+                                                     double* __restrict__ r, double* __restrict__ r0, double* __restrict__ p,
+                                                     double* __restrict__ v, double* partial, int stride) {
+    double rr = 0, bb = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double bi = b[i];
+        const double ri = y ? bi - y[i] : bi;
+        r[i] = ri;
+        r0[i] = ri;
+        p[i] = 0.0;
+        v[i] = 0.0;
+        rr += ri * ri;
+        bb += bi * bi;
+    }
+    double vv[3] = {rr, rr, bb};
+    const int slots[3] = {PS_RHO, PS_RR, PS_AUX};
+    blockSumStore<3>(vv, partial, stride, slots);
+}
+__global__ void k_init_scal(double* scal, const double* partial, int stride, int nPart, double relTol, int parityPrev,
+                            bool setNorm) {
+    const double bb = bankSum(partial, stride, PS_AUX, nPart);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (setNorm) {
+            scal[SC_BNORM2] = bb;
+            scal[SC_TOL2] = relTol * relTol * bb;
+        }
+        scal[SC_RHO0 + parityPrev] = 1.0;
+        scal[SC_ALPHA] = 1.0;
+        scal[SC_OMEGA] = 1.0;
+        scal[SC_DONE] = 0.0;
+        scal[SC_BAD] = 0.0;
+    }
+}
+
+// K_A: beta = (rho/rho_old)(alpha/omega) ; p = r + beta (p - omega v) ; phat = dinv .* p      [+ convergence test]
+__global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __restrict__ r, double* __restrict__ p,
+                                                         const double* __restrict__ v, const double* __restrict__ dinv,
+                                                         double* __restrict__ ph, double* scal, const double* partial,
+                                                         int stride, int nPart, int parity, int iterIndex) {
+    const double rho = bankSum(partial, stride, PS_RHO, nPart);
+    const double rr = bankSum(partial, stride, PS_RR, nPart);
+    const double rhoOld = scal[SC_RHO0 + (parity ^ 1)], alpha = scal[SC_ALPHA], omega = scal[SC_OMEGA];
+    const bool wasDone = scal[SC_DONE] != 0.0;
+    const bool conv = rr <= scal[SC_TOL2];
+    const bool bad = !(rr == rr) || !(rho == rho) || rho == 0.0 || omega == 0.0 || rhoOld == 0.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && !wasDone) {
+        scal[SC_RES2] = rr;
+        scal[SC_ITERS] = (double)iterIndex;
+        if (conv || bad) scal[SC_DONE] = 1.0;
+        if (bad && !conv) scal[SC_BAD] = 1.0;
+        scal[SC_RHO0 + parity] = rho;
+    }
+    if (wasDone || conv || bad) return;
+    const double beta = (rho / rhoOld) * (alpha / omega);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double pi = r[i] + beta * (p[i] - omega * v[i]);
+        p[i] = pi;
+        ph[i] = dinv[i] * pi;
+    }
+}
+// K_C: alpha = rho / (r0,v) ; s = r - alpha v ; shat = dinv .* s
+__global__ void __launch_bounds__(RB_THREADS) k_update_s(int n, const double* __restrict__ r, const double* __restrict__ v,
+                                                         const double* __restrict__ dinv, double* __restrict__ s,
+                                                         double* __restrict__ sh, double* scal, const double* partial,
+                                                         int stride, int nPart, int parity) {
+    if (scal[SC_DONE] != 0.0) return;
+    const double sigma = bankSum(partial, stride, PS_SIGMA, nPart);
+    const double alpha = scal[SC_RHO0 + parity] / sigma;
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_ALPHA] = alpha;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double si = r[i] - alpha * v[i];
+        s[i] = si;
+        sh[i] = dinv[i] * si;
+    }
+}
+// K_E: omega = (t,s)/(t,t) ; x += alpha phat + omega shat ; r = s - omega t ; partials (r0,r), (r,r)
+__global__ void __launch_bounds__(RB_THREADS) k_update_xr(int n, double* __restrict__ x, double* __restrict__ r,
+                                                          const double* __restrict__ r0, const double* __restrict__ s,
+                                                          const double* __restrict__ t, const double* __restrict__ ph,
+                                                          const double* __restrict__ sh, double* scal, double* partial,
+                                                          int stride, int nPart) {
+    if (scal[SC_DONE] != 0.0) return;
+    const double ts = bankSum(partial, stride, PS_TS, nPart);
+    const double tt = bankSum(partial, stride, PS_TT, nPart);
+    const double omega = tt > 0.0 ? ts / tt : 0.0;
+    const double alpha = scal[SC_ALPHA];
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_OMEGA] = omega;
+    double rho = 0, rr = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        x[i] += alpha * ph[i] + omega * sh[i];
+        const double ri = s[i] - omega * t[i];
+        r[i] = ri;
+        rho += r0[i] * ri;
+        rr += ri * ri;
+    }
+    double vv[2] = {rho, rr};
+    const int slots[2] = {PS_RHO, PS_RR};
+    blockSumStore<2>(vv, partial, stride, slots);
+}
+// d = b - y ; partial ||d||^2 (true residual)
+__global__ void __launch_bounds__(RB_THREADS) k_resid(int n, const double* __restrict__ b, const double* __restrict__ y,
+                                                      double* partial, int stride) {
+    double rr = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double d = y[i] - b[i];
+        rr += d * d;
+    }
+    double vv[1] = {rr};
+    const int slots[1] = {PS_AUX + 1};
+    blockSumStore<1>(vv, partial, stride, slots);
+}
+__global__ void k_bank_to_scal(double* scal, int dst, const double* partial, int stride, int slot, int nPart) {
+    const double s = bankSum(partial, stride, slot, nPart);
+    if (threadIdx.x == 0) scal[dst] = s;
+}
+__global__ void k_zero(double* p, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
+}
+// ABI layout q[n + d*N]  <->  internal node*BS + d
+__global__ void k_to_internal(const double* __restrict__ q, double* __restrict__ dst, int nNodes, int BS) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nNodes * BS) return;
+    const int n = (int)(t / BS), d = (int)(t % BS);
+    dst[t] = q[(size_t)d * nNodes + n];
+}
+__global__ void k_from_internal(const double* __restrict__ src, double* __restrict__ q, int nNodes, int BS) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nNodes * BS) return;
+    const int d = (int)(t / nNodes), n = (int)(t % nNodes);
+    q[t] = src[(size_t)n * BS + d];
+}
+
+struct KrylovDims {
+    int n, BS, vecGrid, spmvGrid, stride;
+};
+KrylovDims setup(pfem_ctx* c) {
+    KrylovDims k;
+    k.BS = c->dim + 1;
+    k.n = c->nNodes * k.BS;
+    k.vecGrid = std::max(1, std::min(c->smCount * 4, divUp(k.n, RB_THREADS)));
+    k.spmvGrid = std::max(1, std::min(c->smCount * 8, divUp(c->nNodes, 8)));
+    k.stride = std::max(k.vecGrid, k.spmvGrid);
+    c->reduceBlocks = k.stride;
+    for (auto* b : {&c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt, &c->kph, &c->ksh}) b->reserve(k.n);
+    c->partial.reserve((size_t)PS_COUNT * k.stride);
+    c->scal.reserve(SC_COUNT);
+    if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
+    return k;
+}
+void spmv(pfem_ctx* c, const KrylovDims& k, const double* x, double* y, const double* w1, int slotYW, int slotYY,
+          bool honourDone) {
+    const double* sc = honourDone ? c->scal.p : nullptr;
+    if (k.BS == 4)
+        k_spmv<4><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
+                                                     k.stride, slotYW, slotYY, sc);
+    else
+        k_spmv<3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
+                                                     k.stride, slotYW, slotYY, sc);
+    LAUNCH_CHECK(c);
+}
+
+}  // namespace
+
+void krylovLoadVector(pfem_ctx* c, const double* qHost, double* dst) {
+    const int BS = c->dim + 1;
+    const size_t n = (size_t)c->nNodes * BS;
+    c->stageD.reserve(n);
+    CUDA_CHECK(cudaMemcpyAsync(c->stageD.p, qHost, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    k_to_internal<<<divUp(n, 256), 256, 0, c->stream>>>(c->stageD.p, dst, c->nNodes, BS);
+    LAUNCH_CHECK(c);
+}
+void krylovStoreVector(pfem_ctx* c, const double* src, double* qHost) {
+    const int BS = c->dim + 1;
+    const size_t n = (size_t)c->nNodes * BS;
+    c->stageD.reserve(n);
+    k_from_internal<<<divUp(n, 256), 256, 0, c->stream>>>(src, c->stageD.p, c->nNodes, BS);
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaMemcpyAsync(qHost, c->stageD.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+void krylovFetchSolution(pfem_ctx* c, double* q) {
+    PFEM_REQUIRE(c->haveSolution, PFEM_ERR_STATE, "no solution on the device");
+    krylovStoreVector(c, c->kx.p, q);
+}
+void krylovMatvec(pfem_ctx* c, const double* xInternal, double* yInternal) {
+    PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "matvec: no assembled system");
+    KrylovDims k = setup(c);
+    spmv(c, k, xInternal, yInternal, nullptr, -1, -1, false);
+}
+// ||A x - b||_2  (Res::Ax_f, PSPG.inl:368)
+double krylovResidualNorm(pfem_ctx* c, const double* xInternal) {
+    PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "residual: no assembled system");
+    PhaseScope ph(c, "Compute Picard Algo residual");
+    KrylovDims k = setup(c);
+    spmv(c, k, xInternal, c->kt.p, nullptr, -1, -1, false);
+    k_resid<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, c->kt.p, c->partial.p, k.stride);
+    LAUNCH_CHECK(c);
+    k_bank_to_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, SC_COUNT - 1, c->partial.p, k.stride, PS_AUX + 1, k.vecGrid);
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p + SC_COUNT - 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    return sqrt(c->hScal[0]);
+}
+
+int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* relResOut, bool warmStart) {
+    PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "solve: no assembled system (pfem_pspg_assemble)");
+    PFEM_REQUIRE(relTol > 0 && maxIter > 0, PFEM_ERR_INVALID, "solve: relTol and maxIter must be positive");
+    PhaseScope ph(c, "Solve system");
+    KrylovDims k = setup(c);
+    const int checkEvery = 20;
+    int totalIters = 0, status = PFEM_OK;
+    double relRes = 0;
+    if (!(warmStart && c->haveSolution)) {
+        k_zero<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(c->kx.p, k.n);
+        LAUNCH_CHECK(c);
+        warmStart = false;
+    }
+    c->haveSolution = true;
+    const int maxRestarts = 4;
+    for (int restart = 0; restart <= maxRestarts; ++restart) {
+        // r = b - A x
+        const bool zeroGuess = !warmStart && restart == 0;
+        if (!zeroGuess) spmv(c, k, c->kx.p, c->kt.p, nullptr, -1, -1, false);
+        k_init<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, zeroGuess ? nullptr : c->kt.p, c->kr.p, c->kr0.p,
+                                                        c->kp.p, c->kv.p, c->partial.p, k.stride);
+        LAUNCH_CHECK(c);
+        k_init_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, c->partial.p, k.stride, k.vecGrid, relTol, 1, restart == 0);
+        LAUNCH_CHECK(c);
+        bool done = false;
+        int it = 0;  // iterations inside this restart cycle
+        while (!done && totalIters + it < maxIter) {
+            const int batch = std::min(checkEvery, maxIter - totalIters - it);
+            for (int b = 0; b < batch; ++b, ++it) {
+                const int parity = it & 1;
+                k_update_p<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kp.p, c->kv.p, c->dinv.p, c->kph.p,
+                                                                    c->scal.p, c->partial.p, k.stride, k.vecGrid, parity, it);
+                LAUNCH_CHECK(c);
+                spmv(c, k, c->kph.p, c->kv.p, c->kr0.p, PS_SIGMA, -1, true);
+                k_update_s<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kv.p, c->dinv.p, c->ks.p, c->ksh.p,
+                                                                    c->scal.p, c->partial.p, k.stride, k.spmvGrid, parity);
+                LAUNCH_CHECK(c);
+                spmv(c, k, c->ksh.p, c->kt.p, c->ks.p, PS_TS, PS_TT, true);
+                k_update_xr<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kx.p, c->kr.p, c->kr0.p, c->ks.p, c->kt.p,
+                                                                     c->kph.p, c->ksh.p, c->scal.p, c->partial.p, k.stride,
+                                                                     k.spmvGrid);
+                LAUNCH_CHECK(c);
+            }
+            // poll: one more K_A-style test is folded into the next batch; here read what the last K_A saw + latest rr
+            k_bank_to_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, SC_COUNT - 2, c->partial.p, k.stride, PS_RR, k.vecGrid);
+            LAUNCH_CHECK(c);
+            CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            const double rrLatest = c->hScal[SC_COUNT - 2];
+            if (c->hScal[SC_DONE] != 0.0) {
+                done = true;
+                it = (int)c->hScal[SC_ITERS];  // iterations completed when the test fired
+            } else if (rrLatest <= c->hScal[SC_TOL2] || !(rrLatest == rrLatest)) {
+                done = true;
+            }
+        }
+        totalIters += it;
+        // true residual
+        const double bnorm = sqrt(c->hScal[SC_BNORM2]);
+        if (bnorm == 0.0) {  // b = 0 -> x = 0
+            k_zero<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(c->kx.p, k.n);
+            LAUNCH_CHECK(c);
+            relRes = 0;
+            break;
+        }
+        const double trueRes = krylovResidualNorm(c, c->kx.p);
+        relRes = trueRes / bnorm;
+        if (!(relRes == relRes)) {
+            status = PFEM_NAN;
+            break;
+        }
+        if (relRes <= relTol * 1.0000001) {
+            status = PFEM_OK;
+            break;
+        }
+        status = PFEM_NOT_CONVERGED;
+        if (totalIters >= maxIter) break;
+        warmStart = true;  // restart from the current iterate (residual replacement / breakdown recovery)
+    }
+    if (itersOut) *itersOut = totalIters;
+    if (relResOut) *relResOut = relRes;
+    return status;
+}

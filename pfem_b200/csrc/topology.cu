@@ -1,0 +1,298 @@
+// topology.cu -- per-remesh pattern build on the device.
+//
+// Replaces the pattern half of Eigen::SparseMatrix::setFromTriplets (MomContEquationPSPG.inl:136) and the
+// Node::m_elements / m_neighbourNodes lists the reference keeps per node (Node.hpp:95-99): from the element
+// connectivity alone it builds
+//   n2ePtr/n2e : node -> incident elements, ascending element index (the order in which setFromTriplets sums
+//                duplicates, so the assembly kernel can reproduce that order),
+//   nbrPtr/nbr : node -> sorted neighbour nodes incl. itself == the (dim+1)x(dim+1) block-row pattern of m_A.
+// All kernels are integer/HBM-bound; one warp per node for the neighbour pass.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void k_convert_conn(const unsigned long long* __restrict__ in, int* __restrict__ conn, int64_t n, int nNodes,
+                               int* __restrict__ cnt, int* __restrict__ bad) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long v = in[i];
+    if (v >= (unsigned long long)nNodes) {
+        atomicOr(bad, 1);
+        conn[i] = 0;
+        return;
+    }
+    conn[i] = (int)v;
+    atomicAdd(&cnt[(int)v], 1);
+}
+
+// tile-local exclusive scan; tile totals to blockSums
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile(int* __restrict__ data, int n, int* __restrict__ blockSums) {
+    __shared__ int warpSums[SCAN_THREADS / 32];
+    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
+    int v[SCAN_ITEMS];
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        v[k] = (base + k < n) ? data[base + k] : 0;
+        sum += v[k];
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warpSums[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int s = (lane < SCAN_THREADS / 32) ? warpSums[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane < SCAN_THREADS / 32) warpSums[lane] = s;  // inclusive over warps
+    }
+    __syncthreads();
+    int excl = inc - sum + (w > 0 ? warpSums[w - 1] : 0);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        if (base + k < n) data[base + k] = excl;
+        excl += v[k];
+    }
+    if (threadIdx.x == SCAN_THREADS - 1 && blockSums) blockSums[blockIdx.x] = excl;
+}
+
+__global__ void k_scan_add(int* __restrict__ data, int n, const int* __restrict__ blockSums) {
+    const int i = blockIdx.x * SCAN_TILE + threadIdx.x;
+    const int add = blockSums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) {
+        int idx = i + k * SCAN_THREADS;
+        if (idx < n) data[idx] += add;
+    }
+}
+
+__global__ void k_fill_n2e(const int* __restrict__ conn, int64_t n, int npe, const int* __restrict__ ptr,
+                           int* __restrict__ cursor, int* __restrict__ n2e) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int node = conn[i];
+    const int pos = atomicAdd(&cursor[node], 1);
+    n2e[ptr[node] + pos] = (int)(i / npe);
+}
+
+// ascending element index per node (lists are short: ~6 in 2-D, ~24 in 3-D); also the valence maximum
+__global__ void k_sort_n2e(const int* __restrict__ ptr, int* __restrict__ n2e, int nNodes, int* __restrict__ maxE) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    int len = 0;
+    if (n < nNodes) {
+        const int b = ptr[n];
+        len = ptr[n + 1] - b;
+        int* a = n2e + b;
+        for (int i = 1; i < len; ++i) {
+            const int key = a[i];
+            int j = i - 1;
+            while (j >= 0 && a[j] > key) {
+                a[j + 1] = a[j];
+                --j;
+            }
+            a[j + 1] = key;
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, o));
+    if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(maxE, len);
+}
+
+// FREE bit := node belongs to no element (Node.inl:48-51), whatever the caller passed
+__global__ void k_fix_free_flag(uint8_t* __restrict__ flags, const int* __restrict__ ptr, int nNodes) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nNodes) return;
+    uint8_t f = flags[n] & ~(uint8_t)PFEM_NODE_FREE;
+    if (ptr[n + 1] == ptr[n]) f |= PFEM_NODE_FREE;
+    flags[n] = f;
+}
+
+// One warp per node.  FILL=false: count distinct neighbours; FILL=true: write them sorted + diagSlot.
+template <bool FILL>
+__global__ void k_neighbours(const int* __restrict__ conn, int npe, const int* __restrict__ n2ePtr,
+                             const int* __restrict__ n2e, int nNodes, int candCap, int* __restrict__ nbrCntOrPtr,
+                             int* __restrict__ nbr, int* __restrict__ diagSlot, int* __restrict__ maxNb) {
+    extern __shared__ int smem[];
+    const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int node = blockIdx.x * (blockDim.x >> 5) + warpInBlock;
+    if (node >= nNodes) return;
+    unsigned* cand = reinterpret_cast<unsigned*>(smem) + (size_t)warpInBlock * candCap;
+    const int eb = n2ePtr[node], ne = n2ePtr[node + 1] - eb;
+    const int C = ne * npe;
+    if (ne == 0) {  // isolated node: the block row is its own diagonal block
+        if (lane == 0) {
+            if (FILL) {
+                nbr[nbrCntOrPtr[node]] = node;
+                diagSlot[node] = 0;
+            } else
+                nbrCntOrPtr[node] = 1;
+        }
+        return;
+    }
+    for (int c = lane; c < C; c += 32) cand[c] = (unsigned)conn[(size_t)n2e[eb + c / npe] * npe + (c % npe)];
+    __syncwarp();
+    // sweep 1: mark later duplicates (bit 31)
+    for (int c = lane; c < C; c += 32) {
+        const unsigned v = cand[c] & 0x7fffffffu;
+        bool first = true;
+        for (int q = 0; q < c; ++q)
+            if ((cand[q] & 0x7fffffffu) == v) {
+                first = false;
+                break;
+            }
+        if (!first) cand[c] = v | 0x80000000u;
+    }
+    __syncwarp();
+    int nDistinct = 0;
+    for (int c = lane; c < C; c += 32) {
+        const unsigned v = cand[c];
+        if (v & 0x80000000u) continue;
+        ++nDistinct;
+        if (FILL) {
+            int rank = 0;
+            for (int q = 0; q < C; ++q) {
+                const unsigned u = cand[q];
+                rank += (!(u & 0x80000000u) && u < v) ? 1 : 0;
+            }
+            nbr[nbrCntOrPtr[node] + rank] = (int)v;
+            if ((int)v == node) diagSlot[node] = rank;
+        }
+    }
+    if (!FILL) {
+        for (int o = 16; o > 0; o >>= 1) nDistinct += __shfl_xor_sync(0xffffffffu, nDistinct, o);
+        if (lane == 0) {
+            nbrCntOrPtr[node] = nDistinct;
+            atomicMax(maxNb, nDistinct);
+        }
+    }
+}
+
+}  // namespace
+
+// In-place exclusive scan of n ints (recursive tile scan); if totalOut != null the grand total is stored there
+// (device pointer).
+static void scanRec(pfem_ctx* c, int* data, int n, int* scratch, int* totalOut) {
+    const int tiles = divUp(n, SCAN_TILE);
+    k_scan_tile<<<tiles, SCAN_THREADS, 0, c->stream>>>(data, n, scratch);
+    LAUNCH_CHECK(c);
+    if (tiles == 1) {
+        if (totalOut) CUDA_CHECK(cudaMemcpyAsync(totalOut, scratch, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+        return;
+    }
+    scanRec(c, scratch, tiles, scratch + tiles + 1, totalOut);
+    k_scan_add<<<tiles, SCAN_THREADS, 0, c->stream>>>(data, n, scratch);
+    LAUNCH_CHECK(c);
+}
+
+void exclusiveScanInt(pfem_ctx* c, int* data, int n, int* totalOut) {
+    size_t need = 0;
+    for (int m = n;;) {
+        const int tiles = divUp(m, SCAN_TILE);
+        need += tiles + 1;
+        if (tiles == 1) break;
+        m = tiles;
+    }
+    c->scanScratch.reserve(need + 8);
+    scanRec(c, data, n, c->scanScratch.p, totalOut);
+}
+
+void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* elemNodes, const uint8_t* flagsHost) {
+    PhaseScope ph(c, "Build pattern");
+    const int npe = c->dim + 1;
+    PFEM_REQUIRE(nNodes64 > 0 && nElems64 >= 0, PFEM_ERR_INVALID, "set_topology: empty mesh");
+    PFEM_REQUIRE(nNodes64 < (1ll << 30) && nElems64 * npe < (1ll << 31), PFEM_ERR_INVALID,
+                 "set_topology: mesh too large for int32 device indices");
+    const int nNodes = (int)nNodes64, nElems = (int)nElems64;
+    const int64_t nConn = (int64_t)nElems * npe;
+    c->nNodes = nNodes;
+    c->nElems = nElems;
+    c->haveTopology = false;
+    c->haveSystem = c->haveSolution = c->haveQprev = c->haveSnapshot = c->havePositions = c->haveDirichlet = false;
+    c->nnzReference = -1;
+
+    c->conn.reserve(nConn + 4);
+    c->flags.reserve(nNodes);
+    c->n2ePtr.reserve(nNodes + 2);
+    c->n2e.reserve(nConn + 4);
+    c->nbrPtr.reserve(nNodes + 2);
+    c->diagSlot.reserve(nNodes);
+    c->stage64.reserve(nConn + 4);
+    c->scratchI.reserve((size_t)nNodes + 64);
+    int* cursor = c->scratchI.p;
+    int* misc = c->scratchI.p + nNodes;  // [0]=bad, [1]=maxE, [2]=maxNb, [3]=total
+    CUDA_CHECK(cudaMemcpyAsync(c->stage64.p, elemNodes, nConn * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->flags.p, flagsHost, nNodes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->n2ePtr.p, 0, (nNodes + 2) * sizeof(int), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->scratchI.p, 0, ((size_t)nNodes + 64) * sizeof(int), c->stream));
+    if (nConn > 0) {
+        k_convert_conn<<<divUp(nConn, 256), 256, 0, c->stream>>>(c->stage64.p, c->conn.p, nConn, nNodes, c->n2ePtr.p, misc);
+        LAUNCH_CHECK(c);
+    }
+    exclusiveScanInt(c, c->n2ePtr.p, nNodes + 1, nullptr);
+    if (nConn > 0) {
+        k_fill_n2e<<<divUp(nConn, 256), 256, 0, c->stream>>>(c->conn.p, nConn, npe, c->n2ePtr.p, cursor, c->n2e.p);
+        LAUNCH_CHECK(c);
+    }
+    k_sort_n2e<<<divUp(nNodes, 128), 128, 0, c->stream>>>(c->n2ePtr.p, c->n2e.p, nNodes, misc + 1);
+    LAUNCH_CHECK(c);
+    k_fix_free_flag<<<divUp(nNodes, 256), 256, 0, c->stream>>>(c->flags.p, c->n2ePtr.p, nNodes);
+    LAUNCH_CHECK(c);
+    int h[4];
+    CUDA_CHECK(cudaMemcpyAsync(h, misc, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    PFEM_REQUIRE(h[0] == 0, PFEM_ERR_INVALID, "set_topology: element node index out of range");
+    c->maxE = h[1];
+    PFEM_REQUIRE(c->maxE <= 4096, PFEM_ERR_INVALID, "set_topology: node valence above 4096 elements");
+
+    // neighbour lists
+    const int warps = 8;
+    const int candCap = max(c->maxE, 1) * npe;
+    const size_t smem = (size_t)warps * candCap * sizeof(int);
+    if (smem > 48 * 1024) {
+        CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    CUDA_CHECK(cudaMemsetAsync(c->nbrPtr.p, 0, (nNodes + 2) * sizeof(int), c->stream));
+    k_neighbours<false><<<divUp(nNodes, warps), warps * 32, smem, c->stream>>>(
+        c->conn.p, npe, c->n2ePtr.p, c->n2e.p, nNodes, candCap, c->nbrPtr.p, nullptr, nullptr, misc + 2);
+    LAUNCH_CHECK(c);
+    exclusiveScanInt(c, c->nbrPtr.p, nNodes + 1, misc + 3);
+    CUDA_CHECK(cudaMemcpyAsync(h, misc, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->maxNb = h[2];
+    c->nBlocks = h[3];
+    PFEM_REQUIRE(c->maxNb <= 255, PFEM_ERR_INVALID, "set_topology: node with more than 255 neighbours");
+    c->nbr.reserve(c->nBlocks + 4);
+    k_neighbours<true><<<divUp(nNodes, warps), warps * 32, smem, c->stream>>>(
+        c->conn.p, npe, c->n2ePtr.p, c->n2e.p, nNodes, candCap, c->nbrPtr.p, c->nbr.p, c->diagSlot.p, nullptr);
+    LAUNCH_CHECK(c);
+
+    // nodal fields sized for the new mesh
+    const size_t n4 = (size_t)nNodes * 4;
+    c->X4.reserve(n4);
+    c->Xsave4.reserve(n4);
+    c->V4.reserve(n4);
+    c->A4.reserve(n4);
+    c->VP4.reserve(n4);
+    c->dirMask.reserve(nNodes);
+    c->dirVal4.reserve(n4);
+    CUDA_CHECK(cudaMemsetAsync(c->X4.p, 0, n4 * sizeof(double), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->V4.p, 0, n4 * sizeof(double), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->A4.p, 0, n4 * sizeof(double), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->VP4.p, 0, n4 * sizeof(double), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->dirMask.p, 0, nNodes, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->dirVal4.p, 0, n4 * sizeof(double), c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->haveTopology = true;
+}

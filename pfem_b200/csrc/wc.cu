@@ -1,0 +1,444 @@
+// wc.cu -- explicit weakly-compressible step (SolverWCompNewton::m_solveWCompNewtonNoT, WCompNewton/Solver.cpp:236-263)
+// and the CFL time step (computeNextDT, :192-234) on the device.
+//
+// Reference structure: omp element loop -> per-element temporaries -> SERIAL nodal scatter (ContEquation.inl:398-408,
+// MomEquation.inl:279-298).  B200 design: node GATHER.  LPN lanes own one node, stride over its incident elements
+// (ascending element index == the reference's serial scatter order), recompute the element geometry from coordinates,
+// keep only the row of node i, reduce over the LPN lanes and apply the nodal epilogue (1/M, BC, EOS, kick) in the same
+// kernel.  No atomics, no per-element temporaries (the reference stores a 12x12 matrix per element just to read its
+// diagonal, MomEquation.inl:237), deterministic.  Three launches per step:
+//   k_wc_kick_move : v_half = v + dt/2 a ; x += dt v_half (non-fixed)                       (Solver.cpp:249-253)
+//   k_wc_cont      : F0, lumped M -> p = F0/M (free: 0) -> rho = Tait-Murnaghan(p)          (ContEquation.inl:123-148)
+//   k_wc_mom       : F = -K v + D^T p + F_b, lumped rho-mass -> a -> v = v_half + dt/2 a    (MomEquation.inl:201-226)
+// Device layout: X4=(x,y,z,p), V4=(u,v,w,rho), A4=(ax,ay,az,-); cont writes the ping-pong copies X4b/V4b so that the
+// gathers of other nodes never see half-updated p/rho.
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+__device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+    *reinterpret_cast<double2*>(p) = make_double2(a, b);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+}
+
+__global__ void k_wc_kick_move(int nNodes, int dim, double dt, const uint8_t* __restrict__ flags, double* __restrict__ X4,
+                               double* __restrict__ V4, const double* __restrict__ A4) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nNodes) return;
+    const bool fixed = flags[n] & PFEM_NODE_FIXED;
+    for (int d = 0; d < dim; ++d) {
+        const double vh = V4[(size_t)n * 4 + d] + 0.5 * dt * A4[(size_t)n * 4 + d];
+        V4[(size_t)n * 4 + d] = vh;
+        if (!fixed) X4[(size_t)n * 4 + d] += vh * dt;
+    }
+}
+
+template <int DIM> struct ElemGeo {
+    double g[DIM][DIM + 1];
+    double V;
+};
+
+// gather the 4-double records of the element nodes and build grad N and the volume (Element.cpp:15-135, MB.inl:93-127)
+template <int DIM>
+__device__ __forceinline__ void loadElem(const int* __restrict__ conn, int e, const double* __restrict__ XA,
+                                         const double* __restrict__ VA, int (&nd)[DIM + 1], double (&xw)[DIM + 1],
+                                         double (&vel)[DIM + 1][DIM], double (&vw)[DIM + 1], ElemGeo<DIM>& G) {
+    constexpr int NPE = DIM + 1;
+    constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
+    if constexpr (DIM == 3) {
+        const int4 q = *reinterpret_cast<const int4*>(conn + (size_t)e * 4);
+        nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
+    } else {
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) nd[m] = conn[(size_t)e * NPE + m];
+    }
+    double px[NPE][DIM];
+#pragma unroll
+    for (int m = 0; m < NPE; ++m) {
+        const double* xp = XA + (size_t)nd[m] * 4;
+        const double* vp = VA + (size_t)nd[m] * 4;
+        const double2 x01 = ld2(xp), x23 = ld2(xp + 2), v01 = ld2(vp), v23 = ld2(vp + 2);
+        px[m][0] = x01.x, px[m][1] = x01.y;
+        vel[m][0] = v01.x, vel[m][1] = v01.y;
+        if constexpr (DIM == 3) {
+            px[m][2] = x23.x;
+            vel[m][2] = v23.x;
+        }
+        xw[m] = x23.y;
+        vw[m] = v23.y;
+    }
+    double J[DIM][DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+        for (int m = 0; m < DIM; ++m) J[d][m] = px[m + 1][d] - px[0][d];
+    double det, inv[DIM][DIM];
+    if constexpr (DIM == 2) {
+        det = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+        const double rd = 1.0 / det;
+        inv[0][0] = J[1][1] * rd;
+        inv[0][1] = -J[0][1] * rd;
+        inv[1][0] = -J[1][0] * rd;
+        inv[1][1] = J[0][0] * rd;
+    } else {
+        det = J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
+              J[2][0] * J[1][1] * J[0][2] - J[2][1] * J[1][2] * J[0][0] - J[2][2] * J[1][0] * J[0][1];
+        const double rd = 1.0 / det;
+        inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * rd;
+        inv[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) * rd;
+        inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rd;
+        inv[1][0] = (J[2][0] * J[1][2] - J[1][0] * J[2][2]) * rd;
+        inv[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) * rd;
+        inv[1][2] = (J[1][0] * J[0][2] - J[0][0] * J[1][2]) * rd;
+        inv[2][0] = (J[1][0] * J[2][1] - J[2][0] * J[1][1]) * rd;
+        inv[2][1] = (J[2][0] * J[0][1] - J[0][0] * J[2][1]) * rd;
+        inv[2][2] = (J[0][0] * J[1][1] - J[1][0] * J[0][1]) * rd;
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        double s = -inv[0][d];
+#pragma unroll
+        for (int m = 1; m < DIM; ++m) s -= inv[m][d];
+        G.g[d][0] = s;
+#pragma unroll
+        for (int m = 0; m < DIM; ++m) G.g[d][m + 1] = inv[m][d];
+    }
+    G.V = det * REF;
+}
+
+template <int N> __device__ __forceinline__ double pick(const double (&a)[N], int idx) {
+    double t = a[0];
+#pragma unroll
+    for (int m = 1; m < N; ++m) t = (idx == m) ? a[m] : t;
+    return t;
+}
+template <int LPN> __device__ __forceinline__ double groupSum(double v) {
+#pragma unroll
+    for (int o = LPN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct WcArgs {
+    const int* conn;
+    const int* n2ePtr;
+    const int* n2e;
+    const uint8_t* flags;
+    const uint8_t* dirMask;
+    const double* dirVal4;
+    int nNodes;
+    double dt, mu, K0, K0p, rhoStar, body[3];
+    int meduri;
+};
+
+// continuity, CDS_dpdt (ContEquation.inl:353-413, 334-350, 139-146, 319-331)
+template <int DIM, int LPN>
+__global__ void __launch_bounds__(256) k_wc_cont(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
+                                                 double* __restrict__ X4n, double* __restrict__ V4n) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / LPN, sub = t % LPN;
+    const bool valid = i < a.nNodes;
+    double m = 0, F0 = 0;
+    if (valid) {
+        const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+        for (int k = sub; k < ne; k += LPN) {
+            const int e = a.n2e[eb + k];
+            int nd[NPE];
+            double P[NPE], vel[NPE][DIM], rho[NPE];
+            ElemGeo<DIM> G;
+            loadElem<DIM>(a.conn, e, X4, V4, nd, P, vel, rho, G);
+            int li = 0;
+            double sumP = 0, divv = 0;
+#pragma unroll
+            for (int q = 0; q < NPE; ++q) {
+                li = (nd[q] == i) ? q : li;
+                sumP += P[q];
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) divv += G.g[c][q] * vel[q][c];
+            }
+            const double pi = pick<NPE>(P, li);
+            const double si = a.K0 / NPE + a.K0p * PHI * (pi + sumP);       // sum_g w (K0 + K0' N.p) N_i
+            const double stab = a.meduri ? G.V * PHI * (pi + sumP) : (G.V / NPE) * pi;  // Me*P | MeLumped*P
+            F0 += -a.dt * G.V * si * divv + stab;
+            m += G.V / NPE;                                                  // lump2(M), f = 1
+        }
+    }
+    m = groupSum<LPN>(m);
+    F0 = groupSum<LPN>(F0);
+    if (valid && sub == 0) {
+        const bool isFree = a.flags[i] & PFEM_NODE_FREE;
+        double inv = 1.0 / m;
+        if (isFree) {
+            F0 = 0.0;
+            inv = 1.0;
+        }
+        const double p = inv * F0;
+        const double rho = pow((a.K0p / a.K0) * p + 1.0, 1.0 / a.K0p) * a.rhoStar;
+        const double* xp = X4 + (size_t)i * 4;
+        const double* vp = V4 + (size_t)i * 4;
+        st4(X4n + (size_t)i * 4, xp[0], xp[1], xp[2], p);
+        st4(V4n + (size_t)i * 4, vp[0], vp[1], vp[2], rho);
+    }
+}
+
+// momentum (MomEquation.inl:229-302, 305-374, 216-222)
+template <int DIM, int LPN>
+__global__ void __launch_bounds__(256) k_wc_mom(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
+                                                double* __restrict__ V4out, double* __restrict__ A4out) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / LPN, sub = t % LPN;
+    const bool valid = i < a.nNodes;
+    double M = 0, F[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) F[c] = 0;
+    if (valid) {
+        const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+        for (int k = sub; k < ne; k += LPN) {
+            const int e = a.n2e[eb + k];
+            int nd[NPE];
+            double P[NPE], vel[NPE][DIM], rho[NPE];
+            ElemGeo<DIM> G;
+            loadElem<DIM>(a.conn, e, X4, V4, nd, P, vel, rho, G);
+            int li = 0;
+            double sumP = 0, sumR = 0;
+            double Gm[DIM][DIM];  // G_ac = sum_j v_{j,a} g[c][j]
+#pragma unroll
+            for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) Gm[aa][c] = 0;
+#pragma unroll
+            for (int q = 0; q < NPE; ++q) {
+                li = (nd[q] == i) ? q : li;
+                sumP += P[q];
+                sumR += rho[q];
+#pragma unroll
+                for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) Gm[aa][c] += vel[q][aa] * G.g[c][q];
+            }
+            double tr = 0;
+#pragma unroll
+            for (int aa = 0; aa < DIM; ++aa) tr += Gm[aa][aa];
+            double gi[DIM];
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) gi[c] = pick<NPE>(G.g[c], li);
+            const double pbar = sumP / NPE;
+            const double li_mass = G.V * PHI * (pick<NPE>(rho, li) + sumR);  // lumped rho-mass == sum_g w (N.rho) N_i
+#pragma unroll
+            for (int aa = 0; aa < DIM; ++aa) {
+                double sg = 0;  // sum_c sigma_ac g[c][i],  sigma = mu (G + G^T - 2/3 tr I)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    double sig = Gm[aa][c] + Gm[c][aa];
+                    if (c == aa) sig -= (2.0 / 3.0) * tr;
+                    sg += a.mu * sig * gi[c];
+                }
+                F[aa] += -G.V * sg + G.V * pbar * gi[aa] + a.body[aa] * li_mass;
+            }
+            M += li_mass;
+        }
+    }
+    M = groupSum<LPN>(M);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) F[c] = groupSum<LPN>(F[c]);
+    if (valid && sub == 0) {
+        const uint8_t fl = a.flags[i];
+        const bool isFree = fl & PFEM_NODE_FREE, isBound = fl & PFEM_NODE_BOUND;
+        const double* vp = V4 + (size_t)i * 4;
+        double inv = 1.0 / M;
+        double acc[3] = {0, 0, 0}, vn[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+            double f = F[c], iv = inv;
+            if (isFree && !isBound) {
+                f = a.body[c];
+                iv = 1.0;
+            } else if (isBound && a.dirMask[i]) {
+                f = a.dirVal4[(size_t)i * 4 + c];  // reference hazard 10: the Dirichlet *velocity* becomes the acceleration
+                iv = 1.0;
+            }
+            acc[c] = iv * f;
+            vn[c] = vp[c] + 0.5 * a.dt * acc[c];
+        }
+        st4(V4out + (size_t)i * 4, vn[0], vn[1], vn[2], vp[3]);
+        st4(A4out + (size_t)i * 4, acc[0], acc[1], acc[2], 0.0);
+    }
+}
+
+// CFL (Solver.cpp:192-234) with Element::getRin (Element.cpp:226-294): one thread per element, block min -> partial
+template <int DIM>
+__global__ void __launch_bounds__(256) k_wc_dt(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
+                                               const double* __restrict__ V4, double mu, double K0, double K0p, double sc2,
+                                               double* __restrict__ partial) {
+    constexpr int NPE = DIM + 1;
+    constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
+    double best = 1.7976931348623157e308;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nElems; e += gridDim.x * blockDim.x) {
+        int nd[NPE];
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) nd[m] = conn[(size_t)e * NPE + m];
+        double px[NPE][3], mx = 0, alphaMax = 0;
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) {
+            const double* xp = X4 + (size_t)nd[m] * 4;
+            const double* vp = V4 + (size_t)nd[m] * 4;
+            const double2 x01 = ld2(xp), x23 = ld2(xp + 2), v01 = ld2(vp), v23 = ld2(vp + 2);
+            px[m][0] = x01.x, px[m][1] = x01.y, px[m][2] = x23.x;
+            double u2 = v01.x * v01.x + v01.y * v01.y;
+            if (DIM == 3) u2 += v23.x * v23.x;
+            const double c2 = (K0 + K0p * x23.y) / v23.y;
+            const double alpha = mu / v23.y;
+            mx = fmax(fmax(u2, c2), mx);
+            alphaMax = fmax(alphaMax, alpha * alpha);
+        }
+        double he;
+        if constexpr (DIM == 2) {
+            const double J00 = px[1][0] - px[0][0], J01 = px[2][0] - px[0][0], J10 = px[1][1] - px[0][1], J11 = px[2][1] - px[0][1];
+            const double A = (J00 * J11 - J10 * J01) * REF;
+            auto dist = [&](int p, int q) {
+                const double dx = px[p][0] - px[q][0], dy = px[p][1] - px[q][1];
+                return sqrt(dx * dx + dy * dy);
+            };
+            const double s = (dist(0, 1) + dist(1, 2) + dist(0, 2)) / 2;
+            he = 2 * (A / s);
+        } else {
+            const double x0 = px[0][0], x1 = px[1][0], x2 = px[2][0], x3 = px[3][0];
+            const double y0 = px[0][1], y1 = px[1][1], y2 = px[2][1], y3 = px[3][1];
+            const double z0 = px[0][2], z1 = px[1][2], z2 = px[2][2], z3 = px[3][2];
+            const double J00 = x1 - x0, J01 = x2 - x0, J02 = x3 - x0, J10 = y1 - y0, J11 = y2 - y0, J12 = y3 - y0,
+                         J20 = z1 - z0, J21 = z2 - z0, J22 = z3 - z0;
+            const double det = J00 * J11 * J22 + J01 * J12 * J20 + J02 * J10 * J21 - J20 * J11 * J02 - J21 * J12 * J00 -
+                               J22 * J10 * J01;
+            auto nrm = [](double p, double q, double r) { return sqrt(p * p + q * q + r * r); };
+            const double n1 = nrm(J10 * J21 - J20 * J11, J20 * J01 - J00 * J21, J00 * J11 - J10 * J01);
+            const double n2 = nrm(J12 * J21 - J22 * J11, J22 * J01 - J02 * J21, J02 * J11 - J12 * J01);
+            const double n3 = nrm(J10 * J22 - J20 * J12, J20 * J02 - J00 * J22, J00 * J12 - J10 * J02);
+            const double n4 = nrm((y1 - y3) * (z2 - z3) - (z1 - z3) * (y2 - y3), (z1 - z3) * (x2 - x3) - (x1 - x3) * (z2 - z3),
+                                  (x1 - x3) * (y2 - y3) - (y1 - y3) * (x2 - x3));
+            he = 2 * (6 * (det * REF) / (n1 + n2 + n3 + n4));
+        }
+        // max over nodes of max(u2, c2, 4 alpha^2/he^2): he is per element, so the alpha term can be taken outside
+        mx = fmax(mx, 4 * alphaMax / (he * he));
+        const double cand = sc2 * he * he / mx;
+        best = (cand < best || cand != cand) ? cand : best;  // NaN propagates (Solver.cpp:231-232)
+    }
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = (other < best || other != other) ? other : best;
+    }
+    if (lane == 0) sh[w] = best;
+    __syncthreads();
+    if (w == 0) {
+        double b2 = lane < (blockDim.x >> 5) ? sh[lane] : 1.7976931348623157e308;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, b2, o);
+            b2 = (other < b2 || other != other) ? other : b2;
+        }
+        if (lane == 0) partial[blockIdx.x] = b2;
+    }
+}
+__global__ void k_min_final(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    double best = 1.7976931348623157e308;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double o = partial[k];
+        best = (o < best || o != o) ? o : best;
+    }
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = (other < best || other != other) ? other : best;
+    }
+    if (lane == 0) sh[w] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            const double o = sh[k];
+            best = (o < best || o != o) ? o : best;
+        }
+        out[0] = best;
+    }
+}
+
+WcArgs makeArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
+    WcArgs a;
+    a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.flags = c->flags.p;
+    a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p, a.nNodes = c->nNodes;
+    a.dt = dt, a.mu = p.mu, a.K0 = p.K0, a.K0p = p.K0p, a.rhoStar = p.rhoStar;
+    for (int d = 0; d < 3; ++d) a.body[d] = p.bodyForce[d];
+    a.meduri = p.meduri;
+    return a;
+}
+
+}  // namespace
+
+void commExchangeNodal(pfem_ctx* c, int what);  // comm.cu (multi-GPU only)
+
+void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
+    PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, "wc_step: topology/positions missing");
+    PFEM_REQUIRE(dt > 0 && p.K0 > 0 && p.K0p != 0, PFEM_ERR_INVALID, "wc_step: dt, K0 must be positive and K0p non-zero");
+    PFEM_REQUIRE(c->nRanks == 1, PFEM_ERR_STATE, "wc_step: use the sharded entry point on a multi-rank context");
+    const size_t n4 = (size_t)c->nNodes * 4;
+    c->X4b.reserve(n4);
+    c->V4b.reserve(n4);
+    const WcArgs a = makeArgs(c, p, dt);
+    constexpr int LPN = 8;
+    const int grid = divUp((int64_t)c->nNodes * LPN, 256);
+    {
+        PhaseScope ph(c, "Update solutions");
+        k_wc_kick_move<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->nNodes, c->dim, dt, c->flags.p, c->X4.p, c->V4.p, c->A4.p);
+        LAUNCH_CHECK(c);
+    }
+    {
+        PhaseScope ph(c, "Solving continuity eq");
+        if (c->dim == 2)
+            k_wc_cont<2, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else
+            k_wc_cont<3, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        LAUNCH_CHECK(c);
+    }
+    {
+        PhaseScope ph(c, "Solving momentum eq");
+        if (c->dim == 2)
+            k_wc_mom<2, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else
+            k_wc_mom<3, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        LAUNCH_CHECK(c);
+    }
+    std::swap(c->X4.p, c->X4b.p);  // X4b holds (x, p_new): make it current
+    std::swap(c->X4.cap, c->X4b.cap);
+}
+
+int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dtOut) {
+    PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, "wc_next_dt: topology/positions missing");
+    PFEM_REQUIRE(dtOut, PFEM_ERR_INVALID, "wc_next_dt: null");
+    PhaseScope ph(c, "Compute next dt");
+    const int grid = std::max(1, std::min(c->smCount * 8, divUp(c->nElems, 256)));
+    c->dtPartial.reserve(grid + 8);
+    c->scal.reserve(SC_COUNT);
+    if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
+    const double sc2 = securityCoeff * securityCoeff;
+    if (c->dim == 2)
+        k_wc_dt<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
+    else
+        k_wc_dt<3><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
+    LAUNCH_CHECK(c);
+    k_min_final<<<1, 256, 0, c->stream>>>(c->dtPartial.p, grid, c->scal.p + SC_COUNT - 1);
+    LAUNCH_CHECK(c);
+    if (c->nRanks > 1) commAllReduceMin(c, c->scal.p + SC_COUNT - 1);
+    CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p + SC_COUNT - 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const double ts = c->hScal[0];
+    const double dt = fmin(sqrt(ts), maxDT);  // Solver.cpp:228
+    *dtOut = dt;
+    return (dt != dt || ts != ts) ? PFEM_NAN : PFEM_OK;
+}

@@ -1,0 +1,207 @@
+"""Synthetic meshes and fields for parity tests and benchmarks.
+
+Host-side input generation only (numpy); nothing here is on the hot path.  The reference
+gets its meshes from gmsh + CGAL alpha shapes (srcs/mesh/Mesh.cpp:762-917, Mesh2D.cpp,
+Mesh3D.cpp), neither of which is available here, so the stand-in is a Kuhn/Freudenthal
+split of the unit box: 2 triangles per square / 6 tetrahedra per cube, all with detJ > 0
+(the orientation CGAL alpha-shape cells have, Mesh3D.cpp:166-170).
+
+Node flag bits follow the C ABI (include/pfem_b200.h): bit0 isBound, bit1 isFree,
+bit2 isFixed, bit3 isOnFreeSurface (Node.hpp:93-105, Node.inl:48-66).
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass, field
+
+import numpy as np
+
+F_BOUND, F_FREE, F_FIXED, F_FS = 1, 2, 4, 8
+
+
+@dataclass
+class Mesh:
+    dim: int
+    x: np.ndarray          # (dim*nNodes,) float64, layout x[n + d*nNodes]
+    conn: np.ndarray       # (nElm, dim+1) int64, row-major, positive orientation
+    flags: np.ndarray      # (nNodes,) uint8
+    dir_mask: np.ndarray   # (nNodes,) uint8: bound node whose tag carries a velocity BC
+    dir_val: np.ndarray    # (dim*nNodes,) float64 Dirichlet velocity, layout n + d*nNodes
+    n_cells: int = 0
+    meta: dict = field(default_factory=dict)
+
+    @property
+    def n_nodes(self) -> int:
+        return self.flags.shape[0]
+
+    @property
+    def n_elems(self) -> int:
+        return self.conn.shape[0]
+
+    def coords(self) -> np.ndarray:
+        """(nNodes, dim) view-copy of the positions."""
+        return self.x.reshape(self.dim, self.n_nodes).T.copy()
+
+
+def _perm_sign(p) -> int:
+    s = 1
+    p = list(p)
+    for i in range(len(p)):
+        while p[i] != i:
+            j = p[i]
+            p[i], p[j] = p[j], p[i]
+            s = -s
+    return s
+
+
+def kuhn_box(dim: int, n: int, *, jitter: float = 0.1, seed: int = 1234, permute: bool = False,
+             perm_seed: int = 4321, free_fraction: float = 0.0, free_seed: int = 7,
+             extent: float = 1.0) -> Mesh:
+    """Unit box split into n^dim cells, each cut into dim! simplices along the main diagonal.
+
+    jitter: interior nodes are displaced by U(-jitter*h, jitter*h) per coordinate (seed).
+    permute: apply a random permutation to node and element numbering (models PFEM node
+             insert/delete renumbering, Mesh.cpp:139-144, 181-204).
+    free_fraction: append that fraction of extra isolated nodes (isFree: in no element).
+    Flags: the faces x=0, x=1, (y=0, y=1,) and the bottom (last coordinate = 0) are
+    isBound|isFixed with a zero-velocity Dirichlet BC; the top face is isOnFreeSurface.
+    """
+    assert dim in (2, 3)
+    m = n + 1
+    h = extent / n
+    axes = [np.arange(m)] * dim
+    grid = np.meshgrid(*axes, indexing="ij")           # grid[d][i0,i1,(i2)]
+    idx = [g.ravel() for g in grid]
+    strides = [m ** (dim - 1 - d) for d in range(dim)]  # lexicographic, last coord fastest
+    n_nodes = m ** dim
+    pts = np.stack([i.astype(np.float64) * h for i in idx], axis=1)  # (nNodes, dim)
+
+    on_lo = [i == 0 for i in idx]
+    on_hi = [i == n for i in idx]
+    boundary = np.zeros(n_nodes, dtype=bool)
+    for d in range(dim):
+        boundary |= on_lo[d] | on_hi[d]
+    top = on_hi[dim - 1]
+    wall = np.zeros(n_nodes, dtype=bool)
+    for d in range(dim - 1):
+        wall |= on_lo[d] | on_hi[d]
+    wall |= on_lo[dim - 1]
+
+    if jitter > 0:
+        rng = np.random.default_rng(seed)
+        disp = rng.uniform(-jitter * h, jitter * h, size=(n_nodes, dim))
+        disp[boundary] = 0.0
+        pts = pts + disp
+
+    # cells and their simplices
+    caxes = [np.arange(n)] * dim
+    cgrid = np.meshgrid(*caxes, indexing="ij")
+    base = sum(c.ravel().astype(np.int64) * s for c, s in zip(cgrid, strides))  # node id of cell origin
+    simplices = []
+    for perm in itertools.permutations(range(dim)):
+        verts = [base]
+        cur = base
+        for a in perm:
+            cur = cur + strides[a]
+            verts.append(cur)
+        if _perm_sign(perm) < 0:
+            verts[-1], verts[-2] = verts[-2], verts[-1]
+        simplices.append(np.stack(verts, axis=1))
+    # interleave so that the dim! simplices of one cell are consecutive
+    conn = np.stack(simplices, axis=1).reshape(-1, dim + 1).astype(np.int64)
+
+    flags = np.zeros(n_nodes, dtype=np.uint8)
+    flags[wall] |= F_BOUND | F_FIXED
+    flags[top & ~wall] |= F_FS
+    dir_mask = wall.astype(np.uint8)
+
+    if free_fraction > 0:
+        k = max(1, int(round(free_fraction * n_nodes)))
+        rng = np.random.default_rng(free_seed)
+        extra = rng.uniform(0.05 * extent, 0.95 * extent, size=(k, dim))
+        extra[:, dim - 1] += extent  # detached drops above the box
+        pts = np.concatenate([pts, extra], axis=0)
+        flags = np.concatenate([flags, np.full(k, F_FREE, dtype=np.uint8)])
+        dir_mask = np.concatenate([dir_mask, np.zeros(k, dtype=np.uint8)])
+        n_nodes += k
+
+    if permute:
+        rng = np.random.default_rng(perm_seed)
+        new_of_old = rng.permutation(n_nodes)
+        old_of_new = np.empty_like(new_of_old)
+        old_of_new[new_of_old] = np.arange(n_nodes)
+        pts = pts[old_of_new]
+        flags = flags[old_of_new]
+        dir_mask = dir_mask[old_of_new]
+        conn = new_of_old[conn]
+        conn = conn[rng.permutation(conn.shape[0])]
+
+    x = np.ascontiguousarray(pts.T).reshape(-1)
+    dir_val = np.zeros(dim * n_nodes, dtype=np.float64)
+    return Mesh(dim=dim, x=x, conn=np.ascontiguousarray(conn), flags=flags, dir_mask=dir_mask, dir_val=dir_val,
+                n_cells=n, meta=dict(jitter=jitter, seed=seed, permute=permute, free_fraction=free_fraction))
+
+
+def det_j(mesh: Mesh) -> np.ndarray:
+    """detJ per element (Element.cpp:71-86) -- used to check orientation of generated meshes."""
+    c = mesh.coords()
+    p0 = c[mesh.conn[:, 0]]
+    J = np.stack([c[mesh.conn[:, k + 1]] - p0 for k in range(mesh.dim)], axis=2)  # (nElm, dim, dim) columns = edges
+    return np.linalg.det(J)
+
+
+# --------------------------------------------------------------------------------------
+# Fields
+# --------------------------------------------------------------------------------------
+PSPG_PARAMS = dict(rho=1000.0, mu=1e-3, dt=1e-3)       # damBreakKoshizuka3DIncomp.lua:30-31,44,50
+WC_PARAMS = dict(mu=1e-3, K0=2.2e5, K0p=7.6, rhoStar=1000.0, securityCoeff=0.1)  # ...3DComp.lua:32-34,46
+
+
+def gravity(dim: int) -> np.ndarray:
+    g = np.zeros(3)
+    g[dim - 1] = -9.81
+    return g
+
+
+def velocity_field(mesh: Mesh, *, noise: float = 0.01, seed: int = 99, zero_on_walls: bool = True) -> np.ndarray:
+    """v = (sin2pi x cos2pi y, -cos2pi x sin2pi y, 0.1 sin2pi z) + noise*N(0,1); layout n + d*nNodes."""
+    c = mesh.coords()
+    nn = mesh.n_nodes
+    v = np.zeros((mesh.dim, nn))
+    tp = 2 * np.pi
+    v[0] = np.sin(tp * c[:, 0]) * np.cos(tp * c[:, 1])
+    v[1] = -np.cos(tp * c[:, 0]) * np.sin(tp * c[:, 1])
+    if mesh.dim == 3:
+        v[2] = 0.1 * np.sin(tp * c[:, 2])
+    rng = np.random.default_rng(seed)
+    v += noise * rng.standard_normal(v.shape)
+    if zero_on_walls:
+        v[:, (mesh.flags & F_BOUND) != 0] = 0.0
+    return v.reshape(-1)
+
+
+def hydrostatic_pressure(mesh: Mesh, rho: float = 1000.0, g: float = 9.81, height: float = 1.0) -> np.ndarray:
+    c = mesh.coords()
+    return rho * g * np.maximum(height - c[:, mesh.dim - 1], 0.0)
+
+
+def tait_density(p: np.ndarray, K0: float, K0p: float, rho_star: float) -> np.ndarray:
+    """rho = rho*.((K0'/K0) p + 1)^(1/K0')  (WCompNewton/ContEquation.inl:319-331)."""
+    return rho_star * np.power((K0p / K0) * p + 1.0, 1.0 / K0p)
+
+
+def pspg_state(mesh: Mesh, **kw):
+    """(q_cur, q_prev): each (dim+1)*nNodes in Q.hpp layout [u,v,(w),p]; v_prev = v."""
+    v = velocity_field(mesh, **kw)
+    p = hydrostatic_pressure(mesh)
+    q = np.concatenate([v, p])
+    return q.copy(), q.copy()
+
+
+def wc_state(mesh: Mesh, **kw):
+    """dict of SoA arrays for the weakly-compressible problem: v, p, rho, acc (WC/Problem.cpp:17-18)."""
+    v = velocity_field(mesh, **kw)
+    p = hydrostatic_pressure(mesh)
+    rho = tait_density(p, WC_PARAMS["K0"], WC_PARAMS["K0p"], WC_PARAMS["rhoStar"])
+    acc = np.zeros_like(v)
+    return dict(v=v, p=p, rho=rho, acc=acc)

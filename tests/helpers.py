@@ -1,0 +1,60 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+from oracle import oracle as orc
+from pfem_b200 import meshgen as mg
+
+TOL_AB = 1e-12   # north_star: assembled matrices and RHS to 1e-12 relative (per block type)
+TOL_Q = 1e-8     # north_star: per-step fields to 1e-8 relative
+
+
+def body_force(dim):
+    return mg.gravity(dim)
+
+
+def pspg_case(dim, n, **kw):
+    mesh = mg.kuhn_box(dim, n, **kw)
+    q, q_prev = mg.pspg_state(mesh)
+    rng = np.random.default_rng(5)
+    q_prev = q_prev + 0.02 * rng.standard_normal(q_prev.shape)   # v_prev != v so that both enter distinctly
+    # non-zero Dirichlet data on part of the walls exercises the column elimination
+    vals = mesh.dir_val.reshape(dim, mesh.n_nodes)
+    sel = (mesh.dir_mask != 0) & (np.arange(mesh.n_nodes) % 3 == 0)
+    vals[:, sel] = 0.1 * rng.standard_normal((dim, int(sel.sum())))
+    mesh.dir_val = vals.reshape(-1)
+    # a bound node whose tag carries no velocity BC (reference hazard 11)
+    bound = np.flatnonzero(mesh.dir_mask)
+    if bound.size:
+        mesh.dir_mask[bound[::7]] = 0
+    P = mg.PSPG_PARAMS
+    par = orc.pspg_param_array(P["rho"], P["mu"], P["dt"], body_force(dim))
+    return mesh, q, q_prev, par
+
+
+def block_errors(A, A_ref, n_nodes, dim):
+    """max|dA|/max|A_ref| per block type (vv, vp, pv, pp): the blocks differ in scale by up to 1e13."""
+    assert (A.indptr == A_ref.indptr).all(), "CSC column pointers differ"
+    assert (A.indices == A_ref.indices).all(), "CSC row indices differ"
+    cols = np.repeat(np.arange(A_ref.shape[1]), np.diff(A_ref.indptr))
+    rows = A_ref.indices
+    rp = rows >= dim * n_nodes
+    cp = cols >= dim * n_nodes
+    out = {}
+    for name, sel in (("vv", ~rp & ~cp), ("vp", ~rp & cp), ("pv", rp & ~cp), ("pp", rp & cp)):
+        if sel.any():
+            ref = np.abs(A_ref.data[sel]).max()
+            out[name] = float(np.abs(A.data[sel] - A_ref.data[sel]).max() / (ref if ref > 0 else 1.0))
+    return out
+
+
+def vec_block_errors(b, b_ref, n_nodes, dim):
+    out = {}
+    for name, sl in (("v", slice(0, dim * n_nodes)), ("p", slice(dim * n_nodes, None))):
+        ref = np.abs(b_ref[sl]).max()
+        out[name] = float(np.abs(b[sl] - b_ref[sl]).max() / (ref if ref > 0 else 1.0))
+    return out
+
+
+def rel_err(a, ref):
+    m = np.abs(ref).max()
+    return float(np.abs(a - ref).max() / (m if m > 0 else 1.0))

@@ -1,0 +1,77 @@
+"""CUDA explicit weakly-compressible step and CFL time step vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from pfem_b200 import meshgen as mg
+from pfem_b200.capi import PfemContext
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _pack(st):
+    return np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
+
+
+@pytest.mark.parametrize("dim,n,kw,meduri", [
+    (2, 24, dict(free_fraction=0.01), True),          # ~C3 size
+    (2, 10, dict(permute=True), False),
+    (3, 4, dict(), True),
+    (3, 10, dict(free_fraction=0.01, permute=True), True),
+    (3, 8, dict(), False),
+])
+def test_wc_steps_match_oracle(dim, n, kw, meduri):
+    mesh = mg.kuhn_box(dim, n, **kw)
+    st = mg.wc_state(mesh)
+    st["acc"] = 0.5 * np.random.default_rng(4).standard_normal(st["acc"].shape)
+    W = mg.WC_PARAMS
+    g = mg.gravity(dim)
+    wp_ref = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri)
+    with PfemContext(dim, 0) as ctx:
+        ctx.set_mesh(mesh)
+        ctx.set_states(0, _pack(st))
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri)
+        x_ref, st_ref = mesh.x, st
+        for step in range(3):
+            dt_ref = orc.wc_next_dt(mesh, x_ref, st_ref, wp_ref, W["securityCoeff"], 1e-3)
+            dt = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+            assert abs(dt - dt_ref) <= 1e-13 * dt_ref
+            ctx.wc_step(wp, dt_ref)
+            x_ref, st_ref = orc.wc_step(mesh, x_ref, st_ref, wp_ref, dt_ref)
+            out = ctx.get_states(0, 2 * dim + 2)
+            nn = mesh.n_nodes
+            got = dict(v=out[: dim * nn], p=out[dim * nn:(dim + 1) * nn], rho=out[(dim + 1) * nn:(dim + 2) * nn],
+                       acc=out[(dim + 2) * nn:])
+            for k in ("v", "p", "rho", "acc"):
+                assert rel_err(got[k], st_ref[k]) < TOL * (10 ** step), (k, step)
+            assert np.abs(ctx.get_positions() - x_ref).max() < 1e-13
+
+
+def test_wc_bit_reproducible():
+    mesh = mg.kuhn_box(3, 6, permute=True)
+    st = mg.wc_state(mesh)
+    W = mg.WC_PARAMS
+    outs = []
+    for _ in range(2):
+        with PfemContext(3, 0) as ctx:
+            ctx.set_mesh(mesh)
+            ctx.set_states(0, _pack(st))
+            wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], mg.gravity(3), True)
+            for _s in range(2):
+                ctx.wc_step(wp, 1e-6)
+            outs.append(ctx.get_states(0, 8))
+    assert (outs[0] == outs[1]).all()
+
+
+def test_state_roundtrip():
+    mesh = mg.kuhn_box(2, 3)
+    q = np.random.default_rng(1).standard_normal(6 * mesh.n_nodes)
+    with PfemContext(2, 0) as ctx:
+        ctx.set_mesh(mesh)
+        ctx.set_states(0, q)
+        assert (ctx.get_states(0, 6) == q).all()
+        assert (ctx.get_states(2, 2) == q[2 * mesh.n_nodes: 4 * mesh.n_nodes]).all()
+        assert (ctx.get_positions() == mesh.x).all()
