@@ -259,6 +259,12 @@ class PfemContext:
         A = sp.csc_matrix((val, row_idx, col_ptr), shape=(self.n_dof, self.n_dof))
         return A, b
 
+    def pspg_reference_nnz(self) -> int:
+        """nnz of the reference's m_A for the current system (count pass of the export only)."""
+        nnz = C.c_int64(0)
+        self._chk(self._L.pfem_pspg_export_csc(self._h, C.byref(nnz), None, None, None, None))
+        return nnz.value
+
     def pspg_matvec(self, x):
         x = _f64(x, self.n_dof)
         y = np.empty(self.n_dof)

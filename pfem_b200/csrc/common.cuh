@@ -96,6 +96,11 @@ struct pfem_ctx {
     DevBuf<int> n2ePtr, n2e;   // node -> incident elements, ascending element index
     DevBuf<int> nbrPtr, nbr;   // node -> sorted neighbour nodes (incl. itself) == block-row pattern
     DevBuf<int> diagSlot;      // position of the node in its own neighbour list
+    DevBuf<unsigned> n2eSlots; // per (node, incident element): slot bytes of the element's nodes in the node's nbr list
+    DevBuf<unsigned> blkMask;  // per block (i,slot): maskWords words, bit k = incident element k of i contains the neighbour
+    int maskWords = 1;
+    DevBuf<unsigned> rowDir;   // per node: bit s = neighbour slot s is a Dirichlet node (rebuilt when topology/BC change)
+    bool rowDirDirty = true;
     DevBuf<int> scratchI;      // counters / cursors
     DevBuf<int> scanScratch;   // tile sums of exclusiveScanInt
     DevBuf<unsigned long long> stage64;
@@ -152,6 +157,9 @@ struct pfem_ctx {
                         &kp, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &ifaceBuf})
             b->accounting = &deviceBytes;
         stage64.accounting = &deviceBytes;
+        n2eSlots.accounting = &deviceBytes;
+        blkMask.accounting = &deviceBytes;
+        rowDir.accounting = &deviceBytes;
     }
 };
 

@@ -136,6 +136,7 @@ void fieldsSetDirichlet(pfem_ctx* c, const uint8_t* mask, const double* values) 
     LAUNCH_CHECK(c);
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->haveDirichlet = true;
+    c->rowDirDirty = true;
 }
 void fieldsSnapshot(pfem_ctx* c) {
     needTopo(c);

@@ -12,6 +12,8 @@
 //   * 5 kernels per iteration, the loop runs `checkEvery` iterations between convergence polls; a device-side DONE
 //     flag freezes the state once ||r|| <= tol ||b||.
 // Vectors use the internal dof order node*BS + d.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -63,8 +65,34 @@ __device__ __forceinline__ double bankSum(const double* __restrict__ partial, in
 }
 
 // ---- SpMV y = A x with up to two fused dots  (y,w1) and (y,y) ------------------------------------------------------
+// Software-pipelined over block rows: row pointers are fetched two rows ahead and column indices one row ahead, so the
+// only loads a row waits for are its own A rows (streamed once, evict-first) and the x gathers (L2-resident).
+template <int BS> struct RowLoad {
+    double2 a01, a23, x01, x23;
+};
 template <int BS>
-__global__ void __launch_bounds__(256) k_spmv(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+__device__ __forceinline__ void loadSlot(const double* __restrict__ Aval, const double* __restrict__ x, int blk, int col,
+                                         int r, RowLoad<BS>& L) {
+    const double* ap = Aval + ((size_t)blk * BS + r) * BS;
+    const double* xp = x + (size_t)col * BS;
+    if constexpr (BS == 4) {
+        L.a01 = __ldcs(reinterpret_cast<const double2*>(ap));
+        L.a23 = __ldcs(reinterpret_cast<const double2*>(ap + 2));
+        L.x01 = __ldg(reinterpret_cast<const double2*>(xp));
+        L.x23 = __ldg(reinterpret_cast<const double2*>(xp + 2));
+    } else {
+        L.a01 = make_double2(__ldcs(ap), __ldcs(ap + 1));
+        L.a23 = make_double2(__ldcs(ap + 2), 0.0);
+        L.x01 = make_double2(__ldg(xp), __ldg(xp + 1));
+        L.x23 = make_double2(__ldg(xp + 2), 0.0);
+    }
+}
+template <int BS> __device__ __forceinline__ double dotSlot(const RowLoad<BS>& L) {
+    return L.a01.x * L.x01.x + L.a01.y * L.x01.y + L.a23.x * L.x23.x + L.a23.y * L.x23.y;
+}
+
+template <int BS, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
                                               const double* __restrict__ Aval, const double* __restrict__ x,
                                               double* __restrict__ y, const double* __restrict__ w1, double* partial,
                                               int stride, int slotYW, int slotYY, const double* __restrict__ scal) {
@@ -74,25 +102,40 @@ __global__ void __launch_bounds__(256) k_spmv(int nNodes, const int* __restrict_
     double accYW = 0, accYY = 0;
     const bool frozen = scal && scal[SC_DONE] != 0.0;
     if (!frozen) {
-        for (int i = gw; i < nNodes; i += nw) {
-            const int b0 = nbrPtr[i], nb = nbrPtr[i + 1] - b0;
+        int i = gw;
+        int pb0 = 0, pb1 = 0, qb0 = 0, qb1 = 0;  // row i / row i+nw block ranges
+        if (i < nNodes) {
+            pb0 = __ldg(nbrPtr + i);
+            pb1 = __ldg(nbrPtr + i + 1);
+        }
+        if (i + nw < nNodes) {
+            qb0 = __ldg(nbrPtr + i + nw);
+            qb1 = __ldg(nbrPtr + i + nw + 1);
+        }
+        int c0 = -1, c1 = -1;
+        if (grp < pb1 - pb0) c0 = __ldg(nbr + pb0 + grp);
+        if (grp + 8 < pb1 - pb0) c1 = __ldg(nbr + pb0 + grp + 8);
+        for (; i < nNodes; i += nw) {
+            int fb0 = 0, fb1 = 0;
+            if (i + 2 * nw < nNodes) {
+                fb0 = __ldg(nbrPtr + i + 2 * nw);
+                fb1 = __ldg(nbrPtr + i + 2 * nw + 1);
+            }
+            int d0 = -1, d1 = -1;
+            if (grp < qb1 - qb0) d0 = __ldg(nbr + qb0 + grp);
+            if (grp + 8 < qb1 - qb0) d1 = __ldg(nbr + qb0 + grp + 8);
+            const int nb = pb1 - pb0;
             double acc = 0;
-            for (int s0 = 0; s0 < nb; s0 += 8) {
-                const int s = s0 + grp;
-                if (s < nb && r < BS) {
-                    const int col = nbr[b0 + s];
-                    const double* ap = Aval + ((size_t)(b0 + s) * BS + r) * BS;
-                    const double* xp = x + (size_t)col * BS;
-                    if constexpr (BS == 4) {
-                        const double2 a01 = *reinterpret_cast<const double2*>(ap);
-                        const double2 a23 = *reinterpret_cast<const double2*>(ap + 2);
-                        const double2 x01 = *reinterpret_cast<const double2*>(xp);
-                        const double2 x23 = *reinterpret_cast<const double2*>(xp + 2);
-                        acc += a01.x * x01.x + a01.y * x01.y + a23.x * x23.x + a23.y * x23.y;
-                    } else {
-#pragma unroll
-                        for (int cidx = 0; cidx < BS; ++cidx) acc += ap[cidx] * xp[cidx];
-                    }
+            if (r < BS) {
+                RowLoad<BS> L0, L1;
+                if (c0 >= 0) loadSlot<BS>(Aval, x, pb0 + grp, c0, r, L0);
+                if (c1 >= 0) loadSlot<BS>(Aval, x, pb0 + grp + 8, c1, r, L1);
+                if (c0 >= 0) acc += dotSlot<BS>(L0);
+                if (c1 >= 0) acc += dotSlot<BS>(L1);
+                for (int s = grp + 16; s < nb; s += 8) {  // rows with more than 16 blocks (rare)
+                    RowLoad<BS> L;
+                    loadSlot<BS>(Aval, x, pb0 + s, __ldg(nbr + pb0 + s), r, L);
+                    acc += dotSlot<BS>(L);
                 }
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 4);
@@ -104,6 +147,7 @@ __global__ void __launch_bounds__(256) k_spmv(int nNodes, const int* __restrict_
                 if (slotYW >= 0) accYW += acc * w1[o];
                 if (slotYY >= 0) accYY += acc * acc;
             }
+            pb0 = qb0, pb1 = qb1, qb0 = fb0, qb1 = fb1, c0 = d0, c1 = d1;
         }
     }
     if (slotYW >= 0 || slotYY >= 0) {
@@ -267,12 +311,17 @@ KrylovDims setup(pfem_ctx* c) {
 void spmv(pfem_ctx* c, const KrylovDims& k, const double* x, double* y, const double* w1, int slotYW, int slotYY,
           bool honourDone) {
     const double* sc = honourDone ? c->scal.p : nullptr;
-    if (k.BS == 4)
-        k_spmv<4><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
-                                                     k.stride, slotYW, slotYY, sc);
+    PhaseScope ph(c, "SpMV");
+    static const int minb = getenv("PFEM_SPMV_MINB") ? atoi(getenv("PFEM_SPMV_MINB")) : 3;
+    if (k.BS == 4 && minb == 4)
+        k_spmv<4, 4><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
+                                                        k.stride, slotYW, slotYY, sc);
+    else if (k.BS == 4)
+        k_spmv<4, 3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
+                                                        k.stride, slotYW, slotYY, sc);
     else
-        k_spmv<3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
-                                                     k.stride, slotYW, slotYY, sc);
+        k_spmv<3, 3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
+                                                        k.stride, slotYW, slotYY, sc);
     LAUNCH_CHECK(c);
 }
 

@@ -15,27 +15,37 @@
 // Storage: node-block CSR ("BSR") with BS=(dim+1): Aval[(nbrPtr[i]+slot)*BS*BS + r*BS + c] = A(i + r*N, nbr[slot] + c*N).
 // Masked rows are held as explicit zero rows + unit diagonal internally; pfem_pspg_export_csc emits the reference's
 // exact CSC pattern.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
 
-template <int DIM> struct ElemS {
-    double g[DIM * (DIM + 1)];  // grad N, g[d*NPE + k]   (MatricesBuilder.inl:93-127)
-    double cmass;               // rho V phi / dt          M/dt   (phi = 1/((dim+1)(dim+2)))
-    double cvisc;               // mu V                    K
-    double cdiv;                // V / npe                 D
-    double cpc;                 // (tau/dt) V / npe        (tau/dt) C
-    double cL;                  // tau V / rho             tau L
+// per-element record staged in shared memory by phase 1 (one per incident element of the node)
+template <int DIM> struct alignas(16) ElemS {
+    static constexpr int GP = (DIM == 3) ? 4 : 2;  // doubles per node gradient (16-byte aligned for LDS.128)
+    double g[DIM + 1][GP];  // grad N_m = g[m][0..DIM)   (MatricesBuilder.inl:93-127)
+    double V;               // element size detJ*ref; all five block coefficients are multiples of V and tau*V:
+    double tauV;            //   M/dt: rho phi/dt V | K: mu V | D: V/npe | (tau/dt) C: tauV/(npe dt) | tau L: tauV/rho
+    unsigned slots;         // slot byte of each local node in the neighbour list of i
+    int li;                 // local index of node i in this element
+    double pad_[(DIM == 3) ? 2 : 1];  // record stride = odd multiple of 16 B: LDS.128 of different records spread over banks
+};
+struct BlockCoef {
+    double kmass, kvisc, kdiv, kpc, kL;  // rho phi/dt, mu, 1/npe, 1/(npe dt), 1/rho
 };
 
 struct AsmArgs {
     const int* conn;
     const int* n2ePtr;
     const int* n2e;
+    const unsigned* n2eSlots;
+    const unsigned* blkMask;
     const int* nbrPtr;
     const int* nbr;
     const int* diagSlot;
     const uint8_t* flags;
+    const unsigned* rowDir;   // per node: dirWords words, bit s = neighbour slot s is a Dirichlet node
     const uint8_t* dirMask;
     const double* dirVal4;
     const double* X4;
@@ -43,7 +53,7 @@ struct AsmArgs {
     double* Aval;
     double* b;
     double* dinv;
-    int nNodes, ecap, nbcap;
+    int nNodes, ecap, nbcap, CH, dirWords;
     double rho, mu, dt, body[3];
 };
 
@@ -61,301 +71,413 @@ __global__ void k_vnorm(const double* __restrict__ V4, double* __restrict__ VP4,
     VP4[(size_t)n * 4 + 3] = sqrt(s);
 }
 
-template <int DIM> __device__ __forceinline__ int findByte(unsigned packed, int v) {
+// rowDir bit s of node i: neighbour slot s is a bound node whose tag carries a velocity BC (PSPG.inl:206-208)
+__global__ void k_row_dir(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+                          const uint8_t* __restrict__ flags, const uint8_t* __restrict__ dirMask, int W,
+                          unsigned* __restrict__ rowDir) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nNodes) return;
+    const int b0 = nbrPtr[i], nb = nbrPtr[i + 1] - b0;
+    for (int w = 0; w < W; ++w) {
+        unsigned bits = 0;
+        for (int s = w * 32; s < min(nb, w * 32 + 32); ++s) {
+            const int nd = nbr[b0 + s];
+            if (dirMask[nd] && (flags[nd] & PFEM_NODE_BOUND)) bits |= 1u << (s & 31);
+        }
+        rowDir[(size_t)i * W + w] = bits;
+    }
+}
+
+__device__ __forceinline__ int findByte(unsigned packed, int v) {
     const unsigned eq = __vcmpeq4(packed, (unsigned)v * 0x01010101u);
     return (__ffs(eq) - 1) >> 3;
 }
 
-// contribution of one element to row r of block (i,j)
+// full (dim+1)x(dim+1) contribution of one element to block (i,j); acc is 4x4 row-major for both dims
 template <int DIM>
-__device__ __forceinline__ void accumRow(const ElemS<DIM>& E, int li, int lj, int r, double (&out)[DIM + 1]) {
-    constexpr int NPE = DIM + 1;
-    double gi[DIM], gj[DIM], dot = 0;
-#pragma unroll
-    for (int d = 0; d < DIM; ++d) {
-        gi[d] = E.g[d * NPE + li];
-        gj[d] = E.g[d * NPE + lj];
-        dot += gi[d] * gj[d];
+__device__ __forceinline__ void accumBlock(const ElemS<DIM>& E, const BlockCoef& K, int li, int lj, double (&acc)[16]) {
+    double gi[DIM], gj[DIM];
+    if constexpr (DIM == 3) {
+        const double2 a = ld2(&E.g[li][0]), a2 = ld2(&E.g[li][2]), c = ld2(&E.g[lj][0]), c2 = ld2(&E.g[lj][2]);
+        gi[0] = a.x, gi[1] = a.y, gi[2] = a2.x;
+        gj[0] = c.x, gj[1] = c.y, gj[2] = c2.x;
+    } else {
+        const double2 a = ld2(&E.g[li][0]), c = ld2(&E.g[lj][0]);
+        gi[0] = a.x, gi[1] = a.y;
+        gj[0] = c.x, gj[1] = c.y;
     }
-    const bool vrow = r < DIM;
-    const int rr = vrow ? r : 0;
-    const double gjr = E.g[rr * NPE + lj], gir = E.g[rr * NPE + li];
-    // velocity row a=r :  mu V g[c][i] g[a][j] + delta_ac (rho V phi (1+delta_ij)/dt + mu V g_i.g_j) ; -(V/npe) g[a][i]
-    // pressure row     :  (tau/dt)(V/npe) g[c][i] + (V/npe) g[c][j]                                 ; tau (V/rho) g_i.g_j
-    const double ca = vrow ? E.cvisc * gjr : E.cpc;
-    const double cb = vrow ? 0.0 : E.cdiv;
-    const double diag = E.cmass * (li == lj ? 2.0 : 1.0) + E.cvisc * dot;
+    const double2 vt = ld2(&E.V);
+    const double cmass = K.kmass * vt.x, cvisc = K.kvisc * vt.x, cdiv = K.kdiv * vt.x, cpc = K.kpc * vt.y, cL = K.kL * vt.y;
+    double dot = 0;
 #pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-        double v = ca * gi[c] + cb * gj[c];
-        if (vrow && c == r) v += diag;
-        out[c] += v;
+    for (int d = 0; d < DIM; ++d) dot += gi[d] * gj[d];
+    const double diag = cmass * (li == lj ? 2.0 : 1.0) + cvisc * dot;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+        // velocity row a :  mu V g[c][i] g[a][j] + delta_ac (rho V phi (1+delta_ij)/dt + mu V g_i.g_j) ; -(V/npe) g[a][i]
+        const double t = cvisc * gj[a];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) acc[a * 4 + c] += t * gi[c];
+        acc[a * 4 + a] += diag;
+        acc[a * 4 + DIM] -= cdiv * gi[a];
     }
-    out[DIM] += vrow ? -E.cdiv * gir : E.cL * dot;
+    // pressure row :  (tau/dt)(V/npe) g[c][i] + (V/npe) g[c][j] ; tau (V/rho) g_i.g_j
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) acc[DIM * 4 + c] += cpc * gi[c] + cdiv * gj[c];
+    acc[DIM * 4 + DIM] += cL * dot;
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(256) k_pspg_assemble(const AsmArgs a) {
+// per-node header and the first-chunk per-lane data; prefetched one node ahead by the persistent warp
+struct NodeHdr {
+    int eb, ne, nb0, nb, si;
+    unsigned fl, dir0;
+};
+struct LaneData {
+    int nbrNode;      // neighbour node of slot `lane` (lane < nb)
+    unsigned packed;  // slot bytes of incident element `lane` (lane < ne)
+    unsigned mask;    // lanes 0..15: element mask of off-diagonal block `lane` (first 32 incident elements)
+};
+// per-neighbour nodal record staged once per node in shared memory: (x, y, z, -, u_prev, v_prev, w_prev, |v_cur|)
+struct alignas(16) NodeRec {
+    double x[4];
+    double v[4];
+    double pad_[2];  // 80-byte stride (odd multiple of 16 B)
+};
+
+template <int DIM, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a) {
     constexpr int NPE = DIM + 1, BS = DIM + 1;
     constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
     extern __shared__ __align__(16) unsigned char smemRaw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int i = blockIdx.x * wpb + wib;
-    const int CH = a.ecap >> 5;
-    // per-warp shared memory carve-up
-    const size_t perWarp = (size_t)a.ecap * (sizeof(ElemS<DIM>) + 4) + (size_t)a.nbcap * 4 * (1 + CH) + (size_t)a.nbcap;
-    const size_t perWarpAl = (perWarp + 15) & ~(size_t)15;
-    unsigned char* base = smemRaw + perWarpAl * wib;
-    ElemS<DIM>* es = reinterpret_cast<ElemS<DIM>*>(base);
-    unsigned* eslots = reinterpret_cast<unsigned*>(base + (size_t)a.ecap * sizeof(ElemS<DIM>));
-    int* nbrS = reinterpret_cast<int*>(eslots + a.ecap);
-    unsigned* emask = reinterpret_cast<unsigned*>(nbrS + a.nbcap);
-    unsigned char* dirS = reinterpret_cast<unsigned char*>(emask + (size_t)a.nbcap * CH);
-    if (i >= a.nNodes) return;
-
-    const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
-    const int nb0 = a.nbrPtr[i], nb = a.nbrPtr[i + 1] - nb0;
-    const int si = a.diagSlot[i];
-    const uint8_t fl = a.flags[i];
-    const bool isBound = fl & PFEM_NODE_BOUND, isFree = fl & PFEM_NODE_FREE;
-    const bool maskV = isBound || isFree, maskP = isFree;
+    const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
+    const int CH = a.CH;
+    unsigned char* wbase = smemRaw + (size_t)wib * ((size_t)a.ecap * sizeof(ElemS<DIM>) + (size_t)a.nbcap * sizeof(NodeRec));
+    ElemS<DIM>* es = reinterpret_cast<ElemS<DIM>*>(wbase);
+    NodeRec* nrec = reinterpret_cast<NodeRec*>(wbase + (size_t)a.ecap * sizeof(ElemS<DIM>));
     const double invdt = 1.0 / a.dt;
+    BlockCoef KC;
+    KC.kmass = a.rho * PHI * invdt, KC.kvisc = a.mu, KC.kdiv = 1.0 / NPE, KC.kpc = invdt / NPE, KC.kL = 1.0 / a.rho;
+    // lane roles in phase 2: lanes 16..19 own the diagonal block, the other 28 lanes one off-diagonal block each
+    const bool diagLane = (lane & 28) == 16;
+    const int dq = lane & 3;                       // diagonal lane: handles incident elements k = dq (mod 4)
+    const int offIdx = lane < 16 ? lane : lane - 4;  // off-diagonal lane: block index within a round of 28
 
-    for (int s = lane; s < nb; s += 32) {
-        const int nd = a.nbr[nb0 + s];
-        nbrS[s] = nd;
-        dirS[s] = a.dirMask[nd];
-    }
-    for (int s = lane; s < nb * CH; s += 32) emask[s] = 0u;
-    __syncwarp();
-
-    // ------------------------------------------------------------------ phase 1: element geometry + RHS rows of node i
-    double be[BS];
-#pragma unroll
-    for (int r = 0; r < BS; ++r) be[r] = 0.0;
-    for (int ch = 0; ch < CH; ++ch) {
-        const int k = ch * 32 + lane;
-        if (k < ne) {
-            const int e = a.n2e[eb + k];
-            int nd[NPE];
-            if constexpr (DIM == 3) {
-                const int4 q = *reinterpret_cast<const int4*>(a.conn + (size_t)e * 4);
-                nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
-            } else {
-#pragma unroll
-                for (int m = 0; m < NPE; ++m) nd[m] = a.conn[(size_t)e * NPE + m];
-            }
-            double px[NPE][DIM], vp[NPE][DIM], usum = 0;
-#pragma unroll
-            for (int m = 0; m < NPE; ++m) {
-                const double* xp = a.X4 + (size_t)nd[m] * 4;
-                const double* vq = a.VP4 + (size_t)nd[m] * 4;
-                const double2 x01 = ld2(xp), v01 = ld2(vq), v23 = ld2(vq + 2);
-                px[m][0] = x01.x, px[m][1] = x01.y;
-                vp[m][0] = v01.x, vp[m][1] = v01.y;
-                if constexpr (DIM == 3) {
-                    px[m][2] = xp[2];
-                    vp[m][2] = v23.x;
-                }
-                usum += v23.y;  // |v_cur| of the node
-            }
-            // J, detJ, inverse (Element.cpp:15-135)
-            double J[DIM][DIM];
-#pragma unroll
-            for (int d = 0; d < DIM; ++d)
-#pragma unroll
-                for (int m = 0; m < DIM; ++m) J[d][m] = px[m + 1][d] - px[0][d];
-            double det, inv[DIM][DIM];
-            if constexpr (DIM == 2) {
-                det = J[0][0] * J[1][1] - J[1][0] * J[0][1];
-                const double rd = 1.0 / det;
-                inv[0][0] = J[1][1] * rd;
-                inv[0][1] = -J[0][1] * rd;
-                inv[1][0] = -J[1][0] * rd;
-                inv[1][1] = J[0][0] * rd;
-            } else {
-                det = J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
-                      J[2][0] * J[1][1] * J[0][2] - J[2][1] * J[1][2] * J[0][0] - J[2][2] * J[1][0] * J[0][1];
-                const double rd = 1.0 / det;
-                inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * rd;
-                inv[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) * rd;
-                inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rd;
-                inv[1][0] = (J[2][0] * J[1][2] - J[1][0] * J[2][2]) * rd;
-                inv[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) * rd;
-                inv[1][2] = (J[1][0] * J[0][2] - J[0][0] * J[1][2]) * rd;
-                inv[2][0] = (J[1][0] * J[2][1] - J[2][0] * J[1][1]) * rd;
-                inv[2][1] = (J[2][0] * J[0][1] - J[0][0] * J[2][1]) * rd;
-                inv[2][2] = (J[0][0] * J[1][1] - J[1][0] * J[0][1]) * rd;
-            }
-            ElemS<DIM> E;
-#pragma unroll
-            for (int d = 0; d < DIM; ++d) {
-                double s = -inv[0][d];
-#pragma unroll
-                for (int m = 1; m < DIM; ++m) s -= inv[m][d];
-                E.g[d * NPE] = s;
-#pragma unroll
-                for (int m = 0; m < DIM; ++m) E.g[d * NPE + m + 1] = inv[m][d];
-            }
-            // tau (PSPG.inl:238-259): h = sqrt(ref detJ / pi) also in 3-D (reference hazard 7, reproduced)
-            const double V = det * REF;
-            const double h2 = REF * det / 3.14159265358979323846;
-            const double U = usum / NPE;
-            const double t1 = 2.0 * invdt, t3 = 4.0 * a.mu / (h2 * a.rho);
-            const double tau = 1.0 / sqrt(t1 * t1 + 4.0 * U * U / h2 + 9.0 * t3 * t3);
-            E.cmass = a.rho * V * PHI * invdt;
-            E.cvisc = a.mu * V;
-            E.cdiv = V / NPE;
-            E.cpc = tau * invdt * E.cdiv;
-            E.cL = tau * V / a.rho;
-            // slots of the element's nodes in the neighbour list of i (sorted -> binary search)
-            unsigned packed = 0;
-            int li = 0;
-#pragma unroll
-            for (int m = 0; m < NPE; ++m) {
-                int lo = 0, hi = nb - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    if (nbrS[mid] < nd[m]) lo = mid + 1;
-                    else hi = mid;
-                }
-                packed |= (unsigned)lo << (8 * m);
-                if (nd[m] == i) li = m;
-                atomicOr(&emask[lo * CH + ch], 1u << lane);
-            }
-            if constexpr (DIM == 2) packed |= 0xff000000u;  // unused byte never matches a slot (< 255)
-            es[k] = E;
-            eslots[k] = packed;
-            // RHS rows of node i: be = [F + (M/dt) vPrev ; tau H + (tau/dt) C vPrev]   (PSPG.inl:53)
-            double sumvp[DIM], gb = 0, gs = 0;
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) {
-                double s = 0;
-#pragma unroll
-                for (int m = 0; m < NPE; ++m) s += vp[m][c];
-                sumvp[c] = s;
-                const double gci = E.g[c * NPE + li];
-                gb += gci * a.body[c];
-                gs += gci * s;
-            }
-            double vpi[DIM];
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) {
-                double t = vp[0][c];
-#pragma unroll
-                for (int m = 1; m < NPE; ++m) t = (li == m) ? vp[m][c] : t;
-                vpi[c] = t;
-            }
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) be[c] += a.rho * E.cdiv * a.body[c] + E.cmass * (vpi[c] + sumvp[c]);
-            be[DIM] += tau * V * gb + E.cpc * gs;
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < BS; ++r)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) be[r] += __shfl_xor_sync(0xffffffffu, be[r], o);
-    __syncwarp();
-
-    // ------------------------------------------------------------------ phase 2: block rows
-    const int grp = lane >> 2, r = lane & 3;
-    const bool rowActive = r < BS;
-    const bool rowMasked = (r < DIM) ? maskV : maskP;
-    double bsub = 0.0;
-    double* Arow = a.Aval + (size_t)nb0 * BS * BS;
-
-    auto finishBlock = [&](int jb, double (&out)[BS], bool writer) {
-        // row masks + identity (PSPG.inl:68, 81, 108-128), then Dirichlet column elimination (PSPG.inl:216-228)
-        if (rowMasked) {
-#pragma unroll
-            for (int c = 0; c < BS; ++c) out[c] = (jb == si && c == r) ? 1.0 : 0.0;
-        } else if (dirS[jb]) {
-            const double* gd = a.dirVal4 + (size_t)nbrS[jb] * 4;
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) {
-                if (!(jb == si && c == r)) {
-                    bsub += out[c] * gd[c];
-                    out[c] = 0.0;
-                }
-            }
-        }
-        if (writer && rowActive) {
-            double* dst = Arow + (size_t)jb * BS * BS + r * BS;
-            if constexpr (BS == 4) {
-                *reinterpret_cast<double2*>(dst) = make_double2(out[0], out[1]);
-                *reinterpret_cast<double2*>(dst + 2) = make_double2(out[2], out[3]);
-            } else {
-#pragma unroll
-                for (int c = 0; c < BS; ++c) dst[c] = out[c];
-            }
+    auto loadHdr = [&](int i, NodeHdr& h) {
+        h.eb = __ldg(a.n2ePtr + i);
+        h.ne = __ldg(a.n2ePtr + i + 1) - h.eb;
+        h.nb0 = __ldg(a.nbrPtr + i);
+        h.nb = __ldg(a.nbrPtr + i + 1) - h.nb0;
+        h.si = __ldg(a.diagSlot + i);
+        h.fl = __ldg(a.flags + i);
+        h.dir0 = __ldg(a.rowDir + (size_t)i * a.dirWords);
+    };
+    auto loadLane = [&](const NodeHdr& h, LaneData& d) {
+        d.nbrNode = 0, d.packed = 0, d.mask = 0;
+        if (lane < h.ne) d.packed = __ldg(a.n2eSlots + h.eb + lane);
+        if (lane < h.nb) d.nbrNode = __ldg(a.nbr + h.nb0 + lane);
+        if (!diagLane && offIdx < h.nb - 1) {
+            const int jb = offIdx + (offIdx >= h.si ? 1 : 0);
+            d.mask = __ldg(a.blkMask + (size_t)(h.nb0 + jb) * CH);
         }
     };
+    auto stageNode = [&](int slot, int node) {
+        const double* xp = a.X4 + (size_t)node * 4;
+        const double* vq = a.VP4 + (size_t)node * 4;
+        const double2 x01 = ld2(xp), x23 = ld2(xp + 2), v01 = ld2(vq), v23 = ld2(vq + 2);
+        NodeRec& R = nrec[slot];
+        *reinterpret_cast<double2*>(&R.x[0]) = x01;
+        *reinterpret_cast<double2*>(&R.x[2]) = x23;
+        *reinterpret_cast<double2*>(&R.v[0]) = v01;
+        *reinterpret_cast<double2*>(&R.v[2]) = v23;
+    };
 
-    // off-diagonal blocks: 8 blocks per round, ascending element order inside each
-    for (int m0 = 0; m0 < nb - 1; m0 += 8) {
-        const int m = m0 + grp;
-        const bool act = m < nb - 1;
-        const int jb = act ? (m + (m >= si ? 1 : 0)) : 0;
-        double out[BS];
+    // phase-1 body for one (node, incident element) pair; returns the element's contribution to the RHS rows of node i
+    auto elementPhase = [&](int k, unsigned packed, int si, double (&be)[BS]) {
+        const int li = findByte(packed, si);
+        // previous velocities: only their element sum and the value at node i are needed
+        double sv[DIM], vpi[DIM], usum = 0;
 #pragma unroll
-        for (int c = 0; c < BS; ++c) out[c] = 0.0;
-        if (act && rowActive && !rowMasked) {
-            for (int ch = 0; ch < CH; ++ch) {
-                unsigned mk = emask[jb * CH + ch];
-                while (mk) {
-                    const int k = ch * 32 + __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    const unsigned sl = eslots[k];
-                    accumRow<DIM>(es[k], findByte<DIM>(sl, si), findByte<DIM>(sl, jb), r, out);
+        for (int c = 0; c < DIM; ++c) sv[c] = 0.0, vpi[c] = 0.0;
+        double px[NPE][DIM];
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) {
+            const NodeRec& R = nrec[(packed >> (8 * m)) & 0xffu];
+            const double* vq = R.v;
+            const double* xp = R.x;
+            const double2 v01 = ld2(vq), v23 = ld2(vq + 2), x01 = ld2(xp);
+            sv[0] += v01.x, sv[1] += v01.y;
+            vpi[0] = (li == m) ? v01.x : vpi[0];
+            vpi[1] = (li == m) ? v01.y : vpi[1];
+            px[m][0] = x01.x, px[m][1] = x01.y;
+            if constexpr (DIM == 3) {
+                sv[2] += v23.x;
+                vpi[2] = (li == m) ? v23.x : vpi[2];
+                px[m][2] = xp[2];
+            }
+            usum += v23.y;  // |v_cur| of the node
+        }
+        // J, detJ, inverse (Element.cpp:15-135)
+        double J[DIM][DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d)
+#pragma unroll
+            for (int m = 0; m < DIM; ++m) J[d][m] = px[m + 1][d] - px[0][d];
+        double det, inv[DIM][DIM];
+        if constexpr (DIM == 2) {
+            det = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+            const double rd = 1.0 / det;
+            inv[0][0] = J[1][1] * rd;
+            inv[0][1] = -J[0][1] * rd;
+            inv[1][0] = -J[1][0] * rd;
+            inv[1][1] = J[0][0] * rd;
+        } else {
+            det = J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
+                  J[2][0] * J[1][1] * J[0][2] - J[2][1] * J[1][2] * J[0][0] - J[2][2] * J[1][0] * J[0][1];
+            const double rd = 1.0 / det;
+            inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * rd;
+            inv[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) * rd;
+            inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rd;
+            inv[1][0] = (J[2][0] * J[1][2] - J[1][0] * J[2][2]) * rd;
+            inv[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) * rd;
+            inv[1][2] = (J[1][0] * J[0][2] - J[0][0] * J[1][2]) * rd;
+            inv[2][0] = (J[1][0] * J[2][1] - J[2][0] * J[1][1]) * rd;
+            inv[2][1] = (J[2][0] * J[0][1] - J[0][0] * J[2][1]) * rd;
+            inv[2][2] = (J[0][0] * J[1][1] - J[1][0] * J[0][1]) * rd;
+        }
+        double g[NPE][DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            double s = -inv[0][d];
+#pragma unroll
+            for (int m = 1; m < DIM; ++m) s -= inv[m][d];
+            g[0][d] = s;
+#pragma unroll
+            for (int m = 0; m < DIM; ++m) g[m + 1][d] = inv[m][d];
+        }
+        // tau (PSPG.inl:238-259): h = sqrt(ref detJ / pi) also in 3-D (reference hazard 7, reproduced)
+        const double V = det * REF;
+        const double h2 = REF * det / 3.14159265358979323846;
+        const double U = usum / NPE;
+        const double t1 = 2.0 * invdt, t3 = 4.0 * a.mu / (h2 * a.rho);
+        const double tau = 1.0 / sqrt(t1 * t1 + 4.0 * U * U / h2 + 9.0 * t3 * t3);
+        const double cmass = KC.kmass * V, cdiv = KC.kdiv * V, cpc = KC.kpc * (tau * V);
+        ElemS<DIM>& E = es[k];
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) {
+            *reinterpret_cast<double2*>(&E.g[m][0]) = make_double2(g[m][0], g[m][1]);
+            if constexpr (DIM == 3) *reinterpret_cast<double2*>(&E.g[m][2]) = make_double2(g[m][2], 0.0);
+        }
+        *reinterpret_cast<double2*>(&E.V) = make_double2(V, tau * V);
+        *reinterpret_cast<uint2*>(&E.slots) = make_uint2(packed, (unsigned)li);
+        // RHS rows of node i: be = [F + (M/dt) vPrev ; tau H + (tau/dt) C vPrev]   (PSPG.inl:53)
+        double gb = 0, gs = 0;
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+            double gci = g[0][c];
+#pragma unroll
+            for (int m = 1; m < NPE; ++m) gci = (li == m) ? g[m][c] : gci;
+            gb += gci * a.body[c];
+            gs += gci * sv[c];
+            be[c] += a.rho * cdiv * a.body[c] + cmass * (vpi[c] + sv[c]);
+        }
+        be[DIM] += tau * V * gb + cpc * gs;
+    };
+
+    // ---- software pipeline prologue: header, lane data and connectivity of the first node ---------------------------
+    int i = gw;
+    if (i >= a.nNodes) return;
+    NodeHdr H, Hn;
+    LaneData L, Ln;
+    loadHdr(i, H);
+    loadLane(H, L);
+    Hn = H, Ln = L;
+
+    for (; i < a.nNodes; i += nw) {
+        const int inext = i + nw;
+        const bool haveNext = inext < a.nNodes;
+        if (haveNext) loadHdr(inext, Hn);  // level-1 loads of the next node fly during phase 1
+
+        const int eb = H.eb, ne = H.ne, nb0 = H.nb0, nb = H.nb, si = H.si;
+        const bool isBound = H.fl & PFEM_NODE_BOUND, isFree = H.fl & PFEM_NODE_FREE;
+        const bool maskV = isBound || isFree, maskP = isFree;
+        bool anyDir = H.dir0 != 0;
+        for (int w = 1; w < a.dirWords; ++w) anyDir |= a.rowDir[(size_t)i * a.dirWords + w] != 0;
+
+        // -------------------------------------------------------------- phase 1: element geometry + RHS rows of node i
+        double be[BS];
+#pragma unroll
+        for (int r = 0; r < BS; ++r) be[r] = 0.0;
+        // stage the nodal records of all neighbours once (instead of once per incident element)
+        if (lane < nb) stageNode(lane, L.nbrNode);
+        for (int s2 = lane + 32; s2 < nb; s2 += 32) stageNode(s2, a.nbr[nb0 + s2]);
+        __syncwarp();
+        if (lane < ne) elementPhase(lane, L.packed, si, be);
+        for (int k = lane + 32; k < ne; k += 32)  // nodes with more than 32 incident elements (rare)
+            elementPhase(k, a.n2eSlots[eb + k], si, be);
+        if (haveNext) loadLane(Hn, Ln);  // level-2 loads of the next node fly during phase 2
+        // transposing butterfly: BS row sums over 32 lanes; lane l ends with the total of row 2*(l>>4) + ((l>>3)&1)
+        {
+            double t2[2], t1;
+            const bool u16 = lane & 16, u8 = lane & 8;
+            const double be3 = (BS == 4) ? be[BS - 1] : 0.0;
+            t2[0] = (u16 ? be[2] : be[0]) + __shfl_xor_sync(0xffffffffu, u16 ? be[0] : be[2], 16);
+            t2[1] = (u16 ? be3 : be[1]) + __shfl_xor_sync(0xffffffffu, u16 ? be[1] : be3, 16);
+            t1 = (u8 ? t2[1] : t2[0]) + __shfl_xor_sync(0xffffffffu, u8 ? t2[0] : t2[1], 8);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 4);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
+            t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
+            be[0] = t1;
+        }
+        __syncwarp();
+
+        // -------------------------------------------------------------- phase 2: one lane = one (dim+1)^2 block
+        // lanes 0..15 : off-diagonal blocks, 16 per round, elements of the edge (i,j) in ascending order (blkMask)
+        // lanes 16..31: the diagonal block, incident elements dealt round-robin, then a transposing butterfly reduction
+        double bsub[BS];
+#pragma unroll
+        for (int r = 0; r < BS; ++r) bsub[r] = 0.0;
+        double* Arow = a.Aval + (size_t)nb0 * BS * BS;
+
+        for (int m0 = 0; m0 == 0 || m0 < nb - 1; m0 += 28) {
+            const int m = m0 + offIdx;
+            const bool offAct = !diagLane && m < nb - 1;
+            const bool dgAct = diagLane && m0 == 0;
+            const int jb = offAct ? (m + (m >= si ? 1 : 0)) : si;
+            double acc[16];
+#pragma unroll
+            for (int t = 0; t < 16; ++t) acc[t] = 0.0;
+            if (offAct || dgAct) {
+                for (int ch = 0; ch < CH; ++ch) {
+                    unsigned mk;
+                    if (offAct)
+                        mk = (m0 == 0 && ch == 0) ? L.mask : a.blkMask[(size_t)(nb0 + jb) * CH + ch];
+                    else {
+                        const int rem = ne - ch * 32;
+                        const unsigned valid = rem >= 32 ? 0xffffffffu : (rem > 0 ? (1u << rem) - 1u : 0u);
+                        mk = (0x11111111u << dq) & valid;
+                    }
+                    while (mk) {
+                        const int k = ch * 32 + __ffs(mk) - 1;
+                        mk &= mk - 1;
+                        const ElemS<DIM>& E = es[k];
+                        const int li = E.li;
+                        const int lj = offAct ? findByte(E.slots, jb) : li;
+                        accumBlock<DIM>(E, KC, li, lj, acc);
+                    }
+                }
+            }
+            if (m0 == 0) {
+                // diagonal: 4 partial blocks on lanes 16..19 -> two transposing butterfly steps -> lane 16+r holds row r
+                double v8[8], v4[4];
+                {
+                    const bool up = lane & 2;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const double mine = up ? acc[8 + t] : acc[t], send = up ? acc[t] : acc[8 + t];
+                        v8[t] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
+                    }
+                }
+                {
+                    const bool up = lane & 1;
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const double mine = up ? v8[4 + t] : v8[t], send = up ? v8[t] : v8[4 + t];
+                        v4[t] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
+                    }
+                }
+                if (diagLane && dq < BS) {
+                    const int r = dq;
+                    const bool rowMasked = (r < DIM) ? maskV : maskP;
+                    const bool selfDir = (si < 32) ? ((H.dir0 >> si) & 1u)
+                                                   : ((a.rowDir[(size_t)i * a.dirWords + (si >> 5)] >> (si & 31)) & 1u);
+#pragma unroll
+                    for (int cc = 0; cc < BS; ++cc) {
+                        if (rowMasked) v4[cc] = (r == cc) ? 1.0 : 0.0;
+                    }
+                    if (!rowMasked && selfDir) {
+                        double sub = 0.0;
+#pragma unroll
+                        for (int cc = 0; cc < DIM; ++cc)
+                            if (cc != r) {
+                                sub += v4[cc] * a.dirVal4[(size_t)i * 4 + cc];
+                                v4[cc] = 0.0;
+                            }
+#pragma unroll
+                        for (int rr = 0; rr < BS; ++rr) bsub[rr] += (rr == r) ? sub : 0.0;
+                    }
+                    double* dst = Arow + (size_t)si * BS * BS + r * BS;
+                    double dg = v4[0];
+#pragma unroll
+                    for (int cc = 0; cc < BS; ++cc) {
+                        dst[cc] = v4[cc];
+                        dg = (cc == r) ? v4[cc] : dg;
+                    }
+                    a.dinv[(size_t)i * BS + r] = (dg != 0.0) ? 1.0 / dg : 1.0;
+                }
+            }
+            if (offAct) {
+                // row masks (PSPG.inl:68, 81): masked rows hold no off-diagonal entries
+#pragma unroll
+                for (int r = 0; r < BS; ++r) {
+                    const bool rowMasked = (r < DIM) ? maskV : maskP;
+                    if (rowMasked) {
+#pragma unroll
+                        for (int cc = 0; cc < BS; ++cc) acc[r * 4 + cc] = 0.0;
+                    }
+                }
+                const bool colDir = anyDir && ((jb < 32) ? ((H.dir0 >> jb) & 1u)
+                                                         : ((a.rowDir[(size_t)i * a.dirWords + (jb >> 5)] >> (jb & 31)) & 1u));
+                if (colDir) {  // Dirichlet column elimination (PSPG.inl:216-228)
+                    const double* gd = a.dirVal4 + (size_t)a.nbr[nb0 + jb] * 4;
+#pragma unroll
+                    for (int cc = 0; cc < DIM; ++cc) {
+                        const double gv = gd[cc];
+#pragma unroll
+                        for (int r = 0; r < BS; ++r) {
+                            bsub[r] += acc[r * 4 + cc] * gv;
+                            acc[r * 4 + cc] = 0.0;
+                        }
+                    }
+                }
+                double* dst = Arow + (size_t)jb * BS * BS;
+                if constexpr (BS == 4) {
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        __stcs(reinterpret_cast<double2*>(dst + 2 * t), make_double2(acc[2 * t], acc[2 * t + 1]));
+                } else {
+#pragma unroll
+                    for (int r = 0; r < BS; ++r)
+#pragma unroll
+                        for (int cc = 0; cc < BS; ++cc) dst[r * BS + cc] = acc[r * 4 + cc];
                 }
             }
         }
-        if (act) finishBlock(jb, out, true);
-    }
-    // diagonal block: every incident element contributes; split them over the 8 lane groups, then reduce
-    {
-        double out[BS];
+        // -------------------------------------------------------------- RHS (PSPG.inl:140-144 then :190-232)
+        if (anyDir) {
 #pragma unroll
-        for (int c = 0; c < BS; ++c) out[c] = 0.0;
-        if (rowActive && !rowMasked) {
-            for (int k = grp; k < ne; k += 8) {
-                const int li = findByte<DIM>(eslots[k], si);
-                accumRow<DIM>(es[k], li, li, r, out);
+            for (int r = 0; r < BS; ++r)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) bsub[r] += __shfl_xor_sync(0xffffffffu, bsub[r], o);
+        }
+        {
+            const int r = 2 * (lane >> 4) + ((lane >> 3) & 1);
+            if ((lane & 7) == 0 && r < BS) {
+                double bv = be[0], bs = bsub[0];
+#pragma unroll
+                for (int c = 1; c < BS; ++c) bs = (c == r) ? bsub[c] : bs;
+                bv -= bs;
+                if (isFree) {
+                    if (r == DIM) bv = 0.0;
+                    else if (!isBound) bv = a.VP4[(size_t)i * 4 + r] + a.dt * a.body[r];
+                }
+                if (isBound && a.dirMask[i] && r < DIM) bv = a.dirVal4[(size_t)i * 4 + r];
+                a.b[(size_t)i * BS + r] = bv;
             }
         }
-#pragma unroll
-        for (int c = 0; c < BS; ++c) {
-            out[c] += __shfl_xor_sync(0xffffffffu, out[c], 4);
-            out[c] += __shfl_xor_sync(0xffffffffu, out[c], 8);
-            out[c] += __shfl_xor_sync(0xffffffffu, out[c], 16);
-        }
-        if (grp == 0) {
-            finishBlock(si, out, true);
-            if (rowActive) {
-                double d = out[0];
-#pragma unroll
-                for (int c = 1; c < BS; ++c) d = (c == r) ? out[c] : d;
-                a.dinv[(size_t)i * BS + r] = (d != 0.0) ? 1.0 / d : 1.0;
-            }
-        }
-    }
-    bsub += __shfl_xor_sync(0xffffffffu, bsub, 4);
-    bsub += __shfl_xor_sync(0xffffffffu, bsub, 8);
-    bsub += __shfl_xor_sync(0xffffffffu, bsub, 16);
-
-    // ------------------------------------------------------------------ RHS (PSPG.inl:140-144 then :190-232)
-    if (grp == 0 && rowActive) {
-        double bv = be[0];
-#pragma unroll
-        for (int c = 1; c < BS; ++c) bv = (c == r) ? be[c] : bv;
-        bv -= bsub;
-        if (isFree) {
-            if (r == DIM) bv = 0.0;
-            else if (!isBound) bv = a.VP4[(size_t)i * 4 + r] + a.dt * a.body[r];
-        }
-        if (isBound && a.dirMask[i] && r < DIM) bv = a.dirVal4[(size_t)i * 4 + r];
-        a.b[(size_t)i * BS + r] = bv;
+        __syncwarp();  // all lanes are done with es[] before the next node's phase 1 overwrites it
+        H = Hn, L = Ln;
     }
 }
 
@@ -423,9 +545,7 @@ __global__ void k_b_out(const double* __restrict__ b, double* __restrict__ dst, 
 }
 
 template <int DIM> size_t asmSmemPerWarp(int ecap, int nbcap) {
-    const int CH = ecap >> 5;
-    const size_t perWarp = (size_t)ecap * (sizeof(ElemS<DIM>) + 4) + (size_t)nbcap * 4 * (1 + CH) + (size_t)nbcap;
-    return (perWarp + 15) & ~(size_t)15;
+    return (size_t)ecap * sizeof(ElemS<DIM>) + (size_t)nbcap * sizeof(NodeRec);
 }
 
 }  // namespace
@@ -438,36 +558,52 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
     c->Aval.reserve((size_t)c->nBlocks * BS * BS);
     c->bvec.reserve((size_t)c->nNodes * BS);
     c->dinv.reserve((size_t)c->nNodes * BS);
+    const int dirWords = (std::max(c->maxNb, 1) + 31) / 32;
     {
         PhaseScope ph(c, "Prepare matrix assembly");
         k_vnorm<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->V4.p, c->VP4.p, c->nNodes, c->dim);
         LAUNCH_CHECK(c);
+        if (c->rowDirDirty) {
+            c->rowDir.reserve((size_t)c->nNodes * dirWords + 4);
+            k_row_dir<<<divUp(c->nNodes, 128), 128, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->flags.p, c->dirMask.p,
+                                                                  dirWords, c->rowDir.p);
+            LAUNCH_CHECK(c);
+            c->rowDirDirty = false;
+        }
     }
     AsmArgs a;
     a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.nbrPtr = c->nbrPtr.p, a.nbr = c->nbr.p;
+    a.n2eSlots = c->n2eSlots.p, a.blkMask = c->blkMask.p, a.rowDir = c->rowDir.p;
     a.diagSlot = c->diagSlot.p, a.flags = c->flags.p, a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p;
     a.X4 = c->X4.p, a.VP4 = c->VP4.p, a.Aval = c->Aval.p, a.b = c->bvec.p, a.dinv = c->dinv.p;
     a.nNodes = c->nNodes;
-    a.ecap = ((std::max(c->maxE, 1) + 31) / 32) * 32;
-    a.nbcap = ((std::max(c->maxNb, 1) + 7) / 8) * 8;
+    a.CH = c->maskWords;
+    a.dirWords = dirWords;
+    a.ecap = std::max(c->maxE, 1);
+    a.nbcap = std::max(c->maxNb, 1);
     a.rho = p.rho, a.mu = p.mu, a.dt = p.dt;
     for (int d = 0; d < 3; ++d) a.body[d] = p.bodyForce[d];
     {
         PhaseScope ph(c, "Assemble system");  // = Compute triplets + Push back + Assemble matrix/vector + Apply BC
-        int wpb = 8;
-        size_t per = c->dim == 2 ? asmSmemPerWarp<2>(a.ecap, a.nbcap) : asmSmemPerWarp<3>(a.ecap, a.nbcap);
-        while (wpb > 1 && per * wpb > 200 * 1024) wpb >>= 1;
+        static const int cfg = getenv("PFEM_ASM_CFG") ? atoi(getenv("PFEM_ASM_CFG")) : 0;
+        const int wpb = (cfg >= 2) ? 4 : 8;
+        const int blocksPerSm = (cfg == 0) ? 2 : (cfg == 1 ? 3 : (cfg == 2 ? 6 : 8));
+        const size_t per = c->dim == 2 ? asmSmemPerWarp<2>(a.ecap, a.nbcap) : asmSmemPerWarp<3>(a.ecap, a.nbcap);
         const size_t smem = per * wpb;
         PFEM_REQUIRE(smem <= 227 * 1024, PFEM_ERR_INVALID, "pspg_assemble: node valence too large for shared memory");
-        if (c->dim == 2) {
-            if (smem > 48 * 1024)
-                CUDA_CHECK(cudaFuncSetAttribute(k_pspg_assemble<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_pspg_assemble<2><<<divUp(c->nNodes, wpb), wpb * 32, smem, c->stream>>>(a);
-        } else {
-            if (smem > 48 * 1024)
-                CUDA_CHECK(cudaFuncSetAttribute(k_pspg_assemble<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_pspg_assemble<3><<<divUp(c->nNodes, wpb), wpb * 32, smem, c->stream>>>(a);
-        }
+        const int grid = std::max(1, std::min(divUp(c->nNodes, wpb), c->smCount * blocksPerSm));
+#define PFEM_LAUNCH_ASM(DIM_, T_, M_)                                                                                     \
+    do {                                                                                                                  \
+        if (smem > 48 * 1024)                                                                                             \
+            CUDA_CHECK(cudaFuncSetAttribute(k_pspg_assemble<DIM_, T_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                                            (int)smem));                                                                  \
+        k_pspg_assemble<DIM_, T_, M_><<<grid, T_, smem, c->stream>>>(a);                                                  \
+    } while (0)
+        if (c->dim == 2) PFEM_LAUNCH_ASM(2, 256, 2);
+        else if (cfg == 1) PFEM_LAUNCH_ASM(3, 256, 3);
+        else if (cfg == 2) PFEM_LAUNCH_ASM(3, 128, 6);
+        else if (cfg == 3) PFEM_LAUNCH_ASM(3, 128, 8);
+        else PFEM_LAUNCH_ASM(3, 256, 2);
         LAUNCH_CHECK(c);
     }
     c->haveSystem = true;

@@ -118,16 +118,23 @@ __global__ void k_fix_free_flag(uint8_t* __restrict__ flags, const int* __restri
     flags[n] = f;
 }
 
-// One warp per node.  FILL=false: count distinct neighbours; FILL=true: write them sorted + diagSlot.
+// One warp per node.  FILL=false: count distinct neighbours.  FILL=true: write them sorted + diagSlot, and for every
+// incident element k the slots of its nodes in that sorted list (n2eSlots, one byte per local node) and for every
+// block (i, slot) the bit mask of the incident elements that contain that neighbour (blkMask, CH words per block).
+// Both are what the assembly kernel needs to gather without searching.
 template <bool FILL>
 __global__ void k_neighbours(const int* __restrict__ conn, int npe, const int* __restrict__ n2ePtr,
-                             const int* __restrict__ n2e, int nNodes, int candCap, int* __restrict__ nbrCntOrPtr,
-                             int* __restrict__ nbr, int* __restrict__ diagSlot, int* __restrict__ maxNb) {
+                             const int* __restrict__ n2e, int nNodes, int candCap, int nbCap, int CH,
+                             int* __restrict__ nbrCntOrPtr, int* __restrict__ nbr, int* __restrict__ diagSlot,
+                             int* __restrict__ maxNb, unsigned* __restrict__ n2eSlots, unsigned* __restrict__ blkMask) {
     extern __shared__ int smem[];
     const int warpInBlock = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int node = blockIdx.x * (blockDim.x >> 5) + warpInBlock;
     if (node >= nNodes) return;
-    unsigned* cand = reinterpret_cast<unsigned*>(smem) + (size_t)warpInBlock * candCap;
+    const int perWarp = candCap + (FILL ? nbCap * (1 + CH) : 0);
+    unsigned* cand = reinterpret_cast<unsigned*>(smem) + (size_t)warpInBlock * perWarp;
+    unsigned* sorted = cand + candCap;     // FILL only
+    unsigned* masks = sorted + nbCap;      // FILL only, nbCap*CH
     const int eb = n2ePtr[node], ne = n2ePtr[node + 1] - eb;
     const int C = ne * npe;
     if (ne == 0) {  // isolated node: the block row is its own diagonal block
@@ -135,6 +142,7 @@ __global__ void k_neighbours(const int* __restrict__ conn, int npe, const int* _
             if (FILL) {
                 nbr[nbrCntOrPtr[node]] = node;
                 diagSlot[node] = 0;
+                for (int ch = 0; ch < CH; ++ch) blkMask[(size_t)nbrCntOrPtr[node] * CH + ch] = 0u;
             } else
                 nbrCntOrPtr[node] = 1;
         }
@@ -166,6 +174,7 @@ __global__ void k_neighbours(const int* __restrict__ conn, int npe, const int* _
                 rank += (!(u & 0x80000000u) && u < v) ? 1 : 0;
             }
             nbr[nbrCntOrPtr[node] + rank] = (int)v;
+            sorted[rank] = v;
             if ((int)v == node) diagSlot[node] = rank;
         }
     }
@@ -175,7 +184,28 @@ __global__ void k_neighbours(const int* __restrict__ conn, int npe, const int* _
             nbrCntOrPtr[node] = nDistinct;
             atomicMax(maxNb, nDistinct);
         }
+        return;
     }
+    const int nb0 = nbrCntOrPtr[node], nb = nbrCntOrPtr[node + 1] - nb0;
+    for (int t = lane; t < nb * CH; t += 32) masks[t] = 0u;
+    __syncwarp();
+    // slot of every candidate = lower_bound in the sorted distinct list; one byte per (element, local node)
+    unsigned char* slotBytes = reinterpret_cast<unsigned char*>(n2eSlots + eb);
+    for (int c = lane; c < C; c += 32) {
+        const unsigned v = cand[c] & 0x7fffffffu;
+        int lo = 0, hi = nb - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (sorted[mid] < v) lo = mid + 1;
+            else hi = mid;
+        }
+        const int k = c / npe, m = c % npe;
+        slotBytes[k * 4 + m] = (unsigned char)lo;
+        if (npe == 3 && m == 0) slotBytes[k * 4 + 3] = 0xff;  // unused 4th byte never matches a slot
+        atomicOr(&masks[lo * CH + (k >> 5)], 1u << (k & 31));
+    }
+    __syncwarp();
+    for (int t = lane; t < nb * CH; t += 32) blkMask[(size_t)nb0 * CH + t] = masks[t];
 }
 
 }  // namespace
@@ -220,6 +250,7 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     c->haveTopology = false;
     c->haveSystem = c->haveSolution = c->haveQprev = c->haveSnapshot = c->havePositions = c->haveDirichlet = false;
     c->nnzReference = -1;
+    c->rowDirDirty = true;
 
     c->conn.reserve(nConn + 4);
     c->flags.reserve(nNodes);
@@ -258,24 +289,31 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     // neighbour lists
     const int warps = 8;
     const int candCap = max(c->maxE, 1) * npe;
-    const size_t smem = (size_t)warps * candCap * sizeof(int);
-    if (smem > 48 * 1024) {
+    const int CH = (max(c->maxE, 1) + 31) / 32;
+    c->maskWords = CH;
+    size_t smem = (size_t)warps * candCap * sizeof(int);
+    if (smem > 48 * 1024)
         CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
     CUDA_CHECK(cudaMemsetAsync(c->nbrPtr.p, 0, (nNodes + 2) * sizeof(int), c->stream));
     k_neighbours<false><<<divUp(nNodes, warps), warps * 32, smem, c->stream>>>(
-        c->conn.p, npe, c->n2ePtr.p, c->n2e.p, nNodes, candCap, c->nbrPtr.p, nullptr, nullptr, misc + 2);
+        c->conn.p, npe, c->n2ePtr.p, c->n2e.p, nNodes, candCap, 0, CH, c->nbrPtr.p, nullptr, nullptr, misc + 2, nullptr, nullptr);
     LAUNCH_CHECK(c);
     exclusiveScanInt(c, c->nbrPtr.p, nNodes + 1, misc + 3);
     CUDA_CHECK(cudaMemcpyAsync(h, misc, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     c->maxNb = h[2];
     c->nBlocks = h[3];
-    PFEM_REQUIRE(c->maxNb <= 255, PFEM_ERR_INVALID, "set_topology: node with more than 255 neighbours");
+    PFEM_REQUIRE(c->maxNb <= 254, PFEM_ERR_INVALID, "set_topology: node with more than 254 neighbours");
     c->nbr.reserve(c->nBlocks + 4);
+    c->n2eSlots.reserve(nConn + 4);
+    c->blkMask.reserve((size_t)c->nBlocks * CH + 4);
+    const int nbCap = c->maxNb;
+    smem = (size_t)warps * (candCap + nbCap * (1 + CH)) * sizeof(int);
+    if (smem > 48 * 1024)
+        CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_neighbours<true><<<divUp(nNodes, warps), warps * 32, smem, c->stream>>>(
-        c->conn.p, npe, c->n2ePtr.p, c->n2e.p, nNodes, candCap, c->nbrPtr.p, c->nbr.p, c->diagSlot.p, nullptr);
+        c->conn.p, npe, c->n2ePtr.p, c->n2e.p, nNodes, candCap, nbCap, CH, c->nbrPtr.p, c->nbr.p, c->diagSlot.p, nullptr,
+        c->n2eSlots.p, c->blkMask.p);
     LAUNCH_CHECK(c);
 
     // nodal fields sized for the new mesh
