@@ -144,9 +144,17 @@ int pfem_wc_next_dt(pfem_ctx* ctx, const pfem_wc_params* p, double securityCoeff
 
 /* ---- multi-GPU (one context per rank/GPU; elements sharded by RCB) ---- */
 /* ncclUniqueId: the 128 opaque bytes of ncclGetUniqueId obtained by rank 0 (pfem_comm_unique_id) and broadcast by the
- * launcher.  After this call pfem_set_topology expects the GLOBAL mesh on every rank and keeps only this rank's part. */
+ * launcher.  Each rank then passes its LOCAL mesh (owned + ghost nodes, one ghost-element layer) to pfem_set_topology
+ * followed by pfem_set_partition. */
 int pfem_comm_unique_id(void* id128);
 int pfem_comm_init(pfem_ctx* ctx, int nRanks, int rank, const void* id128);
+/* Halo plan of the LOCAL mesh previously given to pfem_set_topology on this rank (built on the host per remesh, e.g. by
+ * pfem_b200/partition.py): nodes [0, nOwned) are owned (their rows are computed here), nodes [nOwned, nNodes) are ghosts
+ * grouped by owner.  Peer p receives the owned nodes sendIdx[sendOffsets[p] .. sendOffsets[p+1]) and fills the ghost
+ * range [recvStart[p], recvStart[p]+recvCount[p]).  Local elements must be sorted by global element index so that the
+ * gather kernels sum in the single-GPU order (sharded results are then bit-identical to one GPU). */
+int pfem_set_partition(pfem_ctx* ctx, int64_t nOwned, int nPeers, const int32_t* peerRank, const int64_t* sendOffsets,
+                       const int32_t* sendIdx, const int64_t* recvStart, const int64_t* recvCount);
 
 /* ---- instrumentation (phase names = the reference's m_accumalatedTimes keys, PSPG.inl:19-369) ---- */
 int pfem_profile_enable(pfem_ctx* ctx, int on);

@@ -69,6 +69,7 @@ SYMBOLS = {
     "pfem_wc_next_dt": (C.c_int, [_VP, C.POINTER(WcParams), C.c_double, C.c_double, _DP]),
     "pfem_comm_unique_id": (C.c_int, [_VP]),
     "pfem_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "pfem_set_partition": (C.c_int, [_VP, C.c_int64, C.c_int, _I32P, _I64P, _I32P, _I64P, _I64P]),
     "pfem_profile_enable": (C.c_int, [_VP, C.c_int]),
     "pfem_profile_reset": (C.c_int, [_VP]),
     "pfem_profile_get": (C.c_int, [_VP, C.c_char_p, _DP, _I64P]),
@@ -237,10 +238,10 @@ class PfemContext:
         return r.value
 
     def pspg_picard_iter(self, params, q_prev, rel_tol=1e-12, max_iter=10000, fetch=True):
-        qp = _f64(q_prev, self.n_dof)
+        qp = None if q_prev is None else _f64(q_prev, self.n_dof)  # None: keep the qPrev already on the device
         q = np.empty(self.n_dof) if fetch else None
         res, it = C.c_double(0), C.c_int(0)
-        rc = self._chk(self._L.pfem_pspg_picard_iter(self._h, C.byref(params), _dptr(qp), rel_tol, max_iter,
+        rc = self._chk(self._L.pfem_pspg_picard_iter(self._h, C.byref(params), None if qp is None else _dptr(qp), rel_tol, max_iter,
                                                      _dptr(q) if fetch else None, C.byref(res), C.byref(it)),
                        allow=(PFEM_NOT_CONVERGED, PFEM_NAN))
         return dict(status=rc, q=q, res=res.value, iters=it.value)
@@ -300,6 +301,20 @@ class PfemContext:
     def comm_init(self, n_ranks, rank, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         self._chk(self._L.pfem_comm_init(self._h, n_ranks, rank, C.cast(buf, _VP)))
+
+    def set_partition(self, part):
+        """Halo plan of a partition.LocalPart whose local mesh was given to set_topology/set_mesh."""
+        n_peers = len(part.peers)
+        peer = np.asarray(part.peers, dtype=np.int32)
+        counts = np.array([len(s) for s in part.send_idx], dtype=np.int64)
+        send_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        send_idx = (np.concatenate(part.send_idx).astype(np.int32) if n_peers else np.zeros(0, dtype=np.int32))
+        send_idx = np.ascontiguousarray(send_idx)
+        recv_start = np.asarray(part.recv_start, dtype=np.int64)
+        recv_count = np.asarray(part.recv_count, dtype=np.int64)
+        self._chk(self._L.pfem_set_partition(self._h, part.n_owned, n_peers, peer.ctypes.data_as(_I32P),
+                                             send_off.ctypes.data_as(_I64P), send_idx.ctypes.data_as(_I32P),
+                                             recv_start.ctypes.data_as(_I64P), recv_count.ctypes.data_as(_I64P)))
 
     # -- instrumentation --------------------------------------------------------------
     def profile_enable(self, on=True):

@@ -197,7 +197,7 @@ int pfem_pspg_solve(pfem_ctx* c, double relTol, int maxIter, double* q, int* ite
 int pfem_pspg_residual(pfem_ctx* c, const double* q, double* res) {
     API_BEGIN(c)
     PFEM_REQUIRE(res, PFEM_ERR_INVALID, "pspg_residual: null");
-    const double* xi = c->kx.p;
+    double* xi = c->kx.p;
     if (q) {
         c->ks.reserve((size_t)c->nNodes * (c->dim + 1));
         krylovLoadVector(c, q, c->ks.p);
@@ -283,6 +283,13 @@ int pfem_comm_unique_id(void* id128) {
 int pfem_comm_init(pfem_ctx* c, int nRanks, int rank, const void* id128) {
     API_BEGIN(c)
     commInit(c, nRanks, rank, id128);
+    API_END(c)
+}
+
+int pfem_set_partition(pfem_ctx* c, int64_t nOwned, int nPeers, const int32_t* peerRank, const int64_t* sendOffsets,
+                       const int32_t* sendIdx, const int64_t* recvStart, const int64_t* recvCount) {
+    API_BEGIN(c)
+    commSetPartition(c, nOwned, nPeers, peerRank, sendOffsets, sendIdx, recvStart, recvCount);
     API_END(c)
 }
 

@@ -70,7 +70,7 @@ struct PendingPhase {
 struct NcclApi;  // dlopen'ed NCCL entry points (comm.cu)
 
 // slots of the Krylov scalar bank kept on the device (krylov.cu)
-enum { SC_RHO0 = 0, SC_RHO1, SC_ALPHA, SC_OMEGA, SC_DONE, SC_ITERS, SC_RES2, SC_BNORM2, SC_TOL2, SC_BAD, SC_COUNT = 16 };
+enum { SC_RHO0 = 0, SC_RHO1, SC_ALPHA, SC_OMEGA, SC_DONE, SC_ITERS, SC_RES2, SC_BNORM2, SC_TOL2, SC_BAD, SC_TMP0, SC_TMP1, SC_COUNT = 16 };
 // slots of the per-block partial-sum bank
 enum { PS_RHO = 0, PS_SIGMA, PS_TS, PS_TT, PS_RR, PS_AUX, PS_COUNT = 8 };
 
@@ -84,6 +84,7 @@ struct pfem_ctx {
 
     // ---- mesh (device) ----
     int nNodes = 0, nElems = 0;
+    int nRows = 0;             // rows computed by this rank: nNodes, or the owned-node count of a partitioned mesh
     int64_t nBlocks = 0;       // node-block non-zeros
     int64_t nnzReference = -1; // lazily counted
     int maxE = 0, maxNb = 0;
@@ -136,12 +137,13 @@ struct pfem_ctx {
     // ---- multi-GPU ----
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
-    DevBuf<int> ifaceIdx;      // local ids of interface nodes, ordered by global id
-    DevBuf<double> ifaceBuf;
-    int nIface = 0;
-    std::vector<int> l2gNodes; // local -> global node id (host)
-    int nNodesGlobal = 0, nElemsGlobal = 0;
-    DevBuf<int> ownedMask;
+    struct Peer {
+        int rank, sendOff, sendCount, recvStart, recvCount;
+    };
+    std::vector<Peer> peers;   // halo plan of the local mesh (pfem_set_partition)
+    DevBuf<int> sendIdx;       // local ids of owned nodes to send, concatenated per peer
+    DevBuf<double> sendBuf;
+    int nSendTotal = 0;
 
     // ---- profiling ----
     bool profiling = false;
@@ -150,11 +152,11 @@ struct pfem_ctx {
     std::vector<cudaEvent_t> eventPool;
 
     pfem_ctx() {
-        for (auto* b : {&conn, &n2ePtr, &n2e, &nbrPtr, &nbr, &diagSlot, &scratchI, &scanScratch, &cscPtr, &cscRow, &ifaceIdx, &ownedMask})
+        for (auto* b : {&conn, &n2ePtr, &n2e, &nbrPtr, &nbr, &diagSlot, &scratchI, &scanScratch, &cscPtr, &cscRow, &sendIdx})
             b->accounting = &deviceBytes;
         for (auto* b : {&flags, &dirMask, &stageB}) b->accounting = &deviceBytes;
         for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &kx, &kr, &kr0,
-                        &kp, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &ifaceBuf})
+                        &kp, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &sendBuf})
             b->accounting = &deviceBytes;
         stage64.accounting = &deviceBytes;
         n2eSlots.accounting = &deviceBytes;
@@ -223,8 +225,8 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* iters, double* rel
 void krylovFetchSolution(pfem_ctx* c, double* q);
 void krylovLoadVector(pfem_ctx* c, const double* qHost, double* dst);  // ABI layout -> internal dof order
 void krylovStoreVector(pfem_ctx* c, const double* src, double* qHost);
-double krylovResidualNorm(pfem_ctx* c, const double* xInternal);
-void krylovMatvec(pfem_ctx* c, const double* xInternal, double* yInternal);
+double krylovResidualNorm(pfem_ctx* c, double* xInternal);
+void krylovMatvec(pfem_ctx* c, double* xInternal, double* yInternal);
 // wc.cu
 void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt);
 int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dt);
@@ -232,5 +234,8 @@ int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double 
 void commUniqueId(void* id128);
 void commInit(pfem_ctx* c, int nRanks, int rank, const void* id128);
 void commDestroy(pfem_ctx* c);
-void commAllReduceSumInterface(pfem_ctx* c, double* buf, int count);
+void commSetPartition(pfem_ctx* c, int64_t nOwned, int nPeers, const int32_t* peerRank, const int64_t* sendOffsets,
+                      const int32_t* sendIdx, const int64_t* recvStart, const int64_t* recvCount);
+void commHalo(pfem_ctx* c, double* arr0, double* arr1, int width);  // owners -> ghosts, up to two nodal arrays
+void commAllReduceSum(pfem_ctx* c, double* buf, int count);
 void commAllReduceMin(pfem_ctx* c, double* devScalar);

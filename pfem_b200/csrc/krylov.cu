@@ -274,6 +274,16 @@ __global__ void k_bank_to_scal(double* scal, int dst, const double* partial, int
     const double s = bankSum(partial, stride, slot, nPart);
     if (threadIdx.x == 0) scal[dst] = s;
 }
+// multi-rank: collapse bank entries to their first element so that one all-reduce makes them global sums and the
+// consumer kernels (which re-reduce the bank) simply read a bank of length 1
+__global__ void k_bank_collapse(double* partial, int stride, int slot0, int slot1, int nPart) {
+    const double s0 = bankSum(partial, stride, slot0, nPart);
+    const double s1 = slot1 >= 0 ? bankSum(partial, stride, slot1, nPart) : 0.0;
+    if (threadIdx.x == 0) {
+        partial[(size_t)slot0 * stride] = s0;
+        if (slot1 >= 0) partial[(size_t)slot1 * stride] = s1;
+    }
+}
 __global__ void k_zero(double* p, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = 0.0;
 }
@@ -292,37 +302,52 @@ __global__ void k_from_internal(const double* __restrict__ src, double* __restri
 }
 
 struct KrylovDims {
-    int n, BS, vecGrid, spmvGrid, stride;
+    int n;      // owned dofs: the rows this rank computes and the extent of every dot product
+    int nAll;   // owned + ghost dofs: extent of the vectors SpMV gathers from
+    int BS, vecGrid, spmvGrid, stride;
+    bool multi;
 };
 KrylovDims setup(pfem_ctx* c) {
     KrylovDims k;
     k.BS = c->dim + 1;
-    k.n = c->nNodes * k.BS;
+    k.n = c->nRows * k.BS;
+    k.nAll = c->nNodes * k.BS;
+    k.multi = c->nRanks > 1;
     k.vecGrid = std::max(1, std::min(c->smCount * 4, divUp(k.n, RB_THREADS)));
-    k.spmvGrid = std::max(1, std::min(c->smCount * 8, divUp(c->nNodes, 8)));
+    k.spmvGrid = std::max(1, std::min(c->smCount * 8, divUp(c->nRows, 8)));
     k.stride = std::max(k.vecGrid, k.spmvGrid);
     c->reduceBlocks = k.stride;
-    for (auto* b : {&c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt, &c->kph, &c->ksh}) b->reserve(k.n);
+    for (auto* b : {&c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt, &c->kph, &c->ksh}) b->reserve(k.nAll + 8);
     c->partial.reserve((size_t)PS_COUNT * k.stride);
     c->scal.reserve(SC_COUNT);
     if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
     return k;
 }
-void spmv(pfem_ctx* c, const KrylovDims& k, const double* x, double* y, const double* w1, int slotYW, int slotYY,
-          bool honourDone) {
+// y_owned = A_owned,local x_local ; on a partitioned mesh the ghost entries of x are refreshed from their owners first
+void spmv(pfem_ctx* c, const KrylovDims& k, double* x, double* y, const double* w1, int slotYW, int slotYY, bool honourDone) {
     const double* sc = honourDone ? c->scal.p : nullptr;
+    if (k.multi) commHalo(c, x, nullptr, k.BS);
     PhaseScope ph(c, "SpMV");
     static const int minb = getenv("PFEM_SPMV_MINB") ? atoi(getenv("PFEM_SPMV_MINB")) : 3;
     if (k.BS == 4 && minb == 4)
-        k_spmv<4, 4><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
+        k_spmv<4, 4><<<k.spmvGrid, 256, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
                                                         k.stride, slotYW, slotYY, sc);
     else if (k.BS == 4)
-        k_spmv<4, 3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
+        k_spmv<4, 3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
                                                         k.stride, slotYW, slotYY, sc);
     else
-        k_spmv<3, 3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nNodes, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
+        k_spmv<3, 3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
                                                         k.stride, slotYW, slotYY, sc);
     LAUNCH_CHECK(c);
+}
+// multi-rank: make the bank entries slot0 (and slot1) global sums; returns the bank length consumers must use
+int globalise(pfem_ctx* c, const KrylovDims& k, int slot0, int slot1, int nPart) {
+    if (!k.multi) return nPart;
+    k_bank_collapse<<<1, RB_THREADS, 0, c->stream>>>(c->partial.p, k.stride, slot0, slot1, nPart);
+    LAUNCH_CHECK(c);
+    commAllReduceSum(c, c->partial.p + (size_t)slot0 * k.stride, 1);
+    if (slot1 >= 0) commAllReduceSum(c, c->partial.p + (size_t)slot1 * k.stride, 1);
+    return 1;
 }
 
 }  // namespace
@@ -346,24 +371,26 @@ void krylovStoreVector(pfem_ctx* c, const double* src, double* qHost) {
 }
 void krylovFetchSolution(pfem_ctx* c, double* q) {
     PFEM_REQUIRE(c->haveSolution, PFEM_ERR_STATE, "no solution on the device");
+    if (c->nRanks > 1) commHalo(c, c->kx.p, nullptr, c->dim + 1);  // ghost entries follow their owners
     krylovStoreVector(c, c->kx.p, q);
 }
-void krylovMatvec(pfem_ctx* c, const double* xInternal, double* yInternal) {
+void krylovMatvec(pfem_ctx* c, double* xInternal, double* yInternal) {
     PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "matvec: no assembled system");
     KrylovDims k = setup(c);
     spmv(c, k, xInternal, yInternal, nullptr, -1, -1, false);
 }
-// ||A x - b||_2  (Res::Ax_f, PSPG.inl:368)
-double krylovResidualNorm(pfem_ctx* c, const double* xInternal) {
+// ||A x - b||_2  (Res::Ax_f, PSPG.inl:368); global over all ranks
+double krylovResidualNorm(pfem_ctx* c, double* xInternal) {
     PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "residual: no assembled system");
     PhaseScope ph(c, "Compute Picard Algo residual");
     KrylovDims k = setup(c);
     spmv(c, k, xInternal, c->kt.p, nullptr, -1, -1, false);
     k_resid<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, c->kt.p, c->partial.p, k.stride);
     LAUNCH_CHECK(c);
-    k_bank_to_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, SC_COUNT - 1, c->partial.p, k.stride, PS_AUX + 1, k.vecGrid);
+    const int np = globalise(c, k, PS_AUX + 1, -1, k.vecGrid);
+    k_bank_to_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, SC_TMP0, c->partial.p, k.stride, PS_AUX + 1, np);
     LAUNCH_CHECK(c);
-    CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p + SC_COUNT - 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p + SC_TMP0, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return sqrt(c->hScal[0]);
 }
@@ -377,7 +404,7 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
     int totalIters = 0, status = PFEM_OK;
     double relRes = 0;
     if (!(warmStart && c->haveSolution)) {
-        k_zero<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(c->kx.p, k.n);
+        k_zero<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(c->kx.p, k.nAll);
         LAUNCH_CHECK(c);
         warmStart = false;
     }
@@ -390,7 +417,9 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
         k_init<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, zeroGuess ? nullptr : c->kt.p, c->kr.p, c->kr0.p,
                                                         c->kp.p, c->kv.p, c->partial.p, k.stride);
         LAUNCH_CHECK(c);
-        k_init_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, c->partial.p, k.stride, k.vecGrid, relTol, 1, restart == 0);
+        int npVec = globalise(c, k, PS_RHO, PS_RR, k.vecGrid);
+        globalise(c, k, PS_AUX, -1, k.vecGrid);
+        k_init_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, c->partial.p, k.stride, npVec, relTol, 1, restart == 0);
         LAUNCH_CHECK(c);
         bool done = false;
         int it = 0;  // iterations inside this restart cycle
@@ -399,24 +428,26 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
             for (int b = 0; b < batch; ++b, ++it) {
                 const int parity = it & 1;
                 k_update_p<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kp.p, c->kv.p, c->dinv.p, c->kph.p,
-                                                                    c->scal.p, c->partial.p, k.stride, k.vecGrid, parity, it);
+                                                                    c->scal.p, c->partial.p, k.stride, npVec, parity, it);
                 LAUNCH_CHECK(c);
                 spmv(c, k, c->kph.p, c->kv.p, c->kr0.p, PS_SIGMA, -1, true);
+                const int npS = globalise(c, k, PS_SIGMA, -1, k.spmvGrid);
                 k_update_s<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kv.p, c->dinv.p, c->ks.p, c->ksh.p,
-                                                                    c->scal.p, c->partial.p, k.stride, k.spmvGrid, parity);
+                                                                    c->scal.p, c->partial.p, k.stride, npS, parity);
                 LAUNCH_CHECK(c);
                 spmv(c, k, c->ksh.p, c->kt.p, c->ks.p, PS_TS, PS_TT, true);
+                const int npT = globalise(c, k, PS_TS, PS_TT, k.spmvGrid);
                 k_update_xr<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kx.p, c->kr.p, c->kr0.p, c->ks.p, c->kt.p,
-                                                                     c->kph.p, c->ksh.p, c->scal.p, c->partial.p, k.stride,
-                                                                     k.spmvGrid);
+                                                                     c->kph.p, c->ksh.p, c->scal.p, c->partial.p, k.stride, npT);
                 LAUNCH_CHECK(c);
+                npVec = globalise(c, k, PS_RHO, PS_RR, k.vecGrid);
             }
-            // poll: one more K_A-style test is folded into the next batch; here read what the last K_A saw + latest rr
-            k_bank_to_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, SC_COUNT - 2, c->partial.p, k.stride, PS_RR, k.vecGrid);
+            // poll: what the last K_A saw + the latest ||r||^2
+            k_bank_to_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, SC_TMP1, c->partial.p, k.stride, PS_RR, npVec);
             LAUNCH_CHECK(c);
             CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            const double rrLatest = c->hScal[SC_COUNT - 2];
+            const double rrLatest = c->hScal[SC_TMP1];
             if (c->hScal[SC_DONE] != 0.0) {
                 done = true;
                 it = (int)c->hScal[SC_ITERS];  // iterations completed when the test fired
@@ -428,7 +459,7 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
         // true residual
         const double bnorm = sqrt(c->hScal[SC_BNORM2]);
         if (bnorm == 0.0) {  // b = 0 -> x = 0
-            k_zero<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(c->kx.p, k.n);
+            k_zero<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(c->kx.p, k.nAll);
             LAUNCH_CHECK(c);
             relRes = 0;
             break;

@@ -576,7 +576,7 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
     a.n2eSlots = c->n2eSlots.p, a.blkMask = c->blkMask.p, a.rowDir = c->rowDir.p;
     a.diagSlot = c->diagSlot.p, a.flags = c->flags.p, a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p;
     a.X4 = c->X4.p, a.VP4 = c->VP4.p, a.Aval = c->Aval.p, a.b = c->bvec.p, a.dinv = c->dinv.p;
-    a.nNodes = c->nNodes;
+    a.nNodes = c->nRows;  // rows assembled by this rank (owned nodes of a partitioned mesh)
     a.CH = c->maskWords;
     a.dirWords = dirWords;
     a.ecap = std::max(c->maxE, 1);
@@ -591,7 +591,7 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
         const size_t per = c->dim == 2 ? asmSmemPerWarp<2>(a.ecap, a.nbcap) : asmSmemPerWarp<3>(a.ecap, a.nbcap);
         const size_t smem = per * wpb;
         PFEM_REQUIRE(smem <= 227 * 1024, PFEM_ERR_INVALID, "pspg_assemble: node valence too large for shared memory");
-        const int grid = std::max(1, std::min(divUp(c->nNodes, wpb), c->smCount * blocksPerSm));
+        const int grid = std::max(1, std::min(divUp(c->nRows, wpb), c->smCount * blocksPerSm));
 #define PFEM_LAUNCH_ASM(DIM_, T_, M_)                                                                                     \
     do {                                                                                                                  \
         if (smem > 48 * 1024)                                                                                             \
@@ -613,6 +613,7 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
 void pspgPicardUpdate(pfem_ctx* c, double dt) {
     PFEM_REQUIRE(c->haveSolution && c->haveSnapshot, PFEM_ERR_STATE, "picard: need a solution and a position snapshot");
     PhaseScope ph(c, "Update solutions");
+    if (c->nRanks > 1) commHalo(c, c->kx.p, nullptr, c->dim + 1);  // ghost nodes move with their owners' velocities
     k_picard_update<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->kx.p, c->nNodes, c->dim, dt, c->flags.p, c->Xsave4.p,
                                                                   c->X4.p, c->V4.p);
     LAUNCH_CHECK(c);
@@ -620,6 +621,7 @@ void pspgPicardUpdate(pfem_ctx* c, double dt) {
 
 void pspgExportCsc(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b) {
     PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "export_csc: no assembled system");
+    PFEM_REQUIRE(c->nRows == c->nNodes, PFEM_ERR_STATE, "export_csc: not available on a partitioned mesh");
     PFEM_REQUIRE(nnz, PFEM_ERR_INVALID, "export_csc: nnz is null");
     const int BS = c->dim + 1;
     const int64_t nDof = (int64_t)c->nNodes * BS;

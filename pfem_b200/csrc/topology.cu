@@ -247,6 +247,9 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     const int64_t nConn = (int64_t)nElems * npe;
     c->nNodes = nNodes;
     c->nElems = nElems;
+    c->nRows = nNodes;  // until pfem_set_partition narrows it to the owned nodes
+    c->peers.clear();
+    c->nSendTotal = 0;
     c->haveTopology = false;
     c->haveSystem = c->haveSolution = c->haveQprev = c->haveSnapshot = c->havePositions = c->haveDirichlet = false;
     c->nnzReference = -1;

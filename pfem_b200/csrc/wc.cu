@@ -372,7 +372,7 @@ __global__ void k_min_final(const double* __restrict__ partial, int n, double* _
 WcArgs makeArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     WcArgs a;
     a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.flags = c->flags.p;
-    a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p, a.nNodes = c->nNodes;
+    a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p, a.nNodes = c->nRows;  // rows = owned nodes
     a.dt = dt, a.mu = p.mu, a.K0 = p.K0, a.K0p = p.K0p, a.rhoStar = p.rhoStar;
     for (int d = 0; d < 3; ++d) a.body[d] = p.bodyForce[d];
     a.meduri = p.meduri;
@@ -381,18 +381,15 @@ WcArgs makeArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
 
 }  // namespace
 
-void commExchangeNodal(pfem_ctx* c, int what);  // comm.cu (multi-GPU only)
-
 void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, "wc_step: topology/positions missing");
     PFEM_REQUIRE(dt > 0 && p.K0 > 0 && p.K0p != 0, PFEM_ERR_INVALID, "wc_step: dt, K0 must be positive and K0p non-zero");
-    PFEM_REQUIRE(c->nRanks == 1, PFEM_ERR_STATE, "wc_step: use the sharded entry point on a multi-rank context");
     const size_t n4 = (size_t)c->nNodes * 4;
     c->X4b.reserve(n4);
     c->V4b.reserve(n4);
     const WcArgs a = makeArgs(c, p, dt);
     constexpr int LPN = 8;
-    const int grid = divUp((int64_t)c->nNodes * LPN, 256);
+    const int grid = divUp((int64_t)c->nRows * LPN, 256);
     {
         PhaseScope ph(c, "Update solutions");
         k_wc_kick_move<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->nNodes, c->dim, dt, c->flags.p, c->X4.p, c->V4.p, c->A4.p);
@@ -405,6 +402,7 @@ void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
         else
             k_wc_cont<3, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         LAUNCH_CHECK(c);
+        if (c->nRanks > 1) commHalo(c, c->X4b.p, c->V4b.p, 4);  // (x, p_new) and (v_half, rho_new) of interface nodes
     }
     {
         PhaseScope ph(c, "Solving momentum eq");
@@ -413,6 +411,7 @@ void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
         else
             k_wc_mom<3, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
         LAUNCH_CHECK(c);
+        if (c->nRanks > 1) commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
     }
     std::swap(c->X4.p, c->X4b.p);  // X4b holds (x, p_new): make it current
     std::swap(c->X4.cap, c->X4b.cap);
