@@ -119,7 +119,8 @@ struct pfem_ctx {
     // ---- PSPG system ----
     DevBuf<double> Aval;       // nBlocks * BS*BS, block row-major
     DevBuf<double> bvec;       // nNodes*BS, internal dof = node*BS + d
-    DevBuf<double> dinv;       // 1/diag
+    DevBuf<double> dinv;       // symmetric Jacobi scale 1/sqrt|a_ii|
+    DevBuf<double> Wblk;       // node-block Jacobi: A_ii^-1 S_i^-1 per node
     DevBuf<double> kx, kr, kr0, kp, kv, ks, kt, kph, ksh;  // Krylov vectors (internal dof order)
     DevBuf<double> partial;    // PS_COUNT * reduceBlocks
     DevBuf<double> scal;       // SC_COUNT
@@ -155,7 +156,7 @@ struct pfem_ctx {
         for (auto* b : {&conn, &n2ePtr, &n2e, &nbrPtr, &nbr, &diagSlot, &scratchI, &scanScratch, &cscPtr, &cscRow, &sendIdx})
             b->accounting = &deviceBytes;
         for (auto* b : {&flags, &dirMask, &stageB}) b->accounting = &deviceBytes;
-        for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &kx, &kr, &kr0,
+        for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &Wblk, &kx, &kr, &kr0,
                         &kp, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &sendBuf})
             b->accounting = &deviceBytes;
         stage64.accounting = &deviceBytes;

@@ -13,6 +13,7 @@
 //     flag freezes the state once ||r|| <= tol ||b||.
 // Vectors use the internal dof order node*BS + d.
 #include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 
@@ -95,7 +96,8 @@ template <int BS, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
                                               const double* __restrict__ Aval, const double* __restrict__ x,
                                               double* __restrict__ y, const double* __restrict__ w1, double* partial,
-                                              int stride, int slotYW, int slotYY, const double* __restrict__ scal) {
+                                              int stride, int slotYW, int slotYY, const double* __restrict__ scal,
+                                              const double* __restrict__ rowScale) {
     const int lane = threadIdx.x & 31, grp = lane >> 2, r = lane & 3;
     const int warpsPerBlock = blockDim.x >> 5;
     const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nw = gridDim.x * warpsPerBlock;
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
             if (grp == 0 && r < BS) {
                 const size_t o = (size_t)i * BS + r;
+                if (rowScale) acc *= rowScale[o];  // symmetric Jacobi scaling: y = S A x
                 y[o] = acc;
                 if (slotYW >= 0) accYW += acc * w1[o];
                 if (slotYY >= 0) accYY += acc * acc;
@@ -160,11 +163,12 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
 // ---- vector kernels ---------------------------------------------------------------------------------------------------
 // r = b - y (y = A x0 precomputed, or nullptr for x0 = 0) ; r0 = r ; p = v = 0 ; partials rho=(r0,r)=||r||^2, ||b||^2
 __global__ void __launch_bounds__(RB_THREADS) k_init(int n, const double* __restrict__ b, const double* __restrict__ y,
-                                                     double* __restrict__ r, double* __restrict__ r0, double* __restrict__ p,
+                                                     const double* __restrict__ sc, double* __restrict__ r,
+                                                     double* __restrict__ r0, double* __restrict__ p,
                                                      double* __restrict__ v, double* partial, int stride) {
     double rr = 0, bb = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double bi = b[i];
+        const double bi = sc[i] * b[i];  // S b
         const double ri = y ? bi - y[i] : bi;
         r[i] = ri;
         r0[i] = ri;
@@ -194,9 +198,11 @@ __global__ void k_init_scal(double* scal, const double* partial, int stride, int
 }
 
 // K_A: beta = (rho/rho_old)(alpha/omega) ; p = r + beta (p - omega v) ; phat = dinv .* p      [+ convergence test]
+template <int BS>
 __global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __restrict__ r, double* __restrict__ p,
                                                          const double* __restrict__ v, const double* __restrict__ dinv,
-                                                         double* __restrict__ ph, double* scal, const double* partial,
+                                                         const double* __restrict__ W, double* __restrict__ ph,
+                                                         double* scal, const double* partial,
                                                          int stride, int nPart, int parity, int iterIndex) {
     const double rho = bankSum(partial, stride, PS_RHO, nPart);
     const double rr = bankSum(partial, stride, PS_RR, nPart);
@@ -213,6 +219,26 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __
     }
     if (wasDone || conv || bad) return;
     const double beta = (rho / rhoOld) * (alpha / omega);
+    if (W) {  // node-block Jacobi: phat_i = W_i p_i with W_i = A_ii^-1 S_i^-1 (one thread per node)
+        for (int nd = blockIdx.x * blockDim.x + threadIdx.x; nd < n / BS; nd += gridDim.x * blockDim.x) {
+            double pn[4];
+#pragma unroll
+            for (int c = 0; c < BS; ++c) {
+                const int i = nd * BS + c;
+                pn[c] = r[i] + beta * (p[i] - omega * v[i]);
+                p[i] = pn[c];
+            }
+            const double* Wn = W + (size_t)nd * BS * BS;
+#pragma unroll
+            for (int rr2 = 0; rr2 < BS; ++rr2) {
+                double a = 0;
+#pragma unroll
+                for (int c = 0; c < BS; ++c) a += Wn[rr2 * BS + c] * pn[c];
+                ph[nd * BS + rr2] = a;
+            }
+        }
+        return;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double pi = r[i] + beta * (p[i] - omega * v[i]);
         p[i] = pi;
@@ -220,19 +246,100 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __
     }
 }
 // K_C: alpha = rho / (r0,v) ; s = r - alpha v ; shat = dinv .* s
+template <int BS>
 __global__ void __launch_bounds__(RB_THREADS) k_update_s(int n, const double* __restrict__ r, const double* __restrict__ v,
-                                                         const double* __restrict__ dinv, double* __restrict__ s,
+                                                         const double* __restrict__ dinv, const double* __restrict__ W,
+                                                         double* __restrict__ s,
                                                          double* __restrict__ sh, double* scal, const double* partial,
                                                          int stride, int nPart, int parity) {
     if (scal[SC_DONE] != 0.0) return;
     const double sigma = bankSum(partial, stride, PS_SIGMA, nPart);
     const double alpha = scal[SC_RHO0 + parity] / sigma;
+    if (!(fabs(alpha) < 1e300)) {  // breakdown (r0, v) = 0: leave x untouched, let the host restart from it
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_DONE] = 1.0, scal[SC_BAD] = 1.0;
+        return;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_ALPHA] = alpha;
+    if (W) {
+        for (int nd = blockIdx.x * blockDim.x + threadIdx.x; nd < n / BS; nd += gridDim.x * blockDim.x) {
+            double sn[4];
+#pragma unroll
+            for (int c = 0; c < BS; ++c) {
+                const int i = nd * BS + c;
+                sn[c] = r[i] - alpha * v[i];
+                s[i] = sn[c];
+            }
+            const double* Wn = W + (size_t)nd * BS * BS;
+#pragma unroll
+            for (int rr2 = 0; rr2 < BS; ++rr2) {
+                double a = 0;
+#pragma unroll
+                for (int c = 0; c < BS; ++c) a += Wn[rr2 * BS + c] * sn[c];
+                sh[nd * BS + rr2] = a;
+            }
+        }
+        return;
+    }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double si = r[i] - alpha * v[i];
         s[i] = si;
         sh[i] = dinv[i] * si;
     }
+}
+// W_i = A_ii^-1 diag(1/s_i): inverse of the (dim+1)^2 diagonal node block (Gauss-Jordan, partial pivoting) folded with the
+// symmetric scale, so that phat = S M^-1 p for the node-block Jacobi preconditioner M = blockdiag(S A S)
+template <int BS>
+__global__ void k_block_inverse(int nRows, const int* __restrict__ nbrPtr, const int* __restrict__ diagSlot,
+                                const double* __restrict__ Aval, const double* __restrict__ sc, double* __restrict__ W) {
+    const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nd >= nRows) return;
+    const double* Ad = Aval + ((size_t)nbrPtr[nd] + diagSlot[nd]) * BS * BS;
+    double M[BS][2 * BS];
+#pragma unroll
+    for (int r = 0; r < BS; ++r)
+#pragma unroll
+        for (int c = 0; c < BS; ++c) {
+            M[r][c] = Ad[r * BS + c];
+            M[r][BS + c] = (r == c) ? 1.0 : 0.0;
+        }
+    bool singular = false;
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        int piv = k;
+        double best = fabs(M[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < BS; ++r)
+            if (fabs(M[r][k]) > best) best = fabs(M[r][k]), piv = r;
+        if (!(best > 0.0)) singular = true;
+#pragma unroll
+        for (int r = k + 1; r < BS; ++r)
+            if (r == piv) {
+#pragma unroll
+                for (int c = 0; c < 2 * BS; ++c) {
+                    const double t = M[k][c];
+                    M[k][c] = M[r][c];
+                    M[r][c] = t;
+                }
+            }
+        const double inv = 1.0 / M[k][k];
+#pragma unroll
+        for (int c = 0; c < 2 * BS; ++c) M[k][c] *= inv;
+#pragma unroll
+        for (int r = 0; r < BS; ++r)
+            if (r != k) {
+                const double f = M[r][k];
+#pragma unroll
+                for (int c = 0; c < 2 * BS; ++c) M[r][c] -= f * M[k][c];
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < BS; ++r)
+#pragma unroll
+        for (int c = 0; c < BS; ++c) {
+            const double s = sc[(size_t)nd * BS + c];
+            // singular block (cannot happen for a valid mesh): fall back to the point Jacobi scale
+            W[(size_t)nd * BS * BS + r * BS + c] = singular ? ((r == c) ? s : 0.0) : M[r][BS + c] / s;
+        }
 }
 // K_E: omega = (t,s)/(t,t) ; x += alpha phat + omega shat ; r = s - omega t ; partials (r0,r), (r,r)
 __global__ void __launch_bounds__(RB_THREADS) k_update_xr(int n, double* __restrict__ x, double* __restrict__ r,
@@ -245,6 +352,10 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_xr(int n, double* __restr
     const double tt = bankSum(partial, stride, PS_TT, nPart);
     const double omega = tt > 0.0 ? ts / tt : 0.0;
     const double alpha = scal[SC_ALPHA];
+    if (!(fabs(omega) < 1e300) || !(tt == tt)) {  // NaN/inf in t: freeze before x is polluted
+        if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_DONE] = 1.0, scal[SC_BAD] = 1.0;
+        return;
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_OMEGA] = omega;
     double rho = 0, rr = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -260,10 +371,10 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_xr(int n, double* __restr
 }
 // d = b - y ; partial ||d||^2 (true residual)
 __global__ void __launch_bounds__(RB_THREADS) k_resid(int n, const double* __restrict__ b, const double* __restrict__ y,
-                                                      double* partial, int stride) {
+                                                      const double* __restrict__ sc, double* partial, int stride) {
     double rr = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double d = y[i] - b[i];
+        const double d = y[i] - (sc ? sc[i] * b[i] : b[i]);
         rr += d * d;
     }
     double vv[1] = {rr};
@@ -324,20 +435,21 @@ KrylovDims setup(pfem_ctx* c) {
     return k;
 }
 // y_owned = A_owned,local x_local ; on a partitioned mesh the ghost entries of x are refreshed from their owners first
-void spmv(pfem_ctx* c, const KrylovDims& k, double* x, double* y, const double* w1, int slotYW, int slotYY, bool honourDone) {
+void spmv(pfem_ctx* c, const KrylovDims& k, double* x, double* y, const double* w1, int slotYW, int slotYY, bool honourDone,
+          const double* rowScale = nullptr) {
     const double* sc = honourDone ? c->scal.p : nullptr;
     if (k.multi) commHalo(c, x, nullptr, k.BS);
     PhaseScope ph(c, "SpMV");
     static const int minb = getenv("PFEM_SPMV_MINB") ? atoi(getenv("PFEM_SPMV_MINB")) : 3;
     if (k.BS == 4 && minb == 4)
         k_spmv<4, 4><<<k.spmvGrid, 256, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
-                                                        k.stride, slotYW, slotYY, sc);
+                                                        k.stride, slotYW, slotYY, sc, rowScale);
     else if (k.BS == 4)
         k_spmv<4, 3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
-                                                        k.stride, slotYW, slotYY, sc);
+                                                        k.stride, slotYW, slotYY, sc, rowScale);
     else
         k_spmv<3, 3><<<k.spmvGrid, 256, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
-                                                        k.stride, slotYW, slotYY, sc);
+                                                        k.stride, slotYW, slotYY, sc, rowScale);
     LAUNCH_CHECK(c);
 }
 // multi-rank: make the bank entries slot0 (and slot1) global sums; returns the bank length consumers must use
@@ -380,12 +492,12 @@ void krylovMatvec(pfem_ctx* c, double* xInternal, double* yInternal) {
     spmv(c, k, xInternal, yInternal, nullptr, -1, -1, false);
 }
 // ||A x - b||_2  (Res::Ax_f, PSPG.inl:368); global over all ranks
-double krylovResidualNorm(pfem_ctx* c, double* xInternal) {
+static double residualNorm(pfem_ctx* c, double* xInternal, const double* scale) {
     PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "residual: no assembled system");
     PhaseScope ph(c, "Compute Picard Algo residual");
     KrylovDims k = setup(c);
-    spmv(c, k, xInternal, c->kt.p, nullptr, -1, -1, false);
-    k_resid<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, c->kt.p, c->partial.p, k.stride);
+    spmv(c, k, xInternal, c->kt.p, nullptr, -1, -1, false, scale);
+    k_resid<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, c->kt.p, scale, c->partial.p, k.stride);
     LAUNCH_CHECK(c);
     const int np = globalise(c, k, PS_AUX + 1, -1, k.vecGrid);
     k_bank_to_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, SC_TMP0, c->partial.p, k.stride, PS_AUX + 1, np);
@@ -394,6 +506,7 @@ double krylovResidualNorm(pfem_ctx* c, double* xInternal) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return sqrt(c->hScal[0]);
 }
+double krylovResidualNorm(pfem_ctx* c, double* xInternal) { return residualNorm(c, xInternal, nullptr); }
 
 int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* relResOut, bool warmStart) {
     PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "solve: no assembled system (pfem_pspg_assemble)");
@@ -409,13 +522,27 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
         warmStart = false;
     }
     c->haveSolution = true;
-    const int maxRestarts = 4;
+    // preconditioner: node-block Jacobi (default) or point Jacobi (PFEM_PRECOND=point), both on the equilibrated system
+    static const bool pointJacobi = getenv("PFEM_PRECOND") && std::string(getenv("PFEM_PRECOND")) == "point";
+    const double* W = nullptr;
+    if (!pointJacobi) {
+        c->Wblk.reserve((size_t)c->nRows * k.BS * k.BS + 8);
+        if (k.BS == 4)
+            k_block_inverse<4><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->diagSlot.p, c->Aval.p,
+                                                                          c->dinv.p, c->Wblk.p);
+        else
+            k_block_inverse<3><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->diagSlot.p, c->Aval.p,
+                                                                          c->dinv.p, c->Wblk.p);
+        LAUNCH_CHECK(c);
+        W = c->Wblk.p;
+    }
+    const int maxRestarts = 12;
     for (int restart = 0; restart <= maxRestarts; ++restart) {
         // r = b - A x
         const bool zeroGuess = !warmStart && restart == 0;
-        if (!zeroGuess) spmv(c, k, c->kx.p, c->kt.p, nullptr, -1, -1, false);
-        k_init<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, zeroGuess ? nullptr : c->kt.p, c->kr.p, c->kr0.p,
-                                                        c->kp.p, c->kv.p, c->partial.p, k.stride);
+        if (!zeroGuess) spmv(c, k, c->kx.p, c->kt.p, nullptr, -1, -1, false, c->dinv.p);
+        k_init<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, zeroGuess ? nullptr : c->kt.p, c->dinv.p, c->kr.p,
+                                                        c->kr0.p, c->kp.p, c->kv.p, c->partial.p, k.stride);
         LAUNCH_CHECK(c);
         int npVec = globalise(c, k, PS_RHO, PS_RR, k.vecGrid);
         globalise(c, k, PS_AUX, -1, k.vecGrid);
@@ -427,15 +554,23 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
             const int batch = std::min(checkEvery, maxIter - totalIters - it);
             for (int b = 0; b < batch; ++b, ++it) {
                 const int parity = it & 1;
-                k_update_p<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kp.p, c->kv.p, c->dinv.p, c->kph.p,
-                                                                    c->scal.p, c->partial.p, k.stride, npVec, parity, it);
+                if (k.BS == 4)
+                    k_update_p<4><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kp.p, c->kv.p, c->dinv.p, W, c->kph.p,
+                                                                           c->scal.p, c->partial.p, k.stride, npVec, parity, it);
+                else
+                    k_update_p<3><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kp.p, c->kv.p, c->dinv.p, W, c->kph.p,
+                                                                           c->scal.p, c->partial.p, k.stride, npVec, parity, it);
                 LAUNCH_CHECK(c);
-                spmv(c, k, c->kph.p, c->kv.p, c->kr0.p, PS_SIGMA, -1, true);
+                spmv(c, k, c->kph.p, c->kv.p, c->kr0.p, PS_SIGMA, -1, true, c->dinv.p);
                 const int npS = globalise(c, k, PS_SIGMA, -1, k.spmvGrid);
-                k_update_s<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kv.p, c->dinv.p, c->ks.p, c->ksh.p,
-                                                                    c->scal.p, c->partial.p, k.stride, npS, parity);
+                if (k.BS == 4)
+                    k_update_s<4><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kv.p, c->dinv.p, W, c->ks.p, c->ksh.p,
+                                                                           c->scal.p, c->partial.p, k.stride, npS, parity);
+                else
+                    k_update_s<3><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kv.p, c->dinv.p, W, c->ks.p, c->ksh.p,
+                                                                           c->scal.p, c->partial.p, k.stride, npS, parity);
                 LAUNCH_CHECK(c);
-                spmv(c, k, c->ksh.p, c->kt.p, c->ks.p, PS_TS, PS_TT, true);
+                spmv(c, k, c->ksh.p, c->kt.p, c->ks.p, PS_TS, PS_TT, true, c->dinv.p);
                 const int npT = globalise(c, k, PS_TS, PS_TT, k.spmvGrid);
                 k_update_xr<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kx.p, c->kr.p, c->kr0.p, c->ks.p, c->kt.p,
                                                                      c->kph.p, c->ksh.p, c->scal.p, c->partial.p, k.stride, npT);
@@ -464,7 +599,7 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
             relRes = 0;
             break;
         }
-        const double trueRes = krylovResidualNorm(c, c->kx.p);
+        const double trueRes = residualNorm(c, c->kx.p, c->dinv.p);  // of the equilibrated system S A S, S b
         relRes = trueRes / bnorm;
         if (!(relRes == relRes)) {
             status = PFEM_NAN;

@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
                         dst[cc] = v4[cc];
                         dg = (cc == r) ? v4[cc] : dg;
                     }
-                    a.dinv[(size_t)i * BS + r] = (dg != 0.0) ? 1.0 / dg : 1.0;
+                    a.dinv[(size_t)i * BS + r] = (dg != 0.0) ? rsqrt(fabs(dg)) : 1.0;  // symmetric Jacobi scale 1/sqrt|a_ii|
                 }
             }
             if (offAct) {
