@@ -12,6 +12,8 @@
 //   k_wc_mom       : F = -K v + D^T p + F_b, lumped rho-mass -> a -> v = v_half + dt/2 a    (MomEquation.inl:201-226)
 // Device layout: X4=(x,y,z,p), V4=(u,v,w,rho), A4=(ax,ay,az,-); cont writes the ping-pong copies X4b/V4b so that the
 // gathers of other nodes never see half-updated p/rho.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace {
@@ -132,8 +134,8 @@ struct WcArgs {
 };
 
 // continuity, CDS_dpdt (ContEquation.inl:353-413, 334-350, 139-146, 319-331)
-template <int DIM, int LPN>
-__global__ void __launch_bounds__(256) k_wc_cont(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
+template <int DIM, int LPN, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_wc_cont(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
                                                  double* __restrict__ X4n, double* __restrict__ V4n) {
     constexpr int NPE = DIM + 1;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
@@ -184,8 +186,8 @@ __global__ void __launch_bounds__(256) k_wc_cont(const WcArgs a, const double* _
 }
 
 // momentum (MomEquation.inl:229-302, 305-374, 216-222)
-template <int DIM, int LPN>
-__global__ void __launch_bounds__(256) k_wc_mom(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
+template <int DIM, int LPN, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
                                                 double* __restrict__ V4out, double* __restrict__ A4out) {
     constexpr int NPE = DIM + 1;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
@@ -265,6 +267,252 @@ __global__ void __launch_bounds__(256) k_wc_mom(const WcArgs a, const double* __
             vn[c] = vp[c] + 0.5 * a.dt * acc[c];
         }
         st4(V4out + (size_t)i * 4, vn[0], vn[1], vn[2], vp[3]);
+        st4(A4out + (size_t)i * 4, acc[0], acc[1], acc[2], 0.0);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Staged variants: the LPN lanes of a node first copy the 64-byte records (x,y,z,p | u,v,w,rho) of the node's
+// neighbours into shared memory ONCE (instead of gathering them once per incident element, ~5x redundantly), then read
+// the element nodes by neighbour SLOT (n2eSlots) -- no n2e -> conn -> node dependent chain, ~3x fewer L1 wavefronts.
+struct alignas(16) WcRec {
+    double x[4];  // x, y, z, p
+    double v[4];  // u, v, w, rho
+    double pad_[2];
+};
+struct WcArgsS {
+    const int* n2ePtr;
+    const unsigned* n2eSlots;
+    const int* nbrPtr;
+    const int* nbr;
+    const int* diagSlot;
+    const uint8_t* flags;
+    const uint8_t* dirMask;
+    const double* dirVal4;
+    int nNodes, nbcap;
+    double dt, mu, K0, K0p, rhoStar, body[3];
+    int meduri;
+};
+template <int DIM>
+__device__ __forceinline__ void elemFromRecs(const WcRec* __restrict__ recs, unsigned packed, double (&xw)[DIM + 1],
+                                             double (&vel)[DIM + 1][DIM], double (&vw)[DIM + 1], ElemGeo<DIM>& G) {
+    constexpr int NPE = DIM + 1;
+    constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
+    double px[NPE][DIM];
+#pragma unroll
+    for (int m = 0; m < NPE; ++m) {
+        const WcRec& R = recs[(packed >> (8 * m)) & 0xffu];
+        const double2 x01 = ld2(R.x), x23 = ld2(R.x + 2), v01 = ld2(R.v), v23 = ld2(R.v + 2);
+        px[m][0] = x01.x, px[m][1] = x01.y;
+        vel[m][0] = v01.x, vel[m][1] = v01.y;
+        if constexpr (DIM == 3) {
+            px[m][2] = x23.x;
+            vel[m][2] = v23.x;
+        }
+        xw[m] = x23.y;
+        vw[m] = v23.y;
+    }
+    double J[DIM][DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+        for (int m = 0; m < DIM; ++m) J[d][m] = px[m + 1][d] - px[0][d];
+    double det, inv[DIM][DIM];
+    if constexpr (DIM == 2) {
+        det = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+        const double rd = 1.0 / det;
+        inv[0][0] = J[1][1] * rd;
+        inv[0][1] = -J[0][1] * rd;
+        inv[1][0] = -J[1][0] * rd;
+        inv[1][1] = J[0][0] * rd;
+    } else {
+        det = J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
+              J[2][0] * J[1][1] * J[0][2] - J[2][1] * J[1][2] * J[0][0] - J[2][2] * J[1][0] * J[0][1];
+        const double rd = 1.0 / det;
+        inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * rd;
+        inv[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) * rd;
+        inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rd;
+        inv[1][0] = (J[2][0] * J[1][2] - J[1][0] * J[2][2]) * rd;
+        inv[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) * rd;
+        inv[1][2] = (J[1][0] * J[0][2] - J[0][0] * J[1][2]) * rd;
+        inv[2][0] = (J[1][0] * J[2][1] - J[2][0] * J[1][1]) * rd;
+        inv[2][1] = (J[2][0] * J[0][1] - J[0][0] * J[2][1]) * rd;
+        inv[2][2] = (J[0][0] * J[1][1] - J[1][0] * J[0][1]) * rd;
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        double s = -inv[0][d];
+#pragma unroll
+        for (int m = 1; m < DIM; ++m) s -= inv[m][d];
+        G.g[d][0] = s;
+#pragma unroll
+        for (int m = 0; m < DIM; ++m) G.g[d][m + 1] = inv[m][d];
+    }
+    G.V = det * REF;
+}
+__device__ __forceinline__ int findSlotByte(unsigned packed, int v) {
+    const unsigned eq = __vcmpeq4(packed, (unsigned)v * 0x01010101u);
+    return (__ffs(eq) - 1) >> 3;
+}
+template <int LPN>
+__device__ __forceinline__ void stageRecords(const WcArgsS& a, int i, int sub, bool valid, const double* __restrict__ X4,
+                                             const double* __restrict__ V4, WcRec* recs) {
+    if (valid) {
+        const int nb0 = a.nbrPtr[i], nb = a.nbrPtr[i + 1] - nb0;
+        for (int s = sub; s < nb; s += LPN) {
+            const int nd = a.nbr[nb0 + s];
+            const double* xp = X4 + (size_t)nd * 4;
+            const double* vp = V4 + (size_t)nd * 4;
+            const double2 x01 = ld2(xp), x23 = ld2(xp + 2), v01 = ld2(vp), v23 = ld2(vp + 2);
+            WcRec& R = recs[s];
+            *reinterpret_cast<double2*>(R.x) = x01;
+            *reinterpret_cast<double2*>(R.x + 2) = x23;
+            *reinterpret_cast<double2*>(R.v) = v01;
+            *reinterpret_cast<double2*>(R.v + 2) = v23;
+        }
+    }
+    __syncwarp();
+}
+
+template <int DIM, int LPN, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_wc_cont_s(const WcArgsS a, const double* __restrict__ X4,
+                                                         const double* __restrict__ V4, double* __restrict__ X4n,
+                                                         double* __restrict__ V4n) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    extern __shared__ __align__(16) unsigned char smemWc[];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / LPN, sub = t % LPN;
+    const bool valid = i < a.nNodes;
+    WcRec* recs = reinterpret_cast<WcRec*>(smemWc) + (size_t)(threadIdx.x / LPN) * a.nbcap;
+    stageRecords<LPN>(a, i, sub, valid, X4, V4, recs);
+    double m = 0, F0 = 0;
+    int si = 0;
+    if (valid) {
+        si = a.diagSlot[i];
+        const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+        for (int k = sub; k < ne; k += LPN) {
+            const unsigned packed = a.n2eSlots[eb + k];
+            double P[NPE], vel[NPE][DIM], rho[NPE];
+            ElemGeo<DIM> G;
+            elemFromRecs<DIM>(recs, packed, P, vel, rho, G);
+            const int li = findSlotByte(packed, si);
+            double sumP = 0, divv = 0;
+#pragma unroll
+            for (int q = 0; q < NPE; ++q) {
+                sumP += P[q];
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) divv += G.g[c][q] * vel[q][c];
+            }
+            const double pi = pick<NPE>(P, li);
+            const double sI = a.K0 / NPE + a.K0p * PHI * (pi + sumP);
+            const double stab = a.meduri ? G.V * PHI * (pi + sumP) : (G.V / NPE) * pi;
+            F0 += -a.dt * G.V * sI * divv + stab;
+            m += G.V / NPE;
+        }
+    }
+    m = groupSum<LPN>(m);
+    F0 = groupSum<LPN>(F0);
+    if (valid && sub == 0) {
+        const bool isFree = a.flags[i] & PFEM_NODE_FREE;
+        double inv = 1.0 / m;
+        if (isFree) {
+            F0 = 0.0;
+            inv = 1.0;
+        }
+        const double p = inv * F0;
+        const double rho = pow((a.K0p / a.K0) * p + 1.0, 1.0 / a.K0p) * a.rhoStar;
+        const WcRec& R = recs[si];
+        st4(X4n + (size_t)i * 4, R.x[0], R.x[1], R.x[2], p);
+        st4(V4n + (size_t)i * 4, R.v[0], R.v[1], R.v[2], rho);
+    }
+}
+
+template <int DIM, int LPN, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_wc_mom_s(const WcArgsS a, const double* __restrict__ X4,
+                                                        const double* __restrict__ V4, double* __restrict__ V4out,
+                                                        double* __restrict__ A4out) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    extern __shared__ __align__(16) unsigned char smemWc[];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / LPN, sub = t % LPN;
+    const bool valid = i < a.nNodes;
+    WcRec* recs = reinterpret_cast<WcRec*>(smemWc) + (size_t)(threadIdx.x / LPN) * a.nbcap;
+    stageRecords<LPN>(a, i, sub, valid, X4, V4, recs);
+    double M = 0, F[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) F[c] = 0;
+    int si = 0;
+    if (valid) {
+        si = a.diagSlot[i];
+        const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+        for (int k = sub; k < ne; k += LPN) {
+            const unsigned packed = a.n2eSlots[eb + k];
+            double P[NPE], vel[NPE][DIM], rho[NPE];
+            ElemGeo<DIM> G;
+            elemFromRecs<DIM>(recs, packed, P, vel, rho, G);
+            const int li = findSlotByte(packed, si);
+            double sumP = 0, sumR = 0;
+            double Gm[DIM][DIM];
+#pragma unroll
+            for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) Gm[aa][c] = 0;
+#pragma unroll
+            for (int q = 0; q < NPE; ++q) {
+                sumP += P[q];
+                sumR += rho[q];
+#pragma unroll
+                for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) Gm[aa][c] += vel[q][aa] * G.g[c][q];
+            }
+            double tr = 0;
+#pragma unroll
+            for (int aa = 0; aa < DIM; ++aa) tr += Gm[aa][aa];
+            double gi[DIM];
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) gi[c] = pick<NPE>(G.g[c], li);
+            const double pbar = sumP / NPE;
+            const double li_mass = G.V * PHI * (pick<NPE>(rho, li) + sumR);
+#pragma unroll
+            for (int aa = 0; aa < DIM; ++aa) {
+                double sg = 0;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) {
+                    double sig = Gm[aa][c] + Gm[c][aa];
+                    if (c == aa) sig -= (2.0 / 3.0) * tr;
+                    sg += a.mu * sig * gi[c];
+                }
+                F[aa] += -G.V * sg + G.V * pbar * gi[aa] + a.body[aa] * li_mass;
+            }
+            M += li_mass;
+        }
+    }
+    M = groupSum<LPN>(M);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) F[c] = groupSum<LPN>(F[c]);
+    if (valid && sub == 0) {
+        const uint8_t fl = a.flags[i];
+        const bool isFree = fl & PFEM_NODE_FREE, isBound = fl & PFEM_NODE_BOUND;
+        const WcRec& R = recs[si];
+        double inv = 1.0 / M;
+        double acc[3] = {0, 0, 0}, vn[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+            double f = F[c], iv = inv;
+            if (isFree && !isBound) {
+                f = a.body[c];
+                iv = 1.0;
+            } else if (isBound && a.dirMask[i]) {
+                f = a.dirVal4[(size_t)i * 4 + c];  // reference hazard 10
+                iv = 1.0;
+            }
+            acc[c] = iv * f;
+            vn[c] = R.v[c] + 0.5 * a.dt * acc[c];
+        }
+        st4(V4out + (size_t)i * 4, vn[0], vn[1], vn[2], R.v[3]);
         st4(A4out + (size_t)i * 4, acc[0], acc[1], acc[2], 0.0);
     }
 }
@@ -388,28 +636,66 @@ void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     c->X4b.reserve(n4);
     c->V4b.reserve(n4);
     const WcArgs a = makeArgs(c, p, dt);
-    constexpr int LPN = 8;
-    const int grid = divUp((int64_t)c->nRows * LPN, 256);
+    static const int cfg = getenv("PFEM_WC_CFG") ? atoi(getenv("PFEM_WC_CFG")) : 6;
     {
         PhaseScope ph(c, "Update solutions");
         k_wc_kick_move<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->nNodes, c->dim, dt, c->flags.p, c->X4.p, c->V4.p, c->A4.p);
         LAUNCH_CHECK(c);
     }
+    WcArgsS as;
+    as.n2ePtr = c->n2ePtr.p, as.n2eSlots = c->n2eSlots.p, as.nbrPtr = c->nbrPtr.p, as.nbr = c->nbr.p, as.diagSlot = c->diagSlot.p;
+    as.flags = c->flags.p, as.dirMask = c->dirMask.p, as.dirVal4 = c->dirVal4.p, as.nNodes = c->nRows;
+    as.nbcap = std::max(c->maxNb, 1);
+    as.dt = dt, as.mu = p.mu, as.K0 = p.K0, as.K0p = p.K0p, as.rhoStar = p.rhoStar, as.meduri = p.meduri;
+    for (int d = 0; d < 3; ++d) as.body[d] = p.bodyForce[d];
+#define PFEM_WC_LAUNCH_S(KERNEL, LPN_, MINB_, ...)                                                                  \
+    do {                                                                                                            \
+        const int grid_ = divUp((int64_t)c->nRows * LPN_, 256);                                                     \
+        const size_t smem_ = (size_t)(256 / LPN_) * as.nbcap * sizeof(WcRec);                                       \
+        PFEM_REQUIRE(smem_ <= 200 * 1024, PFEM_ERR_INVALID, "wc_step: node valence too large for shared memory");   \
+        if (c->dim == 2) {                                                                                          \
+            if (smem_ > 48 * 1024)                                                                                  \
+                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<2, LPN_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+            KERNEL<2, LPN_, MINB_><<<grid_, 256, smem_, c->stream>>>(as, __VA_ARGS__);                               \
+        } else {                                                                                                    \
+            if (smem_ > 48 * 1024)                                                                                  \
+                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<3, LPN_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+            KERNEL<3, LPN_, MINB_><<<grid_, 256, smem_, c->stream>>>(as, __VA_ARGS__);                               \
+        }                                                                                                           \
+    } while (0)
+#define PFEM_WC_LAUNCH(KERNEL, LPN_, MINB_, ...)                                                  \
+    do {                                                                                          \
+        const int grid_ = divUp((int64_t)c->nRows * LPN_, 256);                                   \
+        if (c->dim == 2) KERNEL<2, LPN_, MINB_><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);      \
+        else KERNEL<3, LPN_, MINB_><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);                  \
+    } while (0)
     {
         PhaseScope ph(c, "Solving continuity eq");
-        if (c->dim == 2)
-            k_wc_cont<2, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else
-            k_wc_cont<3, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, 2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 8) PFEM_WC_LAUNCH_S(k_wc_cont_s, 4, 2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 9) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 1) PFEM_WC_LAUNCH(k_wc_cont, 8, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 2) PFEM_WC_LAUNCH(k_wc_cont, 8, 4, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 3) PFEM_WC_LAUNCH(k_wc_cont, 4, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 4) PFEM_WC_LAUNCH(k_wc_cont, 2, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 5) PFEM_WC_LAUNCH(k_wc_cont, 1, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 6) PFEM_WC_LAUNCH(k_wc_cont, 4, 2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else PFEM_WC_LAUNCH(k_wc_cont, 8, 2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         LAUNCH_CHECK(c);
         if (c->nRanks > 1) commHalo(c, c->X4b.p, c->V4b.p, 4);  // (x, p_new) and (v_half, rho_new) of interface nodes
     }
     {
         PhaseScope ph(c, "Solving momentum eq");
-        if (c->dim == 2)
-            k_wc_mom<2, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else
-            k_wc_mom<3, LPN><<<grid, 256, 0, c->stream>>>(a, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_mom_s, 8, 2, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else if (cfg == 8) PFEM_WC_LAUNCH_S(k_wc_mom_s, 4, 2, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else if (cfg == 9) PFEM_WC_LAUNCH_S(k_wc_mom_s, 8, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else if (cfg == 1) PFEM_WC_LAUNCH(k_wc_mom, 8, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else if (cfg == 2) PFEM_WC_LAUNCH(k_wc_mom, 8, 4, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else if (cfg == 3) PFEM_WC_LAUNCH(k_wc_mom, 4, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else if (cfg == 4) PFEM_WC_LAUNCH(k_wc_mom, 2, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else if (cfg == 5) PFEM_WC_LAUNCH(k_wc_mom, 1, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else if (cfg == 6) PFEM_WC_LAUNCH(k_wc_mom, 4, 2, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        else PFEM_WC_LAUNCH(k_wc_mom, 8, 2, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
         LAUNCH_CHECK(c);
         if (c->nRanks > 1) commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
     }
