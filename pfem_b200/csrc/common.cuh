@@ -121,7 +121,7 @@ struct pfem_ctx {
     DevBuf<double> bvec;       // nNodes*BS, internal dof = node*BS + d
     DevBuf<double> dinv;       // symmetric Jacobi scale 1/sqrt|a_ii|
     DevBuf<double> Wblk;       // node-block Jacobi: A_ii^-1 S_i^-1 per node
-    DevBuf<double> kx, kr, kr0, kp, kv, ks, kt, kph, ksh;  // Krylov vectors (internal dof order)
+    DevBuf<double> kx, kr, kr0, kp, kp2, kv, ks, kt, kph, ksh;  // Krylov vectors (internal dof order)
     DevBuf<double> partial;    // PS_COUNT * reduceBlocks
     DevBuf<double> scal;       // SC_COUNT
     double* hScal = nullptr;   // pinned mirror
@@ -157,7 +157,7 @@ struct pfem_ctx {
             b->accounting = &deviceBytes;
         for (auto* b : {&flags, &dirMask, &stageB}) b->accounting = &deviceBytes;
         for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &Wblk, &kx, &kr, &kr0,
-                        &kp, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &sendBuf})
+                        &kp, &kp2, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &sendBuf})
             b->accounting = &deviceBytes;
         stage64.accounting = &deviceBytes;
         n2eSlots.accounting = &deviceBytes;

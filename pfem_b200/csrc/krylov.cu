@@ -160,6 +160,143 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
     }
 }
 
+// ---- SpMV, bulk-copy (TMA) staged variant for 4x4 blocks ----------------------------------------------------------------
+// A block row is one contiguous run of nb*128 bytes, so one elected lane fetches it with a single cp.async.bulk into a
+// per-warp shared-memory ring (STAGES rows deep) that completes on an mbarrier; the data path of A needs no registers and
+// each warp keeps STAGES-1 rows (~2 KB each) in flight -> enough bytes in flight per SM to run HBM at copy speed.
+// Column indices and the x gathers (L2-resident) stay on the LDG path, prefetched one row ahead.
+__device__ __forceinline__ unsigned smemAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbarInit(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulkLoad(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smemAddr(dst)),
+                 "l"(src), "r"(bytes), "r"(smemAddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbarWait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    const unsigned addr = smemAddr(bar);
+    while (!ok) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    }
+}
+
+template <int STAGES, int CAPB>
+__global__ void __launch_bounds__(256) k_spmv_tma(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+                                                  const double* __restrict__ Aval, const double* __restrict__ x,
+                                                  double* __restrict__ y, const double* __restrict__ w1, double* partial,
+                                                  int stride, int slotYW, int slotYY, const double* __restrict__ scal,
+                                                  const double* __restrict__ rowScale) {
+    constexpr int BS = 4, ROWB = CAPB * BS * BS;  // doubles per stage
+    extern __shared__ __align__(128) unsigned char smemSp[];
+    const int lane = threadIdx.x & 31, grp = lane >> 2, r = lane & 3, wib = threadIdx.x >> 5;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const int gw = blockIdx.x * warpsPerBlock + wib, nw = gridDim.x * warpsPerBlock;
+    double* ring = reinterpret_cast<double*>(smemSp) + (size_t)wib * STAGES * ROWB;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smemSp + (size_t)warpsPerBlock * STAGES * ROWB * 8) + wib * STAGES;
+    double accYW = 0, accYY = 0;
+    const bool frozen = scal && scal[SC_DONE] != 0.0;
+    if (lane == 0)
+        for (int s = 0; s < STAGES; ++s) mbarInit(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    if (!frozen) {
+        const int nMine = gw < nNodes ? (nNodes - gw + nw - 1) / nw : 0;
+        auto issue = [&](int j) {  // lane 0 only
+            const int row = gw + j * nw;
+            const int b0 = __ldg(nbrPtr + row), nb = __ldg(nbrPtr + row + 1) - b0;
+            const unsigned bytes = (unsigned)min(nb, CAPB) * BS * BS * 8u;
+            unsigned long long* bar = bars + (j % STAGES);
+            mbarExpectTx(bar, bytes);
+            bulkLoad(ring + (size_t)(j % STAGES) * ROWB, Aval + (size_t)b0 * BS * BS, bytes, bar);
+        };
+        if (lane == 0)
+            for (int j = 0; j < STAGES - 1 && j < nMine; ++j) issue(j);
+        // column indices of the first row
+        int pb0 = 0, pb1 = 0, c0 = -1, c1 = -1;
+        if (nMine > 0) {
+            pb0 = __ldg(nbrPtr + gw);
+            pb1 = __ldg(nbrPtr + gw + 1);
+            if (grp < pb1 - pb0) c0 = __ldg(nbr + pb0 + grp);
+            if (grp + 8 < pb1 - pb0) c1 = __ldg(nbr + pb0 + grp + 8);
+        }
+        for (int j = 0; j < nMine; ++j) {
+            const int i = gw + j * nw;
+            if (lane == 0 && j + STAGES - 1 < nMine) issue(j + STAGES - 1);
+            // prefetch next row's pointers + column indices
+            int qb0 = 0, qb1 = 0, d0 = -1, d1 = -1;
+            if (j + 1 < nMine) {
+                qb0 = __ldg(nbrPtr + i + nw);
+                qb1 = __ldg(nbrPtr + i + nw + 1);
+            }
+            const int nb = pb1 - pb0;
+            // x gathers for this row can start before A has landed
+            double2 x01a = make_double2(0, 0), x23a = x01a, x01b = x01a, x23b = x01a;
+            if (c0 >= 0) {
+                const double* xp = x + (size_t)c0 * BS;
+                x01a = __ldg(reinterpret_cast<const double2*>(xp));
+                x23a = __ldg(reinterpret_cast<const double2*>(xp + 2));
+            }
+            if (c1 >= 0) {
+                const double* xp = x + (size_t)c1 * BS;
+                x01b = __ldg(reinterpret_cast<const double2*>(xp));
+                x23b = __ldg(reinterpret_cast<const double2*>(xp + 2));
+            }
+            if (j + 1 < nMine) {
+                if (grp < qb1 - qb0) d0 = __ldg(nbr + qb0 + grp);
+                if (grp + 8 < qb1 - qb0) d1 = __ldg(nbr + qb0 + grp + 8);
+            }
+            const double* buf = ring + (size_t)(j % STAGES) * ROWB;
+            mbarWait(bars + (j % STAGES), (unsigned)((j / STAGES) & 1));
+            double acc = 0;
+            if (c0 >= 0) {
+                const double2 a01 = *reinterpret_cast<const double2*>(buf + (grp * BS + r) * BS);
+                const double2 a23 = *reinterpret_cast<const double2*>(buf + (grp * BS + r) * BS + 2);
+                acc += a01.x * x01a.x + a01.y * x01a.y + a23.x * x23a.x + a23.y * x23a.y;
+            }
+            if (c1 >= 0) {
+                const double2 a01 = *reinterpret_cast<const double2*>(buf + ((grp + 8) * BS + r) * BS);
+                const double2 a23 = *reinterpret_cast<const double2*>(buf + ((grp + 8) * BS + r) * BS + 2);
+                acc += a01.x * x01b.x + a01.y * x01b.y + a23.x * x23b.x + a23.y * x23b.y;
+            }
+            for (int s = grp + 16; s < nb; s += 8) {  // blocks beyond the staged CAPB (rare): direct loads
+                RowLoad<BS> L;
+                loadSlot<BS>(Aval, x, pb0 + s, __ldg(nbr + pb0 + s), r, L);
+                acc += dotSlot<BS>(L);
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (grp == 0) {
+                const size_t o = (size_t)i * BS + r;
+                if (rowScale) acc *= rowScale[o];
+                y[o] = acc;
+                if (slotYW >= 0) accYW += acc * w1[o];
+                if (slotYY >= 0) accYY += acc * acc;
+            }
+            __syncwarp();  // every lane is done with this stage before lane 0 re-arms it
+            pb0 = qb0, pb1 = qb1, c0 = d0, c1 = d1;
+        }
+    }
+    if (slotYW >= 0 || slotYY >= 0) {
+        double v[2] = {accYW, accYY};
+        const int slots[2] = {slotYW >= 0 ? slotYW : PS_AUX, slotYY >= 0 ? slotYY : PS_AUX + 1};
+        blockSumStore<2>(v, partial, stride, slots);
+    }
+}
+
 // ---- vector kernels ---------------------------------------------------------------------------------------------------
 // r = b - y (y = A x0 precomputed, or nullptr for x0 = 0) ; r0 = r ; p = v = 0 ; partials rho=(r0,r)=||r||^2, ||b||^2
 __global__ void __launch_bounds__(RB_THREADS) k_init(int n, const double* __restrict__ b, const double* __restrict__ y,
@@ -199,8 +336,9 @@ __global__ void k_init_scal(double* scal, const double* partial, int stride, int
 
 // K_A: beta = (rho/rho_old)(alpha/omega) ; p = r + beta (p - omega v) ; phat = dinv .* p      [+ convergence test]
 template <int BS>
-__global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __restrict__ r, double* __restrict__ p,
-                                                         const double* __restrict__ v, const double* __restrict__ dinv,
+__global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __restrict__ r, const double* __restrict__ p,
+                                                         double* __restrict__ pnew, const double* __restrict__ v,
+                                                         const double* __restrict__ dinv,
                                                          const double* __restrict__ W, double* __restrict__ ph,
                                                          double* scal, const double* partial,
                                                          int stride, int nPart, int parity, int iterIndex) {
@@ -219,29 +357,26 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __
     }
     if (wasDone || conv || bad) return;
     const double beta = (rho / rhoOld) * (alpha / omega);
-    if (W) {  // node-block Jacobi: phat_i = W_i p_i with W_i = A_ii^-1 S_i^-1 (one thread per node)
-        for (int nd = blockIdx.x * blockDim.x + threadIdx.x; nd < n / BS; nd += gridDim.x * blockDim.x) {
-            double pn[4];
+    if (W) {  // node-block Jacobi: phat_i = W_i p_i with W_i = A_ii^-1 S_i^-1; one thread per dof (= one row of W_i), the
+              // BS entries of the node are recomputed per thread (same 32-byte sector) so that every load is coalesced
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int base = (i / BS) * BS;
+            const double* Wr = W + (size_t)i * BS;
+            double a = 0, mine = 0;
 #pragma unroll
             for (int c = 0; c < BS; ++c) {
-                const int i = nd * BS + c;
-                pn[c] = r[i] + beta * (p[i] - omega * v[i]);
-                p[i] = pn[c];
+                const double pc = r[base + c] + beta * (p[base + c] - omega * v[base + c]);
+                a += Wr[c] * pc;
+                mine = (base + c == i) ? pc : mine;
             }
-            const double* Wn = W + (size_t)nd * BS * BS;
-#pragma unroll
-            for (int rr2 = 0; rr2 < BS; ++rr2) {
-                double a = 0;
-#pragma unroll
-                for (int c = 0; c < BS; ++c) a += Wn[rr2 * BS + c] * pn[c];
-                ph[nd * BS + rr2] = a;
-            }
+            pnew[i] = mine;
+            ph[i] = a;
         }
         return;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double pi = r[i] + beta * (p[i] - omega * v[i]);
-        p[i] = pi;
+        pnew[i] = pi;
         ph[i] = dinv[i] * pi;
     }
 }
@@ -260,23 +395,19 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_s(int n, const double* __
         return;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[SC_ALPHA] = alpha;
-    if (W) {
-        for (int nd = blockIdx.x * blockDim.x + threadIdx.x; nd < n / BS; nd += gridDim.x * blockDim.x) {
-            double sn[4];
+    if (W) {  // one thread per dof, see k_update_p
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            const int base = (i / BS) * BS;
+            const double* Wr = W + (size_t)i * BS;
+            double a = 0, mine = 0;
 #pragma unroll
             for (int c = 0; c < BS; ++c) {
-                const int i = nd * BS + c;
-                sn[c] = r[i] - alpha * v[i];
-                s[i] = sn[c];
+                const double sc2 = r[base + c] - alpha * v[base + c];
+                a += Wr[c] * sc2;
+                mine = (base + c == i) ? sc2 : mine;
             }
-            const double* Wn = W + (size_t)nd * BS * BS;
-#pragma unroll
-            for (int rr2 = 0; rr2 < BS; ++rr2) {
-                double a = 0;
-#pragma unroll
-                for (int c = 0; c < BS; ++c) a += Wn[rr2 * BS + c] * sn[c];
-                sh[nd * BS + rr2] = a;
-            }
+            s[i] = mine;
+            sh[i] = a;
         }
         return;
     }
@@ -412,6 +543,14 @@ __global__ void k_from_internal(const double* __restrict__ src, double* __restri
     q[t] = src[(size_t)n * BS + d];
 }
 
+// SpMV flavour for 4x4 blocks.  Default 0 = register-pipelined kernel (156 us at C4 on B200).  PFEM_SPMV_TMA=2..6 selects
+// the cp.async.bulk ring of that depth: measured SLOWER (217 us at depth 2-4; one 1.9 KB bulk copy per block row is too
+// fine a granularity for the copy engine), kept for experiments with coarser row groups.
+int spmvTmaStages() {
+    static const int v = getenv("PFEM_SPMV_TMA") ? atoi(getenv("PFEM_SPMV_TMA")) : 0;
+    return v;
+}
+
 struct KrylovDims {
     int n;      // owned dofs: the rows this rank computes and the extent of every dot product
     int nAll;   // owned + ghost dofs: extent of the vectors SpMV gathers from
@@ -425,10 +564,10 @@ KrylovDims setup(pfem_ctx* c) {
     k.nAll = c->nNodes * k.BS;
     k.multi = c->nRanks > 1;
     k.vecGrid = std::max(1, std::min(c->smCount * 4, divUp(k.n, RB_THREADS)));
-    k.spmvGrid = std::max(1, std::min(c->smCount * 8, divUp(c->nRows, 8)));
+    k.spmvGrid = std::max(1, std::min(c->smCount * ((k.BS == 4 && spmvTmaStages() > 0) ? 3 : 8), divUp(c->nRows, 8)));
     k.stride = std::max(k.vecGrid, k.spmvGrid);
     c->reduceBlocks = k.stride;
-    for (auto* b : {&c->kx, &c->kr, &c->kr0, &c->kp, &c->kv, &c->ks, &c->kt, &c->kph, &c->ksh}) b->reserve(k.nAll + 8);
+    for (auto* b : {&c->kx, &c->kr, &c->kr0, &c->kp, &c->kp2, &c->kv, &c->ks, &c->kt, &c->kph, &c->ksh}) b->reserve(k.nAll + 8);
     c->partial.reserve((size_t)PS_COUNT * k.stride);
     c->scal.reserve(SC_COUNT);
     if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
@@ -441,6 +580,23 @@ void spmv(pfem_ctx* c, const KrylovDims& k, double* x, double* y, const double* 
     if (k.multi) commHalo(c, x, nullptr, k.BS);
     PhaseScope ph(c, "SpMV");
     static const int minb = getenv("PFEM_SPMV_MINB") ? atoi(getenv("PFEM_SPMV_MINB")) : 3;
+    const int tmaStages = spmvTmaStages();
+    if (k.BS == 4 && tmaStages > 0) {
+        constexpr int CAPB = 16, WARPS = 8;
+        const int grid = k.spmvGrid;
+        auto launch = [&](auto kern, int stages) {
+            const size_t smem = (size_t)WARPS * stages * (CAPB * 16 * 8 + 8);
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, WARPS * 32, smem, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p, k.stride,
+                                                      slotYW, slotYY, sc, rowScale);
+        };
+        if (tmaStages == 2) launch(k_spmv_tma<2, CAPB>, 2);
+        else if (tmaStages == 3) launch(k_spmv_tma<3, CAPB>, 3);
+        else if (tmaStages == 6) launch(k_spmv_tma<6, CAPB>, 6);
+        else launch(k_spmv_tma<4, CAPB>, 4);
+        LAUNCH_CHECK(c);
+        return;
+    }
     if (k.BS == 4 && minb == 4)
         k_spmv<4, 4><<<k.spmvGrid, 256, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p,
                                                         k.stride, slotYW, slotYY, sc, rowScale);
@@ -554,11 +710,14 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
             const int batch = std::min(checkEvery, maxIter - totalIters - it);
             for (int b = 0; b < batch; ++b, ++it) {
                 const int parity = it & 1;
+                // p is double-buffered (k_update_p reads the whole node block of the old p): even iterations read kp, odd kp2
+                double* pOld = parity ? c->kp2.p : c->kp.p;
+                double* pNew = parity ? c->kp.p : c->kp2.p;
                 if (k.BS == 4)
-                    k_update_p<4><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kp.p, c->kv.p, c->dinv.p, W, c->kph.p,
+                    k_update_p<4><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, pOld, pNew, c->kv.p, c->dinv.p, W, c->kph.p,
                                                                            c->scal.p, c->partial.p, k.stride, npVec, parity, it);
                 else
-                    k_update_p<3><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kp.p, c->kv.p, c->dinv.p, W, c->kph.p,
+                    k_update_p<3><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, pOld, pNew, c->kv.p, c->dinv.p, W, c->kph.p,
                                                                            c->scal.p, c->partial.p, k.stride, npVec, parity, it);
                 LAUNCH_CHECK(c);
                 spmv(c, k, c->kph.p, c->kv.p, c->kr0.p, PS_SIGMA, -1, true, c->dinv.p);
