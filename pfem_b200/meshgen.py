@@ -205,3 +205,57 @@ def wc_state(mesh: Mesh, **kw):
     rho = tait_density(p, WC_PARAMS["K0"], WC_PARAMS["K0p"], WC_PARAMS["rhoStar"])
     acc = np.zeros_like(v)
     return dict(v=v, p=p, rho=rho, acc=acc)
+
+
+def delaunay_cloud(dim: int, n_points: int, *, seed: int = 11, alpha: float = 1.3, free_fraction: float = 0.0) -> Mesh:
+    """Unstructured stand-in for the gmsh + CGAL alpha-shape meshes of the examples (no gmsh/CGAL here): Delaunay
+    triangulation of a jittered point cloud in the unit box, cells kept when their circumradius < alpha*h
+    (the criterion of Mesh2D.cpp:54 / Mesh3D.cpp:60), positive orientation enforced.  Node valence varies widely
+    (3-D: up to ~40 incident tets), which exercises the multi-chunk paths of the gather kernels."""
+    from scipy.spatial import Delaunay
+    rng = np.random.default_rng(seed)
+    m = max(2, int(round(n_points ** (1.0 / dim))))
+    h = 1.0 / (m - 1)
+    axes = np.meshgrid(*([np.linspace(0, 1, m)] * dim), indexing="ij")
+    pts = np.stack([a.ravel() for a in axes], axis=1)
+    on_b = ((pts == 0) | (pts == 1)).any(axis=1)
+    pts = pts + rng.uniform(-0.35 * h, 0.35 * h, pts.shape) * (~on_b)[:, None]
+    tri = Delaunay(pts)
+    conn = tri.simplices.astype(np.int64)
+    p0 = pts[conn[:, 0]]
+    J = np.stack([pts[conn[:, k + 1]] - p0 for k in range(dim)], axis=2)
+    det = np.linalg.det(J)
+    neg = det < 0
+    conn[neg, -1], conn[neg, -2] = conn[neg, -2].copy(), conn[neg, -1].copy()
+    det = np.abs(det)
+    # circumradius filter + drop slivers
+    A = 2 * np.transpose(J, (0, 2, 1))
+    rhs = (np.transpose(J, (0, 2, 1)) ** 2).sum(axis=2)
+    ok = det > 1e-9 * h ** dim
+    cc = np.zeros((conn.shape[0], dim))
+    cc[ok] = np.linalg.solve(A[ok], rhs[ok][..., None])[..., 0]
+    rad = np.linalg.norm(cc, axis=1)
+    conn = conn[ok & (rad < alpha * h)]
+    n_nodes = pts.shape[0]
+    wall = np.zeros(n_nodes, dtype=bool)
+    for d in range(dim - 1):
+        wall |= (pts[:, d] == 0) | (pts[:, d] == 1)
+    wall |= pts[:, dim - 1] == 0
+    flags = np.zeros(n_nodes, dtype=np.uint8)
+    flags[wall] |= F_BOUND | F_FIXED
+    flags[(pts[:, dim - 1] == 1) & ~wall] |= F_FS
+    used = np.zeros(n_nodes, dtype=bool)
+    used[conn.ravel()] = True
+    flags[~used] |= F_FREE                                       # nodes left without elements by the alpha criterion
+    dir_mask = wall.astype(np.uint8)
+    if free_fraction > 0:
+        k = max(1, int(round(free_fraction * n_nodes)))
+        extra = rng.uniform(0.05, 0.95, size=(k, dim))
+        extra[:, dim - 1] += 1.0
+        pts = np.concatenate([pts, extra])
+        flags = np.concatenate([flags, np.full(k, F_FREE, dtype=np.uint8)])
+        dir_mask = np.concatenate([dir_mask, np.zeros(k, dtype=np.uint8)])
+        n_nodes += k
+    x = np.ascontiguousarray(pts.T).reshape(-1)
+    return Mesh(dim=dim, x=x, conn=np.ascontiguousarray(conn), flags=flags, dir_mask=dir_mask,
+                dir_val=np.zeros(dim * n_nodes), n_cells=m, meta=dict(kind="delaunay", seed=seed))
