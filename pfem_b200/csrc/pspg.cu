@@ -27,9 +27,11 @@ template <int DIM> struct alignas(16) ElemS {
     double g[DIM + 1][GP];  // grad N_m = g[m][0..DIM)   (MatricesBuilder.inl:93-127)
     double V;               // element size detJ*ref; all five block coefficients are multiples of V and tau*V:
     double tauV;            //   M/dt: rho phi/dt V | K: mu V | D: V/npe | (tau/dt) C: tauV/(npe dt) | tau L: tauV/rho
+    double be[4];           // this element's contribution to the RHS rows of node i (summed by the diagonal lanes)
     unsigned slots;         // slot byte of each local node in the neighbour list of i
     int li;                 // local index of node i in this element
-    double pad_[(DIM == 3) ? 2 : 1];  // record stride = odd multiple of 16 B: LDS.128 of different records spread over banks
+    double pad_[(DIM == 3) ? 3 : 1];  // record stride = odd multiple of 16 B (208 | 112): LDS.128 of different records
+                                      // spread over the banks
 };
 struct BlockCoef {
     double kmass, kvisc, kdiv, kpc, kL;  // rho phi/dt, mu, 1/npe, 1/(npe dt), 1/rho
@@ -194,7 +196,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
     };
 
     // phase-1 body for one (node, incident element) pair; returns the element's contribution to the RHS rows of node i
-    auto elementPhase = [&](int k, unsigned packed, int si, double (&be)[BS]) {
+    auto elementPhase = [&](int k, unsigned packed, int si) {
         const int li = findByte(packed, si);
         // previous velocities: only their element sum and the value at node i are needed
         double sv[DIM], vpi[DIM], usum = 0;
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
         *reinterpret_cast<double2*>(&E.V) = make_double2(V, tau * V);
         *reinterpret_cast<uint2*>(&E.slots) = make_uint2(packed, (unsigned)li);
         // RHS rows of node i: be = [F + (M/dt) vPrev ; tau H + (tau/dt) C vPrev]   (PSPG.inl:53)
-        double gb = 0, gs = 0;
+        double gb = 0, gs = 0, bloc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
         for (int c = 0; c < DIM; ++c) {
             double gci = g[0][c];
@@ -280,9 +282,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
             for (int m = 1; m < NPE; ++m) gci = (li == m) ? g[m][c] : gci;
             gb += gci * a.body[c];
             gs += gci * sv[c];
-            be[c] += a.rho * cdiv * a.body[c] + cmass * (vpi[c] + sv[c]);
+            bloc[c] = a.rho * cdiv * a.body[c] + cmass * (vpi[c] + sv[c]);
         }
-        be[DIM] += tau * V * gb + cpc * gs;
+        bloc[DIM] = tau * V * gb + cpc * gs;
+        *reinterpret_cast<double2*>(&E.be[0]) = make_double2(bloc[0], bloc[1]);
+        *reinterpret_cast<double2*>(&E.be[2]) = make_double2(bloc[2], bloc[3]);
     };
 
     // ---- software pipeline prologue: header, lane data and connectivity of the first node ---------------------------
@@ -306,36 +310,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
         for (int w = 1; w < a.dirWords; ++w) anyDir |= a.rowDir[(size_t)i * a.dirWords + w] != 0;
 
         // -------------------------------------------------------------- phase 1: element geometry + RHS rows of node i
-        double be[BS];
-#pragma unroll
-        for (int r = 0; r < BS; ++r) be[r] = 0.0;
         // stage the nodal records of all neighbours once (instead of once per incident element)
         if (lane < nb) stageNode(lane, L.nbrNode);
         for (int s2 = lane + 32; s2 < nb; s2 += 32) stageNode(s2, a.nbr[nb0 + s2]);
         __syncwarp();
-        if (lane < ne) elementPhase(lane, L.packed, si, be);
+        if (lane < ne) elementPhase(lane, L.packed, si);
         for (int k = lane + 32; k < ne; k += 32)  // nodes with more than 32 incident elements (rare)
-            elementPhase(k, a.n2eSlots[eb + k], si, be);
+            elementPhase(k, a.n2eSlots[eb + k], si);
         if (haveNext) loadLane(Hn, Ln);  // level-2 loads of the next node fly during phase 2
-        // transposing butterfly: BS row sums over 32 lanes; lane l ends with the total of row 2*(l>>4) + ((l>>3)&1)
-        {
-            double t2[2], t1;
-            const bool u16 = lane & 16, u8 = lane & 8;
-            const double be3 = (BS == 4) ? be[BS - 1] : 0.0;
-            t2[0] = (u16 ? be[2] : be[0]) + __shfl_xor_sync(0xffffffffu, u16 ? be[0] : be[2], 16);
-            t2[1] = (u16 ? be3 : be[1]) + __shfl_xor_sync(0xffffffffu, u16 ? be[1] : be3, 16);
-            t1 = (u8 ? t2[1] : t2[0]) + __shfl_xor_sync(0xffffffffu, u8 ? t2[0] : t2[1], 8);
-            t1 += __shfl_xor_sync(0xffffffffu, t1, 4);
-            t1 += __shfl_xor_sync(0xffffffffu, t1, 2);
-            t1 += __shfl_xor_sync(0xffffffffu, t1, 1);
-            be[0] = t1;
-        }
         __syncwarp();
 
         // -------------------------------------------------------------- phase 2: one lane = one (dim+1)^2 block
         // lanes 0..15 : off-diagonal blocks, 16 per round, elements of the edge (i,j) in ascending order (blkMask)
         // lanes 16..31: the diagonal block, incident elements dealt round-robin, then a transposing butterfly reduction
-        double bsub[BS];
+        double bsub[BS], beTot = 0.0;
 #pragma unroll
         for (int r = 0; r < BS; ++r) bsub[r] = 0.0;
         double* Arow = a.Aval + (size_t)nb0 * BS * BS;
@@ -345,7 +333,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
             const bool offAct = !diagLane && m < nb - 1;
             const bool dgAct = diagLane && m0 == 0;
             const int jb = offAct ? (m + (m >= si ? 1 : 0)) : si;
-            double acc[16];
+            double acc[16], beAcc[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
             for (int t = 0; t < 16; ++t) acc[t] = 0.0;
             if (offAct || dgAct) {
@@ -358,63 +346,64 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
                         const unsigned valid = rem >= 32 ? 0xffffffffu : (rem > 0 ? (1u << rem) - 1u : 0u);
                         mk = (0x11111111u << dq) & valid;
                     }
-                    while (mk) {
-                        const int k = ch * 32 + __ffs(mk) - 1;
+                    while (mk) {  // two elements per trip: the second one's shared-memory loads overlap the first one's math
+                        const int k0 = ch * 32 + __ffs(mk) - 1;
                         mk &= mk - 1;
-                        const ElemS<DIM>& E = es[k];
-                        const int li = E.li;
-                        const int lj = offAct ? findByte(E.slots, jb) : li;
-                        accumBlock<DIM>(E, KC, li, lj, acc);
+                        const bool two = mk != 0;
+                        const int k1 = two ? ch * 32 + __ffs(mk) - 1 : k0;
+                        mk &= mk - 1;
+                        const ElemS<DIM>& E0 = es[k0];
+                        const ElemS<DIM>& E1 = es[k1];
+                        const int li0 = E0.li, li1 = E1.li;
+                        const int lj0 = offAct ? findByte(E0.slots, jb) : li0;
+                        const int lj1 = offAct ? findByte(E1.slots, jb) : li1;
+                        accumBlock<DIM>(E0, KC, li0, lj0, acc);
+                        if (two) accumBlock<DIM>(E1, KC, li1, lj1, acc);
+                        if (!offAct) {  // diagonal lanes also sum the element RHS rows of node i
+                            const double2 b01 = ld2(&E0.be[0]), b23 = ld2(&E0.be[2]);
+                            beAcc[0] += b01.x, beAcc[1] += b01.y, beAcc[2] += b23.x, beAcc[3] += b23.y;
+                            if (two) {
+                                const double2 c01 = ld2(&E1.be[0]), c23 = ld2(&E1.be[2]);
+                                beAcc[0] += c01.x, beAcc[1] += c01.y, beAcc[2] += c23.x, beAcc[3] += c23.y;
+                            }
+                        }
                     }
                 }
             }
             if (m0 == 0) {
-                // diagonal: 4 partial blocks on lanes 16..19 -> two transposing butterfly steps -> lane 16+r holds row r
-                double v8[8], v4[4];
-                {
-                    const bool up = lane & 2;
+                // diagonal block + RHS rows: the 4 diagonal lanes park their partial sums (16 + 4 doubles each) in shared
+                // memory (the neighbour-record area is free after phase 1); lanes 0..15 then own one diagonal entry each,
+                // lanes 16..19 one RHS row each
+                double* scr = reinterpret_cast<double*>(nrec);
+                if (diagLane) {
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
-                        const double mine = up ? acc[8 + t] : acc[t], send = up ? acc[t] : acc[8 + t];
-                        v8[t] = mine + __shfl_xor_sync(0xffffffffu, send, 2);
-                    }
+                    for (int t = 0; t < 8; ++t)
+                        *reinterpret_cast<double2*>(scr + dq * 20 + 2 * t) = make_double2(acc[2 * t], acc[2 * t + 1]);
+                    *reinterpret_cast<double2*>(scr + dq * 20 + 16) = make_double2(beAcc[0], beAcc[1]);
+                    *reinterpret_cast<double2*>(scr + dq * 20 + 18) = make_double2(beAcc[2], beAcc[3]);
                 }
-                {
-                    const bool up = lane & 1;
+                __syncwarp();
+                if (lane < 20) {
+                    const double tot = (scr[lane] + scr[20 + lane]) + (scr[40 + lane] + scr[60 + lane]);
+                    if (lane < 16) {
+                        const int r = lane >> 2, cc = lane & 3;
+                        if (r < BS && cc < BS) {
+                            const bool rowMasked = (r < DIM) ? maskV : maskP;
+                            const bool selfDir = (si < 32) ? ((H.dir0 >> si) & 1u)
+                                                           : ((a.rowDir[(size_t)i * a.dirWords + (si >> 5)] >> (si & 31)) & 1u);
+                            double val = tot;
+                            if (rowMasked) val = (r == cc) ? 1.0 : 0.0;
+                            else if (selfDir && cc < DIM && cc != r) {  // node i itself is a Dirichlet node (PSPG.inl:219-228)
+                                const double sub = val * a.dirVal4[(size_t)i * 4 + cc];
 #pragma unroll
-                    for (int t = 0; t < 4; ++t) {
-                        const double mine = up ? v8[4 + t] : v8[t], send = up ? v8[t] : v8[4 + t];
-                        v4[t] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
-                    }
-                }
-                if (diagLane && dq < BS) {
-                    const int r = dq;
-                    const bool rowMasked = (r < DIM) ? maskV : maskP;
-                    const bool selfDir = (si < 32) ? ((H.dir0 >> si) & 1u)
-                                                   : ((a.rowDir[(size_t)i * a.dirWords + (si >> 5)] >> (si & 31)) & 1u);
-#pragma unroll
-                    for (int cc = 0; cc < BS; ++cc) {
-                        if (rowMasked) v4[cc] = (r == cc) ? 1.0 : 0.0;
-                    }
-                    if (!rowMasked && selfDir) {
-                        double sub = 0.0;
-#pragma unroll
-                        for (int cc = 0; cc < DIM; ++cc)
-                            if (cc != r) {
-                                sub += v4[cc] * a.dirVal4[(size_t)i * 4 + cc];
-                                v4[cc] = 0.0;
+                                for (int rr = 0; rr < BS; ++rr) bsub[rr] += (rr == r) ? sub : 0.0;
+                                val = 0.0;
                             }
-#pragma unroll
-                        for (int rr = 0; rr < BS; ++rr) bsub[rr] += (rr == r) ? sub : 0.0;
-                    }
-                    double* dst = Arow + (size_t)si * BS * BS + r * BS;
-                    double dg = v4[0];
-#pragma unroll
-                    for (int cc = 0; cc < BS; ++cc) {
-                        dst[cc] = v4[cc];
-                        dg = (cc == r) ? v4[cc] : dg;
-                    }
-                    a.dinv[(size_t)i * BS + r] = (dg != 0.0) ? rsqrt(fabs(dg)) : 1.0;  // symmetric Jacobi scale 1/sqrt|a_ii|
+                            Arow[(size_t)si * BS * BS + r * BS + cc] = val;
+                            if (r == cc) a.dinv[(size_t)i * BS + r] = (val != 0.0) ? rsqrt(fabs(val)) : 1.0;  // 1/sqrt|a_ii|
+                        }
+                    } else
+                        beTot = tot;  // lane 16 + r holds the assembled RHS of row r
                 }
             }
             if (offAct) {
@@ -461,20 +450,18 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) bsub[r] += __shfl_xor_sync(0xffffffffu, bsub[r], o);
         }
-        {
-            const int r = 2 * (lane >> 4) + ((lane >> 3) & 1);
-            if ((lane & 7) == 0 && r < BS) {
-                double bv = be[0], bs = bsub[0];
+        if (lane >= 16 && lane < 16 + BS) {
+            const int r = lane - 16;
+            double bv = beTot, bs = bsub[0];
 #pragma unroll
-                for (int c = 1; c < BS; ++c) bs = (c == r) ? bsub[c] : bs;
-                bv -= bs;
-                if (isFree) {
-                    if (r == DIM) bv = 0.0;
-                    else if (!isBound) bv = a.VP4[(size_t)i * 4 + r] + a.dt * a.body[r];
-                }
-                if (isBound && a.dirMask[i] && r < DIM) bv = a.dirVal4[(size_t)i * 4 + r];
-                a.b[(size_t)i * BS + r] = bv;
+            for (int c = 1; c < BS; ++c) bs = (c == r) ? bsub[c] : bs;
+            bv -= bs;
+            if (isFree) {
+                if (r == DIM) bv = 0.0;
+                else if (!isBound) bv = a.VP4[(size_t)i * 4 + r] + a.dt * a.body[r];
             }
+            if (isBound && a.dirMask[i] && r < DIM) bv = a.dirVal4[(size_t)i * 4 + r];
+            a.b[(size_t)i * BS + r] = bv;
         }
         __syncwarp();  // all lanes are done with es[] before the next node's phase 1 overwrites it
         H = Hn, L = Ln;
@@ -580,7 +567,7 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
     a.CH = c->maskWords;
     a.dirWords = dirWords;
     a.ecap = std::max(c->maxE, 1);
-    a.nbcap = std::max(c->maxNb, 1);
+    a.nbcap = std::max(c->maxNb, 8);  // >= 640 B per warp: the area doubles as the diagonal-reduction scratch
     a.rho = p.rho, a.mu = p.mu, a.dt = p.dt;
     for (int d = 0; d < 3; ++d) a.body[d] = p.bodyForce[d];
     {
