@@ -141,6 +141,11 @@ int pfem_pspg_matvec(pfem_ctx* ctx, const double* x, double* y);
 int pfem_wc_step(pfem_ctx* ctx, const pfem_wc_params* p, double dt);
 /* SolverWCompNewton::computeNextDT (WCompNewton/Solver.cpp:192-234) incl. Element::getRin (Element.cpp:226-294) */
 int pfem_wc_next_dt(pfem_ctx* ctx, const pfem_wc_params* p, double securityCoeff, double maxDT, double* dt);
+/* nSteps iterations of the Problem::simulate loop body for the explicit solver between two remeshes
+ * (Problem.cpp:344-369: solveOneTimeStep then computeNextDT) without returning to the host: *dt is the first time step on
+ * entry and the next one on exit, *elapsed the simulated time covered.  One CUDA graph per step.  Single-GPU contexts. */
+int pfem_wc_run(pfem_ctx* ctx, const pfem_wc_params* p, int nSteps, double securityCoeff, double maxDT, double* dt,
+                double* elapsed);
 
 /* ---- multi-GPU (one context per rank/GPU; elements sharded by RCB) ---- */
 /* ncclUniqueId: the 128 opaque bytes of ncclGetUniqueId obtained by rank 0 (pfem_comm_unique_id) and broadcast by the

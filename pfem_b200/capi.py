@@ -67,6 +67,7 @@ SYMBOLS = {
     "pfem_pspg_matvec": (C.c_int, [_VP, _DP, _DP]),
     "pfem_wc_step": (C.c_int, [_VP, C.POINTER(WcParams), C.c_double]),
     "pfem_wc_next_dt": (C.c_int, [_VP, C.POINTER(WcParams), C.c_double, C.c_double, _DP]),
+    "pfem_wc_run": (C.c_int, [_VP, C.POINTER(WcParams), C.c_int, C.c_double, C.c_double, _DP, _DP]),
     "pfem_comm_unique_id": (C.c_int, [_VP]),
     "pfem_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "pfem_set_partition": (C.c_int, [_VP, C.c_int64, C.c_int, _I32P, _I64P, _I32P, _I64P, _I64P]),
@@ -291,6 +292,15 @@ class PfemContext:
         if rc == PFEM_NAN:
             raise PfemError(rc, "NaN time step!")  # WCompNewton/Solver.cpp:231-232
         return dt.value
+
+    def wc_run(self, params, n_steps, security_coeff, max_dt, dt0):
+        """n_steps explicit steps with the CFL dt chained on the device; returns (next dt, elapsed simulated time)."""
+        dt, el = C.c_double(dt0), C.c_double(0)
+        rc = self._chk(self._L.pfem_wc_run(self._h, C.byref(params), int(n_steps), security_coeff, max_dt, C.byref(dt), C.byref(el)),
+                       allow=(PFEM_NAN,))
+        if rc == PFEM_NAN:
+            raise PfemError(rc, "NaN time step!")  # WCompNewton/Solver.cpp:231-232
+        return dt.value, el.value
 
     # -- multi-GPU ------------------------------------------------------------------
     def comm_unique_id(self) -> bytes:

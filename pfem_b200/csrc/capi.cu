@@ -271,6 +271,19 @@ int pfem_wc_next_dt(pfem_ctx* c, const pfem_wc_params* p, double securityCoeff, 
     }
 }
 
+int pfem_wc_run(pfem_ctx* c, const pfem_wc_params* p, int nSteps, double securityCoeff, double maxDT, double* dt, double* elapsed) {
+    if (!c) return PFEM_ERR_INVALID;
+    try {
+        cudaSetDevice(c->device);
+        PFEM_REQUIRE(p, PFEM_ERR_INVALID, "wc_run: params is null");
+        return wcRun(c, *p, nSteps, securityCoeff, maxDT, dt, elapsed);
+    } catch (const PfemFail& f) {
+        c->err = f.msg;
+        cudaGetLastError();
+        return f.code;
+    }
+}
+
 int pfem_comm_unique_id(void* id128) {
     try {
         commUniqueId(id128);

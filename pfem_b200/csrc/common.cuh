@@ -231,6 +231,7 @@ void krylovMatvec(pfem_ctx* c, double* xInternal, double* yInternal);
 // wc.cu
 void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt);
 int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dt);
+int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff, double maxDT, double* dtInOut, double* elapsed);
 // comm.cu
 void commUniqueId(void* id128);
 void commInit(pfem_ctx* c, int nRanks, int rank, const void* id128);

@@ -24,10 +24,12 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
     *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
 }
 
-__global__ void k_wc_kick_move(int nNodes, int dim, double dt, const uint8_t* __restrict__ flags, double* __restrict__ X4,
-                               double* __restrict__ V4, const double* __restrict__ A4) {
+__global__ void k_wc_kick_move(int nNodes, int dim, double dtVal, const double* __restrict__ dtPtr,
+                               const uint8_t* __restrict__ flags, double* __restrict__ X4, double* __restrict__ V4,
+                               const double* __restrict__ A4) {
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= nNodes) return;
+    const double dt = dtPtr ? *dtPtr : dtVal;  // device-resident dt when steps are chained without a host round trip
     const bool fixed = flags[n] & PFEM_NODE_FIXED;
     for (int d = 0; d < dim; ++d) {
         const double vh = V4[(size_t)n * 4 + d] + 0.5 * dt * A4[(size_t)n * 4 + d];
@@ -43,18 +45,11 @@ template <int DIM> struct ElemGeo {
 
 // gather the 4-double records of the element nodes and build grad N and the volume (Element.cpp:15-135, MB.inl:93-127)
 template <int DIM>
-__device__ __forceinline__ void loadElem(const int* __restrict__ conn, int e, const double* __restrict__ XA,
-                                         const double* __restrict__ VA, int (&nd)[DIM + 1], double (&xw)[DIM + 1],
-                                         double (&vel)[DIM + 1][DIM], double (&vw)[DIM + 1], ElemGeo<DIM>& G) {
+__device__ __forceinline__ void loadElem(const double* __restrict__ XA, const double* __restrict__ VA,
+                                         const int (&nd)[DIM + 1], double (&xw)[DIM + 1], double (&vel)[DIM + 1][DIM],
+                                         double (&vw)[DIM + 1], ElemGeo<DIM>& G) {
     constexpr int NPE = DIM + 1;
     constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
-    if constexpr (DIM == 3) {
-        const int4 q = *reinterpret_cast<const int4*>(conn + (size_t)e * 4);
-        nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
-    } else {
-#pragma unroll
-        for (int m = 0; m < NPE; ++m) nd[m] = conn[(size_t)e * NPE + m];
-    }
     double px[NPE][DIM];
 #pragma unroll
     for (int m = 0; m < NPE; ++m) {
@@ -109,6 +104,56 @@ __device__ __forceinline__ void loadElem(const int* __restrict__ conn, int e, co
     G.V = det * REF;
 }
 
+// Incident-element stream of one lane with look-ahead: element ids are fetched three trips ahead, connectivity two trips
+// ahead, and the nodal records of the NEXT element are prefetched into L1 while the current element is computed, so the
+// n2e -> conn -> record dependent chain is paid once per node instead of once per element.
+template <int DIM, int LPN> struct ElemStream {
+    static constexpr int NPE = DIM + 1;
+    const int* conn;
+    const int* n2e;
+    const double* XA;
+    const double* VA;
+    int pos, end;          // current position in n2e, one past the last
+    int nd[NPE], nd1[NPE], nd2[NPE], e3;
+    __device__ __forceinline__ void ldConn(int e, int (&out)[NPE]) const {
+        if constexpr (DIM == 3) {
+            const int4 q = __ldg(reinterpret_cast<const int4*>(conn + (size_t)e * 4));
+            out[0] = q.x, out[1] = q.y, out[2] = q.z, out[3] = q.w;
+        } else {
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) out[m] = __ldg(conn + (size_t)e * NPE + m);
+        }
+    }
+    __device__ __forceinline__ void init(const int* c, const int* l, const double* xa, const double* va, int first, int last) {
+        conn = c, n2e = l, XA = xa, VA = va, pos = first, end = last;
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) nd[m] = nd1[m] = nd2[m] = 0;
+        e3 = 0;
+        if (pos < end) ldConn(__ldg(n2e + pos), nd);
+        if (pos + LPN < end) ldConn(__ldg(n2e + pos + LPN), nd1);
+        if (pos + 2 * LPN < end) ldConn(__ldg(n2e + pos + 2 * LPN), nd2);
+        if (pos + 3 * LPN < end) e3 = __ldg(n2e + pos + 3 * LPN);
+    }
+    __device__ __forceinline__ bool valid() const { return pos < end; }
+    // call at the top of a trip: warm L1 with the records of the next element
+    __device__ __forceinline__ void prefetchNext() const {
+        if (pos + LPN < end) {
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(XA + (size_t)nd1[m] * 4));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(VA + (size_t)nd1[m] * 4));
+            }
+        }
+    }
+    __device__ __forceinline__ void advance() {
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) nd[m] = nd1[m], nd1[m] = nd2[m];
+        pos += LPN;
+        if (pos + 2 * LPN < end) ldConn(e3, nd2);
+        if (pos + 3 * LPN < end) e3 = __ldg(n2e + pos + 3 * LPN);
+    }
+};
+
 template <int N> __device__ __forceinline__ double pick(const double (&a)[N], int idx) {
     double t = a[0];
 #pragma unroll
@@ -130,6 +175,7 @@ struct WcArgs {
     const double* dirVal4;
     int nNodes;
     double dt, mu, K0, K0p, rhoStar, body[3];
+    const double* dtPtr;  // if non-null the time step is read from the device (pfem_wc_run)
     int meduri;
 };
 
@@ -142,15 +188,18 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont(const WcArgs a, const dou
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = t / LPN, sub = t % LPN;
     const bool valid = i < a.nNodes;
+    const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
     double m = 0, F0 = 0;
     if (valid) {
         const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
-        for (int k = sub; k < ne; k += LPN) {
-            const int e = a.n2e[eb + k];
-            int nd[NPE];
+        ElemStream<DIM, LPN> es;
+        es.init(a.conn, a.n2e, X4, V4, eb + sub, eb + ne);
+        for (; es.valid(); es.advance()) {
+            es.prefetchNext();
+            const int(&nd)[NPE] = es.nd;
             double P[NPE], vel[NPE][DIM], rho[NPE];
             ElemGeo<DIM> G;
-            loadElem<DIM>(a.conn, e, X4, V4, nd, P, vel, rho, G);
+            loadElem<DIM>(X4, V4, nd, P, vel, rho, G);
             int li = 0;
             double sumP = 0, divv = 0;
 #pragma unroll
@@ -163,7 +212,7 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont(const WcArgs a, const dou
             const double pi = pick<NPE>(P, li);
             const double si = a.K0 / NPE + a.K0p * PHI * (pi + sumP);       // sum_g w (K0 + K0' N.p) N_i
             const double stab = a.meduri ? G.V * PHI * (pi + sumP) : (G.V / NPE) * pi;  // Me*P | MeLumped*P
-            F0 += -a.dt * G.V * si * divv + stab;
+            F0 += -dtStep * G.V * si * divv + stab;
             m += G.V / NPE;                                                  // lump2(M), f = 1
         }
     }
@@ -188,23 +237,26 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont(const WcArgs a, const dou
 // momentum (MomEquation.inl:229-302, 305-374, 216-222)
 template <int DIM, int LPN, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
-                                                double* __restrict__ V4out, double* __restrict__ A4out) {
+                                                double* __restrict__ V4out, double* __restrict__ A4out, double* __restrict__ X4out) {
     constexpr int NPE = DIM + 1;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = t / LPN, sub = t % LPN;
     const bool valid = i < a.nNodes;
+    const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
     double M = 0, F[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) F[c] = 0;
     if (valid) {
         const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
-        for (int k = sub; k < ne; k += LPN) {
-            const int e = a.n2e[eb + k];
-            int nd[NPE];
+        ElemStream<DIM, LPN> es;
+        es.init(a.conn, a.n2e, X4, V4, eb + sub, eb + ne);
+        for (; es.valid(); es.advance()) {
+            es.prefetchNext();
+            const int(&nd)[NPE] = es.nd;
             double P[NPE], vel[NPE][DIM], rho[NPE];
             ElemGeo<DIM> G;
-            loadElem<DIM>(a.conn, e, X4, V4, nd, P, vel, rho, G);
+            loadElem<DIM>(X4, V4, nd, P, vel, rho, G);
             int li = 0;
             double sumP = 0, sumR = 0;
             double Gm[DIM][DIM];  // G_ac = sum_j v_{j,a} g[c][j]
@@ -264,10 +316,12 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const doub
                 iv = 1.0;
             }
             acc[c] = iv * f;
-            vn[c] = vp[c] + 0.5 * a.dt * acc[c];
+            vn[c] = vp[c] + 0.5 * dtStep * acc[c];
         }
         st4(V4out + (size_t)i * 4, vn[0], vn[1], vn[2], vp[3]);
         st4(A4out + (size_t)i * 4, acc[0], acc[1], acc[2], 0.0);
+        const double* xq = X4 + (size_t)i * 4;
+        st4(X4out + (size_t)i * 4, xq[0], xq[1], xq[2], xq[3]);  // (x, p_new) becomes the current record: no buffer swap
     }
 }
 
@@ -291,6 +345,7 @@ struct WcArgsS {
     const double* dirVal4;
     int nNodes, nbcap;
     double dt, mu, K0, K0p, rhoStar, body[3];
+    const double* dtPtr;  // if non-null the time step is read from the device (pfem_wc_run)
     int meduri;
 };
 template <int DIM>
@@ -384,6 +439,7 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont_s(const WcArgsS a, const 
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = t / LPN, sub = t % LPN;
     const bool valid = i < a.nNodes;
+    const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
     WcRec* recs = reinterpret_cast<WcRec*>(smemWc) + (size_t)(threadIdx.x / LPN) * a.nbcap;
     stageRecords<LPN>(a, i, sub, valid, X4, V4, recs);
     double m = 0, F0 = 0;
@@ -407,7 +463,7 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont_s(const WcArgsS a, const 
             const double pi = pick<NPE>(P, li);
             const double sI = a.K0 / NPE + a.K0p * PHI * (pi + sumP);
             const double stab = a.meduri ? G.V * PHI * (pi + sumP) : (G.V / NPE) * pi;
-            F0 += -a.dt * G.V * sI * divv + stab;
+            F0 += -dtStep * G.V * sI * divv + stab;
             m += G.V / NPE;
         }
     }
@@ -431,13 +487,14 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont_s(const WcArgsS a, const 
 template <int DIM, int LPN, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_wc_mom_s(const WcArgsS a, const double* __restrict__ X4,
                                                         const double* __restrict__ V4, double* __restrict__ V4out,
-                                                        double* __restrict__ A4out) {
+                                                        double* __restrict__ A4out, double* __restrict__ X4out) {
     constexpr int NPE = DIM + 1;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
     extern __shared__ __align__(16) unsigned char smemWc[];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = t / LPN, sub = t % LPN;
     const bool valid = i < a.nNodes;
+    const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
     WcRec* recs = reinterpret_cast<WcRec*>(smemWc) + (size_t)(threadIdx.x / LPN) * a.nbcap;
     stageRecords<LPN>(a, i, sub, valid, X4, V4, recs);
     double M = 0, F[DIM];
@@ -510,10 +567,11 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom_s(const WcArgsS a, const d
                 iv = 1.0;
             }
             acc[c] = iv * f;
-            vn[c] = R.v[c] + 0.5 * a.dt * acc[c];
+            vn[c] = R.v[c] + 0.5 * dtStep * acc[c];
         }
         st4(V4out + (size_t)i * 4, vn[0], vn[1], vn[2], R.v[3]);
         st4(A4out + (size_t)i * 4, acc[0], acc[1], acc[2], 0.0);
+        st4(X4out + (size_t)i * 4, R.x[0], R.x[1], R.x[2], R.x[3]);
     }
 }
 
@@ -617,90 +675,120 @@ __global__ void k_min_final(const double* __restrict__ partial, int n, double* _
     }
 }
 
-WcArgs makeArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
+// chained steps: dtDev[0] = current dt, dtDev[1] = elapsed simulated time, dtDev[2] = NaN flag.  Runs after k_wc_dt of
+// step n: elapsed += dt_n ; dt_{n+1} = min(sqrt(min_e ...), maxDT)   (Solver.cpp:228, Problem::updateTime)
+__global__ void k_dt_chain(const double* __restrict__ partial, int n, double maxDT, double* __restrict__ dtDev) {
+    double best = 1.7976931348623157e308;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const double o = partial[k];
+        best = (o < best || o != o) ? o : best;
+    }
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = (other < best || other != other) ? other : best;
+    }
+    if (lane == 0) sh[w] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            const double o = sh[k];
+            best = (o < best || o != o) ? o : best;
+        }
+        const double dtNew = fmin(sqrt(best), maxDT);
+        dtDev[1] += dtDev[0];
+        if (dtNew != dtNew) dtDev[2] = 1.0;
+        dtDev[0] = dtNew;
+    }
+}
+
+// kick + continuity + momentum of one step on the context's stream; dtPtr != null: dt is read from the device
+void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* dtPtr) {
+    static const int cfg = getenv("PFEM_WC_CFG") ? atoi(getenv("PFEM_WC_CFG")) : 6;
     WcArgs a;
     a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.flags = c->flags.p;
     a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p, a.nNodes = c->nRows;  // rows = owned nodes
-    a.dt = dt, a.mu = p.mu, a.K0 = p.K0, a.K0p = p.K0p, a.rhoStar = p.rhoStar;
-    for (int d = 0; d < 3; ++d) a.body[d] = p.bodyForce[d];
-    a.meduri = p.meduri;
-    return a;
-}
-
-}  // namespace
-
-void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
-    PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, "wc_step: topology/positions missing");
-    PFEM_REQUIRE(dt > 0 && p.K0 > 0 && p.K0p != 0, PFEM_ERR_INVALID, "wc_step: dt, K0 must be positive and K0p non-zero");
-    const size_t n4 = (size_t)c->nNodes * 4;
-    c->X4b.reserve(n4);
-    c->V4b.reserve(n4);
-    const WcArgs a = makeArgs(c, p, dt);
-    static const int cfg = getenv("PFEM_WC_CFG") ? atoi(getenv("PFEM_WC_CFG")) : 6;
-    {
-        PhaseScope ph(c, "Update solutions");
-        k_wc_kick_move<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->nNodes, c->dim, dt, c->flags.p, c->X4.p, c->V4.p, c->A4.p);
-        LAUNCH_CHECK(c);
-    }
+    a.dt = dt, a.dtPtr = dtPtr, a.mu = p.mu, a.K0 = p.K0, a.K0p = p.K0p, a.rhoStar = p.rhoStar, a.meduri = p.meduri;
     WcArgsS as;
     as.n2ePtr = c->n2ePtr.p, as.n2eSlots = c->n2eSlots.p, as.nbrPtr = c->nbrPtr.p, as.nbr = c->nbr.p, as.diagSlot = c->diagSlot.p;
     as.flags = c->flags.p, as.dirMask = c->dirMask.p, as.dirVal4 = c->dirVal4.p, as.nNodes = c->nRows;
     as.nbcap = std::max(c->maxNb, 1);
-    as.dt = dt, as.mu = p.mu, as.K0 = p.K0, as.K0p = p.K0p, as.rhoStar = p.rhoStar, as.meduri = p.meduri;
-    for (int d = 0; d < 3; ++d) as.body[d] = p.bodyForce[d];
-#define PFEM_WC_LAUNCH_S(KERNEL, LPN_, MINB_, ...)                                                                  \
+    as.dt = dt, as.dtPtr = dtPtr, as.mu = p.mu, as.K0 = p.K0, as.K0p = p.K0p, as.rhoStar = p.rhoStar, as.meduri = p.meduri;
+    for (int d = 0; d < 3; ++d) a.body[d] = as.body[d] = p.bodyForce[d];
+    {
+        PhaseScope ph(c, "Update solutions");
+        k_wc_kick_move<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->nNodes, c->dim, dt, dtPtr, c->flags.p, c->X4.p, c->V4.p,
+                                                                     c->A4.p);
+        LAUNCH_CHECK(c);
+    }
+#define PFEM_WC_LAUNCH_S(KERNEL, LPN_, ...)                                                                         \
     do {                                                                                                            \
         const int grid_ = divUp((int64_t)c->nRows * LPN_, 256);                                                     \
         const size_t smem_ = (size_t)(256 / LPN_) * as.nbcap * sizeof(WcRec);                                       \
         PFEM_REQUIRE(smem_ <= 200 * 1024, PFEM_ERR_INVALID, "wc_step: node valence too large for shared memory");   \
         if (c->dim == 2) {                                                                                          \
             if (smem_ > 48 * 1024)                                                                                  \
-                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<2, LPN_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
-            KERNEL<2, LPN_, MINB_><<<grid_, 256, smem_, c->stream>>>(as, __VA_ARGS__);                               \
+                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<2, LPN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+            KERNEL<2, LPN_, 2><<<grid_, 256, smem_, c->stream>>>(as, __VA_ARGS__);                                   \
         } else {                                                                                                    \
             if (smem_ > 48 * 1024)                                                                                  \
-                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<3, LPN_, MINB_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
-            KERNEL<3, LPN_, MINB_><<<grid_, 256, smem_, c->stream>>>(as, __VA_ARGS__);                               \
+                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<3, LPN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+            KERNEL<3, LPN_, 2><<<grid_, 256, smem_, c->stream>>>(as, __VA_ARGS__);                                   \
         }                                                                                                           \
     } while (0)
-#define PFEM_WC_LAUNCH(KERNEL, LPN_, MINB_, ...)                                                  \
-    do {                                                                                          \
-        const int grid_ = divUp((int64_t)c->nRows * LPN_, 256);                                   \
-        if (c->dim == 2) KERNEL<2, LPN_, MINB_><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);      \
-        else KERNEL<3, LPN_, MINB_><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);                  \
+#define PFEM_WC_LAUNCH(KERNEL, LPN_, ...)                                                     \
+    do {                                                                                      \
+        const int grid_ = divUp((int64_t)c->nRows * LPN_, 256);                               \
+        if (c->dim == 2) KERNEL<2, LPN_, 2><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);      \
+        else KERNEL<3, LPN_, 2><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);                  \
     } while (0)
+    // PFEM_WC_CFG: 6 (default) direct gathers, 4 lanes per node | 0: 8 lanes per node | 7: staged records, 8 lanes per node
     {
         PhaseScope ph(c, "Solving continuity eq");
-        if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, 2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else if (cfg == 8) PFEM_WC_LAUNCH_S(k_wc_cont_s, 4, 2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else if (cfg == 9) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else if (cfg == 1) PFEM_WC_LAUNCH(k_wc_cont, 8, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else if (cfg == 2) PFEM_WC_LAUNCH(k_wc_cont, 8, 4, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else if (cfg == 3) PFEM_WC_LAUNCH(k_wc_cont, 4, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else if (cfg == 4) PFEM_WC_LAUNCH(k_wc_cont, 2, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else if (cfg == 5) PFEM_WC_LAUNCH(k_wc_cont, 1, 3, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else if (cfg == 6) PFEM_WC_LAUNCH(k_wc_cont, 4, 2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        else PFEM_WC_LAUNCH(k_wc_cont, 8, 2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else if (cfg == 0) PFEM_WC_LAUNCH(k_wc_cont, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        else PFEM_WC_LAUNCH(k_wc_cont, 4, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         LAUNCH_CHECK(c);
         if (c->nRanks > 1) commHalo(c, c->X4b.p, c->V4b.p, 4);  // (x, p_new) and (v_half, rho_new) of interface nodes
     }
     {
         PhaseScope ph(c, "Solving momentum eq");
-        if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_mom_s, 8, 2, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else if (cfg == 8) PFEM_WC_LAUNCH_S(k_wc_mom_s, 4, 2, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else if (cfg == 9) PFEM_WC_LAUNCH_S(k_wc_mom_s, 8, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else if (cfg == 1) PFEM_WC_LAUNCH(k_wc_mom, 8, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else if (cfg == 2) PFEM_WC_LAUNCH(k_wc_mom, 8, 4, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else if (cfg == 3) PFEM_WC_LAUNCH(k_wc_mom, 4, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else if (cfg == 4) PFEM_WC_LAUNCH(k_wc_mom, 2, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else if (cfg == 5) PFEM_WC_LAUNCH(k_wc_mom, 1, 3, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else if (cfg == 6) PFEM_WC_LAUNCH(k_wc_mom, 4, 2, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
-        else PFEM_WC_LAUNCH(k_wc_mom, 8, 2, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p);
+        if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_mom_s, 8, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
+        else if (cfg == 0) PFEM_WC_LAUNCH(k_wc_mom, 8, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
+        else PFEM_WC_LAUNCH(k_wc_mom, 4, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
         LAUNCH_CHECK(c);
-        if (c->nRanks > 1) commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
+        if (c->nRanks > 1) {
+            commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
+            const size_t g0 = (size_t)c->nRows * 4, gn = (size_t)(c->nNodes - c->nRows) * 4;  // ghosts: (x, p_new) from X4b
+            if (gn) CUDA_CHECK(cudaMemcpyAsync(c->X4.p + g0, c->X4b.p + g0, gn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        }
     }
-    std::swap(c->X4.p, c->X4b.p);  // X4b holds (x, p_new): make it current
-    std::swap(c->X4.cap, c->X4b.cap);
+}
+
+void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int grid) {
+    const double sc2 = securityCoeff * securityCoeff;
+    if (c->dim == 2)
+        k_wc_dt<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
+    else
+        k_wc_dt<3><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
+    LAUNCH_CHECK(c);
+}
+
+void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
+    PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, "wc_step: topology/positions missing");
+    PFEM_REQUIRE(dt > 0 && p.K0 > 0 && p.K0p != 0, PFEM_ERR_INVALID, "wc_step: dt, K0 must be positive and K0p non-zero");
+    const size_t n4 = (size_t)c->nNodes * 4;
+    c->X4b.reserve(n4);
+    c->V4b.reserve(n4);
+}
+
+}  // namespace
+
+void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
+    checkStepArgs(c, p, dt);
+    launchStep(c, p, dt, nullptr);
 }
 
 int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dtOut) {
@@ -711,12 +799,7 @@ int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double 
     c->dtPartial.reserve(grid + 8);
     c->scal.reserve(SC_COUNT);
     if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
-    const double sc2 = securityCoeff * securityCoeff;
-    if (c->dim == 2)
-        k_wc_dt<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
-    else
-        k_wc_dt<3><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
-    LAUNCH_CHECK(c);
+    launchDt(c, p, securityCoeff, grid);
     k_min_final<<<1, 256, 0, c->stream>>>(c->dtPartial.p, grid, c->scal.p + SC_COUNT - 1);
     LAUNCH_CHECK(c);
     if (c->nRanks > 1) commAllReduceMin(c, c->scal.p + SC_COUNT - 1);
@@ -726,4 +809,57 @@ int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double 
     const double dt = fmin(sqrt(ts), maxDT);  // Solver.cpp:228
     *dtOut = dt;
     return (dt != dt || ts != ts) ? PFEM_NAN : PFEM_OK;
+}
+
+// nSteps explicit steps with the CFL time step recomputed ON THE DEVICE after every step (computeNextDT) and no host round
+// trip in between: the 5 launches of a step (kick, continuity, momentum, CFL, dt chain) are captured once into a CUDA
+// graph and replayed -- the small reference configurations (1-14 k elements, ~4e5 steps) are launch-latency bound.
+int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff, double maxDT, double* dtInOut, double* elapsed) {
+    PFEM_REQUIRE(dtInOut && nSteps >= 0, PFEM_ERR_INVALID, "wc_run: bad arguments");
+    checkStepArgs(c, p, *dtInOut);
+    PFEM_REQUIRE(c->nRanks == 1, PFEM_ERR_STATE, "wc_run: single-GPU contexts only (use pfem_wc_step + pfem_wc_next_dt when sharded)");
+    const int grid = std::max(1, std::min(c->smCount * 8, divUp(c->nElems, 256)));
+    c->dtPartial.reserve(grid + 8);
+    c->scal.reserve(SC_COUNT);
+    if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
+    double* dtDev = c->scal.p + SC_COUNT - 4;  // [dt, elapsed, nan]
+    c->hScal[0] = *dtInOut, c->hScal[1] = 0.0, c->hScal[2] = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(dtDev, c->hScal, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const bool wasProfiling = c->profiling;
+    c->profiling = false;  // no event records inside a capture
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    try {
+        CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        launchStep(c, p, *dtInOut, dtDev);
+        launchDt(c, p, securityCoeff, grid);
+        k_dt_chain<<<1, 256, 0, c->stream>>>(c->dtPartial.p, grid, maxDT, dtDev);
+        LAUNCH_CHECK(c);
+        CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));
+        CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+        c->launches -= 5;  // the capture itself launched nothing
+        for (int s = 0; s < nSteps; ++s) {
+            CUDA_CHECK(cudaGraphLaunch(exec, c->stream));
+            c->launches += 5;
+        }
+        CUDA_CHECK(cudaMemcpyAsync(c->hScal, dtDev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    } catch (...) {
+        cudaStreamCaptureStatus st;
+        if (cudaStreamIsCapturing(c->stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone) {
+            cudaGraph_t g2 = nullptr;
+            cudaStreamEndCapture(c->stream, &g2);
+            if (g2) cudaGraphDestroy(g2);
+        }
+        if (exec) cudaGraphExecDestroy(exec);
+        if (graph) cudaGraphDestroy(graph);
+        c->profiling = wasProfiling;
+        throw;
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    c->profiling = wasProfiling;
+    *dtInOut = c->hScal[0];
+    if (elapsed) *elapsed = c->hScal[1];
+    return (c->hScal[2] != 0.0 || c->hScal[0] != c->hScal[0]) ? PFEM_NAN : PFEM_OK;
 }

@@ -75,3 +75,32 @@ def test_state_roundtrip():
         assert (ctx.get_states(0, 6) == q).all()
         assert (ctx.get_states(2, 2) == q[2 * mesh.n_nodes: 4 * mesh.n_nodes]).all()
         assert (ctx.get_positions() == mesh.x).all()
+
+
+@pytest.mark.parametrize("dim,n", [(2, 20), (3, 6)])
+def test_wc_run_equals_step_loop(dim, n):
+    """pfem_wc_run (device-chained CFL dt, one CUDA graph per step) == the host loop of wc_step + wc_next_dt, bit for bit."""
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.01)
+    st = mg.wc_state(mesh)
+    W = mg.WC_PARAMS
+    g = mg.gravity(dim)
+    n_steps = 7
+    with PfemContext(dim, 0) as ctx:
+        ctx.set_mesh(mesh)
+        ctx.set_states(0, _pack(st))
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+        dt = dt0 = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+        elapsed = 0.0
+        for _ in range(n_steps):
+            ctx.wc_step(wp, dt)
+            elapsed += dt
+            dt = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+        ref_states, ref_x, ref_dt = ctx.get_states(0, 2 * dim + 2), ctx.get_positions(), dt
+    with PfemContext(dim, 0) as ctx:
+        ctx.set_mesh(mesh)
+        ctx.set_states(0, _pack(st))
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+        dt_next, el = ctx.wc_run(wp, n_steps, W["securityCoeff"], 1e-3, dt0)
+        assert (ctx.get_states(0, 2 * dim + 2) == ref_states).all()
+        assert (ctx.get_positions() == ref_x).all()
+    assert dt_next == ref_dt and abs(el - elapsed) <= 1e-15 * elapsed
