@@ -60,12 +60,18 @@ typedef struct pfem_pspg_params {
     double bodyForce[3];
 } pfem_pspg_params;
 
+/* continuity-equation variant = the reference's WCompNewton solver id (ContEquation.inl:38-43) */
+#define PFEM_WC_CDS_DPDT 0   /* "CDS_dpdt":   dp/dt form, rho from Tait-Murnaghan (ContEquation.inl:353-413)          */
+#define PFEM_WC_CDS_DRHODT 1 /* "CDS_drhodt": d(rho)/dt form, p from Tait-Murnaghan (ContEquation.inl:234-301)        */
+#define PFEM_WC_CDS_RHO 2    /* "CDS_rho":    mass conservation M(x_new) rho = M(x_old) rho_old (:196-232, 234-301)   */
+
 /* ContEqWCompNewton / MomEqWCompNewton scalars (ContEquation.inl:26-37; MomEquation.inl:28-29, 149-153);
- * meduri != 0  <=>  stabilization == "Meduri" (ContEquation.inl:387-390) */
+ * meduri != 0  <=>  stabilization == "Meduri" (ContEquation.inl:387-390); eqType: PFEM_WC_CDS_* */
 typedef struct pfem_wc_params {
     double mu, K0, K0p, rhoStar;
     double bodyForce[3];
     int32_t meduri;
+    int32_t eqType;
 } pfem_wc_params;
 
 typedef struct pfem_info {

@@ -162,10 +162,18 @@ def pspg_assemble_dense(mesh, Ae, be, q_prev, dt, body, apply_bc=True):
     return A, b
 
 
-def wc_step(mesh, x, st, mu, K0, K0p, rho_star, body, dt, meduri=True):
-    """One explicit step: WC/Solver.cpp:236-263, ContEquation.inl:123-148, 334-413, MomEquation.inl:201-374."""
+def wc_step(mesh, x, st, mu, K0, K0p, rho_star, body, dt, meduri=True, eq_type="CDS_dpdt"):
+    """One explicit step: WC/Solver.cpp:236-263, ContEquation.inl:123-301, 334-413, MomEquation.inl:201-374."""
     dim, npe, nn = mesh.dim, mesh.dim + 1, mesh.n_nodes
     body = np.asarray(body[:dim], dtype=float)
+    F0pre = None
+    if eq_type == "CDS_rho":    # preCompute() on the configuration before the move, ContEquation.inl:196-232
+        mb0 = MatrixBuilder(dim)
+        c0 = x.reshape(dim, nn).T
+        F0pre = np.zeros(nn)
+        for en in mesh.conn:
+            _, detJ, _ = mb0.geometry(c0[en])
+            np.add.at(F0pre, en, mb0.getM(detJ, lambda N: 1.0) @ st["rho"][en])
     v = st["v"] + 0.5 * dt * st["acc"]
     x = x.copy()
     fixed = (mesh.flags & 4) != 0
@@ -182,20 +190,41 @@ def wc_step(mesh, x, st, mu, K0, K0p, rho_star, body, dt, meduri=True):
     # continuity
     p = st["p"]
     invM = np.zeros(nn); F0 = np.zeros(nn)
-    for en in mesh.conn:
-        _, detJ, invJ = mb.geometry(c[en])
-        Me = mb.getM(detJ, lambda N: 1.0)
-        MeL = Me.sum(axis=1)
-        P = p[en]; V = _elem_vec(v, en, nn, dim)
-        g = mb.gradN(invJ); B = mb.B(g)
-        D = mb.getD(detJ, B, lambda N: K0 + K0p * (N @ P).item())
-        F0e = -dt * D @ V + (Me @ P if meduri else MeL * P)
-        np.add.at(invM, en, MeL); np.add.at(F0, en, F0e)
-    with np.errstate(divide="ignore"):
-        invM = 1 / invM
-    F0[free] = 0; invM[free] = 1
-    p = invM * F0
-    rho = np.power((K0p / K0) * p + 1, 1 / K0p) * rho_star
+    if eq_type == "CDS_dpdt":
+        for en in mesh.conn:
+            _, detJ, invJ = mb.geometry(c[en])
+            Me = mb.getM(detJ, lambda N: 1.0)
+            MeL = Me.sum(axis=1)
+            P = p[en]; V = _elem_vec(v, en, nn, dim)
+            g = mb.gradN(invJ); B = mb.B(g)
+            D = mb.getD(detJ, B, lambda N: K0 + K0p * (N @ P).item())
+            F0e = -dt * D @ V + (Me @ P if meduri else MeL * P)
+            np.add.at(invM, en, MeL); np.add.at(F0, en, F0e)
+        with np.errstate(divide="ignore"):
+            invM = 1 / invM
+        F0[free] = 0; invM[free] = 1
+        p = invM * F0
+        rho = np.power((K0p / K0) * p + 1, 1 / K0p) * rho_star
+    else:
+        rho0 = st["rho"]
+        for en in mesh.conn:
+            _, detJ, invJ = mb.geometry(c[en])
+            Me = mb.getM(detJ, lambda N: 1.0)
+            MeL = Me.sum(axis=1)
+            np.add.at(invM, en, MeL)
+            if eq_type == "CDS_drhodt":
+                R = rho0[en]; V = _elem_vec(v, en, nn, dim)
+                g = mb.gradN(invJ); B = mb.B(g)
+                D = mb.getD(detJ, B, lambda N: (N @ R).item())
+                np.add.at(F0, en, -dt * D @ V + (Me @ R if meduri else MeL * R))
+        if eq_type == "CDS_rho":
+            F0 = F0pre
+        with np.errstate(divide="ignore"):
+            invM = 1 / invM
+        fs = free | ((mesh.flags & 8) != 0)
+        F0[fs] = rho_star; invM[fs] = 1
+        rho = invM * F0
+        p = (K0 / K0p) * (np.power(rho / rho_star, K0p) - 1)
     # momentum
     Md = np.zeros(dim * nn); F = np.zeros(dim * nn)
     for en in mesh.conn:

@@ -80,10 +80,14 @@ def pspg_param_array(rho, mu, dt, body_force):
     return np.array([rho, mu, dt, bf[0], bf[1], bf[2]], dtype=np.float64)
 
 
-def wc_param_array(mu, K0, K0p, rhoStar, body_force, meduri=True):
+EQ_TYPES = {"CDS_dpdt": 0, "CDS_drhodt": 1, "CDS_rho": 2}   # solver ids, ContEquation.inl:38-43
+
+
+def wc_param_array(mu, K0, K0p, rhoStar, body_force, meduri=True, eq_type="CDS_dpdt"):
     bf = np.zeros(3)
     bf[: len(body_force)] = body_force
-    return np.array([mu, K0, K0p, rhoStar, bf[0], bf[1], bf[2], 1.0 if meduri else 0.0], dtype=np.float64)
+    return np.array([mu, K0, K0p, rhoStar, bf[0], bf[1], bf[2], 1.0 if meduri else 0.0,
+                     float(EQ_TYPES[eq_type])], dtype=np.float64)
 
 
 def pspg_elements(mesh, vcur, q_prev, params):

@@ -558,7 +558,12 @@ void pspgApplyBC(int64_t nNodes, const uint8_t* flags, const uint8_t* dirMask, c
 struct WcParams {
     double mu, K0, K0p, rhoStar, bodyForce[3];
     int meduri;
+    int eqType;  // 0 CDS_dpdt, 1 CDS_drhodt, 2 CDS_rho  (ContEquation.inl:38-43)
 };
+
+inline WcParams wcParamsFromArray(const double* a) {
+    return WcParams{a[0], a[1], a[2], a[3], {a[4], a[5], a[6]}, (int)a[7], (int)a[8]};
+}
 
 // ------------------------------------------------------------------------------------
 // Mesh::updateNodesPosition.  srcs/mesh/Mesh.cpp:1101-1137: x += delta unless m_isFixed.
@@ -629,6 +634,96 @@ void wcCont(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, 
     for (int64_t n = 0; n < nNodes; ++n) {
         p[n] = invM[n] * F0[n];
         rho[n] = std::pow((P.K0p / P.K0) * p[n] + 1, 1 / P.K0p) * P.rhoStar;
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// ContEqWCompNewton (CDS_rho / CDS_drhodt).  WCompNewton/ContEquation.inl:196-232
+// (m_buildF0, called by preCompute :171-175 on the configuration *before* the move),
+// :234-301 (m_buildSystem), :177-194 (BC: free or free-surface nodes get rho*),
+// :149-165 (solve), :303-316 (Tait-Murnaghan p(rho)); factors :75-97 (M: 1, D: N.rho_e).
+// ------------------------------------------------------------------------------------
+template <int DIM>
+void wcBuildF0(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const double* rho, double* F0) {
+    constexpr int NPE = DIM + 1, NS = MB<DIM>::NS;
+    MB<DIM> mb;
+    for (int i = 0; i < NS; ++i) mb.m[i] = (i < DIM) ? 1.0 : 0.0;
+    std::vector<double> F0e((size_t)nElm * NPE);
+#pragma omp parallel for default(shared)
+    for (int64_t elm = 0; elm < nElm; ++elm) {
+        const int64_t* en = conn + elm * NPE;
+        Geo<DIM> G;
+        computeGeo<DIM>(x, nNodes, en, G);
+        double Me[NPE][NPE];
+        mb.getM(G, [](const double*) { return 1.0; }, Me);
+        for (int i = 0; i < NPE; ++i) {
+            double s = 0;
+            for (int j = 0; j < NPE; ++j) s += Me[i][j] * rho[en[j]];
+            F0e[elm * NPE + i] = s;
+        }
+    }
+    for (int64_t n = 0; n < nNodes; ++n) F0[n] = 0;
+    for (int64_t elm = 0; elm < nElm; ++elm)
+        for (int i = 0; i < NPE; ++i) F0[conn[elm * NPE + i]] += F0e[elm * NPE + i];
+}
+
+template <int DIM>
+void wcContRho(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const uint8_t* flags,
+               const double* v, double* p, double* rho, const WcParams& P, double dt, std::vector<double>& F0) {
+    constexpr int NPE = DIM + 1, ND = DIM * NPE, NS = MB<DIM>::NS;
+    MB<DIM> mb;
+    for (int i = 0; i < NS; ++i) mb.m[i] = (i < DIM) ? 1.0 : 0.0;
+    const bool drhodt = P.eqType == 1;
+    std::vector<double> MeL((size_t)nElm * NPE), F0e(drhodt ? (size_t)nElm * NPE : 0);
+#pragma omp parallel for default(shared)
+    for (int64_t elm = 0; elm < nElm; ++elm) {
+        const int64_t* en = conn + elm * NPE;
+        Geo<DIM> G;
+        computeGeo<DIM>(x, nNodes, en, G);
+        double Me[NPE][NPE];
+        mb.getM(G, [](const double*) { return 1.0; }, Me);
+        double lumped[NPE];
+        for (int i = 0; i < NPE; ++i) {
+            lumped[i] = 0;
+            for (int j = 0; j < NPE; ++j) lumped[i] += Me[i][j];
+            MeL[elm * NPE + i] = lumped[i];
+        }
+        if (!drhodt) continue;
+        double Re[NPE], V[ND];
+        for (int k = 0; k < NPE; ++k) Re[k] = rho[en[k]];
+        for (int d = 0; d < DIM; ++d)
+            for (int k = 0; k < NPE; ++k) V[d * NPE + k] = v[en[k] + (int64_t)d * nNodes];
+        double g[DIM][NPE], B[NS][ND], D[NPE][ND];
+        MB<DIM>::gradN(G, g);
+        MB<DIM>::Bmat(g, B);
+        mb.getD(G, B, [&](const double* N) { return dotN<DIM>(N, Re); }, D);
+        for (int i = 0; i < NPE; ++i) {
+            double a = 0;
+            for (int c = 0; c < ND; ++c) a += (-dt * D[i][c]) * V[c];
+            double s = 0;
+            if (P.meduri)  // "!= Stab::None", :268-271
+                for (int j = 0; j < NPE; ++j) s += Me[i][j] * Re[j];
+            else
+                s = lumped[i] * Re[i];
+            F0e[elm * NPE + i] = a + s;
+        }
+    }
+    std::vector<double> invM(nNodes, 0.0);
+    if (drhodt) F0.assign(nNodes, 0.0);
+    for (int64_t elm = 0; elm < nElm; ++elm)
+        for (int i = 0; i < NPE; ++i) {
+            invM[conn[elm * NPE + i]] += MeL[elm * NPE + i];
+            if (drhodt) F0[conn[elm * NPE + i]] += F0e[elm * NPE + i];
+        }
+    for (int64_t n = 0; n < nNodes; ++n) invM[n] = 1 / invM[n];
+    for (int64_t n = 0; n < nNodes; ++n)
+        if (flags[n] & (F_FREE | F_FS)) {
+            F0[n] = P.rhoStar;
+            invM[n] = 1;
+        }
+    for (int64_t n = 0; n < nNodes; ++n) {
+        rho[n] = invM[n] * F0[n];
+        p[n] = (P.K0 / P.K0p) * (std::pow(rho[n] / P.rhoStar, P.K0p) - 1);
     }
 }
 
@@ -874,9 +969,18 @@ void oracle_move_positions(int dim, int64_t nNodes, const uint8_t* flags, const 
 int oracle_wc_step(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, double* x, const uint8_t* flags,
                    const uint8_t* dirMask, const double* dirVal, double* v, double* acc, double* p, double* rho,
                    const double* params, double dt) {
-    WcParams P{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}, (int)params[7]};
+    WcParams P = wcParamsFromArray(params);
     const int64_t nv = (int64_t)dim * nNodes;
-    std::vector<double> delta(nv);
+    std::vector<double> delta(nv), F0;
+    if (dim != 2 && dim != 3) return -1;
+    // preCompute() before the move (Solver.cpp:244-246); only CDS_rho does anything there.
+    if (P.eqType == 2) {
+        F0.resize(nNodes);
+        if (dim == 2)
+            wcBuildF0<2>(nNodes, nElm, conn, x, rho, F0.data());
+        else
+            wcBuildF0<3>(nNodes, nElm, conn, x, rho, F0.data());
+    }
     // qV1half = qVPrev + 0.5*dt*qAccPrev ; states <- v_half ; x += v_half*dt   (Solver.cpp:249-253)
     for (int64_t i = 0; i < nv; ++i) {
         v[i] = v[i] + 0.5 * dt * acc[i];
@@ -884,19 +988,24 @@ int oracle_wc_step(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, d
     }
     movePositions(dim, nNodes, flags, delta.data(), x, x);
     if (dim == 2) {
-        wcCont<2>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt);
+        if (P.eqType == 0)
+            wcCont<2>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt);
+        else
+            wcContRho<2>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt, F0);
         wcMom<2>(nNodes, nElm, conn, x, flags, dirMask, dirVal, v, acc, p, rho, P, dt);
-    } else if (dim == 3) {
-        wcCont<3>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt);
+    } else {
+        if (P.eqType == 0)
+            wcCont<3>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt);
+        else
+            wcContRho<3>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt, F0);
         wcMom<3>(nNodes, nElm, conn, x, flags, dirMask, dirVal, v, acc, p, rho, P, dt);
-    } else
-        return -1;
+    }
     return 0;
 }
 
 double oracle_wc_next_dt(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const double* v,
                          const double* p, const double* rho, const double* params, double securityCoeff, double maxDT) {
-    WcParams P{params[0], params[1], params[2], params[3], {params[4], params[5], params[6]}, (int)params[7]};
+    WcParams P = wcParamsFromArray(params);
     if (dim == 2) return wcNextDt<2>(nNodes, nElm, conn, x, v, p, rho, P, securityCoeff, maxDT);
     return wcNextDt<3>(nNodes, nElm, conn, x, v, p, rho, P, securityCoeff, maxDT);
 }

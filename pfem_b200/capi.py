@@ -29,7 +29,7 @@ class PspgParams(C.Structure):
 
 class WcParams(C.Structure):
     _fields_ = [("mu", C.c_double), ("K0", C.c_double), ("K0p", C.c_double), ("rhoStar", C.c_double),
-                ("bodyForce", C.c_double * 3), ("meduri", C.c_int32)]
+                ("bodyForce", C.c_double * 3), ("meduri", C.c_int32), ("eqType", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -275,11 +275,12 @@ class PfemContext:
 
     # -- weakly compressible --------------------------------------------------------
     @staticmethod
-    def wc_params(mu, K0, K0p, rhoStar, body_force, meduri=True):
+    def wc_params(mu, K0, K0p, rhoStar, body_force, meduri=True, eq_type="CDS_dpdt"):
         p = WcParams(mu, K0, K0p, rhoStar)
         for i, v in enumerate(body_force[:3]):
             p.bodyForce[i] = v
         p.meduri = 1 if meduri else 0
+        p.eqType = {"CDS_dpdt": 0, "CDS_drhodt": 1, "CDS_rho": 2}[eq_type]
         return p
 
     def wc_step(self, params, dt):

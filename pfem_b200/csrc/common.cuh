@@ -134,6 +134,7 @@ struct pfem_ctx {
 
     // ---- explicit step ----
     DevBuf<double> dtPartial;
+    DevBuf<double> wcF0;  // CDS_rho: F0 = sum_e M_e rho_e on the configuration before the move
 
     // ---- multi-GPU ----
     NcclApi* nccl = nullptr;

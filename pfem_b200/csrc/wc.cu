@@ -234,6 +234,68 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont(const WcArgs a, const dou
     }
 }
 
+// continuity in the density forms.  MODE 1: CDS_drhodt (ContEquation.inl:234-301: F0e = -dt D_rho V + M rho | M_lumped rho),
+// MODE 2: CDS_rho (lumped mass on the moved mesh, F0 from the pre-pass), MODE 3: the CDS_rho pre-pass
+// F0 = sum_e M_e rho_e on the configuration before the move (m_buildF0, :196-232).  BC (:177-194): free or
+// free-surface nodes get rho*; p(rho) by Tait-Murnaghan (:303-316).
+template <int DIM, int LPN, int MINB, int MODE>
+__global__ void __launch_bounds__(256, MINB) k_wc_cont_rho(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
+                                                     double* __restrict__ X4n, double* __restrict__ V4n, double* __restrict__ F0pre) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / LPN, sub = t % LPN;
+    const bool valid = i < a.nNodes;
+    const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
+    double m = 0, F0 = 0;
+    if (valid) {
+        const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+        ElemStream<DIM, LPN> es;
+        es.init(a.conn, a.n2e, X4, V4, eb + sub, eb + ne);
+        for (; es.valid(); es.advance()) {
+            es.prefetchNext();
+            const int(&nd)[NPE] = es.nd;
+            double P[NPE], vel[NPE][DIM], rho[NPE];
+            ElemGeo<DIM> G;
+            loadElem<DIM>(X4, V4, nd, P, vel, rho, G);
+            int li = 0;
+            double sumR = 0, divv = 0;
+#pragma unroll
+            for (int q = 0; q < NPE; ++q) {
+                li = (nd[q] == i) ? q : li;
+                sumR += rho[q];
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) divv += G.g[c][q] * vel[q][c];
+            }
+            const double ri = pick<NPE>(rho, li);
+            const double cons = G.V * PHI * (ri + sumR);  // (M_e rho_e)_i == V sum_g w (N.rho) N_i
+            if (MODE == 1) F0 += -dtStep * cons * divv + (a.meduri ? cons : (G.V / NPE) * ri);
+            if (MODE == 3) F0 += cons;
+            m += G.V / NPE;
+        }
+    }
+    m = groupSum<LPN>(m);
+    F0 = groupSum<LPN>(F0);
+    if (valid && sub == 0) {
+        if (MODE == 3) {
+            F0pre[i] = F0;
+            return;
+        }
+        if (MODE == 2) F0 = F0pre[i];
+        double inv = 1.0 / m;
+        if (a.flags[i] & (PFEM_NODE_FREE | PFEM_NODE_FREE_SURFACE)) {
+            F0 = a.rhoStar;
+            inv = 1.0;
+        }
+        const double rho = inv * F0;
+        const double p = (a.K0 / a.K0p) * (pow(rho / a.rhoStar, a.K0p) - 1.0);
+        const double* xp = X4 + (size_t)i * 4;
+        const double* vp = V4 + (size_t)i * 4;
+        st4(X4n + (size_t)i * 4, xp[0], xp[1], xp[2], p);
+        st4(V4n + (size_t)i * 4, vp[0], vp[1], vp[2], rho);
+    }
+}
+
 // momentum (MomEquation.inl:229-302, 305-374, 216-222)
 template <int DIM, int LPN, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
@@ -717,6 +779,17 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
     as.nbcap = std::max(c->maxNb, 1);
     as.dt = dt, as.dtPtr = dtPtr, as.mu = p.mu, as.K0 = p.K0, as.K0p = p.K0p, as.rhoStar = p.rhoStar, as.meduri = p.meduri;
     for (int d = 0; d < 3; ++d) a.body[d] = as.body[d] = p.bodyForce[d];
+#define PFEM_WC_LAUNCH_RHO(MODE_, ...)                                                                    \
+    do {                                                                                                  \
+        const int grid_ = divUp((int64_t)c->nRows * 4, 256);                                              \
+        if (c->dim == 2) k_wc_cont_rho<2, 4, 2, MODE_><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);       \
+        else k_wc_cont_rho<3, 4, 2, MODE_><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);                   \
+    } while (0)
+    if (p.eqType == PFEM_WC_CDS_RHO) {  // ContEqWCompNewton::preCompute, before the kick and the move (Solver.cpp:244-246)
+        PhaseScope ph(c, "Solving continuity eq");
+        PFEM_WC_LAUNCH_RHO(3, c->X4.p, c->V4.p, nullptr, nullptr, c->wcF0.p);
+        LAUNCH_CHECK(c);
+    }
     {
         PhaseScope ph(c, "Update solutions");
         k_wc_kick_move<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->nNodes, c->dim, dt, dtPtr, c->flags.p, c->X4.p, c->V4.p,
@@ -747,7 +820,9 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
     // PFEM_WC_CFG: 6 (default) direct gathers, 4 lanes per node | 0: 8 lanes per node | 7: staged records, 8 lanes per node
     {
         PhaseScope ph(c, "Solving continuity eq");
-        if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+        if (p.eqType == PFEM_WC_CDS_DRHODT) PFEM_WC_LAUNCH_RHO(1, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, nullptr);
+        else if (p.eqType == PFEM_WC_CDS_RHO) PFEM_WC_LAUNCH_RHO(2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcF0.p);
+        else if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         else if (cfg == 0) PFEM_WC_LAUNCH(k_wc_cont, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         else PFEM_WC_LAUNCH(k_wc_cont, 4, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         LAUNCH_CHECK(c);
@@ -779,9 +854,12 @@ void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int gr
 void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, "wc_step: topology/positions missing");
     PFEM_REQUIRE(dt > 0 && p.K0 > 0 && p.K0p != 0, PFEM_ERR_INVALID, "wc_step: dt, K0 must be positive and K0p non-zero");
+    PFEM_REQUIRE(p.eqType >= PFEM_WC_CDS_DPDT && p.eqType <= PFEM_WC_CDS_RHO, PFEM_ERR_INVALID, "wc_step: unknown eqType");
+    PFEM_REQUIRE(p.eqType == PFEM_WC_CDS_DPDT || p.rhoStar > 0, PFEM_ERR_INVALID, "wc_step: rhoStar must be positive");
     const size_t n4 = (size_t)c->nNodes * 4;
     c->X4b.reserve(n4);
     c->V4b.reserve(n4);
+    if (p.eqType == PFEM_WC_CDS_RHO) c->wcF0.reserve((size_t)c->nNodes);
 }
 
 }  // namespace
@@ -830,6 +908,7 @@ int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     try {
+        const long long launches0 = c->launches;
         CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         launchStep(c, p, *dtInOut, dtDev);
         launchDt(c, p, securityCoeff, grid);
@@ -837,10 +916,11 @@ int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff
         LAUNCH_CHECK(c);
         CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));
         CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
-        c->launches -= 5;  // the capture itself launched nothing
+        const long long perStep = c->launches - launches0;  // 5 kernels (6 with the CDS_rho pre-pass)
+        c->launches = launches0;                            // the capture itself launched nothing
         for (int s = 0; s < nSteps; ++s) {
             CUDA_CHECK(cudaGraphLaunch(exec, c->stream));
-            c->launches += 5;
+            c->launches += perStep;
         }
         CUDA_CHECK(cudaMemcpyAsync(c->hScal, dtDev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));

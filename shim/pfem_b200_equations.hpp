@@ -180,7 +180,11 @@ public:
         const std::string stab = contParams.template checkAndGet<std::string>("stabilization");
         if (stab != "None" && stab != "Meduri") throw std::runtime_error("unknown stabilization: " + stab);  // ContEquation.inl:32-37
         m_par.meduri = stab == "Meduri";
-        if (m_pSolver->getID() != "CDS_dpdt") throw std::runtime_error("the B200 path implements CDS_dpdt only");
+        const std::string id = m_pSolver->getID();  // ContEquation.inl:38-43
+        if (id == "CDS_dpdt") m_par.eqType = PFEM_WC_CDS_DPDT;
+        else if (id == "CDS_drhodt") m_par.eqType = PFEM_WC_CDS_DRHODT;
+        else if (id == "CDS_rho") m_par.eqType = PFEM_WC_CDS_RHO;
+        else throw std::runtime_error("unknown WCompNewton solver id: " + id);
         auto bodyForce = momParams.template checkAndGet<std::vector<double>>("bodyForce");
         for (unsigned short d = 0; d < 3; ++d) m_par.bodyForce[d] = d < dim ? bodyForce[d] : 0.0;
         const int rc = pfem_create(&m_ctx, dim, pfem_b200_shim::deviceFromEnv());

@@ -16,24 +16,28 @@ def _pack(st):
     return np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
 
 
-@pytest.mark.parametrize("dim,n,kw,meduri", [
-    (2, 24, dict(free_fraction=0.01), True),          # ~C3 size
-    (2, 10, dict(permute=True), False),
-    (3, 4, dict(), True),
-    (3, 10, dict(free_fraction=0.01, permute=True), True),
-    (3, 8, dict(), False),
+@pytest.mark.parametrize("dim,n,kw,meduri,eq", [
+    (2, 24, dict(free_fraction=0.01), True, "CDS_dpdt"),          # ~C3 size
+    (2, 10, dict(permute=True), False, "CDS_dpdt"),
+    (3, 4, dict(), True, "CDS_dpdt"),
+    (3, 10, dict(free_fraction=0.01, permute=True), True, "CDS_dpdt"),
+    (3, 8, dict(), False, "CDS_dpdt"),
+    (2, 24, dict(free_fraction=0.01), True, "CDS_drhodt"),
+    (3, 8, dict(permute=True), False, "CDS_drhodt"),
+    (2, 10, dict(permute=True), False, "CDS_rho"),
+    (3, 10, dict(free_fraction=0.01, permute=True), True, "CDS_rho"),
 ])
-def test_wc_steps_match_oracle(dim, n, kw, meduri):
+def test_wc_steps_match_oracle(dim, n, kw, meduri, eq):
     mesh = mg.kuhn_box(dim, n, **kw)
     st = mg.wc_state(mesh)
     st["acc"] = 0.5 * np.random.default_rng(4).standard_normal(st["acc"].shape)
     W = mg.WC_PARAMS
     g = mg.gravity(dim)
-    wp_ref = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri)
+    wp_ref = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri, eq)
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
         ctx.set_states(0, _pack(st))
-        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri)
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri, eq)
         x_ref, st_ref = mesh.x, st
         for step in range(3):
             dt_ref = orc.wc_next_dt(mesh, x_ref, st_ref, wp_ref, W["securityCoeff"], 1e-3)
@@ -77,8 +81,8 @@ def test_state_roundtrip():
         assert (ctx.get_positions() == mesh.x).all()
 
 
-@pytest.mark.parametrize("dim,n", [(2, 20), (3, 6)])
-def test_wc_run_equals_step_loop(dim, n):
+@pytest.mark.parametrize("dim,n,eq", [(2, 20, "CDS_dpdt"), (3, 6, "CDS_dpdt"), (3, 5, "CDS_rho")])
+def test_wc_run_equals_step_loop(dim, n, eq):
     """pfem_wc_run (device-chained CFL dt, one CUDA graph per step) == the host loop of wc_step + wc_next_dt, bit for bit."""
     mesh = mg.kuhn_box(dim, n, free_fraction=0.01)
     st = mg.wc_state(mesh)
@@ -88,7 +92,7 @@ def test_wc_run_equals_step_loop(dim, n):
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
         ctx.set_states(0, _pack(st))
-        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True, eq)
         dt = dt0 = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
         elapsed = 0.0
         for _ in range(n_steps):
@@ -99,7 +103,7 @@ def test_wc_run_equals_step_loop(dim, n):
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
         ctx.set_states(0, _pack(st))
-        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True, eq)
         dt_next, el = ctx.wc_run(wp, n_steps, W["securityCoeff"], 1e-3, dt0)
         assert (ctx.get_states(0, 2 * dim + 2) == ref_states).all()
         assert (ctx.get_positions() == ref_x).all()

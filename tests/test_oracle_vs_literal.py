@@ -44,16 +44,18 @@ def test_pspg_assembly_and_bc(dim, n):
     assert ((Ad != 0) <= stored).all()
 
 
-@pytest.mark.parametrize("dim,n,meduri", [(2, 5, True), (2, 4, False), (3, 3, True)])
-def test_wc_step(dim, n, meduri):
+@pytest.mark.parametrize("dim,n,meduri,eq", [(2, 5, True, "CDS_dpdt"), (2, 4, False, "CDS_dpdt"), (3, 3, True, "CDS_dpdt"),
+                                              (2, 5, True, "CDS_drhodt"), (3, 3, False, "CDS_drhodt"),
+                                              (2, 4, False, "CDS_rho"), (3, 3, True, "CDS_rho")])
+def test_wc_step(dim, n, meduri, eq):
     mesh = mg.kuhn_box(dim, n, free_fraction=0.02)
     st = mg.wc_state(mesh)
     st["acc"] = 0.1 * np.random.default_rng(2).standard_normal(st["acc"].shape)
     W = mg.WC_PARAMS
     g = mg.gravity(dim)
-    wp = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri)
+    wp = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri, eq)
     x1, s1 = orc.wc_step(mesh, mesh.x, st, wp, 1e-5)
-    x2, s2 = lit.wc_step(mesh, mesh.x, st, W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, 1e-5, meduri)
+    x2, s2 = lit.wc_step(mesh, mesh.x, st, W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, 1e-5, meduri, eq)
     assert rel_err(x1, x2) < 1e-15
     for k in ("v", "p", "rho", "acc"):
         assert rel_err(s1[k], s2[k]) < 1e-12, k
