@@ -121,10 +121,22 @@ int pfem_pspg_assemble(pfem_ctx* ctx, const pfem_pspg_params* p, const double* q
  * qPrevVec[0]) uploads it once: set_qprev copies it to the device, assemble_resident assembles from device-resident data. */
 int pfem_pspg_set_qprev(pfem_ctx* ctx, const double* qPrev);
 int pfem_pspg_assemble_resident(pfem_ctx* ctx, const pfem_pspg_params* p);
-/* Replaces m_solver.analyzePattern/factorize/solve (PSPG.inl:281-290) by Jacobi-preconditioned BiCGSTAB on the device.
+/* Replaces m_solver.analyzePattern/factorize/solve (PSPG.inl:281-290) by preconditioned BiCGSTAB on the device.
  * q (out, (dim+1)*nNodes) may be NULL to leave the solution on the device.  relTol is on ||b - A q|| / ||b||.
  * Returns PFEM_NOT_CONVERGED / PFEM_NAN like a failed factorisation would (PSPG.inl:304-312). */
 int pfem_pspg_solve(pfem_ctx* ctx, double relTol, int maxIter, double* q, int* iters, double* relRes);
+/* Preconditioner of that BiCGSTAB.  kind: PFEM_PRECOND_AUTO (multigrid when the mesh has more than 64 nodes, else node-block
+ * Jacobi), _POINT (diagonal, what Eigen's iterative solvers default to, MomContEquation.hpp:49), _BLOCK (node-block Jacobi),
+ * _MG (aggregation multigrid, V(sweeps,sweeps), node-block Jacobi smoothing with the local damping `damping`/r_i, r_i the
+ * inf-norm of block row i of D^-1 A).  sweeps <= 0 / damping <= 0 keep the defaults (2, 2.0).  Under _AUTO a multigrid solve
+ * that has not converged after 300 iterations continues with node-block Jacobi.  get_preconditioner reports what the last
+ * solve used and its number of multigrid levels (1: none). */
+#define PFEM_PRECOND_AUTO 0
+#define PFEM_PRECOND_POINT 1
+#define PFEM_PRECOND_BLOCK 2
+#define PFEM_PRECOND_MG 3
+int pfem_pspg_set_preconditioner(pfem_ctx* ctx, int kind, int sweeps, double damping);
+int pfem_pspg_get_preconditioner(pfem_ctx* ctx, int* kindUsed, int* levelsOut);
 /* ||A q - b||_2 of the currently assembled system (Res::Ax_f, PSPG.inl:368).  q NULL: the last device solution. */
 int pfem_pspg_residual(pfem_ctx* ctx, const double* q, double* resAxf);
 /* One body of the Picard loop (PSPG.inl:278-313 + :366-370): solve -> node states <- q -> positions = snapshot + dt*v

@@ -61,6 +61,8 @@ SYMBOLS = {
     "pfem_pspg_assemble": (C.c_int, [_VP, C.POINTER(PspgParams), _DP]),
     "pfem_pspg_assemble_resident": (C.c_int, [_VP, C.POINTER(PspgParams)]),
     "pfem_pspg_solve": (C.c_int, [_VP, C.c_double, C.c_int, _DP, C.POINTER(C.c_int), _DP]),
+    "pfem_pspg_set_preconditioner": (C.c_int, [_VP, C.c_int, C.c_int, C.c_double]),
+    "pfem_pspg_get_preconditioner": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "pfem_pspg_residual": (C.c_int, [_VP, _DP, _DP]),
     "pfem_pspg_picard_iter": (C.c_int, [_VP, C.POINTER(PspgParams), _DP, C.c_double, C.c_int, _DP, _DP, C.POINTER(C.c_int)]),
     "pfem_pspg_export_csc": (C.c_int, [_VP, _I64P, _I32P, _I32P, _DP, _DP]),
@@ -231,6 +233,18 @@ class PfemContext:
         rc = self._chk(self._L.pfem_pspg_solve(self._h, rel_tol, max_iter, _dptr(q) if fetch else None,
                                                C.byref(it), C.byref(rr)), allow=(PFEM_NOT_CONVERGED, PFEM_NAN))
         return dict(status=rc, q=q, iters=it.value, rel_res=rr.value)
+
+    PRECOND = {"auto": 0, "point": 1, "block": 2, "mg": 3}
+
+    def pspg_set_preconditioner(self, kind="auto", sweeps=0, damping=0.0):
+        """kind: auto | point | block | mg (pfem_pspg_set_preconditioner)."""
+        self._chk(self._L.pfem_pspg_set_preconditioner(self._h, self.PRECOND[kind], int(sweeps), float(damping)))
+
+    def pspg_get_preconditioner(self):
+        """(kind used by the last solve, multigrid levels)."""
+        k, lv = C.c_int(0), C.c_int(0)
+        self._chk(self._L.pfem_pspg_get_preconditioner(self._h, C.byref(k), C.byref(lv)))
+        return {v: n for n, v in self.PRECOND.items()}[k.value], lv.value
 
     def pspg_residual(self, q=None):
         r = C.c_double(0)

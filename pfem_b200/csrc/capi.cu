@@ -79,6 +79,7 @@ int pfem_destroy(pfem_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     commDestroy(c);
+    mgDestroy(c);
     for (auto& p : c->pending) {
         cudaEventDestroy(p.e0);
         cudaEventDestroy(p.e1);
@@ -193,6 +194,21 @@ int pfem_pspg_solve(pfem_ctx* c, double relTol, int maxIter, double* q, int* ite
         return f.code;
     }
     return status;
+}
+int pfem_pspg_set_preconditioner(pfem_ctx* c, int kind, int sweeps, double damping) {
+    API_BEGIN(c)
+    PFEM_REQUIRE(kind >= PFEM_PRECOND_AUTO && kind <= PFEM_PRECOND_MG, PFEM_ERR_INVALID, "set_preconditioner: unknown kind");
+    PFEM_REQUIRE(sweeps <= 16 && damping <= 8.0, PFEM_ERR_INVALID, "set_preconditioner: sweeps <= 16, damping <= 8");
+    c->precondKind = kind;
+    c->mgSweeps = sweeps > 0 ? sweeps : 0;
+    c->mgDamping = damping > 0 ? damping : 0.0;
+    API_END(c)
+}
+int pfem_pspg_get_preconditioner(pfem_ctx* c, int* kindUsed, int* levelsOut) {
+    API_BEGIN(c)
+    if (kindUsed) *kindUsed = c->lastPrecond;
+    if (levelsOut) *levelsOut = c->lastPrecond == PFEM_PRECOND_MG ? mgLevelCount(c) : 1;
+    API_END(c)
 }
 int pfem_pspg_residual(pfem_ctx* c, const double* q, double* res) {
     API_BEGIN(c)

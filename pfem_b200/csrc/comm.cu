@@ -115,6 +115,7 @@ void commSetPartition(pfem_ctx* c, int64_t nOwned, int nPeers, const int32_t* pe
     PFEM_REQUIRE(nOwned >= 0 && nOwned <= c->nNodes && nPeers >= 0, PFEM_ERR_INVALID, "set_partition: bad sizes");
     PFEM_REQUIRE(nPeers == 0 || (peerRank && sendOffsets && recvStart && recvCount), PFEM_ERR_INVALID, "set_partition: null");
     c->nRows = (int)nOwned;
+    mgInvalidate(c, true);
     c->peers.clear();
     int64_t total = nPeers ? sendOffsets[nPeers] : 0;
     for (int p = 0; p < nPeers; ++p) {

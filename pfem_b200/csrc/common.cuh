@@ -67,7 +67,8 @@ struct PendingPhase {
     cudaEvent_t e0, e1;
 };
 
-struct NcclApi;  // dlopen'ed NCCL entry points (comm.cu)
+struct NcclApi;      // dlopen'ed NCCL entry points (comm.cu)
+struct MgHierarchy;  // multigrid preconditioner state (mg.cu)
 
 // slots of the Krylov scalar bank kept on the device (krylov.cu)
 enum { SC_RHO0 = 0, SC_RHO1, SC_ALPHA, SC_OMEGA, SC_DONE, SC_ITERS, SC_RES2, SC_BNORM2, SC_TOL2, SC_BAD, SC_TMP0, SC_TMP1, SC_COUNT = 16 };
@@ -121,6 +122,12 @@ struct pfem_ctx {
     DevBuf<double> bvec;       // nNodes*BS, internal dof = node*BS + d
     DevBuf<double> dinv;       // symmetric Jacobi scale 1/sqrt|a_ii|
     DevBuf<double> Wblk;       // node-block Jacobi: A_ii^-1 S_i^-1 per node
+    MgHierarchy* mg = nullptr; // aggregation multigrid preconditioner (mg.cu)
+    int precondKind = 0;       // PFEM_PRECOND_*: 0 auto
+    int mgSweeps = 0;          // 0: default
+    double mgDamping = 0.0;    // 0: default
+    int lastPrecond = 0;       // what the last solve used
+    double asmStamp = 0.0;     // dt of the assembled system (the multigrid dampings are re-tuned when it changes)
     DevBuf<double> kx, kr, kr0, kp, kp2, kv, ks, kt, kph, ksh;  // Krylov vectors (internal dof order)
     DevBuf<double> partial;    // PS_COUNT * reduceBlocks
     DevBuf<double> scal;       // SC_COUNT
@@ -229,6 +236,13 @@ void krylovLoadVector(pfem_ctx* c, const double* qHost, double* dst);  // ABI la
 void krylovStoreVector(pfem_ctx* c, const double* src, double* qHost);
 double krylovResidualNorm(pfem_ctx* c, double* xInternal);
 void krylovMatvec(pfem_ctx* c, double* xInternal, double* yInternal);
+// mg.cu
+void mgInvalidate(pfem_ctx* c, bool symbolic);
+void mgDestroy(pfem_ctx* c);
+bool mgSetup(pfem_ctx* c);
+double* mgRhs(pfem_ctx* c);
+int mgLevelCount(pfem_ctx* c);
+void mgApply(pfem_ctx* c, double* out);
 // wc.cu
 void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt);
 int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dt);

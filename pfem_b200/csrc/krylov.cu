@@ -16,149 +16,9 @@
 #include <string>
 
 #include "common.cuh"
+#include "spmv.cuh"
 
 namespace {
-
-constexpr int RB_THREADS = 256;
-
-// ---- block reduction helpers ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double warpSum(double v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-template <int NV> __device__ __forceinline__ void blockSumStore(double (&v)[NV], double* partial, int stride, const int* slots) {
-    __shared__ double sh[NV][32];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        const double s = warpSum(v[k]);
-        if (lane == 0) sh[k][w] = s;
-    }
-    __syncthreads();
-    if (w == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double s = lane < nw ? sh[k][lane] : 0.0;
-            s = warpSum(s);
-            if (lane == 0) partial[(size_t)slots[k] * stride + blockIdx.x] = s;
-        }
-    }
-}
-// every block reduces the bank entry `slot` identically (fixed order) -> same bits in every block
-__device__ __forceinline__ double bankSum(const double* __restrict__ partial, int stride, int slot, int nPart) {
-    __shared__ double sh[32];
-    __shared__ double result;
-    double s = 0;
-    for (int k = threadIdx.x; k < nPart; k += blockDim.x) s += partial[(size_t)slot * stride + k];
-    s = warpSum(s);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    __syncthreads();
-    if (lane == 0) sh[w] = s;
-    __syncthreads();
-    if (w == 0) {
-        double t = lane < nw ? sh[lane] : 0.0;
-        t = warpSum(t);
-        if (lane == 0) result = t;
-    }
-    __syncthreads();
-    return result;
-}
-
-// ---- SpMV y = A x with up to two fused dots  (y,w1) and (y,y) ------------------------------------------------------
-// Software-pipelined over block rows: row pointers are fetched two rows ahead and column indices one row ahead, so the
-// only loads a row waits for are its own A rows (streamed once, evict-first) and the x gathers (L2-resident).
-template <int BS> struct RowLoad {
-    double2 a01, a23, x01, x23;
-};
-template <int BS>
-__device__ __forceinline__ void loadSlot(const double* __restrict__ Aval, const double* __restrict__ x, int blk, int col,
-                                         int r, RowLoad<BS>& L) {
-    const double* ap = Aval + ((size_t)blk * BS + r) * BS;
-    const double* xp = x + (size_t)col * BS;
-    if constexpr (BS == 4) {
-        L.a01 = __ldcs(reinterpret_cast<const double2*>(ap));
-        L.a23 = __ldcs(reinterpret_cast<const double2*>(ap + 2));
-        L.x01 = __ldg(reinterpret_cast<const double2*>(xp));
-        L.x23 = __ldg(reinterpret_cast<const double2*>(xp + 2));
-    } else {
-        L.a01 = make_double2(__ldcs(ap), __ldcs(ap + 1));
-        L.a23 = make_double2(__ldcs(ap + 2), 0.0);
-        L.x01 = make_double2(__ldg(xp), __ldg(xp + 1));
-        L.x23 = make_double2(__ldg(xp + 2), 0.0);
-    }
-}
-template <int BS> __device__ __forceinline__ double dotSlot(const RowLoad<BS>& L) {
-    return L.a01.x * L.x01.x + L.a01.y * L.x01.y + L.a23.x * L.x23.x + L.a23.y * L.x23.y;
-}
-
-template <int BS, int MINB>
-__global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
-                                              const double* __restrict__ Aval, const double* __restrict__ x,
-                                              double* __restrict__ y, const double* __restrict__ w1, double* partial,
-                                              int stride, int slotYW, int slotYY, const double* __restrict__ scal,
-                                              const double* __restrict__ rowScale) {
-    const int lane = threadIdx.x & 31, grp = lane >> 2, r = lane & 3;
-    const int warpsPerBlock = blockDim.x >> 5;
-    const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nw = gridDim.x * warpsPerBlock;
-    double accYW = 0, accYY = 0;
-    const bool frozen = scal && scal[SC_DONE] != 0.0;
-    if (!frozen) {
-        int i = gw;
-        int pb0 = 0, pb1 = 0, qb0 = 0, qb1 = 0;  // row i / row i+nw block ranges
-        if (i < nNodes) {
-            pb0 = __ldg(nbrPtr + i);
-            pb1 = __ldg(nbrPtr + i + 1);
-        }
-        if (i + nw < nNodes) {
-            qb0 = __ldg(nbrPtr + i + nw);
-            qb1 = __ldg(nbrPtr + i + nw + 1);
-        }
-        int c0 = -1, c1 = -1;
-        if (grp < pb1 - pb0) c0 = __ldg(nbr + pb0 + grp);
-        if (grp + 8 < pb1 - pb0) c1 = __ldg(nbr + pb0 + grp + 8);
-        for (; i < nNodes; i += nw) {
-            int fb0 = 0, fb1 = 0;
-            if (i + 2 * nw < nNodes) {
-                fb0 = __ldg(nbrPtr + i + 2 * nw);
-                fb1 = __ldg(nbrPtr + i + 2 * nw + 1);
-            }
-            int d0 = -1, d1 = -1;
-            if (grp < qb1 - qb0) d0 = __ldg(nbr + qb0 + grp);
-            if (grp + 8 < qb1 - qb0) d1 = __ldg(nbr + qb0 + grp + 8);
-            const int nb = pb1 - pb0;
-            double acc = 0;
-            if (r < BS) {
-                RowLoad<BS> L0, L1;
-                if (c0 >= 0) loadSlot<BS>(Aval, x, pb0 + grp, c0, r, L0);
-                if (c1 >= 0) loadSlot<BS>(Aval, x, pb0 + grp + 8, c1, r, L1);
-                if (c0 >= 0) acc += dotSlot<BS>(L0);
-                if (c1 >= 0) acc += dotSlot<BS>(L1);
-                for (int s = grp + 16; s < nb; s += 8) {  // rows with more than 16 blocks (rare)
-                    RowLoad<BS> L;
-                    loadSlot<BS>(Aval, x, pb0 + s, __ldg(nbr + pb0 + s), r, L);
-                    acc += dotSlot<BS>(L);
-                }
-            }
-            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-            if (grp == 0 && r < BS) {
-                const size_t o = (size_t)i * BS + r;
-                if (rowScale) acc *= rowScale[o];  // symmetric Jacobi scaling: y = S A x
-                y[o] = acc;
-                if (slotYW >= 0) accYW += acc * w1[o];
-                if (slotYY >= 0) accYY += acc * acc;
-            }
-            pb0 = qb0, pb1 = qb1, qb0 = fb0, qb1 = fb1, c0 = d0, c1 = d1;
-        }
-    }
-    if (slotYW >= 0 || slotYY >= 0) {
-        double v[2] = {accYW, accYY};
-        const int slots[2] = {slotYW >= 0 ? slotYW : PS_AUX, slotYY >= 0 ? slotYY : PS_AUX + 1};
-        blockSumStore<2>(v, partial, stride, slots);
-    }
-}
 
 // ---- SpMV, bulk-copy (TMA) staged variant for 4x4 blocks ----------------------------------------------------------------
 // A block row is one contiguous run of nb*128 bytes, so one elected lane fetches it with a single cp.async.bulk into a
@@ -341,7 +201,8 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __
                                                          const double* __restrict__ dinv,
                                                          const double* __restrict__ W, double* __restrict__ ph,
                                                          double* scal, const double* partial,
-                                                         int stride, int nPart, int parity, int iterIndex) {
+                                                         int stride, int nPart, int parity, int iterIndex,
+                                                         double* __restrict__ mgRhs) {
     const double rho = bankSum(partial, stride, PS_RHO, nPart);
     const double rr = bankSum(partial, stride, PS_RR, nPart);
     const double rhoOld = scal[SC_RHO0 + (parity ^ 1)], alpha = scal[SC_ALPHA], omega = scal[SC_OMEGA];
@@ -377,7 +238,8 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_p(int n, const double* __
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double pi = r[i] + beta * (p[i] - omega * v[i]);
         pnew[i] = pi;
-        ph[i] = dinv[i] * pi;
+        if (mgRhs) mgRhs[i] = pi / dinv[i];  // S^-1 p: right-hand side of the multigrid cycle in the physical variables
+        else ph[i] = dinv[i] * pi;
     }
 }
 // K_C: alpha = rho / (r0,v) ; s = r - alpha v ; shat = dinv .* s
@@ -386,7 +248,7 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_s(int n, const double* __
                                                          const double* __restrict__ dinv, const double* __restrict__ W,
                                                          double* __restrict__ s,
                                                          double* __restrict__ sh, double* scal, const double* partial,
-                                                         int stride, int nPart, int parity) {
+                                                         int stride, int nPart, int parity, double* __restrict__ mgRhs) {
     if (scal[SC_DONE] != 0.0) return;
     const double sigma = bankSum(partial, stride, PS_SIGMA, nPart);
     const double alpha = scal[SC_RHO0 + parity] / sigma;
@@ -414,7 +276,8 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_s(int n, const double* __
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double si = r[i] - alpha * v[i];
         s[i] = si;
-        sh[i] = dinv[i] * si;
+        if (mgRhs) mgRhs[i] = si / dinv[i];
+        else sh[i] = dinv[i] * si;
     }
 }
 // W_i = A_ii^-1 diag(1/s_i): inverse of the (dim+1)^2 diagonal node block (Gauss-Jordan, partial pivoting) folded with the
@@ -669,7 +532,6 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
     PFEM_REQUIRE(relTol > 0 && maxIter > 0, PFEM_ERR_INVALID, "solve: relTol and maxIter must be positive");
     PhaseScope ph(c, "Solve system");
     KrylovDims k = setup(c);
-    const int checkEvery = 20;
     int totalIters = 0, status = PFEM_OK;
     double relRes = 0;
     if (!(warmStart && c->haveSolution)) {
@@ -679,9 +541,25 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
     }
     c->haveSolution = true;
     // preconditioner: node-block Jacobi (default) or point Jacobi (PFEM_PRECOND=point), both on the equilibrated system
-    static const bool pointJacobi = getenv("PFEM_PRECOND") && std::string(getenv("PFEM_PRECOND")) == "point";
+    // PFEM_PRECOND=point|block|mg overrides the AUTO choice (pfem_pspg_set_preconditioner wins over the environment)
+    static const std::string envPre = getenv("PFEM_PRECOND") ? getenv("PFEM_PRECOND") : "";
+    int kind = c->precondKind;
+    if (kind == PFEM_PRECOND_AUTO) {
+        if (envPre == "point") kind = PFEM_PRECOND_POINT;
+        else if (envPre == "block") kind = PFEM_PRECOND_BLOCK;
+        else kind = PFEM_PRECOND_MG;
+    }
+    if (kind == PFEM_PRECOND_MG && !mgSetup(c)) kind = PFEM_PRECOND_BLOCK;  // mesh too small for a second level
+    c->lastPrecond = kind;
+    double* mgB = kind == PFEM_PRECOND_MG ? mgRhs(c) : nullptr;
+    // a multigrid iteration costs ~10 SpMV: poll every iteration; the Jacobi variants poll every 20
+    const int checkEvery = kind == PFEM_PRECOND_MG ? 1 : 20;
+    // the multigrid cycle is not guaranteed to be a contraction on every mesh: give it a bounded number of iterations and
+    // hand over to node-block Jacobi (from the current iterate) if it has not converged by then
+    const int maxIterAll = maxIter;
+    if (kind == PFEM_PRECOND_MG && c->precondKind == PFEM_PRECOND_AUTO) maxIter = std::min(maxIter, 300);
     const double* W = nullptr;
-    if (!pointJacobi) {
+    if (kind == PFEM_PRECOND_BLOCK) {
         c->Wblk.reserve((size_t)c->nRows * k.BS * k.BS + 8);
         if (k.BS == 4)
             k_block_inverse<4><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(c->nRows, c->nbrPtr.p, c->diagSlot.p, c->Aval.p,
@@ -715,20 +593,22 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
                 double* pNew = parity ? c->kp.p : c->kp2.p;
                 if (k.BS == 4)
                     k_update_p<4><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, pOld, pNew, c->kv.p, c->dinv.p, W, c->kph.p,
-                                                                           c->scal.p, c->partial.p, k.stride, npVec, parity, it);
+                                                                           c->scal.p, c->partial.p, k.stride, npVec, parity, it, mgB);
                 else
                     k_update_p<3><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, pOld, pNew, c->kv.p, c->dinv.p, W, c->kph.p,
-                                                                           c->scal.p, c->partial.p, k.stride, npVec, parity, it);
+                                                                           c->scal.p, c->partial.p, k.stride, npVec, parity, it, mgB);
                 LAUNCH_CHECK(c);
+                if (mgB) mgApply(c, c->kph.p);
                 spmv(c, k, c->kph.p, c->kv.p, c->kr0.p, PS_SIGMA, -1, true, c->dinv.p);
                 const int npS = globalise(c, k, PS_SIGMA, -1, k.spmvGrid);
                 if (k.BS == 4)
                     k_update_s<4><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kv.p, c->dinv.p, W, c->ks.p, c->ksh.p,
-                                                                           c->scal.p, c->partial.p, k.stride, npS, parity);
+                                                                           c->scal.p, c->partial.p, k.stride, npS, parity, mgB);
                 else
                     k_update_s<3><<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->kv.p, c->dinv.p, W, c->ks.p, c->ksh.p,
-                                                                           c->scal.p, c->partial.p, k.stride, npS, parity);
+                                                                           c->scal.p, c->partial.p, k.stride, npS, parity, mgB);
                 LAUNCH_CHECK(c);
+                if (mgB) mgApply(c, c->ksh.p);
                 spmv(c, k, c->ksh.p, c->kt.p, c->ks.p, PS_TS, PS_TT, true, c->dinv.p);
                 const int npT = globalise(c, k, PS_TS, PS_TT, k.spmvGrid);
                 k_update_xr<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kx.p, c->kr.p, c->kr0.p, c->ks.p, c->kt.p,
@@ -771,6 +651,18 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
         status = PFEM_NOT_CONVERGED;
         if (totalIters >= maxIter) break;
         warmStart = true;  // restart from the current iterate (residual replacement / breakdown recovery)
+    }
+    if (kind == PFEM_PRECOND_MG && c->precondKind == PFEM_PRECOND_AUTO && status != PFEM_OK && totalIters < maxIterAll) {
+        int it2 = 0;
+        c->precondKind = PFEM_PRECOND_BLOCK;
+        try {
+            status = krylovSolve(c, relTol, maxIterAll - totalIters, &it2, &relRes, status != PFEM_NAN);
+        } catch (...) {
+            c->precondKind = PFEM_PRECOND_AUTO;
+            throw;
+        }
+        c->precondKind = PFEM_PRECOND_AUTO;
+        totalIters += it2;
     }
     if (itersOut) *itersOut = totalIters;
     if (relResOut) *relResOut = relRes;

@@ -1,0 +1,923 @@
+// mg.cu -- aggregation multigrid preconditioner for the BiCGSTAB solve of the monolithic PSPG system.
+//
+// The reference factorises m_A with Eigen::SparseLU every Picard iterate (MomContEquationPSPG.inl:281-290).  The Krylov
+// replacement with a node-block Jacobi preconditioner needs O(1/h) iterations (1622 at 2 M tets); the Schur complement of
+// the (v,p) system is a pressure Laplacian, so a multilevel correction is what removes the mesh dependence.  Design:
+//   * monolithic: every level keeps the (dim+1)x(dim+1) node blocks, so all levels reuse the node-block SpMV kernel
+//     (spmv.cuh) -- smoothing sweep and residual are SpMV epilogues, nothing else touches A;
+//   * aggregates = nodes that fall in the same cell of a uniform grid laid over the level's node coordinates (PFEM keeps
+//     the node spacing near h_char everywhere, Mesh.cpp:27-147), cell size chosen so that an aggregate holds ~2^dim nodes;
+//     piecewise-constant prolongation in the physical variables (v, p), Galerkin coarse matrices P^T A P;
+//   * node-block Jacobi smoothing with an l1-type LOCAL damping theta / r_i, r_i = sum_j ||A_ii^-1 A_ij||_inf taken in the
+//     equilibrated variables: the (v,p) coupling gives D^-1 A complex eigenvalues and a uniform damping that is stable on
+//     one mesh diverges on the next (measured: 0.5 fine at 1.3 M tets, divergent at 2 M); V(nu,nu) cycle, over-correction
+//     of the coarse update (standard for unsmoothed aggregation), dense inverse on the coarsest level (<= 64 nodes);
+//   * symbolic part (aggregates, coarse patterns, fine-block -> coarse-slot map) once per topology; numeric part
+//     (Galerkin sums, block inverses, coarsest inverse) once per assembly.  Everything is gather-style and ordered, no
+//     floating-point atomics: the preconditioner, hence the whole solve, is bit-reproducible run to run.
+// On a partitioned mesh every rank builds the hierarchy of its owned rows and drops the ghost columns (an additive-Schwarz
+// combination of per-rank multigrids; no communication inside the cycle).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <vector>
+
+#include "common.cuh"
+#include "spmv.cuh"
+
+struct MgLevel {
+    int n = 0;        // rows (nodes) of this level
+    int nVec = 0;     // vector extent in nodes (level 0 of a partitioned mesh: owned + ghost)
+    int maxNb = 0;
+    int64_t nBlocks = 0;
+    const int* nbrPtr = nullptr;  // level 0 aliases the context's pattern and values
+    const int* nbr = nullptr;
+    const int* diagSlot = nullptr;
+    const double* Aval = nullptr;
+    const double* X = nullptr;    // 4 doubles per node
+    DevBuf<int> nbrPtrB, nbrB, diagSlotB;
+    DevBuf<double> AvalB, XB;
+    // transfer to the next level
+    int nc = 0;
+    DevBuf<int> agg, aggPtr, aggNodes, cslot;
+    // numeric
+    DevBuf<double> Dw;            // omega * A_ii^-1
+    DevBuf<double> sc;            // 1/sqrt|a_dd| per dof (l1 damping works in the equilibrated variables)
+    double omega = 0.5;           // damping of this level's smoother (tuned or fixed)
+    DevBuf<double> b, xa, xb, t, xo;
+};
+struct MgHierarchy {
+    std::vector<std::unique_ptr<MgLevel>> lev;
+    DevBuf<double> dense;  // coarsest level: [A | I] -> [I | A^-1], nD x 2 nD
+    DevBuf<int> flag;
+    int nD = 0;
+    bool denseOk = false;
+    bool symbolicValid = false, numericValid = false, symbolicFailed = false;
+    int nu = 2;
+    double fixedOmega = 0.0;  // > 0: the caller's damping on every level; 0: tuned per level (tuneDamping)
+    double over = 1.5;
+    bool tuned = false;
+    double stamp = 0.0;       // dt of the system the dampings were tuned for
+};
+
+namespace {
+
+constexpr int COARSEST_NODES = 64;
+constexpr int NBR_CAP = 512;  // distinct coarse neighbours a warp can collect
+
+// ---- symbolic ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_bbox(const double* __restrict__ X, int n, int dim, double* __restrict__ out) {
+    __shared__ double slo[3][32], shi[3][32];
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        for (int d = 0; d < dim; ++d) {
+            const double v = X[(size_t)i * 4 + d];
+            lo[d] = fmin(lo[d], v);
+            hi[d] = fmax(hi[d], v);
+        }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int d = 0; d < 3; ++d) {
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+            hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+        if (lane == 0) slo[d][w] = lo[d], shi[d][w] = hi[d];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        const int d = threadIdx.x;
+        double a = 1e300, b = -1e300;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a = fmin(a, slo[d][k]), b = fmax(b, shi[d][k]);
+        if (d >= dim) a = b = 0.0;
+        out[d] = a;
+        out[3 + d] = b;
+    }
+}
+
+// mean element size -> node spacing h0 of level 0 (two-stage ordered sum: deterministic)
+__global__ void __launch_bounds__(256) k_vol_partial(const int* __restrict__ conn, int nElems, int dim,
+                                                     const double* __restrict__ X4, double* __restrict__ partial) {
+    __shared__ double sh[8];
+    const int npe = dim + 1;
+    double s = 0;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nElems; e += gridDim.x * blockDim.x) {
+        const int* en = conn + (size_t)e * npe;
+        const double* p0 = X4 + (size_t)en[0] * 4;
+        double J[3][3];
+        for (int m = 0; m < dim; ++m) {
+            const double* pm = X4 + (size_t)en[m + 1] * 4;
+            for (int d = 0; d < dim; ++d) J[d][m] = pm[d] - p0[d];
+        }
+        double det;
+        if (dim == 2) det = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+        else
+            det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                  J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        s += fabs(det);  // = dim! * element size: the volume of the cube whose Kuhn split has this element size
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int k = 0; k < 8; ++k) t += sh[k];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void k_vol_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0;
+        for (int k = 0; k < nb; ++k) t += partial[k];
+        *out = t;
+    }
+}
+
+__global__ void k_cell_key(const double* __restrict__ X, int n, int dim, double lox, double loy, double loz, double invH, int nx,
+                           int ny, int nz, int* __restrict__ key, int* __restrict__ flag) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* x = X + (size_t)i * 4;
+    const int ix = min(nx - 1, max(0, (int)floor((x[0] - lox) * invH + 1e-6)));
+    const int iy = min(ny - 1, max(0, (int)floor((x[1] - loy) * invH + 1e-6)));
+    const int iz = dim == 3 ? min(nz - 1, max(0, (int)floor((x[2] - loz) * invH + 1e-6))) : 0;
+    const int k = (iz * ny + iy) * nx + ix;
+    key[i] = k;
+    flag[k] = 1;
+}
+__global__ void k_assign_agg(int n, const int* __restrict__ key, const int* __restrict__ cellId, int* __restrict__ agg,
+                             int* __restrict__ count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = cellId[key[i]];
+    agg[i] = a;
+    atomicAdd(&count[a], 1);
+}
+__global__ void k_fill_members(int n, const int* __restrict__ agg, const int* __restrict__ aggPtr, int* __restrict__ cursor,
+                               int* __restrict__ aggNodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = agg[i];
+    aggNodes[aggPtr[a] + atomicAdd(&cursor[a], 1)] = i;
+}
+// ascending member order (fixes the summation order of every later gather) + coarse coordinates = member mean
+__global__ void k_sort_members(int nc, int dim, const int* __restrict__ aggPtr, int* __restrict__ aggNodes,
+                               const double* __restrict__ X, double* __restrict__ Xc) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nc) return;
+    const int b = aggPtr[a], len = aggPtr[a + 1] - b;
+    int* v = aggNodes + b;
+    for (int i = 1; i < len; ++i) {
+        const int k = v[i];
+        int j = i - 1;
+        while (j >= 0 && v[j] > k) {
+            v[j + 1] = v[j];
+            --j;
+        }
+        v[j + 1] = k;
+    }
+    double s[3] = {0, 0, 0};
+    for (int i = 0; i < len; ++i)
+        for (int d = 0; d < dim; ++d) s[d] += X[(size_t)v[i] * 4 + d];
+    for (int d = 0; d < 3; ++d) Xc[(size_t)a * 4 + d] = len > 0 ? s[d] / len : 0.0;
+    Xc[(size_t)a * 4 + 3] = 0.0;
+}
+
+// coarse neighbour list of aggregate I = sorted set { agg[j] : i in I, j in nbr(i), j owned }.  One warp per aggregate.
+template <bool FILL>
+__global__ void k_coarse_nbr(int nc, const int* __restrict__ aggPtr, const int* __restrict__ aggNodes, const int* __restrict__ agg,
+                             int nFine, const int* __restrict__ nbrPtr, const int* __restrict__ nbr, int* __restrict__ cPtr,
+                             int* __restrict__ cNbr, int* __restrict__ cDiag, int* __restrict__ misc) {
+    __shared__ int lists[8][NBR_CAP];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int I = blockIdx.x * 8 + w;
+    if (I >= nc) return;
+    int* list = lists[w];
+    int cnt = 0;
+    for (int m = aggPtr[I]; m < aggPtr[I + 1]; ++m) {
+        const int i = aggNodes[m];
+        const int b0 = nbrPtr[i], nb = nbrPtr[i + 1] - b0;
+        for (int s0 = 0; s0 < nb; s0 += 32) {
+            const int s = s0 + lane;
+            int J = -1;
+            if (s < nb) {
+                const int j = nbr[b0 + s];
+                if (j < nFine) J = agg[j];
+            }
+            bool isNew = J >= 0;
+            const int lim = min(cnt, NBR_CAP);
+            for (int k = 0; k < lim; ++k)
+                if (list[k] == J) isNew = false;
+            const unsigned same = __match_any_sync(0xffffffffu, isNew ? J : -1 - lane);
+            const bool leader = isNew && (__ffs(same) - 1 == lane);
+            const unsigned lead = __ballot_sync(0xffffffffu, leader);
+            const int pos = cnt + __popc(lead & ((1u << lane) - 1u));
+            if (leader && pos < NBR_CAP) list[pos] = J;
+            cnt += __popc(lead);
+            __syncwarp();
+        }
+    }
+    if (cnt > NBR_CAP) {
+        if (lane == 0) atomicOr(misc + 1, 1);  // overflow: the caller gives up on the hierarchy
+        cnt = NBR_CAP;
+    }
+    if (!FILL) {
+        if (lane == 0) {
+            cPtr[I] = cnt;
+            atomicMax(misc, cnt);
+        }
+    } else {
+        const int base = cPtr[I];
+        for (int k = lane; k < cnt; k += 32) {
+            const int v = list[k];
+            int rank = 0;
+            for (int q = 0; q < cnt; ++q) rank += list[q] < v;
+            cNbr[base + rank] = v;
+            if (v == I) cDiag[I] = rank;
+        }
+    }
+}
+// slot of every fine block in the coarse row of its aggregate (-1: ghost column, dropped)
+__global__ void k_cslot(int nFine, const int* __restrict__ nbrPtr, const int* __restrict__ nbr, const int* __restrict__ agg,
+                        const int* __restrict__ cPtr, const int* __restrict__ cNbr, int* __restrict__ cslot) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nFine) return;
+    const int I = agg[i];
+    const int c0 = cPtr[I], cn = cPtr[I + 1] - c0;
+    for (int k = nbrPtr[i]; k < nbrPtr[i + 1]; ++k) {
+        const int j = nbr[k];
+        int res = -1;
+        if (j < nFine) {
+            const int J = agg[j];
+            int lo = 0, hi = cn - 1;
+            while (lo <= hi) {
+                const int mid = (lo + hi) >> 1;
+                const int v = cNbr[c0 + mid];
+                if (v == J) {
+                    res = mid;
+                    break;
+                }
+                if (v < J) lo = mid + 1;
+                else hi = mid - 1;
+            }
+        }
+        cslot[k] = res;
+    }
+}
+
+// ---- numeric ----------------------------------------------------------------------------------------------------------
+// Galerkin sum A_c(I,J) = sum_{i in I, j in J} A(i,j), block-wise.  One half-warp per coarse row, lane = block entry: every
+// lane only ever touches "its" entry of each accumulator block, members and fine blocks are walked in ascending order.
+template <int BS>
+__global__ void k_galerkin(int nc, const int* __restrict__ aggPtr, const int* __restrict__ aggNodes,
+                                                  const int* __restrict__ fPtr, const double* __restrict__ fA,
+                                                  const int* __restrict__ cslot, const int* __restrict__ cPtr,
+                                                  double* __restrict__ cA, int nbcap) {
+    constexpr int BB = BS * BS;
+    extern __shared__ double accAll[];
+    const int l = threadIdx.x & 15;
+    const int I = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    double* acc = accAll + (size_t)(threadIdx.x >> 4) * nbcap * BB;
+    if (I >= nc || l >= BB) return;
+    const int c0 = cPtr[I], cn = cPtr[I + 1] - c0;
+    for (int k = 0; k < cn; ++k) acc[k * BB + l] = 0.0;
+    for (int m = aggPtr[I]; m < aggPtr[I + 1]; ++m) {
+        const int i = aggNodes[m];
+        for (int k = fPtr[i]; k < fPtr[i + 1]; ++k) {
+            const int cs = cslot[k];
+            if (cs >= 0) acc[cs * BB + l] += fA[(size_t)k * BB + l];
+        }
+    }
+    for (int k = 0; k < cn; ++k) cA[(size_t)(c0 + k) * BB + l] = acc[k * BB + l];
+}
+
+// Dw_i = omega * A_ii^-1 (Gauss-Jordan with partial pivoting); singular block -> omega * diag^-1
+template <int BS>
+__global__ void k_mg_block_inv(int n, const int* __restrict__ nbrPtr, const int* __restrict__ diagSlot,
+                               const double* __restrict__ Aval, double omega, double* __restrict__ Dw) {
+    const int nd = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nd >= n) return;
+    const double* Ad = Aval + ((size_t)nbrPtr[nd] + diagSlot[nd]) * BS * BS;
+    double M[BS][2 * BS];
+#pragma unroll
+    for (int r = 0; r < BS; ++r)
+#pragma unroll
+        for (int c = 0; c < BS; ++c) {
+            M[r][c] = Ad[r * BS + c];
+            M[r][BS + c] = (r == c) ? 1.0 : 0.0;
+        }
+    bool singular = false;
+#pragma unroll
+    for (int k = 0; k < BS; ++k) {
+        int piv = k;
+        double best = fabs(M[k][k]);
+#pragma unroll
+        for (int r = k + 1; r < BS; ++r)
+            if (fabs(M[r][k]) > best) best = fabs(M[r][k]), piv = r;
+        if (!(best > 0.0)) singular = true;
+#pragma unroll
+        for (int r = k + 1; r < BS; ++r)
+            if (r == piv) {
+#pragma unroll
+                for (int c = 0; c < 2 * BS; ++c) {
+                    const double t = M[k][c];
+                    M[k][c] = M[r][c];
+                    M[r][c] = t;
+                }
+            }
+        const double inv = 1.0 / M[k][k];
+#pragma unroll
+        for (int c = 0; c < 2 * BS; ++c) M[k][c] *= inv;
+#pragma unroll
+        for (int r = 0; r < BS; ++r)
+            if (r != k) {
+                const double f = M[r][k];
+#pragma unroll
+                for (int c = 0; c < 2 * BS; ++c) M[r][c] -= f * M[k][c];
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < BS; ++r)
+#pragma unroll
+        for (int c = 0; c < BS; ++c) {
+            double v = omega * M[r][BS + c];
+            if (singular) {
+                const double d = Ad[r * BS + r];
+                v = (r == c) ? (d != 0.0 ? omega / d : omega) : 0.0;
+            }
+            Dw[(size_t)nd * BS * BS + r * BS + c] = v;
+        }
+}
+
+// l1-type local damping: Dw_i *= theta / r_i with r_i = sum_j ||A_ii^-1 A_ij||_inf (>= 1), the inf-norm of block row i of
+// D^-1 A.  Rows of a consistent mass matrix get theta/2.5 (3-D), rows next to slivers or with strong (v,p) coupling get
+// less, without one bad row dictating the damping of the whole level.  Half-warp per row, lane = entry of the 4x4 product.
+// sc = 1/sqrt|a_dd| per dof: the block norms below are taken in the equilibrated variables (v and p differ by 1e6 in scale)
+template <int BS>
+__global__ void k_mg_diag_scale(int n, const int* __restrict__ nbrPtr, const int* __restrict__ diagSlot,
+                                const double* __restrict__ Aval, double* __restrict__ sc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * BS) return;
+    const int i = t / BS, d = t % BS;
+    const double a = fabs(Aval[((size_t)nbrPtr[i] + diagSlot[i]) * BS * BS + d * BS + d]);
+    sc[t] = a > 0.0 ? rsqrt(a) : 1.0;
+}
+template <int BS>
+__global__ void k_mg_l1_scale(int n, const int* __restrict__ nbrPtr, const int* __restrict__ nbr, const double* __restrict__ Aval,
+                              const double* __restrict__ sc, double theta, double wcap, double* __restrict__ Dw, double* __restrict__ rmax) {
+    constexpr int BB = BS * BS;
+    const int l = threadIdx.x & 15;
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const bool act = i < n;
+    const int r = l / BS, cc = l % BS;  // lanes >= BB idle (2-D)
+    const bool ent = act && l < BB;
+    double dinvRow[BS];
+#pragma unroll
+    for (int k = 0; k < BS; ++k) dinvRow[k] = ent ? Dw[(size_t)i * BB + r * BS + k] : 0.0;
+    double ri = 0;
+    const int b0 = act ? nbrPtr[i] : 0, b1 = act ? nbrPtr[i + 1] : 0;
+    const unsigned hm = 0xffffu << (threadIdx.x & 16);  // this half-warp
+    for (int k = b0; k < b1; ++k) {
+        double p = 0;
+        if (ent) {
+#pragma unroll
+            for (int q = 0; q < BS; ++q) p += dinvRow[q] * Aval[(size_t)k * BB + q * BS + cc];
+            p *= sc[(size_t)nbr[k] * BS + cc] / sc[(size_t)i * BS + r];  // S_i^-1 (D^-1 A)_ij S_j
+        }
+        p = fabs(p);
+        // row sums over cc (lanes of the same r), then max over r
+        double rs = 0;
+#pragma unroll
+        for (int q = 0; q < BS; ++q) {
+            const double v = __shfl_sync(hm, p, (threadIdx.x & 16) + min(r * BS + q, 15));
+            rs += (l < BB) ? v : 0.0;
+        }
+        double mx = rs;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(hm, mx, o));
+        ri += mx;
+    }
+    ri = fmax(ri, 1.0);
+    if (ent) Dw[(size_t)i * BB + l] *= fmin(theta / ri, wcap);
+    if (act && l == 0 && rmax) atomicMax(reinterpret_cast<unsigned long long*>(rmax), (unsigned long long)__double_as_longlong(ri));
+}
+
+// coarsest level: dense [A | I]
+__global__ void k_dense_build(int n, int BS, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+                              const double* __restrict__ Aval, double* __restrict__ D) {
+    const int nD = n * BS;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nD * 2 * nD; t += gridDim.x * blockDim.x) {
+        const int r = t / (2 * nD), c = t % (2 * nD);
+        D[t] = (c == nD + r) ? 1.0 : 0.0;
+    }
+}
+__global__ void k_dense_fill(int n, int BS, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+                             const double* __restrict__ Aval, double* __restrict__ D) {
+    const int nD = n * BS;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = nbrPtr[i]; k < nbrPtr[i + 1]; ++k) {
+        const int j = nbr[k];
+        for (int r = 0; r < BS; ++r)
+            for (int c = 0; c < BS; ++c) D[(size_t)(i * BS + r) * 2 * nD + j * BS + c] = Aval[(size_t)k * BS * BS + r * BS + c];
+    }
+}
+// in-place Gauss-Jordan with partial pivoting on the augmented matrix, one CTA (the matrix is <= 256 x 512, L2-resident)
+__global__ void __launch_bounds__(1024) k_dense_invert(int nD, double* __restrict__ D, int* __restrict__ flag) {
+    __shared__ double sval[32];
+    __shared__ int sidx[32];
+    __shared__ int pivRow;
+    __shared__ double pivInv;
+    const int W = 2 * nD;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = 0; k < nD; ++k) {
+        double best = -1.0;
+        int bi = k;
+        for (int r = k + threadIdx.x; r < nD; r += blockDim.x) {
+            const double v = fabs(D[(size_t)r * W + k]);
+            if (v > best) best = v, bi = r;
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) best = ov, bi = oi;
+        }
+        if (lane == 0) sval[w] = best, sidx[w] = bi;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double b = sval[0];
+            int id = sidx[0];
+            for (int q = 1; q < nw; ++q)
+                if (sval[q] > b || (sval[q] == b && sidx[q] < id)) b = sval[q], id = sidx[q];
+            pivRow = id;
+            if (!(b > 1e-300)) {
+                *flag = 1;
+                pivInv = 0.0;
+            } else
+                pivInv = 1.0 / D[(size_t)id * W + k];
+        }
+        __syncthreads();
+        const int p = pivRow;
+        const double pinv = pivInv;
+        if (pinv == 0.0) return;
+        // swap rows k and p, scale the pivot row
+        for (int c = threadIdx.x; c < W; c += blockDim.x) {
+            const double a = D[(size_t)p * W + c], b = D[(size_t)k * W + c];
+            D[(size_t)p * W + c] = b;
+            D[(size_t)k * W + c] = a * pinv;
+        }
+        __syncthreads();
+        // eliminate column k from every other row: warp per row
+        for (int r = w; r < nD; r += nw) {
+            if (r == k) continue;
+            double f = 0.0;
+            if (lane == 0) f = D[(size_t)r * W + k];
+            f = __shfl_sync(0xffffffffu, f, 0);  // read before any lane overwrites column k of this row
+            if (f != 0.0)
+                for (int c = lane; c < W; c += 32) D[(size_t)r * W + c] -= f * D[(size_t)k * W + c];
+        }
+        __syncthreads();
+    }
+}
+// x = A^-1 b with the inverse in the right half of D: warp per row
+__global__ void __launch_bounds__(1024) k_dense_apply(int nD, const double* __restrict__ D, const double* __restrict__ b,
+                                                      double* __restrict__ x) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int W = 2 * nD;
+    for (int r = w; r < nD; r += nw) {
+        double s = 0;
+        for (int c = lane; c < nD; c += 32) s += D[(size_t)r * W + nD + c] * b[c];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) x[r] = s;
+    }
+}
+
+// ---- cycle ------------------------------------------------------------------------------------------------------------
+// first sweep from a zero guess: x = Dw b
+template <int BS>
+__global__ void k_mg_jacobi0(int nDof, const double* __restrict__ Dw, const double* __restrict__ b, double* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nDof) return;
+    const int base = (i / BS) * BS;
+    double a = 0;
+#pragma unroll
+    for (int c = 0; c < BS; ++c) a += Dw[(size_t)i * BS + c] * b[base + c];
+    x[i] = a;
+}
+template <int BS>
+__global__ void k_mg_restrict(int nc, const int* __restrict__ aggPtr, const int* __restrict__ aggNodes,
+                              const double* __restrict__ r, double* __restrict__ bc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nc * BS) return;
+    const int I = t / BS, d = t % BS;
+    double s = 0;
+    for (int m = aggPtr[I]; m < aggPtr[I + 1]; ++m) s += r[(size_t)aggNodes[m] * BS + d];
+    bc[t] = s;
+}
+template <int BS>
+__global__ void k_mg_prolong(int nDof, const int* __restrict__ agg, const double* __restrict__ xc, double over,
+                             double* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nDof) return;
+    x[i] += over * xc[(size_t)agg[i / BS] * BS + (i % BS)];
+}
+
+// deterministic start vector of the power iteration (all frequencies present) and ordered 2-norm, single CTA
+__global__ void k_mg_noise(int nDof, double* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nDof) return;
+    unsigned h = (unsigned)i * 2654435761u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    x[i] = (double)(h & 0xffffu) / 32768.0 - 1.0;
+}
+__global__ void __launch_bounds__(1024) k_mg_norm2(int nDof, const double* __restrict__ x, double* __restrict__ out) {
+    __shared__ double sh[32];
+    double s = 0;
+    for (int i = threadIdx.x; i < nDof; i += blockDim.x) s += x[i] * x[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int k = 0; k < 32; ++k) t += sh[k];
+        *out = t;
+    }
+}
+
+template <int EPI>
+void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const double* x, double* y, const double* b) {
+    SpmvEpi e;
+    e.b = b;
+    e.Dw = L.Dw.p;
+    const int grid = std::max(1, std::min(c->smCount * 8, divUp(L.n, 8)));
+    if (BS == 4)
+        k_spmv<4, 3, EPI><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, x, y, nullptr, nullptr, 0, -1, -1, nullptr,
+                                                     nullptr, e);
+    else
+        k_spmv<3, 3, EPI><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, x, y, nullptr, nullptr, 0, -1, -1, nullptr,
+                                                     nullptr, e);
+    LAUNCH_CHECK(c);
+}
+
+void cycle(pfem_ctx* c, MgHierarchy& H, int l, const double* b, double* out) {
+    const int BS = c->dim + 1;
+    MgLevel& L = *H.lev[l];
+    const int nDof = L.n * BS;
+    const bool last = l + 1 == (int)H.lev.size();
+    if (last && H.denseOk) {
+        k_dense_apply<<<1, 1024, 0, c->stream>>>(H.nD, H.dense.p, b, out);
+        LAUNCH_CHECK(c);
+        return;
+    }
+    double* cur = L.xa.p;
+    double* oth = L.xb.p;
+    auto jac0 = [&](double* dst) {
+        if (BS == 4) k_mg_jacobi0<4><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.Dw.p, b, dst);
+        else k_mg_jacobi0<3><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.Dw.p, b, dst);
+        LAUNCH_CHECK(c);
+    };
+    const int nPre = last ? 4 * H.nu : H.nu, nPost = last ? 0 : H.nu;
+    jac0(cur);
+    for (int k = 1; k < nPre; ++k) {
+        double* dst = (last && k == nPre - 1) ? out : oth;
+        launchSpmv<EPI_SMOOTH>(c, L, BS, cur, dst, b);
+        std::swap(cur, oth);
+        if (dst == out) cur = out;
+    }
+    if (last) {  // coarsest level without a dense inverse: smoothing only
+        if (cur != out) CUDA_CHECK(cudaMemcpyAsync(out, cur, (size_t)nDof * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        return;
+    }
+    MgLevel& C = *H.lev[l + 1];
+    launchSpmv<EPI_RESID>(c, L, BS, cur, L.t.p, b);
+    if (BS == 4) k_mg_restrict<4><<<divUp(L.nc * BS, 256), 256, 0, c->stream>>>(L.nc, L.aggPtr.p, L.aggNodes.p, L.t.p, C.b.p);
+    else k_mg_restrict<3><<<divUp(L.nc * BS, 256), 256, 0, c->stream>>>(L.nc, L.aggPtr.p, L.aggNodes.p, L.t.p, C.b.p);
+    LAUNCH_CHECK(c);
+    cycle(c, H, l + 1, C.b.p, C.xo.p);
+    if (BS == 4) k_mg_prolong<4><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, C.xo.p, H.over, cur);
+    else k_mg_prolong<3><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, C.xo.p, H.over, cur);
+    LAUNCH_CHECK(c);
+    for (int k = 1; k <= nPost; ++k) {
+        double* dst = (k == nPost) ? out : oth;
+        launchSpmv<EPI_SMOOTH>(c, L, BS, cur, dst, b);
+        std::swap(cur, oth);
+    }
+}
+
+// one coarsening step; returns false when the level cannot be coarsened further
+bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSize) {
+    const int dim = c->dim, n = L.n;
+    const double target = dim == 3 ? 8.0 : 4.0;
+    c->scratchI.reserve((size_t)std::max(n, c->nNodes) + 64);
+    H.flag.reserve(16);
+    DevBuf<double> box;
+    box.reserve(8);
+    k_bbox<<<1, 1024, 0, c->stream>>>(L.X, n, dim, box.p);
+    LAUNCH_CHECK(c);
+    double hb[6];
+    CUDA_CHECK(cudaMemcpyAsync(hb, box.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    double ext[3], vol = 1.0, maxExt = 0.0;
+    for (int d = 0; d < dim; ++d) {
+        ext[d] = std::max(hb[3 + d] - hb[d], 0.0);
+        maxExt = std::max(maxExt, ext[d]);
+    }
+    if (!(maxExt > 0.0)) return false;
+    for (int d = 0; d < dim; ++d) vol *= std::max(ext[d], 1e-3 * maxExt);
+    // cell edge: the caller's suggestion (twice the node spacing of this level), else twice the spacing of a filled box
+    double Hc = cellSize > 0.0 ? cellSize : 2.0 * std::pow(vol / n, 1.0 / dim);
+    const double slack = cellSize > 0.0 ? 3.0 : 1.7;  // a suggested size is only overridden when it is far off
+    L.agg.reserve(n);
+    DevBuf<int> key, cell;
+    key.reserve(n);
+    int nc = 0;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        int nx, ny, nz;
+        for (;;) {
+            nx = (int)std::floor(ext[0] / Hc) + 1;
+            ny = (int)std::floor(ext[1] / Hc) + 1;
+            nz = dim == 3 ? (int)std::floor(ext[2] / Hc) + 1 : 1;
+            if ((double)nx * ny * nz <= 64.0e6) break;
+            Hc *= 1.5;
+        }
+        const int ncell = nx * ny * nz;
+        cell.reserve((size_t)ncell + 2);
+        CUDA_CHECK(cudaMemsetAsync(cell.p, 0, ((size_t)ncell + 2) * sizeof(int), c->stream));
+        k_cell_key<<<divUp(n, 256), 256, 0, c->stream>>>(L.X, n, dim, hb[0], hb[1], hb[2], 1.0 / Hc, nx, ny, nz, key.p, cell.p);
+        LAUNCH_CHECK(c);
+        exclusiveScanInt(c, cell.p, ncell + 1, H.flag.p + 4);
+        CUDA_CHECK(cudaMemcpyAsync(&nc, H.flag.p + 4, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        const double ratio = (double)n / std::max(nc, 1);
+        if (ratio > slack * target || ratio < target / (slack + 0.8)) {
+            if (attempt < 5) {
+                Hc *= std::pow(target / ratio, 1.0 / dim);
+                continue;
+            }
+        }
+        break;
+    }
+    if (nc < 1 || nc > 0.8 * n) return false;
+    cellSize = Hc;
+    // members
+    L.nc = nc;
+    L.aggPtr.reserve((size_t)nc + 2);
+    L.aggNodes.reserve(n);
+    CUDA_CHECK(cudaMemsetAsync(L.aggPtr.p, 0, ((size_t)nc + 2) * sizeof(int), c->stream));
+    k_assign_agg<<<divUp(n, 256), 256, 0, c->stream>>>(n, key.p, cell.p, L.agg.p, L.aggPtr.p);
+    LAUNCH_CHECK(c);
+    exclusiveScanInt(c, L.aggPtr.p, nc + 1, nullptr);
+    CUDA_CHECK(cudaMemsetAsync(c->scratchI.p, 0, (size_t)nc * sizeof(int), c->stream));
+    k_fill_members<<<divUp(n, 256), 256, 0, c->stream>>>(n, L.agg.p, L.aggPtr.p, c->scratchI.p, L.aggNodes.p);
+    LAUNCH_CHECK(c);
+    C.XB.reserve((size_t)nc * 4);
+    k_sort_members<<<divUp(nc, 128), 128, 0, c->stream>>>(nc, dim, L.aggPtr.p, L.aggNodes.p, L.X, C.XB.p);
+    LAUNCH_CHECK(c);
+    // coarse pattern
+    C.n = C.nVec = nc;
+    C.nbrPtrB.reserve((size_t)nc + 2);
+    C.diagSlotB.reserve(nc);
+    CUDA_CHECK(cudaMemsetAsync(C.nbrPtrB.p, 0, ((size_t)nc + 2) * sizeof(int), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(H.flag.p, 0, 4 * sizeof(int), c->stream));
+    k_coarse_nbr<false><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, n, L.nbrPtr, L.nbr, C.nbrPtrB.p,
+                                                            nullptr, nullptr, H.flag.p);
+    LAUNCH_CHECK(c);
+    exclusiveScanInt(c, C.nbrPtrB.p, nc + 1, H.flag.p + 2);
+    int hf[4];
+    CUDA_CHECK(cudaMemcpyAsync(hf, H.flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    if (hf[1] != 0) return false;  // a coarse row with more than NBR_CAP neighbours
+    C.maxNb = hf[0];
+    C.nBlocks = hf[2];
+    C.nbrB.reserve((size_t)C.nBlocks + 4);
+    k_coarse_nbr<true><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, n, L.nbrPtr, L.nbr, C.nbrPtrB.p,
+                                                           C.nbrB.p, C.diagSlotB.p, H.flag.p);
+    LAUNCH_CHECK(c);
+    L.cslot.reserve((size_t)L.nBlocks + 4);
+    k_cslot<<<divUp(n, 128), 128, 0, c->stream>>>(n, L.nbrPtr, L.nbr, L.agg.p, C.nbrPtrB.p, C.nbrB.p, L.cslot.p);
+    LAUNCH_CHECK(c);
+    C.nbrPtr = C.nbrPtrB.p, C.nbr = C.nbrB.p, C.diagSlot = C.diagSlotB.p, C.X = C.XB.p;
+    const int BS = dim + 1;
+    C.AvalB.reserve((size_t)C.nBlocks * BS * BS + 8);
+    C.Aval = C.AvalB.p;
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // key/cell/box are released on return
+    return true;
+}
+
+void allocVectors(pfem_ctx* c, MgLevel& L, int BS) {
+    const size_t nv = (size_t)L.nVec * BS + 8;
+    for (auto* v : {&L.b, &L.xa, &L.xb, &L.t, &L.xo}) {
+        const bool fresh = nv > v->cap;
+        v->reserve(nv);
+        if (fresh) CUDA_CHECK(cudaMemsetAsync(v->p, 0, v->cap * sizeof(double), c->stream));  // ghost entries stay zero
+    }
+    L.Dw.reserve((size_t)L.n * BS * BS + 8);
+}
+
+void buildSymbolic(pfem_ctx* c, MgHierarchy& H) {
+    PhaseScope ph(c, "Preconditioner pattern");
+    const int BS = c->dim + 1;
+    H.lev.clear();
+    H.symbolicFailed = false;
+    auto L0 = std::make_unique<MgLevel>();
+    L0->n = c->nRows, L0->nVec = c->nNodes, L0->maxNb = c->maxNb, L0->nBlocks = c->nBlocks;
+    H.lev.push_back(std::move(L0));
+    // node spacing of level 0 from the mean element size: h0 = (mean |detJ|)^(1/dim)
+    double cellSize = 0.0;
+    if (c->nElems > 0) {
+        const int nb = 256;
+        DevBuf<double> part;
+        part.reserve(nb + 8);
+        k_vol_partial<<<nb, 256, 0, c->stream>>>(c->conn.p, c->nElems, c->dim, c->X4.p, part.p);
+        LAUNCH_CHECK(c);
+        k_vol_final<<<1, 32, 0, c->stream>>>(part.p, nb, part.p + nb);
+        LAUNCH_CHECK(c);
+        double tot = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&tot, part.p + nb, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (tot > 0.0) cellSize = 2.0 * std::pow(tot / c->nElems, 1.0 / c->dim);
+    }
+    for (int l = 0; l < 16; ++l) {
+        MgLevel& L = *H.lev[l];
+        if (l == 0) {  // aliases may have been reallocated since the last build
+            L.nbrPtr = c->nbrPtr.p, L.nbr = c->nbr.p, L.diagSlot = c->diagSlot.p, L.Aval = c->Aval.p, L.X = c->X4.p;
+        }
+        allocVectors(c, L, BS);
+        if (L.n <= COARSEST_NODES) break;
+        auto C = std::make_unique<MgLevel>();
+        if (!coarsen(c, H, L, *C, cellSize)) break;
+        cellSize *= 2.0;
+        H.lev.push_back(std::move(C));
+    }
+    H.symbolicValid = true;
+    H.numericValid = false;
+}
+
+// Dw = damping * A_ii^-1: uniform damping L.omega, or (l1 = true) theta / r_i per node
+void blockInverse(pfem_ctx* c, MgLevel& L, int BS, bool l1 = false, double theta = 1.0) {
+    const double w = l1 ? 1.0 : L.omega;
+    if (BS == 4) k_mg_block_inv<4><<<divUp(L.n, 128), 128, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, w, L.Dw.p);
+    else k_mg_block_inv<3><<<divUp(L.n, 128), 128, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, w, L.Dw.p);
+    LAUNCH_CHECK(c);
+    if (!l1) return;
+    static const double wcap = getenv("PFEM_MG_WCAP") ? atof(getenv("PFEM_MG_WCAP")) : 1.0;
+    // level 0 of a partitioned mesh: ghost columns carry no diagonal here; their scale stays 1 (set at allocation)
+    if (L.sc.cap < (size_t)L.nVec * BS + 8) {
+        L.sc.reserve((size_t)L.nVec * BS + 8);
+        std::vector<double> ones(L.sc.cap, 1.0);
+        CUDA_CHECK(cudaMemcpyAsync(L.sc.p, ones.data(), L.sc.cap * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    if (BS == 4) {
+        k_mg_diag_scale<4><<<divUp(L.n * BS, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, L.sc.p);
+        LAUNCH_CHECK(c);
+        k_mg_l1_scale<4><<<divUp((int64_t)L.n * 16, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, L.sc.p, theta, wcap, L.Dw.p, nullptr);
+    } else {
+        k_mg_diag_scale<3><<<divUp(L.n * BS, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, L.sc.p);
+        LAUNCH_CHECK(c);
+        k_mg_l1_scale<3><<<divUp((int64_t)L.n * 16, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, L.sc.p, theta, wcap, L.Dw.p, nullptr);
+    }
+    LAUNCH_CHECK(c);
+}
+
+// Damped node-block Jacobi is only a smoother if it does not amplify anything: the (v,p) coupling gives D^-1 A complex
+// eigenvalues, so the admissible damping depends on dt, the material and the mesh.  Largest damping of a short ladder
+// whose error propagation I - omega D^-1 A has a spectral radius (power iteration, deterministic start) below 0.97.
+void tuneDamping(pfem_ctx* c, MgHierarchy& H, MgLevel& L, int BS) {
+    static const double ladder[] = {0.7, 0.55, 0.45, 0.36, 0.28, 0.2, 0.12};
+    const int nDof = L.n * BS, nIt = 14, nTail = 6;
+    H.flag.reserve(16);
+    double* dNorm = reinterpret_cast<double*>(H.flag.p + 10);  // 8-byte aligned: flag.p is cudaMalloc'ed, offset 40 B
+    CUDA_CHECK(cudaMemsetAsync(L.t.p, 0, (size_t)nDof * sizeof(double), c->stream));
+    for (double w : ladder) {
+        L.omega = w;
+        blockInverse(c, L, BS);
+        k_mg_noise<<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.xa.p);
+        LAUNCH_CHECK(c);
+        double* cur = L.xa.p;
+        double* oth = L.xb.p;
+        double nrm[32];
+        for (int it = 0; it <= nIt; ++it) {
+            if (it > 0) {
+                launchSpmv<EPI_SMOOTH>(c, L, BS, cur, oth, L.t.p);
+                std::swap(cur, oth);
+            }
+            k_mg_norm2<<<1, 1024, 0, c->stream>>>(nDof, cur, dNorm);
+            LAUNCH_CHECK(c);
+            CUDA_CHECK(cudaMemcpyAsync(&nrm[it], dNorm, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        }
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        const double a = nrm[nIt - nTail], b = nrm[nIt];
+        const double rho = (a > 0.0 && b == b) ? std::pow(b / a, 0.5 / nTail) : 0.0;  // norms are squared
+        if (b == b && rho <= 0.97) break;
+    }
+    // the work vectors go back to their resting state (ghost entries were never touched)
+    CUDA_CHECK(cudaMemsetAsync(L.xa.p, 0, (size_t)nDof * sizeof(double), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(L.xb.p, 0, (size_t)nDof * sizeof(double), c->stream));
+}
+
+void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
+    PhaseScope ph(c, "Preconditioner setup");
+    const int BS = c->dim + 1, BB = BS * BS;
+    MgLevel& L0 = *H.lev[0];
+    L0.nbrPtr = c->nbrPtr.p, L0.nbr = c->nbr.p, L0.diagSlot = c->diagSlot.p, L0.Aval = c->Aval.p, L0.X = c->X4.p;
+    for (size_t l = 0; l < H.lev.size(); ++l) {
+        MgLevel& L = *H.lev[l];
+        static const int dampMode = getenv("PFEM_MG_DAMP") ? atoi(getenv("PFEM_MG_DAMP")) : 0;  // 0 l1 | 1 uniform | 2 tuned
+        if (dampMode == 0) {
+            L.omega = H.fixedOmega > 0.0 ? H.fixedOmega : 2.0;  // theta: 2.0 measured best-robust (2.5 turns unstable in 2-D)
+            blockInverse(c, L, BS, true, L.omega);
+        } else if (H.fixedOmega > 0.0 || dampMode == 1) {
+            L.omega = H.fixedOmega > 0.0 ? H.fixedOmega : 0.45;
+            blockInverse(c, L, BS);
+        } else if (!H.tuned)
+            tuneDamping(c, H, L, BS);  // leaves Dw for the accepted damping
+        else
+            blockInverse(c, L, BS);
+        if (l + 1 == H.lev.size()) break;
+        MgLevel& C = *H.lev[l + 1];
+        const int nbcap = std::max(C.maxNb, 1);
+        const int hwPerBlock = std::max(1, std::min(8, (int)((96 * 1024) / ((size_t)nbcap * BB * sizeof(double)))));
+        const size_t smem = (size_t)hwPerBlock * nbcap * BB * sizeof(double);
+        if (BS == 4) {
+            if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_galerkin<4><<<divUp(L.nc, hwPerBlock), hwPerBlock * 16, smem, c->stream>>>(L.nc, L.aggPtr.p, L.aggNodes.p, L.nbrPtr, L.Aval,
+                                                                                       L.cslot.p, C.nbrPtr, C.AvalB.p, nbcap);
+        } else {
+            if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_galerkin<3><<<divUp(L.nc, hwPerBlock), hwPerBlock * 16, smem, c->stream>>>(L.nc, L.aggPtr.p, L.aggNodes.p, L.nbrPtr, L.Aval,
+                                                                                       L.cslot.p, C.nbrPtr, C.AvalB.p, nbcap);
+        }
+        LAUNCH_CHECK(c);
+    }
+    // coarsest level: dense inverse when it is small enough
+    MgLevel& Lc = *H.lev.back();
+    H.denseOk = false;
+    if (Lc.n <= COARSEST_NODES && Lc.nVec == Lc.n) {
+        H.nD = Lc.n * BS;
+        H.dense.reserve((size_t)H.nD * 2 * H.nD + 8);
+        H.flag.reserve(16);
+        CUDA_CHECK(cudaMemsetAsync(H.flag.p + 8, 0, sizeof(int), c->stream));
+        k_dense_build<<<64, 256, 0, c->stream>>>(Lc.n, BS, Lc.nbrPtr, Lc.nbr, Lc.Aval, H.dense.p);
+        LAUNCH_CHECK(c);
+        k_dense_fill<<<divUp(Lc.n, 64), 64, 0, c->stream>>>(Lc.n, BS, Lc.nbrPtr, Lc.nbr, Lc.Aval, H.dense.p);
+        LAUNCH_CHECK(c);
+        k_dense_invert<<<1, 1024, 0, c->stream>>>(H.nD, H.dense.p, H.flag.p + 8);
+        LAUNCH_CHECK(c);
+        int bad = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&bad, H.flag.p + 8, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        H.denseOk = bad == 0;
+    }
+    static const bool verbose = getenv("PFEM_MG_VERBOSE") != nullptr;
+    if (verbose && !H.tuned) {
+        fprintf(stderr, "[pfem mg] levels:");
+        for (auto& L : H.lev) fprintf(stderr, " %d(nb<=%d, omega %.2f)", L->n, L->maxNb, L->omega);
+        fprintf(stderr, "  coarsest dense: %s\n", H.denseOk ? "yes" : "no");
+    }
+    H.tuned = true;
+    H.numericValid = true;
+}
+
+}  // namespace
+
+void mgInvalidate(pfem_ctx* c, bool symbolic) {
+    if (!c->mg) return;
+    c->mg->numericValid = false;
+    if (symbolic) c->mg->symbolicValid = false;
+}
+void mgDestroy(pfem_ctx* c) {
+    delete c->mg;
+    c->mg = nullptr;
+}
+// (re)build what is stale; false: no usable hierarchy (single level) -> the caller keeps node-block Jacobi
+bool mgSetup(pfem_ctx* c) {
+    if (!c->mg) c->mg = new MgHierarchy();
+    MgHierarchy& H = *c->mg;
+    static const int envNu = getenv("PFEM_MG_NU") ? atoi(getenv("PFEM_MG_NU")) : 0;
+    static const double envOmega = getenv("PFEM_MG_OMEGA") ? atof(getenv("PFEM_MG_OMEGA")) : 0.0;
+    static const double envOver = getenv("PFEM_MG_OVER") ? atof(getenv("PFEM_MG_OVER")) : 0.0;
+    const int nu = c->mgSweeps > 0 ? c->mgSweeps : (envNu > 0 ? envNu : 2);
+    const double omega = c->mgDamping > 0 ? c->mgDamping : (envOmega > 0 ? envOmega : 0.0);  // 0: tuned per level
+    const double over = envOver > 0 ? envOver : 1.5;
+    if (omega != H.fixedOmega) H.numericValid = false, H.tuned = false;  // Dw carries the damping
+    if (c->asmStamp != H.stamp) H.tuned = false;                          // another dt: the spectrum moved
+    H.nu = nu, H.fixedOmega = omega, H.over = over, H.stamp = c->asmStamp;
+    if (!H.symbolicValid) {
+        buildSymbolic(c, H);
+        H.tuned = false;
+    }
+    if (H.lev.size() < 2) return false;
+    if (!H.numericValid) buildNumeric(c, H);
+    return true;
+}
+double* mgRhs(pfem_ctx* c) { return c->mg->lev[0]->b.p; }
+int mgLevelCount(pfem_ctx* c) { return c->mg ? (int)c->mg->lev.size() : 0; }
+// out = V-cycle(rhs held in mgRhs()): an approximation of A^-1 rhs in the physical variables
+void mgApply(pfem_ctx* c, double* out) {
+    PhaseScope ph(c, "Preconditioner apply");
+    cycle(c, *c->mg, 0, c->mg->lev[0]->b.p, out);
+}

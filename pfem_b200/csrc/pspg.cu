@@ -594,6 +594,8 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
         LAUNCH_CHECK(c);
     }
     c->haveSystem = true;
+    mgInvalidate(c, false);  // the coarse matrices follow A
+    c->asmStamp = p.dt;
     c->haveSolution = false;
 }
 

@@ -1,0 +1,175 @@
+// spmv.cuh -- node-block SpMV kernel and the block-reduction helpers shared by krylov.cu (BiCGSTAB) and mg.cu (multigrid
+// smoother / residual).  Included inside each translation unit's anonymous namespace users; everything here is static.
+#pragma once
+#include "common.cuh"
+
+namespace {
+
+constexpr int RB_THREADS = 256;
+
+// ---- block reduction helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warpSum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+template <int NV> __device__ __forceinline__ void blockSumStore(double (&v)[NV], double* partial, int stride, const int* slots) {
+    __shared__ double sh[NV][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const double s = warpSum(v[k]);
+        if (lane == 0) sh[k][w] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double s = lane < nw ? sh[k][lane] : 0.0;
+            s = warpSum(s);
+            if (lane == 0) partial[(size_t)slots[k] * stride + blockIdx.x] = s;
+        }
+    }
+}
+// every block reduces the bank entry `slot` identically (fixed order) -> same bits in every block
+__device__ __forceinline__ double bankSum(const double* __restrict__ partial, int stride, int slot, int nPart) {
+    __shared__ double sh[32];
+    __shared__ double result;
+    double s = 0;
+    for (int k = threadIdx.x; k < nPart; k += blockDim.x) s += partial[(size_t)slot * stride + k];
+    s = warpSum(s);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[w] = s;
+    __syncthreads();
+    if (w == 0) {
+        double t = lane < nw ? sh[lane] : 0.0;
+        t = warpSum(t);
+        if (lane == 0) result = t;
+    }
+    __syncthreads();
+    return result;
+}
+
+// ---- SpMV y = A x with up to two fused dots  (y,w1) and (y,y) ------------------------------------------------------
+// Software-pipelined over block rows: row pointers are fetched two rows ahead and column indices one row ahead, so the
+// only loads a row waits for are its own A rows (streamed once, evict-first) and the x gathers (L2-resident).
+template <int BS> struct RowLoad {
+    double2 a01, a23, x01, x23;
+};
+template <int BS>
+__device__ __forceinline__ void loadSlot(const double* __restrict__ Aval, const double* __restrict__ x, int blk, int col,
+                                         int r, RowLoad<BS>& L) {
+    const double* ap = Aval + ((size_t)blk * BS + r) * BS;
+    const double* xp = x + (size_t)col * BS;
+    if constexpr (BS == 4) {
+        L.a01 = __ldcs(reinterpret_cast<const double2*>(ap));
+        L.a23 = __ldcs(reinterpret_cast<const double2*>(ap + 2));
+        L.x01 = __ldg(reinterpret_cast<const double2*>(xp));
+        L.x23 = __ldg(reinterpret_cast<const double2*>(xp + 2));
+    } else {
+        L.a01 = make_double2(__ldcs(ap), __ldcs(ap + 1));
+        L.a23 = make_double2(__ldcs(ap + 2), 0.0);
+        L.x01 = make_double2(__ldg(xp), __ldg(xp + 1));
+        L.x23 = make_double2(__ldg(xp + 2), 0.0);
+    }
+}
+template <int BS> __device__ __forceinline__ double dotSlot(const RowLoad<BS>& L) {
+    return L.a01.x * L.x01.x + L.a01.y * L.x01.y + L.a23.x * L.x23.x + L.a23.y * L.x23.y;
+}
+
+// Epilogue of a block row.  EPI_PLAIN: y = rowScale .* (A x) with the fused dots (BiCGSTAB).  EPI_RESID: y = b - A x.
+// EPI_SMOOTH: damped node-block Jacobi sweep y = x + Dw_i (b_i - (A x)_i), Dw_i = omega A_ii^-1 (multigrid smoother).
+enum { EPI_PLAIN = 0, EPI_RESID = 1, EPI_SMOOTH = 2 };
+struct SpmvEpi {
+    const double* b = nullptr;
+    const double* Dw = nullptr;
+};
+
+template <int BS, int MINB, int EPI = EPI_PLAIN>
+__global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+                                              const double* __restrict__ Aval, const double* __restrict__ x,
+                                              double* __restrict__ y, const double* __restrict__ w1, double* partial,
+                                              int stride, int slotYW, int slotYY, const double* __restrict__ scal,
+                                              const double* __restrict__ rowScale, const SpmvEpi epi = SpmvEpi()) {
+    const int lane = threadIdx.x & 31, grp = lane >> 2, r = lane & 3;
+    const int warpsPerBlock = blockDim.x >> 5;
+    const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nw = gridDim.x * warpsPerBlock;
+    double accYW = 0, accYY = 0;
+    const bool frozen = scal && scal[SC_DONE] != 0.0;
+    if (!frozen) {
+        int i = gw;
+        int pb0 = 0, pb1 = 0, qb0 = 0, qb1 = 0;  // row i / row i+nw block ranges
+        if (i < nNodes) {
+            pb0 = __ldg(nbrPtr + i);
+            pb1 = __ldg(nbrPtr + i + 1);
+        }
+        if (i + nw < nNodes) {
+            qb0 = __ldg(nbrPtr + i + nw);
+            qb1 = __ldg(nbrPtr + i + nw + 1);
+        }
+        int c0 = -1, c1 = -1;
+        if (grp < pb1 - pb0) c0 = __ldg(nbr + pb0 + grp);
+        if (grp + 8 < pb1 - pb0) c1 = __ldg(nbr + pb0 + grp + 8);
+        for (; i < nNodes; i += nw) {
+            int fb0 = 0, fb1 = 0;
+            if (i + 2 * nw < nNodes) {
+                fb0 = __ldg(nbrPtr + i + 2 * nw);
+                fb1 = __ldg(nbrPtr + i + 2 * nw + 1);
+            }
+            int d0 = -1, d1 = -1;
+            if (grp < qb1 - qb0) d0 = __ldg(nbr + qb0 + grp);
+            if (grp + 8 < qb1 - qb0) d1 = __ldg(nbr + qb0 + grp + 8);
+            const int nb = pb1 - pb0;
+            double acc = 0;
+            if (r < BS) {
+                RowLoad<BS> L0, L1;
+                if (c0 >= 0) loadSlot<BS>(Aval, x, pb0 + grp, c0, r, L0);
+                if (c1 >= 0) loadSlot<BS>(Aval, x, pb0 + grp + 8, c1, r, L1);
+                if (c0 >= 0) acc += dotSlot<BS>(L0);
+                if (c1 >= 0) acc += dotSlot<BS>(L1);
+                for (int s = grp + 16; s < nb; s += 8) {  // rows with more than 16 blocks (rare)
+                    RowLoad<BS> L;
+                    loadSlot<BS>(Aval, x, pb0 + s, __ldg(nbr + pb0 + s), r, L);
+                    acc += dotSlot<BS>(L);
+                }
+            }
+            acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+            acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if constexpr (EPI == EPI_PLAIN) {
+                if (grp == 0 && r < BS) {
+                    const size_t o = (size_t)i * BS + r;
+                    if (rowScale) acc *= rowScale[o];  // symmetric Jacobi scaling: y = S A x
+                    y[o] = acc;
+                    if (slotYW >= 0) accYW += acc * w1[o];
+                    if (slotYY >= 0) accYY += acc * acc;
+                }
+            } else if constexpr (EPI == EPI_RESID) {
+                if (grp == 0 && r < BS) {
+                    const size_t o = (size_t)i * BS + r;
+                    y[o] = epi.b[o] - acc;
+                }
+            } else {
+                const size_t o = (size_t)i * BS + (r < BS ? r : 0);
+                const double res = (grp == 0 && r < BS) ? epi.b[o] - acc : 0.0;
+                double upd = 0;
+#pragma unroll
+                for (int cc = 0; cc < BS; ++cc) {
+                    const double rc = __shfl_sync(0xffffffffu, res, cc);
+                    if (grp == 0 && r < BS) upd += epi.Dw[o * BS + cc] * rc;
+                }
+                if (grp == 0 && r < BS) y[o] = x[o] + upd;
+            }
+            pb0 = qb0, pb1 = qb1, qb0 = fb0, qb1 = fb1, c0 = d0, c1 = d1;
+        }
+    }
+    if (slotYW >= 0 || slotYY >= 0) {
+        double v[2] = {accYW, accYY};
+        const int slots[2] = {slotYW >= 0 ? slotYW : PS_AUX, slotYY >= 0 ? slotYY : PS_AUX + 1};
+        blockSumStore<2>(v, partial, stride, slots);
+    }
+}
+
+
+}  // namespace
