@@ -125,7 +125,7 @@ int pfem_pspg_assemble_resident(pfem_ctx* ctx, const pfem_pspg_params* p);
  * q (out, (dim+1)*nNodes) may be NULL to leave the solution on the device.  relTol is on ||b - A q|| / ||b||.
  * Returns PFEM_NOT_CONVERGED / PFEM_NAN like a failed factorisation would (PSPG.inl:304-312). */
 int pfem_pspg_solve(pfem_ctx* ctx, double relTol, int maxIter, double* q, int* iters, double* relRes);
-/* Preconditioner of that BiCGSTAB.  kind: PFEM_PRECOND_AUTO (multigrid when the mesh has more than 64 nodes, else node-block
+/* Preconditioner of that BiCGSTAB.  kind: PFEM_PRECOND_AUTO (multigrid when the mesh has more than 32 nodes, else node-block
  * Jacobi), _POINT (diagonal, what Eigen's iterative solvers default to, MomContEquation.hpp:49), _BLOCK (node-block Jacobi),
  * _MG (aggregation multigrid, V(sweeps,sweeps), node-block Jacobi smoothing with the local damping `damping`/r_i, r_i the
  * inf-norm of block row i of D^-1 A).  sweeps <= 0 / damping <= 0 keep the defaults (2, 2.0).  Under _AUTO a multigrid solve
@@ -180,6 +180,7 @@ int pfem_set_partition(pfem_ctx* ctx, int64_t nOwned, int nPeers, const int32_t*
                        const int32_t* sendIdx, const int64_t* recvStart, const int64_t* recvCount);
 
 /* ---- instrumentation (phase names = the reference's m_accumalatedTimes keys, PSPG.inl:19-369) ---- */
+/* on: 0 off | 1 phases | 2 phases + per-kernel phases of the multigrid cycle (which then runs un-graphed) */
 int pfem_profile_enable(pfem_ctx* ctx, int on);
 int pfem_profile_reset(pfem_ctx* ctx);
 /* accumulated device milliseconds (CUDA events on the context's stream) and call count of one phase */

@@ -343,7 +343,8 @@ class PfemContext:
 
     # -- instrumentation --------------------------------------------------------------
     def profile_enable(self, on=True):
-        self._chk(self._L.pfem_profile_enable(self._h, 1 if on else 0))
+        """on: False/0 off, True/1 phases, 2 also the per-kernel phases of the multigrid cycle (un-graphed)."""
+        self._chk(self._L.pfem_profile_enable(self._h, int(on)))
 
     def profile_reset(self):
         self._chk(self._L.pfem_profile_reset(self._h))

@@ -326,6 +326,7 @@ int pfem_profile_enable(pfem_ctx* c, int on) {
     API_BEGIN(c)
     pfemFlushPhases(c);
     c->profiling = on != 0;
+    c->profileDetail = on == 2;
     API_END(c)
 }
 int pfem_profile_reset(pfem_ctx* c) {

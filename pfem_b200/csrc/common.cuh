@@ -156,6 +156,7 @@ struct pfem_ctx {
 
     // ---- profiling ----
     bool profiling = false;
+    bool profileDetail = false;  // per-kernel phases inside the multigrid cycle (no CUDA graph then)
     std::map<std::string, PhaseAcc> phases;
     std::vector<PendingPhase> pending;
     std::vector<cudaEvent_t> eventPool;

@@ -10,8 +10,8 @@
 //     piecewise-constant prolongation in the physical variables (v, p), Galerkin coarse matrices P^T A P;
 //   * node-block Jacobi smoothing with an l1-type LOCAL damping theta / r_i, r_i = sum_j ||A_ii^-1 A_ij||_inf taken in the
 //     equilibrated variables: the (v,p) coupling gives D^-1 A complex eigenvalues and a uniform damping that is stable on
-//     one mesh diverges on the next (measured: 0.5 fine at 1.3 M tets, divergent at 2 M); V(nu,nu) cycle, over-correction
-//     of the coarse update (standard for unsmoothed aggregation), dense inverse on the coarsest level (<= 64 nodes);
+//     one mesh diverges on the next (measured: 0.5 fine at 1.3 M tets, divergent at 2 M); V(nu,nu) cycle (nu+1 sweeps on the cheap coarse levels), over-correction
+//     of the coarse update (standard for unsmoothed aggregation), dense inverse on the coarsest level (<= 32 nodes);
 //   * symbolic part (aggregates, coarse patterns, fine-block -> coarse-slot map) once per topology; numeric part
 //     (Galerkin sums, block inverses, coarsest inverse) once per assembly.  Everything is gather-style and ordered, no
 //     floating-point atomics: the preconditioner, hence the whole solve, is bit-reproducible run to run.
@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <vector>
 
@@ -39,6 +40,7 @@ struct MgLevel {
     const double* X = nullptr;    // 4 doubles per node
     DevBuf<int> nbrPtrB, nbrB, diagSlotB;
     DevBuf<double> AvalB, XB;
+    DevBuf<float> Af;             // fp32 copy of Aval streamed by the cycle (PFEM_MG_FP32=0: not used)
     // transfer to the next level
     int nc = 0;
     DevBuf<int> agg, aggPtr, aggNodes, cslot;
@@ -50,21 +52,42 @@ struct MgLevel {
 };
 struct MgHierarchy {
     std::vector<std::unique_ptr<MgLevel>> lev;
-    DevBuf<double> dense;  // coarsest level: [A | I] -> [I | A^-1], nD x 2 nD
+    DevBuf<double> dense;  // coarsest level: A^-1, nD x nD
     DevBuf<int> flag;
     int nD = 0;
     bool denseOk = false;
     bool symbolicValid = false, numericValid = false, symbolicFailed = false;
-    int nu = 2;
+    int nu = 2, nuCoarse = 2;
     double fixedOmega = 0.0;  // > 0: the caller's damping on every level; 0: tuned per level (tuneDamping)
     double over = 1.5;
     bool tuned = false;
     double stamp = 0.0;       // dt of the system the dampings were tuned for
+    // one captured CUDA graph per output vector: a cycle is ~40 launches, most of them on tiny coarse levels
+    struct GraphSlot {
+        double* out = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long sig = 0;
+        int launches = 0;
+    };
+    std::vector<GraphSlot> graphs;
+    bool graphBroken = false;
+    void dropGraphs() {
+        for (auto& g : graphs)
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+        graphs.clear();
+    }
+    ~MgHierarchy() { dropGraphs(); }
 };
 
 namespace {
 
-constexpr int COARSEST_NODES = 64;
+inline long long __double_as_longlong_host(double v) {
+    long long r;
+    memcpy(&r, &v, sizeof r);
+    return r;
+}
+
+constexpr int COARSEST_NODES = 32;
 constexpr int NBR_CAP = 512;  // distinct coarse neighbours a warp can collect
 
 // ---- symbolic ---------------------------------------------------------------------------------------------------------
@@ -403,39 +426,35 @@ __global__ void k_mg_l1_scale(int n, const int* __restrict__ nbrPtr, const int* 
     if (act && l == 0 && rmax) atomicMax(reinterpret_cast<unsigned long long*>(rmax), (unsigned long long)__double_as_longlong(ri));
 }
 
-// coarsest level: dense [A | I]
-__global__ void k_dense_build(int n, int BS, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
-                              const double* __restrict__ Aval, double* __restrict__ D) {
+// coarsest level (<= 32 nodes, <= 128 dofs): dense matrix gathered into shared memory, inverted in place by Gauss-Jordan
+// with partial pivoting (row swaps, columns unscrambled at the end), written back as a dense nD x nD inverse.  One CTA.
+__global__ void __launch_bounds__(1024) k_dense_invert(int n, int BS, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+                                                       const double* __restrict__ Aval, double* __restrict__ Dinv,
+                                                       int* __restrict__ flag) {
+    extern __shared__ double sm[];
     const int nD = n * BS;
-    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < nD * 2 * nD; t += gridDim.x * blockDim.x) {
-        const int r = t / (2 * nD), c = t % (2 * nD);
-        D[t] = (c == nD + r) ? 1.0 : 0.0;
-    }
-}
-__global__ void k_dense_fill(int n, int BS, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
-                             const double* __restrict__ Aval, double* __restrict__ D) {
-    const int nD = n * BS;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    for (int k = nbrPtr[i]; k < nbrPtr[i + 1]; ++k) {
-        const int j = nbr[k];
-        for (int r = 0; r < BS; ++r)
-            for (int c = 0; c < BS; ++c) D[(size_t)(i * BS + r) * 2 * nD + j * BS + c] = Aval[(size_t)k * BS * BS + r * BS + c];
-    }
-}
-// in-place Gauss-Jordan with partial pivoting on the augmented matrix, one CTA (the matrix is <= 256 x 512, L2-resident)
-__global__ void __launch_bounds__(1024) k_dense_invert(int nD, double* __restrict__ D, int* __restrict__ flag) {
+    double* a = sm;                   // nD x nD
+    double* colk = sm + nD * nD;      // nD
+    int* piv = reinterpret_cast<int*>(colk + nD);
     __shared__ double sval[32];
     __shared__ int sidx[32];
     __shared__ int pivRow;
-    __shared__ double pivInv;
-    const int W = 2 * nD;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __shared__ double pivVal;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, w = tid >> 5, nw = nt >> 5;
+    for (int t = tid; t < nD * nD; t += nt) a[t] = 0.0;
+    __syncthreads();
+    for (int i = tid; i < n; i += nt)
+        for (int k = nbrPtr[i]; k < nbrPtr[i + 1]; ++k) {
+            const int j = nbr[k];
+            for (int r = 0; r < BS; ++r)
+                for (int c = 0; c < BS; ++c) a[(i * BS + r) * nD + j * BS + c] = Aval[(size_t)k * BS * BS + r * BS + c];
+        }
+    __syncthreads();
     for (int k = 0; k < nD; ++k) {
         double best = -1.0;
         int bi = k;
-        for (int r = k + threadIdx.x; r < nD; r += blockDim.x) {
-            const double v = fabs(D[(size_t)r * W + k]);
+        for (int r = k + tid; r < nD; r += nt) {
+            const double v = fabs(a[r * nD + k]);
             if (v > best) best = v, bi = r;
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -445,49 +464,56 @@ __global__ void __launch_bounds__(1024) k_dense_invert(int nD, double* __restric
         }
         if (lane == 0) sval[w] = best, sidx[w] = bi;
         __syncthreads();
-        if (threadIdx.x == 0) {
+        if (tid == 0) {
             double b = sval[0];
             int id = sidx[0];
             for (int q = 1; q < nw; ++q)
                 if (sval[q] > b || (sval[q] == b && sidx[q] < id)) b = sval[q], id = sidx[q];
             pivRow = id;
-            if (!(b > 1e-300)) {
-                *flag = 1;
-                pivInv = 0.0;
-            } else
-                pivInv = 1.0 / D[(size_t)id * W + k];
+            piv[k] = id;
+            pivVal = b > 1e-300 ? a[id * nD + k] : 0.0;
+            if (!(b > 1e-300)) *flag = 1;
         }
         __syncthreads();
         const int p = pivRow;
-        const double pinv = pivInv;
-        if (pinv == 0.0) return;
-        // swap rows k and p, scale the pivot row
-        for (int c = threadIdx.x; c < W; c += blockDim.x) {
-            const double a = D[(size_t)p * W + c], b = D[(size_t)k * W + c];
-            D[(size_t)p * W + c] = b;
-            D[(size_t)k * W + c] = a * pinv;
+        const double d = pivVal;
+        if (d == 0.0) return;
+        // swap rows k and p; pivot row: a[k][k] <- 1, then divide by the pivot
+        for (int c = tid; c < nD; c += nt) {
+            const double up = a[p * nD + c], uk = a[k * nD + c];
+            a[p * nD + c] = uk;
+            a[k * nD + c] = ((c == k) ? 1.0 : up) / d;
         }
         __syncthreads();
-        // eliminate column k from every other row: warp per row
-        for (int r = w; r < nD; r += nw) {
+        for (int r = tid; r < nD; r += nt) colk[r] = a[r * nD + k];
+        __syncthreads();
+        for (int t = tid; t < nD * nD; t += nt) {
+            const int r = t / nD, c = t - r * nD;
             if (r == k) continue;
-            double f = 0.0;
-            if (lane == 0) f = D[(size_t)r * W + k];
-            f = __shfl_sync(0xffffffffu, f, 0);  // read before any lane overwrites column k of this row
-            if (f != 0.0)
-                for (int c = lane; c < W; c += 32) D[(size_t)r * W + c] -= f * D[(size_t)k * W + c];
+            const double cur = (c == k) ? 0.0 : a[t];
+            a[t] = cur - colk[r] * a[k * nD + c];
         }
         __syncthreads();
     }
+    for (int k = nD - 1; k >= 0; --k) {  // undo the row swaps as column swaps, in reverse order
+        const int p = piv[k];
+        if (p != k)
+            for (int r = tid; r < nD; r += nt) {
+                const double u = a[r * nD + k];
+                a[r * nD + k] = a[r * nD + p];
+                a[r * nD + p] = u;
+            }
+        __syncthreads();
+    }
+    for (int t = tid; t < nD * nD; t += nt) Dinv[t] = a[t];
 }
-// x = A^-1 b with the inverse in the right half of D: warp per row
-__global__ void __launch_bounds__(1024) k_dense_apply(int nD, const double* __restrict__ D, const double* __restrict__ b,
+// x = A^-1 b: warp per row
+__global__ void __launch_bounds__(1024) k_dense_apply(int nD, const double* __restrict__ Dinv, const double* __restrict__ b,
                                                       double* __restrict__ x) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int W = 2 * nD;
     for (int r = w; r < nD; r += nw) {
         double s = 0;
-        for (int c = lane; c < nD; c += 32) s += D[(size_t)r * W + nD + c] * b[c];
+        for (int c = lane; c < nD; c += 32) s += Dinv[(size_t)r * nD + c] * b[c];
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) x[r] = s;
     }
@@ -547,12 +573,35 @@ __global__ void __launch_bounds__(1024) k_mg_norm2(int nDof, const double* __res
     }
 }
 
+__global__ void k_to_float(size_t n, const double* __restrict__ a, float* __restrict__ f) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f[i] = (float)a[i];
+}
+bool mgFp32() {
+    static const bool v = !(getenv("PFEM_MG_FP32") && atoi(getenv("PFEM_MG_FP32")) == 0);
+    return v;
+}
+
 template <int EPI>
 void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const double* x, double* y, const double* b) {
     SpmvEpi e;
     e.b = b;
     e.Dw = L.Dw.p;
     const int grid = std::max(1, std::min(c->smCount * 8, divUp(L.n, 8)));
+    std::unique_ptr<PhaseScope> ph;
+    if (c->profileDetail && L.Aval == c->Aval.p) ph.reset(new PhaseScope(c, EPI == EPI_SMOOTH ? "MG smooth L0" : "MG resid L0"));
+    if (mgFp32() && L.Af.p) {
+        if (BS == 4 && L.maxNb > 16)  // aggregated levels: ~27 blocks per row
+            k_spmv<4, 2, EPI, float, 4><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1, -1,
+                                                                   nullptr, nullptr, e);
+        else if (BS == 4)
+            k_spmv<4, 3, EPI, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1, -1,
+                                                                nullptr, nullptr, e);
+        else
+            k_spmv<3, 3, EPI, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1, -1,
+                                                                nullptr, nullptr, e);
+        LAUNCH_CHECK(c);
+        return;
+    }
     if (BS == 4)
         k_spmv<4, 3, EPI><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, x, y, nullptr, nullptr, 0, -1, -1, nullptr,
                                                      nullptr, e);
@@ -579,7 +628,8 @@ void cycle(pfem_ctx* c, MgHierarchy& H, int l, const double* b, double* out) {
         else k_mg_jacobi0<3><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.Dw.p, b, dst);
         LAUNCH_CHECK(c);
     };
-    const int nPre = last ? 4 * H.nu : H.nu, nPost = last ? 0 : H.nu;
+    const int nu = l == 0 ? H.nu : H.nuCoarse;  // coarse sweeps are cheap: the fine level may run fewer than the rest
+    const int nPre = last ? 4 * nu : nu, nPost = last ? 0 : nu;
     jac0(cur);
     for (int k = 1; k < nPre; ++k) {
         double* dst = (last && k == nPre - 1) ? out : oth;
@@ -720,6 +770,7 @@ void allocVectors(pfem_ctx* c, MgLevel& L, int BS) {
 void buildSymbolic(pfem_ctx* c, MgHierarchy& H) {
     PhaseScope ph(c, "Preconditioner pattern");
     const int BS = c->dim + 1;
+    H.dropGraphs();
     H.lev.clear();
     H.symbolicFailed = false;
     auto L0 = std::make_unique<MgLevel>();
@@ -827,6 +878,13 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
     for (size_t l = 0; l < H.lev.size(); ++l) {
         MgLevel& L = *H.lev[l];
         static const int dampMode = getenv("PFEM_MG_DAMP") ? atoi(getenv("PFEM_MG_DAMP")) : 0;  // 0 l1 | 1 uniform | 2 tuned
+        std::unique_ptr<PhaseScope> sub(new PhaseScope(c, l == 0 ? "MG smoother setup L0" : "MG smoother setup coarse"));
+        if (mgFp32()) {
+            const size_t nv = (size_t)L.nBlocks * BB;
+            L.Af.reserve(nv + 8);
+            k_to_float<<<std::max(1, std::min(c->smCount * 8, divUp((int64_t)nv, 1024))), 256, 0, c->stream>>>(nv, L.Aval, L.Af.p);
+            LAUNCH_CHECK(c);
+        }
         if (dampMode == 0) {
             L.omega = H.fixedOmega > 0.0 ? H.fixedOmega : 2.0;  // theta: 2.0 measured best-robust (2.5 turns unstable in 2-D)
             blockInverse(c, L, BS, true, L.omega);
@@ -837,7 +895,9 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
             tuneDamping(c, H, L, BS);  // leaves Dw for the accepted damping
         else
             blockInverse(c, L, BS);
+        sub.reset();
         if (l + 1 == H.lev.size()) break;
+        PhaseScope sub2(c, l == 0 ? "MG Galerkin L0" : "MG Galerkin coarse");
         MgLevel& C = *H.lev[l + 1];
         const int nbcap = std::max(C.maxNb, 1);
         const int hwPerBlock = std::max(1, std::min(8, (int)((96 * 1024) / ((size_t)nbcap * BB * sizeof(double)))));
@@ -856,16 +916,15 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
     // coarsest level: dense inverse when it is small enough
     MgLevel& Lc = *H.lev.back();
     H.denseOk = false;
+    PhaseScope sub3(c, "MG coarsest inverse");
     if (Lc.n <= COARSEST_NODES && Lc.nVec == Lc.n) {
         H.nD = Lc.n * BS;
-        H.dense.reserve((size_t)H.nD * 2 * H.nD + 8);
+        H.dense.reserve((size_t)H.nD * H.nD + 8);
         H.flag.reserve(16);
         CUDA_CHECK(cudaMemsetAsync(H.flag.p + 8, 0, sizeof(int), c->stream));
-        k_dense_build<<<64, 256, 0, c->stream>>>(Lc.n, BS, Lc.nbrPtr, Lc.nbr, Lc.Aval, H.dense.p);
-        LAUNCH_CHECK(c);
-        k_dense_fill<<<divUp(Lc.n, 64), 64, 0, c->stream>>>(Lc.n, BS, Lc.nbrPtr, Lc.nbr, Lc.Aval, H.dense.p);
-        LAUNCH_CHECK(c);
-        k_dense_invert<<<1, 1024, 0, c->stream>>>(H.nD, H.dense.p, H.flag.p + 8);
+        const size_t smem = ((size_t)H.nD * H.nD + H.nD) * sizeof(double) + (size_t)H.nD * sizeof(int);
+        CUDA_CHECK(cudaFuncSetAttribute(k_dense_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dense_invert<<<1, 1024, smem, c->stream>>>(Lc.n, BS, Lc.nbrPtr, Lc.nbr, Lc.Aval, H.dense.p, H.flag.p + 8);
         LAUNCH_CHECK(c);
         int bad = 0;
         CUDA_CHECK(cudaMemcpyAsync(&bad, H.flag.p + 8, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -905,7 +964,8 @@ bool mgSetup(pfem_ctx* c) {
     const double over = envOver > 0 ? envOver : 1.5;
     if (omega != H.fixedOmega) H.numericValid = false, H.tuned = false;  // Dw carries the damping
     if (c->asmStamp != H.stamp) H.tuned = false;                          // another dt: the spectrum moved
-    H.nu = nu, H.fixedOmega = omega, H.over = over, H.stamp = c->asmStamp;
+    static const int envNuC = getenv("PFEM_MG_NUC") ? atoi(getenv("PFEM_MG_NUC")) : 0;
+    H.nu = nu, H.nuCoarse = envNuC > 0 ? envNuC : nu + 1, H.fixedOmega = omega, H.over = over, H.stamp = c->asmStamp;
     if (!H.symbolicValid) {
         buildSymbolic(c, H);
         H.tuned = false;
@@ -919,5 +979,59 @@ int mgLevelCount(pfem_ctx* c) { return c->mg ? (int)c->mg->lev.size() : 0; }
 // out = V-cycle(rhs held in mgRhs()): an approximation of A^-1 rhs in the physical variables
 void mgApply(pfem_ctx* c, double* out) {
     PhaseScope ph(c, "Preconditioner apply");
-    cycle(c, *c->mg, 0, c->mg->lev[0]->b.p, out);
+    MgHierarchy& H = *c->mg;
+    static const bool noGraph = getenv("PFEM_MG_NOGRAPH") != nullptr;
+    if (noGraph || H.graphBroken || c->profileDetail) {
+        cycle(c, H, 0, H.lev[0]->b.p, out);
+        return;
+    }
+    // everything a captured cycle bakes in: buffers that can be reallocated, and the cycle parameters
+    unsigned long long sig = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
+    mix((unsigned long long)(uintptr_t)H.lev[0]->Aval), mix((unsigned long long)(uintptr_t)H.lev[0]->nbr);
+    mix((unsigned long long)(uintptr_t)H.lev[0]->b.p), mix((unsigned long long)H.lev.size()), mix((unsigned long long)H.nu), mix((unsigned long long)H.nuCoarse);
+    mix((unsigned long long)__double_as_longlong_host(H.over)), mix(H.denseOk ? 1ull : 0ull), mix((unsigned long long)H.nD);
+    for (auto& L : H.lev) mix((unsigned long long)(uintptr_t)L->Dw.p), mix((unsigned long long)(uintptr_t)L->Af.p), mix((unsigned long long)L->n);
+    for (auto& g : H.graphs)
+        if (g.out == out && g.sig == sig) {
+            CUDA_CHECK(cudaGraphLaunch(g.exec, c->stream));
+            c->launches += g.launches;
+            return;
+        }
+    for (size_t k = 0; k < H.graphs.size();)  // stale capture for this output vector
+        if (H.graphs[k].out == out) {
+            cudaGraphExecDestroy(H.graphs[k].exec);
+            H.graphs.erase(H.graphs.begin() + k);
+        } else
+            ++k;
+    const bool wasProfiling = c->profiling;
+    const int64_t launches0 = c->launches;
+    c->profiling = false;  // no event records inside a capture
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+        try {
+            cycle(c, H, 0, H.lev[0]->b.p, out);
+        } catch (...) {
+            ok = false;
+        }
+        if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess || !graph) ok = false;
+        if (ok && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) ok = false;
+        if (graph) cudaGraphDestroy(graph);
+    }
+    c->profiling = wasProfiling;
+    const int per = (int)(c->launches - launches0);
+    c->launches = launches0;
+    if (!ok) {
+        cudaGetLastError();
+        H.graphBroken = true;
+        cycle(c, H, 0, H.lev[0]->b.p, out);
+        return;
+    }
+    MgHierarchy::GraphSlot g;
+    g.out = out, g.exec = exec, g.sig = sig, g.launches = per;
+    H.graphs.push_back(g);
+    CUDA_CHECK(cudaGraphLaunch(exec, c->stream));
+    c->launches += per;
 }

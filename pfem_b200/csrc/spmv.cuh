@@ -74,6 +74,26 @@ __device__ __forceinline__ void loadSlot(const double* __restrict__ Aval, const 
         L.x23 = make_double2(__ldg(xp + 2), 0.0);
     }
 }
+// fp32 copy of the matrix (multigrid levels: the preconditioner may use a rounded A, it stays a fixed linear operator):
+// half the bytes per block row, products and sums still in fp64
+template <int BS>
+__device__ __forceinline__ void loadSlot(const float* __restrict__ Aval, const double* __restrict__ x, int blk, int col,
+                                         int r, RowLoad<BS>& L) {
+    const float* ap = Aval + ((size_t)blk * BS + r) * BS;
+    const double* xp = x + (size_t)col * BS;
+    if constexpr (BS == 4) {
+        const float4 v = __ldcs(reinterpret_cast<const float4*>(ap));
+        L.a01 = make_double2((double)v.x, (double)v.y);
+        L.a23 = make_double2((double)v.z, (double)v.w);
+        L.x01 = __ldg(reinterpret_cast<const double2*>(xp));
+        L.x23 = __ldg(reinterpret_cast<const double2*>(xp + 2));
+    } else {
+        L.a01 = make_double2((double)__ldcs(ap), (double)__ldcs(ap + 1));
+        L.a23 = make_double2((double)__ldcs(ap + 2), 0.0);
+        L.x01 = make_double2(__ldg(xp), __ldg(xp + 1));
+        L.x23 = make_double2(__ldg(xp + 2), 0.0);
+    }
+}
 template <int BS> __device__ __forceinline__ double dotSlot(const RowLoad<BS>& L) {
     return L.a01.x * L.x01.x + L.a01.y * L.x01.y + L.a23.x * L.x23.x + L.a23.y * L.x23.y;
 }
@@ -86,9 +106,11 @@ struct SpmvEpi {
     const double* Dw = nullptr;
 };
 
-template <int BS, int MINB, int EPI = EPI_PLAIN>
+// SL: block slots per lane group held in registers (8 groups x SL blocks per row on the pipelined path; 2 covers the
+// <= 16 blocks of a tetrahedral mesh row, 4 the ~27 of an aggregated level)
+template <int BS, int MINB, int EPI = EPI_PLAIN, typename AT = double, int SL = 2>
 __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
-                                              const double* __restrict__ Aval, const double* __restrict__ x,
+                                              const AT* __restrict__ Aval, const double* __restrict__ x,
                                               double* __restrict__ y, const double* __restrict__ w1, double* partial,
                                               int stride, int slotYW, int slotYY, const double* __restrict__ scal,
                                               const double* __restrict__ rowScale, const SpmvEpi epi = SpmvEpi()) {
@@ -108,27 +130,29 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             qb0 = __ldg(nbrPtr + i + nw);
             qb1 = __ldg(nbrPtr + i + nw + 1);
         }
-        int c0 = -1, c1 = -1;
-        if (grp < pb1 - pb0) c0 = __ldg(nbr + pb0 + grp);
-        if (grp + 8 < pb1 - pb0) c1 = __ldg(nbr + pb0 + grp + 8);
+        int cs[SL];
+#pragma unroll
+        for (int k = 0; k < SL; ++k) cs[k] = (grp + 8 * k < pb1 - pb0) ? __ldg(nbr + pb0 + grp + 8 * k) : -1;
         for (; i < nNodes; i += nw) {
             int fb0 = 0, fb1 = 0;
             if (i + 2 * nw < nNodes) {
                 fb0 = __ldg(nbrPtr + i + 2 * nw);
                 fb1 = __ldg(nbrPtr + i + 2 * nw + 1);
             }
-            int d0 = -1, d1 = -1;
-            if (grp < qb1 - qb0) d0 = __ldg(nbr + qb0 + grp);
-            if (grp + 8 < qb1 - qb0) d1 = __ldg(nbr + qb0 + grp + 8);
+            int ds[SL];
+#pragma unroll
+            for (int k = 0; k < SL; ++k) ds[k] = (grp + 8 * k < qb1 - qb0) ? __ldg(nbr + qb0 + grp + 8 * k) : -1;
             const int nb = pb1 - pb0;
             double acc = 0;
             if (r < BS) {
-                RowLoad<BS> L0, L1;
-                if (c0 >= 0) loadSlot<BS>(Aval, x, pb0 + grp, c0, r, L0);
-                if (c1 >= 0) loadSlot<BS>(Aval, x, pb0 + grp + 8, c1, r, L1);
-                if (c0 >= 0) acc += dotSlot<BS>(L0);
-                if (c1 >= 0) acc += dotSlot<BS>(L1);
-                for (int s = grp + 16; s < nb; s += 8) {  // rows with more than 16 blocks (rare)
+                RowLoad<BS> Ls[SL];
+#pragma unroll
+                for (int k = 0; k < SL; ++k)
+                    if (cs[k] >= 0) loadSlot<BS>(Aval, x, pb0 + grp + 8 * k, cs[k], r, Ls[k]);
+#pragma unroll
+                for (int k = 0; k < SL; ++k)
+                    if (cs[k] >= 0) acc += dotSlot<BS>(Ls[k]);
+                for (int s = grp + 8 * SL; s < nb; s += 8) {  // rows with more than 8*SL blocks (rare)
                     RowLoad<BS> L;
                     loadSlot<BS>(Aval, x, pb0 + s, __ldg(nbr + pb0 + s), r, L);
                     acc += dotSlot<BS>(L);
@@ -161,7 +185,9 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
                 }
                 if (grp == 0 && r < BS) y[o] = x[o] + upd;
             }
-            pb0 = qb0, pb1 = qb1, qb0 = fb0, qb1 = fb1, c0 = d0, c1 = d1;
+            pb0 = qb0, pb1 = qb1, qb0 = fb0, qb1 = fb1;
+#pragma unroll
+            for (int k = 0; k < SL; ++k) cs[k] = ds[k];
         }
     }
     if (slotYW >= 0 || slotYY >= 0) {

@@ -1,3 +1,7 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-python tools/solve_n.py 69 mg block 2>&1
-python bench.py --steps 3 --warmup 1 2>/dev/null | tail -1
+python tools/solve_n.py 69 mg 2>&1 | grep -v "MG smoother"
+PFEM_MG_NUC=2 python tools/solve_n.py 69 mg:1 2>&1 | grep -v "^n=" | head -1
+PFEM_MG_NUC=3 python tools/solve_n.py 69 mg:1 2>&1 | grep -v "^n=" | head -1
+PFEM_MG_NUC=3 python tools/solve_n.py 69 mg:2 2>&1 | grep -v "^n=" | head -1
+PFEM_MG_NUC=4 python tools/solve_n.py 69 mg:1 2>&1 | grep -v "^n=" | head -1
+PFEM_MG_NUC=3 python tools/solve_n.py 50 mg:1 mg:2 --cloud 2>&1 | grep -v "^n=\|^    "
+PFEM_MG_NUC=3 python tools/solve_n.py 700 mg:1 mg:2 --dim 2 2>&1 | grep -v "^n=\|^    "

@@ -17,6 +17,8 @@ for r in rows:
     u = d['Metric Unit']
     v *= {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 's': 1e6}.get(u, 1e-3)
     name = d['Kernel Name'].split('(')[0].replace('void ', '').replace('<unnamed>::', '')
+    if '--by-grid' in sys.argv:
+        name += ' grid=' + d.get('Grid Size', '?').replace(' ', '')
     agg[name][0] += 1
     agg[name][1] += v
 tot = sum(v[1] for v in agg.values())
@@ -24,6 +26,6 @@ out = ["| kernel | launches | total us | avg us | share |", "|---|---:|---:|---:
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"| {k} | {v[0]} | {v[1]:.1f} | {v[1]/v[0]:.1f} | {100*v[1]/tot:.1f}% |")
 txt = "\n".join(out)
-if len(sys.argv) > 2:
+if len(sys.argv) > 2 and not sys.argv[2].startswith('--'):
     open(sys.argv[2], 'w').write(txt + "\n")
 print(txt)

@@ -53,7 +53,9 @@ def main():
             dq = np.abs(s["q"] - ref).max() / np.abs(ref).max()
             print(f"{kind:14s} used={used} levels={lv} status={s['status']} iters={s['iters']} rel={s['rel_res']:.2e} "
                   f"wall={dt * 1e3:.1f} ms  |q-q0|/|q0|={dq:.1e}", flush=True)
-            names = ["Solve system", "SpMV", "Preconditioner pattern", "Preconditioner setup", "Preconditioner apply"]
+            names = ["Solve system", "SpMV", "Preconditioner pattern", "Preconditioner setup", "Preconditioner apply",
+                     "MG smoother setup L0", "MG smoother setup coarse", "MG Galerkin L0", "MG Galerkin coarse",
+                     "MG coarsest inverse"]
             ph = {k: ctx.profile_get(k) for k in names}
             print("    " + "  ".join(f"{k}={v[0]:.2f}ms/{v[1]}" for k, v in ph.items()), flush=True)
 
