@@ -6,7 +6,7 @@
 
 Workload at N=1 (BASELINE.json configs[3], "C4"): synthetic Kuhn box n=69 -> 1 971 054 tets, 343 000 nodes,
 1 372 000 dof.  One STEP = one body of the PSPG Picard loop: m_buildAbPSPG + m_applyBCPSPG (assembly) followed by the
-linear solve (Jacobi-BiCGSTAB to ||r||/||b|| <= 1e-10), inputs resident in HBM.
+linear solve (multigrid-preconditioned BiCGSTAB to ||r||/||b|| <= 1e-10), inputs resident in HBM.
 At N>1 the box grows with N (n = round(69 N^(1/3)): ~2 M tets per GPU, weak scaling); nodes are split by RCB, every
 rank assembles the rows of its nodes from its elements + one ghost-element layer (no collective in the assembly), the
 Krylov solve exchanges interface values of x before each SpMV and all-reduces its dot products over NCCL/NVLink.
@@ -16,8 +16,10 @@ Krylov solve exchanges interface values of x before each SpMV and all-reduces it
 `krylov`      = the linear solve of the same steps (ms, iterations, SpMV time).  `ms_per_step` = assembly + solve.
 `e2e`         = the same assembly metric through the host-buffer C-ABI calls (H2D of positions, states, qPrev and D2H of
                 the nodal states inside the timed region); `e2e.picard_body_*` = assemble + solve + solution to the host.
-`roofline`    = SpMV, the kernel that dominates the step; `roofline_assembly` = the assembly kernel.  Both: ALGORITHMIC
-                bytes of SURVEY.md section 8(d) / average launch duration / measured HBM copy peak.
+`roofline`    = the fine-level smoothing sweep of the multigrid cycle (SpMV + block-Jacobi epilogue on the fp32 copy of A),
+                the kernel with the largest share of the step; `roofline_spmv` = the fp64 BiCGSTAB SpMV and
+                `roofline_assembly` = the assembly kernel with the ALGORITHMIC bytes of SURVEY.md section 8(d).  All:
+                bytes per launch / average launch duration (CUDA events) / measured HBM copy peak.
 `cpu_baseline`= the reference's CPU structure (oracle/pfem_oracle.cpp) on a bounded sample, rank 0 only.
 
 --impl reference: the CPU arm alone (OpenMP element loop -> triplets -> serial duplicate-summing CSC compression ->
@@ -41,6 +43,8 @@ sys.path.insert(0, ROOT)
 
 from pfem_b200 import meshgen as mg  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one fine-level smoothing sweep at C4 (ncu --set full, profiles/r1_ncu_mg.md)
+TRAFFIC_SMOOTH = 422.7e6
 METRIC = "FE assembly Melem/s (+ Krylov solve ms/step under 'krylov'; % of HBM roofline under 'roofline*')"
 UNIT = "Melem/s"
 REL_TOL = 1e-10
@@ -256,6 +260,16 @@ def run_gpu(args):
         spmv_ms, spmv_calls = ctx.profile_get("SpMV")
         solve_ms, solve_calls = ctx.profile_get("Solve system")
         halo_ms, halo_calls = ctx.profile_get("Halo exchange")
+        pre_setup_ms, pre_setup_calls = ctx.profile_get("Preconditioner setup")
+        pre_apply_ms, pre_apply_calls = ctx.profile_get("Preconditioner apply")
+        precond_used, precond_levels = ctx.pspg_get_preconditioner()
+        ctx.profile_enable(False)
+        # one more (untimed) step with per-kernel phases: the multigrid cycle runs un-graphed so that its fine-level smoothing
+        # sweep -- the kernel with the largest share of the step -- can be timed with events on the launching stream
+        ctx.profile_reset()
+        ctx.profile_enable(2)
+        step()
+        smooth_ms, smooth_calls = ctx.profile_get("MG smooth L0")
         ctx.profile_enable(False)
 
         # ---- end to end through the host-buffer ABI: H2D(x, states, qPrev) + assemble + D2H(nodal states) ---------
@@ -291,17 +305,25 @@ def run_gpu(args):
     # max over ranks of the device times; sums of per-rank sizes
     asm_per = (asm_ms + prep_ms) / max(asm_calls, 1)
     t_max = torch.tensor([step_ms, asm_per, spmv_ms / max(spmv_calls, 1), solve_ms / max(solve_calls, 1), e2e_s, e2e_picard_s,
-                          halo_ms / max(halo_calls, 1) if halo_calls else 0.0], device="cuda", dtype=torch.float64)
+                          halo_ms / max(halo_calls, 1) if halo_calls else 0.0,
+                          smooth_ms / max(smooth_calls, 1), pre_setup_ms / max(pre_setup_calls, 1),
+                          pre_apply_ms / max(pre_apply_calls, 1)], device="cuda", dtype=torch.float64)
     sizes = torch.tensor([float(info.nnzBlocks), float(mesh.n_nodes), float(mesh.n_elems)], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
         dist.all_reduce(sizes, op=dist.ReduceOp.SUM)
-    step_ms, asm_ms_per, spmv_ms_per, solve_ms_per, e2e_s, e2e_picard_s, halo_ms_per = [float(v) for v in t_max]
+    (step_ms, asm_ms_per, spmv_ms_per, solve_ms_per, e2e_s, e2e_picard_s, halo_ms_per, smooth_ms_per, pre_setup_ms_per,
+     pre_apply_ms_per) = [float(v) for v in t_max]
     if nnz is None:
         nnz = int(sizes[0]) * 16  # block storage (no masked-row savings): upper bound of the reference nnz
     value = n_elems_global / (asm_ms_per * 1e-3) / 1e6
     b_asm, b_spmv = algorithmic_bytes(n_nodes_global, n_elems_global, nnz, 3)
     spmv_us = 1e3 * spmv_ms_per
+    # fine-level smoothing sweep of the multigrid cycle: bytes it has to move on its storage:
+    # fp32 4x4 blocks + block column index, per dof the row of Dw (4 doubles), b, x (own) read and y written
+    n_blocks_global = int(sizes[0])
+    b_smooth = n_blocks_global * (16 * 4 + 4) + 4 * n_nodes_global * (4 * 8 + 3 * 8)
+    smooth_us = 1e3 * smooth_ms_per
 
     line = None
     if rank == 0:
@@ -312,7 +334,7 @@ def run_gpu(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"synthetic 3D Kuhn box n={cells} ({n_elems_global} tets, {n_elems_global / world / 1e6:.2f} M per GPU), "
-                                   f"incompressible PSPG: assembly+BC then Jacobi-BiCGSTAB (rel tol {REL_TOL:g}) per step"
+                                   f"incompressible PSPG: assembly+BC then multigrid-preconditioned BiCGSTAB (rel tol {REL_TOL:g}) per step"
                                    + ("" if world == 1 else "; RCB node partition + ghost-element layer, NCCL halo/all-reduce in the solve"),
                        "n_elems": n_elems_global, "n_nodes": n_nodes_global, "n_dof": 4 * n_nodes_global, "nnz": nnz,
                        "l2_policy": "inputs larger than L2 (A = %.0f MB per GPU vs 126 MB L2)" % (nnz * 8 / 1e6 / world),
@@ -322,11 +344,24 @@ def run_gpu(args):
             "pattern_build_ms": 1e3 * t_topo, "partition_host_s": t_part,
             "krylov": {"solve_ms": solve_ms_per, "iters": sol["iters"], "rel_res": sol["rel_res"], "status": sol["status"],
                        "ms_per_iter": solve_ms_per / max(sol["iters"], 1), "spmv_us": spmv_us,
-                       "spmv_launches_per_step": spmv_calls // max(args.steps, 1), "halo_us": 1e3 * halo_ms_per},
-            "roofline": {"kernel": "k_spmv<4>", "bound": "hbm", "achieved": b_spmv / (spmv_us * 1e-6) / 1e9, "peak": agg_peak,
-                         "unit": "GB/s", "frac": b_spmv / (spmv_us * 1e-6) / 1e9 / agg_peak, "traffic": None,
-                         "algorithmic_bytes": b_spmv, "peak_source": peak_src + (" x n_gpus" if world > 1 else ""),
-                         "frac_of_8TBs_nominal": b_spmv / (spmv_us * 1e-6) / 1e9 / (8000.0 * world)},
+                       "spmv_launches_per_step": spmv_calls // max(args.steps, 1), "halo_us": 1e3 * halo_ms_per,
+                       "preconditioner": precond_used, "mg_levels": precond_levels,
+                       "precond_setup_ms": pre_setup_ms_per, "precond_apply_us": 1e3 * pre_apply_ms_per,
+                       "precond_applies_per_step": pre_apply_calls // max(args.steps, 1),
+                       "mg_smooth_l0_us": smooth_us, "mg_smooth_l0_launches_per_step": smooth_calls},
+            "roofline": ({"kernel": "k_spmv<4,float,EPI_SMOOTH> (fine-level multigrid smoothing sweep)", "bound": "hbm",
+                          "achieved": b_smooth / (smooth_us * 1e-6) / 1e9, "peak": agg_peak, "unit": "GB/s",
+                          "frac": b_smooth / (smooth_us * 1e-6) / 1e9 / agg_peak, "traffic": TRAFFIC_SMOOTH if world == 1 else None,
+                          "algorithmic_bytes": b_smooth, "peak_source": peak_src + (" x n_gpus" if world > 1 else ""),
+                          "frac_of_8TBs_nominal": b_smooth / (smooth_us * 1e-6) / 1e9 / (8000.0 * world)}
+                         if smooth_calls else
+                         {"kernel": "k_spmv<4>", "bound": "hbm", "achieved": b_spmv / (spmv_us * 1e-6) / 1e9, "peak": agg_peak,
+                          "unit": "GB/s", "frac": b_spmv / (spmv_us * 1e-6) / 1e9 / agg_peak, "traffic": None,
+                          "algorithmic_bytes": b_spmv, "peak_source": peak_src + (" x n_gpus" if world > 1 else ""),
+                          "frac_of_8TBs_nominal": b_spmv / (spmv_us * 1e-6) / 1e9 / (8000.0 * world)}),
+            "roofline_spmv": {"kernel": "k_spmv<4> (fp64 BiCGSTAB SpMV)", "bound": "hbm", "achieved": b_spmv / (spmv_us * 1e-6) / 1e9,
+                              "peak": agg_peak, "unit": "GB/s", "frac": b_spmv / (spmv_us * 1e-6) / 1e9 / agg_peak, "traffic": None,
+                              "algorithmic_bytes": b_spmv},
             "roofline_assembly": {"kernel": "k_pspg_assemble<3>", "bound": "hbm",
                                   "achieved": b_asm / (asm_ms_per * 1e-3) / 1e9, "peak": agg_peak, "unit": "GB/s",
                                   "frac": b_asm / (asm_ms_per * 1e-3) / 1e9 / agg_peak, "traffic": None, "algorithmic_bytes": b_asm,

@@ -15,8 +15,8 @@
 //   * symbolic part (aggregates, coarse patterns, fine-block -> coarse-slot map) once per topology; numeric part
 //     (Galerkin sums, block inverses, coarsest inverse) once per assembly.  Everything is gather-style and ordered, no
 //     floating-point atomics: the preconditioner, hence the whole solve, is bit-reproducible run to run.
-// On a partitioned mesh every rank builds the hierarchy of its owned rows and drops the ghost columns (an additive-Schwarz
-// combination of per-rank multigrids; no communication inside the cycle).
+// On a partitioned mesh every rank builds the hierarchy of its owned rows; the fine-level sweeps use the global matrix
+// (halo exchange of the iterate before each of them), the coarse levels drop the couplings across ranks.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -583,16 +583,41 @@ bool mgFp32() {
 
 template <int EPI>
 void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const double* x, double* y, const double* b) {
+    // partitioned mesh: the fine-level sweeps act on the GLOBAL matrix (ghost entries of the iterate follow their owners);
+    // the coarse levels stay rank-local
+    if (c->nRanks > 1 && L.Aval == c->Aval.p) commHalo(c, const_cast<double*>(x), nullptr, BS);
     SpmvEpi e;
     e.b = b;
     e.Dw = L.Dw.p;
     const int grid = std::max(1, std::min(c->smCount * 8, divUp(L.n, 8)));
     std::unique_ptr<PhaseScope> ph;
     if (c->profileDetail && L.Aval == c->Aval.p) ph.reset(new PhaseScope(c, EPI == EPI_SMOOTH ? "MG smooth L0" : "MG resid L0"));
+    static const bool minb4 = !(getenv("PFEM_MG_MINB4") && atoi(getenv("PFEM_MG_MINB4")) == 0);  // 64 registers, 32 warps/SM
+    // cp.async ring variant: measured equal to the 64-register kernel (126 vs 118 us smoothing sweep at 2 M tets): the sweep is
+    // bound by instruction issue and gather latency (ncu: 47 % issue active, 67 M instructions, DRAM 3.1 TB/s), not by the
+    // bytes of A in flight.  Opt-in (PFEM_MG_RING=3|4|6).
+    static const int ringDepth = getenv("PFEM_MG_RING") ? atoi(getenv("PFEM_MG_RING")) : 0;
+    if (mgFp32() && L.Af.p && BS == 4 && L.maxNb <= 16 && ringDepth > 0) {
+        // fine level of a tetrahedral mesh: cp.async ring, DEPTH-1 rows of A in flight per warp
+        const int g = std::max(1, std::min(c->smCount * 4, divUp(L.n, 8)));
+        auto launch = [&](auto kern, int depth) {
+            const size_t smem = (size_t)8 * depth * 16 * 16 * sizeof(float);
+            if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<g, 256, smem, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, e);
+        };
+        if (ringDepth == 3) launch(k_spmv_ring<EPI, float, 3, 4>, 3);
+        else if (ringDepth == 6) launch(k_spmv_ring<EPI, float, 6, 4>, 6);
+        else launch(k_spmv_ring<EPI, float, 4, 4>, 4);
+        LAUNCH_CHECK(c);
+        return;
+    }
     if (mgFp32() && L.Af.p) {
         if (BS == 4 && L.maxNb > 16)  // aggregated levels: ~27 blocks per row
             k_spmv<4, 2, EPI, float, 4><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1, -1,
                                                                    nullptr, nullptr, e);
+        else if (BS == 4 && minb4)
+            k_spmv<4, 4, EPI, float><<<std::max(1, std::min(c->smCount * 8, divUp(L.n, 8))), 256, 0, c->stream>>>(
+                L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1, -1, nullptr, nullptr, e);
         else if (BS == 4)
             k_spmv<4, 3, EPI, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1, -1,
                                                                 nullptr, nullptr, e);
@@ -981,7 +1006,7 @@ void mgApply(pfem_ctx* c, double* out) {
     PhaseScope ph(c, "Preconditioner apply");
     MgHierarchy& H = *c->mg;
     static const bool noGraph = getenv("PFEM_MG_NOGRAPH") != nullptr;
-    if (noGraph || H.graphBroken || c->profileDetail) {
+    if (noGraph || H.graphBroken || c->profileDetail || c->nRanks > 1) {  // no NCCL calls inside a capture
         cycle(c, H, 0, H.lev[0]->b.p, out);
         return;
     }

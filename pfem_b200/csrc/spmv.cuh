@@ -143,6 +143,24 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
 #pragma unroll
             for (int k = 0; k < SL; ++k) ds[k] = (grp + 8 * k < qb1 - qb0) ? __ldg(nbr + qb0 + grp + 8 * k) : -1;
             const int nb = pb1 - pb0;
+            // epilogue operands are fetched with the row, not after its reduction (one more exposed latency per row otherwise)
+            // (only where the register budget allows it: at 64 registers the hoisted operands spill and cost more than they save)
+            constexpr bool HOIST = MINB <= 3;
+            const bool epiLane = grp == 0 && r < BS;
+            const size_t oe = (size_t)i * BS + (r < BS ? r : 0);
+            double e0 = 0, e1 = 0;
+            if (HOIST && epiLane) {
+                if constexpr (EPI == EPI_PLAIN) {
+                    if (rowScale) e0 = rowScale[oe];
+                    if (slotYW >= 0) e1 = w1[oe];
+                } else if constexpr (EPI == EPI_RESID) {
+                    e0 = epi.b[oe];
+                } else {
+                    e0 = epi.b[oe];
+                    e1 = x[oe];
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(epi.Dw + oe * BS));  // the row of Dw: no registers held
+                }
+            }
             double acc = 0;
             if (r < BS) {
                 RowLoad<BS> Ls[SL];
@@ -161,29 +179,33 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             acc += __shfl_xor_sync(0xffffffffu, acc, 4);
             acc += __shfl_xor_sync(0xffffffffu, acc, 8);
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (!HOIST && epiLane) {
+                if constexpr (EPI == EPI_PLAIN) {
+                    if (rowScale) e0 = rowScale[oe];
+                    if (slotYW >= 0) e1 = w1[oe];
+                } else {
+                    e0 = epi.b[oe];
+                    if constexpr (EPI == EPI_SMOOTH) e1 = x[oe];
+                }
+            }
             if constexpr (EPI == EPI_PLAIN) {
-                if (grp == 0 && r < BS) {
-                    const size_t o = (size_t)i * BS + r;
-                    if (rowScale) acc *= rowScale[o];  // symmetric Jacobi scaling: y = S A x
-                    y[o] = acc;
-                    if (slotYW >= 0) accYW += acc * w1[o];
+                if (epiLane) {
+                    if (rowScale) acc *= e0;  // symmetric Jacobi scaling: y = S A x
+                    y[oe] = acc;
+                    if (slotYW >= 0) accYW += acc * e1;
                     if (slotYY >= 0) accYY += acc * acc;
                 }
             } else if constexpr (EPI == EPI_RESID) {
-                if (grp == 0 && r < BS) {
-                    const size_t o = (size_t)i * BS + r;
-                    y[o] = epi.b[o] - acc;
-                }
+                if (epiLane) y[oe] = e0 - acc;
             } else {
-                const size_t o = (size_t)i * BS + (r < BS ? r : 0);
-                const double res = (grp == 0 && r < BS) ? epi.b[o] - acc : 0.0;
+                const double res = epiLane ? e0 - acc : 0.0;
                 double upd = 0;
 #pragma unroll
                 for (int cc = 0; cc < BS; ++cc) {
                     const double rc = __shfl_sync(0xffffffffu, res, cc);
-                    if (grp == 0 && r < BS) upd += epi.Dw[o * BS + cc] * rc;
+                    if (epiLane) upd += epi.Dw[oe * BS + cc] * rc;
                 }
-                if (grp == 0 && r < BS) y[o] = x[o] + upd;
+                if (epiLane) y[oe] = e1 + upd;
             }
             pb0 = qb0, pb1 = qb1, qb0 = fb0, qb1 = fb1;
 #pragma unroll
@@ -197,5 +219,132 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
     }
 }
 
+// ---- SpMV with an asynchronous shared-memory ring for A (4x4 blocks) ------------------------------------------------------
+// The register-pipelined kernel above keeps ONE block row (~1-2 KB) of A in flight per warp; with the 24-32 warps an SM
+// holds that is below the ~45 KB per SM that HBM3e needs to stream at full rate, so it is latency-bound -- clearly so once
+// A is fp32 (multigrid levels).  Here every warp owns a DEPTH-deep ring of row buffers filled with cp.async (16 B per lane,
+// no registers, no copy-engine descriptors): DEPTH-1 rows per warp stay in flight while the current one is multiplied.
+// Column indices and the x gathers (L2-resident) stay on the LDG path.  Rows with more than ROWCAP blocks: the tail beyond
+// ROWCAP is read directly.
+__device__ __forceinline__ void cpAsync16(void* smemDst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int EPI, typename AT, int DEPTH, int MINB, int ROWCAP = 16>
+__global__ void __launch_bounds__(256, MINB) k_spmv_ring(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
+                                                   const AT* __restrict__ Aval, const double* __restrict__ x,
+                                                   double* __restrict__ y, const SpmvEpi epi) {
+    constexpr int BS = 4, BB = 16;
+    constexpr int CPB = BB * (int)sizeof(AT) / 16;       // 16-byte chunks per block: 4 (fp32) | 8 (fp64)
+    constexpr int ROWBYTES = ROWCAP * BB * (int)sizeof(AT);
+    extern __shared__ __align__(16) unsigned char ringAll[];
+    const int lane = threadIdx.x & 31, grp = lane >> 2, r = lane & 3;
+    const int wib = threadIdx.x >> 5, warpsPerBlock = blockDim.x >> 5;
+    const int gw = blockIdx.x * warpsPerBlock + wib, nw = gridDim.x * warpsPerBlock;
+    unsigned char* ring = ringAll + (size_t)wib * DEPTH * ROWBYTES;
+
+    // block ranges of rows i, i+nw, ..., i+DEPTH*nw (the last one is only a prefetch of the pointers)
+    int pb[DEPTH + 1], pe[DEPTH + 1];
+#pragma unroll
+    for (int d = 0; d <= DEPTH; ++d) {
+        const int row = gw + d * nw;
+        pb[d] = pe[d] = 0;
+        if (row < nNodes) {
+            pb[d] = __ldg(nbrPtr + row);
+            pe[d] = __ldg(nbrPtr + row + 1);
+        }
+    }
+    auto issue = [&](int b0, int b1, int slot) {
+        const int nchunk = min(b1 - b0, ROWCAP) * CPB;
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(Aval + (size_t)b0 * BB);
+        unsigned char* dst = ring + (size_t)slot * ROWBYTES;
+        for (int e = lane; e < nchunk; e += 32) cpAsync16(dst + (size_t)e * 16, src + (size_t)e * 16);
+        cpAsyncCommit();
+    };
+#pragma unroll
+    for (int d = 0; d < DEPTH - 1; ++d) issue(pb[d], pe[d], d);
+    int cs[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) cs[k] = (grp + 8 * k < pe[0] - pb[0]) ? __ldg(nbr + pb[0] + grp + 8 * k) : -1;
+    int slot = 0;
+    for (int i = gw; i < nNodes; i += nw) {
+        // keep the ring full: row i + (DEPTH-1) nw goes into the slot that was consumed last iteration
+        issue(pb[DEPTH - 1], pe[DEPTH - 1], (slot + DEPTH - 1) % DEPTH);
+        int nb0 = 0, nb1 = 0;
+        if (i + (DEPTH + 1) * nw < nNodes) {
+            nb0 = __ldg(nbrPtr + i + (DEPTH + 1) * nw);
+            nb1 = __ldg(nbrPtr + i + (DEPTH + 1) * nw + 1);
+        }
+        int ds[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) ds[k] = (grp + 8 * k < pe[1] - pb[1]) ? __ldg(nbr + pb[1] + grp + 8 * k) : -1;
+        const int b0 = pb[0], nb = pe[0] - pb[0];
+        // x gathers first (longest latency), then wait for this row's A
+        double2 x01[2], x23[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (cs[k] >= 0) {
+                const double* xp = x + (size_t)cs[k] * BS;
+                x01[k] = __ldg(reinterpret_cast<const double2*>(xp));
+                x23[k] = __ldg(reinterpret_cast<const double2*>(xp + 2));
+            }
+        const size_t o = (size_t)i * BS + r;
+        double e0 = 0, e1 = 0;
+        if (grp == 0) {
+            if constexpr (EPI != EPI_PLAIN) e0 = epi.b[o];
+            if constexpr (EPI == EPI_SMOOTH) {
+                e1 = x[o];
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(epi.Dw + o * BS));
+            }
+        }
+        cpAsyncWait<DEPTH - 1>();
+        __syncwarp();
+        const unsigned char* buf = ring + (size_t)slot * ROWBYTES;
+        double acc = 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (cs[k] >= 0) {
+                const AT* ap = reinterpret_cast<const AT*>(buf) + ((grp + 8 * k) * BS + r) * BS;
+                if constexpr (sizeof(AT) == 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(ap);
+                    acc += (double)v.x * x01[k].x + (double)v.y * x01[k].y + (double)v.z * x23[k].x + (double)v.w * x23[k].y;
+                } else {
+                    const double2 a01 = *reinterpret_cast<const double2*>(ap), a23 = *reinterpret_cast<const double2*>(ap + 2);
+                    acc += a01.x * x01[k].x + a01.y * x01[k].y + a23.x * x23[k].x + a23.y * x23[k].y;
+                }
+            }
+        for (int s = grp + 16; s < nb; s += 8) {  // rows with more than 16 blocks (rare): direct loads
+            RowLoad<BS> L;
+            loadSlot<BS>(Aval, x, b0 + s, __ldg(nbr + b0 + s), r, L);
+            acc += dotSlot<BS>(L);
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+        if constexpr (EPI == EPI_RESID) {
+            if (grp == 0) y[o] = e0 - acc;
+        } else if constexpr (EPI == EPI_SMOOTH) {
+            const double res = (grp == 0) ? e0 - acc : 0.0;
+            double upd = 0;
+#pragma unroll
+            for (int cc = 0; cc < BS; ++cc) {
+                const double rc = __shfl_sync(0xffffffffu, res, cc);
+                if (grp == 0) upd += epi.Dw[o * BS + cc] * rc;
+            }
+            if (grp == 0) y[o] = e1 + upd;
+        } else {
+            if (grp == 0) y[o] = acc;
+        }
+        __syncwarp();  // every lane is done with this slot before the next iteration refills it
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d) pb[d] = pb[d + 1], pe[d] = pe[d + 1];
+        pb[DEPTH] = nb0, pe[DEPTH] = nb1;
+        cs[0] = ds[0], cs[1] = ds[1];
+        slot = (slot + 1) % DEPTH;
+    }
+    cpAsyncWait<0>();
+}
 
 }  // namespace

@@ -42,7 +42,7 @@ def main():
             for rep in range(2):
                 ctx.pspg_assemble_resident(par)
                 ctx.profile_reset()
-                ctx.profile_enable(rep == 1)
+                ctx.profile_enable((2 if '--detail' in sys.argv else 1) if rep == 1 else 0)
                 t0 = time.perf_counter()
                 s = ctx.pspg_solve(tol, maxit, fetch=True)
                 dt = time.perf_counter() - t0
@@ -55,7 +55,7 @@ def main():
                   f"wall={dt * 1e3:.1f} ms  |q-q0|/|q0|={dq:.1e}", flush=True)
             names = ["Solve system", "SpMV", "Preconditioner pattern", "Preconditioner setup", "Preconditioner apply",
                      "MG smoother setup L0", "MG smoother setup coarse", "MG Galerkin L0", "MG Galerkin coarse",
-                     "MG coarsest inverse"]
+                     "MG coarsest inverse", "MG smooth L0", "MG resid L0"]
             ph = {k: ctx.profile_get(k) for k in names}
             print("    " + "  ".join(f"{k}={v[0]:.2f}ms/{v[1]}" for k, v in ph.items()), flush=True)
 
