@@ -557,7 +557,10 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
     // the multigrid cycle is not guaranteed to be a contraction on every mesh: give it a bounded number of iterations and
     // hand over to node-block Jacobi (from the current iterate) if it has not converged by then
     const int maxIterAll = maxIter;
-    if (kind == PFEM_PRECOND_MG && c->precondKind == PFEM_PRECOND_AUTO) maxIter = std::min(maxIter, 300);
+    const bool mgAuto = kind == PFEM_PRECOND_MG && c->precondKind == PFEM_PRECOND_AUTO;
+    bool mgGiveUp = false, mgDiverged = false;
+    double rrFirst = -1.0;
+    if (mgAuto) maxIter = std::min(maxIter, 300);
     const double* W = nullptr;
     if (kind == PFEM_PRECOND_BLOCK) {
         c->Wblk.reserve((size_t)c->nRows * k.BS * k.BS + 8);
@@ -627,9 +630,21 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
                 it = (int)c->hScal[SC_ITERS];  // iterations completed when the test fired
             } else if (rrLatest <= c->hScal[SC_TOL2] || !(rrLatest == rrLatest)) {
                 done = true;
+            } else if (mgAuto) {
+                // node-block Jacobi smoothing is not a smoother in every regime (large dt, viscosity-dominated: the (v,p)
+                // coupling dominates the diagonal blocks).  Judge the cycle early: a residual two orders above where it
+                // started, or less than 1.5 orders of magnitude after 50 iterations (> 300 iterations projected; a multigrid
+                // iteration costs ~5 Jacobi ones) -> hand over to node-block Jacobi.
+                if (rrFirst < 0.0) rrFirst = rrLatest;
+                if (rrLatest > 1e4 * rrFirst) mgGiveUp = mgDiverged = done = true;
+                else if (it >= 50 && rrLatest > 1e-3 * rrFirst) mgGiveUp = done = true;
             }
         }
         totalIters += it;
+        if (mgGiveUp) {
+            status = PFEM_NOT_CONVERGED;
+            break;
+        }
         // true residual
         const double bnorm = sqrt(c->hScal[SC_BNORM2]);
         if (bnorm == 0.0) {  // b = 0 -> x = 0
@@ -656,7 +671,7 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
         int it2 = 0;
         c->precondKind = PFEM_PRECOND_BLOCK;
         try {
-            status = krylovSolve(c, relTol, maxIterAll - totalIters, &it2, &relRes, status != PFEM_NAN);
+            status = krylovSolve(c, relTol, maxIterAll - totalIters, &it2, &relRes, status != PFEM_NAN && !mgDiverged);
         } catch (...) {
             c->precondKind = PFEM_PRECOND_AUTO;
             throw;

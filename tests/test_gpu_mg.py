@@ -74,3 +74,17 @@ def test_tiny_mesh_keeps_block_jacobi():
     mesh, q, q_prev, par = pspg_case(2, 4)          # 25 nodes: no second level
     sol = _solve(mesh, q, q_prev, par, "auto")
     assert sol["status"] == 0 and sol["used"] == "block" and sol["levels"] == 1
+
+
+def test_auto_hands_over_when_the_cycle_is_not_a_contraction():
+    """Viscosity-dominated regime: node-block Jacobi is no smoother for the coupled system, the multigrid-preconditioned
+    iteration diverges; AUTO must detect it early and finish with node-block Jacobi (same answer as BLOCK alone)."""
+    mesh = mg.kuhn_box(3, 12)
+    q, q_prev = mg.pspg_state(mesh)
+    par = orc.pspg_param_array(1000.0, 10.0, 1e-2, mg.gravity(3))
+    blk = _solve(mesh, q, q_prev, par, "block", tol=1e-11)
+    aut = _solve(mesh, q, q_prev, par, "auto", tol=1e-11)
+    assert blk["status"] == 0 and aut["status"] == 0, (blk, aut)
+    assert aut["used"] == "block"
+    assert aut["iters"] < 2 * blk["iters"] + 100
+    assert rel_err(aut["q"], blk["q"]) < TOL_Q
