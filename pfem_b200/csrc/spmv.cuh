@@ -75,25 +75,35 @@ __device__ __forceinline__ void loadSlot(const double* __restrict__ Aval, const 
     }
 }
 // fp32 copy of the matrix (multigrid levels: the preconditioner may use a rounded A, it stays a fixed linear operator):
-// half the bytes per block row, products and sums still in fp64
+// half the bytes per block row, products and sums still in fp64.  The row stays packed (4 registers) until it is used.
+template <int BS> struct RowLoadF {
+    float4 a;
+    double2 x01, x23;
+};
 template <int BS>
 __device__ __forceinline__ void loadSlot(const float* __restrict__ Aval, const double* __restrict__ x, int blk, int col,
-                                         int r, RowLoad<BS>& L) {
+                                         int r, RowLoadF<BS>& L) {
     const float* ap = Aval + ((size_t)blk * BS + r) * BS;
     const double* xp = x + (size_t)col * BS;
     if constexpr (BS == 4) {
-        const float4 v = __ldcs(reinterpret_cast<const float4*>(ap));
-        L.a01 = make_double2((double)v.x, (double)v.y);
-        L.a23 = make_double2((double)v.z, (double)v.w);
+        L.a = __ldcs(reinterpret_cast<const float4*>(ap));
         L.x01 = __ldg(reinterpret_cast<const double2*>(xp));
         L.x23 = __ldg(reinterpret_cast<const double2*>(xp + 2));
     } else {
-        L.a01 = make_double2((double)__ldcs(ap), (double)__ldcs(ap + 1));
-        L.a23 = make_double2((double)__ldcs(ap + 2), 0.0);
+        L.a = make_float4(__ldcs(ap), __ldcs(ap + 1), __ldcs(ap + 2), 0.f);
         L.x01 = make_double2(__ldg(xp), __ldg(xp + 1));
         L.x23 = make_double2(__ldg(xp + 2), 0.0);
     }
 }
+template <int BS> __device__ __forceinline__ double dotSlot(const RowLoadF<BS>& L) {
+    return (double)L.a.x * L.x01.x + (double)L.a.y * L.x01.y + (double)L.a.z * L.x23.x + (double)L.a.w * L.x23.y;
+}
+template <int BS, typename AT> struct RowLoadOf {
+    using type = RowLoad<BS>;
+};
+template <int BS> struct RowLoadOf<BS, float> {
+    using type = RowLoadF<BS>;
+};
 template <int BS> __device__ __forceinline__ double dotSlot(const RowLoad<BS>& L) {
     return L.a01.x * L.x01.x + L.a01.y * L.x01.y + L.a23.x * L.x23.x + L.a23.y * L.x23.y;
 }
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             }
             double acc = 0;
             if (r < BS) {
-                RowLoad<BS> Ls[SL];
+                typename RowLoadOf<BS, AT>::type Ls[SL];
 #pragma unroll
                 for (int k = 0; k < SL; ++k)
                     if (cs[k] >= 0) loadSlot<BS>(Aval, x, pb0 + grp + 8 * k, cs[k], r, Ls[k]);
@@ -171,7 +181,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
                 for (int k = 0; k < SL; ++k)
                     if (cs[k] >= 0) acc += dotSlot<BS>(Ls[k]);
                 for (int s = grp + 8 * SL; s < nb; s += 8) {  // rows with more than 8*SL blocks (rare)
-                    RowLoad<BS> L;
+                    typename RowLoadOf<BS, AT>::type L;
                     loadSlot<BS>(Aval, x, pb0 + s, __ldg(nbr + pb0 + s), r, L);
                     acc += dotSlot<BS>(L);
                 }
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmv_ring(int nNodes, const int* 
                 }
             }
         for (int s = grp + 16; s < nb; s += 8) {  // rows with more than 16 blocks (rare): direct loads
-            RowLoad<BS> L;
+            typename RowLoadOf<BS, AT>::type L;
             loadSlot<BS>(Aval, x, b0 + s, __ldg(nbr + b0 + s), r, L);
             acc += dotSlot<BS>(L);
         }
