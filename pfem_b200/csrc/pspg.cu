@@ -2,12 +2,15 @@
 // (MomContEquationPSPG.inl:7-146 m_buildAbPSPG, :149-235 m_applyBCPSPG, :238-259 m_computeTauPSPG) on the device.
 //
 // Design (B200: HBM-bound, no tensor cores -- 4x4 blocks are far too small):
-//   * node-row GATHER instead of element scatter: one warp owns one node i == one (dim+1)-row block row of A.
-//     Phase 1: lanes = incident elements of i; each lane recomputes that element's geometry from coordinates
-//              (Element.cpp:15-135, nothing stored per element), tau, and the five scalar coefficients of the closed
-//              form and stages them in shared memory.
-//     Phase 2: lanes = (neighbour block, row) pairs; each lane sums, in ASCENDING ELEMENT ORDER (the order in which
-//              setFromTriplets sums duplicates), the contributions of the elements that contain the edge (i,j).
+//   * node-row GATHER instead of element scatter: one persistent warp owns one node i == one (dim+1)-row block row of A,
+//     software-pipelined (header and per-lane words of the next node are fetched while this one is computed).
+//     Phase 0: lanes = neighbours; each neighbour's nodal record (x, v_prev, |v_cur|) is staged once in shared memory.
+//     Phase 1: lanes = incident elements of i; each lane rebuilds that element's geometry from the staged records
+//              (Element.cpp:15-135, nothing stored per element), tau, and writes a 208-byte record (grad N, V, tau V, the
+//              element's contribution to the RHS rows of i, slot bytes) to shared memory.
+//     Phase 2: lane = one (dim+1)^2 block: 28 lanes own the off-diagonal blocks and walk, in ASCENDING ELEMENT ORDER (the
+//              order in which setFromTriplets sums duplicates), the bit mask of the elements around edge (i,j), two
+//              elements per trip; 4 lanes share the diagonal block and the RHS rows, reduced through shared memory.
 //   * A is written exactly once, fully coalesced (1 KB per warp store), no atomics, bit-reproducible run to run.
 //   * m_applyBCPSPG is fused into the epilogue: row masks / identity rows (PSPG.inl:68,81,108-128), Dirichlet column
 //     elimination (PSPG.inl:216-228) as a per-row operation, free-node RHS (PSPG.inl:193-204), and 1/diag for the

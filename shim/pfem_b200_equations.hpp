@@ -97,6 +97,14 @@ public:
         m_needNormalCurv = false;
         const int rc = pfem_create(&m_ctx, dim, pfem_b200_shim::deviceFromEnv());
         if (rc != PFEM_OK) throw std::runtime_error(std::string("pfem_create: ") + pfem_last_error(nullptr));
+        // optional new key: preconditioner = "auto" | "point" | "block" | "mg"   (default auto: multigrid with hand-over)
+        if (m_equationParams[0].doesVarExist("preconditioner")) {
+            const std::string pre = m_equationParams[0].template checkAndGet<std::string>("preconditioner");
+            const int kind = pre == "auto" ? PFEM_PRECOND_AUTO : pre == "point" ? PFEM_PRECOND_POINT : pre == "block" ? PFEM_PRECOND_BLOCK
+                           : pre == "mg" ? PFEM_PRECOND_MG : -1;
+            if (kind < 0) throw std::runtime_error("unknown preconditioner: " + pre);
+            pfem_b200_shim::check(m_ctx, pfem_pspg_set_preconditioner(m_ctx, kind, 0, 0.0), "pfem_pspg_set_preconditioner");
+        }
     }
     ~MomContEqIncompNewtonB200() override { pfem_destroy(m_ctx); }
 
