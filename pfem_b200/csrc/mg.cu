@@ -402,13 +402,17 @@ __global__ void k_mg_l1_scale(int n, const int* __restrict__ nbrPtr, const int* 
     const int b0 = act ? nbrPtr[i] : 0, b1 = act ? nbrPtr[i + 1] : 0;
     const unsigned hm = 0xffffu << (threadIdx.x & 16);  // this half-warp
     for (int k = b0; k < b1; ++k) {
+        // every lane fetches its own entry of the block once (one coalesced 128-byte row per half-warp); the 4x4 product
+        // takes the column entries from the owning lanes
+        const double aMine = ent ? Aval[(size_t)k * BB + l] : 0.0;
         double p = 0;
-        if (ent) {
 #pragma unroll
-            for (int q = 0; q < BS; ++q) p += dinvRow[q] * Aval[(size_t)k * BB + q * BS + cc];
-            p *= sc[(size_t)nbr[k] * BS + cc] / sc[(size_t)i * BS + r];  // S_i^-1 (D^-1 A)_ij S_j
+        for (int q = 0; q < BS; ++q) {
+            const double aq = __shfl_sync(hm, aMine, (threadIdx.x & 16) + min(q * BS + cc, 15));
+            p += dinvRow[q] * aq;
         }
-        p = fabs(p);
+        if (ent) p *= sc[(size_t)nbr[k] * BS + cc] / sc[(size_t)i * BS + r];  // S_i^-1 (D^-1 A)_ij S_j
+        p = ent ? fabs(p) : 0.0;
         // row sums over cc (lanes of the same r), then max over r
         double rs = 0;
 #pragma unroll

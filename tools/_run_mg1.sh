@@ -1,3 +1,3 @@
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/multi_gpu_check.py 24 2>&1 | grep "pspg\|MULTI\|wc\]" | tail -6
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 3 --warmup 1 2>gpurun_out/b2err.log | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','krylov')})"
-tail -2 gpurun_out/b2err.log
+python tools/small_configs.py 2>&1 | head -3
+PFEM_PRECOND=block python tools/small_configs.py 2>&1 | head -2
+python -m pytest tests/test_gpu_mg.py -m gpu -x -q 2>&1 | tail -2
