@@ -1,7 +1,8 @@
 """ctypes front-end of the CPU oracle (oracle/pfem_oracle.cpp) -- TEST INFRASTRUCTURE ONLY.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / `--impl reference` legs may
-import this module.  PARITY UNPINNED: see the header of pfem_oracle.cpp.
+import this module.  Pinned against the reference's own sources built by oracle/refbuild (tests/golden/,
+tests/test_oracle_vs_reference.py); see the header of pfem_oracle.cpp for the caveat.
 """
 from __future__ import annotations
 

@@ -9,12 +9,19 @@
 // scatters -- and NOT the closed forms the CUDA kernels use, so that a CUDA-vs-oracle
 // comparison is a comparison of two independent derivations.
 //
-// PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for this path
-// (CMakeLists.txt:88 enable_testing() with zero add_test) and cannot be compiled in this
-// environment (needs Eigen, CGAL, gmsh, Lua/sol2 -- all absent, no network).  This file is
-// therefore pinned only by (i) a second, independent numpy restatement
-// (oracle/literal_numpy.py), (ii) algebraic invariants (tests/test_oracle_invariants.py)
-// and (iii) scipy SuperLU as the stand-in for Eigen::SparseLU.
+// PARITY PINNED AGAINST THE REFERENCE'S OWN CODE (with one stated caveat).  The reference ships no tests, golden
+// vectors or fixtures for this path (CMakeLists.txt:88 enable_testing() with zero add_test) and its real build needs
+// Eigen, CGAL, gmsh and Lua/sol2 -- all absent here, no network.  oracle/refbuild/ therefore compiles the reference's
+// UNMODIFIED hot-path sources where they lie under /root/reference (Element.cpp, Mesh.cpp, MatricesBuilder.inl,
+// MomContEquation*.inl, PicardAlgo.cpp, WCompNewton/{Cont,Mom}Equation.inl, both Solver.cpp, ...) against original
+// stand-in headers for the Eigen/sol2/gmsh calls they make, into oracle/_ref/libpfem_ref.so; its outputs are committed
+// as tests/golden/*.npz (generator: tests/golden/make_golden.py).  tests/test_oracle_vs_reference.py checks this file
+// against those fixtures and, where the library is present, against live runs: assembled CSC pattern identical, values,
+// RHS, tau, Picard fields/iteration counts, explicit steps and CFL dt all agree (in practice bit for bit).
+// Caveat: the dense/sparse arithmetic library underneath that build is the stand-in, not Eigen itself -- the element
+// and assembly LOGIC is the reference's, last-bit rounding of Eigen's own kernels is not observable here.
+// Additional pins: a second independent numpy restatement (oracle/literal_numpy.py), algebraic invariants
+// (tests/test_oracle_invariants.py), scipy SuperLU as the stand-in for Eigen::SparseLU.
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
 // may load this library.

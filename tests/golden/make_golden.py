@@ -1,0 +1,126 @@
+"""Generates tests/golden/*.npz from the REFERENCE'S OWN code (oracle/_ref/libpfem_ref.so, see oracle/refbuild/).
+
+Run in the development container, where /root/reference exists:   python tests/golden/make_golden.py
+The GPU box has no /root/reference; the fixtures written here are what travels (together with the prebuilt .so).
+
+Every fixture stores the complete input (mesh arrays, states, parameters) next to the reference output, so the tests
+never depend on the mesh generator reproducing the same numbers.  Outputs come from: MomContEqIncompNewton::
+m_buildAbPSPG / m_applyBCPSPG / m_computeTauPSPG / solve (Picard), SolverWCompNewton::computeNextDT /
+m_solveWCompNewtonNoT, MatrixBuilder get{M,K,D,L,C,F,H}, Element::computeJ/DetJ/InvJ/getRin, Mesh quadrature tables.
+The direct solver behind the stand-in Eigen::SparseLU is SciPy SuperLU (COLAMD) for the Picard fixtures.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import helpers as H  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from oracle import ref  # noqa: E402
+from pfem_b200 import meshgen as mg  # noqa: E402
+
+
+def mesh_arrays(mesh):
+    return dict(dim=np.int64(mesh.dim), x=mesh.x, conn=mesh.conn, flags=mesh.flags, dir_mask=mesh.dir_mask, dir_val=mesh.dir_val)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def pspg_fixture(name, mesh, q, q_prev, par):
+    dim, nn = mesh.dim, mesh.n_nodes
+    with ref.RefCase(mesh, "pspg", par) as rc:
+        rc.set_states(q)
+        detJ, J, invJ, rin = rc.element_geometry()
+        em = rc.element_matrices()
+        Ae, be, tau = rc.pspg_elements(q_prev)
+        A0, b0 = rc.pspg_build(q_prev, False)
+        A1, b1 = rc.pspg_build(q_prev, True)
+    assert (A0.indptr == A1.indptr).all() and (A0.indices == A1.indices).all()
+    keep = np.arange(0, mesh.n_elems, max(1, mesh.n_elems // 24))   # a sample of the element-local systems
+    save(name, **mesh_arrays(mesh), q=q, q_prev=q_prev, par=par, detJ=detJ, invJ=invJ, rin=rin, tau=tau,
+         elem_ids=keep, Ae=Ae[keep], be=be[keep], **{"el_" + k: v[keep] for k, v in em.items()},
+         indptr=A1.indptr.astype(np.int64), indices=A1.indices.astype(np.int32), A_nobc=A0.data, b_nobc=b0, A=A1.data, b=b1)
+
+
+def picard_fixture(name, mesh, q_prev, par, max_iter=10, min_res=1e-6):
+    ref.use_scipy_direct_solver(True)
+    with ref.RefCase(mesh, "pspg", np.concatenate([par, [max_iter, min_res]])) as rc:
+        rc.set_states(q_prev)
+        ok, iters = rc.pspg_solve()
+        q, x = rc.get_states(), rc.positions()
+    ref.use_scipy_direct_solver(False)
+    assert ok
+    save(name, **mesh_arrays(mesh), q_prev=q_prev, par=par, max_iter=np.int64(max_iter), min_res=np.float64(min_res),
+         ok=np.int64(ok), iters=np.int64(iters), q=q, x_new=x)
+
+
+def wc_fixture(name, mesh, st, eq, meduri, n_steps=3, max_dt=1e-3):
+    W = mg.WC_PARAMS
+    g = mg.gravity(mesh.dim)
+    wpar = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri, eq)
+    q0 = np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
+    dts, states, xs = [], [], []
+    with ref.RefCase(mesh, "wc", np.concatenate([wpar, [1e-6, max_dt, W["securityCoeff"]]])) as rc:
+        rc.set_states(q0)
+        for _ in range(n_steps):
+            dt = rc.wc_next_dt()          # SolverWCompNewton::computeNextDT on the current state
+            assert rc.wc_step(dt)         # m_solveWCompNewtonNoT
+            dts.append(dt)
+            states.append(rc.get_states())
+            xs.append(rc.positions())
+    save(name, **mesh_arrays(mesh), q0=q0, wpar=wpar, security_coeff=np.float64(W["securityCoeff"]), max_dt=np.float64(max_dt),
+         dts=np.array(dts), states=np.array(states), xs=np.array(xs))
+
+
+def tables_fixture():
+    mesh = mg.kuhn_box(3, 2)
+    par = orc.pspg_param_array(1000.0, 1e-3, 1e-3, mg.gravity(3))
+    out = {}
+    with ref.RefCase(mesh, "pspg", par) as rc:
+        for dimension, n_gp in ((1, 3), (2, 3), (3, 4)):   # facet + element rules used by the equations (MomContEquation.inl:13-23)
+            gp, w, sf, ref_size = rc.tables(dimension, n_gp)
+            out.update({f"gp{dimension}": gp, f"w{dimension}": w, f"sf{dimension}": sf, f"ref{dimension}": np.float64(ref_size)})
+    save("tables", **out)
+
+
+def main():
+    if not ref.available():
+        raise SystemExit("oracle/_ref not built and /root/reference absent")
+    tables_fixture()
+    for dim, n, kw in ((2, 5, dict(free_fraction=0.03, permute=True)), (3, 3, dict(free_fraction=0.03, permute=True))):
+        mesh, q, q_prev, par = H.pspg_case(dim, n, **kw)
+        pspg_fixture(f"pspg_{dim}d_kuhn", mesh, q, q_prev, par)
+    for dim, npts in ((2, 60), (3, 90)):
+        mesh = mg.delaunay_cloud(dim, npts, free_fraction=0.02)
+        q, q_prev = mg.pspg_state(mesh)
+        q_prev = q_prev + 0.02 * np.random.default_rng(8).standard_normal(q_prev.shape)
+        P = mg.PSPG_PARAMS
+        par = orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim))
+        pspg_fixture(f"pspg_{dim}d_delaunay", mesh, q, q_prev, par)
+    for dim, n in ((2, 8), (3, 4)):
+        mesh = mg.kuhn_box(dim, n)
+        _, q_prev = mg.pspg_state(mesh)
+        P = mg.PSPG_PARAMS
+        picard_fixture(f"picard_{dim}d", mesh, q_prev, orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim)))
+    for dim, n, kw in ((2, 6, dict(free_fraction=0.03, permute=True)), (3, 3, dict(free_fraction=0.03, permute=True))):
+        mesh = mg.kuhn_box(dim, n, **kw)
+        for eq in ("CDS_dpdt", "CDS_drhodt", "CDS_rho"):
+            for meduri in (True, False):
+                st = mg.wc_state(mesh)
+                st["acc"] = 0.5 * np.random.default_rng(4).standard_normal(st["acc"].shape)
+                wc_fixture(f"wc_{dim}d_{eq}_{'meduri' if meduri else 'none'}", mesh, st, eq, meduri)
+
+
+if __name__ == "__main__":
+    main()

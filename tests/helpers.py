@@ -58,3 +58,35 @@ def vec_block_errors(b, b_ref, n_nodes, dim):
 def rel_err(a, ref):
     m = np.abs(ref).max()
     return float(np.abs(a - ref).max() / (m if m > 0 else 1.0))
+
+
+# ---- golden fixtures generated from the reference's own code (tests/golden/make_golden.py) ----
+import glob as _glob
+import os as _os
+
+GOLDEN_DIR = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "golden")
+
+
+def golden_names(prefix):
+    return sorted(_os.path.basename(p)[:-4] for p in _glob.glob(_os.path.join(GOLDEN_DIR, prefix + "*.npz")))
+
+
+def load_golden(name):
+    """Returns (mesh, dict of arrays) of one fixture."""
+    z = dict(np.load(_os.path.join(GOLDEN_DIR, name + ".npz")))
+    mesh = None
+    if "conn" in z:
+        mesh = mg.Mesh(dim=int(z["dim"]), x=np.ascontiguousarray(z["x"]), conn=np.ascontiguousarray(z["conn"]),
+                       flags=np.ascontiguousarray(z["flags"]), dir_mask=np.ascontiguousarray(z["dir_mask"]),
+                       dir_val=np.ascontiguousarray(z["dir_val"]))
+    return mesh, z
+
+
+def golden_csc(z, key="A"):
+    import scipy.sparse as sp
+    n = z["indptr"].shape[0] - 1
+    return sp.csc_matrix((z[key], z["indices"], z["indptr"]), shape=(n, n))
+
+
+def split_wc(q, dim, nn):
+    return dict(v=q[: dim * nn], p=q[dim * nn:(dim + 1) * nn], rho=q[(dim + 1) * nn:(dim + 2) * nn], acc=q[(dim + 2) * nn:])

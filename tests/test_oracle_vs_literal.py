@@ -1,4 +1,4 @@
-"""The C++ oracle against the independent numpy restatement (no reference tests exist: parity unpinned)."""
+"""The C++ oracle against the independent numpy restatement (the pin against the reference's own code is tests/test_oracle_vs_reference.py)."""
 import numpy as np
 import pytest
 

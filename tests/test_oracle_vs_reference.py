@@ -1,0 +1,180 @@
+"""Pins the CPU oracle against the REFERENCE'S OWN code.
+
+tests/golden/*.npz hold outputs of the reference's unmodified hot-path sources (MatricesBuilder.inl, Element.cpp,
+MomContEquationPSPG.inl, PicardAlgo.cpp, WCompNewton/{Cont,Mom}Equation.inl, WCompNewton/Solver.cpp, ...) compiled in
+place from /root/reference against stand-in Eigen/sol2/gmsh headers (oracle/refbuild/, generator
+tests/golden/make_golden.py).  These tests check oracle/pfem_oracle.cpp and oracle/literal_numpy.py against them; where
+the library itself is present (development container) further randomised cases are compared live.
+Tolerance 1e-12 relative per block type (the stand-in evaluates dense products in the order they are written, real
+Eigen may reassociate small products; in practice the oracle reproduces these fixtures bit for bit).
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import ref
+from pfem_b200 import meshgen as mg
+
+from helpers import (block_errors, golden_csc, golden_names, load_golden, pspg_case, rel_err, split_wc,
+                     vec_block_errors)
+
+TOL = 1e-12
+
+
+def test_fixtures_present():
+    assert len(golden_names("pspg_")) >= 4 and len(golden_names("wc_")) >= 12 and len(golden_names("picard_")) >= 2
+
+
+def test_quadrature_tables_match_reference():
+    """Mesh::getGaussPoints/getGaussWeight/getShapeFunctions/getRefElementSize (Mesh.cpp:342-530) vs SURVEY appendix A literals."""
+    _, z = load_golden("tables")
+    a, b = 0.585410196624968, 0.138196601125011
+    assert np.array_equal(z["gp2"][:, :2], np.array([[1 / 6, 1 / 6], [1 / 6, 2 / 3], [2 / 3, 1 / 6]]))
+    assert np.array_equal(z["w2"], np.full(3, 1 / 3)) and z["ref2"] == 0.5
+    assert np.array_equal(z["gp3"], np.array([[a, b, b], [b, a, b], [b, b, a], [b, b, b]]))
+    assert np.array_equal(z["w3"], np.full(4, 0.25)) and z["ref3"] == 1 / 6
+    for d in (2, 3):                                   # N = [1 - sum(xi), xi...]
+        gp, sf = z[f"gp{d}"][:, :d], z[f"sf{d}"]
+        assert np.abs(sf[:, 0] - (1 - gp.sum(1))).max() < 3e-16 and np.array_equal(sf[:, 1:], gp)
+
+
+@pytest.mark.parametrize("name", golden_names("pspg_"))
+def test_pspg_oracle_matches_reference_fixture(name):
+    mesh, z = load_golden(name)
+    dim, nn = mesh.dim, mesh.n_nodes
+    vcur = z["q"][: dim * nn].copy()
+    Ae, be, tau = orc.pspg_elements(mesh, vcur, z["q_prev"], z["par"])
+    assert rel_err(tau, z["tau"]) < TOL
+    ids = z["elem_ids"]
+    assert rel_err(Ae[ids], z["Ae"]) < TOL and rel_err(be[ids], z["be"]) < TOL
+    assert rel_err(mg.det_j(mesh), z["detJ"]) < TOL
+    for bc, (ka, kb) in ((False, ("A_nobc", "b_nobc")), (True, ("A", "b"))):
+        A, b = orc.pspg_build(mesh, vcur, z["q_prev"], z["par"], bc)
+        A_ref = golden_csc(z, ka)
+        errs = block_errors(A, A_ref, nn, dim)         # asserts the identical CSC pattern
+        assert max(errs.values()) < TOL, (bc, errs)
+        berr = vec_block_errors(b, z[kb], nn, dim)
+        assert max(berr.values()) < TOL, (bc, berr)
+
+
+@pytest.mark.parametrize("name", golden_names("pspg_"))
+def test_literal_numpy_matches_reference_fixture(name):
+    """The second restatement (dense products in numpy) against the reference's element systems."""
+    from oracle import literal_numpy as lit
+    mesh, z = load_golden(name)
+    dim, nn = mesh.dim, mesh.n_nodes
+    ids, P = z["elem_ids"], z["par"]
+    Ae, be, tau = lit.pspg_elements(mesh, z["q"][: dim * nn], z["q_prev"], P[0], P[1], P[2], P[3:6])
+    assert rel_err(Ae[ids], z["Ae"]) < 1e-11 and rel_err(be[ids], z["be"]) < 1e-11 and rel_err(tau, z["tau"]) < 1e-12
+
+
+@pytest.mark.parametrize("name", golden_names("picard_"))
+def test_picard_oracle_matches_reference_fixture(name):
+    """MomContEqIncompNewton::solve -> PicardAlgo::solve (PicardAlgo.cpp:31-94, PSPG.inl:262-373): same iteration
+    count, fields to 1e-8 (north_star), moved positions to 1e-12."""
+    mesh, z = load_golden(name)
+    dim, nn = mesh.dim, mesh.n_nodes
+    out = orc.pspg_picard(mesh, z["q_prev"], z["q_prev"], z["par"], max_iter=int(z["max_iter"]), min_res=float(z["min_res"]))
+    assert out["ok"] and out["iters"] == int(z["iters"])
+    assert rel_err(out["q"][: dim * nn], z["q"][: dim * nn]) < 1e-8
+    assert rel_err(out["q"][dim * nn:], z["q"][dim * nn:]) < 1e-8
+    assert np.abs(out["x"] - z["x_new"]).max() < 1e-12
+
+
+@pytest.mark.parametrize("name", golden_names("wc_"))
+def test_wc_oracle_matches_reference_fixture(name):
+    """SolverWCompNewton::computeNextDT + m_solveWCompNewtonNoT (WC/Solver.cpp:192-276) over three steps."""
+    mesh, z = load_golden(name)
+    dim, nn = mesh.dim, mesh.n_nodes
+    st, x = split_wc(z["q0"], dim, nn), mesh.x
+    st = {k: np.ascontiguousarray(v) for k, v in st.items()}
+    for step in range(z["dts"].shape[0]):
+        dt = orc.wc_next_dt(mesh, x, st, z["wpar"], float(z["security_coeff"]), float(z["max_dt"]))
+        assert abs(dt - z["dts"][step]) <= 1e-13 * z["dts"][step]
+        x, st = orc.wc_step(mesh, x, st, z["wpar"], float(z["dts"][step]))
+        want = split_wc(z["states"][step], dim, nn)
+        for k in ("v", "p", "rho", "acc"):
+            assert rel_err(st[k], want[k]) < TOL * 10 ** step, (k, step)
+        assert np.abs(x - z["xs"][step]).max() < 1e-13
+
+
+# ---- live comparisons (development container only: needs oracle/_ref/libpfem_ref.so) ----------------------------------
+needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
+
+
+@needs_ref
+@pytest.mark.parametrize("dim,n,kw", [(2, 14, dict(free_fraction=0.02, permute=True)), (3, 6, dict(free_fraction=0.01)),
+                                      (3, 5, dict(permute=True)), (2, 9, dict())])
+def test_live_pspg_assembly(dim, n, kw):
+    mesh, q, q_prev, par = pspg_case(dim, n, **kw)
+    nn = mesh.n_nodes
+    with ref.RefCase(mesh, "pspg", par) as rc:
+        rc.set_states(q)
+        A_ref, b_ref = rc.pspg_build(q_prev, True)
+        em = rc.element_matrices()
+    A, b = orc.pspg_build(mesh, q[: dim * nn].copy(), q_prev, par, True)
+    assert max(block_errors(A, A_ref, nn, dim).values()) < TOL
+    assert max(vec_block_errors(b, b_ref, nn, dim).values()) < TOL
+    # algebraic invariants on the REFERENCE'S element matrices: sum(M) = rho*V, K.translation = 0, L.1 = 0
+    V = mg.det_j(mesh) * (0.5 if dim == 2 else 1 / 6)
+    assert np.abs(em["M"].sum((1, 2)) - par[0] * V).max() < 1e-12 * np.abs(par[0] * V).max()
+    t = np.zeros(dim * (dim + 1)); t[: dim + 1] = 1.0
+    assert np.abs(em["K"] @ t).max() < 1e-9 * np.abs(em["K"]).max()
+    assert np.abs(em["L"].sum(2)).max() < 1e-9 * np.abs(em["L"]).max()
+
+
+@needs_ref
+@pytest.mark.parametrize("dim,npts", [(2, 150), (3, 200)])
+def test_live_pspg_unstructured(dim, npts):
+    mesh = mg.delaunay_cloud(dim, npts, free_fraction=0.02, seed=21)
+    q, q_prev = mg.pspg_state(mesh)
+    P = mg.PSPG_PARAMS
+    par = orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim))
+    nn = mesh.n_nodes
+    with ref.RefCase(mesh, "pspg", par) as rc:
+        rc.set_states(q)
+        A_ref, b_ref = rc.pspg_build(q_prev, True)
+    A, b = orc.pspg_build(mesh, q[: dim * nn].copy(), q_prev, par, True)
+    assert max(block_errors(A, A_ref, nn, dim).values()) < TOL
+    assert max(vec_block_errors(b, b_ref, nn, dim).values()) < TOL
+
+
+@needs_ref
+@pytest.mark.parametrize("dim,n,eq,meduri", [(2, 12, "CDS_dpdt", True), (3, 5, "CDS_dpdt", False), (3, 5, "CDS_drhodt", True),
+                                             (2, 12, "CDS_rho", False)])
+def test_live_wc_steps(dim, n, eq, meduri):
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.02, permute=True)
+    st = mg.wc_state(mesh)
+    st["acc"] = 0.3 * np.random.default_rng(12).standard_normal(st["acc"].shape)
+    W = mg.WC_PARAMS
+    wpar = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], mg.gravity(dim), meduri, eq)
+    nn, x = mesh.n_nodes, mesh.x
+    with ref.RefCase(mesh, "wc", np.concatenate([wpar, [1e-6, 1e-3, W["securityCoeff"]]])) as rc:
+        rc.set_states(np.concatenate([st["v"], st["p"], st["rho"], st["acc"]]))
+        for step in range(4):
+            dt_ref = rc.wc_next_dt()
+            dt = orc.wc_next_dt(mesh, x, st, wpar, W["securityCoeff"], 1e-3)
+            assert abs(dt - dt_ref) <= 1e-13 * dt_ref
+            assert rc.wc_step(dt_ref)
+            x, st = orc.wc_step(mesh, x, st, wpar, dt_ref)
+            want = split_wc(rc.get_states(), dim, nn)
+            for k in ("v", "p", "rho", "acc"):
+                assert rel_err(st[k], want[k]) < TOL * 10 ** step, (k, step)
+            assert np.abs(x - rc.positions()).max() < 1e-13
+
+
+@needs_ref
+def test_live_picard_dense_lu():
+    """Same Picard loop with the stand-in's own dense LU instead of SuperLU: the direct solver does not matter at 1e-8."""
+    mesh = mg.kuhn_box(2, 8)
+    _, q_prev = mg.pspg_state(mesh)
+    P = mg.PSPG_PARAMS
+    par = orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(2))
+    ref.use_scipy_direct_solver(False)
+    with ref.RefCase(mesh, "pspg", np.concatenate([par, [10, 1e-6]])) as rc:
+        rc.set_states(q_prev)
+        ok, iters = rc.pspg_solve()
+        q = rc.get_states()
+    out = orc.pspg_picard(mesh, q_prev, q_prev, par, max_iter=10, min_res=1e-6)
+    assert ok and out["ok"] and iters == out["iters"]
+    assert rel_err(out["q"], q) < 1e-8
