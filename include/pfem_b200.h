@@ -113,9 +113,22 @@ int pfem_get_states(pfem_ctx* ctx, int first, int count, double* q);
 /* Host-evaluated Lua velocity BC: mask[n] != 0 <=> node.isBound() && getBcTagFlags(tag, flag 0); values[n + d*nNodes]
  * = "<type>V"(pos, t+dt) (PSPG.inl:206-214; WCompNewton/MomEquation.inl:355-364). */
 int pfem_set_dirichlet(pfem_ctx* ctx, const uint8_t* mask, const double* values);
+/* Boundary facets of the current mesh = Mesh::m_facetsList after the alpha shape (Mesh3D.cpp:218-262, Mesh2D.cpp):
+ * facetNodes[f*dim + k] = Facet::m_nodesIndexes, outNode[f] = Facet::m_outNodeIndex (the element node in front of the
+ * facet), elemIndex[f] = Facet::m_elementIndex.  Call after pfem_set_mesh (a new mesh drops the facets); nFacets = 0
+ * clears them.  Facet geometry (Facet::computeJ/DetJ/Normal, Facet.cpp:16-77, 130-210) is recomputed on the device from
+ * the current positions whenever it is used. */
+int pfem_set_facets(pfem_ctx* ctx, int64_t nFacets, const uint64_t* facetNodes, const uint64_t* outNode,
+                    const uint64_t* elemIndex);
+/* Surface-tension coefficient gamma (Material.gamma: MomContEquation.inl:30, WCompNewton/MomEquation.inl:29).  With
+ * gamma >= 1e-15 and facets set, pfem_pspg_assemble adds MatrixBuilder::getFST (MatricesBuilder.inl:389-403) of every
+ * facet with a node on the free surface to the velocity rows of b before the nodal BC pass (PSPG.inl:155-187), and the
+ * explicit step adds it to F for facets entirely on the free surface (WCompNewton/MomEquation.inl:312-336).  Default 0
+ * (the reference's `if(m_gamma < 1e-15) continue`). */
+int pfem_set_surface_tension(pfem_ctx* ctx, double gamma);
 
 /* ---- incompressible PSPG (MomContEqIncompNewton<dim>) ------------------------------- */
-/* m_buildAbPSPG + m_applyBCPSPG (PSPG.inl:7-146, 149-235) with gamma = 0.  qPrev: (dim+1)*nNodes. */
+/* m_buildAbPSPG + m_applyBCPSPG (PSPG.inl:7-146, 149-235; facet terms: pfem_set_surface_tension).  qPrev: (dim+1)*nNodes. */
 int pfem_pspg_assemble(pfem_ctx* ctx, const pfem_pspg_params* p, const double* qPrev);
 /* The same split in two, so that a caller that keeps qPrev across Picard iterations (PSPG.inl:273, 298 pass the same
  * qPrevVec[0]) uploads it once: set_qprev copies it to the device, assemble_resident assembles from device-resident data. */

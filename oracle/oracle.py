@@ -40,6 +40,7 @@ def lib():
         L.oracle_pspg_elements.argtypes = [C.c_int, i64, i64, ip, dp, dp, dp, dp, dp, dp, dp]
         L.oracle_pspg_build.restype = C.c_void_p
         L.oracle_pspg_build.argtypes = [C.c_int, i64, i64, ip, dp, dp, dp, bp, dp, C.c_int, bp, dp, dp, dp]
+        L.oracle_set_facets.argtypes = [C.c_int, i64, ip, C.c_double]
         L.oracle_csc_nnz.restype = i64
         L.oracle_csc_nnz.argtypes = [C.c_void_p]
         L.oracle_csc_copy.argtypes = [C.c_void_p, ip, C.POINTER(C.c_int32), dp]
@@ -89,6 +90,16 @@ def wc_param_array(mu, K0, K0p, rhoStar, body_force, meduri=True, eq_type="CDS_d
     bf[: len(body_force)] = body_force
     return np.array([mu, K0, K0p, rhoStar, bf[0], bf[1], bf[2], 1.0 if meduri else 0.0,
                      float(EQ_TYPES[eq_type])], dtype=np.float64)
+
+
+def set_facets(dim, facets=None, gamma=0.0):
+    """Boundary facets (nF x (dim+2): facet nodes, out node, element) and surface tension for the following
+    pspg_build(apply_bc=True) / wc_step calls; set_facets(dim) switches the facet terms off again."""
+    if facets is None or gamma == 0.0:
+        lib().oracle_set_facets(dim, 0, None, 0.0)
+        return
+    f = np.ascontiguousarray(facets, dtype=np.int64)
+    lib().oracle_set_facets(dim, f.shape[0], _i(f), float(gamma))
 
 
 def pspg_elements(mesh, vcur, q_prev, params):

@@ -529,6 +529,126 @@ void pspgBuild(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* 
 }
 
 // ------------------------------------------------------------------------------------
+// Surface tension on free-surface facets.  Facet::computeJ/computeDetJ/computeNormal (srcs/mesh/Facet.cpp:16-77,
+// 130-210), MatrixBuilder::getP/getT/getFST (MB.inl:167-214, 389-403; factor = gamma, MomContEquation.inl:213-218,
+// WC/MomEquation.inl:141-146), the facet loops of m_applyBCPSPG (PSPG.inl:155-187: a facet counts when ANY of its
+// nodes is on the free surface) and of MomEqWCompNewton::m_applyBC (WC/MomEquation.inl:312-336: Facet::
+// isOnFreeSurface = ALL nodes, Facet.cpp:249-255).  Facet quadrature: 3 points in both dimensions
+// (MomContEquation.inl:13-23) with weights summing to one (Mesh.cpp:428, 443-444), reference sizes 2 and 1/2 (:476-480).
+// facets: nF x (DIM+2) = DIM facet nodes, the node in front of the facet (m_outNodeIndex), the element index.
+// ------------------------------------------------------------------------------------
+struct FacetCtx {
+    int64_t nF = 0;
+    std::vector<int64_t> facets;
+    double gamma = 0;
+};
+FacetCtx g_facets;
+
+template <int DIM>
+void addFST(int64_t nNodes, const int64_t* conn, const double* x, const uint8_t* flags, bool allNodesRule, double* target) {
+    constexpr int NPE = DIM + 1, ND = DIM * NPE, NS = MB<DIM>::NS, NPF = DIM;
+    const FacetCtx& C = g_facets;
+    if (C.gamma < 1e-15) return;                       // PSPG.inl:157 / MomEquation.inl:314 (DgammaDT = 0 outside Boussinesq)
+    const double wLD[3] = {DIM == 2 ? 5.0 / 18.0 : 1.0 / 3.0, DIM == 2 ? 8.0 / 18.0 : 1.0 / 3.0, DIM == 2 ? 5.0 / 18.0 : 1.0 / 3.0};
+    const double refLD = (DIM == 2) ? 2.0 : 0.5;
+    auto X = [&](int64_t node, int d) { return x[node + (int64_t)d * nNodes]; };
+    for (int64_t f = 0; f < C.nF; ++f) {
+        const int64_t* row = C.facets.data() + f * (DIM + 2);
+        int nOnFS = 0;
+        for (int k = 0; k < NPF; ++k) nOnFS += (flags[row[k]] & F_FS) ? 1 : 0;
+        if (allNodesRule ? (nOnFS != NPF) : (nOnFS == 0)) continue;
+        const int64_t out = row[NPF], elm = row[NPF + 1];
+        // Facet::computeJ / computeDetJ / computeNormal
+        double detJf, nrm[3] = {0, 0, 0};
+        if constexpr (DIM == 2) {
+            const double x0 = X(row[0], 0), x1 = X(row[1], 0), y0 = X(row[0], 1), y1 = X(row[1], 1);
+            const double J00 = (x1 - x0) / 2, J10 = (y1 - y0) / 2;
+            detJf = std::sqrt(J00 * J00 + J10 * J10);
+            nrm[0] = y1 - y0;
+            nrm[1] = x0 - x1;
+            const double vo[2] = {X(out, 0) - x0, X(out, 1) - y0};
+            if (nrm[0] * vo[0] + nrm[1] * vo[1] > 0) {
+                nrm[0] *= -1;
+                nrm[1] *= -1;
+            }
+            const double norm = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1]);
+            nrm[0] /= norm;
+            nrm[1] /= norm;
+        } else {
+            double J[3][2];
+            for (int d = 0; d < 3; ++d) {
+                J[d][0] = X(row[1], d) - X(row[0], d);
+                J[d][1] = X(row[2], d) - X(row[0], d);
+            }
+            const double dG[3] = {J[1][0] * J[2][1] - J[1][1] * J[2][0], J[2][0] * J[0][1] - J[2][1] * J[0][0],
+                                  J[0][0] * J[1][1] - J[1][0] * J[0][1]};
+            detJf = std::sqrt(dG[0] * dG[0] + dG[1] * dG[1] + dG[2] * dG[2]);
+            const double a[3] = {J[0][0], J[1][0], J[2][0]}, b[3] = {J[0][1], J[1][1], J[2][1]};
+            nrm[0] = a[1] * b[2] - a[2] * b[1];
+            nrm[1] = a[2] * b[0] - a[0] * b[2];
+            nrm[2] = a[0] * b[1] - a[1] * b[0];
+            const double vo[3] = {X(out, 0) - X(row[0], 0), X(out, 1) - X(row[0], 1), X(out, 2) - X(row[0], 2)};
+            if (vo[0] * nrm[0] + vo[1] * nrm[1] + vo[2] * nrm[2] > 0)
+                for (int d = 0; d < 3; ++d) nrm[d] *= -1.0;
+            const double norm = std::sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+            for (int d = 0; d < 3; ++d) nrm[d] /= norm;
+        }
+        // getP, getT
+        double P[NS], T[NS][NS];
+        if constexpr (DIM == 2) {
+            P[0] = 1 - nrm[0] * nrm[0];
+            P[1] = 1 - nrm[1] * nrm[1];
+            P[2] = -nrm[0] * nrm[1];
+            T[0][0] = P[0] * P[0]; T[0][1] = P[2] * P[2]; T[0][2] = 2 * P[0] * P[2];
+            T[1][0] = T[0][1];     T[1][1] = P[1] * P[1]; T[1][2] = 2 * P[2] * P[1];
+            T[2][0] = P[0] * P[2]; T[2][1] = P[2] * P[1]; T[2][2] = P[0] * P[1] + P[2] * P[2];
+        } else {
+            P[0] = 1 - nrm[0] * nrm[0];
+            P[1] = 1 - nrm[1] * nrm[1];
+            P[2] = 1 - nrm[2] * nrm[2];
+            P[3] = -nrm[0] * nrm[1];
+            P[4] = -nrm[0] * nrm[2];
+            P[5] = -nrm[1] * nrm[2];
+            T[0][0] = P[0] * P[0]; T[0][1] = P[3] * P[3]; T[0][2] = P[4] * P[4]; T[0][3] = 2 * P[0] * P[3]; T[0][5] = 2 * P[4] * P[3]; T[0][4] = 2 * P[0] * P[4];
+            T[1][0] = T[0][1];     T[1][1] = P[1] * P[1]; T[1][2] = P[5] * P[5]; T[1][3] = 2 * P[3] * P[1]; T[1][5] = 2 * P[5] * P[1]; T[1][4] = 2 * P[3] * P[5];
+            T[2][0] = T[0][2];     T[2][1] = T[1][2];     T[2][2] = P[2] * P[2]; T[2][3] = 2 * P[5] * P[4]; T[2][5] = 2 * P[5] * P[2]; T[2][4] = 2 * P[2] * P[4];
+            T[3][0] = P[0] * P[3]; T[3][1] = P[3] * P[1]; T[3][2] = P[4] * P[5]; T[3][3] = P[0] * P[1] + P[3] * P[3]; T[3][5] = P[4] * P[1] + P[5] * P[3]; T[3][4] = P[4] * P[3] + P[0] * P[5];
+            T[5][0] = P[3] * P[4]; T[5][1] = P[5] * P[1]; T[5][2] = P[5] * P[2]; T[5][3] = P[4] * P[1] + P[5] * P[3]; T[5][5] = P[1] * P[2] + P[5] * P[5]; T[5][4] = P[5] * P[4] + P[3] * P[2];
+            T[4][0] = P[0] * P[4]; T[4][1] = P[3] * P[5]; T[4][2] = P[2] * P[4]; T[4][3] = P[4] * P[3] + P[0] * P[5]; T[4][5] = P[5] * P[4] + P[3] * P[2]; T[4][4] = P[2] * P[0] + P[4] * P[4];
+        }
+        // element gradN, B
+        const int64_t* en = conn + elm * NPE;
+        Geo<DIM> G;
+        computeGeo<DIM>(x, nNodes, en, G);
+        double g[DIM][NPE], B[NS][ND];
+        MB<DIM>::gradN(G, g);
+        MB<DIM>::Bmat(g, B);
+        // getFST: FST -= fact*Be^T*T*P*w per Gauss point (left to right), then *= detJ*refSize
+        double FST[ND];
+        for (int r = 0; r < ND; ++r) FST[r] = 0.0;
+        for (int gp = 0; gp < 3; ++gp) {
+            double gBt[ND][NS], gBtT[ND][NS];
+            for (int r = 0; r < ND; ++r)
+                for (int k = 0; k < NS; ++k) gBt[r][k] = C.gamma * B[k][r];
+            for (int r = 0; r < ND; ++r)
+                for (int c = 0; c < NS; ++c) {
+                    double sum = 0;
+                    for (int k = 0; k < NS; ++k) sum += gBt[r][k] * T[k][c];
+                    gBtT[r][c] = sum;
+                }
+            for (int r = 0; r < ND; ++r) {
+                double sum = 0;
+                for (int k = 0; k < NS; ++k) sum += gBtT[r][k] * P[k];
+                FST[r] -= sum * wLD[gp];
+            }
+        }
+        for (int r = 0; r < ND; ++r) FST[r] *= detJf * refLD;
+        for (int n = 0; n < NPE; ++n)
+            for (int d = 0; d < DIM; ++d) target[en[n] + (int64_t)d * nNodes] += FST[n + d * NPE];
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // m_applyBCPSPG.  MomContEquationPSPG.inl:149-235 (gamma = 0: facet loop skipped, :157).
 // dirMask[n] != 0  <=>  node.isBound() && getBcTagFlags(tag, flag0) (:206-208);
 // dirVal[n + d*nNodes] = the Lua "<type>V" result (:211-214), host-evaluated.
@@ -802,6 +922,7 @@ void wcMom(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, c
                 F[conn[elm * NPE + i] + (int64_t)d * nNodes] += FTot[elm * ND + i + d * NPE];
             }
     for (size_t i = 0; i < invM.size(); ++i) invM[i] = 1 / invM[i];
+    addFST<DIM>(nNodes, conn, x, flags, true, F.data());  // m_applyBC facet loop, MomEquation.inl:312-336
     for (int64_t n = 0; n < nNodes; ++n) {
         const bool bound = flags[n] & F_BOUND, free_ = flags[n] & F_FREE;
         if (free_ && !bound) {
@@ -948,6 +1069,10 @@ void* oracle_pspg_build(int dim, int64_t nNodes, int64_t nElm, const int64_t* co
     }
     if (applyBC) {
         double t0 = omp_get_wtime();
+        if (dim == 2)   // facet loop of m_applyBCPSPG (PSPG.inl:155-187) comes before the nodal BC pass
+            addFST<2>(nNodes, conn, x, flags, false, b);
+        else
+            addFST<3>(nNodes, conn, x, flags, false, b);
         if (dim == 2)
             pspgApplyBC<2>(nNodes, flags, dirMask, dirVal, qPrev, P, H->colPtr.data(), H->rowIdx.data(), H->val.data(), b);
         else
@@ -955,6 +1080,13 @@ void* oracle_pspg_build(int dim, int64_t nNodes, int64_t nElm, const int64_t* co
         if (phaseSec) phaseSec[5] += omp_get_wtime() - t0;
     }
     return H;
+}
+// Boundary facets + surface-tension coefficient used by the next oracle_pspg_build(applyBC) / oracle_wc_step calls
+// (gamma < 1e-15 or nF = 0: no facet terms, the default).  facets: nF x (dim+2), see addFST.
+void oracle_set_facets(int dim, int64_t nF, const int64_t* facets, double gamma) {
+    g_facets.nF = nF;
+    g_facets.facets.assign(facets, facets + (nF > 0 ? nF * (dim + 2) : 0));
+    g_facets.gamma = (nF > 0) ? gamma : 0.0;
 }
 int64_t oracle_csc_nnz(void* h) { return (int64_t) static_cast<CscHandle*>(h)->val.size(); }
 void oracle_csc_copy(void* h, int64_t* colPtr, int32_t* rowIdx, double* val) {

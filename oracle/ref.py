@@ -61,6 +61,8 @@ def lib():
         L.pfem_ref_wc_next_dt.argtypes = [C.c_void_p]
         L.pfem_ref_set_direct_solver.argtypes = [C.c_void_p]
         L.pfem_ref_direct_solves.restype = C.c_long
+        L.pfem_ref_cg_log.restype = C.c_long
+        L.pfem_ref_cg_log.argtypes = [DP, C.c_long]
         _lib = L
     return _lib
 
@@ -106,7 +108,8 @@ class RefCase:
         if kind == "pspg":      # params = oracle.pspg_param_array + (max_iter, min_res)
             rho, mu, dt, bx, by, bz = params[:6]
             max_iter, min_res = (params[6], params[7]) if len(params) >= 8 else (10, 1e-6)
-            p = np.array([rho, mu, dt, bx, by, bz, gamma, max_iter, min_res], dtype=np.float64)
+            gamma_fs, residual = (params[8], params[9]) if len(params) >= 10 else (1.0, 0.0)
+            p = np.array([rho, mu, dt, bx, by, bz, gamma, max_iter, min_res, gamma_fs, residual], dtype=np.float64)
             prob, sid = b"IncompNewtonNoT", (solver_id or "PSPG").encode()
             self.n_states = self.dim + 1
         elif kind == "wc":      # params = oracle.wc_param_array + (initial_dt, max_dt, security_coeff)
@@ -197,6 +200,13 @@ class RefCase:
         n0 = lib().pfem_ref_direct_solves()
         ok = self._chk(lib().pfem_ref_pspg_solve(self._h), "pspg_solve")
         return bool(ok), lib().pfem_ref_direct_solves() - n0
+
+    @staticmethod
+    def cg_log(max_rows=256):
+        """(n, iterations, relative residual, info) of the stand-in ConjugateGradient solves since the last call."""
+        out = np.zeros((max_rows, 4))
+        k = lib().pfem_ref_cg_log(_d(out), max_rows)
+        return out[:k]
 
     def wc_step(self, dt):
         return bool(self._chk(lib().pfem_ref_wc_step(self._h, float(dt)), "wc_step"))

@@ -176,8 +176,18 @@ const char* pfem_ref_last_error() { return g_lastError.c_str(); }
 // Direct solver used by the stand-in Eigen::SparseLU (nullptr -> built-in dense LU).
 void pfem_ref_set_direct_solver(Eigen::standin::DirectSolverFn fn) { Eigen::standin::directSolverHook() = fn; }
 long pfem_ref_direct_solves() { return Eigen::standin::directSolveCount(); }
+// log of the stand-in ConjugateGradient solves since the last call: rows of (n, iterations, error, info)
+long pfem_ref_cg_log(double* out, long maxRows) {
+    auto& log = Eigen::standin::cgLog();
+    long k = 0;
+    for (; k < static_cast<long>(log.size()) && k < maxRows; ++k) {
+        out[4 * k] = log[k].n; out[4 * k + 1] = log[k].iterations; out[4 * k + 2] = log[k].error; out[4 * k + 3] = log[k].info;
+    }
+    log.clear();
+    return k;
+}
 
-// params: IncompNewtonNoT/PSPG -> [rho, mu, dt, bx, by, bz, gamma, maxIter, minRes]
+// params: IncompNewtonNoT/PSPG|FracStep -> [rho, mu, dt, bx, by, bz, gamma, maxIter, minRes, gammaFS, residual (0 Ax_f, 1 U, 2 U_P)]
 //         WCompNewtonNoT/CDS_* -> [mu, K0, K0p, rhoStar, bx, by, bz, meduri, gamma, initialDT, maxDT, securityCoeff]
 // facets: nFacets x (dim+2) = facet nodes, out node, element index (may be null / 0)
 void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const std::int64_t* conn, const double* x,
@@ -242,7 +252,8 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
             sol::table eqT;
             eqT.set("maxIter", p[7]);
             eqT.set("minRes", p[8]);
-            eqT.set("residual", std::string("Ax_f"));
+            eqT.set("residual", std::string(p[10] == 1 ? "U" : p[10] == 2 ? "U_P" : "Ax_f"));
+            eqT.set("gammaFS", p[9]);
             eqT.set("bodyForce", std::vector<double>(p + 3, p + 3 + dim));
             eqT.set("BC", bc);
             solverT.set("id", rc->solverId);

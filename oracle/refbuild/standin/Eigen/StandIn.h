@@ -482,6 +482,8 @@ namespace standin {
 using DirectSolverFn = int (*)(int n, const int* colPtr, const int* rowIdx, const double* val, const double* b, double* x);
 inline DirectSolverFn& directSolverHook() { static DirectSolverFn fn = nullptr; return fn; }
 inline long& directSolveCount() { static long n = 0; return n; }
+struct CgRecord { long n, iterations; double error; int info; };
+inline std::vector<CgRecord>& cgLog() { static std::vector<CgRecord> log; return log; }
 }  // namespace standin
 
 template <typename MatrixType, typename Ordering = COLAMDOrdering<int>> class SparseLU {
@@ -589,6 +591,7 @@ class ConjugateGradient {
         iters_ = i;
         err_ = std::sqrt(resNorm2 / rhsNorm2);
         info_ = (resNorm2 < threshold) ? Success : NoConvergence;
+        standin::cgLog().push_back({static_cast<long>(n), static_cast<long>(iters_), static_cast<double>(err_), static_cast<int>(info_)});
         return x;
     }
 

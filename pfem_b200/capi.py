@@ -57,6 +57,8 @@ SYMBOLS = {
     "pfem_set_states": (C.c_int, [_VP, C.c_int, C.c_int, _DP]),
     "pfem_get_states": (C.c_int, [_VP, C.c_int, C.c_int, _DP]),
     "pfem_set_dirichlet": (C.c_int, [_VP, _U8P, _DP]),
+    "pfem_set_facets": (C.c_int, [_VP, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "pfem_set_surface_tension": (C.c_int, [_VP, C.c_double]),
     "pfem_pspg_set_qprev": (C.c_int, [_VP, _DP]),
     "pfem_pspg_assemble": (C.c_int, [_VP, C.POINTER(PspgParams), _DP]),
     "pfem_pspg_assemble_resident": (C.c_int, [_VP, C.POINTER(PspgParams)]),
@@ -207,6 +209,22 @@ class PfemContext:
         mask = np.ascontiguousarray(mask, dtype=np.uint8)
         values = _f64(values, self.dim * self.n_nodes)
         self._chk(self._L.pfem_set_dirichlet(self._h, mask.ctypes.data_as(_U8P), _dptr(values)))
+
+    def set_facets(self, facets):
+        """facets: (nF, dim+2) rows [facet nodes, out node, element index] (meshgen.boundary_facets); None clears."""
+        if facets is None or len(facets) == 0:
+            self._chk(self._L.pfem_set_facets(self._h, 0, None, None, None))
+            return
+        f = np.ascontiguousarray(facets, dtype=np.uint64)
+        d = self.dim
+        nodes = np.ascontiguousarray(f[:, :d])
+        out, elem = np.ascontiguousarray(f[:, d]), np.ascontiguousarray(f[:, d + 1])
+        u64 = C.POINTER(C.c_uint64)
+        self._chk(self._L.pfem_set_facets(self._h, f.shape[0], nodes.ctypes.data_as(u64), out.ctypes.data_as(u64),
+                                          elem.ctypes.data_as(u64)))
+
+    def set_surface_tension(self, gamma):
+        self._chk(self._L.pfem_set_surface_tension(self._h, float(gamma)))
 
     # -- PSPG ---------------------------------------------------------------------
     @staticmethod

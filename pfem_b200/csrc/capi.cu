@@ -161,6 +161,18 @@ int pfem_set_dirichlet(pfem_ctx* c, const uint8_t* mask, const double* values) {
     API_END(c)
 }
 
+int pfem_set_facets(pfem_ctx* c, int64_t nFacets, const uint64_t* facetNodes, const uint64_t* outNode, const uint64_t* elemIndex) {
+    API_BEGIN(c)
+    facetsSet(c, nFacets, facetNodes, outNode, elemIndex);
+    API_END(c)
+}
+int pfem_set_surface_tension(pfem_ctx* c, double gamma) {
+    API_BEGIN(c)
+    PFEM_REQUIRE(gamma >= 0 && gamma == gamma, PFEM_ERR_INVALID, "set_surface_tension: gamma must be >= 0");
+    c->gammaST = gamma;
+    API_END(c)
+}
+
 int pfem_pspg_set_qprev(pfem_ctx* c, const double* qPrev) {
     API_BEGIN(c)
     fieldsSetQprev(c, qPrev);

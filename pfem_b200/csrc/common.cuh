@@ -143,6 +143,13 @@ struct pfem_ctx {
     DevBuf<double> dtPartial;
     DevBuf<double> wcF0;  // CDS_rho: F0 = sum_e M_e rho_e on the configuration before the move
 
+    // ---- free-surface facets / surface tension (facets.cu) ----
+    int nFacets = 0, nFstNodes = 0;
+    double gammaST = 0.0;      // MomContEqIncompNewton::m_gamma / MomEqWCompNewton::m_gamma
+    DevBuf<int> facetRec;      // per facet: dim facet nodes, out node, element index
+    DevBuf<int> fstNode, fstPtr, fstItem;  // nodes touched by a facet's element -> their facets, ascending facet index
+    DevBuf<double> fst4;       // nodal surface-tension force, 4 doubles per node
+
     // ---- multi-GPU ----
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
@@ -162,8 +169,10 @@ struct pfem_ctx {
     std::vector<cudaEvent_t> eventPool;
 
     pfem_ctx() {
-        for (auto* b : {&conn, &n2ePtr, &n2e, &nbrPtr, &nbr, &diagSlot, &scratchI, &scanScratch, &cscPtr, &cscRow, &sendIdx})
+        for (auto* b : {&conn, &n2ePtr, &n2e, &nbrPtr, &nbr, &diagSlot, &scratchI, &scanScratch, &cscPtr, &cscRow, &sendIdx,
+                        &facetRec, &fstNode, &fstPtr, &fstItem})
             b->accounting = &deviceBytes;
+        fst4.accounting = &deviceBytes;
         for (auto* b : {&flags, &dirMask, &stageB}) b->accounting = &deviceBytes;
         for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &Wblk, &kx, &kr, &kr0,
                         &kp, &kp2, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &sendBuf})
@@ -248,6 +257,9 @@ void mgApply(pfem_ctx* c, double* out);
 void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt);
 int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dt);
 int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff, double maxDT, double* dtInOut, double* elapsed);
+// facets.cu
+void facetsSet(pfem_ctx* c, int64_t nFacets, const uint64_t* facetNodes, const uint64_t* outNode, const uint64_t* elemIndex);
+const double* facetsForces(pfem_ctx* c, const double* X4, bool allNodesRule);  // null when the facet terms are off
 // comm.cu
 void commUniqueId(void* id128);
 void commInit(pfem_ctx* c, int nRanks, int rank, const void* id128);

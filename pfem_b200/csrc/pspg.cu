@@ -55,6 +55,7 @@ struct AsmArgs {
     const double* dirVal4;
     const double* X4;
     const double* VP4;
+    const double* fst4;       // nodal surface-tension force (facets.cu) or null
     double* Aval;
     double* b;
     double* dinv;
@@ -458,6 +459,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_pspg_assemble(const AsmArgs a
             double bv = beTot, bs = bsub[0];
 #pragma unroll
             for (int c = 1; c < BS; ++c) bs = (c == r) ? bsub[c] : bs;
+            if (a.fst4 && r < DIM) bv += a.fst4[(size_t)i * 4 + r];  // facet loop of m_applyBCPSPG (PSPG.inl:155-187)
             bv -= bs;
             if (isFree) {
                 if (r == DIM) bv = 0.0;
@@ -562,6 +564,7 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
         }
     }
     AsmArgs a;
+    a.fst4 = facetsForces(c, c->X4.p, false);  // "any node on the free surface" rule of PSPG.inl:164-173
     a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.nbrPtr = c->nbrPtr.p, a.nbr = c->nbr.p;
     a.n2eSlots = c->n2eSlots.p, a.blkMask = c->blkMask.p, a.rowDir = c->rowDir.p;
     a.diagSlot = c->diagSlot.p, a.flags = c->flags.p, a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p;

@@ -173,6 +173,7 @@ struct WcArgs {
     const uint8_t* flags;
     const uint8_t* dirMask;
     const double* dirVal4;
+    const double* fst4 = nullptr;  // nodal surface-tension force (facets.cu) or null
     int nNodes;
     double dt, mu, K0, K0p, rhoStar, body[3];
     const double* dtPtr;  // if non-null the time step is read from the device (pfem_wc_run)
@@ -370,6 +371,7 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const doub
 #pragma unroll
         for (int c = 0; c < DIM; ++c) {
             double f = F[c], iv = inv;
+            if (a.fst4) f += a.fst4[(size_t)i * 4 + c];  // facet loop of m_applyBC (MomEquation.inl:312-336)
             if (isFree && !isBound) {
                 f = a.body[c];
                 iv = 1.0;
@@ -405,6 +407,7 @@ struct WcArgsS {
     const uint8_t* flags;
     const uint8_t* dirMask;
     const double* dirVal4;
+    const double* fst4 = nullptr;
     int nNodes, nbcap;
     double dt, mu, K0, K0p, rhoStar, body[3];
     const double* dtPtr;  // if non-null the time step is read from the device (pfem_wc_run)
@@ -621,6 +624,7 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom_s(const WcArgsS a, const d
 #pragma unroll
         for (int c = 0; c < DIM; ++c) {
             double f = F[c], iv = inv;
+            if (a.fst4) f += a.fst4[(size_t)i * 4 + c];  // facet loop of m_applyBC (MomEquation.inl:312-336)
             if (isFree && !isBound) {
                 f = a.body[c];
                 iv = 1.0;
@@ -796,6 +800,7 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
                                                                      c->A4.p);
         LAUNCH_CHECK(c);
     }
+    a.fst4 = as.fst4 = facetsForces(c, c->X4.p, true);  // on the moved mesh; Facet::isOnFreeSurface = all nodes (Facet.cpp:249-255)
 #define PFEM_WC_LAUNCH_S(KERNEL, LPN_, ...)                                                                         \
     do {                                                                                                            \
         const int grid_ = divUp((int64_t)c->nRows * LPN_, 256);                                                     \

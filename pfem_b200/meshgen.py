@@ -142,6 +142,27 @@ def kuhn_box(dim: int, n: int, *, jitter: float = 0.1, seed: int = 1234, permute
                 n_cells=n, meta=dict(jitter=jitter, seed=seed, permute=permute, free_fraction=free_fraction))
 
 
+def boundary_facets(mesh: Mesh) -> np.ndarray:
+    """Boundary facets as the reference stores them after the alpha shape (Mesh3D.cpp:218-262, Mesh2D.cpp): one row
+    per element face that belongs to exactly one element = [dim facet nodes, the opposite element node
+    (Facet::m_outNodeIndex), the element index (Facet::m_elementIndex)], int64, ordered by element then local face."""
+    dim, npe = mesh.dim, mesh.dim + 1
+    conn = mesh.conn
+    ne = conn.shape[0]
+    faces = np.empty((ne, npe, dim), dtype=np.int64)
+    for k in range(npe):                       # local face k = all element nodes but node k
+        faces[:, k, :] = conn[:, [j for j in range(npe) if j != k]]
+    key = np.sort(faces.reshape(-1, dim), axis=1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    once = (cnt[inv.reshape(-1)] == 1).reshape(ne, npe)
+    e_idx, k_idx = np.nonzero(once)
+    out = np.empty((e_idx.size, dim + 2), dtype=np.int64)
+    out[:, :dim] = faces[e_idx, k_idx]
+    out[:, dim] = conn[e_idx, k_idx]
+    out[:, dim + 1] = e_idx
+    return out
+
+
 def det_j(mesh: Mesh) -> np.ndarray:
     """detJ per element (Element.cpp:71-86) -- used to check orientation of generated meshes."""
     c = mesh.coords()

@@ -37,9 +37,10 @@ def save(name, **arrays):
     print(f"{name}.npz  {os.path.getsize(path) / 1024:.0f} KiB")
 
 
-def pspg_fixture(name, mesh, q, q_prev, par):
+def pspg_fixture(name, mesh, q, q_prev, par, facets=None, gamma=0.0):
     dim, nn = mesh.dim, mesh.n_nodes
-    with ref.RefCase(mesh, "pspg", par) as rc:
+    extra = {} if facets is None else dict(facets=facets, gamma=np.float64(gamma))
+    with ref.RefCase(mesh, "pspg", par, facets=facets, gamma=gamma) as rc:
         rc.set_states(q)
         detJ, J, invJ, rin = rc.element_geometry()
         em = rc.element_matrices()
@@ -50,7 +51,8 @@ def pspg_fixture(name, mesh, q, q_prev, par):
     keep = np.arange(0, mesh.n_elems, max(1, mesh.n_elems // 24))   # a sample of the element-local systems
     save(name, **mesh_arrays(mesh), q=q, q_prev=q_prev, par=par, detJ=detJ, invJ=invJ, rin=rin, tau=tau,
          elem_ids=keep, Ae=Ae[keep], be=be[keep], **{"el_" + k: v[keep] for k, v in em.items()},
-         indptr=A1.indptr.astype(np.int64), indices=A1.indices.astype(np.int32), A_nobc=A0.data, b_nobc=b0, A=A1.data, b=b1)
+         indptr=A1.indptr.astype(np.int64), indices=A1.indices.astype(np.int32), A_nobc=A0.data, b_nobc=b0, A=A1.data, b=b1,
+         **extra)
 
 
 def picard_fixture(name, mesh, q_prev, par, max_iter=10, min_res=1e-6):
@@ -65,13 +67,14 @@ def picard_fixture(name, mesh, q_prev, par, max_iter=10, min_res=1e-6):
          ok=np.int64(ok), iters=np.int64(iters), q=q, x_new=x)
 
 
-def wc_fixture(name, mesh, st, eq, meduri, n_steps=3, max_dt=1e-3):
+def wc_fixture(name, mesh, st, eq, meduri, n_steps=3, max_dt=1e-3, facets=None, gamma=0.0):
     W = mg.WC_PARAMS
     g = mg.gravity(mesh.dim)
     wpar = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri, eq)
     q0 = np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
     dts, states, xs = [], [], []
-    with ref.RefCase(mesh, "wc", np.concatenate([wpar, [1e-6, max_dt, W["securityCoeff"]]])) as rc:
+    extra = {} if facets is None else dict(facets=facets, gamma=np.float64(gamma))
+    with ref.RefCase(mesh, "wc", np.concatenate([wpar, [1e-6, max_dt, W["securityCoeff"]]]), facets=facets, gamma=gamma) as rc:
         rc.set_states(q0)
         for _ in range(n_steps):
             dt = rc.wc_next_dt()          # SolverWCompNewton::computeNextDT on the current state
@@ -80,7 +83,7 @@ def wc_fixture(name, mesh, st, eq, meduri, n_steps=3, max_dt=1e-3):
             states.append(rc.get_states())
             xs.append(rc.positions())
     save(name, **mesh_arrays(mesh), q0=q0, wpar=wpar, security_coeff=np.float64(W["securityCoeff"]), max_dt=np.float64(max_dt),
-         dts=np.array(dts), states=np.array(states), xs=np.array(xs))
+         dts=np.array(dts), states=np.array(states), xs=np.array(xs), **extra)
 
 
 def tables_fixture():
@@ -120,6 +123,22 @@ def main():
                 st = mg.wc_state(mesh)
                 st["acc"] = 0.5 * np.random.default_rng(4).standard_normal(st["acc"].shape)
                 wc_fixture(f"wc_{dim}d_{eq}_{'meduri' if meduri else 'none'}", mesh, st, eq, meduri)
+    fst_fixtures()
+
+
+def fst_fixtures():
+    """gamma > 0 on a wavy free surface (a flat one has zero net force): MatrixBuilder::getFST through the facet loops of
+    m_applyBCPSPG (PSPG.inl:155-187) and MomEqWCompNewton::m_applyBC (MomEquation.inl:312-336)."""
+    gamma = 7.28   # 100x water-air: makes the term ~1e-3 of the gravity load on these coarse meshes
+    for dim, n in ((2, 6), (3, 4)):
+        mesh, q, q_prev, par = H.pspg_case(dim, n, permute=True)
+        H.wavy_free_surface(mesh)
+        fac = mg.boundary_facets(mesh)
+        pspg_fixture(f"pspg_{dim}d_fst", mesh, q, q_prev, par, facets=fac, gamma=gamma)
+        for eq, meduri in (("CDS_dpdt", True), ("CDS_rho", False)):
+            st = mg.wc_state(mesh)
+            st["acc"] = 0.5 * np.random.default_rng(4).standard_normal(st["acc"].shape)
+            wc_fixture(f"wc_{dim}d_fst_{eq}", mesh, st, eq, meduri, facets=fac, gamma=gamma)
 
 
 if __name__ == "__main__":

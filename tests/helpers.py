@@ -90,3 +90,16 @@ def golden_csc(z, key="A"):
 
 def split_wc(q, dim, nn):
     return dict(v=q[: dim * nn], p=q[dim * nn:(dim + 1) * nn], rho=q[(dim + 1) * nn:(dim + 2) * nn], acc=q[(dim + 2) * nn:])
+
+
+def wavy_free_surface(mesh, amp=0.2, seed=17):
+    """Displace the free-surface nodes (flag bit 3) normal to the box top by U(-amp*h, amp*h): a flat surface has zero
+    net surface-tension force on every interior node, so the facet terms need curvature to show up."""
+    dim, nn = mesh.dim, mesh.n_nodes
+    h = 1.0 / max(1, round((nn ** (1.0 / dim)) - 1))
+    fs = np.flatnonzero(mesh.flags & mg.F_FS)
+    x = mesh.x.reshape(dim, nn).copy()
+    x[dim - 1, fs] += amp * h * np.random.default_rng(seed).uniform(-1, 1, fs.size)
+    mesh.x = np.ascontiguousarray(x.reshape(-1))
+    assert mg.det_j(mesh).min() > 0
+    return mesh

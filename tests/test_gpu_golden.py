@@ -18,10 +18,18 @@ def test_assembly_matches_reference_fixture(name):
     dim, nn, par = mesh.dim, mesh.n_nodes, z["par"]
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
+        if "facets" in z:                                  # surface tension: getFST on the free-surface facets
+            ctx.set_facets(z["facets"])
+            ctx.set_surface_tension(float(z["gamma"]))
         ctx.set_states(0, z["q"])
         p = ctx.pspg_params(par[0], par[1], par[2], par[3:6])
         ctx.pspg_assemble(p, z["q_prev"])
         A, b = ctx.pspg_export_csc()
+        if "facets" in z:
+            ctx.set_surface_tension(0.0)
+            ctx.pspg_assemble(p, z["q_prev"])
+            _, b_off = ctx.pspg_export_csc()
+            assert np.abs(b_off - z["b"]).max() > 1e-6 * np.abs(z["b"]).max()   # the fixture exercises the facet terms
     A_ref = golden_csc(z, "A")
     assert A.nnz == A_ref.nnz
     errs = block_errors(A, A_ref, nn, dim)                 # also asserts the identical CSC pattern
@@ -65,6 +73,9 @@ def test_wc_steps_match_reference_fixture(name):
     eq = {0: "CDS_dpdt", 1: "CDS_drhodt", 2: "CDS_rho"}[int(wpar[8])]
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
+        if "facets" in z:
+            ctx.set_facets(z["facets"])
+            ctx.set_surface_tension(float(z["gamma"]))
         ctx.set_states(0, z["q0"])
         wp = ctx.wc_params(wpar[0], wpar[1], wpar[2], wpar[3], wpar[4:7], bool(wpar[7]), eq)
         for step in range(z["dts"].shape[0]):

@@ -43,6 +43,7 @@ def test_pspg_oracle_matches_reference_fixture(name):
     mesh, z = load_golden(name)
     dim, nn = mesh.dim, mesh.n_nodes
     vcur = z["q"][: dim * nn].copy()
+    orc.set_facets(dim, z.get("facets"), float(z.get("gamma", 0.0)))     # gamma > 0 fixtures: facet terms on
     Ae, be, tau = orc.pspg_elements(mesh, vcur, z["q_prev"], z["par"])
     assert rel_err(tau, z["tau"]) < TOL
     ids = z["elem_ids"]
@@ -55,6 +56,10 @@ def test_pspg_oracle_matches_reference_fixture(name):
         assert max(errs.values()) < TOL, (bc, errs)
         berr = vec_block_errors(b, z[kb], nn, dim)
         assert max(berr.values()) < TOL, (bc, berr)
+    orc.set_facets(dim)
+    if "facets" in z:                                    # the fixture must actually exercise the facet terms
+        _, b0 = orc.pspg_build(mesh, vcur, z["q_prev"], z["par"], True)
+        assert np.abs(b0 - z["b"]).max() > 1e-6 * np.abs(z["b"]).max()
 
 
 @pytest.mark.parametrize("name", golden_names("pspg_"))
@@ -88,6 +93,7 @@ def test_wc_oracle_matches_reference_fixture(name):
     dim, nn = mesh.dim, mesh.n_nodes
     st, x = split_wc(z["q0"], dim, nn), mesh.x
     st = {k: np.ascontiguousarray(v) for k, v in st.items()}
+    orc.set_facets(dim, z.get("facets"), float(z.get("gamma", 0.0)))
     for step in range(z["dts"].shape[0]):
         dt = orc.wc_next_dt(mesh, x, st, z["wpar"], float(z["security_coeff"]), float(z["max_dt"]))
         assert abs(dt - z["dts"][step]) <= 1e-13 * z["dts"][step]
@@ -96,6 +102,11 @@ def test_wc_oracle_matches_reference_fixture(name):
         for k in ("v", "p", "rho", "acc"):
             assert rel_err(st[k], want[k]) < TOL * 10 ** step, (k, step)
         assert np.abs(x - z["xs"][step]).max() < 1e-13
+    orc.set_facets(dim)
+    if "facets" in z:                                    # the fixture must actually exercise the facet terms
+        st0 = {k: np.ascontiguousarray(v) for k, v in split_wc(z["q0"], dim, nn).items()}
+        _, st1 = orc.wc_step(mesh, mesh.x, st0, z["wpar"], float(z["dts"][0]))
+        assert rel_err(st1["acc"], split_wc(z["states"][0], dim, nn)["acc"]) > 1e-7
 
 
 # ---- live comparisons (development container only: needs oracle/_ref/libpfem_ref.so) ----------------------------------
@@ -178,3 +189,28 @@ def test_live_picard_dense_lu():
     out = orc.pspg_picard(mesh, q_prev, q_prev, par, max_iter=10, min_res=1e-6)
     assert ok and out["ok"] and iters == out["iters"]
     assert rel_err(out["q"], q) < 1e-8
+
+
+@needs_ref
+@pytest.mark.parametrize("dim,n", [(2, 12), (3, 5)])
+def test_live_fracstep_pressure_solve_does_not_converge(dim, n):
+    """Evidence for DESIGN.md section 7: the reference's own fractional-step code (MomContEquationFracStep.inl, run here
+    through oracle/_ref) hands the pressure-correction matrix m_L to ConjugateGradient without any Dirichlet row for the
+    free-surface nodes (only isFree rows are masked, :124-130, 349-376), so the system is singular with an inconsistent
+    right-hand side: the stand-in CG (Jacobi-preconditioned, tolerance eps, 2n iterations -- Eigen's defaults as recalled)
+    converges on the two velocity systems and hits the iteration cap with a large residual on every pressure solve."""
+    mesh = mg.kuhn_box(dim, n)
+    _, q_prev = mg.pspg_state(mesh)
+    P = mg.PSPG_PARAMS
+    par = orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim))
+    ref.RefCase.cg_log()
+    with ref.RefCase(mesh, "pspg", np.concatenate([par, [10, 1e-6, 1.0, 2.0]]), solver_id="FracStep") as rc:
+        rc.set_states(q_prev)
+        rc.pspg_solve()
+    log = ref.RefCase.cg_log()
+    vel = log[log[:, 0] == dim * mesh.n_nodes]
+    prs = log[log[:, 0] == mesh.n_nodes]
+    assert len(vel) >= 2 and len(prs) >= 1
+    assert (vel[:2, 3] == 0).all() and (vel[:2, 2] < 1e-14).all()          # first velocity systems: converged to eps
+    assert (prs[:, 3] == 2).all() and (prs[:, 1] == 2 * mesh.n_nodes).all() # pressure: NoConvergence at 2n iterations
+    assert np.nanmax(prs[:, 2]) > 1e-6 and prs[0, 2] > 1e-6
