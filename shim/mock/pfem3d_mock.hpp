@@ -28,8 +28,19 @@ public:
     std::size_t getNodeIndex(unsigned int k) const noexcept { return m_nodesIndexes[k]; }
     std::vector<std::size_t> m_nodesIndexes;
 };
+class Facet {   // Facet.hpp:38-60
+public:
+    std::size_t getNodeIndex(unsigned int k) const noexcept { return m_nodesIndexes[k]; }
+    std::size_t getOutNodeIndex() const noexcept { return m_outNodeIndex; }
+    std::size_t getElementIndex() const noexcept { return m_elementIndex; }
+    std::vector<std::size_t> m_nodesIndexes;
+    std::size_t m_outNodeIndex = 0, m_elementIndex = 0;
+};
 class Mesh {
 public:
+    std::size_t getFacetsCount() const noexcept { return m_facetsList.size(); }
+    const Facet& getFacet(std::size_t f) const noexcept { return m_facetsList[f]; }
+    std::vector<Facet> m_facetsList;
     unsigned short getDim() const noexcept { return m_dim; }
     std::size_t getNodesCount() const noexcept { return m_nodesList.size(); }
     std::size_t getElementsCount() const noexcept { return m_elementsList.size(); }

@@ -36,7 +36,7 @@ inline void check(pfem_ctx* ctx, int rc, const char* what) {
 // serially, exactly where the reference evaluates it: PSPG.inl:206-214, WCompNewton/MomEquation.inl:355-364).
 template <unsigned short dim, class MeshT, class SolverT, class ProblemT, class BcTable>
 void uploadMesh(pfem_ctx* ctx, MeshT* pMesh, SolverT* pSolver, ProblemT* pProblem, BcTable& bc, unsigned short bcFlag,
-                unsigned int firstState, unsigned int stateCount, bool topologyChanged) {
+                unsigned int firstState, unsigned int stateCount, bool topologyChanged, bool withFacets = false) {
     const std::size_t nN = pMesh->getNodesCount(), nE = pMesh->getElementsCount();
     if (topologyChanged) {
         std::vector<uint64_t> conn(nE * (dim + 1));
@@ -49,6 +49,17 @@ void uploadMesh(pfem_ctx* ctx, MeshT* pMesh, SolverT* pSolver, ProblemT* pProble
                        (node.isFixed() ? PFEM_NODE_FIXED : 0u) | (node.isOnFreeSurface() ? PFEM_NODE_FREE_SURFACE : 0u);
         }
         check(ctx, pfem_set_topology(ctx, (int64_t)nN, (int64_t)nE, conn.data(), flags.data()), "pfem_set_topology");
+        if (withFacets) {  // gamma > 0: Mesh::m_facetsList for the surface-tension facet loops (PSPG.inl:155-187, MomEquation.inl:312-336)
+            const std::size_t nF = pMesh->getFacetsCount();
+            std::vector<uint64_t> fNodes(nF * dim), fOut(nF), fElem(nF);
+            for (std::size_t f = 0; f < nF; ++f) {
+                const auto& facet = pMesh->getFacet(f);
+                for (unsigned short k = 0; k < dim; ++k) fNodes[f * dim + k] = facet.getNodeIndex(k);
+                fOut[f] = facet.getOutNodeIndex();
+                fElem[f] = facet.getElementIndex();
+            }
+            check(ctx, pfem_set_facets(ctx, (int64_t)nF, fNodes.data(), fOut.data(), fElem.data()), "pfem_set_facets");
+        }
     }
     std::vector<double> x(dim * nN), q(stateCount * nN), dval(dim * nN, 0.0);
     std::vector<uint8_t> dmask(nN, 0);
@@ -84,8 +95,7 @@ public:
             throw std::runtime_error("the " + getID() + " equation requires one BC flag and one statesIndex");  // MomContEquation.inl:64-69
         m_par.rho = m_materialParams[0].template checkAndGet<double>("rho");
         m_par.mu = m_materialParams[0].template checkAndGet<double>("mu");
-        const double gamma = m_materialParams[0].template checkAndGet<double>("gamma");
-        if (gamma >= 1e-15) throw std::runtime_error("surface tension (gamma > 0) is outside the B200 hot path");
+        m_gamma = m_materialParams[0].template checkAndGet<double>("gamma");
         m_maxIter = m_equationParams[0].template checkAndGet<unsigned int>("maxIter");
         m_minRes = m_equationParams[0].template checkAndGet<double>("minRes");
         m_residual = m_equationParams[0].template checkAndGet<std::string>("residual");
@@ -94,9 +104,10 @@ public:
         if (bodyForce.size() != m_pMesh->getDim()) throw std::runtime_error("the body force vector has not the right dimension!");
         for (unsigned short d = 0; d < 3; ++d) m_par.bodyForce[d] = d < dim ? bodyForce[d] : 0.0;
         m_relTol = m_equationParams[0].doesVarExist("krylovTol") ? m_equationParams[0].template checkAndGet<double>("krylovTol") : 1e-12;
-        m_needNormalCurv = false;
+        m_needNormalCurv = false;  // facet normals are recomputed on the device (MomContEquation.inl:257 asks the host mesh for them)
         const int rc = pfem_create(&m_ctx, dim, pfem_b200_shim::deviceFromEnv());
         if (rc != PFEM_OK) throw std::runtime_error(std::string("pfem_create: ") + pfem_last_error(nullptr));
+        pfem_b200_shim::check(m_ctx, pfem_set_surface_tension(m_ctx, m_gamma), "pfem_set_surface_tension");
         // optional new key: preconditioner = "auto" | "point" | "block" | "mg"   (default auto: multigrid with hand-over)
         if (m_equationParams[0].doesVarExist("preconditioner")) {
             const std::string pre = m_equationParams[0].template checkAndGet<std::string>("preconditioner");
@@ -114,7 +125,8 @@ public:
         const std::size_t nN = m_pMesh->getNodesCount();
         m_par.dt = m_pSolver->getTimeStep();
         // the incompressible solver remeshes after every successful step (IncompNewton/Solver.cpp:241-242): new topology
-        uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bcParams[0], m_bcFlags[0], m_statesIndex[0], dim + 1, true);
+        uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bcParams[0], m_bcFlags[0], m_statesIndex[0], dim + 1, true,
+                        m_gamma >= 1e-15);
         std::vector<double> qPrev((dim + 1) * nN), qIter((dim + 1) * nN, 0.0), qIterPrev;
         for (std::size_t n = 0; n < nN; ++n)
             for (unsigned int s = 0; s <= dim; ++s) qPrev[n + s * nN] = m_pMesh->getNode(n).getState(m_statesIndex[0] + s);
@@ -168,6 +180,7 @@ private:
     }
     pfem_ctx* m_ctx = nullptr;
     pfem_pspg_params m_par{};
+    double m_gamma = 0.0;
     unsigned int m_maxIter = 10;
     double m_minRes = 1e-6, m_relTol = 1e-12;
     std::string m_residual;
@@ -184,7 +197,7 @@ public:
         m_par.K0 = material.template checkAndGet<double>("K0");
         m_par.K0p = material.template checkAndGet<double>("K0p");
         m_par.rhoStar = material.template checkAndGet<double>("rhoStar");
-        if (material.template checkAndGet<double>("gamma") >= 1e-15) throw std::runtime_error("surface tension is outside the B200 hot path");
+        m_gamma = material.template checkAndGet<double>("gamma");
         const std::string stab = contParams.template checkAndGet<std::string>("stabilization");
         if (stab != "None" && stab != "Meduri") throw std::runtime_error("unknown stabilization: " + stab);  // ContEquation.inl:32-37
         m_par.meduri = stab == "Meduri";
@@ -197,6 +210,7 @@ public:
         for (unsigned short d = 0; d < 3; ++d) m_par.bodyForce[d] = d < dim ? bodyForce[d] : 0.0;
         const int rc = pfem_create(&m_ctx, dim, pfem_b200_shim::deviceFromEnv());
         if (rc != PFEM_OK) throw std::runtime_error(std::string("pfem_create: ") + pfem_last_error(nullptr));
+        pfem_b200_shim::check(m_ctx, pfem_set_surface_tension(m_ctx, m_gamma), "pfem_set_surface_tension");
     }
     ~WCompNewtonStepB200() { pfem_destroy(m_ctx); }
 
@@ -206,7 +220,7 @@ public:
     bool step() {
         using namespace pfem_b200_shim;
         if (m_dirty) {
-            uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bc, 0, 0, 2 * dim + 2, true);
+            uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bc, 0, 0, 2 * dim + 2, true, m_gamma >= 1e-15);
             m_dirty = false;
         }
         check(m_ctx, pfem_wc_step(m_ctx, &m_par, m_pSolver->getTimeStep()), "pfem_wc_step");
@@ -241,5 +255,6 @@ private:
     double m_securityCoeff;
     pfem_ctx* m_ctx = nullptr;
     pfem_wc_params m_par{};
+    double m_gamma = 0.0;
     bool m_dirty = true;
 };
