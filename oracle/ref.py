@@ -15,7 +15,9 @@ import scipy.sparse as sp
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_ref", "libpfem_ref.so")
+_SO_DROPIN = os.path.join(_HERE, "_ref", "libpfem_ref_dropin.so")   # + shim/pfem_b200_equations.hpp, linked to libpfem_b200.so
 _lib = None
+_use_dropin = False
 _solver_cb = None   # keeps the ctypes callback alive
 
 DP, IP, BP, I64 = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_uint8), C.c_int64
@@ -33,12 +35,31 @@ def available() -> bool:
     return os.path.exists(_SO)
 
 
+def dropin_available() -> bool:
+    if not os.path.exists(_SO_DROPIN) and os.path.isdir("/root/reference/srcs"):
+        build()
+    return os.path.exists(_SO_DROPIN)
+
+
+def use_dropin_library() -> None:
+    """Load libpfem_ref_dropin.so (reference host code + shim + libpfem_b200.so) instead of libpfem_ref.so.  Must be
+    called before the first lib() of the process; GPU tests only."""
+    global _use_dropin
+    assert _lib is None or _use_dropin, "the plain reference library is already loaded in this process"
+    _use_dropin = True
+
+
 def lib():
     global _lib
     if _lib is None:
-        if not available():
-            raise RuntimeError("oracle/_ref/libpfem_ref.so not built and /root/reference absent")
-        L = C.CDLL(_SO)
+        if not (dropin_available() if _use_dropin else available()):
+            raise RuntimeError("oracle/_ref library not built and /root/reference absent")
+        L = C.CDLL(_SO_DROPIN if _use_dropin else _SO)
+        if _use_dropin:
+            L.pfem_ref_use_b200_equation.argtypes = [C.c_void_p]
+            L.pfem_ref_wc_step_b200.argtypes = [C.c_void_p, C.c_double, C.c_int]
+            L.pfem_ref_wc_next_dt_b200.restype = C.c_double
+            L.pfem_ref_wc_next_dt_b200.argtypes = [C.c_void_p]
         L.pfem_ref_last_error.restype = C.c_char_p
         L.pfem_ref_create.restype = C.c_void_p
         L.pfem_ref_create.argtypes = [C.c_int, I64, I64, IP, DP, BP, BP, DP, I64, IP, C.c_char_p, C.c_char_p, DP]
@@ -207,6 +228,17 @@ class RefCase:
         out = np.zeros((max_rows, 4))
         k = lib().pfem_ref_cg_log(_d(out), max_rows)
         return out[:k]
+
+    # ---- drop-in build only (libpfem_ref_dropin.so) ----
+    def use_b200_equation(self):
+        """Swap the reference's MomContEqIncompNewton<dim> for the shim's MomContEqIncompNewtonB200<dim> (= the REGISTER_EQ edit)."""
+        self._chk(lib().pfem_ref_use_b200_equation(self._h), "use_b200_equation")
+
+    def wc_step_b200(self, dt, download=True):
+        return bool(self._chk(lib().pfem_ref_wc_step_b200(self._h, float(dt), 1 if download else 0), "wc_step_b200"))
+
+    def wc_next_dt_b200(self):
+        return lib().pfem_ref_wc_next_dt_b200(self._h)
 
     def wc_step(self, dt):
         return bool(self._chk(lib().pfem_ref_wc_step(self._h, float(dt)), "wc_step"))

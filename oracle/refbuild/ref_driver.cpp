@@ -36,6 +36,12 @@
 #include "simulation/physics/WCompNewton/MomEquation.hpp"
 #include "simulation/utility/StatesFromToQ.hpp"
 
+#ifdef PFEM_REF_WITH_B200
+// Drop-in build (libpfem_ref_dropin.so): the reference's host code above drives libpfem_b200.so through the shim that a
+// PFEM3D maintainer would add (shim/pfem_b200_equations.hpp).
+#include "pfem_b200_equations.hpp"
+#endif
+
 namespace {
 
 struct PosKey {
@@ -68,6 +74,7 @@ struct RefCase {
     Solver* solver = nullptr;
     std::unordered_map<PosKey, std::size_t, PosHash> byPos;
     std::string error;
+    std::shared_ptr<void> wcShim;  // WCompNewtonStepB200<dim> of the drop-in build
 
     void rebuildPositions() {
         byPos.clear();
@@ -457,5 +464,70 @@ double pfem_ref_wc_next_dt(void* h) {
         return -1.0;
     }
 }
+
+#ifdef PFEM_REF_WITH_B200
+// ---- drop-in build: the reference's solver objects with the B200 equation classes swapped in ---------------------------
+// Equivalent of editing the REGISTER_EQ site (IN/Solver.cpp:38-40): m_pEquations[0] becomes MomContEqIncompNewtonB200<dim>,
+// constructed with exactly the arguments REGISTER_EQ passes (IN/Solver.cpp:6-10, 22-37).
+int pfem_ref_use_b200_equation(void* h) {
+    auto& rc = *static_cast<RefCase*>(h);
+    try {
+        Solver* s = rc.solver;
+        std::vector<SolTable> materialParams(rc.problem->m_problemParams.size());
+        for (std::size_t i = 0; i < materialParams.size(); ++i) materialParams[i] = SolTable("Material", rc.problem->m_problemParams[i]);
+        const std::vector<unsigned short> bcFlags = {0};
+        const std::vector<unsigned int> statesIndex = {0};
+        if (rc.dim == 2)
+            s->m_pEquations[0] = std::make_unique<MomContEqIncompNewtonB200<2>>(rc.problem.get(), s, rc.mesh, s->m_solverParams, materialParams, bcFlags, statesIndex);
+        else
+            s->m_pEquations[0] = std::make_unique<MomContEqIncompNewtonB200<3>>(rc.problem.get(), s, rc.mesh, s->m_solverParams, materialParams, bcFlags, statesIndex);
+        return 0;
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return -1;
+    }
+}
+
+}  // extern "C"
+template <unsigned short dim> int wcStepB200(RefCase& rc, double dt, int download) {
+    using Shim = WCompNewtonStepB200<dim>;
+    Solver* s = rc.solver;
+    if (!rc.wcShim) {  // the object SolverWCompNewton would own; tables as in WC/Solver.cpp:26-30 and Equation.cpp:21-27
+        SolTable material("Material", rc.problem->m_problemParams[0]);
+        SolTable cont("ContEq", s->m_solverParams[0]), mom("MomEq", s->m_solverParams[0]);
+        SolTable bc("BC", mom);
+        rc.wcShim = std::make_shared<Shim>(rc.problem.get(), s, rc.mesh, material, cont, mom, bc, static_cast<SolverWCompNewton*>(s)->m_securityCoeff);
+    }
+    auto* shim = static_cast<Shim*>(rc.wcShim.get());
+    s->m_timeStep = dt;
+    shim->step();                       // replaces kick + move + continuity + momentum of m_solveWCompNewtonNoT
+    rc.problem->updateTime(dt);         // WC/Solver.cpp:265
+    if (download) shim->download();     // what the host does before a remesh / an extractor write
+    return 1;
+}
+extern "C" {
+int pfem_ref_wc_step_b200(void* h, double dt, int download) {
+    auto& rc = *static_cast<RefCase*>(h);
+    try {
+        rc.rebuildPositions();
+        return rc.dim == 2 ? wcStepB200<2>(rc, dt, download) : wcStepB200<3>(rc, dt, download);
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return -1;
+    }
+}
+double pfem_ref_wc_next_dt_b200(void* h) {
+    auto& rc = *static_cast<RefCase*>(h);
+    try {
+        if (!rc.wcShim) return -1.0;
+        const double maxDT = rc.solver->m_maxDT;
+        return rc.dim == 2 ? static_cast<WCompNewtonStepB200<2>*>(rc.wcShim.get())->nextDT(maxDT)
+                           : static_cast<WCompNewtonStepB200<3>*>(rc.wcShim.get())->nextDT(maxDT);
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return -1.0;
+    }
+}
+#endif
 
 }  // extern "C"

@@ -151,7 +151,7 @@ public:
         for (std::size_t n = 0; n < nN; ++n)
             for (unsigned int s = 0; s <= dim; ++s) m_pMesh->setNodeState(n, m_statesIndex[0] + s, qIter[n + s * nN]);
         m_pMesh->saveNodesList();
-        m_pMesh->updateNodesPositionFromSave(scaled(qIter, m_par.dt));
+        m_pMesh->updateNodesPositionFromSave(scaled(qIter, m_par.dt, dim * nN));  // the std::vector overload wants exactly dim*nNodes (Mesh.cpp:1197-1203)
         return true;
     }
 
@@ -173,9 +173,9 @@ private:
         const double resV = rel(0, dim - 1);
         return m_residual == "U_P" ? std::max(resV, rel(dim, dim)) : resV;
     }
-    static std::vector<double> scaled(const std::vector<double>& q, double dt) {
-        std::vector<double> d(q.size());
-        for (std::size_t i = 0; i < q.size(); ++i) d[i] = q[i] * dt;
+    static std::vector<double> scaled(const std::vector<double>& q, double dt, std::size_t count) {
+        std::vector<double> d(count);
+        for (std::size_t i = 0; i < count; ++i) d[i] = q[i] * dt;
         return d;
     }
     pfem_ctx* m_ctx = nullptr;

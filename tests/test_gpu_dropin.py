@@ -1,0 +1,82 @@
+"""Drop-in test of the boundary: the REFERENCE'S OWN host code -- Mesh, SolverIncompNewton /
+SolverWCompNewton, PicardAlgo, compiled from /root/reference into oracle/_ref/libpfem_ref_dropin.so (oracle/refbuild) --
+runs one time step twice: once with its own equation classes (CPU, stand-in Eigen, SciPy SuperLU behind SparseLU) and
+once with the shim classes of shim/pfem_b200_equations.hpp swapped in at the REGISTER_EQ seam, which call
+libpfem_b200.so through the C ABI.  Node states and positions on the reference's Mesh object must agree: 1e-8 for the
+PSPG step (north_star field tolerance), 1e-12 for the explicit steps."""
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import ref
+from pfem_b200 import meshgen as mg
+
+from helpers import rel_err, split_wc, wavy_free_surface
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _dropin_library():
+    if not ref.dropin_available():
+        pytest.skip("oracle/_ref/libpfem_ref_dropin.so was not built (needs /root/reference at build time)")
+    ref.use_dropin_library()
+    ref.use_scipy_direct_solver(True)
+    yield
+    ref.use_scipy_direct_solver(False)
+
+
+@pytest.mark.parametrize("dim,n,gamma", [(2, 12, 0.0), (3, 5, 0.0), (3, 4, 7.28)])
+def test_pspg_time_step_through_the_shim(dim, n, gamma):
+    mesh = mg.kuhn_box(dim, n)
+    facets = None
+    if gamma > 0:
+        wavy_free_surface(mesh)
+        facets = mg.boundary_facets(mesh)
+    _, q_prev = mg.pspg_state(mesh)
+    P = mg.PSPG_PARAMS
+    par = np.concatenate([orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim)), [10, 1e-6]])
+    nn = mesh.n_nodes
+    out = {}
+    for which in ("reference", "b200"):
+        with ref.RefCase(mesh, "pspg", par, facets=facets, gamma=gamma) as rc:
+            if which == "b200":
+                rc.use_b200_equation()
+            rc.set_states(q_prev)
+            ok, _ = rc.pspg_solve()             # Equation::solve() of whichever class sits in m_pEquations[0]
+            assert ok
+            out[which] = (rc.get_states(), rc.positions())
+    (q_ref, x_ref), (q, x) = out["reference"], out["b200"]
+    assert rel_err(q[: dim * nn], q_ref[: dim * nn]) < 1e-8
+    assert rel_err(q[dim * nn:], q_ref[dim * nn:]) < 1e-8
+    assert np.abs(x - x_ref).max() < 1e-9
+    assert np.abs(x_ref - mesh.x).max() > 1e-6  # the step moved the mesh
+
+
+@pytest.mark.parametrize("dim,n,eq,gamma", [(2, 10, "CDS_dpdt", 0.0), (3, 5, "CDS_drhodt", 0.0), (3, 4, "CDS_dpdt", 7.28)])
+def test_wc_steps_through_the_shim(dim, n, eq, gamma):
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.02)
+    facets = None
+    if gamma > 0:
+        wavy_free_surface(mesh)
+        facets = mg.boundary_facets(mesh)
+    st = mg.wc_state(mesh)
+    st["acc"] = 0.3 * np.random.default_rng(2).standard_normal(st["acc"].shape)
+    W = mg.WC_PARAMS
+    wpar = np.concatenate([orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], mg.gravity(dim), True, eq),
+                           [1e-6, 1e-3, W["securityCoeff"]]])
+    q0 = np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
+    nn = mesh.n_nodes
+    with ref.RefCase(mesh, "wc", wpar, facets=facets, gamma=gamma) as a, ref.RefCase(mesh, "wc", wpar, facets=facets, gamma=gamma) as b:
+        a.set_states(q0)
+        b.set_states(q0)
+        dt = a.wc_next_dt()                      # SolverWCompNewton::computeNextDT
+        for step in range(3):
+            assert a.wc_step(dt)                 # reference: m_solveWCompNewtonNoT
+            assert b.wc_step_b200(dt)            # shim: WCompNewtonStepB200::step + download to the reference Mesh
+            want, got = split_wc(a.get_states(), dim, nn), split_wc(b.get_states(), dim, nn)
+            for k in ("v", "p", "rho", "acc"):
+                assert rel_err(got[k], want[k]) < 1e-12 * 10 ** step, (k, step)
+            assert np.abs(a.positions() - b.positions()).max() < 1e-13
+            dt_ref, dt = a.wc_next_dt(), b.wc_next_dt_b200()
+            assert abs(dt - dt_ref) <= 1e-13 * dt_ref
