@@ -82,6 +82,8 @@ def lib():
         L.pfem_ref_wc_next_dt.argtypes = [C.c_void_p]
         L.pfem_ref_set_direct_solver.argtypes = [C.c_void_p]
         L.pfem_ref_direct_solves.restype = C.c_long
+        L.pfem_ref_set_threads.argtypes = [C.c_int]
+        L.pfem_ref_get_threads.restype = C.c_int
         L.pfem_ref_cg_log.restype = C.c_long
         L.pfem_ref_cg_log.argtypes = [DP, C.c_long]
         _lib = L
@@ -91,6 +93,12 @@ def lib():
 def _d(a):
     assert a.dtype == np.float64 and a.flags.c_contiguous
     return a.ctypes.data_as(DP)
+
+
+def set_threads(n: int = 0) -> int:
+    """OpenMP threads (= Problem::m_nThreads, one parameter table each) of the cases created from now on; 0 = all cores."""
+    lib().pfem_ref_set_threads(int(n))
+    return lib().pfem_ref_get_threads()
 
 
 def use_scipy_direct_solver(enable: bool = True) -> None:

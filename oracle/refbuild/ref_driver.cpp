@@ -18,6 +18,7 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -80,7 +81,9 @@ struct RefCase {
         byPos.clear();
         for (std::size_t n = 0; n < mesh->getNodesCount(); ++n) byPos[keyOf(mesh->getNode(n).getPosition())] = n;
     }
+    std::mutex posMutex;
     std::size_t nodeAt(const std::array<double, 3>& pos) {
+        std::lock_guard<std::mutex> lock(posMutex);  // MomEqWCompNewton::m_applyBC calls the BC table from an omp loop
         auto it = byPos.find(keyOf(pos));
         if (it == byPos.end()) {
             rebuildPositions();
@@ -173,12 +176,15 @@ template <unsigned short dim> int elementMatrices(RefCase& rc, double* M, double
 }
 
 thread_local std::string g_lastError;
+int g_threads = 1;  // Problem::m_nThreads of the next case = number of "Lua states" = OpenMP threads (Problem.cpp:30-45)
 
 }  // namespace
 
 extern "C" {
 
 const char* pfem_ref_last_error() { return g_lastError.c_str(); }
+void pfem_ref_set_threads(int n) { g_threads = n > 0 ? n : omp_get_num_procs(); }
+int pfem_ref_get_threads() { return g_threads; }
 
 // Direct solver used by the stand-in Eigen::SparseLU (nullptr -> built-in dense LU).
 void pfem_ref_set_direct_solver(Eigen::standin::DirectSolverFn fn) { Eigen::standin::directSolverHook() = fn; }
@@ -202,7 +208,7 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
                       std::int64_t nFacets, const std::int64_t* facets, const char* problemId, const char* solverId,
                       const double* p) {
     try {
-        omp_set_num_threads(1);  // one parameter table ("Lua state") -> one thread, as Problem::m_nThreads = 1 implies
+        omp_set_num_threads(g_threads);  // one parameter table ("Lua state") per thread, as in Problem.cpp:30-45
         auto rc = std::make_unique<RefCase>();
         rc->dim = dim;
         rc->N = static_cast<std::size_t>(nNodes);
@@ -234,6 +240,7 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
         in.facets = rc->facets.empty() ? nullptr : rc->facets.data();
 
         rc->problem.reset(new Problem(rc->problemId));
+        rc->problem->m_nThreads = static_cast<unsigned int>(g_threads);
         MeshCreateInfo info;
         info.hchar = 1;
         info.boundingBox.assign(2 * dim, 0.0);
@@ -291,7 +298,7 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
         }
         rc->root.set("Solver", solverT);
         rc->root.set("Material", material);
-        rc->problem->m_problemParams = {SolTable(rc->root)};
+        rc->problem->m_problemParams.assign(static_cast<std::size_t>(g_threads), SolTable(rc->root));
         rc->problem->m_statesNumber = in.nStates;
 
         if (!wc)
