@@ -26,7 +26,8 @@ void pfemFlushPhases(pfem_ctx* c) {
 #define API_BEGIN(ctx)                                   \
     if (!(ctx)) return PFEM_ERR_INVALID;                 \
     try {                                                \
-        cudaSetDevice((ctx)->device);
+        cudaSetDevice((ctx)->device);                    \
+        (ctx)->cflFresh = false; /* any call may change positions/states; pfem_wc_step sets it again */
 #define API_END(ctx)                                     \
     }                                                    \
     catch (const PfemFail& f) {                          \
@@ -241,6 +242,7 @@ int pfem_pspg_picard_iter(pfem_ctx* c, const pfem_pspg_params* p, const double* 
     int status = PFEM_OK;
     try {
         cudaSetDevice(c->device);
+        c->cflFresh = false;
         PFEM_REQUIRE(p, PFEM_ERR_INVALID, "picard_iter: params is null");
         PFEM_REQUIRE(c->haveSnapshot, PFEM_ERR_STATE, "picard_iter: call pfem_snapshot_positions first (m_prepare)");
         if (qPrev) fieldsSetQprev(c, qPrev);
@@ -303,6 +305,7 @@ int pfem_wc_run(pfem_ctx* c, const pfem_wc_params* p, int nSteps, double securit
     if (!c) return PFEM_ERR_INVALID;
     try {
         cudaSetDevice(c->device);
+        c->cflFresh = false;
         PFEM_REQUIRE(p, PFEM_ERR_INVALID, "wc_run: params is null");
         return wcRun(c, *p, nSteps, securityCoeff, maxDT, dt, elapsed);
     } catch (const PfemFail& f) {

@@ -142,6 +142,11 @@ struct pfem_ctx {
     // ---- explicit step ----
     DevBuf<double> dtPartial;
     DevBuf<double> wcF0;  // CDS_rho: F0 = sum_e M_e rho_e on the configuration before the move
+    DevBuf<double> wcElemRec;  // two-pass explicit step: per-(local node, element) momentum records
+    DevBuf<double> wcContRec;  // per-element continuity record (alpha, beta, V/NPE, he)
+    DevBuf<double> wcCfl2;     // per node (max(u^2, c^2), alpha^2) of the state the last two-pass step produced
+    bool cflFresh = false;     // wcContRec.he / wcCfl2 describe the current positions and states
+    double cflMu = 0, cflK0 = 0, cflK0p = 0;
 
     // ---- free-surface facets / surface tension (facets.cu) ----
     int nFacets = 0, nFstNodes = 0;
@@ -173,6 +178,9 @@ struct pfem_ctx {
                         &facetRec, &fstNode, &fstPtr, &fstItem})
             b->accounting = &deviceBytes;
         fst4.accounting = &deviceBytes;
+        wcElemRec.accounting = &deviceBytes;
+        wcContRec.accounting = &deviceBytes;
+        wcCfl2.accounting = &deviceBytes;
         for (auto* b : {&flags, &dirMask, &stageB}) b->accounting = &deviceBytes;
         for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &Wblk, &kx, &kr, &kr0,
                         &kp, &kp2, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &sendBuf})

@@ -19,9 +19,17 @@
 namespace {
 
 __device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+// 32-byte records move with ONE 256-bit instruction (sm_100: LDG.E.ENL2.256 / STG.E.ENL2.256); p must be 32-byte aligned
 __device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
-    *reinterpret_cast<double2*>(p) = make_double2(a, b);
-    *reinterpret_cast<double2*>(p + 2) = make_double2(c, d);
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+struct D4 {
+    double x, y, z, w;
+};
+__device__ __forceinline__ D4 ld4(const double* p) {
+    D4 r;
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(p));
+    return r;
 }
 
 __global__ void k_wc_kick_move(int nNodes, int dim, double dtVal, const double* __restrict__ dtPtr,
@@ -53,17 +61,15 @@ __device__ __forceinline__ void loadElem(const double* __restrict__ XA, const do
     double px[NPE][DIM];
 #pragma unroll
     for (int m = 0; m < NPE; ++m) {
-        const double* xp = XA + (size_t)nd[m] * 4;
-        const double* vp = VA + (size_t)nd[m] * 4;
-        const double2 x01 = ld2(xp), x23 = ld2(xp + 2), v01 = ld2(vp), v23 = ld2(vp + 2);
-        px[m][0] = x01.x, px[m][1] = x01.y;
-        vel[m][0] = v01.x, vel[m][1] = v01.y;
+        const D4 xr = ld4(XA + (size_t)nd[m] * 4), vr = ld4(VA + (size_t)nd[m] * 4);
+        px[m][0] = xr.x, px[m][1] = xr.y;
+        vel[m][0] = vr.x, vel[m][1] = vr.y;
         if constexpr (DIM == 3) {
-            px[m][2] = x23.x;
-            vel[m][2] = v23.x;
+            px[m][2] = xr.z;
+            vel[m][2] = vr.z;
         }
-        xw[m] = x23.y;
-        vw[m] = v23.y;
+        xw[m] = xr.w;
+        vw[m] = vr.w;
     }
     double J[DIM][DIM];
 #pragma unroll
@@ -102,6 +108,36 @@ __device__ __forceinline__ void loadElem(const double* __restrict__ XA, const do
         for (int m = 0; m < DIM; ++m) G.g[d][m + 1] = inv[m][d];
     }
     G.V = det * REF;
+}
+
+// he = 2 r_in of Element::getRin (Element.cpp:226-294) from the node positions
+template <int DIM> __device__ __forceinline__ double elemHe(const double (&px)[DIM + 1][3]) {
+    constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
+    if constexpr (DIM == 2) {
+        const double J00 = px[1][0] - px[0][0], J01 = px[2][0] - px[0][0], J10 = px[1][1] - px[0][1], J11 = px[2][1] - px[0][1];
+        const double A = (J00 * J11 - J10 * J01) * REF;
+        auto dist = [&](int p, int q) {
+            const double dx = px[p][0] - px[q][0], dy = px[p][1] - px[q][1];
+            return sqrt(dx * dx + dy * dy);
+        };
+        const double s = (dist(0, 1) + dist(1, 2) + dist(0, 2)) / 2;
+        return 2 * (A / s);
+    } else {
+        const double x0 = px[0][0], x1 = px[1][0], x2 = px[2][0], x3 = px[3][0];
+        const double y0 = px[0][1], y1 = px[1][1], y2 = px[2][1], y3 = px[3][1];
+        const double z0 = px[0][2], z1 = px[1][2], z2 = px[2][2], z3 = px[3][2];
+        const double J00 = x1 - x0, J01 = x2 - x0, J02 = x3 - x0, J10 = y1 - y0, J11 = y2 - y0, J12 = y3 - y0,
+                     J20 = z1 - z0, J21 = z2 - z0, J22 = z3 - z0;
+        const double det = J00 * J11 * J22 + J01 * J12 * J20 + J02 * J10 * J21 - J20 * J11 * J02 - J21 * J12 * J00 -
+                           J22 * J10 * J01;
+        auto nrm = [](double p, double q, double r) { return sqrt(p * p + q * q + r * r); };
+        const double n1 = nrm(J10 * J21 - J20 * J11, J20 * J01 - J00 * J21, J00 * J11 - J10 * J01);
+        const double n2 = nrm(J12 * J21 - J22 * J11, J22 * J01 - J02 * J21, J02 * J11 - J12 * J01);
+        const double n3 = nrm(J10 * J22 - J20 * J12, J20 * J02 - J00 * J22, J00 * J12 - J10 * J02);
+        const double n4 = nrm((y1 - y3) * (z2 - z3) - (z1 - z3) * (y2 - y3), (z1 - z3) * (x2 - x3) - (x1 - x3) * (z2 - z3),
+                              (x1 - x3) * (y2 - y3) - (y1 - y3) * (x2 - x3));
+        return 2 * (6 * (det * REF) / (n1 + n2 + n3 + n4));
+    }
 }
 
 // Incident-element stream of one lane with look-ahead: element ids are fetched three trips ahead, connectivity two trips
@@ -390,6 +426,219 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const doub
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Two-pass ("element record") variants of the CDS_dpdt continuity and of the momentum pass.  The gather kernels above
+// recompute the geometry of every element once per incident node (4x in 3-D) behind a dependent n2e -> conn -> record
+// chain.  Here pass E runs one thread per ELEMENT (coalesced connectivity, four independent record gathers, geometry
+// once) and writes what each of its nodes will need; pass N runs the usual LPN lanes per NODE over its incidence list,
+// in the same order as the gather kernels (bit-reproducible, partition-independent), reads one 32-byte sector per
+// incident element and applies the nodal epilogue.  Still no atomics.
+//  continuity: the nodal contribution is affine in the node's own pressure, F0_i = alpha_e + beta_e p_i, m_i = V/NPE, so
+//              the record is per ELEMENT (alpha, beta, V/NPE, -) and is re-read from L2 by the element's other nodes;
+//  momentum:   the record is per (element, local node): (F_x, F_y, F_z, lumped rho-mass).
+template <int DIM>
+__global__ void __launch_bounds__(256) k_wc_cont_elem(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
+                                                      const double* __restrict__ V4, double dtVal, const double* __restrict__ dtPtr,
+                                                      double K0, double K0p, int meduri, double* __restrict__ rec) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nElems) return;
+    const double dtStep = dtPtr ? *dtPtr : dtVal;
+    int nd[NPE];
+    if constexpr (DIM == 3) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(conn + (size_t)e * 4));
+        nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
+    } else {
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) nd[m] = __ldg(conn + (size_t)e * NPE + m);
+    }
+    double P[NPE], vel[NPE][DIM], rho[NPE];
+    ElemGeo<DIM> G;
+    loadElem<DIM>(X4, V4, nd, P, vel, rho, G);
+    double sumP = 0, divv = 0;
+#pragma unroll
+    for (int q = 0; q < NPE; ++q) {
+        sumP += P[q];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) divv += G.g[c][q] * vel[q][c];
+    }
+    // F0_i = -dt V divv (K0/NPE + K0' PHI (p_i + sumP)) + (meduri ? V PHI (p_i + sumP) : (V/NPE) p_i)
+    const double adv = -dtStep * G.V * divv;
+    const double alpha = adv * (K0 / NPE + K0p * PHI * sumP) + (meduri ? G.V * PHI * sumP : 0.0);
+    const double beta = adv * (K0p * PHI) + (meduri ? G.V * PHI : G.V / NPE);
+    double px[NPE][3];
+#pragma unroll
+    for (int m = 0; m < NPE; ++m) {
+        const double* xp = X4 + (size_t)nd[m] * 4;  // L1 hits: loadElem just read these records
+        px[m][0] = xp[0], px[m][1] = xp[1], px[m][2] = xp[2];
+    }
+    st4(rec + (size_t)e * 4, alpha, beta, G.V / NPE, elemHe<DIM>(px));  // he for the CFL pass (k_wc_dt_fast)
+}
+
+template <int DIM, int LPN>
+__global__ void __launch_bounds__(256) k_wc_cont_node(const WcArgs a, const double* __restrict__ rec, const double* __restrict__ X4,
+                                                      const double* __restrict__ V4, double* __restrict__ X4n,
+                                                      double* __restrict__ V4n) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / LPN, sub = t % LPN;
+    const bool valid = i < a.nNodes;
+    double m = 0, F0 = 0;
+    if (valid) {
+        const int eb = a.n2ePtr[i], end = a.n2ePtr[i + 1];
+        const double pi = X4[(size_t)i * 4 + 3];
+        for (int pos = eb + sub; pos < end; pos += LPN) {
+            const D4 r = ld4(rec + (size_t)__ldg(a.n2e + pos) * 4);
+            F0 += r.x + r.y * pi;
+            m += r.z;
+        }
+    }
+    m = groupSum<LPN>(m);
+    F0 = groupSum<LPN>(F0);
+    if (valid && sub == 0) {
+        const bool isFree = a.flags[i] & PFEM_NODE_FREE;
+        double inv = 1.0 / m;
+        if (isFree) {
+            F0 = 0.0;
+            inv = 1.0;
+        }
+        const double p = inv * F0;
+        const double rho = pow((a.K0p / a.K0) * p + 1.0, 1.0 / a.K0p) * a.rhoStar;
+        const double* xp = X4 + (size_t)i * 4;
+        const double* vp = V4 + (size_t)i * 4;
+        st4(X4n + (size_t)i * 4, xp[0], xp[1], xp[2], p);
+        st4(V4n + (size_t)i * 4, vp[0], vp[1], vp[2], rho);
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256) k_wc_mom_elem(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
+                                                     const double* __restrict__ V4, double mu, double bx, double by, double bz,
+                                                     double* __restrict__ rec) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nElems) return;
+    int nd[NPE];
+    if constexpr (DIM == 3) {
+        const int4 q = __ldg(reinterpret_cast<const int4*>(conn + (size_t)e * 4));
+        nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
+    } else {
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) nd[m] = __ldg(conn + (size_t)e * NPE + m);
+    }
+    double P[NPE], vel[NPE][DIM], rho[NPE];
+    ElemGeo<DIM> G;
+    loadElem<DIM>(X4, V4, nd, P, vel, rho, G);
+    const double body[3] = {bx, by, bz};
+    double sumP = 0, sumR = 0;
+    double Gm[DIM][DIM];  // G_ac = sum_j v_{j,a} g[c][j]
+#pragma unroll
+    for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) Gm[aa][c] = 0;
+#pragma unroll
+    for (int q = 0; q < NPE; ++q) {
+        sumP += P[q];
+        sumR += rho[q];
+#pragma unroll
+        for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) Gm[aa][c] += vel[q][aa] * G.g[c][q];
+    }
+    double tr = 0;
+#pragma unroll
+    for (int aa = 0; aa < DIM; ++aa) tr += Gm[aa][aa];
+    const double pbar = sumP / NPE;
+    double sig[DIM][DIM];  // mu (G + G^T - 2/3 tr I)
+#pragma unroll
+    for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+            double sv = Gm[aa][c] + Gm[c][aa];
+            if (c == aa) sv -= (2.0 / 3.0) * tr;
+            sig[aa][c] = mu * sv;
+        }
+#pragma unroll
+    for (int q = 0; q < NPE; ++q) {
+        const double li_mass = G.V * PHI * (rho[q] + sumR);  // lumped rho-mass == sum_g w (N.rho) N_q
+        double F[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int aa = 0; aa < DIM; ++aa) {
+            double sg = 0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) sg += sig[aa][c] * G.g[c][q];
+            F[aa] = -G.V * sg + G.V * pbar * G.g[aa][q] + body[aa] * li_mass;
+        }
+        st4(rec + ((size_t)q * nElems + e) * 4, F[0], F[1], F[2], li_mass);  // plane q: consecutive lanes, consecutive sectors
+    }
+}
+
+template <int DIM, int LPN>
+__global__ void __launch_bounds__(256) k_wc_mom_node(const WcArgs a, const double* __restrict__ rec, size_t nElems,
+                                                     const unsigned* __restrict__ n2eSlots, const int* __restrict__ diagSlot,
+                                                     const double* __restrict__ X4, const double* __restrict__ V4,
+                                                     double* __restrict__ V4out, double* __restrict__ A4out,
+                                                     double* __restrict__ X4out, double* __restrict__ cfl2) {
+    constexpr int NPE = DIM + 1;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t / LPN, sub = t % LPN;
+    const bool valid = i < a.nNodes;
+    const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
+    double M = 0, F[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) F[c] = 0;
+    if (valid) {
+        const int eb = a.n2ePtr[i], end = a.n2ePtr[i + 1];
+        const unsigned mine = (unsigned)diagSlot[i];
+        for (int pos = eb + sub; pos < end; pos += LPN) {
+            const unsigned sl = __ldg(n2eSlots + pos);  // slots of the element's nodes in this node's neighbour list
+            int li = 0;
+#pragma unroll
+            for (int q = 1; q < NPE; ++q) li = (((sl >> (8 * q)) & 0xffu) == mine) ? q : li;
+            const D4 r = ld4(rec + ((size_t)li * nElems + (size_t)__ldg(a.n2e + pos)) * 4);
+            F[0] += r.x;
+            F[1] += r.y;
+            if constexpr (DIM == 3) F[2] += r.z;
+            M += r.w;
+        }
+    }
+    M = groupSum<LPN>(M);
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) F[c] = groupSum<LPN>(F[c]);
+    if (valid && sub == 0) {
+        const uint8_t fl = a.flags[i];
+        const bool isFree = fl & PFEM_NODE_FREE, isBound = fl & PFEM_NODE_BOUND;
+        const double* vp = V4 + (size_t)i * 4;
+        double inv = 1.0 / M;
+        double acc[3] = {0, 0, 0}, vn[3] = {0, 0, 0};
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) {
+            double f = F[c], iv = inv;
+            if (a.fst4) f += a.fst4[(size_t)i * 4 + c];  // facet loop of m_applyBC (MomEquation.inl:312-336)
+            if (isFree && !isBound) {
+                f = a.body[c];
+                iv = 1.0;
+            } else if (isBound && a.dirMask[i]) {
+                f = a.dirVal4[(size_t)i * 4 + c];  // reference hazard 10
+                iv = 1.0;
+            }
+            acc[c] = iv * f;
+            vn[c] = vp[c] + 0.5 * dtStep * acc[c];
+        }
+        st4(V4out + (size_t)i * 4, vn[0], vn[1], vn[2], vp[3]);
+        st4(A4out + (size_t)i * 4, acc[0], acc[1], acc[2], 0.0);
+        const double* xq = X4 + (size_t)i * 4;
+        st4(X4out + (size_t)i * 4, xq[0], xq[1], xq[2], xq[3]);
+        // nodal CFL quantities of computeNextDT (Solver.cpp:209-216) on the new state: max(u^2, c^2) and alpha^2
+        double u2 = vn[0] * vn[0] + vn[1] * vn[1];
+        if (DIM == 3) u2 += vn[2] * vn[2];
+        const double c2 = (a.K0 + a.K0p * xq[3]) / vp[3];
+        const double alpha = a.mu / vp[3];
+        *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(fmax(u2, c2), alpha * alpha);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Staged variants: the LPN lanes of a node first copy the 64-byte records (x,y,z,p | u,v,w,rho) of the node's
 // neighbours into shared memory ONCE (instead of gathering them once per incident element, ~5x redundantly), then read
 // the element nodes by neighbour SLOT (n2eSlots) -- no n2e -> conn -> node dependent chain, ~3x fewer L1 wavefronts.
@@ -647,7 +896,6 @@ __global__ void __launch_bounds__(256) k_wc_dt(int nElems, const int* __restrict
                                                const double* __restrict__ V4, double mu, double K0, double K0p, double sc2,
                                                double* __restrict__ partial) {
     constexpr int NPE = DIM + 1;
-    constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
     double best = 1.7976931348623157e308;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nElems; e += gridDim.x * blockDim.x) {
         int nd[NPE];
@@ -667,36 +915,58 @@ __global__ void __launch_bounds__(256) k_wc_dt(int nElems, const int* __restrict
             mx = fmax(fmax(u2, c2), mx);
             alphaMax = fmax(alphaMax, alpha * alpha);
         }
-        double he;
-        if constexpr (DIM == 2) {
-            const double J00 = px[1][0] - px[0][0], J01 = px[2][0] - px[0][0], J10 = px[1][1] - px[0][1], J11 = px[2][1] - px[0][1];
-            const double A = (J00 * J11 - J10 * J01) * REF;
-            auto dist = [&](int p, int q) {
-                const double dx = px[p][0] - px[q][0], dy = px[p][1] - px[q][1];
-                return sqrt(dx * dx + dy * dy);
-            };
-            const double s = (dist(0, 1) + dist(1, 2) + dist(0, 2)) / 2;
-            he = 2 * (A / s);
-        } else {
-            const double x0 = px[0][0], x1 = px[1][0], x2 = px[2][0], x3 = px[3][0];
-            const double y0 = px[0][1], y1 = px[1][1], y2 = px[2][1], y3 = px[3][1];
-            const double z0 = px[0][2], z1 = px[1][2], z2 = px[2][2], z3 = px[3][2];
-            const double J00 = x1 - x0, J01 = x2 - x0, J02 = x3 - x0, J10 = y1 - y0, J11 = y2 - y0, J12 = y3 - y0,
-                         J20 = z1 - z0, J21 = z2 - z0, J22 = z3 - z0;
-            const double det = J00 * J11 * J22 + J01 * J12 * J20 + J02 * J10 * J21 - J20 * J11 * J02 - J21 * J12 * J00 -
-                               J22 * J10 * J01;
-            auto nrm = [](double p, double q, double r) { return sqrt(p * p + q * q + r * r); };
-            const double n1 = nrm(J10 * J21 - J20 * J11, J20 * J01 - J00 * J21, J00 * J11 - J10 * J01);
-            const double n2 = nrm(J12 * J21 - J22 * J11, J22 * J01 - J02 * J21, J02 * J11 - J12 * J01);
-            const double n3 = nrm(J10 * J22 - J20 * J12, J20 * J02 - J00 * J22, J00 * J12 - J10 * J02);
-            const double n4 = nrm((y1 - y3) * (z2 - z3) - (z1 - z3) * (y2 - y3), (z1 - z3) * (x2 - x3) - (x1 - x3) * (z2 - z3),
-                                  (x1 - x3) * (y2 - y3) - (y1 - y3) * (x2 - x3));
-            he = 2 * (6 * (det * REF) / (n1 + n2 + n3 + n4));
-        }
+        const double he = elemHe<DIM>(px);
         // max over nodes of max(u2, c2, 4 alpha^2/he^2): he is per element, so the alpha term can be taken outside
         mx = fmax(mx, 4 * alphaMax / (he * he));
         const double cand = sc2 * he * he / mx;
         best = (cand < best || cand != cand) ? cand : best;  // NaN propagates (Solver.cpp:231-232)
+    }
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = (other < best || other != other) ? other : best;
+    }
+    if (lane == 0) sh[w] = best;
+    __syncthreads();
+    if (w == 0) {
+        double b2 = lane < (blockDim.x >> 5) ? sh[lane] : 1.7976931348623157e308;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double other = __shfl_xor_sync(0xffffffffu, b2, o);
+            b2 = (other < b2 || other != other) ? other : b2;
+        }
+        if (lane == 0) partial[blockIdx.x] = b2;
+    }
+}
+// CFL after a two-pass step: he was stored by k_wc_cont_elem (the mesh has not moved since), max(u^2, c^2) and alpha^2 per
+// node by k_wc_mom_node (24x fewer divisions than per element-node visit) -- same candidates, same minimum.
+template <int DIM>
+__global__ void __launch_bounds__(256) k_wc_dt_fast(int nElems, const int* __restrict__ conn, const double* __restrict__ contRec,
+                                                    const double* __restrict__ cfl2, double sc2, double* __restrict__ partial) {
+    constexpr int NPE = DIM + 1;
+    double best = 1.7976931348623157e308;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nElems; e += gridDim.x * blockDim.x) {
+        int nd[NPE];
+        if constexpr (DIM == 3) {
+            const int4 q = __ldg(reinterpret_cast<const int4*>(conn + (size_t)e * 4));
+            nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
+        } else {
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) nd[m] = __ldg(conn + (size_t)e * NPE + m);
+        }
+        const double he = contRec[(size_t)e * 4 + 3];
+        double mx = 0, alphaMax = 0;
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) {
+            const double2 c = ld2(cfl2 + (size_t)nd[m] * 2);
+            mx = fmax(c.x, mx);
+            alphaMax = fmax(alphaMax, c.y);
+        }
+        mx = fmax(mx, 4 * alphaMax / (he * he));
+        const double cand = sc2 * he * he / mx;
+        best = (cand < best || cand != cand) ? cand : best;
     }
     __shared__ double sh[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -770,9 +1040,16 @@ __global__ void k_dt_chain(const double* __restrict__ partial, int n, double max
     }
 }
 
+// PFEM_WC_CFG: 10 (default) two-pass element records | 6: direct gathers, 4 lanes per node | 0: 8 lanes per node | 7: staged records
+int wcCfg() {
+    static const int cfg = getenv("PFEM_WC_CFG") ? atoi(getenv("PFEM_WC_CFG")) : 10;
+    return cfg;
+}
+
 // kick + continuity + momentum of one step on the context's stream; dtPtr != null: dt is read from the device
 void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* dtPtr) {
-    static const int cfg = getenv("PFEM_WC_CFG") ? atoi(getenv("PFEM_WC_CFG")) : 6;
+    const int cfg = wcCfg();
+    c->cflMu = p.mu, c->cflK0 = p.K0, c->cflK0p = p.K0p;
     WcArgs a;
     a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.flags = c->flags.p;
     a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p, a.nNodes = c->nRows;  // rows = owned nodes
@@ -827,6 +1104,18 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         PhaseScope ph(c, "Solving continuity eq");
         if (p.eqType == PFEM_WC_CDS_DRHODT) PFEM_WC_LAUNCH_RHO(1, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, nullptr);
         else if (p.eqType == PFEM_WC_CDS_RHO) PFEM_WC_LAUNCH_RHO(2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcF0.p);
+        else if (cfg == 10) {  // two-pass: element records, then the nodal gather
+            const int ge = divUp(c->nElems, 256), gn = divUp((int64_t)c->nRows * 4, 256);
+            if (c->dim == 2) {
+                k_wc_cont_elem<2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+                LAUNCH_CHECK(c);
+                k_wc_cont_node<2, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+            } else {
+                k_wc_cont_elem<3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+                LAUNCH_CHECK(c);
+                k_wc_cont_node<3, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+            }
+        }
         else if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         else if (cfg == 0) PFEM_WC_LAUNCH(k_wc_cont, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         else PFEM_WC_LAUNCH(k_wc_cont, 4, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
@@ -835,7 +1124,19 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
     }
     {
         PhaseScope ph(c, "Solving momentum eq");
-        if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_mom_s, 8, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
+        if (cfg == 10) {
+            const int ge = divUp(c->nElems, 256), gn = divUp((int64_t)c->nRows * 4, 256);
+            if (c->dim == 2) {
+                k_wc_mom_elem<2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+                LAUNCH_CHECK(c);
+                k_wc_mom_node<2, 4><<<gn, 256, 0, c->stream>>>(a, c->wcElemRec.p, (size_t)c->nElems, c->n2eSlots.p, c->diagSlot.p, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
+            } else {
+                k_wc_mom_elem<3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+                LAUNCH_CHECK(c);
+                k_wc_mom_node<3, 4><<<gn, 256, 0, c->stream>>>(a, c->wcElemRec.p, (size_t)c->nElems, c->n2eSlots.p, c->diagSlot.p, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
+            }
+        }
+        else if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_mom_s, 8, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
         else if (cfg == 0) PFEM_WC_LAUNCH(k_wc_mom, 8, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
         else PFEM_WC_LAUNCH(k_wc_mom, 4, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
         LAUNCH_CHECK(c);
@@ -847,8 +1148,15 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
     }
 }
 
-void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int grid) {
+void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int grid, bool afterTwoPassStep = false) {
     const double sc2 = securityCoeff * securityCoeff;
+    // the stored he / nodal CFL values belong to the two-pass step that has just run with the same material constants
+    if (afterTwoPassStep && c->nRanks == 1 && p.eqType == PFEM_WC_CDS_DPDT && p.mu == c->cflMu && p.K0 == c->cflK0 && p.K0p == c->cflK0p) {
+        if (c->dim == 2) k_wc_dt_fast<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->wcContRec.p, c->wcCfl2.p, sc2, c->dtPartial.p);
+        else k_wc_dt_fast<3><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->wcContRec.p, c->wcCfl2.p, sc2, c->dtPartial.p);
+        LAUNCH_CHECK(c);
+        return;
+    }
     if (c->dim == 2)
         k_wc_dt<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
     else
@@ -865,6 +1173,11 @@ void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     c->X4b.reserve(n4);
     c->V4b.reserve(n4);
     if (p.eqType == PFEM_WC_CDS_RHO) c->wcF0.reserve((size_t)c->nNodes);
+    if (wcCfg() == 10) {  // before any graph capture
+        c->wcElemRec.reserve((size_t)std::max(c->nElems, 1) * (c->dim + 1) * 4);
+        c->wcContRec.reserve((size_t)std::max(c->nElems, 1) * 4);
+        c->wcCfl2.reserve((size_t)c->nNodes * 2);
+    }
 }
 
 }  // namespace
@@ -872,6 +1185,7 @@ void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
 void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     checkStepArgs(c, p, dt);
     launchStep(c, p, dt, nullptr);
+    c->cflFresh = (wcCfg() == 10);  // cleared by the next API call that is not pfem_wc_next_dt (capi.cu)
 }
 
 int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dtOut) {
@@ -882,7 +1196,7 @@ int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double 
     c->dtPartial.reserve(grid + 8);
     c->scal.reserve(SC_COUNT);
     if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
-    launchDt(c, p, securityCoeff, grid);
+    launchDt(c, p, securityCoeff, grid, c->cflFresh);
     k_min_final<<<1, 256, 0, c->stream>>>(c->dtPartial.p, grid, c->scal.p + SC_COUNT - 1);
     LAUNCH_CHECK(c);
     if (c->nRanks > 1) commAllReduceMin(c, c->scal.p + SC_COUNT - 1);
@@ -916,7 +1230,7 @@ int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff
         const long long launches0 = c->launches;
         CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         launchStep(c, p, *dtInOut, dtDev);
-        launchDt(c, p, securityCoeff, grid);
+        launchDt(c, p, securityCoeff, grid, wcCfg() == 10);
         k_dt_chain<<<1, 256, 0, c->stream>>>(c->dtPartial.p, grid, maxDT, dtDev);
         LAUNCH_CHECK(c);
         CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));

@@ -108,3 +108,31 @@ def test_wc_run_equals_step_loop(dim, n, eq):
         assert (ctx.get_states(0, 2 * dim + 2) == ref_states).all()
         assert (ctx.get_positions() == ref_x).all()
     assert dt_next == ref_dt and abs(el - elapsed) <= 1e-15 * elapsed
+
+
+@pytest.mark.parametrize("dim,n", [(2, 16), (3, 8)])
+def test_wc_dt_after_step_matches_full_recomputation(dim, n):
+    """pfem_wc_next_dt right after pfem_wc_step may reuse what the step left on the device (element he, nodal
+    max(u^2, c^2) and alpha^2 -- two-pass configuration); after any other call it recomputes everything.  Same dt."""
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.01, permute=True)
+    st = mg.wc_state(mesh)
+    st["acc"] = 0.5 * np.random.default_rng(9).standard_normal(st["acc"].shape)
+    W = mg.WC_PARAMS
+    g = mg.gravity(dim)
+    wp_ref = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True, "CDS_dpdt")
+    with PfemContext(dim, 0) as ctx:
+        ctx.set_mesh(mesh)
+        ctx.set_states(0, _pack(st))
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True, "CDS_dpdt")
+        x_ref, st_ref = mesh.x, st
+        dt = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+        for _ in range(3):
+            ctx.wc_step(wp, dt)
+            x_ref, st_ref = orc.wc_step(mesh, x_ref, st_ref, wp_ref, dt)
+            dt_after_step = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+            ctx.get_positions()                                   # any other call drops the step's leftovers
+            dt_full = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+            dt_oracle = orc.wc_next_dt(mesh, x_ref, st_ref, wp_ref, W["securityCoeff"], 1e-3)
+            assert abs(dt_after_step - dt_full) <= 1e-15 * dt_full
+            assert abs(dt_full - dt_oracle) <= 1e-12 * dt_oracle
+            dt = dt_full
