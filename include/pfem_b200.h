@@ -170,6 +170,12 @@ int pfem_pspg_matvec(pfem_ctx* ctx, const double* x, double* y);
  * Operates on the device-resident states; nSteps > 1 repeats with the CFL time step recomputed on the device between
  * steps (computeNextDT) when adaptDT != 0. */
 int pfem_wc_step(pfem_ctx* ctx, const pfem_wc_params* p, double dt);
+/* Kernel formulation of the explicit step (a tuning knob like pfem_pspg_set_preconditioner; results agree to rounding,
+ * each variant is bit-reproducible and partition-independent): 0 = chosen by mesh size (default), 6 = one gather kernel
+ * per equation (4 lanes per node over the incident elements), 7 = the same with staged neighbour records, 11 = two
+ * passes per equation (element records, then an ordered nodal gather; the CFL pass reuses what the step stored),
+ * 12 = two-pass continuity + gather momentum. */
+int pfem_wc_set_variant(pfem_ctx* ctx, int variant);
 /* SolverWCompNewton::computeNextDT (WCompNewton/Solver.cpp:192-234) incl. Element::getRin (Element.cpp:226-294) */
 int pfem_wc_next_dt(pfem_ctx* ctx, const pfem_wc_params* p, double securityCoeff, double maxDT, double* dt);
 /* nSteps iterations of the Problem::simulate loop body for the explicit solver between two remeshes

@@ -70,6 +70,7 @@ SYMBOLS = {
     "pfem_pspg_export_csc": (C.c_int, [_VP, _I64P, _I32P, _I32P, _DP, _DP]),
     "pfem_pspg_matvec": (C.c_int, [_VP, _DP, _DP]),
     "pfem_wc_step": (C.c_int, [_VP, C.POINTER(WcParams), C.c_double]),
+    "pfem_wc_set_variant": (C.c_int, [_VP, C.c_int]),
     "pfem_wc_next_dt": (C.c_int, [_VP, C.POINTER(WcParams), C.c_double, C.c_double, _DP]),
     "pfem_wc_run": (C.c_int, [_VP, C.POINTER(WcParams), C.c_int, C.c_double, C.c_double, _DP, _DP]),
     "pfem_comm_unique_id": (C.c_int, [_VP]),
@@ -317,6 +318,9 @@ class PfemContext:
 
     def wc_step(self, params, dt):
         self._chk(self._L.pfem_wc_step(self._h, C.byref(params), float(dt)))
+
+    def wc_set_variant(self, variant):
+        self._chk(self._L.pfem_wc_set_variant(self._h, int(variant)))
 
     def wc_next_dt(self, params, security_coeff, max_dt):
         dt = C.c_double(0)

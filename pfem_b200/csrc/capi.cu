@@ -281,6 +281,13 @@ int pfem_pspg_matvec(pfem_ctx* c, const double* x, double* y) {
     API_END(c)
 }
 
+int pfem_wc_set_variant(pfem_ctx* c, int variant) {
+    API_BEGIN(c)
+    PFEM_REQUIRE(variant == 0 || variant == 6 || variant == 7 || variant == 11 || variant == 12, PFEM_ERR_INVALID,
+                 "wc_set_variant: 0 (by size), 6 (gather), 7 (staged gather), 11 (two-pass), 12 (two-pass continuity + gather momentum)");
+    c->wcVariant = variant;
+    API_END(c)
+}
 int pfem_wc_step(pfem_ctx* c, const pfem_wc_params* p, double dt) {
     API_BEGIN(c)
     PFEM_REQUIRE(p, PFEM_ERR_INVALID, "wc_step: params is null");

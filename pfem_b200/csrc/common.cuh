@@ -145,6 +145,7 @@ struct pfem_ctx {
     DevBuf<double> wcElemRec;  // two-pass explicit step: per-(local node, element) momentum records
     DevBuf<double> wcContRec;  // per-element continuity record (alpha, beta, V/NPE, he)
     DevBuf<double> wcCfl2;     // per node (max(u^2, c^2), alpha^2) of the state the last two-pass step produced
+    int wcVariant = 0;         // pfem_wc_set_variant: 0 = by size (PFEM_WC_CFG), 6 gather, 11 two-pass, 12 mixed
     bool cflFresh = false;     // wcContRec.he / wcCfl2 describe the current positions and states
     double cflMu = 0, cflK0 = 0, cflK0p = 0;
 

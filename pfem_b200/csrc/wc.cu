@@ -336,7 +336,8 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont_rho(const WcArgs a, const
 // momentum (MomEquation.inl:229-302, 305-374, 216-222)
 template <int DIM, int LPN, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const double* __restrict__ X4, const double* __restrict__ V4,
-                                                double* __restrict__ V4out, double* __restrict__ A4out, double* __restrict__ X4out) {
+                                                double* __restrict__ V4out, double* __restrict__ A4out, double* __restrict__ X4out,
+                                                double* __restrict__ cfl2 = nullptr) {
     constexpr int NPE = DIM + 1;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -422,6 +423,13 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const doub
         st4(A4out + (size_t)i * 4, acc[0], acc[1], acc[2], 0.0);
         const double* xq = X4 + (size_t)i * 4;
         st4(X4out + (size_t)i * 4, xq[0], xq[1], xq[2], xq[3]);  // (x, p_new) becomes the current record: no buffer swap
+        if (cfl2) {  // nodal CFL quantities for k_wc_dt_fast (see k_wc_mom_node)
+            double u2 = vn[0] * vn[0] + vn[1] * vn[1];
+            if (DIM == 3) u2 += vn[2] * vn[2];
+            const double c2 = (a.K0 + a.K0p * xq[3]) / vp[3];
+            const double alpha = a.mu / vp[3];
+            *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(fmax(u2, c2), alpha * alpha);
+        }
     }
 }
 
@@ -940,6 +948,20 @@ __global__ void __launch_bounds__(256) k_wc_dt(int nElems, const int* __restrict
         if (lane == 0) partial[blockIdx.x] = b2;
     }
 }
+// nodal CFL quantities for nodes [first, first+count): the ghost nodes of a partitioned mesh, whose new states arrive by halo
+__global__ void k_wc_cfl_nodes(int first, int count, int dim, const double* __restrict__ X4, const double* __restrict__ V4,
+                               double mu, double K0, double K0p, double* __restrict__ cfl2) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    const int i = first + t;
+    const double* vp = V4 + (size_t)i * 4;
+    double u2 = vp[0] * vp[0] + vp[1] * vp[1];
+    if (dim == 3) u2 += vp[2] * vp[2];
+    const double c2 = (K0 + K0p * X4[(size_t)i * 4 + 3]) / vp[3];
+    const double alpha = mu / vp[3];
+    *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(fmax(u2, c2), alpha * alpha);
+}
+
 // CFL after a two-pass step: he was stored by k_wc_cont_elem (the mesh has not moved since), max(u^2, c^2) and alpha^2 per
 // node by k_wc_mom_node (24x fewer divisions than per element-node visit) -- same candidates, same minimum.
 template <int DIM>
@@ -1040,15 +1062,30 @@ __global__ void k_dt_chain(const double* __restrict__ partial, int n, double max
     }
 }
 
-// PFEM_WC_CFG: 10 (default) two-pass element records | 6: direct gathers, 4 lanes per node | 0: 8 lanes per node | 7: staged records
-int wcCfg() {
+// PFEM_WC_CFG: 10 (default) chooses by size -- two-pass continuity + momentum + CFL-from-stored-values on meshes of >= 200 k
+// elements (below that the step is launch-bound and the 5-launch gather path wins) and, on a partitioned mesh, >= 4 M
+// local elements (measured at C5: 2 GPUs 2.20 -> 1.57 ms/step, but 8 GPUs 0.89 -> 1.00 ms: with 2.5 M elements per rank
+// the step is exchange-latency bound and the extra launches cost more than the kernels save) | 11: two-pass always |
+// 12: two-pass continuity, gather momentum | 6: direct gathers, 4 lanes per node | 0: 8 lanes per node | 7: staged records
+int wcCfgRaw() {
     static const int cfg = getenv("PFEM_WC_CFG") ? atoi(getenv("PFEM_WC_CFG")) : 10;
     return cfg;
+}
+bool wcTwoPass(const pfem_ctx* c) {
+    const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();  // pfem_wc_set_variant overrides the environment
+    if (raw == 11 || raw == 12) return true;
+    if (raw != 10) return false;
+    return c->nRanks == 1 ? c->nElems >= 200000 : c->nElems >= 4000000;
+}
+bool wcTwoPassMom(const pfem_ctx* c) { return (c->wcVariant ? c->wcVariant : wcCfgRaw()) != 12; }
+int wcCfg(const pfem_ctx* c) {
+    const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();
+    return wcTwoPass(c) ? 10 : (raw >= 10 ? 6 : raw);
 }
 
 // kick + continuity + momentum of one step on the context's stream; dtPtr != null: dt is read from the device
 void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* dtPtr) {
-    const int cfg = wcCfg();
+    const int cfg = wcCfg(c);
     c->cflMu = p.mu, c->cflK0 = p.K0, c->cflK0p = p.K0p;
     WcArgs a;
     a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.flags = c->flags.p;
@@ -1099,7 +1136,6 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         if (c->dim == 2) KERNEL<2, LPN_, 2><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);      \
         else KERNEL<3, LPN_, 2><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);                  \
     } while (0)
-    // PFEM_WC_CFG: 6 (default) direct gathers, 4 lanes per node | 0: 8 lanes per node | 7: staged records, 8 lanes per node
     {
         PhaseScope ph(c, "Solving continuity eq");
         if (p.eqType == PFEM_WC_CDS_DRHODT) PFEM_WC_LAUNCH_RHO(1, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, nullptr);
@@ -1124,7 +1160,8 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
     }
     {
         PhaseScope ph(c, "Solving momentum eq");
-        if (cfg == 10) {
+        if (cfg == 10 && !wcTwoPassMom(c)) PFEM_WC_LAUNCH(k_wc_mom, 4, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
+        else if (cfg == 10) {
             const int ge = divUp(c->nElems, 256), gn = divUp((int64_t)c->nRows * 4, 256);
             if (c->dim == 2) {
                 k_wc_mom_elem<2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
@@ -1144,6 +1181,11 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
             commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
             const size_t g0 = (size_t)c->nRows * 4, gn = (size_t)(c->nNodes - c->nRows) * 4;  // ghosts: (x, p_new) from X4b
             if (gn) CUDA_CHECK(cudaMemcpyAsync(c->X4.p + g0, c->X4b.p + g0, gn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            if (cfg == 10 && c->nNodes > c->nRows) {  // ghosts: same nodal CFL values their owners computed in k_wc_mom_node
+                k_wc_cfl_nodes<<<divUp(c->nNodes - c->nRows, 256), 256, 0, c->stream>>>(c->nRows, c->nNodes - c->nRows, c->dim, c->X4.p, c->V4.p,
+                                                                                      p.mu, p.K0, p.K0p, c->wcCfl2.p);
+                LAUNCH_CHECK(c);
+            }
         }
     }
 }
@@ -1151,7 +1193,7 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
 void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int grid, bool afterTwoPassStep = false) {
     const double sc2 = securityCoeff * securityCoeff;
     // the stored he / nodal CFL values belong to the two-pass step that has just run with the same material constants
-    if (afterTwoPassStep && c->nRanks == 1 && p.eqType == PFEM_WC_CDS_DPDT && p.mu == c->cflMu && p.K0 == c->cflK0 && p.K0p == c->cflK0p) {
+    if (afterTwoPassStep && p.eqType == PFEM_WC_CDS_DPDT && p.mu == c->cflMu && p.K0 == c->cflK0 && p.K0p == c->cflK0p) {
         if (c->dim == 2) k_wc_dt_fast<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->wcContRec.p, c->wcCfl2.p, sc2, c->dtPartial.p);
         else k_wc_dt_fast<3><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->wcContRec.p, c->wcCfl2.p, sc2, c->dtPartial.p);
         LAUNCH_CHECK(c);
@@ -1173,7 +1215,7 @@ void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     c->X4b.reserve(n4);
     c->V4b.reserve(n4);
     if (p.eqType == PFEM_WC_CDS_RHO) c->wcF0.reserve((size_t)c->nNodes);
-    if (wcCfg() == 10) {  // before any graph capture
+    if (wcCfg(c) == 10) {  // before any graph capture
         c->wcElemRec.reserve((size_t)std::max(c->nElems, 1) * (c->dim + 1) * 4);
         c->wcContRec.reserve((size_t)std::max(c->nElems, 1) * 4);
         c->wcCfl2.reserve((size_t)c->nNodes * 2);
@@ -1185,7 +1227,7 @@ void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
 void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     checkStepArgs(c, p, dt);
     launchStep(c, p, dt, nullptr);
-    c->cflFresh = (wcCfg() == 10);  // cleared by the next API call that is not pfem_wc_next_dt (capi.cu)
+    c->cflFresh = (wcCfg(c) == 10);  // cleared by the next API call that is not pfem_wc_next_dt (capi.cu)
 }
 
 int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dtOut) {
@@ -1230,7 +1272,7 @@ int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff
         const long long launches0 = c->launches;
         CUDA_CHECK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
         launchStep(c, p, *dtInOut, dtDev);
-        launchDt(c, p, securityCoeff, grid, wcCfg() == 10);
+        launchDt(c, p, securityCoeff, grid, wcCfg(c) == 10);
         k_dt_chain<<<1, 256, 0, c->stream>>>(c->dtPartial.p, grid, maxDT, dtDev);
         LAUNCH_CHECK(c);
         CUDA_CHECK(cudaStreamEndCapture(c->stream, &graph));

@@ -66,8 +66,9 @@ def test_picard_matches_reference_fixture(name):
     assert np.abs(x - z["x_new"]).max() < 1e-9           # positions move by dt*v: 1e-3 * (1e-8 relative of O(1))
 
 
+@pytest.mark.parametrize("variant", [6, 11])
 @pytest.mark.parametrize("name", golden_names("wc_"))
-def test_wc_steps_match_reference_fixture(name):
+def test_wc_steps_match_reference_fixture(name, variant):
     mesh, z = load_golden(name)
     dim, nn, wpar = mesh.dim, mesh.n_nodes, z["wpar"]
     eq = {0: "CDS_dpdt", 1: "CDS_drhodt", 2: "CDS_rho"}[int(wpar[8])]
@@ -77,6 +78,7 @@ def test_wc_steps_match_reference_fixture(name):
             ctx.set_facets(z["facets"])
             ctx.set_surface_tension(float(z["gamma"]))
         ctx.set_states(0, z["q0"])
+        ctx.wc_set_variant(variant)                      # gather kernels | two-pass element records
         wp = ctx.wc_params(wpar[0], wpar[1], wpar[2], wpar[3], wpar[4:7], bool(wpar[7]), eq)
         for step in range(z["dts"].shape[0]):
             dt = ctx.wc_next_dt(wp, float(z["security_coeff"]), float(z["max_dt"]))

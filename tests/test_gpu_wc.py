@@ -27,7 +27,9 @@ def _pack(st):
     (2, 10, dict(permute=True), False, "CDS_rho"),
     (3, 10, dict(free_fraction=0.01, permute=True), True, "CDS_rho"),
 ])
-def test_wc_steps_match_oracle(dim, n, kw, meduri, eq):
+@pytest.mark.parametrize("variant", [6, 11, 12])
+def test_wc_steps_match_oracle(dim, n, kw, meduri, eq, variant):
+    """variant: pfem_wc_set_variant -- gather kernels | two-pass element records | mixed (all must match the oracle)."""
     mesh = mg.kuhn_box(dim, n, **kw)
     st = mg.wc_state(mesh)
     st["acc"] = 0.5 * np.random.default_rng(4).standard_normal(st["acc"].shape)
@@ -37,6 +39,7 @@ def test_wc_steps_match_oracle(dim, n, kw, meduri, eq):
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
         ctx.set_states(0, _pack(st))
+        ctx.wc_set_variant(variant)
         wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, meduri, eq)
         x_ref, st_ref = mesh.x, st
         for step in range(3):
@@ -82,7 +85,8 @@ def test_state_roundtrip():
 
 
 @pytest.mark.parametrize("dim,n,eq", [(2, 20, "CDS_dpdt"), (3, 6, "CDS_dpdt"), (3, 5, "CDS_rho")])
-def test_wc_run_equals_step_loop(dim, n, eq):
+@pytest.mark.parametrize("variant", [6, 11])
+def test_wc_run_equals_step_loop(dim, n, eq, variant):
     """pfem_wc_run (device-chained CFL dt, one CUDA graph per step) == the host loop of wc_step + wc_next_dt, bit for bit."""
     mesh = mg.kuhn_box(dim, n, free_fraction=0.01)
     st = mg.wc_state(mesh)
@@ -92,6 +96,7 @@ def test_wc_run_equals_step_loop(dim, n, eq):
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
         ctx.set_states(0, _pack(st))
+        ctx.wc_set_variant(variant)
         wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True, eq)
         dt = dt0 = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
         elapsed = 0.0
@@ -103,6 +108,7 @@ def test_wc_run_equals_step_loop(dim, n, eq):
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
         ctx.set_states(0, _pack(st))
+        ctx.wc_set_variant(variant)
         wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True, eq)
         dt_next, el = ctx.wc_run(wp, n_steps, W["securityCoeff"], 1e-3, dt0)
         assert (ctx.get_states(0, 2 * dim + 2) == ref_states).all()
@@ -111,7 +117,8 @@ def test_wc_run_equals_step_loop(dim, n, eq):
 
 
 @pytest.mark.parametrize("dim,n", [(2, 16), (3, 8)])
-def test_wc_dt_after_step_matches_full_recomputation(dim, n):
+@pytest.mark.parametrize("variant", [11, 12])
+def test_wc_dt_after_step_matches_full_recomputation(dim, n, variant):
     """pfem_wc_next_dt right after pfem_wc_step may reuse what the step left on the device (element he, nodal
     max(u^2, c^2) and alpha^2 -- two-pass configuration); after any other call it recomputes everything.  Same dt."""
     mesh = mg.kuhn_box(dim, n, free_fraction=0.01, permute=True)
@@ -123,6 +130,7 @@ def test_wc_dt_after_step_matches_full_recomputation(dim, n):
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)
         ctx.set_states(0, _pack(st))
+        ctx.wc_set_variant(variant)
         wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True, "CDS_dpdt")
         x_ref, st_ref = mesh.x, st
         dt = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)

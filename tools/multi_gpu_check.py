@@ -34,44 +34,48 @@ def main():
     ok = True
     # ------------------------------------------------------------------ explicit weakly-compressible steps
     W = mg.WC_PARAMS
-    st = mg.wc_state(mesh)
-    st["acc"] = 0.3 * np.random.default_rng(4).standard_normal(st["acc"].shape)
-    packed = np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
-    ctx.set_states(0, part.scatter_nodal(packed, 2 * dim + 2, nn))
-    wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
-    dts = []
-    for _ in range(3):
-        dt = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
-        dts.append(dt)
-        ctx.wc_step(wp, dt)
-    loc = ctx.get_states(0, 2 * dim + 2).reshape(2 * dim + 2, nl)
-    xloc = ctx.get_positions().reshape(dim, nl)
-    # gather owned values on rank 0
-    glob = torch.zeros((2 * dim + 2 + dim, nn), dtype=torch.float64, device="cuda")
-    idx = torch.from_numpy(part.l2g_nodes[: part.n_owned]).cuda()
-    glob[: 2 * dim + 2, idx] = torch.from_numpy(loc[:, : part.n_owned]).cuda()
-    glob[2 * dim + 2:, idx] = torch.from_numpy(xloc[:, : part.n_owned]).cuda()
-    dist.all_reduce(glob)
-    # ghost copies must equal the owners' values after the last exchange
-    gl = glob.cpu().numpy()
-    ghost_ok = np.array_equal(loc[: dim + 2, part.n_owned:], gl[: dim + 2, part.l2g_nodes[part.n_owned:]])
-    if rank == 0:
-        with PfemContext(dim, lrank) as one:
-            one.set_mesh(mesh)
-            one.set_states(0, packed)
-            wp1 = one.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
-            dts1 = []
-            for _ in range(3):
-                dt = one.wc_next_dt(wp1, W["securityCoeff"], 1e-3)
-                dts1.append(dt)
-                one.wc_step(wp1, dt)
-            ref = one.get_states(0, 2 * dim + 2).reshape(2 * dim + 2, nn)
-            xref = one.get_positions().reshape(dim, nn)
-        same = np.array_equal(gl[: 2 * dim + 2], ref) and np.array_equal(gl[2 * dim + 2:], xref) and dts == dts1
-        err = np.abs(gl[: 2 * dim + 2] - ref).max()
-        print(f"[wc] {world} GPUs vs 1 GPU: bit-identical={same} max|diff|={err:.3e} dts={dts}")
-        ok &= same
-    ok &= ghost_ok
+    for variant in (6, 11):   # pfem_wc_set_variant: gather kernels, two-pass element records
+        ctx.set_positions(part.mesh.x)
+        ctx.wc_set_variant(variant)
+        st = mg.wc_state(mesh)
+        st["acc"] = 0.3 * np.random.default_rng(4).standard_normal(st["acc"].shape)
+        packed = np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
+        ctx.set_states(0, part.scatter_nodal(packed, 2 * dim + 2, nn))
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+        dts = []
+        for _ in range(3):
+            dt = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+            dts.append(dt)
+            ctx.wc_step(wp, dt)
+        loc = ctx.get_states(0, 2 * dim + 2).reshape(2 * dim + 2, nl)
+        xloc = ctx.get_positions().reshape(dim, nl)
+        # gather owned values on rank 0
+        glob = torch.zeros((2 * dim + 2 + dim, nn), dtype=torch.float64, device="cuda")
+        idx = torch.from_numpy(part.l2g_nodes[: part.n_owned]).cuda()
+        glob[: 2 * dim + 2, idx] = torch.from_numpy(loc[:, : part.n_owned]).cuda()
+        glob[2 * dim + 2:, idx] = torch.from_numpy(xloc[:, : part.n_owned]).cuda()
+        dist.all_reduce(glob)
+        # ghost copies must equal the owners' values after the last exchange
+        gl = glob.cpu().numpy()
+        ghost_ok = np.array_equal(loc[: dim + 2, part.n_owned:], gl[: dim + 2, part.l2g_nodes[part.n_owned:]])
+        if rank == 0:
+            with PfemContext(dim, lrank) as one:
+                one.set_mesh(mesh)
+                one.set_states(0, packed)
+                one.wc_set_variant(variant)
+                wp1 = one.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+                dts1 = []
+                for _ in range(3):
+                    dt = one.wc_next_dt(wp1, W["securityCoeff"], 1e-3)
+                    dts1.append(dt)
+                    one.wc_step(wp1, dt)
+                ref = one.get_states(0, 2 * dim + 2).reshape(2 * dim + 2, nn)
+                xref = one.get_positions().reshape(dim, nn)
+            same = np.array_equal(gl[: 2 * dim + 2], ref) and np.array_equal(gl[2 * dim + 2:], xref) and dts == dts1
+            err = np.abs(gl[: 2 * dim + 2] - ref).max()
+            print(f"[wc variant {variant}] {world} GPUs vs 1 GPU: bit-identical={same} max|diff|={err:.3e} dts={dts}")
+            ok &= same
+        ok &= ghost_ok
 
     # ------------------------------------------------------------------ PSPG assemble + distributed BiCGSTAB + Picard body
     P = mg.PSPG_PARAMS
