@@ -12,8 +12,10 @@
 //   WCompNewtonStepB200<dim>        replaces the body of SolverWCompNewton::m_solveWCompNewtonNoT + computeNextDT
 //                                   (physics/WCompNewton/Solver.cpp:192-276) with device-resident states between remeshes.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <limits>
 #include <stdexcept>
@@ -32,19 +34,105 @@ inline void check(pfem_ctx* ctx, int rc, const char* what) {
     if (rc < 0) throw std::runtime_error(std::string(what) + ": " + pfem_last_error(ctx));  // fatal, reference style (MomContEquation.inl:240-241)
 }
 
+// Spatial renumbering applied by the shim between the reference's Mesh and the device (PFEM_RENUMBER=0 switches it off).
+// PFEM3D's node numbering drifts towards random as nodes are added and removed (Mesh.cpp:27-147, 928-1017); the gather
+// kernels are ~3x slower on a randomly numbered 20 M-tet mesh (profiles/).  Nothing in the C ABI
+// depends on the numbering, so nodes are uploaded in Morton (Z-order) order of their coordinates and elements by their
+// smallest new node index; every nodal array crossing the ABI is mapped with toNew/toOld.
+struct Renumbering {
+    std::vector<std::size_t> newOfOld, oldOfNew, elemOldOfNew, elemNewOfOld;
+    bool active = false;
+    static bool enabled() {
+        const char* e = std::getenv("PFEM_RENUMBER");
+        return !(e && e[0] == '0');
+    }
+    std::size_t nodeNew(std::size_t n) const { return active ? newOfOld[n] : n; }
+    std::size_t nodeOld(std::size_t n) const { return active ? oldOfNew[n] : n; }
+    // nodal array in the ABI layout q[n + s*nN]
+    std::vector<double> toNew(const std::vector<double>& q, std::size_t nN) const {
+        if (!active) return q;
+        std::vector<double> o(q.size());
+        for (std::size_t s = 0; s < q.size() / nN; ++s)
+            for (std::size_t n = 0; n < nN; ++n) o[newOfOld[n] + s * nN] = q[n + s * nN];
+        return o;
+    }
+    std::vector<double> toOld(const std::vector<double>& q, std::size_t nN) const {
+        if (!active) return q;
+        std::vector<double> o(q.size());
+        for (std::size_t s = 0; s < q.size() / nN; ++s)
+            for (std::size_t n = 0; n < nN; ++n) o[n + s * nN] = q[newOfOld[n] + s * nN];
+        return o;
+    }
+    template <unsigned short dim, class MeshT> void build(MeshT* pMesh) {
+        const std::size_t nN = pMesh->getNodesCount(), nE = pMesh->getElementsCount();
+        active = enabled() && nN > 1;
+        if (!active) return;
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (std::size_t n = 0; n < nN; ++n)
+            for (unsigned short d = 0; d < dim; ++d) {
+                const double c = pMesh->getNode(n).getCoordinate(d);
+                lo[d] = std::min(lo[d], c);
+                hi[d] = std::max(hi[d], c);
+            }
+        auto spread = [](std::uint64_t v) {  // 21 bits -> every third bit
+            v &= 0x1FFFFFull;
+            v = (v | (v << 32)) & 0x1F00000000FFFFull;
+            v = (v | (v << 16)) & 0x1F0000FF0000FFull;
+            v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+            v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+            v = (v | (v << 2)) & 0x1249249249249249ull;
+            return v;
+        };
+        std::vector<std::pair<std::uint64_t, std::size_t>> keys(nN);
+        for (std::size_t n = 0; n < nN; ++n) {
+            std::uint64_t key = 0;
+            for (unsigned short d = 0; d < dim; ++d) {
+                const double span = hi[d] > lo[d] ? hi[d] - lo[d] : 1.0;
+                const double t = (pMesh->getNode(n).getCoordinate(d) - lo[d]) / span * 2097151.0;
+                key |= spread(static_cast<std::uint64_t>(t < 0 ? 0 : (t > 2097151.0 ? 2097151.0 : t))) << d;
+            }
+            keys[n] = {key, n};
+        }
+        std::sort(keys.begin(), keys.end());
+        oldOfNew.resize(nN);
+        newOfOld.resize(nN);
+        for (std::size_t k = 0; k < nN; ++k) {
+            oldOfNew[k] = keys[k].second;
+            newOfOld[keys[k].second] = k;
+        }
+        std::vector<std::pair<std::size_t, std::size_t>> ek(nE);
+        for (std::size_t e = 0; e < nE; ++e) {
+            std::size_t m = newOfOld[pMesh->getElement(e).getNodeIndex(0)];
+            for (unsigned short k = 1; k <= dim; ++k) m = std::min(m, newOfOld[pMesh->getElement(e).getNodeIndex(k)]);
+            ek[e] = {m, e};
+        }
+        std::sort(ek.begin(), ek.end());
+        elemOldOfNew.resize(nE);
+        elemNewOfOld.resize(nE);
+        for (std::size_t k = 0; k < nE; ++k) {
+            elemOldOfNew[k] = ek[k].second;
+            elemNewOfOld[ek[k].second] = k;
+        }
+    }
+};
+
 // Mesh -> device: connectivity, flags, positions, states [first, first+count), Dirichlet mask/values (Lua evaluated here,
 // serially, exactly where the reference evaluates it: PSPG.inl:206-214, WCompNewton/MomEquation.inl:355-364).
 template <unsigned short dim, class MeshT, class SolverT, class ProblemT, class BcTable>
 void uploadMesh(pfem_ctx* ctx, MeshT* pMesh, SolverT* pSolver, ProblemT* pProblem, BcTable& bc, unsigned short bcFlag,
-                unsigned int firstState, unsigned int stateCount, bool topologyChanged, bool withFacets = false) {
+                unsigned int firstState, unsigned int stateCount, bool topologyChanged, Renumbering& rn,
+                bool withFacets = false) {
     const std::size_t nN = pMesh->getNodesCount(), nE = pMesh->getElementsCount();
     if (topologyChanged) {
+        rn.template build<dim>(pMesh);
         std::vector<uint64_t> conn(nE * (dim + 1));
-        for (std::size_t e = 0; e < nE; ++e)
-            for (unsigned short k = 0; k <= dim; ++k) conn[e * (dim + 1) + k] = pMesh->getElement(e).getNodeIndex(k);
+        for (std::size_t e = 0; e < nE; ++e) {
+            const auto& element = pMesh->getElement(rn.active ? rn.elemOldOfNew[e] : e);
+            for (unsigned short k = 0; k <= dim; ++k) conn[e * (dim + 1) + k] = rn.nodeNew(element.getNodeIndex(k));
+        }
         std::vector<uint8_t> flags(nN);
         for (std::size_t n = 0; n < nN; ++n) {
-            const auto& node = pMesh->getNode(n);
+            const auto& node = pMesh->getNode(rn.nodeOld(n));
             flags[n] = (node.isBound() ? PFEM_NODE_BOUND : 0u) | (node.isFree() ? PFEM_NODE_FREE : 0u) |
                        (node.isFixed() ? PFEM_NODE_FIXED : 0u) | (node.isOnFreeSurface() ? PFEM_NODE_FREE_SURFACE : 0u);
         }
@@ -54,9 +142,9 @@ void uploadMesh(pfem_ctx* ctx, MeshT* pMesh, SolverT* pSolver, ProblemT* pProble
             std::vector<uint64_t> fNodes(nF * dim), fOut(nF), fElem(nF);
             for (std::size_t f = 0; f < nF; ++f) {
                 const auto& facet = pMesh->getFacet(f);
-                for (unsigned short k = 0; k < dim; ++k) fNodes[f * dim + k] = facet.getNodeIndex(k);
-                fOut[f] = facet.getOutNodeIndex();
-                fElem[f] = facet.getElementIndex();
+                for (unsigned short k = 0; k < dim; ++k) fNodes[f * dim + k] = rn.nodeNew(facet.getNodeIndex(k));
+                fOut[f] = rn.nodeNew(facet.getOutNodeIndex());
+                fElem[f] = rn.active ? rn.elemNewOfOld[facet.getElementIndex()] : facet.getElementIndex();
             }
             check(ctx, pfem_set_facets(ctx, (int64_t)nF, fNodes.data(), fOut.data(), fElem.data()), "pfem_set_facets");
         }
@@ -64,12 +152,13 @@ void uploadMesh(pfem_ctx* ctx, MeshT* pMesh, SolverT* pSolver, ProblemT* pProble
     std::vector<double> x(dim * nN), q(stateCount * nN), dval(dim * nN, 0.0);
     std::vector<uint8_t> dmask(nN, 0);
     const double tNext = pProblem->getCurrentSimTime() + pSolver->getTimeStep();
-    for (std::size_t n = 0; n < nN; ++n) {
-        const auto& node = pMesh->getNode(n);
+    for (std::size_t nOld = 0; nOld < nN; ++nOld) {  // old order: the Lua BC functions are called as the reference calls them
+        const auto& node = pMesh->getNode(nOld);
+        const std::size_t n = rn.nodeNew(nOld);
         for (unsigned short d = 0; d < dim; ++d) x[n + d * nN] = node.getCoordinate(d);
         for (unsigned int s = 0; s < stateCount; ++s) q[n + s * nN] = node.getState(firstState + s);
         if (node.isBound() && pSolver->getBcTagFlags(node.getTag(), bcFlag)) {
-            const std::array<double, dim> r = bc.template call<std::array<double, dim>>(pMesh->getNodeType(n) + "V", node.getPosition(), tNext);
+            const std::array<double, dim> r = bc.template call<std::array<double, dim>>(pMesh->getNodeType(nOld) + "V", node.getPosition(), tNext);
             dmask[n] = 1;
             for (unsigned short d = 0; d < dim; ++d) dval[n + d * nN] = r[d];
         }
@@ -126,13 +215,13 @@ public:
         m_par.dt = m_pSolver->getTimeStep();
         // the incompressible solver remeshes after every successful step (IncompNewton/Solver.cpp:241-242): new topology
         uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bcParams[0], m_bcFlags[0], m_statesIndex[0], dim + 1, true,
-                        m_gamma >= 1e-15);
+                        m_rn, m_gamma >= 1e-15);
         std::vector<double> qPrev((dim + 1) * nN), qIter((dim + 1) * nN, 0.0), qIterPrev;
         for (std::size_t n = 0; n < nN; ++n)
             for (unsigned int s = 0; s <= dim; ++s) qPrev[n + s * nN] = m_pMesh->getNode(n).getState(m_statesIndex[0] + s);
         qIterPrev = qPrev;
         check(m_ctx, pfem_snapshot_positions(m_ctx), "pfem_snapshot_positions");         // m_prepare: saveNodesList
-        check(m_ctx, pfem_pspg_assemble(m_ctx, &m_par, qPrev.data()), "pfem_pspg_assemble");
+        check(m_ctx, pfem_pspg_assemble(m_ctx, &m_par, m_rn.toNew(qPrev, nN).data()), "pfem_pspg_assemble");
         unsigned int iterCount = 0;
         double res = std::numeric_limits<double>::max();
         while (res > m_minRes) {
@@ -142,6 +231,7 @@ public:
             const int rc = pfem_pspg_picard_iter(m_ctx, &m_par, nullptr, m_relTol, 100000, qIter.data(), &resAxf, &iters);
             check(m_ctx, rc, "pfem_pspg_picard_iter");
             if (rc == PFEM_NOT_CONVERGED || rc == PFEM_NAN) return false;                 // like a failed factorisation, PSPG.inl:304-312
+            qIter = m_rn.toOld(qIter, nN);                                                // device numbering -> the Mesh's
             res = (m_residual == "Ax_f") ? resAxf : relativeChange(qIter, qIterPrev, nN);
             qIterPrev = qIter;
             if (std::isnan(res)) return false;                                            // PicardAlgo.cpp:79-86
@@ -180,6 +270,7 @@ private:
     }
     pfem_ctx* m_ctx = nullptr;
     pfem_pspg_params m_par{};
+    pfem_b200_shim::Renumbering m_rn;
     double m_gamma = 0.0;
     unsigned int m_maxIter = 10;
     double m_minRes = 1e-6, m_relTol = 1e-12;
@@ -220,7 +311,7 @@ public:
     bool step() {
         using namespace pfem_b200_shim;
         if (m_dirty) {
-            uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bc, 0, 0, 2 * dim + 2, true, m_gamma >= 1e-15);
+            uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bc, 0, 0, 2 * dim + 2, true, m_rn, m_gamma >= 1e-15);
             m_dirty = false;
         }
         check(m_ctx, pfem_wc_step(m_ctx, &m_par, m_pSolver->getTimeStep()), "pfem_wc_step");
@@ -240,6 +331,8 @@ public:
         std::vector<double> q((2 * dim + 2) * nN), x(dim * nN), xOld(dim * nN);
         pfem_b200_shim::check(m_ctx, pfem_get_states(m_ctx, 0, 2 * dim + 2, q.data()), "pfem_get_states");
         pfem_b200_shim::check(m_ctx, pfem_get_positions(m_ctx, x.data()), "pfem_get_positions");
+        q = m_rn.toOld(q, nN);
+        x = m_rn.toOld(x, nN);
         for (std::size_t n = 0; n < nN; ++n) {
             for (unsigned int s = 0; s < 2u * dim + 2u; ++s) m_pMesh->setNodeState(n, s, q[n + s * nN]);
             for (unsigned short d = 0; d < dim; ++d) xOld[n + d * nN] = x[n + d * nN] - m_pMesh->getNode(n).getCoordinate(d);
@@ -255,6 +348,7 @@ private:
     double m_securityCoeff;
     pfem_ctx* m_ctx = nullptr;
     pfem_wc_params m_par{};
+    pfem_b200_shim::Renumbering m_rn;
     double m_gamma = 0.0;
     bool m_dirty = true;
 };

@@ -26,9 +26,10 @@ def _dropin_library():
     ref.use_scipy_direct_solver(False)
 
 
-@pytest.mark.parametrize("dim,n,gamma", [(2, 12, 0.0), (3, 5, 0.0), (3, 4, 7.28)])
-def test_pspg_time_step_through_the_shim(dim, n, gamma):
-    mesh = mg.kuhn_box(dim, n)
+@pytest.mark.parametrize("dim,n,gamma,permute", [(2, 12, 0.0, False), (3, 5, 0.0, True), (3, 4, 7.28, True)])
+def test_pspg_time_step_through_the_shim(dim, n, gamma, permute):
+    """permute: random node/element numbering on the reference side; the shim uploads in Morton order (Renumbering)."""
+    mesh = mg.kuhn_box(dim, n, permute=permute)
     facets = None
     if gamma > 0:
         wavy_free_surface(mesh)
@@ -53,9 +54,10 @@ def test_pspg_time_step_through_the_shim(dim, n, gamma):
     assert np.abs(x_ref - mesh.x).max() > 1e-6  # the step moved the mesh
 
 
-@pytest.mark.parametrize("dim,n,eq,gamma", [(2, 10, "CDS_dpdt", 0.0), (3, 5, "CDS_drhodt", 0.0), (3, 4, "CDS_dpdt", 7.28)])
-def test_wc_steps_through_the_shim(dim, n, eq, gamma):
-    mesh = mg.kuhn_box(dim, n, free_fraction=0.02)
+@pytest.mark.parametrize("dim,n,eq,gamma,permute", [(2, 10, "CDS_dpdt", 0.0, True), (3, 5, "CDS_drhodt", 0.0, False),
+                                                     (3, 4, "CDS_dpdt", 7.28, True)])
+def test_wc_steps_through_the_shim(dim, n, eq, gamma, permute):
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.02, permute=permute)
     facets = None
     if gamma > 0:
         wavy_free_surface(mesh)
