@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const doub
 //  continuity: the nodal contribution is affine in the node's own pressure, F0_i = alpha_e + beta_e p_i, m_i = V/NPE, so
 //              the record is per ELEMENT (alpha, beta, V/NPE, -) and is re-read from L2 by the element's other nodes;
 //  momentum:   the record is per (element, local node): (F_x, F_y, F_z, lumped rho-mass).
-template <int DIM>
-__global__ void __launch_bounds__(256) k_wc_cont_elem(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
+template <int DIM, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_wc_cont_elem(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
                                                       const double* __restrict__ V4, double dtVal, const double* __restrict__ dtPtr,
                                                       double K0, double K0p, int meduri, double* __restrict__ rec) {
     constexpr int NPE = DIM + 1;
@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(256) k_wc_cont_node(const WcArgs a, const doub
     }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(256) k_wc_mom_elem(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
+template <int DIM, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_wc_mom_elem(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
                                                      const double* __restrict__ V4, double mu, double bx, double by, double bz,
                                                      double* __restrict__ rec) {
     constexpr int NPE = DIM + 1;
@@ -1067,6 +1067,11 @@ __global__ void k_dt_chain(const double* __restrict__ partial, int n, double max
 // local elements (measured at C5: 2 GPUs 2.20 -> 1.57 ms/step, but 8 GPUs 0.89 -> 1.00 ms: with 2.5 M elements per rank
 // the step is exchange-latency bound and the extra launches cost more than the kernels save) | 11: two-pass always |
 // 12: two-pass continuity, gather momentum | 6: direct gathers, 4 lanes per node | 0: 8 lanes per node | 7: staged records
+// resident 256-thread blocks per SM the element kernels are compiled for: 3 (80 registers, default) | 2 (100) | 4 (64, spills)
+int wcElemBlocks() {
+    static const int b = getenv("PFEM_WC_EB") ? atoi(getenv("PFEM_WC_EB")) : 3;
+    return b;
+}
 int wcCfgRaw() {
     static const int cfg = getenv("PFEM_WC_CFG") ? atoi(getenv("PFEM_WC_CFG")) : 10;
     return cfg;
@@ -1143,11 +1148,13 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         else if (cfg == 10) {  // two-pass: element records, then the nodal gather
             const int ge = divUp(c->nElems, 256), gn = divUp((int64_t)c->nRows * 4, 256);
             if (c->dim == 2) {
-                k_wc_cont_elem<2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+                k_wc_cont_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
                 LAUNCH_CHECK(c);
                 k_wc_cont_node<2, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
             } else {
-                k_wc_cont_elem<3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+                if (wcElemBlocks() == 4) k_wc_cont_elem<3, 4><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+                else if (wcElemBlocks() == 2) k_wc_cont_elem<3, 2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+                else k_wc_cont_elem<3, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
                 LAUNCH_CHECK(c);
                 k_wc_cont_node<3, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
             }
@@ -1164,11 +1171,13 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         else if (cfg == 10) {
             const int ge = divUp(c->nElems, 256), gn = divUp((int64_t)c->nRows * 4, 256);
             if (c->dim == 2) {
-                k_wc_mom_elem<2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+                k_wc_mom_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
                 LAUNCH_CHECK(c);
                 k_wc_mom_node<2, 4><<<gn, 256, 0, c->stream>>>(a, c->wcElemRec.p, (size_t)c->nElems, c->n2eSlots.p, c->diagSlot.p, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
             } else {
-                k_wc_mom_elem<3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+                if (wcElemBlocks() == 4) k_wc_mom_elem<3, 4><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+                else if (wcElemBlocks() == 2) k_wc_mom_elem<3, 2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+                else k_wc_mom_elem<3, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
                 LAUNCH_CHECK(c);
                 k_wc_mom_node<3, 4><<<gn, 256, 0, c->stream>>>(a, c->wcElemRec.p, (size_t)c->nElems, c->n2eSlots.p, c->diagSlot.p, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
             }
