@@ -41,6 +41,7 @@ def lib():
         L.oracle_pspg_build.restype = C.c_void_p
         L.oracle_pspg_build.argtypes = [C.c_int, i64, i64, ip, dp, dp, dp, bp, dp, C.c_int, bp, dp, dp, dp]
         L.oracle_set_facets.argtypes = [C.c_int, i64, ip, C.c_double]
+        L.oracle_set_thermal.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, bp, dp]
         L.oracle_csc_nnz.restype = i64
         L.oracle_csc_nnz.argtypes = [C.c_void_p]
         L.oracle_csc_copy.argtypes = [C.c_void_p, ip, C.POINTER(C.c_int32), dp]
@@ -142,18 +143,37 @@ def move_positions(mesh, delta, base):
     return x
 
 
-def wc_step(mesh, x, state, params, dt):
-    """One explicit step (WC/Solver.cpp:236-263).  Returns new (x, state) copies."""
+def _set_thermal(thermal, T):
+    """thermal: None or dict(k, cv, alpha, Tr, t_mask uint8[nNodes], t_val float64[nNodes]) -- BoussinesqWC."""
+    if thermal is None:
+        lib().oracle_set_thermal(0, 0.0, 1.0, 0.0, 0.0, None, None, None)
+    else:
+        lib().oracle_set_thermal(1, float(thermal["k"]), float(thermal["cv"]), float(thermal["alpha"]), float(thermal["Tr"]),
+                                 _d(T), _b(thermal["t_mask"]), _d(thermal["t_val"]))
+
+
+def wc_step(mesh, x, state, params, dt, thermal=None):
+    """One explicit step (WC/Solver.cpp:236-263; with `thermal` and state["T"]: m_solveBoussinesqWC, :278-320).
+    Returns new (x, state) copies."""
     x = x.copy()
     st = {k: v.copy() for k, v in state.items()}
+    _set_thermal(thermal, st.get("T"))
     rc = lib().oracle_wc_step(mesh.dim, mesh.n_nodes, mesh.n_elems, _i(mesh.conn), _d(x), _b(mesh.flags),
                               _b(mesh.dir_mask), _d(mesh.dir_val), _d(st["v"]), _d(st["acc"]), _d(st["p"]),
                               _d(st["rho"]), _d(params), float(dt))
+    _set_thermal(None, None)
     assert rc == 0
     return x, st
 
 
-def wc_next_dt(mesh, x, state, params, security_coeff, max_dt):
+def wc_next_dt(mesh, x, state, params, security_coeff, max_dt, thermal=None):
+    if thermal is not None:
+        _set_thermal(thermal, state["T"])
+        try:
+            return lib().oracle_wc_next_dt(mesh.dim, mesh.n_nodes, mesh.n_elems, _i(mesh.conn), _d(x), _d(state["v"]),
+                                           _d(state["p"]), _d(state["rho"]), _d(params), float(security_coeff), float(max_dt))
+        finally:
+            _set_thermal(None, None)
     return lib().oracle_wc_next_dt(mesh.dim, mesh.n_nodes, mesh.n_elems, _i(mesh.conn), _d(x), _d(state["v"]),
                                    _d(state["p"]), _d(state["rho"]), _d(params), float(security_coeff), float(max_dt))
 

@@ -859,6 +859,79 @@ void wcContRho(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* 
 // :201-226 (solve); factors :63-103, :135-139.  The "acceleration" of a Dirichlet node is
 // set to the Dirichlet *velocity* value (:361-369), reproduced as is.
 // ------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------
+// BoussinesqWC additions.  HeatEqWCompNewton (WCompNewton/HeatEquation.inl:154-298: lumped
+// M with f = cv (N.rho), L with f = k, FTot = -dt L T + M T, serial scatter, BC :171-226 without the flux terms
+// Q/Qh/Qr, T = invM F), the buoyancy factor rho (1 - alpha (T - Tr)) of the momentum body force
+// (MomEquation.inl:105-112), the thermal diffusivity k/(cv rho) in computeNextDT (Solver.cpp:214-216,
+// HeatEquation.inl:124-127) and the order heat -> continuity -> momentum of m_solveBoussinesqWC (Solver.cpp:278-320).
+// tMask[n] != 0  <=>  getBcTagFlags(node.getTag(), flag 1) (a "<type>T" Lua function exists); tVal[n] its value.
+// ------------------------------------------------------------------------------------
+struct ThermalCtx {
+    bool on = false;
+    double k = 0, cv = 1, alpha = 0, Tr = 0;
+    double* T = nullptr;            // nodal temperature, updated in place by oracle_wc_step
+    const uint8_t* tMask = nullptr;
+    const double* tVal = nullptr;
+};
+ThermalCtx g_thermal;
+
+template <int DIM>
+void wcHeat(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const uint8_t* flags, const double* rho,
+            double dt) {
+    constexpr int NPE = DIM + 1;
+    const ThermalCtx& C = g_thermal;
+    MB<DIM> mb;
+    std::vector<double> Mdiag((size_t)nElm * NPE), FTot((size_t)nElm * NPE);
+#pragma omp parallel for default(shared)
+    for (int64_t elm = 0; elm < nElm; ++elm) {
+        const int64_t* en = conn + elm * NPE;
+        Geo<DIM> G;
+        computeGeo<DIM>(x, nNodes, en, G);
+        double Te[NPE], Re[NPE];
+        for (int k = 0; k < NPE; ++k) {
+            Te[k] = C.T[en[k]];
+            Re[k] = rho[en[k]];
+        }
+        double g[DIM][NPE];
+        MB<DIM>::gradN(G, g);
+        double Me[NPE][NPE], Le[NPE][NPE];
+        mb.getM(G, [&](const double* N) { return C.cv * dotN<DIM>(N, Re); }, Me);
+        for (int i = 0; i < NPE; ++i)  // lump, MB.hpp:104-118
+            for (int j = 0; j < NPE; ++j)
+                if (i != j) {
+                    Me[i][i] += Me[i][j];
+                    Me[i][j] = 0;
+                }
+        mb.getL(G, g, [&](const double*) { return C.k; }, Le);
+        for (int i = 0; i < NPE; ++i) {
+            double lt = 0, mt = 0;
+            for (int j = 0; j < NPE; ++j) lt += ((-dt) * Le[i][j]) * Te[j];
+            for (int j = 0; j < NPE; ++j) mt += Me[i][j] * Te[j];
+            FTot[elm * NPE + i] = lt + mt;
+            Mdiag[elm * NPE + i] = Me[i][i];
+        }
+    }
+    std::vector<double> invM((size_t)nNodes, 0.0), F((size_t)nNodes, 0.0);
+    for (int64_t elm = 0; elm < nElm; ++elm)
+        for (int i = 0; i < NPE; ++i) {
+            invM[conn[elm * NPE + i]] += Mdiag[elm * NPE + i];
+            F[conn[elm * NPE + i]] += FTot[elm * NPE + i];
+        }
+    for (auto& m : invM) m = 1 / m;
+    for (int64_t n = 0; n < nNodes; ++n) {
+        const bool free_ = flags[n] & F_FREE, tbc = C.tMask && C.tMask[n];
+        if (free_ && !tbc) {
+            F[n] = C.T[n];
+            invM[n] = 1;
+        } else if (tbc) {
+            F[n] = C.tVal[n];
+            invM[n] = 1;
+        }
+    }
+    for (int64_t n = 0; n < nNodes; ++n) C.T[n] = invM[n] * F[n];
+}
+
 template <int DIM>
 void wcMom(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const uint8_t* flags,
            const uint8_t* dirMask, const double* dirVal, double* v /*in: v_half, out: v*/, double* acc, const double* p,
@@ -904,7 +977,15 @@ void wcMom(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, c
         double K[ND][ND], D[NPE][ND], F[ND];
         mb.getK(G, B, [&](const double*) { return P.mu; }, K);
         mb.getD(G, B, [](const double*) { return 1.0; }, D);
-        mb.getF(G, P.bodyForce, [&](const double* N) { return dotN<DIM>(N, Re); }, F);
+        if (g_thermal.on) {  // MomEquation.inl:105-112
+            double Te[NPE];
+            for (int k = 0; k < NPE; ++k) Te[k] = g_thermal.T[en[k]];
+            mb.getF(G, P.bodyForce, [&](const double* N) {
+                const double r = dotN<DIM>(N, Re), T = dotN<DIM>(N, Te);
+                return r * (1 - g_thermal.alpha * (T - g_thermal.Tr));
+            }, F);
+        } else
+            mb.getF(G, P.bodyForce, [&](const double* N) { return dotN<DIM>(N, Re); }, F);
         for (int r = 0; r < ND; ++r) {
             double kv = 0;
             for (int c = 0; c < ND; ++c) kv += (-K[r][c]) * V[c];
@@ -995,7 +1076,8 @@ double wcNextDt(int64_t nNodes, int64_t nElm, const int64_t* conn, const double*
             const double c2 = (P.K0 + P.K0p * p[nd]) / rho[nd];
             double u2 = 0;
             for (int d = 0; d < DIM; ++d) u2 += v[nd + (int64_t)d * nNodes] * v[nd + (int64_t)d * nNodes];
-            const double alpha = P.mu / rho[nd];
+            double alpha = P.mu / rho[nd];
+            if (g_thermal.on) alpha = std::max(alpha, g_thermal.k / (g_thermal.cv * rho[nd]));  // Solver.cpp:214-216
             mx = std::max(std::max(u2, c2), mx);
             mx = std::max(mx, 4 * alpha * alpha / (he * he));
         }
@@ -1088,6 +1170,13 @@ void oracle_set_facets(int dim, int64_t nF, const int64_t* facets, double gamma)
     g_facets.facets.assign(facets, facets + (nF > 0 ? nF * (dim + 2) : 0));
     g_facets.gamma = (nF > 0) ? gamma : 0.0;
 }
+// BoussinesqWC: thermal constants and nodal arrays used by the next oracle_wc_step / oracle_wc_next_dt calls (on = 0: off).
+// T is updated in place by oracle_wc_step; the caller keeps the arrays alive.
+void oracle_set_thermal(int on, double k, double cv, double alpha, double Tr, double* T, const uint8_t* tMask, const double* tVal) {
+    g_thermal.on = on != 0;
+    g_thermal.k = k, g_thermal.cv = cv, g_thermal.alpha = alpha, g_thermal.Tr = Tr;
+    g_thermal.T = T, g_thermal.tMask = tMask, g_thermal.tVal = tVal;
+}
 int64_t oracle_csc_nnz(void* h) { return (int64_t) static_cast<CscHandle*>(h)->val.size(); }
 void oracle_csc_copy(void* h, int64_t* colPtr, int32_t* rowIdx, double* val) {
     auto* H = static_cast<CscHandle*>(h);
@@ -1126,6 +1215,12 @@ int oracle_wc_step(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, d
         delta[i] = v[i] * dt;
     }
     movePositions(dim, nNodes, flags, delta.data(), x, x);
+    if (g_thermal.on) {  // m_solveBoussinesqWC: the heat equation comes first, on the moved mesh with the old rho (Solver.cpp:301-303)
+        if (dim == 2)
+            wcHeat<2>(nNodes, nElm, conn, x, flags, rho, dt);
+        else
+            wcHeat<3>(nNodes, nElm, conn, x, flags, rho, dt);
+    }
     if (dim == 2) {
         if (P.eqType == 0)
             wcCont<2>(nNodes, nElm, conn, x, flags, v, p, rho, P, dt);

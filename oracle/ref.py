@@ -83,6 +83,7 @@ def lib():
         L.pfem_ref_set_direct_solver.argtypes = [C.c_void_p]
         L.pfem_ref_direct_solves.restype = C.c_long
         L.pfem_ref_set_threads.argtypes = [C.c_int]
+        L.pfem_ref_set_thermal_bc.argtypes = [I64, BP, DP]
         L.pfem_ref_get_threads.restype = C.c_int
         L.pfem_ref_cg_log.restype = C.c_long
         L.pfem_ref_cg_log.argtypes = [DP, C.c_long]
@@ -130,7 +131,7 @@ def use_scipy_direct_solver(enable: bool = True) -> None:
 class RefCase:
     """One reference Problem/Mesh/Solver/Equation set built from arrays (see refbuild/ref_driver.cpp)."""
 
-    def __init__(self, mesh, kind: str, params, *, solver_id=None, facets=None, gamma=0.0):
+    def __init__(self, mesh, kind: str, params, *, solver_id=None, facets=None, gamma=0.0, thermal=None):
         L = lib()
         self.mesh, self.kind = mesh, kind
         self.dim, self.N, self.E = mesh.dim, mesh.n_nodes, mesh.n_elems
@@ -148,6 +149,13 @@ class RefCase:
             sid = (solver_id or {0: "CDS_dpdt", 1: "CDS_drhodt", 2: "CDS_rho"}[int(eq_type)]).encode()
             prob = b"WCompNewtonNoT"
             self.n_states = 2 * self.dim + 2
+            if thermal is not None:   # BoussinesqWC: dict(k, cv, alpha, Tr, t_mask, t_val); the state vector gains T
+                prob = b"BoussinesqWC"
+                self.n_states = 2 * self.dim + 3
+                p = np.concatenate([p, [thermal["k"], thermal["cv"], thermal["alpha"], thermal["Tr"]]])
+                tm = np.ascontiguousarray(thermal["t_mask"], dtype=np.uint8)
+                tv = np.ascontiguousarray(thermal["t_val"], dtype=np.float64)
+                L.pfem_ref_set_thermal_bc(self.N, tm.ctypes.data_as(BP), _d(tv))
         else:
             raise ValueError(kind)
         fac = np.zeros((0, self.dim + 2), dtype=np.int64) if facets is None else np.ascontiguousarray(facets, dtype=np.int64)

@@ -69,6 +69,8 @@ struct RefCase {
     std::vector<std::uint8_t> flags, dirMask;
     std::vector<std::int32_t> tags;
     std::vector<double> dirVal;
+    std::vector<std::uint8_t> tMask;  // BoussinesqWC: node has a "<type>T" boundary condition
+    std::vector<double> tVal;
     sol::table root;
     std::unique_ptr<Problem> problem;
     Mesh* mesh = nullptr;
@@ -176,13 +178,21 @@ template <unsigned short dim> int elementMatrices(RefCase& rc, double* M, double
 }
 
 thread_local std::string g_lastError;
-int g_threads = 1;  // Problem::m_nThreads of the next case = number of "Lua states" = OpenMP threads (Problem.cpp:30-45)
+int g_threads = 1;
+// temperature Dirichlet data of the next BoussinesqWC case (pfem_ref_set_thermal_bc)
+std::vector<std::uint8_t> g_tMask;
+std::vector<double> g_tVal;  // Problem::m_nThreads of the next case = number of "Lua states" = OpenMP threads (Problem.cpp:30-45)
 
 }  // namespace
 
 extern "C" {
 
 const char* pfem_ref_last_error() { return g_lastError.c_str(); }
+// BoussinesqWC: per-node temperature Dirichlet mask / values consumed by the next pfem_ref_create (n = 0 clears)
+void pfem_ref_set_thermal_bc(std::int64_t n, const std::uint8_t* tMask, const double* tVal) {
+    g_tMask.assign(tMask, tMask + (n > 0 ? n : 0));
+    g_tVal.assign(tVal, tVal + (n > 0 ? n : 0));
+}
 void pfem_ref_set_threads(int n) { g_threads = n > 0 ? n : omp_get_num_procs(); }
 int pfem_ref_get_threads() { return g_threads; }
 
@@ -201,7 +211,8 @@ long pfem_ref_cg_log(double* out, long maxRows) {
 }
 
 // params: IncompNewtonNoT/PSPG|FracStep -> [rho, mu, dt, bx, by, bz, gamma, maxIter, minRes, gammaFS, residual (0 Ax_f, 1 U, 2 U_P)]
-//         WCompNewtonNoT/CDS_* -> [mu, K0, K0p, rhoStar, bx, by, bz, meduri, gamma, initialDT, maxDT, securityCoeff]
+//         WCompNewtonNoT|BoussinesqWC/CDS_* -> [mu, K0, K0p, rhoStar, bx, by, bz, meduri, gamma, initialDT, maxDT, securityCoeff,
+//                                               k, cv, alpha, Tr]   (the last four for BoussinesqWC only)
 // facets: nFacets x (dim+2) = facet nodes, out node, element index (may be null / 0)
 void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const std::int64_t* conn, const double* x,
                       const std::uint8_t* flags, const std::uint8_t* dirMask, const double* dirVal,
@@ -222,21 +233,33 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
         rc->dirVal.assign(dirVal, dirVal + dim * nNodes);
         if (nFacets > 0) rc->facets.assign(facets, facets + nFacets * (dim + 2));
         rc->tags.resize(rc->N);
-        for (std::size_t n = 0; n < rc->N; ++n) rc->tags[n] = (flags[n] & 1) ? (dirMask[n] ? 1 : 2) : 0;
+        const bool boussinesqWC = rc->problemId == "BoussinesqWC";
+        if (boussinesqWC && g_tMask.size() == rc->N) {
+            rc->tMask = g_tMask;
+            rc->tVal = g_tVal;
+        } else {
+            rc->tMask.assign(rc->N, 0);
+            rc->tVal.assign(rc->N, 0.0);
+        }
+        // tags of bound nodes by the boundary conditions they carry: Dir (velocity), BT (temperature), BVT (both), Wall (none)
+        for (std::size_t n = 0; n < rc->N; ++n) {
+            const bool vbc = dirMask[n] != 0, tbc = rc->tMask[n] != 0;
+            rc->tags[n] = (flags[n] & 1) ? (vbc ? (tbc ? 4 : 1) : (tbc ? 3 : 2)) : 0;
+        }
 
-        const bool wc = rc->problemId == "WCompNewtonNoT";
+        const bool wc = rc->problemId == "WCompNewtonNoT" || boussinesqWC;
         refinject::MeshArrays& in = refinject::current();
         in = refinject::MeshArrays();
         in.dim = dim;
         in.nNodes = rc->N;
         in.nElems = rc->E;
         in.nFacets = static_cast<std::size_t>(nFacets > 0 ? nFacets : 0);
-        in.nStates = wc ? 2 * dim + 2 : dim + 1;  // WC/Problem.cpp:17-18, IN/Problem.cpp:13-14
+        in.nStates = boussinesqWC ? 2 * dim + 3 : (wc ? 2 * dim + 2 : dim + 1);  // WC/Problem.cpp:17-18, 130-131; IN/Problem.cpp:13-14
         in.conn = rc->conn.data();
         in.x = rc->x.data();
         in.flags = rc->flags.data();
         in.tags = rc->tags.data();
-        in.tagNames = {"Fluid", "Dir", "Wall"};
+        in.tagNames = {"Fluid", "Dir", "Wall", "BT", "BVT"};
         in.facets = rc->facets.empty() ? nullptr : rc->facets.data();
 
         rc->problem.reset(new Problem(rc->problemId));
@@ -257,8 +280,13 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
             for (int d = 0; d < self->dim; ++d) g[d] = self->dirVal[n + d * self->N];
             return g;
         };
+        sol::function dirT = [self](const sol::Args& a) -> std::any {
+            const auto pos = std::any_cast<std::array<double, 3>>(a.at(1));
+            return std::vector<double>{self->tVal[self->nodeAt(pos)]};
+        };
         sol::table material, solverT, bc;
         bc.set_function("DirV", dirV);
+        bc.set_function("BVTV", dirV);
         if (!wc) {
             material.set("rho", p[0]);
             material.set("mu", p[1]);
@@ -295,6 +323,21 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
             solverT.set("securityCoeff", p[11]);
             solverT.set("ContEq", contT);
             solverT.set("MomEq", momT);
+            if (boussinesqWC) {  // examples/2D/thermalConv/thermalConvComp.lua layout
+                material.set("k", p[12]);
+                material.set("cv", p[13]);
+                material.set("alpha", p[14]);
+                material.set("Tr", p[15]);
+                material.set("DgammaDT", 0.0);
+                material.set("h", 0.0);
+                material.set("Tinf", 0.0);
+                material.set("epsRad", 0.0);
+                sol::table heatT, heatBC;
+                heatBC.set_function("BTT", dirT);
+                heatBC.set_function("BVTT", dirT);
+                heatT.set("BC", heatBC);
+                solverT.set("HeatEq", heatT);
+            }
         }
         rc->root.set("Solver", solverT);
         rc->root.set("Material", material);
@@ -454,7 +497,7 @@ int pfem_ref_wc_step(void* h, double dt) {
         auto* s = dynamic_cast<SolverWCompNewton*>(rc.solver);
         if (!s) return -1;
         s->m_timeStep = dt;
-        return s->m_solveWCompNewtonNoT() ? 1 : 0;
+        return s->solveOneTimeStep() ? 1 : 0;  // m_solveFunc: m_solveWCompNewtonNoT or m_solveBoussinesqWC
     } catch (const std::exception& e) {
         g_lastError = e.what();
         return -1;

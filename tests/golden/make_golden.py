@@ -86,6 +86,38 @@ def wc_fixture(name, mesh, st, eq, meduri, n_steps=3, max_dt=1e-3, facets=None, 
          dts=np.array(dts), states=np.array(states), xs=np.array(xs), **extra)
 
 
+def boussinesq_fixtures():
+    """BoussinesqWC (SURVEY 8f rank 3): SolverWCompNewton::m_solveBoussinesqWC = explicit heat equation, continuity,
+    momentum with the buoyancy factor, CFL with the thermal diffusivity; temperature Dirichlet data on two walls.
+    Conductivity and expansion coefficient are exaggerated so that three steps show them."""
+    W = mg.WC_PARAMS
+    for dim, n in ((2, 8), (3, 4)):
+        mesh = mg.kuhn_box(dim, n, free_fraction=0.02, permute=True)
+        nn = mesh.n_nodes
+        st = mg.wc_state(mesh)
+        st["acc"] = 0.3 * np.random.default_rng(3).standard_normal(st["acc"].shape)
+        c = mesh.coords()
+        T0 = 300.0 + 10.0 * c[:, 0] + 2.0 * np.random.default_rng(5).standard_normal(nn)
+        bound = (mesh.flags & mg.F_BOUND) != 0
+        t_mask = (bound & ((np.abs(c[:, 0]) < 1e-12) | (np.abs(c[:, 0] - 1.0) < 1e-12))).astype(np.uint8)
+        t_val = np.where(c[:, 0] < 0.5, 310.0, 290.0)
+        th = dict(k=6.0e3, cv=4.186, alpha=6.9e-3, Tr=300.0, t_mask=t_mask, t_val=t_val)
+        wpar = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], mg.gravity(dim), True, "CDS_dpdt")
+        q0 = np.concatenate([st["v"], st["p"], st["rho"], st["acc"], T0])
+        dts, states, xs = [], [], []
+        with ref.RefCase(mesh, "wc", np.concatenate([wpar, [1e-6, 1e-3, W["securityCoeff"]]]), thermal=th) as rc:
+            rc.set_states(q0)
+            for _ in range(3):
+                dt = rc.wc_next_dt()
+                assert rc.wc_step(dt)
+                dts.append(dt)
+                states.append(rc.get_states())
+                xs.append(rc.positions())
+        save(f"wcb_{dim}d_boussinesq", **mesh_arrays(mesh), q0=q0, wpar=wpar, security_coeff=np.float64(W["securityCoeff"]),
+             max_dt=np.float64(1e-3), dts=np.array(dts), states=np.array(states), xs=np.array(xs),
+             thermal=np.array([th["k"], th["cv"], th["alpha"], th["Tr"]]), t_mask=t_mask, t_val=t_val)
+
+
 def tables_fixture():
     mesh = mg.kuhn_box(3, 2)
     par = orc.pspg_param_array(1000.0, 1e-3, 1e-3, mg.gravity(3))
@@ -124,6 +156,7 @@ def main():
                 st["acc"] = 0.5 * np.random.default_rng(4).standard_normal(st["acc"].shape)
                 wc_fixture(f"wc_{dim}d_{eq}_{'meduri' if meduri else 'none'}", mesh, st, eq, meduri)
     fst_fixtures()
+    boussinesq_fixtures()
 
 
 def fst_fixtures():

@@ -109,6 +109,39 @@ def test_wc_oracle_matches_reference_fixture(name):
         assert rel_err(st1["acc"], split_wc(z["states"][0], dim, nn)["acc"]) > 1e-7
 
 
+@pytest.mark.parametrize("name", golden_names("wcb_"))
+def test_boussinesq_wc_oracle_matches_reference_fixture(name):
+    """BoussinesqWC: HeatEqWCompNewton (explicit, lumped), buoyancy factor in the momentum body force, thermal diffusivity
+    in computeNextDT, order heat -> continuity -> momentum of m_solveBoussinesqWC (WC/Solver.cpp:278-320).  Oracle level
+    only so far: the CUDA path for this row is the next round's work."""
+    mesh, z = load_golden(name)
+    dim, nn = mesh.dim, mesh.n_nodes
+    k, cv, alpha, Tr = z["thermal"]
+    th = dict(k=k, cv=cv, alpha=alpha, Tr=Tr, t_mask=np.ascontiguousarray(z["t_mask"]), t_val=np.ascontiguousarray(z["t_val"]))
+    q0 = z["q0"]
+    st = {kk: np.ascontiguousarray(v) for kk, v in split_wc(q0[: (2 * dim + 2) * nn], dim, nn).items()}
+    st["T"] = np.ascontiguousarray(q0[(2 * dim + 2) * nn:])
+    x = mesh.x
+    for step in range(z["dts"].shape[0]):
+        dt = orc.wc_next_dt(mesh, x, st, z["wpar"], float(z["security_coeff"]), float(z["max_dt"]), thermal=th)
+        assert abs(dt - z["dts"][step]) <= 1e-13 * z["dts"][step]
+        x, st = orc.wc_step(mesh, x, st, z["wpar"], float(z["dts"][step]), thermal=th)
+        q = z["states"][step]
+        want = split_wc(q[: (2 * dim + 2) * nn], dim, nn)
+        for kk in ("v", "p", "rho", "acc"):
+            assert rel_err(st[kk], want[kk]) < TOL * 10 ** step, (kk, step)
+        assert rel_err(st["T"], q[(2 * dim + 2) * nn:]) < TOL
+        assert np.abs(x - z["xs"][step]).max() < 1e-13
+    # the fixture exercises both couplings: conduction changes interior temperatures, buoyancy changes the acceleration
+    st0 = {kk: np.ascontiguousarray(v) for kk, v in split_wc(q0[: (2 * dim + 2) * nn], dim, nn).items()}
+    st0["T"] = np.ascontiguousarray(q0[(2 * dim + 2) * nn:])
+    _, s_nob = orc.wc_step(mesh, mesh.x, st0, z["wpar"], float(z["dts"][0]), thermal=dict(th, alpha=0.0))
+    _, s_b = orc.wc_step(mesh, mesh.x, st0, z["wpar"], float(z["dts"][0]), thermal=th)
+    assert rel_err(s_nob["acc"], s_b["acc"]) > 1e-3
+    interior = (z["t_mask"] == 0) & ((mesh.flags & mg.F_FREE) == 0)
+    assert np.abs(s_b["T"][interior] - st0["T"][interior]).max() > 1e-3
+
+
 # ---- live comparisons (development container only: needs oracle/_ref/libpfem_ref.so) ----------------------------------
 needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
 
