@@ -41,6 +41,7 @@ def lib():
         L.oracle_pspg_build.restype = C.c_void_p
         L.oracle_pspg_build.argtypes = [C.c_int, i64, i64, ip, dp, dp, dp, bp, dp, C.c_int, bp, dp, dp, dp]
         L.oracle_set_facets.argtypes = [C.c_int, i64, ip, C.c_double]
+        L.oracle_set_bingham.argtypes = [C.c_int, C.c_double, C.c_double]
         L.oracle_set_thermal.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, bp, dp]
         L.oracle_csc_nnz.restype = i64
         L.oracle_csc_nnz.argtypes = [C.c_void_p]
@@ -101,6 +102,14 @@ def set_facets(dim, facets=None, gamma=0.0):
         return
     f = np.ascontiguousarray(facets, dtype=np.int64)
     lib().oracle_set_facets(dim, f.shape[0], _i(f), float(gamma))
+
+
+def set_bingham(tau0=None, m_reg=0.0):
+    """Bingham regularised viscosity (MomContEquation.inl:102-119) for the following pspg_* calls; set_bingham() = off."""
+    if tau0 is None:
+        lib().oracle_set_bingham(0, 0.0, 0.0)
+    else:
+        lib().oracle_set_bingham(1, float(tau0), float(m_reg))
 
 
 def pspg_elements(mesh, vcur, q_prev, params):

@@ -397,6 +397,14 @@ double tauPSPG(const Geo<DIM>& G, const int64_t* en, const double* vcur, int64_t
 // 73-93 (ddev, m), :97-100 (M: rho), :123-128 (K: mu), :131-135 (D: 1), :139-149 (C: 1,
 // L: 1/rho), :203-207 (F: rho), :218-222 (H: 1).
 // ------------------------------------------------------------------------------------
+// Bingham regularised viscosity (Problem id "Bingham"): the K factor of MomContEquation.inl:102-119,
+// mu + tau0 (1 - exp(-mReg gammaDot))/gammaDot with gammaDot = sqrt(V^T B^T ddev B V) of the element's CURRENT velocities.
+struct BinghamCtx {
+    bool on = false;
+    double tau0 = 0, mReg = 0;
+};
+BinghamCtx g_bingham;
+
 template <int DIM>
 void pspgElement(const MB<DIM>& mb, const double* x, const double* vcur, const double* qPrev, int64_t nNodes,
                  const int64_t* en, const PspgParams& P, double* Ae /*[(DIM+1)*NPE]^2 row-major*/, double* be,
@@ -413,7 +421,39 @@ void pspgElement(const MB<DIM>& mb, const double* x, const double* vcur, const d
     mb.getM(G, [&](const double*) { return P.rho; }, M);
     for (int i = 0; i < NPE; ++i)
         for (int j = 0; j < NPE; ++j) M[i][j] = (1 / P.dt) * M[i][j];
-    mb.getK(G, B, [&](const double*) { return P.mu; }, K);
+    if (g_bingham.on) {
+        double V[ND];
+        for (int d = 0; d < DIM; ++d)
+            for (int k = 0; k < NPE; ++k) V[d * NPE + k] = vcur[en[k] + (int64_t)d * nNodes];
+        mb.getK(G, B, [&](const double*) {
+            double t1[NS], t2[NS], t3[ND];  // ((V^T B^T) ddev) B, left to right
+            for (int k = 0; k < NS; ++k) {
+                double a = 0;
+                for (int r = 0; r < ND; ++r) a += V[r] * B[k][r];
+                t1[k] = a;
+            }
+            for (int c = 0; c < NS; ++c) {
+                double a = 0;
+                for (int k = 0; k < NS; ++k) a += t1[k] * mb.ddev[k][c];
+                t2[c] = a;
+            }
+            for (int c = 0; c < ND; ++c) {
+                double a = 0;
+                for (int k = 0; k < NS; ++k) a += t2[k] * B[k][c];
+                t3[c] = a;
+            }
+            double gd2 = 0;
+            for (int r = 0; r < ND; ++r) gd2 += t3[r] * V[r];
+            const double gammaDot = std::sqrt(gd2);
+            double muEq = g_bingham.tau0;
+            if (gammaDot < 1e-15)
+                muEq *= g_bingham.mReg;
+            else
+                muEq *= (1 - std::exp(-g_bingham.mReg * gammaDot)) / gammaDot;
+            return P.mu + muEq;
+        }, K);
+    } else
+        mb.getK(G, B, [&](const double*) { return P.mu; }, K);
     mb.getD(G, B, [&](const double*) { return 1.0; }, D);
     mb.getC(G, g, [&](const double*) { return 1.0; }, C);
     for (int i = 0; i < NPE; ++i)
@@ -1169,6 +1209,11 @@ void oracle_set_facets(int dim, int64_t nF, const int64_t* facets, double gamma)
     g_facets.nF = nF;
     g_facets.facets.assign(facets, facets + (nF > 0 ? nF * (dim + 2) : 0));
     g_facets.gamma = (nF > 0) ? gamma : 0.0;
+}
+// Bingham viscosity for the following oracle_pspg_elements / oracle_pspg_build calls (on = 0: Newtonian, the default)
+void oracle_set_bingham(int on, double tau0, double mReg) {
+    g_bingham.on = on != 0;
+    g_bingham.tau0 = tau0, g_bingham.mReg = mReg;
 }
 // BoussinesqWC: thermal constants and nodal arrays used by the next oracle_wc_step / oracle_wc_next_dt calls (on = 0: off).
 // T is updated in place by oracle_wc_step; the caller keeps the arrays alive.

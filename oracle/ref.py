@@ -131,7 +131,7 @@ def use_scipy_direct_solver(enable: bool = True) -> None:
 class RefCase:
     """One reference Problem/Mesh/Solver/Equation set built from arrays (see refbuild/ref_driver.cpp)."""
 
-    def __init__(self, mesh, kind: str, params, *, solver_id=None, facets=None, gamma=0.0, thermal=None):
+    def __init__(self, mesh, kind: str, params, *, solver_id=None, facets=None, gamma=0.0, thermal=None, bingham=None):
         L = lib()
         self.mesh, self.kind = mesh, kind
         self.dim, self.N, self.E = mesh.dim, mesh.n_nodes, mesh.n_elems
@@ -141,6 +141,9 @@ class RefCase:
             gamma_fs, residual = (params[8], params[9]) if len(params) >= 10 else (1.0, 0.0)
             p = np.array([rho, mu, dt, bx, by, bz, gamma, max_iter, min_res, gamma_fs, residual], dtype=np.float64)
             prob, sid = b"IncompNewtonNoT", (solver_id or "PSPG").encode()
+            if bingham is not None:   # (tau0, mReg): Problem id "Bingham"
+                prob = b"Bingham"
+                p = np.concatenate([p, [bingham[0], bingham[1]]])
             self.n_states = self.dim + 1
         elif kind == "wc":      # params = oracle.wc_param_array + (initial_dt, max_dt, security_coeff)
             mu, K0, K0p, rho_star, bx, by, bz, meduri, eq_type = params[:9]

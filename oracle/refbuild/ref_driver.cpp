@@ -210,7 +210,8 @@ long pfem_ref_cg_log(double* out, long maxRows) {
     return k;
 }
 
-// params: IncompNewtonNoT/PSPG|FracStep -> [rho, mu, dt, bx, by, bz, gamma, maxIter, minRes, gammaFS, residual (0 Ax_f, 1 U, 2 U_P)]
+// params: IncompNewtonNoT|Bingham / PSPG|FracStep -> [rho, mu, dt, bx, by, bz, gamma, maxIter, minRes, gammaFS,
+//                                                       residual (0 Ax_f, 1 U, 2 U_P), tau0, mReg]   (the last two for Bingham)
 //         WCompNewtonNoT|BoussinesqWC/CDS_* -> [mu, K0, K0p, rhoStar, bx, by, bz, meduri, gamma, initialDT, maxDT, securityCoeff,
 //                                               k, cv, alpha, Tr]   (the last four for BoussinesqWC only)
 // facets: nFacets x (dim+2) = facet nodes, out node, element index (may be null / 0)
@@ -291,6 +292,10 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
             material.set("rho", p[0]);
             material.set("mu", p[1]);
             material.set("gamma", p[6]);
+            if (rc->problemId == "Bingham") {
+                material.set("tau0", p[11]);
+                material.set("mReg", p[12]);
+            }
             sol::table eqT;
             eqT.set("maxIter", p[7]);
             eqT.set("minRes", p[8]);

@@ -118,6 +118,19 @@ def boussinesq_fixtures():
              thermal=np.array([th["k"], th["cv"], th["alpha"], th["Tr"]]), t_mask=t_mask, t_val=t_val)
 
 
+def bingham_fixtures():
+    """Problem id "Bingham": shear-rate dependent K factor of MomContEquation.inl:102-119 (regularised yield stress)."""
+    tau0, m_reg = 50.0, 100.0
+    for dim, n in ((2, 6), (3, 4)):
+        mesh, q, q_prev, par = H.pspg_case(dim, n, free_fraction=0.02, permute=True)
+        with ref.RefCase(mesh, "pspg", par, bingham=(tau0, m_reg)) as rc:
+            rc.set_states(q)
+            Ae, be, tau = rc.pspg_elements(q_prev)
+            A1, b1 = rc.pspg_build(q_prev, True)
+        save(f"pspgb_{dim}d_bingham", **mesh_arrays(mesh), q=q, q_prev=q_prev, par=par, bingham=np.array([tau0, m_reg]), tau=tau,
+             indptr=A1.indptr.astype(np.int64), indices=A1.indices.astype(np.int32), A=A1.data, b=b1)
+
+
 def tables_fixture():
     mesh = mg.kuhn_box(3, 2)
     par = orc.pspg_param_array(1000.0, 1e-3, 1e-3, mg.gravity(3))
@@ -157,6 +170,7 @@ def main():
                 wc_fixture(f"wc_{dim}d_{eq}_{'meduri' if meduri else 'none'}", mesh, st, eq, meduri)
     fst_fixtures()
     boussinesq_fixtures()
+    bingham_fixtures()
 
 
 def fst_fixtures():

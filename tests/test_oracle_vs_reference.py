@@ -142,6 +142,24 @@ def test_boussinesq_wc_oracle_matches_reference_fixture(name):
     assert np.abs(s_b["T"][interior] - st0["T"][interior]).max() > 1e-3
 
 
+@pytest.mark.parametrize("name", golden_names("pspgb_"))
+def test_bingham_oracle_matches_reference_fixture(name):
+    """Problem id "Bingham" (MomContEquation.inl:102-119): oracle level only so far, CUDA path next round."""
+    mesh, z = load_golden(name)
+    dim, nn = mesh.dim, mesh.n_nodes
+    vcur = z["q"][: dim * nn].copy()
+    orc.set_bingham(*z["bingham"])
+    try:
+        A, b = orc.pspg_build(mesh, vcur, z["q_prev"], z["par"], True)
+    finally:
+        orc.set_bingham()
+    A_ref = golden_csc(z, "A")
+    assert max(block_errors(A, A_ref, nn, dim).values()) < TOL
+    assert max(vec_block_errors(b, z["b"], nn, dim).values()) < TOL
+    A0, _ = orc.pspg_build(mesh, vcur, z["q_prev"], z["par"], True)       # Newtonian: the vv blocks must differ visibly
+    assert block_errors(A0, A_ref, nn, dim)["vv"] > 1e-3
+
+
 # ---- live comparisons (development container only: needs oracle/_ref/libpfem_ref.so) ----------------------------------
 needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
 
