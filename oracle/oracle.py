@@ -41,6 +41,9 @@ def lib():
         L.oracle_pspg_build.restype = C.c_void_p
         L.oracle_pspg_build.argtypes = [C.c_int, i64, i64, ip, dp, dp, dp, bp, dp, C.c_int, bp, dp, dp, dp]
         L.oracle_set_facets.argtypes = [C.c_int, i64, ip, C.c_double]
+        L.oracle_set_pspg_thermal.argtypes = [C.c_int, C.c_double, C.c_double, dp]
+        L.oracle_in_heat_build.restype = C.c_void_p
+        L.oracle_in_heat_build.argtypes = [C.c_int, i64, i64, ip, dp, bp, bp, dp, dp, dp, C.c_int, dp]
         L.oracle_set_bingham.argtypes = [C.c_int, C.c_double, C.c_double]
         L.oracle_set_thermal.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, dp, bp, dp]
         L.oracle_csc_nnz.restype = i64
@@ -102,6 +105,38 @@ def set_facets(dim, facets=None, gamma=0.0):
         return
     f = np.ascontiguousarray(facets, dtype=np.int64)
     lib().oracle_set_facets(dim, f.shape[0], _i(f), float(gamma))
+
+
+_pspg_thermal_T = None   # keeps the array alive while the context points at it
+
+
+def set_pspg_thermal(alpha=None, Tr=0.0, T=None):
+    """Incompressible Boussinesq buoyancy factors (MomContEquation.inl:166-199) for the following pspg_* calls; () = off."""
+    global _pspg_thermal_T
+    if alpha is None:
+        _pspg_thermal_T = None
+        lib().oracle_set_pspg_thermal(0, 0.0, 0.0, None)
+    else:
+        _pspg_thermal_T = np.ascontiguousarray(T, dtype=np.float64)
+        lib().oracle_set_pspg_thermal(1, float(alpha), float(Tr), _d(_pspg_thermal_T))
+
+
+def in_heat_build(mesh, theta_prev, rho, cv, k, dt, t_mask, t_val, apply_bc=True, x=None):
+    """HeatEqIncompNewton::m_buildAb (+ m_applyBC), IncompNewton/HeatEquation.inl:227-412: (A as CSC, b)."""
+    L = lib()
+    nn = mesh.n_nodes
+    b = np.zeros(nn)
+    x = mesh.x if x is None else x
+    par = np.array([rho, cv, k, dt], dtype=np.float64)
+    h = L.oracle_in_heat_build(mesh.dim, nn, mesh.n_elems, _i(mesh.conn), _d(x), _b(mesh.flags),
+                               _b(np.ascontiguousarray(t_mask, dtype=np.uint8)), _d(np.ascontiguousarray(t_val, dtype=np.float64)),
+                               _d(np.ascontiguousarray(theta_prev, dtype=np.float64)), _d(par), 1 if apply_bc else 0, _d(b))
+    assert h
+    nnz = L.oracle_csc_nnz(h)
+    col_ptr, row_idx, val = np.zeros(nn + 1, dtype=np.int64), np.zeros(nnz, dtype=np.int32), np.zeros(nnz)
+    L.oracle_csc_copy(h, _i(col_ptr), _i32(row_idx), _d(val))
+    L.oracle_csc_free(h)
+    return sp.csc_matrix((val, row_idx, col_ptr), shape=(nn, nn)), b
 
 
 def set_bingham(tau0=None, m_reg=0.0):

@@ -399,6 +399,15 @@ double tauPSPG(const Geo<DIM>& G, const int64_t* en, const double* vcur, int64_t
 // ------------------------------------------------------------------------------------
 // Bingham regularised viscosity (Problem id "Bingham"): the K factor of MomContEquation.inl:102-119,
 // mu + tau0 (1 - exp(-mReg gammaDot))/gammaDot with gammaDot = sqrt(V^T B^T ddev B V) of the element's CURRENT velocities.
+// Incompressible Boussinesq (Problem id "Boussinesq"): F factor rho (1 - alpha (T - Tr)) and H factor (1 - alpha (T - Tr))
+// with T = N . T_e of the CURRENT node states (MomContEquation.inl:166-199), gamma = DgammaDT = 0, no phase change.
+struct PspgThermalCtx {
+    bool on = false;
+    double alpha = 0, Tr = 0;
+    const double* T = nullptr;
+};
+PspgThermalCtx g_pspgThermal;
+
 struct BinghamCtx {
     bool on = false;
     double tau0 = 0, mReg = 0;
@@ -461,8 +470,16 @@ void pspgElement(const MB<DIM>& mb, const double* x, const double* vcur, const d
     mb.getL(G, g, [&](const double*) { return 1 / P.rho; }, L);
     for (int i = 0; i < NPE; ++i)
         for (int j = 0; j < NPE; ++j) L[i][j] = tau * L[i][j];
-    mb.getF(G, P.bodyForce, [&](const double*) { return P.rho; }, F);
-    mb.getH(G, P.bodyForce, g, [&](const double*) { return 1.0; }, H);
+    if (g_pspgThermal.on) {
+        double Te[NPE];
+        for (int k = 0; k < NPE; ++k) Te[k] = g_pspgThermal.T[en[k]];
+        const double al = g_pspgThermal.alpha, Tr = g_pspgThermal.Tr;
+        mb.getF(G, P.bodyForce, [&](const double* N) { return P.rho * (1 - al * (dotN<DIM>(N, Te) - Tr)); }, F);
+        mb.getH(G, P.bodyForce, g, [&](const double* N) { return (1 - al * (dotN<DIM>(N, Te) - Tr)); }, H);
+    } else {
+        mb.getF(G, P.bodyForce, [&](const double*) { return P.rho; }, F);
+        mb.getH(G, P.bodyForce, g, [&](const double*) { return 1.0; }, H);
+    }
     for (int i = 0; i < NPE; ++i) H[i] = tau * H[i];
 
     auto A = [&](int r, int c) -> double& { return Ae[r * NT + c]; };
@@ -566,6 +583,82 @@ void pspgBuild(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* 
     for (const auto& d : indexb) b[d.first] += d.second;
     double t5 = omp_get_wtime();
     if (phaseSec) phaseSec[4] += t5 - t4;  // "Assemble vector"
+}
+
+// ------------------------------------------------------------------------------------
+// HeatEqIncompNewton (IncompNewton/HeatEquation.inl): m_buildAb (:227-319) -- A = M + dt L with f_M = cv rho, f_L = k,
+// rows of nodes with a temperature BC flag or free nodes skipped (identity appended in node order, :300-308), b = M
+// theta_prev through the reference's `indexb[noPerEl*elm + countb]` indexing (a smaller stride than the vector was sized
+// for: the tail keeps default pairs (0, 0.0), harmless) -- and m_applyBC (:321-412) without the flux facet terms:
+// free nodes b = theta_prev, Dirichlet nodes b = g_T with the column elimination keeping explicit zeros.
+// params: [rho, cv, k, dt].  tMask/tVal as in the BoussinesqWC block.
+// ------------------------------------------------------------------------------------
+template <int DIM>
+void inHeatBuild(int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const uint8_t* flags,
+                 const uint8_t* tMask, const double* tVal, const double* thetaPrev, const double* par, int applyBC,
+                 std::vector<int64_t>& colPtr, std::vector<int32_t>& rowIdx, std::vector<double>& val, double* b) {
+    constexpr int NPE = DIM + 1;
+    const double rho = par[0], cv = par[1], k = par[2], dt = par[3];
+    const int64_t tripletPerElm = DIM * NPE * NPE + DIM * NPE * DIM * NPE + 3 * NPE * DIM * NPE + NPE * NPE;  // :230
+    const int64_t doubletPerElm = 2 * DIM * NPE + 2 * NPE;
+    MB<DIM> mb;
+    std::vector<Triplet> indexA(tripletPerElm * nElm, Triplet{0, 0, 0.0});
+    std::vector<std::pair<int64_t, double>> indexb(doubletPerElm * nElm, std::make_pair((int64_t)0, 0.0));
+    for (int64_t i = 0; i < nNodes; ++i) b[i] = 0;
+#pragma omp parallel for default(shared)
+    for (int64_t elm = 0; elm < nElm; ++elm) {
+        const int64_t* en = conn + elm * NPE;
+        Geo<DIM> G;
+        computeGeo<DIM>(x, nNodes, en, G);
+        double g[DIM][NPE];
+        MB<DIM>::gradN(G, g);
+        double Me[NPE][NPE], Le[NPE][NPE];
+        mb.getM(G, [&](const double*) { return cv * rho; }, Me);
+        mb.getL(G, g, [&](const double*) { return k; }, Le);
+        for (int i = 0; i < NPE; ++i)
+            for (int j = 0; j < NPE; ++j) Le[i][j] = dt * Le[i][j];
+        double Mth[NPE];
+        for (int i = 0; i < NPE; ++i) {
+            double a = 0;
+            for (int j = 0; j < NPE; ++j) a += Me[i][j] * thetaPrev[en[j]];
+            Mth[i] = a;
+        }
+        int64_t countA = 0, countb = 0;
+        for (int i = 0; i < NPE; ++i) {
+            const bool free_ = flags[en[i]] & F_FREE, tbc = tMask[en[i]] != 0;
+            for (int j = 0; j < NPE; ++j) {
+                if (!tbc) {
+                    if (!free_) indexA[tripletPerElm * elm + countA] = Triplet{(int32_t)en[i], (int32_t)en[j], Me[i][j]};
+                    countA++;
+                    if (!free_) indexA[tripletPerElm * elm + countA] = Triplet{(int32_t)en[i], (int32_t)en[j], Le[i][j]};
+                    countA++;
+                }
+            }
+            indexb[NPE * elm + countb] = std::make_pair(en[i], Mth[i]);  // the reference's stride (:283)
+            countb++;
+        }
+    }
+    for (int64_t n = 0; n < nNodes; ++n)
+        if (tMask[n] || (flags[n] & F_FREE)) indexA.push_back(Triplet{(int32_t)n, (int32_t)n, 1.0});
+    tripletsToCSC(nNodes, indexA, colPtr, rowIdx, val);
+    for (const auto& d : indexb) b[d.first] += d.second;
+    if (!applyBC) return;
+    for (int64_t n = 0; n < nNodes; ++n) {
+        const bool free_ = flags[n] & F_FREE, tbc = tMask[n] != 0;
+        if (free_ && !tbc) {
+            b[n] = thetaPrev[n];
+        } else if (tbc) {
+            const double r = tVal[n];
+            b[n] = r;
+            for (int64_t kk = colPtr[n]; kk < colPtr[n + 1]; ++kk) {
+                const int64_t row = rowIdx[kk];
+                if (row == n) continue;
+                const double v = val[kk];
+                b[row] -= v * r;
+                val[kk] = 0;
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------
@@ -1209,6 +1302,26 @@ void oracle_set_facets(int dim, int64_t nF, const int64_t* facets, double gamma)
     g_facets.nF = nF;
     g_facets.facets.assign(facets, facets + (nF > 0 ? nF * (dim + 2) : 0));
     g_facets.gamma = (nF > 0) ? gamma : 0.0;
+}
+// Incompressible Boussinesq: buoyancy factors for the following oracle_pspg_* calls (on = 0: off); T = current node temperatures
+void oracle_set_pspg_thermal(int on, double alpha, double Tr, const double* T) {
+    g_pspgThermal.on = on != 0;
+    g_pspgThermal.alpha = alpha, g_pspgThermal.Tr = Tr, g_pspgThermal.T = T;
+}
+// HeatEqIncompNewton::m_buildAb (+ m_applyBC): scalar system of nNodes unknowns; returns a CSC handle like oracle_pspg_build
+void* oracle_in_heat_build(int dim, int64_t nNodes, int64_t nElm, const int64_t* conn, const double* x, const uint8_t* flags,
+                           const uint8_t* tMask, const double* tVal, const double* thetaPrev, const double* params, int applyBC,
+                           double* b) {
+    auto* H = new CscHandle;
+    if (dim == 2)
+        inHeatBuild<2>(nNodes, nElm, conn, x, flags, tMask, tVal, thetaPrev, params, applyBC, H->colPtr, H->rowIdx, H->val, b);
+    else if (dim == 3)
+        inHeatBuild<3>(nNodes, nElm, conn, x, flags, tMask, tVal, thetaPrev, params, applyBC, H->colPtr, H->rowIdx, H->val, b);
+    else {
+        delete H;
+        return nullptr;
+    }
+    return H;
 }
 // Bingham viscosity for the following oracle_pspg_elements / oracle_pspg_build calls (on = 0: Newtonian, the default)
 void oracle_set_bingham(int on, double tau0, double mReg) {

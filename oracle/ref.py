@@ -77,6 +77,9 @@ def lib():
         L.pfem_ref_pspg_build.argtypes = [C.c_void_p, DP, C.c_int]
         L.pfem_ref_csc_copy.argtypes = [C.c_void_p, IP, C.POINTER(C.c_int32), DP, DP]
         L.pfem_ref_pspg_solve.argtypes = [C.c_void_p]
+        L.pfem_ref_in_heat_build.restype = I64
+        L.pfem_ref_in_heat_build.argtypes = [C.c_void_p, DP, C.c_int]
+        L.pfem_ref_in_heat_copy.argtypes = [C.c_void_p, IP, C.POINTER(C.c_int32), DP, DP]
         L.pfem_ref_wc_step.argtypes = [C.c_void_p, C.c_double]
         L.pfem_ref_wc_next_dt.restype = C.c_double
         L.pfem_ref_wc_next_dt.argtypes = [C.c_void_p]
@@ -144,6 +147,13 @@ class RefCase:
             if bingham is not None:   # (tau0, mReg): Problem id "Bingham"
                 prob = b"Bingham"
                 p = np.concatenate([p, [bingham[0], bingham[1]]])
+            elif thermal is not None:   # incompressible Boussinesq: dict(alpha, Tr, k, cv, t_mask, t_val); states gain T
+                prob = b"Boussinesq"
+                self.n_states = self.dim + 2
+                p = np.concatenate([p, [thermal["alpha"], thermal["Tr"], thermal["k"], thermal["cv"]]])
+                tm = np.ascontiguousarray(thermal["t_mask"], dtype=np.uint8)
+                tv = np.ascontiguousarray(thermal["t_val"], dtype=np.float64)
+                L.pfem_ref_set_thermal_bc(self.N, tm.ctypes.data_as(BP), _d(tv))
             self.n_states = self.dim + 1
         elif kind == "wc":      # params = oracle.wc_param_array + (initial_dt, max_dt, security_coeff)
             mu, K0, K0p, rho_star, bx, by, bz, meduri, eq_type = params[:9]
@@ -234,6 +244,15 @@ class RefCase:
         val, b = np.zeros(nnz), np.zeros(n_dof)
         lib().pfem_ref_csc_copy(self._h, col_ptr.ctypes.data_as(IP), row_idx.ctypes.data_as(C.POINTER(C.c_int32)), _d(val), _d(b))
         return sp.csc_matrix((val, row_idx, col_ptr), shape=(n_dof, n_dof)), b
+
+    def in_heat_build(self, theta_prev, apply_bc=True):
+        """HeatEqIncompNewton::m_buildAb (+ m_applyBC) of a "Boussinesq" case: (A as CSC over the nodes, b)."""
+        nnz = self._chk(lib().pfem_ref_in_heat_build(self._h, _d(np.ascontiguousarray(theta_prev, dtype=np.float64)), 1 if apply_bc else 0),
+                        "in_heat_build")
+        col_ptr, row_idx = np.zeros(self.N + 1, dtype=np.int64), np.zeros(nnz, dtype=np.int32)
+        val, b = np.zeros(nnz), np.zeros(self.N)
+        lib().pfem_ref_in_heat_copy(self._h, col_ptr.ctypes.data_as(IP), row_idx.ctypes.data_as(C.POINTER(C.c_int32)), _d(val), _d(b))
+        return sp.csc_matrix((val, row_idx, col_ptr), shape=(self.N, self.N)), b
 
     def pspg_solve(self):
         """MomContEqIncompNewton::solve() (Picard loop).  Returns (ok, number of direct solves = Picard iterations)."""

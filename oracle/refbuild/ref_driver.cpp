@@ -32,6 +32,7 @@
 #include "simulation/Solver.hpp"
 #include "simulation/physics/IncompNewton/Solver.hpp"
 #include "simulation/physics/IncompNewton/MomContEquation.hpp"
+#include "simulation/physics/IncompNewton/HeatEquation.hpp"
 #include "simulation/physics/WCompNewton/Solver.hpp"
 #include "simulation/physics/WCompNewton/ContEquation.hpp"
 #include "simulation/physics/WCompNewton/MomEquation.hpp"
@@ -158,6 +159,20 @@ template <unsigned short dim> const Eigen::SparseMatrix<double>* matrixOf(RefCas
     return &eq->m_A;
 }
 
+template <unsigned short dim> const Eigen::SparseMatrix<double>* heatBuildIN(RefCase& rc, const double* thetaPrev, int applyBC, const Eigen::VectorXd** b) {
+    auto* eq = dynamic_cast<HeatEqIncompNewton<dim>*>(rc.solver->m_pEquations.back().get());
+    if (!eq) return nullptr;
+    Eigen::VectorXd q(rc.N);
+    for (std::size_t i = 0; i < rc.N; ++i) q[i] = thetaPrev[i];
+    eq->m_A.resize(rc.N, rc.N);  // HeatEquation.inl:113-115
+    eq->m_b.resize(rc.N);
+    eq->m_b.setZero();
+    eq->m_buildAb(q);
+    if (applyBC) eq->m_applyBC(q);
+    *b = &eq->m_b;
+    return &eq->m_A;
+}
+
 template <unsigned short dim> int elementMatrices(RefCase& rc, double* M, double* K, double* D, double* L, double* C, double* F, double* H) {
     auto* eq = dynamic_cast<MomContEqIncompNewton<dim>*>(rc.solver->m_pEquations[0].get());
     if (!eq) return -1;
@@ -235,7 +250,8 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
         if (nFacets > 0) rc->facets.assign(facets, facets + nFacets * (dim + 2));
         rc->tags.resize(rc->N);
         const bool boussinesqWC = rc->problemId == "BoussinesqWC";
-        if (boussinesqWC && g_tMask.size() == rc->N) {
+        const bool boussinesqIN = rc->problemId == "Boussinesq";
+        if ((boussinesqWC || boussinesqIN) && g_tMask.size() == rc->N) {
             rc->tMask = g_tMask;
             rc->tVal = g_tVal;
         } else {
@@ -255,7 +271,7 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
         in.nNodes = rc->N;
         in.nElems = rc->E;
         in.nFacets = static_cast<std::size_t>(nFacets > 0 ? nFacets : 0);
-        in.nStates = boussinesqWC ? 2 * dim + 3 : (wc ? 2 * dim + 2 : dim + 1);  // WC/Problem.cpp:17-18, 130-131; IN/Problem.cpp:13-14
+        in.nStates = boussinesqWC ? 2 * dim + 3 : (wc ? 2 * dim + 2 : (boussinesqIN ? dim + 2 : dim + 1));  // WC/Problem.cpp:17-18, 130-131; IN/Problem.cpp:13-14
         in.conn = rc->conn.data();
         in.x = rc->x.data();
         in.flags = rc->flags.data();
@@ -295,6 +311,26 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
             if (rc->problemId == "Bingham") {
                 material.set("tau0", p[11]);
                 material.set("mReg", p[12]);
+            }
+            if (boussinesqIN) {  // examples/2D/thermalConv/thermalConvIncomp.lua layout; params [11..14] = alpha, Tr, k, cv
+                material.set("alpha", p[11]);
+                material.set("Tr", p[12]);
+                material.set("k", p[13]);
+                material.set("cv", p[14]);
+                material.set("DgammaDT", 0.0);
+                material.set("h", 0.0);
+                material.set("Tinf", 0.0);
+                material.set("epsRad", 0.0);
+                bc.set_function("BVTV", dirV);
+                sol::table heatT, heatBC;
+                heatBC.set_function("BTT", dirT);
+                heatBC.set_function("BVTT", dirT);
+                heatT.set("maxIter", p[7]);
+                heatT.set("minRes", p[8]);
+                heatT.set("residual", std::string("Ax_f"));
+                heatT.set("BC", heatBC);
+                solverT.set("HeatEq", heatT);
+                solverT.set("solveHeatFirst", true);
             }
             sol::table eqT;
             eqT.set("maxIter", p[7]);
@@ -473,6 +509,41 @@ int pfem_ref_csc_copy(void* h, std::int64_t* colPtr, std::int32_t* rowIdx, doubl
     const Eigen::VectorXd* b;
     const auto* A = rc.dim == 2 ? matrixOf<2>(rc, &b) : matrixOf<3>(rc, &b);
     if (!A) return -1;
+    for (Eigen::Index j = 0; j <= A->cols(); ++j) colPtr[j] = A->outerIndexPtr()[j];
+    for (Eigen::Index k = 0; k < A->nonZeros(); ++k) {
+        rowIdx[k] = A->innerIndexPtr()[k];
+        val[k] = A->valuePtr()[k];
+    }
+    for (Eigen::Index i = 0; i < b->rows(); ++i) bOut[i] = (*b)[i];
+    return 0;
+}
+
+// HeatEqIncompNewton::m_buildAb (+ m_applyBC) on the current mesh; returns nnz or < 0; copy out with pfem_ref_in_heat_copy
+std::int64_t pfem_ref_in_heat_build(void* h, const double* thetaPrev, int applyBC) {
+    auto& rc = *static_cast<RefCase*>(h);
+    try {
+        rc.rebuildPositions();
+        const Eigen::VectorXd* b;
+        const auto* A = rc.dim == 2 ? heatBuildIN<2>(rc, thetaPrev, applyBC, &b) : heatBuildIN<3>(rc, thetaPrev, applyBC, &b);
+        return A ? A->nonZeros() : -1;
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return -1;
+    }
+}
+int pfem_ref_in_heat_copy(void* h, std::int64_t* colPtr, std::int32_t* rowIdx, double* val, double* bOut) {
+    auto& rc = *static_cast<RefCase*>(h);
+    const Eigen::SparseMatrix<double>* A;
+    const Eigen::VectorXd* b;
+    if (rc.dim == 2) {
+        auto* eq = dynamic_cast<HeatEqIncompNewton<2>*>(rc.solver->m_pEquations.back().get());
+        if (!eq) return -1;
+        A = &eq->m_A, b = &eq->m_b;
+    } else {
+        auto* eq = dynamic_cast<HeatEqIncompNewton<3>*>(rc.solver->m_pEquations.back().get());
+        if (!eq) return -1;
+        A = &eq->m_A, b = &eq->m_b;
+    }
     for (Eigen::Index j = 0; j <= A->cols(); ++j) colPtr[j] = A->outerIndexPtr()[j];
     for (Eigen::Index k = 0; k < A->nonZeros(); ++k) {
         rowIdx[k] = A->innerIndexPtr()[k];

@@ -131,6 +131,29 @@ def bingham_fixtures():
              indptr=A1.indptr.astype(np.int64), indices=A1.indices.astype(np.int32), A=A1.data, b=b1)
 
 
+def boussinesq_incompressible_fixtures():
+    """Problem id "Boussinesq": PSPG system with the buoyancy factors of MomContEquation.inl:166-199 and the implicit heat
+    system HeatEqIncompNewton::m_buildAb + m_applyBC (IncompNewton/HeatEquation.inl:227-412), temperature Dirichlet data
+    on two walls, no flux terms."""
+    for dim, n in ((2, 6), (3, 4)):
+        mesh, q, q_prev, par = H.pspg_case(dim, n, free_fraction=0.02, permute=True)
+        nn = mesh.n_nodes
+        c = mesh.coords()
+        T = 300.0 + 10.0 * c[:, 0] + 2.0 * np.random.default_rng(5).standard_normal(nn)
+        bound = (mesh.flags & mg.F_BOUND) != 0
+        t_mask = (bound & ((np.abs(c[:, 0]) < 1e-12) | (np.abs(c[:, 0] - 1.0) < 1e-12))).astype(np.uint8)
+        t_val = np.where(c[:, 0] < 0.5, 310.0, 290.0)
+        th = dict(alpha=6.9e-3, Tr=300.0, k=0.6, cv=4.186, t_mask=t_mask, t_val=t_val)
+        with ref.RefCase(mesh, "pspg", par, thermal=th) as rc:
+            rc.set_states(np.concatenate([q, T]))
+            A, b = rc.pspg_build(q_prev, True)
+            Ah, bh = rc.in_heat_build(T, True)
+        save(f"inb_{dim}d_boussinesq", **mesh_arrays(mesh), q=q, q_prev=q_prev, par=par, T=T, t_mask=t_mask, t_val=t_val,
+             thermal=np.array([th["alpha"], th["Tr"], th["k"], th["cv"]]),
+             indptr=A.indptr.astype(np.int64), indices=A.indices.astype(np.int32), A=A.data, b=b,
+             h_indptr=Ah.indptr.astype(np.int64), h_indices=Ah.indices.astype(np.int32), h_A=Ah.data, h_b=bh)
+
+
 def tables_fixture():
     mesh = mg.kuhn_box(3, 2)
     par = orc.pspg_param_array(1000.0, 1e-3, 1e-3, mg.gravity(3))
@@ -171,6 +194,7 @@ def main():
     fst_fixtures()
     boussinesq_fixtures()
     bingham_fixtures()
+    boussinesq_incompressible_fixtures()
 
 
 def fst_fixtures():

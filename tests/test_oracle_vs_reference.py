@@ -160,6 +160,29 @@ def test_bingham_oracle_matches_reference_fixture(name):
     assert block_errors(A0, A_ref, nn, dim)["vv"] > 1e-3
 
 
+@pytest.mark.parametrize("name", golden_names("inb_"))
+def test_incompressible_boussinesq_oracle_matches_reference_fixture(name):
+    """Problem id "Boussinesq": buoyancy factors in the PSPG right-hand side and the implicit heat system (oracle level)."""
+    import scipy.sparse as sp
+    mesh, z = load_golden(name)
+    dim, nn = mesh.dim, mesh.n_nodes
+    alpha, Tr, k, cv = z["thermal"]
+    vcur = z["q"][: dim * nn].copy()
+    orc.set_pspg_thermal(alpha, Tr, z["T"])
+    try:
+        A, b = orc.pspg_build(mesh, vcur, z["q_prev"], z["par"], True)
+    finally:
+        orc.set_pspg_thermal()
+    assert max(block_errors(A, golden_csc(z, "A"), nn, dim).values()) < TOL
+    assert max(vec_block_errors(b, z["b"], nn, dim).values()) < TOL
+    _, b0 = orc.pspg_build(mesh, vcur, z["q_prev"], z["par"], True)
+    assert max(vec_block_errors(b0, z["b"], nn, dim).values()) > 1e-4        # buoyancy is visible
+    Ah, bh = orc.in_heat_build(mesh, z["T"], z["par"][0], cv, k, z["par"][2], z["t_mask"], z["t_val"], True)
+    Ah_ref = sp.csc_matrix((z["h_A"], z["h_indices"], z["h_indptr"]), shape=(nn, nn))
+    assert (Ah.indptr == Ah_ref.indptr).all() and (Ah.indices == Ah_ref.indices).all()
+    assert rel_err(Ah.data, Ah_ref.data) < TOL and rel_err(bh, z["h_b"]) < TOL
+
+
 # ---- live comparisons (development container only: needs oracle/_ref/libpfem_ref.so) ----------------------------------
 needs_ref = pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built (no /root/reference here)")
 
