@@ -249,6 +249,31 @@ def test_live_wc_steps(dim, n, eq, meduri):
 
 
 @needs_ref
+def test_live_wc_forty_steps_do_not_drift():
+    """40 explicit steps with the CFL time step of each side: the oracle and the reference's own code stay bit-identical
+    (states, positions, every dt), so the per-step agreement is not an accident of the first steps."""
+    dim = 2
+    mesh = mg.kuhn_box(dim, 10, free_fraction=0.01, permute=True)
+    st = mg.wc_state(mesh)
+    W = mg.WC_PARAMS
+    wpar = orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], mg.gravity(dim), True, "CDS_dpdt")
+    nn, x = mesh.n_nodes, mesh.x
+    with ref.RefCase(mesh, "wc", np.concatenate([wpar, [1e-6, 1e-3, W["securityCoeff"]]])) as rc:
+        rc.set_states(np.concatenate([st["v"], st["p"], st["rho"], st["acc"]]))
+        for _ in range(40):
+            dt_ref = rc.wc_next_dt()
+            dt = orc.wc_next_dt(mesh, x, st, wpar, W["securityCoeff"], 1e-3)
+            assert dt == dt_ref
+            assert rc.wc_step(dt_ref)
+            x, st = orc.wc_step(mesh, x, st, wpar, dt)
+        want = split_wc(rc.get_states(), dim, nn)
+        for k in ("v", "p", "rho", "acc"):
+            assert np.array_equal(st[k], want[k]), k
+        assert np.array_equal(x, rc.positions())
+        assert np.abs(want["v"]).max() > 1e-3          # the column has started to move
+
+
+@needs_ref
 def test_live_picard_dense_lu():
     """Same Picard loop with the stand-in's own dense LU instead of SuperLU: the direct solver does not matter at 1e-8."""
     mesh = mg.kuhn_box(2, 8)
