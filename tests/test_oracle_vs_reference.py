@@ -274,6 +274,35 @@ def test_live_wc_forty_steps_do_not_drift():
 
 
 @needs_ref
+def test_live_pspg_five_time_steps():
+    """Five consecutive PSPG time steps (MomContEqIncompNewton::solve = Picard loop each, states and moved positions carried
+    over, no remeshing) on a C1-like 2-D column: oracle loop vs the reference's own code, same direct solver behind both."""
+    dim = 2
+    mesh = mg.kuhn_box(dim, 10)
+    _, q = mg.pspg_state(mesh)
+    P = mg.PSPG_PARAMS
+    par = orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim))
+    nn = mesh.n_nodes
+    ref.use_scipy_direct_solver(True)
+    try:
+        with ref.RefCase(mesh, "pspg", np.concatenate([par, [10, 1e-6]])) as rc:
+            rc.set_states(q)
+            x = mesh.x.copy()
+            for step in range(5):
+                ok, iters = rc.pspg_solve()
+                moved = mg.Mesh(dim=dim, x=x, conn=mesh.conn, flags=mesh.flags, dir_mask=mesh.dir_mask, dir_val=mesh.dir_val)
+                out = orc.pspg_picard(moved, q, q, par, max_iter=10, min_res=1e-6)
+                assert ok and out["ok"] and iters == out["iters"], step
+                q, x = out["q"], out["x"]
+                assert rel_err(q[: dim * nn], rc.get_states()[: dim * nn]) < 1e-8, step
+                assert rel_err(q[dim * nn:], rc.get_states()[dim * nn:]) < 1e-8, step
+                assert np.abs(x - rc.positions()).max() < 1e-11, step
+            assert np.abs(x - mesh.x).max() > 1e-7          # the mesh has moved over the five steps
+    finally:
+        ref.use_scipy_direct_solver(False)
+
+
+@needs_ref
 def test_live_picard_dense_lu():
     """Same Picard loop with the stand-in's own dense LU instead of SuperLU: the direct solver does not matter at 1e-8."""
     mesh = mg.kuhn_box(2, 8)
