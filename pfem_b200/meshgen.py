@@ -142,6 +142,77 @@ def kuhn_box(dim: int, n: int, *, jitter: float = 0.1, seed: int = 1234, permute
                 n_cells=n, meta=dict(jitter=jitter, seed=seed, permute=permute, free_fraction=free_fraction))
 
 
+def dam_break(dim: int, ncol: int, *, L: float = 0.146, jitter: float = 0.1, seed: int = 1234, permute: bool = False,
+              perm_seed: int = 4321) -> Mesh:
+    """Dam-break start configuration in the proportions of the reference's first three configs
+    (examples/2D/damBreakKoshizuka/geometry.geo:2-44, examples/3D/damBreakKoshizuka/geometry.geo): a water column of
+    width L (x L in 3-D) and height 2L in the left corner of a tank 4L wide and 3L high, node spacing d = L/ncol.
+    The column is a Kuhn grid (stand-in for gmsh + CGAL, see the module docstring); the tank walls carry nodes at the
+    same spacing.  Wall nodes touching the fluid are isBound|isFixed; the DRY wall nodes (floor right of the column,
+    left wall above it, right wall) belong to no element: isBound|isFixed|isFree, the combination every PFEM run has
+    and the unit-box meshes lack.  The column's right and top faces are the free surface.  All walls: velocity BC 0."""
+    assert dim in (2, 3)
+    d = L / ncol
+    counts = [ncol] * (dim - 1) + [2 * ncol]                 # cells per axis of the column (last axis = height)
+    m = [c + 1 for c in counts]
+    grid = np.meshgrid(*[np.arange(k) for k in m], indexing="ij")
+    idx = [g.ravel() for g in grid]
+    strides = [int(np.prod(m[a + 1:])) for a in range(dim)]
+    n_col_nodes = int(np.prod(m))
+    pts = np.stack([i.astype(np.float64) * d for i in idx], axis=1)
+    wall = (idx[0] == 0) | (idx[dim - 1] == 0)                 # left wall, floor
+    if dim == 3:
+        wall |= (idx[1] == 0) | (idx[1] == counts[1])          # front and back walls of a tank exactly L deep
+    fs = ((idx[0] == counts[0]) | (idx[dim - 1] == counts[dim - 1])) & ~wall
+    boundary = wall | fs
+    if jitter > 0:
+        disp = np.random.default_rng(seed).uniform(-jitter * d, jitter * d, size=pts.shape)
+        disp[boundary] = 0.0
+        pts = pts + disp
+    cgrid = np.meshgrid(*[np.arange(c) for c in counts], indexing="ij")
+    base = sum(c.ravel().astype(np.int64) * st for c, st in zip(cgrid, strides))
+    simplices = []
+    for perm in itertools.permutations(range(dim)):
+        verts, cur = [base], base
+        for a in perm:
+            cur = cur + strides[a]
+            verts.append(cur)
+        if _perm_sign(perm) < 0:
+            verts[-1], verts[-2] = verts[-2], verts[-1]
+        simplices.append(np.stack(verts, axis=1))
+    conn = np.stack(simplices, axis=1).reshape(-1, dim + 1).astype(np.int64)
+    # dry wall nodes of the tank (spacing d): floor x in (L, 4L], left wall z in (2L, 3L], right wall z in (0, 3L]
+    lat = [np.arange(m[1]) * d] if dim == 3 else []            # the y lattice of the 3-D tank
+    def line(xs, zs):
+        cols = [np.asarray(xs, dtype=np.float64)] + [None] * (dim - 2) + [np.asarray(zs, dtype=np.float64)]
+        if dim == 2:
+            return np.stack([cols[0], cols[1]], axis=1)
+        yy = lat[0]
+        return np.stack([np.repeat(cols[0], yy.size), np.tile(yy, cols[0].size), np.repeat(cols[2], yy.size)], axis=1)
+    kx = np.arange(ncol + 1, 4 * ncol + 1) * d
+    kz_left = np.arange(2 * ncol + 1, 3 * ncol + 1) * d
+    kz_right = np.arange(1, 3 * ncol + 1) * d
+    dry = np.concatenate([line(kx, np.zeros_like(kx)), line(np.zeros_like(kz_left), kz_left),
+                          line(np.full_like(kz_right, 4 * L), kz_right)], axis=0)
+    pts = np.concatenate([pts, dry], axis=0)
+    n_nodes = pts.shape[0]
+    flags = np.zeros(n_nodes, dtype=np.uint8)
+    flags[:n_col_nodes][wall] |= F_BOUND | F_FIXED
+    flags[:n_col_nodes][fs] |= F_FS
+    flags[n_col_nodes:] |= F_BOUND | F_FIXED | F_FREE
+    dir_mask = ((flags & F_BOUND) != 0).astype(np.uint8)
+    if permute:
+        rng = np.random.default_rng(perm_seed)
+        new_of_old = rng.permutation(n_nodes)
+        old_of_new = np.empty_like(new_of_old)
+        old_of_new[new_of_old] = np.arange(n_nodes)
+        pts, flags, dir_mask = pts[old_of_new], flags[old_of_new], dir_mask[old_of_new]
+        conn = new_of_old[conn]
+        conn = conn[rng.permutation(conn.shape[0])]
+    return Mesh(dim=dim, x=np.ascontiguousarray(pts.T).reshape(-1), conn=np.ascontiguousarray(conn), flags=flags,
+                dir_mask=dir_mask, dir_val=np.zeros(dim * n_nodes), n_cells=ncol, meta=dict(kind="dam_break", L=L, d=d))
+
+
 def boundary_facets(mesh: Mesh) -> np.ndarray:
     """Boundary facets as the reference stores them after the alpha shape (Mesh3D.cpp:218-262, Mesh2D.cpp): one row
     per element face that belongs to exactly one element = [dim facet nodes, the opposite element node

@@ -154,6 +154,26 @@ def boussinesq_incompressible_fixtures():
              h_indptr=Ah.indptr.astype(np.int64), h_indices=Ah.indices.astype(np.int32), h_A=Ah.data, h_b=bh)
 
 
+def dam_break_fixtures():
+    """The reference's first configurations in their real proportions and size (C1/C3: 1001 nodes, 1600 triangles at
+    ncol = 20; a small 3-D tank): water column + tank walls whose DRY nodes are isBound and isFree at once."""
+    P, W = mg.PSPG_PARAMS, mg.WC_PARAMS
+    for dim, ncol in ((2, 20), (3, 4)):
+        mesh = mg.dam_break(dim, ncol, permute=True)
+        nn, L = mesh.n_nodes, mesh.meta["L"]
+        c = mesh.coords()
+        wet = (mesh.flags & mg.F_FREE) == 0
+        p = np.where(wet, P["rho"] * 9.81 * (2 * L - c[:, dim - 1]), 0.0)
+        v = 0.05 * np.random.default_rng(3).standard_normal((dim, nn))
+        v[:, (mesh.flags & mg.F_BOUND) != 0] = 0.0
+        q = np.concatenate([v.reshape(-1), p])
+        par = orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim))
+        pspg_fixture(f"pspg_{dim}d_dambreak", mesh, q, q, par)
+        picard_fixture(f"picard_{dim}d_dambreak", mesh, q, par)
+        st = dict(v=v.reshape(-1).copy(), p=p.copy(), rho=mg.tait_density(p, W["K0"], W["K0p"], W["rhoStar"]), acc=np.zeros(dim * nn))
+        wc_fixture(f"wc_{dim}d_dambreak", mesh, st, "CDS_dpdt", True)
+
+
 def tables_fixture():
     mesh = mg.kuhn_box(3, 2)
     par = orc.pspg_param_array(1000.0, 1e-3, 1e-3, mg.gravity(3))
@@ -195,6 +215,7 @@ def main():
     boussinesq_fixtures()
     bingham_fixtures()
     boussinesq_incompressible_fixtures()
+    dam_break_fixtures()
 
 
 def fst_fixtures():
