@@ -342,3 +342,55 @@ def test_live_fracstep_pressure_solve_does_not_converge(dim, n):
     assert (vel[:2, 3] == 0).all() and (vel[:2, 2] < 1e-14).all()          # first velocity systems: converged to eps
     assert (prs[:, 3] == 2).all() and (prs[:, 1] == 2 * mesh.n_nodes).all() # pressure: NoConvergence at 2n iterations
     assert np.nanmax(prs[:, 2]) > 1e-6 and prs[0, 2] > 1e-6
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(10))
+def test_live_randomised_cases(seed):
+    """Seeded random cases: dimension, mesh family, size, free-node fraction, numbering, Dirichlet mask and data, material
+    constants, continuity variant and stabilisation all drawn at random; assembly (+BC) and two explicit steps must agree
+    with the reference's own code to 1e-12."""
+    rng = np.random.default_rng(1000 + seed)
+    dim = int(rng.integers(2, 4))
+    if rng.random() < 0.5:
+        mesh = mg.kuhn_box(dim, int(rng.integers(3, 7 if dim == 3 else 12)), free_fraction=float(rng.choice([0.0, 0.02, 0.1])),
+                           permute=bool(rng.integers(0, 2)), jitter=float(rng.uniform(0.0, 0.25)), seed=int(rng.integers(1, 10 ** 6)))
+    else:
+        mesh = mg.delaunay_cloud(dim, int(rng.integers(60, 220)), seed=int(rng.integers(1, 10 ** 6)),
+                                 free_fraction=float(rng.choice([0.0, 0.05])))
+    nn = mesh.n_nodes
+    bound = np.flatnonzero(mesh.flags & mg.F_BOUND)
+    mesh.dir_mask[:] = 0
+    mesh.dir_mask[bound[rng.random(bound.size) < 0.8]] = 1          # some bound nodes carry no velocity BC
+    mesh.dir_val = np.ascontiguousarray((0.2 * rng.standard_normal((dim, nn)) * (mesh.dir_mask != 0)).reshape(-1))
+    rho, mu, dt = float(10 ** rng.uniform(2, 3.3)), float(10 ** rng.uniform(-4, 0)), float(10 ** rng.uniform(-4, -2))
+    g = np.zeros(3); g[:dim] = rng.uniform(-10, 10, dim)
+    par = orc.pspg_param_array(rho, mu, dt, g)
+    v = rng.standard_normal(dim * nn)
+    q = np.concatenate([v, 1e3 * rng.standard_normal(nn)])
+    q_prev = q + 0.1 * rng.standard_normal(q.shape)
+    with ref.RefCase(mesh, "pspg", par) as rc:
+        rc.set_states(q)
+        A_ref, b_ref = rc.pspg_build(q_prev, True)
+    A, b = orc.pspg_build(mesh, q[: dim * nn].copy(), q_prev, par, True)
+    assert max(block_errors(A, A_ref, nn, dim).values()) < TOL
+    assert max(vec_block_errors(b, b_ref, nn, dim).values()) < TOL
+
+    eq = str(rng.choice(["CDS_dpdt", "CDS_drhodt", "CDS_rho"]))
+    meduri = bool(rng.integers(0, 2))
+    W = mg.WC_PARAMS
+    wpar = orc.wc_param_array(mu, W["K0"] * float(rng.uniform(0.5, 2)), W["K0p"], W["rhoStar"], g, meduri, eq)
+    st = mg.wc_state(mesh)
+    st["v"] = 0.3 * rng.standard_normal(dim * nn)
+    st["acc"] = rng.standard_normal(dim * nn)
+    x = mesh.x
+    with ref.RefCase(mesh, "wc", np.concatenate([wpar, [1e-6, 1e-3, 0.1]])) as rc:
+        rc.set_states(np.concatenate([st["v"], st["p"], st["rho"], st["acc"]]))
+        for step in range(2):
+            dt_ref = rc.wc_next_dt()
+            assert abs(orc.wc_next_dt(mesh, x, st, wpar, 0.1, 1e-3) - dt_ref) <= 1e-13 * dt_ref
+            assert rc.wc_step(dt_ref)
+            x, st = orc.wc_step(mesh, x, st, wpar, dt_ref)
+            want = split_wc(rc.get_states(), dim, nn)
+            for k in ("v", "p", "rho", "acc"):
+                assert rel_err(st[k], want[k]) < TOL * 10 ** step, (k, step, eq, meduri)
