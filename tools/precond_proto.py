@@ -113,7 +113,7 @@ def prolong(agg, bs):
 class MG:
     """aggregation multigrid, block-Jacobi smoothing (nu pre + nu post, damping w), V- or W(K)-cycle."""
 
-    def __init__(self, A, coords, h, bs, nu=1, w=0.7, min_size=None, factor=2.0, cycle="V", over=1.0):
+    def __init__(self, A, coords, h, bs, nu=1, w=0.7, min_size=None, factor=2.0, cycle="V", over=1.0, smooth_p=False):
         import os
         min_size = int(os.environ.get("MG_MIN", "400")) if min_size is None else min_size
         self.levels = []
@@ -128,6 +128,9 @@ class MG:
             h = h * factor
             agg = aggregate_grid(coords, h)
             P = prolong(agg, bs)
+            if smooth_p:   # smoothed aggregation: one damped (block-)Jacobi step on the tentative prolongator
+                DinvA = sp.bsr_matrix((Dinv, np.arange(Dinv.shape[0]), np.arange(Dinv.shape[0] + 1)), shape=A.shape).tocsr() @ A
+                P = (P - (2.0 / 3.0) * (DinvA @ P)).tocsr()
             lev["P"] = P
             A = (P.T @ A @ P).tocsr()
             coords = coarse_coords(coords, agg)
@@ -183,7 +186,11 @@ def main():
             fac = float(a[3]) if len(a) > 3 else 2.0
             cyc = a[4] if len(a) > 4 else "V"
             over = float(a[5]) if len(a) > 5 else 1.0
-            if v.startswith("monou"):      # hierarchy on the physical (unscaled) matrix: P is constant in (v, p)
+            sa = len(a) > 6 and a[6] == "sa"
+            if v.startswith("monou") and sa:
+                mgp = MG(A_phys, coords, h, bs, nu=nu, w=w, factor=fac, cycle=cyc, over=over, smooth_p=True)
+                M = lambda r, mgp=mgp: mgp(r / s) / s     # noqa: E731
+            elif v.startswith("monou"):      # hierarchy on the physical (unscaled) matrix: P is constant in (v, p)
                 mgp = MG(A_phys, coords, h, bs, nu=nu, w=w, factor=fac, cycle=cyc, over=over)
                 M = lambda r, mgp=mgp: mgp(r / s) / s     # noqa: E731
             else:
@@ -203,7 +210,17 @@ def main():
                 lu = spl.splu(Shat.tocsc())
                 Sinv = lu.solve
             else:
-                Sinv = MG(Shat, coords, h, 1, nu=nu, w=0.7)
+                # schur:nu:ncyc:cycle:over:sa -- ncyc stationary MG iterations per application, optional smoothed aggregation
+                ncyc = int(a[2]) if len(a) > 2 else 1
+                cyc = a[3] if len(a) > 3 else "V"
+                over = float(a[4]) if len(a) > 4 else 1.0
+                mgS = MG(Shat, coords, h, 1, nu=nu, w=0.7, cycle=cyc, over=over, smooth_p=(len(a) > 5 and a[5] == "sa"))
+
+                def Sinv(r, mgS=mgS, ncyc=ncyc):
+                    z = mgS(r)
+                    for _ in range(ncyc - 1):
+                        z = z + mgS(r - Shat @ z)
+                    return z
 
             def M(r, Sinv=Sinv):
                 z = np.zeros_like(r)
