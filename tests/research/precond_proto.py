@@ -1,10 +1,10 @@
 """CPU prototype (scipy) used to choose the device preconditioner of the PSPG BiCGSTAB solve.
 
-Research tooling only: builds the oracle matrix of the bench case at a small size and counts BiCGSTAB iterations for
+Research tooling only (lives under tests/ because it builds its matrix with the oracle, which only tests may import): builds the oracle matrix of the bench case at a small size and counts BiCGSTAB iterations for
   jac   : node-block Jacobi (what round-1 csrc/krylov.cu does)
   schur : block lower-triangular  [A_vv 0; A_pv S^]  with S^ = aggregation-AMG V-cycle on a nodal Laplacian
   mono  : monolithic aggregation multigrid on the node-block matrix, block-Jacobi smoothing
-Usage: python tools/precond_proto.py [n] [variant ...]
+Usage: python tests/research/precond_proto.py [n] [variant ...]
 """
 import sys
 import time
