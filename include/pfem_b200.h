@@ -197,6 +197,34 @@ int pfem_comm_init(pfem_ctx* ctx, int nRanks, int rank, const void* id128);
  * gather kernels sum in the single-GPU order (sharded results are then bit-identical to one GPU). */
 int pfem_set_partition(pfem_ctx* ctx, int64_t nOwned, int nPeers, const int32_t* peerRank, const int64_t* sendOffsets,
                        const int32_t* sendIdx, const int64_t* recvStart, const int64_t* recvCount);
+/* In-process communicator: the ranks are contexts of ONE process (the reference is a single process, Problem.cpp:344-369
+ * runs its time loop on one main thread), each driven by its own host thread; exchanges are device-to-device copies ordered
+ * by CUDA events, the threads meet at barriers inside the collective calls.  Several ranks may share one device (that is
+ * how the parity tests run a partitioned mesh on a single GPU).  The group must outlive its contexts.  Every rank must
+ * issue the same sequence of API calls. */
+int pfem_comm_local_create(int nRanks, void** group);
+int pfem_comm_local_destroy(void* group);
+int pfem_comm_init_local(pfem_ctx* ctx, void* group, int rank);
+/* A rank that failed outside the library releases the others from their barriers (they return PFEM_ERR_COMM). */
+int pfem_comm_abort(pfem_ctx* ctx);
+
+/* ---- partitioner (host, C++/OpenMP; once per remesh -- the call site is where the host hands the new mesh over after
+ * Mesh::remesh, Mesh.cpp:919-926) ---- */
+/* RCB of the node coordinates x[n + d*nNodes] into nRanks parts; a rank keeps every element incident to one of its nodes
+ * (one ghost-element layer) in ascending global element index, numbers its owned nodes first (ascending global id) and its
+ * ghosts grouped by owner.  elemNodes must stay valid until pfem_partition_destroy (it is read, not copied). */
+typedef struct pfem_partition pfem_partition;
+int pfem_partition_create(pfem_partition** part, int dim, int64_t nNodes, int64_t nElems, const uint64_t* elemNodes,
+                          const double* x, int nRanks);
+int pfem_partition_destroy(pfem_partition* part);
+int pfem_partition_owner(const pfem_partition* part, int32_t* owner /* nNodes */);
+/* sizes of the local mesh of `rank`, then its arrays: l2gNodes[nLocalNodes], l2gElems[nLocalElems], localConn[nLocalElems x
+ * (dim+1)] in local node ids, and the halo plan in the layout pfem_set_partition takes (peerRank[nPeers],
+ * sendOffsets[nPeers+1], sendIdx[nSend], recvStart[nPeers], recvCount[nPeers]).  Null outputs are skipped. */
+int pfem_partition_local_sizes(pfem_partition* part, int rank, int64_t* nLocalNodes, int64_t* nOwned, int64_t* nLocalElems,
+                               int32_t* nPeers, int64_t* nSend);
+int pfem_partition_local_get(pfem_partition* part, int rank, int64_t* l2gNodes, int64_t* l2gElems, uint64_t* localConn,
+                             int32_t* peerRank, int64_t* sendOffsets, int32_t* sendIdx, int64_t* recvStart, int64_t* recvCount);
 
 /* ---- instrumentation (phase names = the reference's m_accumalatedTimes keys, PSPG.inl:19-369) ---- */
 /* on: 0 off | 1 phases | 2 phases + per-kernel phases of the multigrid cycle (which then runs un-graphed) */

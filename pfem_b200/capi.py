@@ -76,6 +76,15 @@ SYMBOLS = {
     "pfem_comm_unique_id": (C.c_int, [_VP]),
     "pfem_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "pfem_set_partition": (C.c_int, [_VP, C.c_int64, C.c_int, _I32P, _I64P, _I32P, _I64P, _I64P]),
+    "pfem_comm_local_create": (C.c_int, [C.c_int, C.POINTER(_VP)]),
+    "pfem_comm_local_destroy": (C.c_int, [_VP]),
+    "pfem_comm_init_local": (C.c_int, [_VP, _VP, C.c_int]),
+    "pfem_comm_abort": (C.c_int, [_VP]),
+    "pfem_partition_create": (C.c_int, [C.POINTER(_VP), C.c_int, C.c_int64, C.c_int64, C.POINTER(C.c_uint64), _DP, C.c_int]),
+    "pfem_partition_destroy": (C.c_int, [_VP]),
+    "pfem_partition_owner": (C.c_int, [_VP, _I32P]),
+    "pfem_partition_local_sizes": (C.c_int, [_VP, C.c_int, _I64P, _I64P, _I64P, _I32P, _I64P]),
+    "pfem_partition_local_get": (C.c_int, [_VP, C.c_int, _I64P, _I64P, C.POINTER(C.c_uint64), _I32P, _I64P, _I32P, _I64P, _I64P]),
     "pfem_profile_enable": (C.c_int, [_VP, C.c_int]),
     "pfem_profile_reset": (C.c_int, [_VP]),
     "pfem_profile_get": (C.c_int, [_VP, C.c_char_p, _DP, _I64P]),
@@ -110,6 +119,80 @@ def _f64(a, n=None):
     if n is not None and a.size != n:
         raise ValueError(f"expected {n} doubles, got {a.size}")
     return a
+
+
+class NativePartition:
+    """RCB partition + ghost layer + halo plan computed by the library (pfem_partition_*, csrc/partition.cu)."""
+
+    def __init__(self, dim, conn, x, n_ranks):
+        self._L = load_library()
+        self._h = _VP()
+        conn = np.ascontiguousarray(conn, dtype=np.uint64)
+        x = _f64(x)
+        self.dim, self.n_ranks = dim, n_ranks
+        self._keep = (conn, x)  # the handle reads the caller's connectivity until it is destroyed
+        self.n_nodes, self.n_elems = x.size // dim, conn.shape[0]
+        rc = self._L.pfem_partition_create(C.byref(self._h), dim, self.n_nodes, self.n_elems,
+                                           conn.ctypes.data_as(C.POINTER(C.c_uint64)), _dptr(x), n_ranks)
+        if rc != 0:
+            raise PfemError(rc, "pfem_partition_create failed")
+
+    def owner(self):
+        o = np.empty(self.n_nodes, dtype=np.int32)
+        self._L.pfem_partition_owner(self._h, o.ctypes.data_as(_I32P))
+        return o
+
+    def local(self, rank):
+        nl, no, ne, ns = C.c_int64(0), C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        npeers = C.c_int32(0)
+        rc = self._L.pfem_partition_local_sizes(self._h, rank, C.byref(nl), C.byref(no), C.byref(ne), C.byref(npeers), C.byref(ns))
+        if rc != 0:
+            raise PfemError(rc, "pfem_partition_local_sizes failed")
+        npe = self.dim + 1
+        l2g_nodes = np.empty(nl.value, dtype=np.int64)
+        l2g_elems = np.empty(ne.value, dtype=np.int64)
+        conn = np.empty((ne.value, npe), dtype=np.uint64)
+        peers = np.empty(npeers.value, dtype=np.int32)
+        send_off = np.zeros(npeers.value + 1, dtype=np.int64)
+        send_idx = np.empty(ns.value, dtype=np.int32)
+        recv_start = np.empty(npeers.value, dtype=np.int64)
+        recv_count = np.empty(npeers.value, dtype=np.int64)
+        rc = self._L.pfem_partition_local_get(self._h, rank, l2g_nodes.ctypes.data_as(_I64P), l2g_elems.ctypes.data_as(_I64P),
+                                              conn.ctypes.data_as(C.POINTER(C.c_uint64)), peers.ctypes.data_as(_I32P),
+                                              send_off.ctypes.data_as(_I64P), send_idx.ctypes.data_as(_I32P),
+                                              recv_start.ctypes.data_as(_I64P), recv_count.ctypes.data_as(_I64P))
+        if rc != 0:
+            raise PfemError(rc, "pfem_partition_local_get failed")
+        return dict(n_owned=no.value, l2g_nodes=l2g_nodes, l2g_elems=l2g_elems, conn=conn, peers=peers, send_offsets=send_off,
+                    send_idx=send_idx, recv_start=recv_start, recv_count=recv_count)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self._L.pfem_partition_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LocalGroup:
+    """In-process communicator: n_ranks contexts of this process, each driven by its own thread (pfem_comm_local_*)."""
+
+    def __init__(self, n_ranks):
+        self._L = load_library()
+        self._h = _VP()
+        rc = self._L.pfem_comm_local_create(n_ranks, C.byref(self._h))
+        if rc != 0:
+            raise PfemError(rc, (self._L.pfem_last_error(None) or b"").decode())
+        self.n_ranks = n_ranks
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h:
+            self._L.pfem_comm_local_destroy(self._h)
+            self._h = _VP()
 
 
 class PfemContext:
@@ -348,6 +431,13 @@ class PfemContext:
     def comm_init(self, n_ranks, rank, uid: bytes):
         buf = C.create_string_buffer(uid, 128)
         self._chk(self._L.pfem_comm_init(self._h, n_ranks, rank, C.cast(buf, _VP)))
+
+    def comm_init_local(self, group: "LocalGroup", rank: int):
+        self._chk(self._L.pfem_comm_init_local(self._h, group._h, rank))
+
+    def comm_abort(self):
+        """Release the other ranks of a local group from their barriers after this rank failed outside the library."""
+        self._L.pfem_comm_abort(self._h)
 
     def set_partition(self, part):
         """Halo plan of a partition.LocalPart whose local mesh was given to set_topology/set_mesh."""

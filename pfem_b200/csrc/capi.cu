@@ -33,13 +33,34 @@ void pfemFlushPhases(pfem_ctx* c) {
     catch (const PfemFail& f) {                          \
         (ctx)->err = f.msg;                              \
         cudaGetLastError();                              \
+        if (f.code < 0) commAbort(ctx);                  \
         return f.code;                                   \
     }                                                    \
     catch (const std::exception& e) {                    \
         (ctx)->err = e.what();                           \
         return PFEM_ERR_INVALID;                         \
     }                                                    \
+    catch (...) {                                        \
+        (ctx)->err = "unknown exception";                \
+        return PFEM_ERR_INVALID;                         \
+    }                                                    \
     return PFEM_OK;
+// the same handlers for entry points that return a status of their own: nothing may unwind through extern "C"
+#define API_CATCH(ctx)                                   \
+    catch (const PfemFail& f) {                          \
+        (ctx)->err = f.msg;                              \
+        cudaGetLastError();                              \
+        if (f.code < 0) commAbort(ctx);                  \
+        return f.code;                                   \
+    }                                                    \
+    catch (const std::exception& e) {                    \
+        (ctx)->err = e.what();                           \
+        return PFEM_ERR_INVALID;                         \
+    }                                                    \
+    catch (...) {                                        \
+        (ctx)->err = "unknown exception";                \
+        return PFEM_ERR_INVALID;                         \
+    }
 
 extern "C" {
 
@@ -70,6 +91,10 @@ int pfem_create(pfem_ctx** out, int dim, int device) {
         g_createError = f.msg;
         delete c;
         return f.code;
+    } catch (...) {
+        g_createError = "pfem_create: unexpected exception";
+        delete c;
+        return PFEM_ERR_CUDA;
     }
     *out = c;
     return PFEM_OK;
@@ -201,11 +226,7 @@ int pfem_pspg_solve(pfem_ctx* c, double relTol, int maxIter, double* q, int* ite
         cudaSetDevice(c->device);
         status = krylovSolve(c, relTol, maxIter, iters, relRes, false);
         if (q) krylovFetchSolution(c, q);
-    } catch (const PfemFail& f) {
-        c->err = f.msg;
-        cudaGetLastError();
-        return f.code;
-    }
+    } API_CATCH(c)
     return status;
 }
 int pfem_pspg_set_preconditioner(pfem_ctx* c, int kind, int sweeps, double damping) {
@@ -257,11 +278,7 @@ int pfem_pspg_picard_iter(pfem_ctx* c, const pfem_pspg_params* p, const double* 
             if (r != r) status = PFEM_NAN;
         }
         if (q) krylovFetchSolution(c, q);
-    } catch (const PfemFail& f) {
-        c->err = f.msg;
-        cudaGetLastError();
-        return f.code;
-    }
+    } API_CATCH(c)
     return status;
 }
 int pfem_pspg_export_csc(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b) {
@@ -301,11 +318,7 @@ int pfem_wc_next_dt(pfem_ctx* c, const pfem_wc_params* p, double securityCoeff, 
         cudaSetDevice(c->device);
         PFEM_REQUIRE(p, PFEM_ERR_INVALID, "wc_next_dt: params is null");
         return wcNextDt(c, *p, securityCoeff, maxDT, dt);
-    } catch (const PfemFail& f) {
-        c->err = f.msg;
-        cudaGetLastError();
-        return f.code;
-    }
+    } API_CATCH(c)
 }
 
 int pfem_wc_run(pfem_ctx* c, const pfem_wc_params* p, int nSteps, double securityCoeff, double maxDT, double* dt, double* elapsed) {
@@ -315,11 +328,7 @@ int pfem_wc_run(pfem_ctx* c, const pfem_wc_params* p, int nSteps, double securit
         c->cflFresh = false;
         PFEM_REQUIRE(p, PFEM_ERR_INVALID, "wc_run: params is null");
         return wcRun(c, *p, nSteps, securityCoeff, maxDT, dt, elapsed);
-    } catch (const PfemFail& f) {
-        c->err = f.msg;
-        cudaGetLastError();
-        return f.code;
-    }
+    } API_CATCH(c)
 }
 
 int pfem_comm_unique_id(void* id128) {
@@ -328,12 +337,46 @@ int pfem_comm_unique_id(void* id128) {
     } catch (const PfemFail& f) {
         g_createError = f.msg;
         return f.code;
+    } catch (const std::exception& e) {
+        g_createError = e.what();
+        return PFEM_ERR_COMM;
+    } catch (...) {
+        g_createError = "unknown exception";
+        return PFEM_ERR_COMM;
     }
     return PFEM_OK;
 }
 int pfem_comm_init(pfem_ctx* c, int nRanks, int rank, const void* id128) {
     API_BEGIN(c)
     commInit(c, nRanks, rank, id128);
+    API_END(c)
+}
+int pfem_comm_local_create(int nRanks, void** group) {
+    if (!group) return PFEM_ERR_INVALID;
+    *group = nullptr;
+    try {
+        *group = commLocalCreate(nRanks);
+    } catch (const PfemFail& f) {
+        g_createError = f.msg;
+        return f.code;
+    } catch (...) {
+        g_createError = "comm_local_create: unexpected exception";
+        return PFEM_ERR_COMM;
+    }
+    return PFEM_OK;
+}
+int pfem_comm_local_destroy(void* group) {
+    commLocalDestroy(static_cast<LocalGroup*>(group));
+    return PFEM_OK;
+}
+int pfem_comm_abort(pfem_ctx* c) {
+    if (!c) return PFEM_ERR_INVALID;
+    commAbort(c);
+    return PFEM_OK;
+}
+int pfem_comm_init_local(pfem_ctx* c, void* group, int rank) {
+    API_BEGIN(c)
+    commInitLocal(c, static_cast<LocalGroup*>(group), rank);
     API_END(c)
 }
 

@@ -7,10 +7,17 @@
 // Messages are small (tens of KB .. ~1 MB): latency-bound, one grouped ncclSend/ncclRecv per exchange over NVLink.
 // NCCL is dlopen'ed so that the library loads (and exports its symbols) on a box without NCCL/GPU; a missing NCCL is
 // a loud PFEM_ERR_COMM, never a fallback.
+// Second transport, "local": the ranks are contexts of ONE process, each driven by its own host thread (the reference is
+// a single process: this is how its one main thread's workers reach several GPUs, and how the parity tests run a
+// partitioned mesh on a box with a single GPU).  Exchanges are device-to-device copies between the ranks' buffers, ordered
+// by CUDA events across the ranks' streams; the host threads only meet at barriers.  Same call sequence as the NCCL path.
 #include <dlfcn.h>
 
+#include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -37,8 +44,11 @@ struct NcclApi {
 };
 
 static NcclApi* loadNccl() {
-    static NcclApi api;
-    if (api.handle) return &api;
+    static NcclApi published;
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lock(mtx);
+    if (published.handle) return &published;
+    NcclApi api;  // filled locally; published only when every symbol has resolved
     const char* env = getenv("PFEM_NCCL_LIB");
     const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
@@ -61,7 +71,8 @@ static NcclApi* loadNccl() {
     api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
     api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
-    return &api;
+    published = api;
+    return &published;
 }
 #define NCCL_CHECK(api, expr)                                                                             \
     do {                                                                                                  \
@@ -78,7 +89,99 @@ __global__ void k_pack(const int* __restrict__ idx, int nSend, int width, const 
     const int e = t / width, cidx = t % width;
     buf[t] = arr[(size_t)idx[e] * width + cidx];
 }
+// local transport all-reduce: every rank stores its values in its row of a pinned, device-mapped host bank, then every
+// rank combines the rows in RANK ORDER -> the same bits on every rank
+__global__ void k_slots_store(const double* __restrict__ src, int n, double* __restrict__ row) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) row[t] = src[t];
+}
+__global__ void k_slots_reduce(const double* __restrict__ bank, int rowStride, int nRanks, int n, int isMin, double* __restrict__ dst) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    double a = bank[t];
+    for (int r = 1; r < nRanks; ++r) {
+        const double b = bank[(size_t)r * rowStride + t];
+        if (isMin) a = (b < a || b != b) ? b : a;  // NaN propagates, like the CFL reductions
+        else a += b;
+    }
+    dst[t] = a;
+}
 }  // namespace
+
+// ---- local transport ------------------------------------------------------------------------------------------------
+struct LocalGroup {
+    static constexpr int SLOT_CAP = 64;
+    int n = 0;
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0;
+    unsigned long long gen = 0;
+    bool aborted = false;
+    struct Pub {
+        pfem_ctx* ctx = nullptr;
+        const double* src = nullptr;     // packed send buffer / all-gather source of the current exchange
+        const HaloPlan* plan = nullptr;
+    };
+    std::vector<Pub> pub;
+    double* bank = nullptr;  // pinned + mapped: n rows of SLOT_CAP doubles
+    void barrier() {
+        std::unique_lock<std::mutex> lk(m);
+        if (aborted) pfemThrow(PFEM_ERR_COMM, "local communicator aborted by another rank");
+        const unsigned long long g = gen;
+        if (++arrived == n) {
+            arrived = 0;
+            ++gen;
+            cv.notify_all();
+            return;
+        }
+        const bool ok = cv.wait_for(lk, std::chrono::seconds(300), [&] { return gen != g || aborted; });
+        if (!ok) {
+            aborted = true;
+            cv.notify_all();
+            pfemThrow(PFEM_ERR_COMM, "local communicator: barrier timed out (ranks issued different call sequences?)");
+        }
+        if (gen == g && aborted) pfemThrow(PFEM_ERR_COMM, "local communicator aborted by another rank");
+    }
+};
+
+LocalGroup* commLocalCreate(int nRanks) {
+    PFEM_REQUIRE(nRanks >= 1 && nRanks <= 64, PFEM_ERR_INVALID, "comm_local_create: 1 <= nRanks <= 64");
+    LocalGroup* g = new LocalGroup;
+    g->n = nRanks;
+    g->pub.resize(nRanks);
+    if (cudaHostAlloc(&g->bank, (size_t)nRanks * LocalGroup::SLOT_CAP * sizeof(double), cudaHostAllocPortable | cudaHostAllocMapped) !=
+        cudaSuccess) {
+        cudaGetLastError();
+        delete g;
+        pfemThrow(PFEM_ERR_CUDA, "comm_local_create: cannot allocate the pinned reduction bank");
+    }
+    return g;
+}
+void commLocalDestroy(LocalGroup* g) {
+    if (!g) return;
+    if (g->bank) cudaFreeHost(g->bank);
+    delete g;
+}
+void commInitLocal(pfem_ctx* c, LocalGroup* g, int rank) {
+    PFEM_REQUIRE(g && rank >= 0 && rank < g->n, PFEM_ERR_INVALID, "comm_init_local: bad arguments");
+    PFEM_REQUIRE(!c->comm && !c->local, PFEM_ERR_STATE, "comm_init_local: communicator already initialised");
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->evPacked, cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&c->evCopied, cudaEventDisableTiming));
+    {
+        std::lock_guard<std::mutex> lk(g->m);
+        PFEM_REQUIRE(!g->pub[rank].ctx, PFEM_ERR_STATE, "comm_init_local: rank already taken");
+        g->pub[rank].ctx = c;
+    }
+    c->local = g;
+    c->nRanks = g->n;
+    c->rank = rank;
+}
+void commAbort(pfem_ctx* c) {
+    if (!c || !c->local) return;
+    std::lock_guard<std::mutex> lk(c->local->m);
+    c->local->aborted = true;
+    c->local->cv.notify_all();
+}
 
 void commUniqueId(void* id128) {
     PFEM_REQUIRE(id128, PFEM_ERR_INVALID, "comm_unique_id: null");
@@ -90,7 +193,7 @@ void commUniqueId(void* id128) {
 
 void commInit(pfem_ctx* c, int nRanks, int rank, const void* id128) {
     PFEM_REQUIRE(nRanks >= 1 && rank >= 0 && rank < nRanks && id128, PFEM_ERR_INVALID, "comm_init: bad arguments");
-    PFEM_REQUIRE(!c->comm, PFEM_ERR_STATE, "comm_init: communicator already initialised");
+    PFEM_REQUIRE(!c->comm && !c->local, PFEM_ERR_STATE, "comm_init: communicator already initialised");
     NcclApi* api = loadNccl();
     ncclUniqueId id;
     memcpy(&id, id128, sizeof(id));
@@ -105,6 +208,14 @@ void commInit(pfem_ctx* c, int nRanks, int rank, const void* id128) {
 void commDestroy(pfem_ctx* c) {
     if (c->comm && c->nccl) c->nccl->CommDestroy((ncclComm_t)c->comm);
     c->comm = nullptr;
+    if (c->local) {
+        std::lock_guard<std::mutex> lk(c->local->m);
+        c->local->pub[c->rank].ctx = nullptr;
+    }
+    c->local = nullptr;
+    if (c->evPacked) cudaEventDestroy(c->evPacked);
+    if (c->evCopied) cudaEventDestroy(c->evCopied);
+    c->evPacked = c->evCopied = nullptr;
 }
 
 // Partition description of the LOCAL mesh given to pfem_set_topology: rows [0, nOwned) are computed here, nodes
@@ -116,49 +227,82 @@ void commSetPartition(pfem_ctx* c, int64_t nOwned, int nPeers, const int32_t* pe
     PFEM_REQUIRE(nPeers == 0 || (peerRank && sendOffsets && recvStart && recvCount), PFEM_ERR_INVALID, "set_partition: null");
     c->nRows = (int)nOwned;
     mgInvalidate(c, true);
-    c->peers.clear();
+    HaloPlan& P = c->plan;
+    P.clear();
     int64_t total = nPeers ? sendOffsets[nPeers] : 0;
     for (int p = 0; p < nPeers; ++p) {
         PFEM_REQUIRE(peerRank[p] >= 0 && peerRank[p] < c->nRanks && peerRank[p] != c->rank, PFEM_ERR_INVALID,
                      "set_partition: bad peer rank");
         PFEM_REQUIRE(recvStart[p] >= nOwned && recvStart[p] + recvCount[p] <= c->nNodes, PFEM_ERR_INVALID,
                      "set_partition: receive range outside the ghost nodes");
-        c->peers.push_back({peerRank[p], (int)sendOffsets[p], (int)(sendOffsets[p + 1] - sendOffsets[p]), (int)recvStart[p],
-                            (int)recvCount[p]});
+        P.peers.push_back({peerRank[p], (int)sendOffsets[p], (int)(sendOffsets[p + 1] - sendOffsets[p]), (int)recvStart[p],
+                           (int)recvCount[p]});
     }
-    c->nSendTotal = (int)total;
-    c->sendIdx.reserve(total + 4);
-    if (total > 0) {
-        for (int64_t k = 0; k < total; ++k)
-            PFEM_REQUIRE(sendIdx[k] >= 0 && sendIdx[k] < nOwned, PFEM_ERR_INVALID, "set_partition: send index is not an owned node");
-        CUDA_CHECK(cudaMemcpyAsync(c->sendIdx.p, sendIdx, total * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    }
-    c->sendBuf.reserve((size_t)total * 8 + 8);
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    for (int64_t k = 0; k < total; ++k)
+        PFEM_REQUIRE(sendIdx[k] >= 0 && sendIdx[k] < nOwned, PFEM_ERR_INVALID, "set_partition: send index is not an owned node");
+    P.sendIdxHost.assign(sendIdx, sendIdx + total);
+    commFinishPlan(c, P);
     c->haveSystem = c->haveSolution = false;
+    c->tilesValid = false;
+}
+void commFinishPlan(pfem_ctx* c, HaloPlan& P) {
+    const size_t total = P.sendIdxHost.size();
+    P.nSendTotal = (int)total;
+    P.sendIdx.reserve(total + 4);
+    if (total > 0)
+        CUDA_CHECK(cudaMemcpyAsync(P.sendIdx.p, P.sendIdxHost.data(), total * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    P.sendBuf.reserve(total * 8 + 8);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-// owners -> ghosts for up to two nodal arrays of `width` doubles per node, one NCCL group
-void commHalo(pfem_ctx* c, double* arr0, double* arr1, int width) {
-    if (c->nRanks <= 1 || c->peers.empty()) return;
-    PFEM_REQUIRE(c->comm, PFEM_ERR_COMM, "halo exchange without a communicator");
+// owners -> ghosts for up to two nodal arrays of `width` doubles per node
+void commHaloPlan(pfem_ctx* c, HaloPlan& P, double* arr0, double* arr1, int width) {
+    if (c->nRanks <= 1) return;
+    PFEM_REQUIRE(c->comm || c->local, PFEM_ERR_COMM, "halo exchange without a communicator");
+    if (!c->local && P.peers.empty()) return;  // the local transport meets at barriers: every rank takes part
     PhaseScope ph(c, "Halo exchange");
-    NcclApi* api = c->nccl;
     const int nArr = arr1 ? 2 : 1;
     double* arrs[2] = {arr0, arr1};
-    c->sendBuf.reserve((size_t)c->nSendTotal * width * nArr + 8);
+    P.sendBuf.reserve((size_t)P.nSendTotal * width * nArr + 8);
     for (int k = 0; k < nArr; ++k) {
-        if (c->nSendTotal > 0) {
-            k_pack<<<divUp((int64_t)c->nSendTotal * width, 256), 256, 0, c->stream>>>(
-                c->sendIdx.p, c->nSendTotal, width, arrs[k], c->sendBuf.p + (size_t)k * c->nSendTotal * width);
+        if (P.nSendTotal > 0) {
+            k_pack<<<divUp((int64_t)P.nSendTotal * width, 256), 256, 0, c->stream>>>(
+                P.sendIdx.p, P.nSendTotal, width, arrs[k], P.sendBuf.p + (size_t)k * P.nSendTotal * width);
             LAUNCH_CHECK(c);
         }
     }
+    if (c->local) {
+        LocalGroup* g = c->local;
+        CUDA_CHECK(cudaEventRecord(c->evPacked, c->stream));
+        g->pub[c->rank].src = P.sendBuf.p;
+        g->pub[c->rank].plan = &P;
+        g->barrier();
+        for (const auto& p : P.peers) {
+            if (p.recvCount <= 0) continue;
+            const LocalGroup::Pub& o = g->pub[p.rank];
+            PFEM_REQUIRE(o.ctx && o.plan, PFEM_ERR_COMM, "local halo: peer has no plan");
+            const HaloPlan::Peer* q = nullptr;
+            for (const auto& e : o.plan->peers)
+                if (e.rank == c->rank) q = &e;
+            PFEM_REQUIRE(q && q->sendCount == p.recvCount, PFEM_ERR_COMM, "local halo: send/receive counts of a pair differ");
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, o.ctx->evPacked, 0));
+            for (int k = 0; k < nArr; ++k)
+                CUDA_CHECK(cudaMemcpyAsync(arrs[k] + (size_t)p.recvStart * width,
+                                           o.src + ((size_t)k * o.plan->nSendTotal + q->sendOff) * width,
+                                           (size_t)p.recvCount * width * sizeof(double), cudaMemcpyDefault, c->stream));
+        }
+        CUDA_CHECK(cudaEventRecord(c->evCopied, c->stream));
+        g->barrier();
+        for (const auto& p : P.peers)  // my next pack must not overwrite the buffer a peer is still copying from
+            if (p.sendCount > 0) CUDA_CHECK(cudaStreamWaitEvent(c->stream, g->pub[p.rank].ctx->evCopied, 0));
+        return;
+    }
+    NcclApi* api = c->nccl;
     NCCL_CHECK(api, api->GroupStart());
     for (int k = 0; k < nArr; ++k) {
-        for (const auto& p : c->peers) {
+        for (const auto& p : P.peers) {
             if (p.sendCount > 0)
-                NCCL_CHECK(api, api->Send(c->sendBuf.p + ((size_t)k * c->nSendTotal + p.sendOff) * width,
+                NCCL_CHECK(api, api->Send(P.sendBuf.p + ((size_t)k * P.nSendTotal + p.sendOff) * width,
                                           (size_t)p.sendCount * width, ncclFloat64, p.rank, (ncclComm_t)c->comm, c->stream));
             if (p.recvCount > 0)
                 NCCL_CHECK(api, api->Recv(arrs[k] + (size_t)p.recvStart * width, (size_t)p.recvCount * width, ncclFloat64,
@@ -167,14 +311,95 @@ void commHalo(pfem_ctx* c, double* arr0, double* arr1, int width) {
     }
     NCCL_CHECK(api, api->GroupEnd());
 }
+void commHalo(pfem_ctx* c, double* arr0, double* arr1, int width) { commHaloPlan(c, c->plan, arr0, arr1, width); }
+
+static void localAllReduce(pfem_ctx* c, double* buf, int count, bool isMin) {
+    LocalGroup* g = c->local;
+    PFEM_REQUIRE(count <= LocalGroup::SLOT_CAP, PFEM_ERR_INVALID, "local all-reduce: too many values");
+    // the previous all-reduce's readers are done with the bank (their events were recorded before its second barrier)
+    for (int r = 0; r < g->n; ++r)
+        if (g->pub[r].ctx && g->pub[r].ctx != c) CUDA_CHECK(cudaStreamWaitEvent(c->stream, g->pub[r].ctx->evCopied, 0));
+    k_slots_store<<<1, 64, 0, c->stream>>>(buf, count, g->bank + (size_t)c->rank * LocalGroup::SLOT_CAP);
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaEventRecord(c->evPacked, c->stream));
+    g->barrier();
+    for (int r = 0; r < g->n; ++r)
+        if (g->pub[r].ctx && g->pub[r].ctx != c) CUDA_CHECK(cudaStreamWaitEvent(c->stream, g->pub[r].ctx->evPacked, 0));
+    k_slots_reduce<<<1, 64, 0, c->stream>>>(g->bank, LocalGroup::SLOT_CAP, g->n, count, isMin ? 1 : 0, buf);
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaEventRecord(c->evCopied, c->stream));
+    g->barrier();
+}
 
 void commAllReduceMin(pfem_ctx* c, double* devScalar) {
+    if (c->nRanks <= 1) return;
+    if (c->local) return localAllReduce(c, devScalar, 1, true);
     PFEM_REQUIRE(c->comm, PFEM_ERR_COMM, "no communicator");
     NCCL_CHECK(c->nccl, c->nccl->AllReduce(devScalar, devScalar, 1, ncclFloat64, ncclMin, (ncclComm_t)c->comm, c->stream));
 }
 
 void commAllReduceSum(pfem_ctx* c, double* buf, int count) {
     if (c->nRanks <= 1) return;
+    if (c->local) return localAllReduce(c, buf, count, false);
     PFEM_REQUIRE(c->comm, PFEM_ERR_COMM, "no communicator");
     NCCL_CHECK(c->nccl, c->nccl->AllReduce(buf, buf, (size_t)count, ncclFloat64, ncclSum, (ncclComm_t)c->comm, c->stream));
+}
+
+void commAllGatherBytes(pfem_ctx* c, const void* srcV, void* dstV, const std::vector<int64_t>& counts, const std::vector<int64_t>& displs) {
+    PFEM_REQUIRE((int)counts.size() == c->nRanks && (int)displs.size() == c->nRanks, PFEM_ERR_INVALID, "all-gather: bad counts");
+    const char* src = static_cast<const char*>(srcV);
+    char* dst = static_cast<char*>(dstV);
+    char* mine = dst + displs[c->rank];
+    if (src != mine && counts[c->rank] > 0)
+        CUDA_CHECK(cudaMemcpyAsync(mine, src, (size_t)counts[c->rank], cudaMemcpyDeviceToDevice, c->stream));
+    if (c->nRanks <= 1) return;
+    PhaseScope ph(c, "All-gather");
+    if (c->local) {
+        LocalGroup* g = c->local;
+        CUDA_CHECK(cudaEventRecord(c->evPacked, c->stream));
+        g->pub[c->rank].src = reinterpret_cast<const double*>(mine);
+        g->barrier();
+        for (int r = 0; r < g->n; ++r) {
+            if (r == c->rank || counts[r] <= 0) continue;
+            PFEM_REQUIRE(g->pub[r].ctx, PFEM_ERR_COMM, "local all-gather: missing rank");
+            CUDA_CHECK(cudaStreamWaitEvent(c->stream, g->pub[r].ctx->evPacked, 0));
+            CUDA_CHECK(cudaMemcpyAsync(dst + displs[r], g->pub[r].src, (size_t)counts[r], cudaMemcpyDefault, c->stream));
+        }
+        CUDA_CHECK(cudaEventRecord(c->evCopied, c->stream));
+        g->barrier();
+        for (int r = 0; r < g->n; ++r)
+            if (r != c->rank && g->pub[r].ctx) CUDA_CHECK(cudaStreamWaitEvent(c->stream, g->pub[r].ctx->evCopied, 0));
+        return;
+    }
+    PFEM_REQUIRE(c->comm, PFEM_ERR_COMM, "no communicator");
+    NcclApi* api = c->nccl;
+    NCCL_CHECK(api, api->GroupStart());
+    for (int r = 0; r < c->nRanks; ++r) {
+        if (r == c->rank) continue;
+        if (counts[c->rank] > 0)
+            NCCL_CHECK(api, api->Send(mine, (size_t)counts[c->rank], ncclInt8, r, (ncclComm_t)c->comm, c->stream));
+        if (counts[r] > 0)
+            NCCL_CHECK(api, api->Recv(dst + displs[r], (size_t)counts[r], ncclInt8, r, (ncclComm_t)c->comm, c->stream));
+    }
+    NCCL_CHECK(api, api->GroupEnd());
+}
+void commAllGatherV(pfem_ctx* c, const double* src, double* dst, const std::vector<int64_t>& counts, const std::vector<int64_t>& displs) {
+    std::vector<int64_t> cb(counts), db(displs);
+    for (auto& v : cb) v *= (int64_t)sizeof(double);
+    for (auto& v : db) v *= (int64_t)sizeof(double);
+    commAllGatherBytes(c, src, dst, cb, db);
+}
+
+void commAllGatherHost(pfem_ctx* c, const double* mine, int n, double* all) {
+    if (c->nRanks <= 1) {
+        memcpy(all, mine, (size_t)n * sizeof(double));
+        return;
+    }
+    c->commScratch.reserve((size_t)c->nRanks * n + 8);
+    std::vector<int64_t> counts(c->nRanks, n), displs(c->nRanks);
+    for (int r = 0; r < c->nRanks; ++r) displs[r] = (int64_t)r * n;
+    CUDA_CHECK(cudaMemcpyAsync(c->commScratch.p + displs[c->rank], mine, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    commAllGatherV(c, c->commScratch.p + displs[c->rank], c->commScratch.p, counts, displs);
+    CUDA_CHECK(cudaMemcpyAsync(all, c->commScratch.p, (size_t)c->nRanks * n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }

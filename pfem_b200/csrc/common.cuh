@@ -68,6 +68,25 @@ struct PendingPhase {
 };
 
 struct NcclApi;      // dlopen'ed NCCL entry points (comm.cu)
+struct LocalGroup;   // in-process transport: several contexts (ranks) driven by threads of one process (comm.cu)
+
+// Halo plan of one (multigrid) level of a partitioned mesh: rows [0, nOwned) are computed here, the entries behind them
+// are ghosts grouped by owner; per peer a send list (local owned ids) and one contiguous ghost range to receive into.
+struct HaloPlan {
+    struct Peer {
+        int rank, sendOff, sendCount, recvStart, recvCount;
+    };
+    std::vector<Peer> peers;
+    DevBuf<int> sendIdx;     // local ids of owned entries to send, concatenated per peer
+    std::vector<int> sendIdxHost;
+    DevBuf<double> sendBuf;  // packed send data (grown on demand)
+    int nSendTotal = 0;
+    void clear() {
+        peers.clear();
+        sendIdxHost.clear();
+        nSendTotal = 0;
+    }
+};
 struct MgHierarchy;  // multigrid preconditioner state (mg.cu)
 
 // slots of the Krylov scalar bank kept on the device (krylov.cu)
@@ -147,6 +166,7 @@ struct pfem_ctx {
     DevBuf<double> wcCfl2;     // per node (max(u^2, c^2), alpha^2) of the state the last two-pass step produced
     int wcVariant = 0;         // pfem_wc_set_variant: 0 = by size (PFEM_WC_CFG), 6 gather, 11 two-pass, 12 mixed
     bool cflFresh = false;     // wcContRec.he / wcCfl2 describe the current positions and states
+    bool tilesValid = false;   // node tiles of the fused explicit step (wc_tile.cu) match the current topology/partition
     double cflMu = 0, cflK0 = 0, cflK0p = 0;
 
     // ---- free-surface facets / surface tension (facets.cu) ----
@@ -159,13 +179,10 @@ struct pfem_ctx {
     // ---- multi-GPU ----
     NcclApi* nccl = nullptr;
     void* comm = nullptr;
-    struct Peer {
-        int rank, sendOff, sendCount, recvStart, recvCount;
-    };
-    std::vector<Peer> peers;   // halo plan of the local mesh (pfem_set_partition)
-    DevBuf<int> sendIdx;       // local ids of owned nodes to send, concatenated per peer
-    DevBuf<double> sendBuf;
-    int nSendTotal = 0;
+    LocalGroup* local = nullptr;   // in-process transport (pfem_comm_init_local) instead of NCCL
+    cudaEvent_t evPacked = nullptr, evCopied = nullptr;  // local transport: stream ordering between the ranks' streams
+    HaloPlan plan;                 // halo plan of the local mesh (pfem_set_partition)
+    DevBuf<double> commScratch;    // staging of small host <-> device collectives
 
     // ---- profiling ----
     bool profiling = false;
@@ -175,7 +192,7 @@ struct pfem_ctx {
     std::vector<cudaEvent_t> eventPool;
 
     pfem_ctx() {
-        for (auto* b : {&conn, &n2ePtr, &n2e, &nbrPtr, &nbr, &diagSlot, &scratchI, &scanScratch, &cscPtr, &cscRow, &sendIdx,
+        for (auto* b : {&conn, &n2ePtr, &n2e, &nbrPtr, &nbr, &diagSlot, &scratchI, &scanScratch, &cscPtr, &cscRow, &plan.sendIdx,
                         &facetRec, &fstNode, &fstPtr, &fstItem})
             b->accounting = &deviceBytes;
         fst4.accounting = &deviceBytes;
@@ -184,7 +201,7 @@ struct pfem_ctx {
         wcCfl2.accounting = &deviceBytes;
         for (auto* b : {&flags, &dirMask, &stageB}) b->accounting = &deviceBytes;
         for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &Wblk, &kx, &kr, &kr0,
-                        &kp, &kp2, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &sendBuf})
+                        &kp, &kp2, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &plan.sendBuf, &commScratch})
             b->accounting = &deviceBytes;
         stage64.accounting = &deviceBytes;
         n2eSlots.accounting = &deviceBytes;
@@ -275,6 +292,20 @@ void commInit(pfem_ctx* c, int nRanks, int rank, const void* id128);
 void commDestroy(pfem_ctx* c);
 void commSetPartition(pfem_ctx* c, int64_t nOwned, int nPeers, const int32_t* peerRank, const int64_t* sendOffsets,
                       const int32_t* sendIdx, const int64_t* recvStart, const int64_t* recvCount);
-void commHalo(pfem_ctx* c, double* arr0, double* arr1, int width);  // owners -> ghosts, up to two nodal arrays
+void commHalo(pfem_ctx* c, double* arr0, double* arr1, int width);  // owners -> ghosts, up to two nodal arrays (level-0 plan)
+void commHaloPlan(pfem_ctx* c, HaloPlan& plan, double* arr0, double* arr1, int width);
 void commAllReduceSum(pfem_ctx* c, double* buf, int count);
 void commAllReduceMin(pfem_ctx* c, double* devScalar);
+// every rank contributes counts[rank] doubles from `src`; all of them land in `dst` at displs[r] on every rank (device buffers;
+// src may alias dst + displs[rank])
+void commAllGatherV(pfem_ctx* c, const double* src, double* dst, const std::vector<int64_t>& counts, const std::vector<int64_t>& displs);
+// the same for raw bytes (counts and displacements in bytes)
+void commAllGatherBytes(pfem_ctx* c, const void* src, void* dst, const std::vector<int64_t>& counts, const std::vector<int64_t>& displs);
+// install a halo plan on the device (send list upload, buffers)
+void commFinishPlan(pfem_ctx* c, HaloPlan& P);
+// small host-side all-gather: n doubles per rank -> nRanks*n doubles, rank-major (synchronises the stream)
+void commAllGatherHost(pfem_ctx* c, const double* mine, int n, double* all);
+void commInitLocal(pfem_ctx* c, LocalGroup* g, int rank);
+LocalGroup* commLocalCreate(int nRanks);
+void commLocalDestroy(LocalGroup* g);
+void commAbort(pfem_ctx* c);  // a failing rank releases the others from their barriers (local transport)

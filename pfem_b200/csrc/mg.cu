@@ -15,8 +15,10 @@
 //   * symbolic part (aggregates, coarse patterns, fine-block -> coarse-slot map) once per topology; numeric part
 //     (Galerkin sums, block inverses, coarsest inverse) once per assembly.  Everything is gather-style and ordered, no
 //     floating-point atomics: the preconditioner, hence the whole solve, is bit-reproducible run to run.
-// On a partitioned mesh every rank builds the hierarchy of its owned rows; the fine-level sweeps use the global matrix
-// (halo exchange of the iterate before each of them), the coarse levels drop the couplings across ranks.
+// On a partitioned mesh the hierarchy is GLOBAL: aggregates are rank-local, but the Galerkin operators keep the couplings
+// across ranks (ghost aggregates + a halo plan per distributed level); once a level has fewer than ~50 k nodes in total it
+// is replicated on every rank (all-gather of its rows) and the rest of the hierarchy, down to the dense coarsest solve, is
+// computed redundantly -- no exchange on the small levels, one all-gather of the restricted residual per cycle.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -49,6 +51,17 @@ struct MgLevel {
     DevBuf<double> sc;            // 1/sqrt|a_dd| per dof (l1 damping works in the equilibrated variables)
     double omega = 0.5;           // damping of this level's smoother (tuned or fixed)
     DevBuf<double> b, xa, xb, t, xo;
+    // partitioned mesh: a DISTRIBUTED level holds this rank's rows; its vectors carry a ghost tail that
+    // `plan` refreshes from the owners before every sweep.  Below a size threshold the next level is REPLICATED: every rank
+    // holds all of its rows (this rank contributed rows [rowOff, rowOff + ncLocal)) and works on it redundantly, so the
+    // small levels need no exchange at all -- one all-gather of the restricted residual per cycle.
+    bool distributed = false;
+    HaloPlan* plan = nullptr;            // level 0: the context's plan
+    std::unique_ptr<HaloPlan> ownPlan;   // deeper distributed levels
+    bool nextReplicated = false;
+    int ncLocal = 0, rowOff = 0;
+    std::vector<int64_t> rowCounts, rowDispls;  // per rank, coarse rows
+    std::vector<int64_t> blkCounts, blkDispls;  // per rank, coarse blocks
 };
 struct MgHierarchy {
     std::vector<std::unique_ptr<MgLevel>> lev;
@@ -211,7 +224,7 @@ __global__ void k_sort_members(int nc, int dim, const int* __restrict__ aggPtr, 
 template <bool FILL>
 __global__ void k_coarse_nbr(int nc, const int* __restrict__ aggPtr, const int* __restrict__ aggNodes, const int* __restrict__ agg,
                              int nFine, const int* __restrict__ nbrPtr, const int* __restrict__ nbr, int* __restrict__ cPtr,
-                             int* __restrict__ cNbr, int* __restrict__ cDiag, int* __restrict__ misc) {
+                             int* __restrict__ cNbr, int* __restrict__ cDiag, int* __restrict__ misc, int rowOff) {
     __shared__ int lists[8][NBR_CAP];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int I = blockIdx.x * 8 + w;
@@ -257,21 +270,22 @@ __global__ void k_coarse_nbr(int nc, const int* __restrict__ aggPtr, const int* 
             int rank = 0;
             for (int q = 0; q < cnt; ++q) rank += list[q] < v;
             cNbr[base + rank] = v;
-            if (v == I) cDiag[I] = rank;
+            if (v == I + rowOff) cDiag[I] = rank;  // rowOff: this rank's first row of a replicated level
         }
     }
 }
 // slot of every fine block in the coarse row of its aggregate (-1: ghost column, dropped)
 __global__ void k_cslot(int nFine, const int* __restrict__ nbrPtr, const int* __restrict__ nbr, const int* __restrict__ agg,
-                        const int* __restrict__ cPtr, const int* __restrict__ cNbr, int* __restrict__ cslot) {
+                        const int* __restrict__ cPtr, const int* __restrict__ cNbr, int* __restrict__ cslot, int nCols = -1) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nFine) return;
+    if (nCols < 0) nCols = nFine;  // columns with an aggregate: the rows, plus the ghost tail of a distributed level
     const int I = agg[i];
     const int c0 = cPtr[I], cn = cPtr[I + 1] - c0;
     for (int k = nbrPtr[i]; k < nbrPtr[i + 1]; ++k) {
         const int j = nbr[k];
         int res = -1;
-        if (j < nFine) {
+        if (j < nCols) {
             const int J = agg[j];
             int lo = 0, hi = cn - 1;
             while (lo <= hi) {
@@ -287,6 +301,18 @@ __global__ void k_cslot(int nFine, const int* __restrict__ nbrPtr, const int* __
         }
         cslot[k] = res;
     }
+}
+
+__global__ void k_agg_shift_to_double(int n, int* __restrict__ agg, int shift, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int a = agg[i] + shift;
+    agg[i] = a;
+    out[i] = (double)a;
+}
+__global__ void k_double_to_int(int n, const double* __restrict__ in, int* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)in[i];
 }
 
 // ---- numeric ----------------------------------------------------------------------------------------------------------
@@ -587,9 +613,9 @@ bool mgFp32() {
 
 template <int EPI>
 void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const double* x, double* y, const double* b) {
-    // partitioned mesh: the fine-level sweeps act on the GLOBAL matrix (ghost entries of the iterate follow their owners);
-    // the coarse levels stay rank-local
-    if (c->nRanks > 1 && L.Aval == c->Aval.p) commHalo(c, const_cast<double*>(x), nullptr, BS);
+    // partitioned mesh: the sweeps of a distributed level act on the GLOBAL matrix of that level (ghost entries of the
+    // iterate follow their owners); replicated levels need no exchange
+    if (L.distributed && c->nRanks > 1) commHaloPlan(c, *L.plan, const_cast<double*>(x), nullptr, BS);
     SpmvEpi e;
     e.b = b;
     e.Dw = L.Dw.p;
@@ -672,9 +698,22 @@ void cycle(pfem_ctx* c, MgHierarchy& H, int l, const double* b, double* out) {
     }
     MgLevel& C = *H.lev[l + 1];
     launchSpmv<EPI_RESID>(c, L, BS, cur, L.t.p, b);
-    if (BS == 4) k_mg_restrict<4><<<divUp(L.nc * BS, 256), 256, 0, c->stream>>>(L.nc, L.aggPtr.p, L.aggNodes.p, L.t.p, C.b.p);
-    else k_mg_restrict<3><<<divUp(L.nc * BS, 256), 256, 0, c->stream>>>(L.nc, L.aggPtr.p, L.aggNodes.p, L.t.p, C.b.p);
-    LAUNCH_CHECK(c);
+    {
+        // my aggregates: all coarse rows, or rows [rowOff, rowOff + ncLocal) of a replicated next level (then all-gathered)
+        const int ncL = L.ncLocal;
+        double* dstB = C.b.p + (size_t)L.rowOff * BS;
+        if (ncL > 0) {
+            if (BS == 4) k_mg_restrict<4><<<divUp(ncL * BS, 256), 256, 0, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, L.t.p, dstB);
+            else k_mg_restrict<3><<<divUp(ncL * BS, 256), 256, 0, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, L.t.p, dstB);
+            LAUNCH_CHECK(c);
+        }
+        if (L.nextReplicated) {
+            std::vector<int64_t> cnt(L.rowCounts), dsp(L.rowDispls);
+            for (auto& v : cnt) v *= BS;
+            for (auto& v : dsp) v *= BS;
+            commAllGatherV(c, dstB, C.b.p, cnt, dsp);
+        }
+    }
     cycle(c, H, l + 1, C.b.p, C.xo.p);
     if (BS == 4) k_mg_prolong<4><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, C.xo.p, H.over, cur);
     else k_mg_prolong<3><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, C.xo.p, H.over, cur);
@@ -686,11 +725,18 @@ void cycle(pfem_ctx* c, MgHierarchy& H, int l, const double* b, double* out) {
     }
 }
 
-// one coarsening step; returns false when the level cannot be coarsened further
-bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSize) {
+// total size below which the next level is replicated on every rank (read at every symbolic build: tests change it)
+int mgReplicateNodes() { return getenv("PFEM_MG_REPL_NODES") ? atoi(getenv("PFEM_MG_REPL_NODES")) : 50000; }
+
+// Rank-local part of a coarsening step: aggregates of the OWNED nodes of L (grid cells over their coordinates), member
+// lists in ascending order, coarse coordinates written to Xc (4 doubles per aggregate).  Returns false when this rank's
+// share cannot be coarsened; nc = local aggregate count.
+bool localAggregate(pfem_ctx* c, MgHierarchy& H, MgLevel& L, double& cellSize, int& ncOut, DevBuf<double>& XcLocal) {
     const int dim = c->dim, n = L.n;
+    ncOut = 0;
+    if (n < 1) return false;
     const double target = dim == 3 ? 8.0 : 4.0;
-    c->scratchI.reserve((size_t)std::max(n, c->nNodes) + 64);
+    c->scratchI.reserve((size_t)std::max(L.nVec, c->nNodes) + 64);
     H.flag.reserve(16);
     DevBuf<double> box;
     box.reserve(8);
@@ -709,7 +755,7 @@ bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSi
     // cell edge: the caller's suggestion (twice the node spacing of this level), else twice the spacing of a filled box
     double Hc = cellSize > 0.0 ? cellSize : 2.0 * std::pow(vol / n, 1.0 / dim);
     const double slack = cellSize > 0.0 ? 3.0 : 1.7;  // a suggested size is only overridden when it is far off
-    L.agg.reserve(n);
+    L.agg.reserve((size_t)L.nVec + 4);
     DevBuf<int> key, cell;
     key.reserve(n);
     int nc = 0;
@@ -741,8 +787,6 @@ bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSi
     }
     if (nc < 1 || nc > 0.8 * n) return false;
     cellSize = Hc;
-    // members
-    L.nc = nc;
     L.aggPtr.reserve((size_t)nc + 2);
     L.aggNodes.reserve(n);
     CUDA_CHECK(cudaMemsetAsync(L.aggPtr.p, 0, ((size_t)nc + 2) * sizeof(int), c->stream));
@@ -752,37 +796,222 @@ bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSi
     CUDA_CHECK(cudaMemsetAsync(c->scratchI.p, 0, (size_t)nc * sizeof(int), c->stream));
     k_fill_members<<<divUp(n, 256), 256, 0, c->stream>>>(n, L.agg.p, L.aggPtr.p, c->scratchI.p, L.aggNodes.p);
     LAUNCH_CHECK(c);
-    C.XB.reserve((size_t)nc * 4);
-    k_sort_members<<<divUp(nc, 128), 128, 0, c->stream>>>(nc, dim, L.aggPtr.p, L.aggNodes.p, L.X, C.XB.p);
+    XcLocal.reserve((size_t)nc * 4 + 4);
+    k_sort_members<<<divUp(nc, 128), 128, 0, c->stream>>>(nc, dim, L.aggPtr.p, L.aggNodes.p, L.X, XcLocal.p);
     LAUNCH_CHECK(c);
-    // coarse pattern
-    C.n = C.nVec = nc;
-    C.nbrPtrB.reserve((size_t)nc + 2);
-    C.diagSlotB.reserve(nc);
-    CUDA_CHECK(cudaMemsetAsync(C.nbrPtrB.p, 0, ((size_t)nc + 2) * sizeof(int), c->stream));
-    CUDA_CHECK(cudaMemsetAsync(H.flag.p, 0, 4 * sizeof(int), c->stream));
-    k_coarse_nbr<false><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, n, L.nbrPtr, L.nbr, C.nbrPtrB.p,
-                                                            nullptr, nullptr, H.flag.p);
-    LAUNCH_CHECK(c);
-    exclusiveScanInt(c, C.nbrPtrB.p, nc + 1, H.flag.p + 2);
-    int hf[4];
-    CUDA_CHECK(cudaMemcpyAsync(hf, H.flag.p, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    if (hf[1] != 0) return false;  // a coarse row with more than NBR_CAP neighbours
-    C.maxNb = hf[0];
-    C.nBlocks = hf[2];
-    C.nbrB.reserve((size_t)C.nBlocks + 4);
-    k_coarse_nbr<true><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, n, L.nbrPtr, L.nbr, C.nbrPtrB.p,
-                                                           C.nbrB.p, C.diagSlotB.p, H.flag.p);
-    LAUNCH_CHECK(c);
-    L.cslot.reserve((size_t)L.nBlocks + 4);
-    k_cslot<<<divUp(n, 128), 128, 0, c->stream>>>(n, L.nbrPtr, L.nbr, L.agg.p, C.nbrPtrB.p, C.nbrB.p, L.cslot.p);
-    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // key/cell/box are released on return
+    ncOut = nc;
+    return true;
+}
+
+// one coarsening step; returns false when the level cannot be coarsened further.  On a partitioned mesh every decision
+// (coarsen or stop, keep the next level distributed or replicate it) is taken from all-gathered numbers, so that all ranks
+// build the same number of levels of the same kind and later issue the same sequence of collectives.
+bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSize) {
+    const int dim = c->dim, n = L.n, BS = dim + 1;
+    const bool multi = L.distributed && c->nRanks > 1;
+    int nc = 0;
+    DevBuf<double> XcLocal;
+    bool ok = localAggregate(c, H, L, cellSize, nc, XcLocal);
+    const int R = c->nRanks, me = c->rank;
+    std::vector<double> all(2 * (size_t)R, 0.0);
+    bool replicate = false;
+    int64_t ncGlobal = nc;
+    if (multi) {
+        const double mine[2] = {ok ? 1.0 : 0.0, (double)nc};
+        commAllGatherHost(c, mine, 2, all.data());
+        ncGlobal = 0;
+        for (int r = 0; r < R; ++r) {
+            ok = ok && all[2 * r] != 0.0;
+            ncGlobal += (int64_t)all[2 * r + 1];
+        }
+        replicate = ncGlobal <= mgReplicateNodes();
+    }
+    if (!ok) return false;
+    L.nextReplicated = false;
+    L.ncLocal = nc;
+    L.rowOff = 0;
+    H.flag.reserve(16);
+    int* misc = H.flag.p;
+    DevBuf<double> tmp;  // aggregate ids of the fine vector entries as doubles (halo exchange payload)
+
+    if (!multi) {
+        // ---- single rank, or a replicated level: the whole level is here ------------------------------------------------
+        L.nc = nc;
+        C.n = C.nVec = nc;
+        C.distributed = false;
+        C.plan = nullptr;
+        C.XB.reserve((size_t)nc * 4 + 4);
+        CUDA_CHECK(cudaMemcpyAsync(C.XB.p, XcLocal.p, (size_t)nc * 4 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        C.nbrPtrB.reserve((size_t)nc + 2);
+        C.diagSlotB.reserve(nc);
+        CUDA_CHECK(cudaMemsetAsync(C.nbrPtrB.p, 0, ((size_t)nc + 2) * sizeof(int), c->stream));
+        CUDA_CHECK(cudaMemsetAsync(misc, 0, 4 * sizeof(int), c->stream));
+        k_coarse_nbr<false><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, n, L.nbrPtr, L.nbr, C.nbrPtrB.p,
+                                                                nullptr, nullptr, misc, 0);
+        LAUNCH_CHECK(c);
+        exclusiveScanInt(c, C.nbrPtrB.p, nc + 1, misc + 2);
+        int hf[4];
+        CUDA_CHECK(cudaMemcpyAsync(hf, misc, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        if (hf[1] != 0) return false;  // a coarse row with more than NBR_CAP neighbours
+        C.maxNb = hf[0];
+        C.nBlocks = hf[2];
+        C.nbrB.reserve((size_t)C.nBlocks + 4);
+        k_coarse_nbr<true><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, n, L.nbrPtr, L.nbr, C.nbrPtrB.p,
+                                                               C.nbrB.p, C.diagSlotB.p, misc, 0);
+        LAUNCH_CHECK(c);
+        L.cslot.reserve((size_t)L.nBlocks + 4);
+        k_cslot<<<divUp(n, 128), 128, 0, c->stream>>>(n, L.nbrPtr, L.nbr, L.agg.p, C.nbrPtrB.p, C.nbrB.p, L.cslot.p);
+        LAUNCH_CHECK(c);
+    } else if (replicate) {
+        // ---- distributed level -> replicated next level ---------------------------------------------------------------------
+        L.rowCounts.assign(R, 0), L.rowDispls.assign(R, 0);
+        for (int r = 0; r < R; ++r) L.rowCounts[r] = (int64_t)all[2 * r + 1];
+        for (int r = 1; r < R; ++r) L.rowDispls[r] = L.rowDispls[r - 1] + L.rowCounts[r - 1];
+        const int ncG = (int)ncGlobal, off = (int)L.rowDispls[me];
+        L.nextReplicated = true;
+        L.rowOff = off;
+        L.nc = ncG;
+        // global aggregate ids: owned entries shifted by this rank's row offset, ghost entries from their owners
+        tmp.reserve((size_t)L.nVec + 4);
+        k_agg_shift_to_double<<<divUp(n, 256), 256, 0, c->stream>>>(n, L.agg.p, off, tmp.p);
+        LAUNCH_CHECK(c);
+        commHaloPlan(c, *L.plan, tmp.p, nullptr, 1);
+        if (L.nVec > n) {
+            k_double_to_int<<<divUp(L.nVec - n, 256), 256, 0, c->stream>>>(L.nVec - n, tmp.p + n, L.agg.p + n);
+            LAUNCH_CHECK(c);
+        }
+        C.n = C.nVec = ncG;
+        C.distributed = false;
+        C.plan = nullptr;
+        auto bytes = [&](const std::vector<int64_t>& v, int64_t unit) {
+            std::vector<int64_t> o(v);
+            for (auto& x : o) x *= unit;
+            return o;
+        };
+        // coarse coordinates
+        C.XB.reserve((size_t)ncG * 4 + 4);
+        commAllGatherV(c, XcLocal.p, C.XB.p, bytes(L.rowCounts, 4), bytes(L.rowDispls, 4));
+        // row lengths of my rows -> all ranks -> global row pointers
+        C.nbrPtrB.reserve((size_t)ncG + 2);
+        C.diagSlotB.reserve((size_t)ncG + 2);
+        CUDA_CHECK(cudaMemsetAsync(C.nbrPtrB.p, 0, ((size_t)ncG + 2) * sizeof(int), c->stream));
+        CUDA_CHECK(cudaMemsetAsync(misc, 0, 4 * sizeof(int), c->stream));
+        k_coarse_nbr<false><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, L.nVec, L.nbrPtr, L.nbr,
+                                                                C.nbrPtrB.p + off, nullptr, nullptr, misc, off);
+        LAUNCH_CHECK(c);
+        commAllGatherBytes(c, C.nbrPtrB.p + off, C.nbrPtrB.p, bytes(L.rowCounts, sizeof(int)), bytes(L.rowDispls, sizeof(int)));
+        exclusiveScanInt(c, C.nbrPtrB.p, ncG + 1, misc + 2);
+        int hf[4];
+        CUDA_CHECK(cudaMemcpyAsync(hf, misc, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<int> ptrHost((size_t)ncG + 1);
+        CUDA_CHECK(cudaMemcpyAsync(ptrHost.data(), C.nbrPtrB.p, ((size_t)ncG + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        const double mine2[2] = {(double)hf[0], (double)hf[1]};
+        std::vector<double> all2(2 * (size_t)R);
+        commAllGatherHost(c, mine2, 2, all2.data());
+        int maxNb = 0;
+        bool overflow = false;
+        for (int r = 0; r < R; ++r) {
+            maxNb = std::max(maxNb, (int)all2[2 * r]);
+            overflow = overflow || all2[2 * r + 1] != 0.0;
+        }
+        if (overflow) return false;
+        C.maxNb = maxNb;
+        C.nBlocks = hf[2];
+        L.blkCounts.assign(R, 0), L.blkDispls.assign(R, 0);
+        for (int r = 0; r < R; ++r) {
+            L.blkDispls[r] = ptrHost[L.rowDispls[r]];
+            L.blkCounts[r] = ptrHost[L.rowDispls[r] + L.rowCounts[r]] - ptrHost[L.rowDispls[r]];
+        }
+        C.nbrB.reserve((size_t)C.nBlocks + 4);
+        k_coarse_nbr<true><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, L.nVec, L.nbrPtr, L.nbr,
+                                                               C.nbrPtrB.p + off, C.nbrB.p, C.diagSlotB.p + off, misc, off);
+        LAUNCH_CHECK(c);
+        commAllGatherBytes(c, C.nbrB.p + L.blkDispls[me], C.nbrB.p, bytes(L.blkCounts, sizeof(int)), bytes(L.blkDispls, sizeof(int)));
+        commAllGatherBytes(c, C.diagSlotB.p + off, C.diagSlotB.p, bytes(L.rowCounts, sizeof(int)), bytes(L.rowDispls, sizeof(int)));
+        L.cslot.reserve((size_t)L.nBlocks + 4);
+        k_cslot<<<divUp(n, 128), 128, 0, c->stream>>>(n, L.nbrPtr, L.nbr, L.agg.p, C.nbrPtrB.p, C.nbrB.p, L.cslot.p, L.nVec);
+        LAUNCH_CHECK(c);
+    } else {
+        // ---- distributed level -> distributed next level: ghost aggregates + the next level's halo plan -----------------------
+        L.nc = nc;
+        tmp.reserve((size_t)L.nVec + 4);
+        k_agg_shift_to_double<<<divUp(n, 256), 256, 0, c->stream>>>(n, L.agg.p, 0, tmp.p);
+        LAUNCH_CHECK(c);
+        commHaloPlan(c, *L.plan, tmp.p, nullptr, 1);
+        std::vector<double> aggAll((size_t)L.nVec);
+        CUDA_CHECK(cudaMemcpyAsync(aggAll.data(), tmp.p, (size_t)L.nVec * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        C.ownPlan.reset(new HaloPlan());
+        C.ownPlan->sendIdx.accounting = C.ownPlan->sendBuf.accounting = &c->deviceBytes;
+        HaloPlan& CP = *C.ownPlan;
+        std::vector<int> ghostAgg((size_t)(L.nVec - n), 0);
+        int nGhostC = 0;
+        for (const auto& p : L.plan->peers) {
+            // what I receive: the distinct aggregates (owner-local ids) of the fine ghosts of this peer, ascending
+            std::vector<int> u;
+            u.reserve(p.recvCount);
+            for (int k = 0; k < p.recvCount; ++k) u.push_back((int)aggAll[(size_t)p.recvStart + k]);
+            std::sort(u.begin(), u.end());
+            u.erase(std::unique(u.begin(), u.end()), u.end());
+            for (int k = 0; k < p.recvCount; ++k) {
+                const int a = (int)aggAll[(size_t)p.recvStart + k];
+                ghostAgg[(size_t)p.recvStart - n + k] = nc + nGhostC + (int)(std::lower_bound(u.begin(), u.end(), a) - u.begin());
+            }
+            // what I send: the distinct aggregates of the fine nodes this peer holds as ghosts, ascending -- the same list
+            // the peer derives from the ids it received, so both sides agree on the order without another exchange
+            std::vector<int> sset;
+            sset.reserve(p.sendCount);
+            for (int k = 0; k < p.sendCount; ++k) sset.push_back((int)aggAll[(size_t)L.plan->sendIdxHost[(size_t)p.sendOff + k]]);
+            std::sort(sset.begin(), sset.end());
+            sset.erase(std::unique(sset.begin(), sset.end()), sset.end());
+            CP.peers.push_back({p.rank, (int)CP.sendIdxHost.size(), (int)sset.size(), nc + nGhostC, (int)u.size()});
+            CP.sendIdxHost.insert(CP.sendIdxHost.end(), sset.begin(), sset.end());
+            nGhostC += (int)u.size();
+        }
+        commFinishPlan(c, CP);
+        if (L.nVec > n)
+            CUDA_CHECK(cudaMemcpyAsync(L.agg.p + n, ghostAgg.data(), (size_t)(L.nVec - n) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        C.n = nc;
+        C.nVec = nc + nGhostC;
+        C.distributed = true;
+        C.plan = C.ownPlan.get();
+        C.XB.reserve((size_t)C.nVec * 4 + 4);
+        CUDA_CHECK(cudaMemsetAsync(C.XB.p, 0, ((size_t)C.nVec * 4) * sizeof(double), c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(C.XB.p, XcLocal.p, (size_t)nc * 4 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        C.nbrPtrB.reserve((size_t)nc + 2);
+        C.diagSlotB.reserve(nc);
+        CUDA_CHECK(cudaMemsetAsync(C.nbrPtrB.p, 0, ((size_t)nc + 2) * sizeof(int), c->stream));
+        CUDA_CHECK(cudaMemsetAsync(misc, 0, 4 * sizeof(int), c->stream));
+        k_coarse_nbr<false><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, L.nVec, L.nbrPtr, L.nbr,
+                                                                C.nbrPtrB.p, nullptr, nullptr, misc, 0);
+        LAUNCH_CHECK(c);
+        exclusiveScanInt(c, C.nbrPtrB.p, nc + 1, misc + 2);
+        int hf[4];
+        CUDA_CHECK(cudaMemcpyAsync(hf, misc, 4 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        const double mine2[2] = {(double)hf[0], (double)hf[1]};
+        std::vector<double> all2(2 * (size_t)R);
+        commAllGatherHost(c, mine2, 2, all2.data());
+        bool overflow = false;
+        for (int r = 0; r < R; ++r) overflow = overflow || all2[2 * r + 1] != 0.0;
+        if (overflow) return false;
+        C.maxNb = hf[0];
+        C.nBlocks = hf[2];
+        C.nbrB.reserve((size_t)C.nBlocks + 4);
+        k_coarse_nbr<true><<<divUp(nc, 8), 256, 0, c->stream>>>(nc, L.aggPtr.p, L.aggNodes.p, L.agg.p, L.nVec, L.nbrPtr, L.nbr,
+                                                               C.nbrPtrB.p, C.nbrB.p, C.diagSlotB.p, misc, 0);
+        LAUNCH_CHECK(c);
+        L.cslot.reserve((size_t)L.nBlocks + 4);
+        k_cslot<<<divUp(n, 128), 128, 0, c->stream>>>(n, L.nbrPtr, L.nbr, L.agg.p, C.nbrPtrB.p, C.nbrB.p, L.cslot.p, L.nVec);
+        LAUNCH_CHECK(c);
+    }
     C.nbrPtr = C.nbrPtrB.p, C.nbr = C.nbrB.p, C.diagSlot = C.diagSlotB.p, C.X = C.XB.p;
-    const int BS = dim + 1;
     C.AvalB.reserve((size_t)C.nBlocks * BS * BS + 8);
     C.Aval = C.AvalB.p;
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));  // key/cell/box are released on return
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
     return true;
 }
 
@@ -804,6 +1033,8 @@ void buildSymbolic(pfem_ctx* c, MgHierarchy& H) {
     H.symbolicFailed = false;
     auto L0 = std::make_unique<MgLevel>();
     L0->n = c->nRows, L0->nVec = c->nNodes, L0->maxNb = c->maxNb, L0->nBlocks = c->nBlocks;
+    L0->distributed = c->nRanks > 1;
+    L0->plan = &c->plan;
     H.lev.push_back(std::move(L0));
     // node spacing of level 0 from the mean element size: h0 = (mean |detJ|)^(1/dim)
     double cellSize = 0.0;
@@ -826,7 +1057,7 @@ void buildSymbolic(pfem_ctx* c, MgHierarchy& H) {
             L.nbrPtr = c->nbrPtr.p, L.nbr = c->nbr.p, L.diagSlot = c->diagSlot.p, L.Aval = c->Aval.p, L.X = c->X4.p;
         }
         allocVectors(c, L, BS);
-        if (L.n <= COARSEST_NODES) break;
+        if (!L.distributed && L.n <= COARSEST_NODES) break;  // (a distributed level's size is a per-rank number: coarsen() decides)
         auto C = std::make_unique<MgLevel>();
         if (!coarsen(c, H, L, *C, cellSize)) break;
         cellSize *= 2.0;
@@ -844,7 +1075,7 @@ void blockInverse(pfem_ctx* c, MgLevel& L, int BS, bool l1 = false, double theta
     LAUNCH_CHECK(c);
     if (!l1) return;
     static const double wcap = getenv("PFEM_MG_WCAP") ? atof(getenv("PFEM_MG_WCAP")) : 1.0;
-    // level 0 of a partitioned mesh: ghost columns carry no diagonal here; their scale stays 1 (set at allocation)
+    // distributed level: the scales of the ghost columns come from their owners (halo exchange below)
     if (L.sc.cap < (size_t)L.nVec * BS + 8) {
         L.sc.reserve((size_t)L.nVec * BS + 8);
         std::vector<double> ones(L.sc.cap, 1.0);
@@ -854,10 +1085,12 @@ void blockInverse(pfem_ctx* c, MgLevel& L, int BS, bool l1 = false, double theta
     if (BS == 4) {
         k_mg_diag_scale<4><<<divUp(L.n * BS, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, L.sc.p);
         LAUNCH_CHECK(c);
+        if (L.distributed && c->nRanks > 1) commHaloPlan(c, *L.plan, L.sc.p, nullptr, BS);  // scales of the ghost columns
         k_mg_l1_scale<4><<<divUp((int64_t)L.n * 16, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, L.sc.p, theta, wcap, L.Dw.p, nullptr);
     } else {
         k_mg_diag_scale<3><<<divUp(L.n * BS, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, L.sc.p);
         LAUNCH_CHECK(c);
+        if (L.distributed && c->nRanks > 1) commHaloPlan(c, *L.plan, L.sc.p, nullptr, BS);
         k_mg_l1_scale<3><<<divUp((int64_t)L.n * 16, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, L.sc.p, theta, wcap, L.Dw.p, nullptr);
     }
     LAUNCH_CHECK(c);
@@ -914,7 +1147,7 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
             k_to_float<<<std::max(1, std::min(c->smCount * 8, divUp((int64_t)nv, 1024))), 256, 0, c->stream>>>(nv, L.Aval, L.Af.p);
             LAUNCH_CHECK(c);
         }
-        if (dampMode == 0) {
+        if (dampMode == 0 || c->nRanks > 1) {  // (the tuned ladder takes per-rank decisions: not on a partitioned mesh)
             L.omega = H.fixedOmega > 0.0 ? H.fixedOmega : 2.0;  // theta: 2.0 measured best-robust (2.5 turns unstable in 2-D)
             blockInverse(c, L, BS, true, L.omega);
         } else if (H.fixedOmega > 0.0 || dampMode == 1) {
@@ -931,16 +1164,26 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
         const int nbcap = std::max(C.maxNb, 1);
         const int hwPerBlock = std::max(1, std::min(8, (int)((96 * 1024) / ((size_t)nbcap * BB * sizeof(double)))));
         const size_t smem = (size_t)hwPerBlock * nbcap * BB * sizeof(double);
-        if (BS == 4) {
-            if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_galerkin<4><<<divUp(L.nc, hwPerBlock), hwPerBlock * 16, smem, c->stream>>>(L.nc, L.aggPtr.p, L.aggNodes.p, L.nbrPtr, L.Aval,
-                                                                                       L.cslot.p, C.nbrPtr, C.AvalB.p, nbcap);
-        } else {
-            if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k_galerkin<3><<<divUp(L.nc, hwPerBlock), hwPerBlock * 16, smem, c->stream>>>(L.nc, L.aggPtr.p, L.aggNodes.p, L.nbrPtr, L.Aval,
-                                                                                       L.cslot.p, C.nbrPtr, C.AvalB.p, nbcap);
+        const int ncL = L.ncLocal;  // my aggregates = the coarse rows I sum (all of them unless the next level is replicated)
+        const int* cPtrMine = C.nbrPtr + L.rowOff;
+        if (ncL > 0) {
+            if (BS == 4) {
+                if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_galerkin<4><<<divUp(ncL, hwPerBlock), hwPerBlock * 16, smem, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, L.nbrPtr, L.Aval,
+                                                                                          L.cslot.p, cPtrMine, C.AvalB.p, nbcap);
+            } else {
+                if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_galerkin<3><<<divUp(ncL, hwPerBlock), hwPerBlock * 16, smem, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, L.nbrPtr, L.Aval,
+                                                                                          L.cslot.p, cPtrMine, C.AvalB.p, nbcap);
+            }
+            LAUNCH_CHECK(c);
         }
-        LAUNCH_CHECK(c);
+        if (L.nextReplicated) {  // every rank gets every row of the replicated level
+            std::vector<int64_t> cnt(L.blkCounts), dsp(L.blkDispls);
+            for (auto& v : cnt) v *= BB;
+            for (auto& v : dsp) v *= BB;
+            commAllGatherV(c, C.AvalB.p + (size_t)L.blkDispls[c->rank] * BB, C.AvalB.p, cnt, dsp);
+        }
     }
     // coarsest level: dense inverse when it is small enough
     MgLevel& Lc = *H.lev.back();

@@ -248,8 +248,7 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     c->nNodes = nNodes;
     c->nElems = nElems;
     c->nRows = nNodes;  // until pfem_set_partition narrows it to the owned nodes
-    c->peers.clear();
-    c->nSendTotal = 0;
+    c->plan.clear();
     c->nFacets = c->nFstNodes = 0;  // facets belong to the previous mesh (pfem_set_facets)
     c->haveTopology = false;
     c->haveSystem = c->haveSolution = c->haveQprev = c->haveSnapshot = c->havePositions = c->haveDirichlet = false;

@@ -190,6 +190,8 @@ template <int DIM, int LPN> struct ElemStream {
     }
 };
 
+// max that keeps a NaN operand (fmax drops it): a NaN velocity/density must reach the CFL minimum (Solver.cpp:228-232)
+__device__ __forceinline__ double nanMax(double a, double b) { return (a > b || a != a) ? a : b; }
 template <int N> __device__ __forceinline__ double pick(const double (&a)[N], int idx) {
     double t = a[0];
 #pragma unroll
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const doub
             if (DIM == 3) u2 += vn[2] * vn[2];
             const double c2 = (a.K0 + a.K0p * xq[3]) / vp[3];
             const double alpha = a.mu / vp[3];
-            *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(fmax(u2, c2), alpha * alpha);
+            *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(nanMax(u2, c2), alpha * alpha);
         }
     }
 }
@@ -642,7 +644,7 @@ __global__ void __launch_bounds__(256) k_wc_mom_node(const WcArgs a, const doubl
         if (DIM == 3) u2 += vn[2] * vn[2];
         const double c2 = (a.K0 + a.K0p * xq[3]) / vp[3];
         const double alpha = a.mu / vp[3];
-        *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(fmax(u2, c2), alpha * alpha);
+        *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(nanMax(u2, c2), alpha * alpha);
     }
 }
 
@@ -920,12 +922,12 @@ __global__ void __launch_bounds__(256) k_wc_dt(int nElems, const int* __restrict
             if (DIM == 3) u2 += v23.x * v23.x;
             const double c2 = (K0 + K0p * x23.y) / v23.y;
             const double alpha = mu / v23.y;
-            mx = fmax(fmax(u2, c2), mx);
-            alphaMax = fmax(alphaMax, alpha * alpha);
+            mx = nanMax(nanMax(u2, c2), mx);
+            alphaMax = nanMax(alpha * alpha, alphaMax);
         }
         const double he = elemHe<DIM>(px);
         // max over nodes of max(u2, c2, 4 alpha^2/he^2): he is per element, so the alpha term can be taken outside
-        mx = fmax(mx, 4 * alphaMax / (he * he));
+        mx = nanMax(4 * alphaMax / (he * he), mx);
         const double cand = sc2 * he * he / mx;
         best = (cand < best || cand != cand) ? cand : best;  // NaN propagates (Solver.cpp:231-232)
     }
@@ -959,7 +961,7 @@ __global__ void k_wc_cfl_nodes(int first, int count, int dim, const double* __re
     if (dim == 3) u2 += vp[2] * vp[2];
     const double c2 = (K0 + K0p * X4[(size_t)i * 4 + 3]) / vp[3];
     const double alpha = mu / vp[3];
-    *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(fmax(u2, c2), alpha * alpha);
+    *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(nanMax(u2, c2), alpha * alpha);
 }
 
 // CFL after a two-pass step: he was stored by k_wc_cont_elem (the mesh has not moved since), max(u^2, c^2) and alpha^2 per
@@ -983,10 +985,10 @@ __global__ void __launch_bounds__(256) k_wc_dt_fast(int nElems, const int* __res
 #pragma unroll
         for (int m = 0; m < NPE; ++m) {
             const double2 c = ld2(cfl2 + (size_t)nd[m] * 2);
-            mx = fmax(c.x, mx);
-            alphaMax = fmax(alphaMax, c.y);
+            mx = nanMax(c.x, mx);
+            alphaMax = nanMax(c.y, alphaMax);
         }
-        mx = fmax(mx, 4 * alphaMax / (he * he));
+        mx = nanMax(4 * alphaMax / (he * he), mx);
         const double cand = sc2 * he * he / mx;
         best = (cand < best || cand != cand) ? cand : best;
     }
@@ -1055,7 +1057,9 @@ __global__ void k_dt_chain(const double* __restrict__ partial, int n, double max
             const double o = sh[k];
             best = (o < best || o != o) ? o : best;
         }
-        const double dtNew = fmin(sqrt(best), maxDT);
+        // fmin would return maxDT for a NaN minimum: flag it first, like the reference's "NaN time step!" (Solver.cpp:228-232)
+        const double root = sqrt(best);
+        const double dtNew = (root != root) ? root : fmin(root, maxDT);
         dtDev[1] += dtDev[0];
         if (dtNew != dtNew) dtDev[2] = 1.0;
         dtDev[0] = dtNew;
@@ -1254,7 +1258,8 @@ int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double 
     CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p + SC_COUNT - 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     const double ts = c->hScal[0];
-    const double dt = fmin(sqrt(ts), maxDT);  // Solver.cpp:228
+    const double root = sqrt(ts);
+    const double dt = (root != root) ? root : fmin(root, maxDT);  // Solver.cpp:228; a NaN minimum stays NaN
     *dtOut = dt;
     return (dt != dt || ts != ts) ? PFEM_NAN : PFEM_OK;
 }

@@ -24,7 +24,8 @@ from .meshgen import Mesh
 
 
 def rcb_owner(coords: np.ndarray, n_ranks: int) -> np.ndarray:
-    """Recursive coordinate bisection: rank id per point.  Deterministic (stable argsort on the widest axis)."""
+    """Recursive coordinate bisection: rank id per point.  Deterministic: points are ordered along the widest axis by
+    (coordinate, point index), the same total order csrc/partition.cu selects with."""
     n = coords.shape[0]
     owner = np.zeros(n, dtype=np.int32)
 
@@ -34,7 +35,7 @@ def rcb_owner(coords: np.ndarray, n_ranks: int) -> np.ndarray:
             return
         pts = coords[idx]
         axis = int(np.argmax(pts.max(axis=0) - pts.min(axis=0))) if idx.size else 0
-        order = np.argsort(pts[:, axis], kind="stable")
+        order = np.lexsort((idx, pts[:, axis]))         # total order (coordinate, node index): no dependence on tie handling
         nl = nr // 2
         cut = (idx.size * nl) // nr
         split(idx[order[:cut]], r0, nl)
@@ -121,6 +122,36 @@ def partition_mesh(mesh: Mesh, n_ranks: int, rank: int, owner: np.ndarray | None
         sel = np.flatnonzero(gowner == p)
         part.recv_start.append(int(owned.size + (sel[0] if sel.size else 0)))
         part.recv_count.append(int(sel.size))
+    return part
+
+
+def partition_mesh_native(mesh: Mesh, n_ranks: int, rank: int, handle=None) -> LocalPart:
+    """The same partition computed by the library (csrc/partition.cu: pfem_partition_*, C++/OpenMP) -- what the shim and the
+    bench use; `partition_mesh` above is the numpy statement the tests compare it with."""
+    from .capi import NativePartition
+
+    own = handle is None
+    h = handle or NativePartition(mesh.dim, mesh.conn, mesh.x, n_ranks)
+    try:
+        d = h.local(rank)
+    finally:
+        if own:
+            h.close()
+    dim, nn = mesh.dim, mesh.n_nodes
+    l2g = d["l2g_nodes"]
+    xg = mesh.x.reshape(dim, nn)
+    dv = mesh.dir_val.reshape(dim, nn)
+    lmesh = Mesh(dim=dim, x=np.ascontiguousarray(xg[:, l2g]).reshape(-1), conn=d["conn"].astype(np.int64),
+                 flags=np.ascontiguousarray(mesh.flags[l2g]), dir_mask=np.ascontiguousarray(mesh.dir_mask[l2g]),
+                 dir_val=np.ascontiguousarray(dv[:, l2g]).reshape(-1), n_cells=mesh.n_cells, meta=dict(mesh.meta))
+    part = LocalPart(rank=rank, n_ranks=n_ranks, mesh=lmesh, n_owned=d["n_owned"], l2g_nodes=l2g, l2g_elems=d["l2g_elems"],
+                     elem_primary=None)
+    so = d["send_offsets"]
+    for k, p in enumerate(d["peers"]):
+        part.peers.append(int(p))
+        part.send_idx.append(d["send_idx"][so[k]:so[k + 1]].astype(np.int32))
+        part.recv_start.append(int(d["recv_start"][k]))
+        part.recv_count.append(int(d["recv_count"][k]))
     return part
 
 
