@@ -122,6 +122,7 @@ struct pfem_ctx {
     int maskWords = 1;
     DevBuf<unsigned> rowDir;   // per node: bit s = neighbour slot s is a Dirichlet node (rebuilt when topology/BC change)
     bool rowDirDirty = true;
+    DevBuf<int> nodeHdr;       // per node int4 (n2ePtr, nbrPtr, ne | nb<<8 | diagSlot<<16 | flags<<24, rowDir word 0): one load per node
     DevBuf<int> scratchI;      // counters / cursors
     DevBuf<int> scanScratch;   // tile sums of exclusiveScanInt
     DevBuf<unsigned long long> stage64;
@@ -207,6 +208,7 @@ struct pfem_ctx {
         n2eSlots.accounting = &deviceBytes;
         blkMask.accounting = &deviceBytes;
         rowDir.accounting = &deviceBytes;
+        nodeHdr.accounting = &deviceBytes;
     }
 };
 
