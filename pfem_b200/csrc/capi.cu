@@ -112,6 +112,9 @@ int pfem_destroy(pfem_ctx* c) {
     }
     for (auto e : c->eventPool) cudaEventDestroy(e);
     if (c->hScal) cudaFreeHost(c->hScal);
+    if (c->commStream) cudaStreamDestroy(c->commStream);
+    if (c->evTile) cudaEventDestroy(c->evTile);
+    if (c->evHalo) cudaEventDestroy(c->evHalo);
     cudaStream_t s = c->ownStream;
     delete c;
     if (s) cudaStreamDestroy(s);
@@ -300,8 +303,9 @@ int pfem_pspg_matvec(pfem_ctx* c, const double* x, double* y) {
 
 int pfem_wc_set_variant(pfem_ctx* c, int variant) {
     API_BEGIN(c)
-    PFEM_REQUIRE(variant == 0 || variant == 6 || variant == 7 || variant == 11 || variant == 12, PFEM_ERR_INVALID,
-                 "wc_set_variant: 0 (by size), 6 (gather), 7 (staged gather), 11 (two-pass), 12 (two-pass continuity + gather momentum)");
+    PFEM_REQUIRE(variant == 0 || variant == 6 || variant == 7 || variant == 11 || variant == 12 || variant == 13, PFEM_ERR_INVALID,
+                 "wc_set_variant: 0 (by size), 6 (gather), 7 (staged gather), 11 (two-pass), 12 (two-pass continuity + gather momentum), "
+                 "13 (tiles: element records in shared memory)");
     c->wcVariant = variant;
     API_END(c)
 }

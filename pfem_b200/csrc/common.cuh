@@ -165,9 +165,16 @@ struct pfem_ctx {
     DevBuf<double> wcElemRec;  // two-pass explicit step: per-(local node, element) momentum records
     DevBuf<double> wcContRec;  // per-element continuity record (alpha, beta, V/NPE, he)
     DevBuf<double> wcCfl2;     // per node (max(u^2, c^2), alpha^2) of the state the last two-pass step produced
+    DevBuf<double> wcHmin;     // per node: smallest he = 2 r_in among its incident elements (mesh of the last two-pass step)
     int wcVariant = 0;         // pfem_wc_set_variant: 0 = by size (PFEM_WC_CFG), 6 gather, 11 two-pass, 12 mixed
     bool cflFresh = false;     // wcContRec.he / wcCfl2 describe the current positions and states
-    bool tilesValid = false;   // node tiles of the fused explicit step (wc_tile.cu) match the current topology/partition
+    bool tilesValid = false;   // node tiles of the fused explicit step (wc_tile.cuh) match the current topology/partition
+    int tileT = 0, nTiles = 0, nIfaceTiles = 0, tileCap = 0;  // nodes per tile, tiles, tiles holding interface nodes, max elements per tile
+    DevBuf<int> tilePerm, tileNePrefix, tileElems, tileCnt, tileKey;
+    DevBuf<unsigned short> tileIdx16;
+    DevBuf<uint8_t> tileIface;
+    cudaStream_t commStream = nullptr;  // halo exchanges that overlap the interior tiles (partitioned explicit step)
+    cudaEvent_t evTile = nullptr, evHalo = nullptr;
     double cflMu = 0, cflK0 = 0, cflK0p = 0;
 
     // ---- free-surface facets / surface tension (facets.cu) ----
@@ -200,6 +207,7 @@ struct pfem_ctx {
         wcElemRec.accounting = &deviceBytes;
         wcContRec.accounting = &deviceBytes;
         wcCfl2.accounting = &deviceBytes;
+        wcHmin.accounting = &deviceBytes;
         for (auto* b : {&flags, &dirMask, &stageB}) b->accounting = &deviceBytes;
         for (auto* b : {&dirVal4, &stageD, &X4, &Xsave4, &V4, &A4, &VP4, &X4b, &V4b, &Aval, &bvec, &dinv, &Wblk, &kx, &kr, &kr0,
                         &kp, &kp2, &kv, &ks, &kt, &kph, &ksh, &partial, &scal, &cscVal, &dtPartial, &plan.sendBuf, &commScratch})
@@ -209,6 +217,9 @@ struct pfem_ctx {
         blkMask.accounting = &deviceBytes;
         rowDir.accounting = &deviceBytes;
         nodeHdr.accounting = &deviceBytes;
+        for (auto* b : {&tilePerm, &tileNePrefix, &tileElems, &tileCnt, &tileKey}) b->accounting = &deviceBytes;
+        tileIdx16.accounting = &deviceBytes;
+        tileIface.accounting = &deviceBytes;
     }
 };
 

@@ -249,6 +249,7 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     c->nElems = nElems;
     c->nRows = nNodes;  // until pfem_set_partition narrows it to the owned nodes
     c->plan.clear();
+    c->tilesValid = false;
     c->nFacets = c->nFstNodes = 0;  // facets belong to the previous mesh (pfem_set_facets)
     c->haveTopology = false;
     c->haveSystem = c->haveSolution = c->haveQprev = c->haveSnapshot = c->havePositions = c->haveDirichlet = false;

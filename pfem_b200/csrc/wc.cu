@@ -198,6 +198,13 @@ template <int N> __device__ __forceinline__ double pick(const double (&a)[N], in
     for (int m = 1; m < N; ++m) t = (idx == m) ? a[m] : t;
     return t;
 }
+// min that keeps a NaN operand
+__device__ __forceinline__ double nanMin(double a, double b) { return (a < b || a != a) ? a : b; }
+template <int LPN> __device__ __forceinline__ double groupMin(double v) {
+#pragma unroll
+    for (int o = LPN / 2; o > 0; o >>= 1) v = nanMin(__shfl_xor_sync(0xffffffffu, v, o), v);
+    return v;
+}
 template <int LPN> __device__ __forceinline__ double groupSum(double v) {
 #pragma unroll
     for (int o = LPN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -488,11 +495,11 @@ __global__ void __launch_bounds__(256, MINB) k_wc_cont_elem(int nElems, const in
 template <int DIM, int LPN>
 __global__ void __launch_bounds__(256) k_wc_cont_node(const WcArgs a, const double* __restrict__ rec, const double* __restrict__ X4,
                                                       const double* __restrict__ V4, double* __restrict__ X4n,
-                                                      double* __restrict__ V4n) {
+                                                      double* __restrict__ V4n, double* __restrict__ hminOut) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = t / LPN, sub = t % LPN;
     const bool valid = i < a.nNodes;
-    double m = 0, F0 = 0;
+    double m = 0, F0 = 0, hmin = 1.7976931348623157e308;
     if (valid) {
         const int eb = a.n2ePtr[i], end = a.n2ePtr[i + 1];
         const double pi = X4[(size_t)i * 4 + 3];
@@ -500,11 +507,14 @@ __global__ void __launch_bounds__(256) k_wc_cont_node(const WcArgs a, const doub
             const D4 r = ld4(rec + (size_t)__ldg(a.n2e + pos) * 4);
             F0 += r.x + r.y * pi;
             m += r.z;
+            hmin = nanMin(r.w, hmin);  // smallest he = 2 r_in among the incident elements: the nodal CFL pass (k_wc_dt_nodal)
         }
     }
     m = groupSum<LPN>(m);
     F0 = groupSum<LPN>(F0);
+    hmin = groupMin<LPN>(hmin);
     if (valid && sub == 0) {
+        hminOut[i] = hmin;
         const bool isFree = a.flags[i] & PFEM_NODE_FREE;
         double inv = 1.0 / m;
         if (isFree) {
@@ -950,64 +960,36 @@ __global__ void __launch_bounds__(256) k_wc_dt(int nElems, const int* __restrict
         if (lane == 0) partial[blockIdx.x] = b2;
     }
 }
-// nodal CFL quantities for nodes [first, first+count): the ghost nodes of a partitioned mesh, whose new states arrive by halo
-__global__ void k_wc_cfl_nodes(int first, int count, int dim, const double* __restrict__ X4, const double* __restrict__ V4,
-                               double mu, double K0, double K0p, double* __restrict__ cfl2) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    const int i = first + t;
-    const double* vp = V4 + (size_t)i * 4;
-    double u2 = vp[0] * vp[0] + vp[1] * vp[1];
-    if (dim == 3) u2 += vp[2] * vp[2];
-    const double c2 = (K0 + K0p * X4[(size_t)i * 4 + 3]) / vp[3];
-    const double alpha = mu / vp[3];
-    *reinterpret_cast<double2*>(cfl2 + (size_t)i * 2) = make_double2(nanMax(u2, c2), alpha * alpha);
-}
-
-// CFL after a two-pass step: he was stored by k_wc_cont_elem (the mesh has not moved since), max(u^2, c^2) and alpha^2 per
-// node by k_wc_mom_node (24x fewer divisions than per element-node visit) -- same candidates, same minimum.
-template <int DIM>
-__global__ void __launch_bounds__(256) k_wc_dt_fast(int nElems, const int* __restrict__ conn, const double* __restrict__ contRec,
-                                                    const double* __restrict__ cfl2, double sc2, double* __restrict__ partial) {
-    constexpr int NPE = DIM + 1;
+// CFL after a two-pass / tile step, NODAL form.  The reference takes, per element, he^2 over the largest nodal
+// max(u^2, c^2, 4 alpha^2/he^2) and then the minimum over the elements (Solver.cpp:200-226).  Dividing by a maximum is the
+// minimum of the quotients, so the same set of candidates is   min over (element e, node n of e) of
+//     ((s^2 he) he) / w_n      and      ((s^2 he) he) / (4 alpha_n^2 / (he he)),
+// and every floating-point operation in them is monotone in he: for a fixed node the smallest candidate is the one of its
+// smallest incident he.  So the pass runs over NODES with hmin_n = min_{e containing n} he_e (stored by the continuity node
+// pass) and the nodal w_n, alpha_n^2 (stored by the momentum epilogue): same candidates, same minimum, bit for bit, without
+// touching the connectivity.  On a partitioned mesh every rank covers its owned nodes (all their elements are local).
+__global__ void __launch_bounds__(256) k_wc_dt_nodal(int nRows, const double* __restrict__ hmin, const double* __restrict__ cfl2,
+                                                     double sc2, double* __restrict__ partial) {
     double best = 1.7976931348623157e308;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nElems; e += gridDim.x * blockDim.x) {
-        int nd[NPE];
-        if constexpr (DIM == 3) {
-            const int4 q = __ldg(reinterpret_cast<const int4*>(conn + (size_t)e * 4));
-            nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
-        } else {
-#pragma unroll
-            for (int m = 0; m < NPE; ++m) nd[m] = __ldg(conn + (size_t)e * NPE + m);
-        }
-        const double he = contRec[(size_t)e * 4 + 3];
-        double mx = 0, alphaMax = 0;
-#pragma unroll
-        for (int m = 0; m < NPE; ++m) {
-            const double2 c = ld2(cfl2 + (size_t)nd[m] * 2);
-            mx = nanMax(c.x, mx);
-            alphaMax = nanMax(c.y, alphaMax);
-        }
-        mx = nanMax(4 * alphaMax / (he * he), mx);
-        const double cand = sc2 * he * he / mx;
-        best = (cand < best || cand != cand) ? cand : best;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nRows; i += gridDim.x * blockDim.x) {
+        const double he = hmin[i];
+        if (he == 1.7976931348623157e308) continue;  // node without elements: no candidate
+        const double2 c = ld2(cfl2 + (size_t)i * 2);
+        const double x = sc2 * he * he;
+        const double c1 = x / c.x, c2 = x / (4 * c.y / (he * he));
+        const double cand = nanMin(c1, c2);
+        best = nanMin(cand, best);
     }
     __shared__ double sh[32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = (other < best || other != other) ? other : best;
-    }
+    for (int o = 16; o > 0; o >>= 1) best = nanMin(__shfl_xor_sync(0xffffffffu, best, o), best);
     if (lane == 0) sh[w] = best;
     __syncthreads();
     if (w == 0) {
         double b2 = lane < (blockDim.x >> 5) ? sh[lane] : 1.7976931348623157e308;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double other = __shfl_xor_sync(0xffffffffu, b2, o);
-            b2 = (other < b2 || other != other) ? other : b2;
-        }
+        for (int o = 16; o > 0; o >>= 1) b2 = nanMin(__shfl_xor_sync(0xffffffffu, b2, o), b2);
         if (lane == 0) partial[blockIdx.x] = b2;
     }
 }
@@ -1066,6 +1048,110 @@ __global__ void k_dt_chain(const double* __restrict__ partial, int n, double max
     }
 }
 
+#include "wc_tile.cuh"
+
+// (re)build the node tiles of the fused explicit step for the current topology / partition (per remesh)
+void buildTiles(pfem_ctx* c) {
+    PhaseScope ph(c, "Build tiles");
+    const int n = c->nRows, dim = c->dim, npe = dim + 1;
+    static const int envT = getenv("PFEM_WC_TILE") ? atoi(getenv("PFEM_WC_TILE")) : 64;
+    int T = std::max(8, std::min(64, envT));
+    const int maxE = std::max(c->maxE, 1);
+    while (T > 8 && (int64_t)T * maxE > 8192) T >>= 1;
+    PFEM_REQUIRE((int64_t)T * maxE <= 16384, PFEM_ERR_INVALID, "wc tiles: node valence too large");
+    // bounding box of the owned nodes -> uniform grid with ~64 nodes per cell (locality only: any grouping is correct)
+    c->scal.reserve(SC_COUNT);
+    double* boxDev = c->scal.p;
+    k_tile_bbox<<<1, 1024, 0, c->stream>>>(c->X4.p, n, dim, boxDev);
+    LAUNCH_CHECK(c);
+    double hb[6];
+    CUDA_CHECK(cudaMemcpyAsync(hb, boxDev, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    double ext[3] = {0, 0, 0}, vol = 1.0, maxExt = 0.0;
+    for (int d = 0; d < dim; ++d) {
+        ext[d] = std::max(hb[3 + d] - hb[d], 0.0);
+        maxExt = std::max(maxExt, ext[d]);
+    }
+    if (!(maxExt > 0.0)) maxExt = 1.0;
+    for (int d = 0; d < dim; ++d) vol *= std::max(ext[d], 1e-3 * maxExt);
+    double Hc = std::pow(vol / std::max(n, 1) * 64.0, 1.0 / dim);
+    int nx, ny, nz;
+    for (;;) {
+        nx = (int)std::floor(ext[0] / Hc) + 1;
+        ny = (int)std::floor(ext[1] / Hc) + 1;
+        nz = dim == 3 ? (int)std::floor(ext[2] / Hc) + 1 : 1;
+        if ((double)nx * ny * nz <= 8.0e6) break;
+        Hc *= 1.5;
+    }
+    const int nCells = nx * ny * nz, nBins = 2 * nCells;
+    c->tileIface.reserve((size_t)c->nNodes + 4);
+    CUDA_CHECK(cudaMemsetAsync(c->tileIface.p, 0, (size_t)c->nNodes, c->stream));
+    if (c->nRanks > 1 && c->plan.nSendTotal > 0) {
+        k_tile_mark<<<divUp(c->plan.nSendTotal, 256), 256, 0, c->stream>>>(c->plan.sendIdx.p, c->plan.nSendTotal, c->tileIface.p);
+        LAUNCH_CHECK(c);
+    }
+    c->tileKey.reserve((size_t)n + (size_t)2 * nBins + 16);
+    int* key = c->tileKey.p;
+    int* binPtr = key + n;               // nBins + 1
+    int* cursor = binPtr + nBins + 2;    // nBins
+    CUDA_CHECK(cudaMemsetAsync(binPtr, 0, ((size_t)2 * nBins + 8) * sizeof(int), c->stream));
+    c->tilePerm.reserve((size_t)n + 4);
+    c->tileNePrefix.reserve((size_t)n + 4);
+    if (n > 0) {
+        k_tile_key<<<divUp(n, 256), 256, 0, c->stream>>>(c->X4.p, n, dim, hb[0], hb[1], hb[2], 1.0 / Hc, nx, ny, nz, c->tileIface.p, key, binPtr);
+        LAUNCH_CHECK(c);
+    }
+    exclusiveScanInt(c, binPtr, nBins + 1, nullptr);
+    if (n > 0) {
+        k_tile_fill<<<divUp(n, 256), 256, 0, c->stream>>>(n, key, binPtr, cursor, c->tilePerm.p);
+        LAUNCH_CHECK(c);
+        k_tile_sort_bins<<<divUp(nBins, 128), 128, 0, c->stream>>>(nBins, binPtr, c->tilePerm.p);
+        LAUNCH_CHECK(c);
+        k_tile_valence<<<divUp(n, 256), 256, 0, c->stream>>>(n, c->tilePerm.p, c->n2ePtr.p, c->tileNePrefix.p);
+        LAUNCH_CHECK(c);
+    }
+    CUDA_CHECK(cudaMemsetAsync(c->tileNePrefix.p + n, 0, sizeof(int), c->stream));
+    c->scratchI.reserve(64);
+    int* misc = c->scratchI.p;  // [0] total incidences, [1] max elements per tile
+    CUDA_CHECK(cudaMemsetAsync(misc, 0, 4 * sizeof(int), c->stream));
+    exclusiveScanInt(c, c->tileNePrefix.p, n + 1, misc);
+    int h[2] = {0, 0}, nIface = 0;
+    CUDA_CHECK(cudaMemcpyAsync(h, misc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(&nIface, binPtr + nCells, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const int64_t nConn = (int64_t)c->nElems * npe;
+    c->tileElems.reserve((size_t)h[0] + 8);
+    c->tileIdx16.reserve((size_t)nConn + 8);
+    for (;;) {
+        const int nTiles = divUp(std::max(n, 1), T);
+        int CAP = 256;
+        while (CAP < T * maxE) CAP <<= 1;
+        c->tileCnt.reserve((size_t)nTiles + 4);
+        CUDA_CHECK(cudaMemsetAsync(misc + 1, 0, sizeof(int), c->stream));
+        const size_t smem = (size_t)2 * CAP * sizeof(int);
+        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_tile_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (n > 0) {
+            k_tile_build<<<nTiles, 256, smem, c->stream>>>(T, n, npe, CAP, c->tilePerm.p, c->tileNePrefix.p, c->n2ePtr.p, c->n2e.p, c->conn.p,
+                                                          c->tileElems.p, c->tileCnt.p, c->tileIdx16.p, misc + 1);
+            LAUNCH_CHECK(c);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(h + 1, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->tileT = T, c->nTiles = n > 0 ? nTiles : 0, c->tileCap = (h[1] + 1) & ~1;
+        // the momentum pass keeps (dim+1) planes of 32-byte records per tile element: they must fit in shared memory
+        if ((size_t)c->tileCap * npe * 32 <= 200 * 1024 || T <= 8) break;
+        T >>= 1;
+    }
+    PFEM_REQUIRE((size_t)c->tileCap * npe * 32 <= 227 * 1024, PFEM_ERR_INVALID, "wc tiles: tile element list too large for shared memory");
+    c->nIfaceTiles = c->nRanks > 1 ? std::min(c->nTiles, divUp(nIface, T)) : 0;
+    if (c->nRanks > 1 && !c->commStream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->evTile, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
+    }
+    c->tilesValid = true;
+}
+
 // PFEM_WC_CFG: 10 (default) chooses by size -- two-pass continuity + momentum + CFL-from-stored-values on meshes of >= 200 k
 // elements (below that the step is launch-bound and the 5-launch gather path wins) and, on a partitioned mesh, >= 4 M
 // local elements (measured at C5: 2 GPUs 2.20 -> 1.57 ms/step, but 8 GPUs 0.89 -> 1.00 ms: with 2.5 M elements per rank
@@ -1082,9 +1168,15 @@ int wcCfgRaw() {
 }
 bool wcTwoPass(const pfem_ctx* c) {
     const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();  // pfem_wc_set_variant overrides the environment
-    if (raw == 11 || raw == 12) return true;
+    if (raw == 11 || raw == 12 || raw == 13) return true;
     if (raw != 10) return false;
-    return c->nRanks == 1 ? c->nElems >= 200000 : c->nElems >= 4000000;
+    return c->nElems >= 200000;
+}
+// tiles (element records in shared memory) instead of element records in HBM: the default at size, CDS_dpdt only
+bool wcTiles(const pfem_ctx* c, const pfem_wc_params& p) {
+    const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();
+    if (p.eqType != PFEM_WC_CDS_DPDT || c->maxE > 255) return false;
+    return raw == 13 || (raw == 10 && wcTwoPass(c));
 }
 bool wcTwoPassMom(const pfem_ctx* c) { return (c->wcVariant ? c->wcVariant : wcCfgRaw()) != 12; }
 int wcCfg(const pfem_ctx* c) {
@@ -1145,8 +1237,54 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         if (c->dim == 2) KERNEL<2, LPN_, 2><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);      \
         else KERNEL<3, LPN_, 2><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);                  \
     } while (0)
+    const bool tiles = wcTiles(c, p);
+    TileArgs ta;
+    ta.perm = c->tilePerm.p, ta.nePrefix = c->tileNePrefix.p, ta.tileCnt = c->tileCnt.p, ta.tileElems = c->tileElems.p;
+    ta.idx16 = c->tileIdx16.p, ta.T = c->tileT, ta.nRows = c->nRows, ta.tile0 = 0;
+    // tile passes of a partitioned mesh: the tiles holding interface nodes run first; the exchange of their results
+    // (commStream) overlaps the interior tiles; the main stream joins before the next pass reads the ghosts
+    auto tilePass = [&](auto launchRange, auto exchange) {
+        const bool split = c->nRanks > 1 && c->commStream && !c->local;
+        const int nI = split ? c->nIfaceTiles : 0;
+        if (nI > 0) launchRange(0, nI);
+        if (split) CUDA_CHECK(cudaEventRecord(c->evTile, c->stream));
+        if (c->nTiles > nI) launchRange(nI, c->nTiles - nI);
+        if (c->nRanks > 1) {
+            if (split) {
+                cudaStream_t mainStream = c->stream;
+                CUDA_CHECK(cudaStreamWaitEvent(c->commStream, c->evTile, 0));
+                c->stream = c->commStream;
+                try {
+                    exchange();
+                } catch (...) {
+                    c->stream = mainStream;
+                    throw;
+                }
+                c->stream = mainStream;
+                CUDA_CHECK(cudaEventRecord(c->evHalo, c->commStream));
+                CUDA_CHECK(cudaStreamWaitEvent(c->stream, c->evHalo, 0));
+            } else
+                exchange();
+        }
+    };
     {
         PhaseScope ph(c, "Solving continuity eq");
+        if (tiles) {
+            auto range = [&](int t0, int nt) {
+                TileArgs tb = ta;
+                tb.tile0 = t0;
+                const size_t smem = (size_t)std::max(c->tileCap, 2) * 32;
+                if (c->dim == 2) {
+                    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_wc_cont_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_wc_cont_tile<2><<<nt, 256, smem, c->stream>>>(tb, a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
+                } else {
+                    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_wc_cont_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    k_wc_cont_tile<3><<<nt, 256, smem, c->stream>>>(tb, a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
+                }
+                LAUNCH_CHECK(c);
+            };
+            tilePass(range, [&]() { commHalo(c, c->X4b.p, c->V4b.p, 4); });
+        } else
         if (p.eqType == PFEM_WC_CDS_DRHODT) PFEM_WC_LAUNCH_RHO(1, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, nullptr);
         else if (p.eqType == PFEM_WC_CDS_RHO) PFEM_WC_LAUNCH_RHO(2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcF0.p);
         else if (cfg == 10) {  // two-pass: element records, then the nodal gather
@@ -1154,22 +1292,45 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
             if (c->dim == 2) {
                 k_wc_cont_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
                 LAUNCH_CHECK(c);
-                k_wc_cont_node<2, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+                k_wc_cont_node<2, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
             } else {
                 if (wcElemBlocks() == 4) k_wc_cont_elem<3, 4><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
                 else if (wcElemBlocks() == 2) k_wc_cont_elem<3, 2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
                 else k_wc_cont_elem<3, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
                 LAUNCH_CHECK(c);
-                k_wc_cont_node<3, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
+                k_wc_cont_node<3, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
             }
         }
         else if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         else if (cfg == 0) PFEM_WC_LAUNCH(k_wc_cont, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         else PFEM_WC_LAUNCH(k_wc_cont, 4, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        LAUNCH_CHECK(c);
-        if (c->nRanks > 1) commHalo(c, c->X4b.p, c->V4b.p, 4);  // (x, p_new) and (v_half, rho_new) of interface nodes
+        if (!tiles) {
+            LAUNCH_CHECK(c);
+            if (c->nRanks > 1) commHalo(c, c->X4b.p, c->V4b.p, 4);  // (x, p_new) and (v_half, rho_new) of interface nodes
+        }
     }
-    {
+    if (tiles) {
+        PhaseScope ph(c, "Solving momentum eq");
+        auto range = [&](int t0, int nt) {
+            TileArgs tb = ta;
+            tb.tile0 = t0;
+            const int cap = std::max(c->tileCap, 2);
+            const size_t smem = (size_t)cap * (c->dim + 1) * 32;
+            if (c->dim == 2) {
+                if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_wc_mom_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_wc_mom_tile<2><<<nt, 256, smem, c->stream>>>(tb, a, cap, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
+            } else {
+                if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_wc_mom_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                k_wc_mom_tile<3><<<nt, 256, smem, c->stream>>>(tb, a, cap, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
+            }
+            LAUNCH_CHECK(c);
+        };
+        tilePass(range, [&]() {
+            commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
+            const size_t g0 = (size_t)c->nRows * 4, gn = (size_t)(c->nNodes - c->nRows) * 4;  // ghosts: (x, p_new) from X4b
+            if (gn) CUDA_CHECK(cudaMemcpyAsync(c->X4.p + g0, c->X4b.p + g0, gn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        });
+    } else {
         PhaseScope ph(c, "Solving momentum eq");
         if (cfg == 10 && !wcTwoPassMom(c)) PFEM_WC_LAUNCH(k_wc_mom, 4, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
         else if (cfg == 10) {
@@ -1194,11 +1355,6 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
             commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
             const size_t g0 = (size_t)c->nRows * 4, gn = (size_t)(c->nNodes - c->nRows) * 4;  // ghosts: (x, p_new) from X4b
             if (gn) CUDA_CHECK(cudaMemcpyAsync(c->X4.p + g0, c->X4b.p + g0, gn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-            if (cfg == 10 && c->nNodes > c->nRows) {  // ghosts: same nodal CFL values their owners computed in k_wc_mom_node
-                k_wc_cfl_nodes<<<divUp(c->nNodes - c->nRows, 256), 256, 0, c->stream>>>(c->nRows, c->nNodes - c->nRows, c->dim, c->X4.p, c->V4.p,
-                                                                                      p.mu, p.K0, p.K0p, c->wcCfl2.p);
-                LAUNCH_CHECK(c);
-            }
         }
     }
 }
@@ -1207,8 +1363,7 @@ void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int gr
     const double sc2 = securityCoeff * securityCoeff;
     // the stored he / nodal CFL values belong to the two-pass step that has just run with the same material constants
     if (afterTwoPassStep && p.eqType == PFEM_WC_CDS_DPDT && p.mu == c->cflMu && p.K0 == c->cflK0 && p.K0p == c->cflK0p) {
-        if (c->dim == 2) k_wc_dt_fast<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->wcContRec.p, c->wcCfl2.p, sc2, c->dtPartial.p);
-        else k_wc_dt_fast<3><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->wcContRec.p, c->wcCfl2.p, sc2, c->dtPartial.p);
+        k_wc_dt_nodal<<<grid, 256, 0, c->stream>>>(c->nRows, c->wcHmin.p, c->wcCfl2.p, sc2, c->dtPartial.p);
         LAUNCH_CHECK(c);
         return;
     }
@@ -1228,10 +1383,12 @@ void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     c->X4b.reserve(n4);
     c->V4b.reserve(n4);
     if (p.eqType == PFEM_WC_CDS_RHO) c->wcF0.reserve((size_t)c->nNodes);
+    if (wcTiles(c, p) && !c->tilesValid) buildTiles(c);
     if (wcCfg(c) == 10) {  // before any graph capture
         c->wcElemRec.reserve((size_t)std::max(c->nElems, 1) * (c->dim + 1) * 4);
         c->wcContRec.reserve((size_t)std::max(c->nElems, 1) * 4);
         c->wcCfl2.reserve((size_t)c->nNodes * 2);
+        c->wcHmin.reserve((size_t)c->nNodes + 4);
     }
 }
 

@@ -66,7 +66,7 @@ def test_picard_matches_reference_fixture(name):
     assert np.abs(x - z["x_new"]).max() < 1e-9           # positions move by dt*v: 1e-3 * (1e-8 relative of O(1))
 
 
-@pytest.mark.parametrize("variant", [6, 11])
+@pytest.mark.parametrize("variant", [6, 11, 13])
 @pytest.mark.parametrize("name", golden_names("wc_"))
 def test_wc_steps_match_reference_fixture(name, variant):
     mesh, z = load_golden(name)

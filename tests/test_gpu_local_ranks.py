@@ -23,7 +23,7 @@ def _gather(results, parts, n_comp, nn):
 
 
 @pytest.mark.parametrize("n_ranks", [2, 3, 4])
-@pytest.mark.parametrize("variant", [6, 11])
+@pytest.mark.parametrize("variant", [6, 11, 13])
 def test_wc_steps_bit_identical(n_ranks, variant):
     dim = 3
     mesh = mg.kuhn_box(dim, 10, free_fraction=0.002, permute=True)

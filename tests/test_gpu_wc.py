@@ -27,9 +27,9 @@ def _pack(st):
     (2, 10, dict(permute=True), False, "CDS_rho"),
     (3, 10, dict(free_fraction=0.01, permute=True), True, "CDS_rho"),
 ])
-@pytest.mark.parametrize("variant", [6, 11, 12])
+@pytest.mark.parametrize("variant", [6, 11, 12, 13])
 def test_wc_steps_match_oracle(dim, n, kw, meduri, eq, variant):
-    """variant: pfem_wc_set_variant -- gather kernels | two-pass element records | mixed (all must match the oracle)."""
+    """variant: pfem_wc_set_variant -- gather kernels | two-pass element records | mixed | tiles with the element records in shared memory (all must match the oracle)."""
     mesh = mg.kuhn_box(dim, n, **kw)
     st = mg.wc_state(mesh)
     st["acc"] = 0.5 * np.random.default_rng(4).standard_normal(st["acc"].shape)
@@ -85,7 +85,7 @@ def test_state_roundtrip():
 
 
 @pytest.mark.parametrize("dim,n,eq", [(2, 20, "CDS_dpdt"), (3, 6, "CDS_dpdt"), (3, 5, "CDS_rho")])
-@pytest.mark.parametrize("variant", [6, 11])
+@pytest.mark.parametrize("variant", [6, 11, 13])
 def test_wc_run_equals_step_loop(dim, n, eq, variant):
     """pfem_wc_run (device-chained CFL dt, one CUDA graph per step) == the host loop of wc_step + wc_next_dt, bit for bit."""
     mesh = mg.kuhn_box(dim, n, free_fraction=0.01)
@@ -117,7 +117,7 @@ def test_wc_run_equals_step_loop(dim, n, eq, variant):
 
 
 @pytest.mark.parametrize("dim,n", [(2, 16), (3, 8)])
-@pytest.mark.parametrize("variant", [11, 12])
+@pytest.mark.parametrize("variant", [11, 12, 13])
 def test_wc_dt_after_step_matches_full_recomputation(dim, n, variant):
     """pfem_wc_next_dt right after pfem_wc_step may reuse what the step left on the device (element he, nodal
     max(u^2, c^2) and alpha^2 -- two-pass configuration); after any other call it recomputes everything.  Same dt."""
@@ -144,3 +144,44 @@ def test_wc_dt_after_step_matches_full_recomputation(dim, n, variant):
             assert abs(dt_after_step - dt_full) <= 1e-15 * dt_full
             assert abs(dt_full - dt_oracle) <= 1e-12 * dt_oracle
             dt = dt_full
+
+
+@pytest.mark.parametrize("variant", [6, 11, 13])
+@pytest.mark.parametrize("poison", ["velocity", "density"])
+def test_nan_state_is_reported_not_stepped_over(variant, poison):
+    """A NaN velocity or density must surface as PFEM_NAN ("NaN time step!", WCompNewton/Solver.cpp:228-232) from both
+    pfem_wc_next_dt and pfem_wc_run -- fmin/fmax drop NaN operands, so the reductions must carry it explicitly."""
+    from pfem_b200.capi import PfemError
+    dim = 3
+    mesh = mg.kuhn_box(dim, 6)
+    st = mg.wc_state(mesh)
+    nn = mesh.n_nodes
+    node = nn // 2
+    if poison == "velocity":
+        st["v"][node] = np.nan
+    else:
+        st["rho"][node] = np.nan
+    W = mg.WC_PARAMS
+    g = mg.gravity(dim)
+    with PfemContext(dim, 0) as ctx:
+        ctx.set_mesh(mesh)
+        ctx.set_states(0, _pack(st))
+        ctx.wc_set_variant(variant)
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+        with pytest.raises(PfemError) as e1:
+            ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+        assert e1.value.code == 2
+    # NaN appearing DURING chained steps: start from a clean state, poison after the first dt
+    st = mg.wc_state(mesh)
+    with PfemContext(dim, 0) as ctx:
+        ctx.set_mesh(mesh)
+        ctx.set_states(0, _pack(st))
+        ctx.wc_set_variant(variant)
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+        dt0 = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+        bad = mg.wc_state(mesh)
+        bad["v" if poison == "velocity" else "rho"][node] = np.nan
+        ctx.set_states(0, _pack(bad))
+        with pytest.raises(PfemError) as e2:
+            ctx.wc_run(wp, 4, W["securityCoeff"], 1e-3, dt0)
+        assert e2.value.code == 2
