@@ -174,13 +174,16 @@ int pfem_wc_step(pfem_ctx* ctx, const pfem_wc_params* p, double dt);
  * each variant is bit-reproducible and partition-independent): 0 = chosen by mesh size (default), 6 = one gather kernel
  * per equation (4 lanes per node over the incident elements), 7 = the same with staged neighbour records, 11 = two
  * passes per equation (element records, then an ordered nodal gather; the CFL pass reuses what the step stored),
- * 12 = two-pass continuity + gather momentum. */
+ * 12 = two-pass continuity + gather momentum, 13 = tiles (a CTA computes the elements of ~64 nearby nodes once and keeps
+ * their records in shared memory; CDS_dpdt only). */
 int pfem_wc_set_variant(pfem_ctx* ctx, int variant);
 /* SolverWCompNewton::computeNextDT (WCompNewton/Solver.cpp:192-234) incl. Element::getRin (Element.cpp:226-294) */
 int pfem_wc_next_dt(pfem_ctx* ctx, const pfem_wc_params* p, double securityCoeff, double maxDT, double* dt);
 /* nSteps iterations of the Problem::simulate loop body for the explicit solver between two remeshes
  * (Problem.cpp:344-369: solveOneTimeStep then computeNextDT) without returning to the host: *dt is the first time step on
- * entry and the next one on exit, *elapsed the simulated time covered.  One CUDA graph per step.  Single-GPU contexts. */
+ * entry and the next one on exit, *elapsed the simulated time covered.  One CUDA graph per step on a single-GPU context; on a
+ * partitioned mesh the CFL minimum is all-reduced on the device and the steps are enqueued back to back (every rank calls
+ * it with the same arguments). */
 int pfem_wc_run(pfem_ctx* ctx, const pfem_wc_params* p, int nSteps, double securityCoeff, double maxDT, double* dt,
                 double* elapsed);
 

@@ -243,7 +243,7 @@ void commSetPartition(pfem_ctx* c, int64_t nOwned, int nPeers, const int32_t* pe
     P.sendIdxHost.assign(sendIdx, sendIdx + total);
     commFinishPlan(c, P);
     c->haveSystem = c->haveSolution = false;
-    c->tilesValid = false;
+    c->tilesValid = c->orderValid = false;
 }
 void commFinishPlan(pfem_ctx* c, HaloPlan& P) {
     const size_t total = P.sendIdxHost.size();

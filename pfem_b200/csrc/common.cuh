@@ -11,6 +11,9 @@
 
 #include "../../include/pfem_b200.h"
 
+// dynamic shared memory opt-in: always the device maximum (227 KB) -- the attribute is per-function process state, and rank
+// threads of one process (local communicator) would otherwise race on per-launch values
+#define PFEM_SMEM_OPTIN (225 * 1024)  /* the 227 KB per-block limit minus room for the kernels' static shared memory */
 #define PFEM_MAX_STATES 8  // 2*dim+2 for the weakly-compressible problem in 3-D
 
 // ---- error plumbing: every API entry point is `try { ... } catch (PfemFail&)`, nothing escapes the C ABI ----------
@@ -169,9 +172,15 @@ struct pfem_ctx {
     int wcVariant = 0;         // pfem_wc_set_variant: 0 = by size (PFEM_WC_CFG), 6 gather, 11 two-pass, 12 mixed
     bool cflFresh = false;     // wcContRec.he / wcCfl2 describe the current positions and states
     bool tilesValid = false;   // node tiles of the fused explicit step (wc_tile.cuh) match the current topology/partition
-    int tileT = 0, nTiles = 0, nIfaceTiles = 0, tileCap = 0;  // nodes per tile, tiles, tiles holding interface nodes, max elements per tile
-    DevBuf<int> tilePerm, tileNePrefix, tileElems, tileCnt, tileKey;
-    DevBuf<unsigned short> tileIdx16;
+    bool orderValid = false;   // tilePerm (interface nodes first, then by grid cell) matches the current topology/partition
+    int nIfaceNodes = 0;
+    int tileT = 0, nTiles = 0, nIfaceTiles = 0, tileCap = 0;  // nodes per tile, tiles, tiles holding interface nodes, max record slots per tile
+    DevBuf<int> tilePerm, tileNePrefix, tileElems, tileCnt, tileKey, tileNodes;
+    const int* tileNodeStart = nullptr;  // views into tileCnt
+    const int* tileNodeCnt = nullptr;
+    int tileNodeCap = 0;                 // max entries of a tile's node list
+    DevBuf<unsigned short> tileDst16, tileLconn;
+    int tileMaxElems = 0;
     DevBuf<uint8_t> tileIface;
     cudaStream_t commStream = nullptr;  // halo exchanges that overlap the interior tiles (partitioned explicit step)
     cudaEvent_t evTile = nullptr, evHalo = nullptr;
@@ -217,8 +226,9 @@ struct pfem_ctx {
         blkMask.accounting = &deviceBytes;
         rowDir.accounting = &deviceBytes;
         nodeHdr.accounting = &deviceBytes;
-        for (auto* b : {&tilePerm, &tileNePrefix, &tileElems, &tileCnt, &tileKey}) b->accounting = &deviceBytes;
-        tileIdx16.accounting = &deviceBytes;
+        for (auto* b : {&tilePerm, &tileNePrefix, &tileElems, &tileCnt, &tileKey, &tileNodes}) b->accounting = &deviceBytes;
+        tileDst16.accounting = &deviceBytes;
+        tileLconn.accounting = &deviceBytes;
         tileIface.accounting = &deviceBytes;
     }
 };

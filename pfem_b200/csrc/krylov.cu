@@ -449,7 +449,7 @@ void spmv(pfem_ctx* c, const KrylovDims& k, double* x, double* y, const double* 
         const int grid = k.spmvGrid;
         auto launch = [&](auto kern, int stages) {
             const size_t smem = (size_t)WARPS * stages * (CAPB * 16 * 8 + 8);
-            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
             kern<<<grid, WARPS * 32, smem, c->stream>>>(c->nRows, c->nbrPtr.p, c->nbr.p, c->Aval.p, x, y, w1, c->partial.p, k.stride,
                                                       slotYW, slotYY, sc, rowScale);
         };

@@ -632,7 +632,7 @@ void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const double* x, double* 
         const int g = std::max(1, std::min(c->smCount * 4, divUp(L.n, 8)));
         auto launch = [&](auto kern, int depth) {
             const size_t smem = (size_t)8 * depth * 16 * 16 * sizeof(float);
-            if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            if (smem > 40 * 1024) CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
             kern<<<g, 256, smem, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, e);
         };
         if (ringDepth == 3) launch(k_spmv_ring<EPI, float, 3, 4>, 3);
@@ -1168,11 +1168,11 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
         const int* cPtrMine = C.nbrPtr + L.rowOff;
         if (ncL > 0) {
             if (BS == 4) {
-                if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (smem > 40 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
                 k_galerkin<4><<<divUp(ncL, hwPerBlock), hwPerBlock * 16, smem, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, L.nbrPtr, L.Aval,
                                                                                           L.cslot.p, cPtrMine, C.AvalB.p, nbcap);
             } else {
-                if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                if (smem > 40 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_galerkin<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
                 k_galerkin<3><<<divUp(ncL, hwPerBlock), hwPerBlock * 16, smem, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, L.nbrPtr, L.Aval,
                                                                                           L.cslot.p, cPtrMine, C.AvalB.p, nbcap);
             }
@@ -1195,7 +1195,7 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
         H.flag.reserve(16);
         CUDA_CHECK(cudaMemsetAsync(H.flag.p + 8, 0, sizeof(int), c->stream));
         const size_t smem = ((size_t)H.nD * H.nD + H.nD) * sizeof(double) + (size_t)H.nD * sizeof(int);
-        CUDA_CHECK(cudaFuncSetAttribute(k_dense_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_CHECK(cudaFuncSetAttribute(k_dense_invert, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
         k_dense_invert<<<1, 1024, smem, c->stream>>>(Lc.n, BS, Lc.nbrPtr, Lc.nbr, Lc.Aval, H.dense.p, H.flag.p + 8);
         LAUNCH_CHECK(c);
         int bad = 0;

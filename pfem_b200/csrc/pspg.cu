@@ -1130,18 +1130,18 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
             while (wpb > 1 && per * wpb > 110 * 1024) wpb >>= 1;
             if (per * wpb > 110 * 1024) {
                 wpb = 8;
-                while (wpb > 1 && per * wpb > 227 * 1024) wpb >>= 1;
+                while (wpb > 1 && per * wpb > 225 * 1024) wpb >>= 1;
             }
             const size_t smem = per * wpb;
-            PFEM_REQUIRE(smem <= 227 * 1024, PFEM_ERR_INVALID, "pspg_assemble: node valence too large for shared memory");
+            PFEM_REQUIRE(smem <= 225 * 1024, PFEM_ERR_INVALID, "pspg_assemble: node valence too large for shared memory");
             const int blocksPerSm = smem <= 110 * 1024 ? (cfg == 1 ? 3 : 2) : 1;
             const int nPairs = (c->nRows + 1) / 2;
             const int grid = std::max(1, std::min(divUp(nPairs, wpb), c->smCount * blocksPerSm * (8 / wpb)));
 #define PFEM_LAUNCH_ASM2(DIM_, M_, D_, P_)                                                                                 \
     do {                                                                                                                  \
-        if (smem > 48 * 1024)                                                                                             \
+        if (smem > 40 * 1024)                                                                                             \
             CUDA_CHECK(cudaFuncSetAttribute(k_pspg_assemble2<DIM_, 256, M_, D_, P_>,                                      \
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                     \
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));                     \
         k_pspg_assemble2<DIM_, 256, M_, D_, P_><<<grid, wpb * 32, smem, c->stream>>>(a);                                  \
     } while (0)
             // ver: 2 = row-sum diagonal | 3 = row-sum + next-pair prefetch | 4 = direct diagonal | 5 = direct + prefetch
@@ -1156,13 +1156,13 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
         const int blocksPerSm = (cfg == 0) ? 2 : (cfg == 1 ? 3 : (cfg == 2 ? 6 : 8));
         const size_t per = c->dim == 2 ? asmSmemPerWarp<2>(a.ecap, a.nbcap) : asmSmemPerWarp<3>(a.ecap, a.nbcap);
         const size_t smem = per * wpb;
-        PFEM_REQUIRE(smem <= 227 * 1024, PFEM_ERR_INVALID, "pspg_assemble: node valence too large for shared memory");
+        PFEM_REQUIRE(smem <= 225 * 1024, PFEM_ERR_INVALID, "pspg_assemble: node valence too large for shared memory");
         const int grid = std::max(1, std::min(divUp(c->nRows, wpb), c->smCount * blocksPerSm));
 #define PFEM_LAUNCH_ASM(DIM_, T_, M_)                                                                                     \
     do {                                                                                                                  \
-        if (smem > 48 * 1024)                                                                                             \
+        if (smem > 40 * 1024)                                                                                             \
             CUDA_CHECK(cudaFuncSetAttribute(k_pspg_assemble<DIM_, T_, M_>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
-                                            (int)smem));                                                                  \
+                                            PFEM_SMEM_OPTIN));                                                                  \
         k_pspg_assemble<DIM_, T_, M_><<<grid, T_, smem, c->stream>>>(a);                                                  \
     } while (0)
         if (c->dim == 2) PFEM_LAUNCH_ASM(2, 256, 2);

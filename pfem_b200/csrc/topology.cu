@@ -249,7 +249,7 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     c->nElems = nElems;
     c->nRows = nNodes;  // until pfem_set_partition narrows it to the owned nodes
     c->plan.clear();
-    c->tilesValid = false;
+    c->tilesValid = c->orderValid = false;
     c->nFacets = c->nFstNodes = 0;  // facets belong to the previous mesh (pfem_set_facets)
     c->haveTopology = false;
     c->haveSystem = c->haveSolution = c->haveQprev = c->haveSnapshot = c->havePositions = c->haveDirichlet = false;
@@ -297,8 +297,8 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     const int CH = (max(c->maxE, 1) + 31) / 32;
     c->maskWords = CH;
     size_t smem = (size_t)warps * candCap * sizeof(int);
-    if (smem > 48 * 1024)
-        CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024)
+        CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
     CUDA_CHECK(cudaMemsetAsync(c->nbrPtr.p, 0, (nNodes + 2) * sizeof(int), c->stream));
     k_neighbours<false><<<divUp(nNodes, warps), warps * 32, smem, c->stream>>>(
         c->conn.p, npe, c->n2ePtr.p, c->n2e.p, nNodes, candCap, 0, CH, c->nbrPtr.p, nullptr, nullptr, misc + 2, nullptr, nullptr);
@@ -314,8 +314,8 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     c->blkMask.reserve((size_t)c->nBlocks * CH + 4);
     const int nbCap = c->maxNb;
     smem = (size_t)warps * (candCap + nbCap * (1 + CH)) * sizeof(int);
-    if (smem > 48 * 1024)
-        CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 40 * 1024)
+        CUDA_CHECK(cudaFuncSetAttribute(k_neighbours<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
     k_neighbours<true><<<divUp(nNodes, warps), warps * 32, smem, c->stream>>>(
         c->conn.p, npe, c->n2ePtr.p, c->n2e.p, nNodes, candCap, nbCap, CH, c->nbrPtr.p, c->nbr.p, c->diagSlot.p, nullptr,
         c->n2eSlots.p, c->blkMask.p);

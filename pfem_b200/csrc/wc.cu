@@ -51,26 +51,9 @@ template <int DIM> struct ElemGeo {
     double V;
 };
 
-// gather the 4-double records of the element nodes and build grad N and the volume (Element.cpp:15-135, MB.inl:93-127)
-template <int DIM>
-__device__ __forceinline__ void loadElem(const double* __restrict__ XA, const double* __restrict__ VA,
-                                         const int (&nd)[DIM + 1], double (&xw)[DIM + 1], double (&vel)[DIM + 1][DIM],
-                                         double (&vw)[DIM + 1], ElemGeo<DIM>& G) {
-    constexpr int NPE = DIM + 1;
+// grad N and the element size from the node coordinates (Element.cpp:15-135, MatricesBuilder.inl:93-127)
+template <int DIM> __device__ __forceinline__ void buildGeo(const double (&px)[DIM + 1][DIM], ElemGeo<DIM>& G) {
     constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
-    double px[NPE][DIM];
-#pragma unroll
-    for (int m = 0; m < NPE; ++m) {
-        const D4 xr = ld4(XA + (size_t)nd[m] * 4), vr = ld4(VA + (size_t)nd[m] * 4);
-        px[m][0] = xr.x, px[m][1] = xr.y;
-        vel[m][0] = vr.x, vel[m][1] = vr.y;
-        if constexpr (DIM == 3) {
-            px[m][2] = xr.z;
-            vel[m][2] = vr.z;
-        }
-        xw[m] = xr.w;
-        vw[m] = vr.w;
-    }
     double J[DIM][DIM];
 #pragma unroll
     for (int d = 0; d < DIM; ++d)
@@ -108,6 +91,28 @@ __device__ __forceinline__ void loadElem(const double* __restrict__ XA, const do
         for (int m = 0; m < DIM; ++m) G.g[d][m + 1] = inv[m][d];
     }
     G.V = det * REF;
+}
+
+// gather the 4-double records of the element nodes and build grad N and the volume (Element.cpp:15-135, MB.inl:93-127)
+template <int DIM>
+__device__ __forceinline__ void loadElem(const double* __restrict__ XA, const double* __restrict__ VA,
+                                         const int (&nd)[DIM + 1], double (&xw)[DIM + 1], double (&vel)[DIM + 1][DIM],
+                                         double (&vw)[DIM + 1], ElemGeo<DIM>& G) {
+    constexpr int NPE = DIM + 1;
+    double px[NPE][DIM];
+#pragma unroll
+    for (int m = 0; m < NPE; ++m) {
+        const D4 xr = ld4(XA + (size_t)nd[m] * 4), vr = ld4(VA + (size_t)nd[m] * 4);
+        px[m][0] = xr.x, px[m][1] = xr.y;
+        vel[m][0] = vr.x, vel[m][1] = vr.y;
+        if constexpr (DIM == 3) {
+            px[m][2] = xr.z;
+            vel[m][2] = vr.z;
+        }
+        xw[m] = xr.w;
+        vw[m] = vr.w;
+    }
+    buildGeo<DIM>(px, G);
 }
 
 // he = 2 r_in of Element::getRin (Element.cpp:226-294) from the node positions
@@ -223,7 +228,12 @@ struct WcArgs {
     double dt, mu, K0, K0p, rhoStar, body[3];
     const double* dtPtr;  // if non-null the time step is read from the device (pfem_wc_run)
     int meduri;
+    // node passes of the two-pass formulation may cover a slice of an ORDER of the nodes (interface nodes first, so that
+    // their halo exchange overlaps the rest): node = order[k0 + k], k < nNodes; order == null: node = k0 + k
+    const int* order = nullptr;
+    int k0 = 0;
 };
+__device__ __forceinline__ int wcNodeOf(const WcArgs& a, int k) { return a.order ? __ldg(a.order + a.k0 + k) : a.k0 + k; }
 
 // continuity, CDS_dpdt (ContEquation.inl:353-413, 334-350, 139-146, 319-331)
 template <int DIM, int LPN, int MINB>
@@ -497,8 +507,9 @@ __global__ void __launch_bounds__(256) k_wc_cont_node(const WcArgs a, const doub
                                                       const double* __restrict__ V4, double* __restrict__ X4n,
                                                       double* __restrict__ V4n, double* __restrict__ hminOut) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = t / LPN, sub = t % LPN;
-    const bool valid = i < a.nNodes;
+    const int kn = t / LPN, sub = t % LPN;
+    const bool valid = kn < a.nNodes;
+    const int i = valid ? wcNodeOf(a, kn) : 0;
     double m = 0, F0 = 0, hmin = 1.7976931348623157e308;
     if (valid) {
         const int eb = a.n2ePtr[i], end = a.n2ePtr[i + 1];
@@ -601,8 +612,9 @@ __global__ void __launch_bounds__(256) k_wc_mom_node(const WcArgs a, const doubl
                                                      double* __restrict__ X4out, double* __restrict__ cfl2) {
     constexpr int NPE = DIM + 1;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = t / LPN, sub = t % LPN;
-    const bool valid = i < a.nNodes;
+    const int kn = t / LPN, sub = t % LPN;
+    const bool valid = kn < a.nNodes;
+    const int i = valid ? wcNodeOf(a, kn) : 0;
     const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
     double M = 0, F[DIM];
 #pragma unroll
@@ -1050,15 +1062,13 @@ __global__ void k_dt_chain(const double* __restrict__ partial, int n, double max
 
 #include "wc_tile.cuh"
 
-// (re)build the node tiles of the fused explicit step for the current topology / partition (per remesh)
-void buildTiles(pfem_ctx* c) {
-    PhaseScope ph(c, "Build tiles");
-    const int n = c->nRows, dim = c->dim, npe = dim + 1;
-    static const int envT = getenv("PFEM_WC_TILE") ? atoi(getenv("PFEM_WC_TILE")) : 64;
-    int T = std::max(8, std::min(64, envT));
-    const int maxE = std::max(c->maxE, 1);
-    while (T > 8 && (int64_t)T * maxE > 8192) T >>= 1;
-    PFEM_REQUIRE((int64_t)T * maxE <= 16384, PFEM_ERR_INVALID, "wc tiles: node valence too large");
+// Node order of the explicit step for the current topology / partition (per remesh): owned nodes sorted by (interface
+// node first, cell of a uniform grid over their coordinates) with a counting sort.  Nothing the ABI sees is renumbered: the
+// order only decides which nodes a launch covers -- the interface nodes first, so that their halo exchange overlaps the
+// rest -- and, for the tile kernels, which nodes share a CTA.
+void buildNodeOrder(pfem_ctx* c) {
+    PhaseScope ph(c, "Build node order");
+    const int n = c->nRows, dim = c->dim;
     // bounding box of the owned nodes -> uniform grid with ~64 nodes per cell (locality only: any grouping is correct)
     c->scal.reserve(SC_COUNT);
     double* boxDev = c->scal.p;
@@ -1096,7 +1106,6 @@ void buildTiles(pfem_ctx* c) {
     int* cursor = binPtr + nBins + 2;    // nBins
     CUDA_CHECK(cudaMemsetAsync(binPtr, 0, ((size_t)2 * nBins + 8) * sizeof(int), c->stream));
     c->tilePerm.reserve((size_t)n + 4);
-    c->tileNePrefix.reserve((size_t)n + 4);
     if (n > 0) {
         k_tile_key<<<divUp(n, 256), 256, 0, c->stream>>>(c->X4.p, n, dim, hb[0], hb[1], hb[2], 1.0 / Hc, nx, ny, nz, c->tileIface.p, key, binPtr);
         LAUNCH_CHECK(c);
@@ -1107,6 +1116,32 @@ void buildTiles(pfem_ctx* c) {
         LAUNCH_CHECK(c);
         k_tile_sort_bins<<<divUp(nBins, 128), 128, 0, c->stream>>>(nBins, binPtr, c->tilePerm.p);
         LAUNCH_CHECK(c);
+    }
+    int nIface = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&nIface, binPtr + nCells, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->nIfaceNodes = c->nRanks > 1 ? nIface : 0;
+    if (c->nRanks > 1 && !c->commStream) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->evTile, cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
+    }
+    c->orderValid = true;
+}
+
+// (re)build the node tiles of the fused explicit step for the current topology / partition (per remesh)
+void buildTiles(pfem_ctx* c) {
+    if (!c->orderValid) buildNodeOrder(c);
+    PhaseScope ph(c, "Build tiles");
+    const int n = c->nRows, dim = c->dim, npe = dim + 1;
+    (void)dim;
+    static const int envT = getenv("PFEM_WC_TILE") ? atoi(getenv("PFEM_WC_TILE")) : 64;
+    int T = std::max(8, std::min(64, envT));
+    const int maxE = std::max(c->maxE, 1);
+    while (T > 8 && (int64_t)T * maxE > 8192) T >>= 1;
+    PFEM_REQUIRE((int64_t)T * maxE <= 16384, PFEM_ERR_INVALID, "wc tiles: node valence too large");
+    c->tileNePrefix.reserve((size_t)n + 4);
+    if (n > 0) {
         k_tile_valence<<<divUp(n, 256), 256, 0, c->stream>>>(n, c->tilePerm.p, c->n2ePtr.p, c->tileNePrefix.p);
         LAUNCH_CHECK(c);
     }
@@ -1115,41 +1150,60 @@ void buildTiles(pfem_ctx* c) {
     int* misc = c->scratchI.p;  // [0] total incidences, [1] max elements per tile
     CUDA_CHECK(cudaMemsetAsync(misc, 0, 4 * sizeof(int), c->stream));
     exclusiveScanInt(c, c->tileNePrefix.p, n + 1, misc);
-    int h[2] = {0, 0}, nIface = 0;
+    int h[2] = {0, 0};
+    const int nIface = c->nIfaceNodes;
     CUDA_CHECK(cudaMemcpyAsync(h, misc, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(&nIface, binPtr + nCells, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     const int64_t nConn = (int64_t)c->nElems * npe;
     c->tileElems.reserve((size_t)h[0] + 8);
-    c->tileIdx16.reserve((size_t)nConn + 8);
+    c->tileLconn.reserve((size_t)h[0] * 4 + 8);
+    c->tileDst16.reserve((size_t)h[0] * 4 + 8);
+    int nodeListCap = 0;
     for (;;) {
         const int nTiles = divUp(std::max(n, 1), T);
         int CAP = 256;
         while (CAP < T * maxE) CAP <<= 1;
-        c->tileCnt.reserve((size_t)nTiles + 4);
-        CUDA_CHECK(cudaMemsetAsync(misc + 1, 0, sizeof(int), c->stream));
-        const size_t smem = (size_t)2 * CAP * sizeof(int);
-        if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_tile_build, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        c->tileCnt.reserve((size_t)3 * nTiles + 8);  // element count, node-list start, node-list count per tile
+        int* nodeStart = c->tileCnt.p + nTiles + 2;
+        int* nodeCnt = nodeStart + nTiles + 2;
+        if (nodeListCap == 0) nodeListCap = nTiles * 8 * T;
+        c->tileNodes.reserve((size_t)nodeListCap + 8);
+        CUDA_CHECK(cudaMemsetAsync(misc + 1, 0, 6 * sizeof(int), c->stream));
+        const size_t smem = (size_t)6 * CAP * sizeof(int);
+        CUDA_CHECK(cudaFuncSetAttribute(k_tile_build, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
         if (n > 0) {
             k_tile_build<<<nTiles, 256, smem, c->stream>>>(T, n, npe, CAP, c->tilePerm.p, c->tileNePrefix.p, c->n2ePtr.p, c->n2e.p, c->conn.p,
-                                                          c->tileElems.p, c->tileCnt.p, c->tileIdx16.p, misc + 1);
+                                                          c->tileElems.p, c->tileCnt.p, c->tileDst16.p, misc + 1, nodeStart, nodeCnt,
+                                                          c->tileNodes.p, nodeListCap, c->tileLconn.p);
             LAUNCH_CHECK(c);
         }
-        CUDA_CHECK(cudaMemcpyAsync(h + 1, misc + 1, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        int hm[5] = {0, 0, 0, 0, 0};  // max elements / listed nodes per tile, total node-list entries, overflow, max record slots
+        CUDA_CHECK(cudaMemcpyAsync(hm, misc + 1, 5 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        c->tileT = T, c->nTiles = n > 0 ? nTiles : 0, c->tileCap = (h[1] + 1) & ~1;
-        // the momentum pass keeps (dim+1) planes of 32-byte records per tile element: they must fit in shared memory
-        if ((size_t)c->tileCap * npe * 32 <= 200 * 1024 || T <= 8) break;
+        if (hm[2] > nodeListCap) {  // the node lists did not fit the guess: the cursor holds the exact total
+            nodeListCap = hm[2];
+            continue;
+        }
+        c->tileT = T, c->nTiles = n > 0 ? nTiles : 0, c->tileCap = (hm[4] + 1) & ~1, c->tileNodeCap = (hm[1] + 1) & ~1, c->tileMaxElems = hm[0];
+        c->tileNodeStart = nodeStart, c->tileNodeCnt = nodeCnt;
+        // staged node records (80 B per listed node) + one 32-byte record per (tile node, incident element) incidence
+        const size_t need = (size_t)c->tileNodeCap * 80 + (size_t)c->tileCap * 32;
+        if ((need <= 200 * 1024 && hm[3] == 0) || T <= 8) {
+            PFEM_REQUIRE(hm[3] == 0, PFEM_ERR_INVALID, "wc tiles: node list of a tile exceeds its build buffer");
+            break;
+        }
         T >>= 1;
+        nodeListCap = 0;
     }
-    PFEM_REQUIRE((size_t)c->tileCap * npe * 32 <= 227 * 1024, PFEM_ERR_INVALID, "wc tiles: tile element list too large for shared memory");
+    PFEM_REQUIRE((size_t)c->tileNodeCap * 80 + (size_t)c->tileCap * 32 <= 225 * 1024, PFEM_ERR_INVALID,
+                 "wc tiles: tile lists too large for shared memory");
     c->nIfaceTiles = c->nRanks > 1 ? std::min(c->nTiles, divUp(nIface, T)) : 0;
-    if (c->nRanks > 1 && !c->commStream) {
-        CUDA_CHECK(cudaStreamCreateWithFlags(&c->commStream, cudaStreamNonBlocking));
-        CUDA_CHECK(cudaEventCreateWithFlags(&c->evTile, cudaEventDisableTiming));
-        CUDA_CHECK(cudaEventCreateWithFlags(&c->evHalo, cudaEventDisableTiming));
-    }
     c->tilesValid = true;
+    static const bool verbose = getenv("PFEM_WC_VERBOSE") != nullptr;
+    if (verbose)
+        fprintf(stderr, "[pfem wc tiles] rank %d: %d owned nodes, T=%d, %d tiles (%d interface), max %d elements / %d listed nodes / "
+                        "%d record slots, element-list entries %d for %d elements\n",
+                c->rank, n, c->tileT, c->nTiles, c->nIfaceTiles, c->tileMaxElems, c->tileNodeCap, c->tileCap, h[0], c->nElems);
 }
 
 // PFEM_WC_CFG: 10 (default) chooses by size -- two-pass continuity + momentum + CFL-from-stored-values on meshes of >= 200 k
@@ -1176,7 +1230,12 @@ bool wcTwoPass(const pfem_ctx* c) {
 bool wcTiles(const pfem_ctx* c, const pfem_wc_params& p) {
     const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();
     if (p.eqType != PFEM_WC_CDS_DPDT || c->maxE > 255) return false;
-    return raw == 13 || (raw == 10 && wcTwoPass(c));
+    return raw == 13;  // opt-in: measured slower than the two-pass kernels on B200
+}
+// overlap of the halo exchanges with the interior node pass (PFEM_WC_OVERLAP=0 serialises them: A/B switch)
+bool wcOverlap() {
+    static const bool v = !(getenv("PFEM_WC_OVERLAP") && atoi(getenv("PFEM_WC_OVERLAP")) == 0);
+    return v;
 }
 bool wcTwoPassMom(const pfem_ctx* c) { return (c->wcVariant ? c->wcVariant : wcCfgRaw()) != 12; }
 int wcCfg(const pfem_ctx* c) {
@@ -1222,12 +1281,12 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         const size_t smem_ = (size_t)(256 / LPN_) * as.nbcap * sizeof(WcRec);                                       \
         PFEM_REQUIRE(smem_ <= 200 * 1024, PFEM_ERR_INVALID, "wc_step: node valence too large for shared memory");   \
         if (c->dim == 2) {                                                                                          \
-            if (smem_ > 48 * 1024)                                                                                  \
-                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<2, LPN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+            if (smem_ > 40 * 1024)                                                                                  \
+                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<2, LPN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN)); \
             KERNEL<2, LPN_, 2><<<grid_, 256, smem_, c->stream>>>(as, __VA_ARGS__);                                   \
         } else {                                                                                                    \
-            if (smem_ > 48 * 1024)                                                                                  \
-                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<3, LPN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_)); \
+            if (smem_ > 40 * 1024)                                                                                  \
+                CUDA_CHECK(cudaFuncSetAttribute(KERNEL<3, LPN_, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN)); \
             KERNEL<3, LPN_, 2><<<grid_, 256, smem_, c->stream>>>(as, __VA_ARGS__);                                   \
         }                                                                                                           \
     } while (0)
@@ -1238,17 +1297,22 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         else KERNEL<3, LPN_, 2><<<grid_, 256, 0, c->stream>>>(a, __VA_ARGS__);                  \
     } while (0)
     const bool tiles = wcTiles(c, p);
+    // two-pass node passes of a partitioned mesh run over the node order (interface nodes first) when it exists
+    const bool useOrder = c->nRanks > 1 && c->orderValid && !c->local && wcOverlap();
+    bool twoPassContDone = false;
     TileArgs ta;
     ta.perm = c->tilePerm.p, ta.nePrefix = c->tileNePrefix.p, ta.tileCnt = c->tileCnt.p, ta.tileElems = c->tileElems.p;
-    ta.idx16 = c->tileIdx16.p, ta.T = c->tileT, ta.nRows = c->nRows, ta.tile0 = 0;
+    ta.dst16 = c->tileDst16.p, ta.T = c->tileT, ta.nRows = c->nRows, ta.tile0 = 0;
+    ta.nodeStart = c->tileNodeStart, ta.nodeCnt = c->tileNodeCnt, ta.tileNodes = c->tileNodes.p, ta.lconn = c->tileLconn.p;
+    ta.nodeCap = std::max(c->tileNodeCap, 2), ta.slotCap = std::max(c->tileCap, 2);
     // tile passes of a partitioned mesh: the tiles holding interface nodes run first; the exchange of their results
     // (commStream) overlaps the interior tiles; the main stream joins before the next pass reads the ghosts
-    auto tilePass = [&](auto launchRange, auto exchange) {
-        const bool split = c->nRanks > 1 && c->commStream && !c->local;
-        const int nI = split ? c->nIfaceTiles : 0;
+    auto splitPass = [&](int nFirst, int nTotal, auto launchRange, auto exchange) {
+        const bool split = c->nRanks > 1 && c->commStream && !c->local && wcOverlap();
+        const int nI = split ? nFirst : 0;
         if (nI > 0) launchRange(0, nI);
         if (split) CUDA_CHECK(cudaEventRecord(c->evTile, c->stream));
-        if (c->nTiles > nI) launchRange(nI, c->nTiles - nI);
+        if (nTotal > nI) launchRange(nI, nTotal - nI);
         if (c->nRanks > 1) {
             if (split) {
                 cudaStream_t mainStream = c->stream;
@@ -1273,38 +1337,42 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
             auto range = [&](int t0, int nt) {
                 TileArgs tb = ta;
                 tb.tile0 = t0;
-                const size_t smem = (size_t)std::max(c->tileCap, 2) * 32;
+                const size_t smem = (size_t)ta.nodeCap * 80 + (size_t)std::max(c->tileCap, 2) * 32;
                 if (c->dim == 2) {
-                    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_wc_cont_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    CUDA_CHECK(cudaFuncSetAttribute(k_wc_cont_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
                     k_wc_cont_tile<2><<<nt, 256, smem, c->stream>>>(tb, a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
                 } else {
-                    if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_wc_cont_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    CUDA_CHECK(cudaFuncSetAttribute(k_wc_cont_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
                     k_wc_cont_tile<3><<<nt, 256, smem, c->stream>>>(tb, a, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
                 }
                 LAUNCH_CHECK(c);
             };
-            tilePass(range, [&]() { commHalo(c, c->X4b.p, c->V4b.p, 4); });
+            splitPass(c->nIfaceTiles, c->nTiles, range, [&]() { commHalo(c, c->X4b.p, c->V4b.p, 4); });
         } else
         if (p.eqType == PFEM_WC_CDS_DRHODT) PFEM_WC_LAUNCH_RHO(1, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, nullptr);
         else if (p.eqType == PFEM_WC_CDS_RHO) PFEM_WC_LAUNCH_RHO(2, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcF0.p);
         else if (cfg == 10) {  // two-pass: element records, then the nodal gather
-            const int ge = divUp(c->nElems, 256), gn = divUp((int64_t)c->nRows * 4, 256);
-            if (c->dim == 2) {
-                k_wc_cont_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+            const int ge = divUp(c->nElems, 256);
+            if (c->dim == 2) k_wc_cont_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+            else if (wcElemBlocks() == 4) k_wc_cont_elem<3, 4><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+            else if (wcElemBlocks() == 2) k_wc_cont_elem<3, 2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+            else k_wc_cont_elem<3, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
+            LAUNCH_CHECK(c);
+            auto range = [&](int k0, int cnt) {
+                WcArgs b = a;
+                b.nNodes = cnt, b.k0 = k0, b.order = useOrder ? c->tilePerm.p : nullptr;
+                const int gn = divUp((int64_t)cnt * 4, 256);
+                if (c->dim == 2) k_wc_cont_node<2, 4><<<gn, 256, 0, c->stream>>>(b, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
+                else k_wc_cont_node<3, 4><<<gn, 256, 0, c->stream>>>(b, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
                 LAUNCH_CHECK(c);
-                k_wc_cont_node<2, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
-            } else {
-                if (wcElemBlocks() == 4) k_wc_cont_elem<3, 4><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
-                else if (wcElemBlocks() == 2) k_wc_cont_elem<3, 2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
-                else k_wc_cont_elem<3, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, dt, dtPtr, p.K0, p.K0p, p.meduri, c->wcContRec.p);
-                LAUNCH_CHECK(c);
-                k_wc_cont_node<3, 4><<<gn, 256, 0, c->stream>>>(a, c->wcContRec.p, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p, c->wcHmin.p);
-            }
+            };
+            splitPass(useOrder ? c->nIfaceNodes : 0, c->nRows, range, [&]() { commHalo(c, c->X4b.p, c->V4b.p, 4); });
+            twoPassContDone = true;
         }
         else if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_cont_s, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         else if (cfg == 0) PFEM_WC_LAUNCH(k_wc_cont, 8, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
         else PFEM_WC_LAUNCH(k_wc_cont, 4, c->X4.p, c->V4.p, c->X4b.p, c->V4b.p);
-        if (!tiles) {
+        if (!tiles && !twoPassContDone) {
             LAUNCH_CHECK(c);
             if (c->nRanks > 1) commHalo(c, c->X4b.p, c->V4b.p, 4);  // (x, p_new) and (v_half, rho_new) of interface nodes
         }
@@ -1314,18 +1382,17 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         auto range = [&](int t0, int nt) {
             TileArgs tb = ta;
             tb.tile0 = t0;
-            const int cap = std::max(c->tileCap, 2);
-            const size_t smem = (size_t)cap * (c->dim + 1) * 32;
+            const size_t smem = (size_t)ta.nodeCap * 80 + (size_t)ta.slotCap * 32;
             if (c->dim == 2) {
-                if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_wc_mom_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_wc_mom_tile<2><<<nt, 256, smem, c->stream>>>(tb, a, cap, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
+                CUDA_CHECK(cudaFuncSetAttribute(k_wc_mom_tile<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
+                k_wc_mom_tile<2><<<nt, 256, smem, c->stream>>>(tb, a, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
             } else {
-                if (smem > 48 * 1024) CUDA_CHECK(cudaFuncSetAttribute(k_wc_mom_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                k_wc_mom_tile<3><<<nt, 256, smem, c->stream>>>(tb, a, cap, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
+                CUDA_CHECK(cudaFuncSetAttribute(k_wc_mom_tile<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PFEM_SMEM_OPTIN));
+                k_wc_mom_tile<3><<<nt, 256, smem, c->stream>>>(tb, a, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
             }
             LAUNCH_CHECK(c);
         };
-        tilePass(range, [&]() {
+        splitPass(c->nIfaceTiles, c->nTiles, range, [&]() {
             commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
             const size_t g0 = (size_t)c->nRows * 4, gn = (size_t)(c->nNodes - c->nRows) * 4;  // ghosts: (x, p_new) from X4b
             if (gn) CUDA_CHECK(cudaMemcpyAsync(c->X4.p + g0, c->X4b.p + g0, gn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
@@ -1334,18 +1401,26 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         PhaseScope ph(c, "Solving momentum eq");
         if (cfg == 10 && !wcTwoPassMom(c)) PFEM_WC_LAUNCH(k_wc_mom, 4, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
         else if (cfg == 10) {
-            const int ge = divUp(c->nElems, 256), gn = divUp((int64_t)c->nRows * 4, 256);
-            if (c->dim == 2) {
-                k_wc_mom_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+            const int ge = divUp(c->nElems, 256);
+            if (c->dim == 2) k_wc_mom_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+            else if (wcElemBlocks() == 4) k_wc_mom_elem<3, 4><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+            else if (wcElemBlocks() == 2) k_wc_mom_elem<3, 2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+            else k_wc_mom_elem<3, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+            LAUNCH_CHECK(c);
+            auto range = [&](int k0, int cnt) {
+                WcArgs b = a;
+                b.nNodes = cnt, b.k0 = k0, b.order = useOrder ? c->tilePerm.p : nullptr;
+                const int gn = divUp((int64_t)cnt * 4, 256);
+                if (c->dim == 2) k_wc_mom_node<2, 4><<<gn, 256, 0, c->stream>>>(b, c->wcElemRec.p, (size_t)c->nElems, c->n2eSlots.p, c->diagSlot.p, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
+                else k_wc_mom_node<3, 4><<<gn, 256, 0, c->stream>>>(b, c->wcElemRec.p, (size_t)c->nElems, c->n2eSlots.p, c->diagSlot.p, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
                 LAUNCH_CHECK(c);
-                k_wc_mom_node<2, 4><<<gn, 256, 0, c->stream>>>(a, c->wcElemRec.p, (size_t)c->nElems, c->n2eSlots.p, c->diagSlot.p, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
-            } else {
-                if (wcElemBlocks() == 4) k_wc_mom_elem<3, 4><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
-                else if (wcElemBlocks() == 2) k_wc_mom_elem<3, 2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
-                else k_wc_mom_elem<3, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
-                LAUNCH_CHECK(c);
-                k_wc_mom_node<3, 4><<<gn, 256, 0, c->stream>>>(a, c->wcElemRec.p, (size_t)c->nElems, c->n2eSlots.p, c->diagSlot.p, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
-            }
+            };
+            splitPass(useOrder ? c->nIfaceNodes : 0, c->nRows, range, [&]() {
+                commHalo(c, c->V4.p, c->A4.p, 4);  // (v, rho) and acceleration of interface nodes
+                const size_t g0 = (size_t)c->nRows * 4, gn = (size_t)(c->nNodes - c->nRows) * 4;  // ghosts: (x, p_new) from X4b
+                if (gn) CUDA_CHECK(cudaMemcpyAsync(c->X4.p + g0, c->X4b.p + g0, gn * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            });
+            return;
         }
         else if (cfg == 7) PFEM_WC_LAUNCH_S(k_wc_mom_s, 8, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
         else if (cfg == 0) PFEM_WC_LAUNCH(k_wc_mom, 8, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p);
@@ -1363,10 +1438,12 @@ void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int gr
     const double sc2 = securityCoeff * securityCoeff;
     // the stored he / nodal CFL values belong to the two-pass step that has just run with the same material constants
     if (afterTwoPassStep && p.eqType == PFEM_WC_CDS_DPDT && p.mu == c->cflMu && p.K0 == c->cflK0 && p.K0p == c->cflK0p) {
+        PhaseScope ph(c, "CFL nodal pass");
         k_wc_dt_nodal<<<grid, 256, 0, c->stream>>>(c->nRows, c->wcHmin.p, c->wcCfl2.p, sc2, c->dtPartial.p);
         LAUNCH_CHECK(c);
         return;
     }
+    PhaseScope ph(c, "CFL element pass");
     if (c->dim == 2)
         k_wc_dt<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
     else
@@ -1384,6 +1461,7 @@ void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     c->V4b.reserve(n4);
     if (p.eqType == PFEM_WC_CDS_RHO) c->wcF0.reserve((size_t)c->nNodes);
     if (wcTiles(c, p) && !c->tilesValid) buildTiles(c);
+    if (c->nRanks > 1 && !c->local && wcCfg(c) == 10 && !c->orderValid && wcOverlap()) buildNodeOrder(c);
     if (wcCfg(c) == 10) {  // before any graph capture
         c->wcElemRec.reserve((size_t)std::max(c->nElems, 1) * (c->dim + 1) * 4);
         c->wcContRec.reserve((size_t)std::max(c->nElems, 1) * 4);
@@ -1427,7 +1505,6 @@ int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double 
 int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff, double maxDT, double* dtInOut, double* elapsed) {
     PFEM_REQUIRE(dtInOut && nSteps >= 0, PFEM_ERR_INVALID, "wc_run: bad arguments");
     checkStepArgs(c, p, *dtInOut);
-    PFEM_REQUIRE(c->nRanks == 1, PFEM_ERR_STATE, "wc_run: single-GPU contexts only (use pfem_wc_step + pfem_wc_next_dt when sharded)");
     const int grid = std::max(1, std::min(c->smCount * 8, divUp(c->nElems, 256)));
     c->dtPartial.reserve(grid + 8);
     c->scal.reserve(SC_COUNT);
@@ -1435,6 +1512,26 @@ int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff
     double* dtDev = c->scal.p + SC_COUNT - 4;  // [dt, elapsed, nan]
     c->hScal[0] = *dtInOut, c->hScal[1] = 0.0, c->hScal[2] = 0.0;
     CUDA_CHECK(cudaMemcpyAsync(dtDev, c->hScal, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    if (c->nRanks > 1) {
+        // partitioned mesh: the same chain with the CFL minimum all-reduced on the device; nothing returns to the host between
+        // steps (no CUDA graph: the exchanges are NCCL calls / local-transport copies enqueued per step)
+        double* gmin = c->scal.p + SC_COUNT - 1;
+        for (int s = 0; s < nSteps; ++s) {
+            launchStep(c, p, *dtInOut, dtDev);
+            launchDt(c, p, securityCoeff, grid, wcCfg(c) == 10);
+            k_min_final<<<1, 256, 0, c->stream>>>(c->dtPartial.p, grid, gmin);
+            LAUNCH_CHECK(c);
+            commAllReduceMin(c, gmin);
+            k_dt_chain<<<1, 256, 0, c->stream>>>(gmin, 1, maxDT, dtDev);
+            LAUNCH_CHECK(c);
+        }
+        CUDA_CHECK(cudaMemcpyAsync(c->hScal, dtDev, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        c->cflFresh = false;
+        *dtInOut = c->hScal[0];
+        if (elapsed) *elapsed = c->hScal[1];
+        return (c->hScal[2] != 0.0 || c->hScal[0] != c->hScal[0]) ? PFEM_NAN : PFEM_OK;
+    }
     const bool wasProfiling = c->profiling;
     c->profiling = false;  // no event records inside a capture
     cudaGraph_t graph = nullptr;

@@ -17,13 +17,23 @@
 // which the halo exchange of their results overlaps the launch over the interior tiles (wc.cu: launchStep).
 #pragma once
 
+// staged node record: (x, y, z, p | u, v, w, rho) padded to 80 B -- an odd multiple of 16 B, so that LDS.128 of different
+// records spread over all banks (a 64-byte stride would put every record's first quarter in 2 of the 8 bank groups)
+constexpr int TILE_NSTRIDE = 10;
+
 struct TileArgs {
     const int* perm;        // owned nodes in tile order
     const int* nePrefix;    // prefix sum of the valences in tile order: tile t's element list starts at nePrefix[t*T]
     const int* tileCnt;     // per tile: number of elements
     const int* tileElems;
-    const unsigned short* idx16;  // per (node, incident element): tile element index | local node index << 14
-    int T, nRows, tile0;
+    const unsigned short* dst16;  // per tile element (same indexing as tileElems) and local node: the SLOT of that (node, element)
+                                  // incidence in the tile's record array -- the tile nodes' incidence lists laid end to end --
+                                  // or 0xffff when the node belongs to another tile
+    const int* nodeStart;   // per tile: offset of its node list (tile nodes + the other nodes of its elements) in tileNodes
+    const int* nodeCnt;
+    const int* tileNodes;
+    const unsigned short* lconn;  // per tile element (same indexing as tileElems): 4 indices into the tile's node list
+    int T, nRows, tile0, nodeCap, slotCap;
 };
 
 // ---- build ----------------------------------------------------------------------------------------------------------------
@@ -104,11 +114,16 @@ __global__ void k_tile_valence(int n, const int* __restrict__ perm, const int* _
 __global__ void __launch_bounds__(256) k_tile_build(int T, int nRows, int npe, int CAP, const int* __restrict__ perm,
                                                     const int* __restrict__ nePrefix, const int* __restrict__ n2ePtr,
                                                     const int* __restrict__ n2e, const int* __restrict__ conn, int* __restrict__ tileElems,
-                                                    int* __restrict__ tileCnt, unsigned short* __restrict__ idx16, int* __restrict__ maxCnt) {
+                                                    int* __restrict__ tileCnt, unsigned short* __restrict__ dst16, int* __restrict__ maxCnt,
+                                                    int* __restrict__ nodeStart, int* __restrict__ nodeCnt, int* __restrict__ tileNodes,
+                                                    int nodeListCap, unsigned short* __restrict__ lconn) {
+    // maxCnt: [0] max elements per tile, [1] max nodes per tile list, [2] bump cursor of tileNodes, [3] overflow flag,
+    //         [4] max incidences (record slots) per tile
     extern __shared__ int sm[];
     int* keys = sm;          // CAP
     int* uniq = sm + CAP;    // CAP
-    __shared__ int warpTot[8], total;
+    int* cand = sm + 2 * CAP;  // npe*CAP (<= 4 CAP): nodes of the tile's elements
+    __shared__ int warpTot[8], total, nodeOff;
     const int t = blockIdx.x, tid = threadIdx.x;
     const int k0 = t * T, k1 = min(nRows, k0 + T);
     const int base = nePrefix[k0], nInc = nePrefix[k1] - base;
@@ -175,10 +190,14 @@ __global__ void __launch_bounds__(256) k_tile_build(int T, int nRows, int npe, i
         tileCnt[t] = nU;
         atomicMax(maxCnt, nU);
     }
-    // index of every (node, incident element) pair in the tile's list, and the node's local index in the element
+    // slot of every (tile node, incident element) incidence = its position in the tile nodes' incidence lists laid end to end;
+    // stored per (tile element, local node) so that the element phase scatters its records straight to where the node phase
+    // reads them contiguously, in ascending element order
+    for (int j = tid; j < nU * 4; j += 256) dst16[(size_t)base * 4 + j] = 0xffffu;
+    __syncthreads();
     for (int s = tid >> 2; s < k1 - k0; s += 64) {
         const int i = perm[k0 + s];
-        const int eb = n2ePtr[i], ne = n2ePtr[i + 1] - eb;
+        const int eb = n2ePtr[i], ne = n2ePtr[i + 1] - eb, off = nePrefix[k0 + s] - base;
         for (int k = tid & 3; k < ne; k += 4) {
             const int e = n2e[eb + k];
             int lo = 0, hi = nU - 1;
@@ -189,9 +208,122 @@ __global__ void __launch_bounds__(256) k_tile_build(int T, int nRows, int npe, i
             }
             int li = 0;
             for (int q = 1; q < npe; ++q) li = (conn[(size_t)e * npe + q] == i) ? q : li;
-            idx16[eb + k] = (unsigned short)(lo | (li << 14));
+            dst16[((size_t)base + lo) * 4 + li] = (unsigned short)(off + k);
         }
     }
+    if (tid == 0) atomicMax(maxCnt + 4, nInc);
+    // ---- the tile's node list = sorted distinct nodes of its elements; local connectivity of every element ----------------
+    const int CAP2 = 4 * CAP, nCand = nU * npe;
+    for (int j = tid; j < CAP2; j += 256) cand[j] = j < nCand ? conn[(size_t)uniq[j / npe] * npe + (j % npe)] : 0x7fffffff;
+    __syncthreads();
+    for (int size = 2; size <= CAP2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int j = tid; j < CAP2 / 2; j += 256) {
+                const int lo = 2 * j - (j & (stride - 1));
+                const int hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const int a = cand[lo], b = cand[hi];
+                if ((a > b) == up) {
+                    cand[lo] = b;
+                    cand[hi] = a;
+                }
+            }
+            __syncthreads();
+        }
+    const int per2 = CAP2 / 256;
+    int cnt2 = 0;
+    for (int q = 0; q < per2; ++q) {
+        const int j = tid * per2 + q;
+        if (j < nCand && (j == 0 || cand[j] != cand[j - 1])) ++cnt2;
+    }
+    int inc2 = cnt2;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (lane >= o) inc2 += v;
+    }
+    __syncthreads();
+    if (lane == 31) warpTot[w] = inc2;
+    __syncthreads();
+    if (tid == 0) {
+        int s2 = 0;
+        for (int q = 0; q < 8; ++q) {
+            const int v = warpTot[q];
+            warpTot[q] = s2;
+            s2 += v;
+        }
+        total = s2;
+        nodeOff = atomicAdd(maxCnt + 2, s2);
+        nodeStart[t] = nodeOff;
+        nodeCnt[t] = s2;
+        atomicMax(maxCnt + 1, s2);
+        if (s2 > CAP) atomicOr(maxCnt + 3, 1);
+    }
+    __syncthreads();
+    const int nLoc = total;
+    int pos2 = inc2 - cnt2 + warpTot[w];
+    for (int q = 0; q < per2; ++q) {  // distinct nodes -> keys[] (free since the element sort) and the global list
+        const int j = tid * per2 + q;
+        if (j < nCand && (j == 0 || cand[j] != cand[j - 1])) {
+            if (pos2 < CAP) keys[pos2] = cand[j];
+            if (nodeOff + pos2 < nodeListCap) tileNodes[nodeOff + pos2] = cand[j];  // (too small: the host re-runs with the total)
+            ++pos2;
+        }
+    }
+    __syncthreads();
+    if (nLoc <= CAP)
+        for (int j = tid; j < nCand; j += 256) {
+            const int nd = conn[(size_t)uniq[j / npe] * npe + (j % npe)];
+            int lo = 0, hi = nLoc - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (keys[mid] < nd) lo = mid + 1;
+                else hi = mid;
+            }
+            lconn[((size_t)base + j / npe) * 4 + (j % npe)] = (unsigned short)lo;
+        }
+}
+
+// ---- run time ---------------------------------------------------------------------------------------------------------------
+// Stage the records (x, y, z, p | u, v, w, rho) of the tile's node list in shared memory: one independent pair of 32-byte loads
+// per thread, all in flight at once -- the element phase then never waits on global memory.
+__device__ __forceinline__ void stageTileNodes(const TileArgs& ta, int t, const double* __restrict__ X4, const double* __restrict__ V4,
+                                               double* __restrict__ nodeS) {
+    const int off = ta.nodeStart[t], n = ta.nodeCnt[t];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int nd = __ldg(ta.tileNodes + off + k);
+        const D4 xr = ld4(X4 + (size_t)nd * 4), vr = ld4(V4 + (size_t)nd * 4);
+        double* r = nodeS + (size_t)k * TILE_NSTRIDE;
+        *reinterpret_cast<double2*>(r) = make_double2(xr.x, xr.y);
+        *reinterpret_cast<double2*>(r + 2) = make_double2(xr.z, xr.w);
+        *reinterpret_cast<double2*>(r + 4) = make_double2(vr.x, vr.y);
+        *reinterpret_cast<double2*>(r + 6) = make_double2(vr.z, vr.w);
+    }
+}
+// element j of the tile from the staged records: same values, same arithmetic as loadElem
+template <int DIM>
+__device__ __forceinline__ void loadElemStaged(const double* __restrict__ nodeS, const unsigned short* __restrict__ lc,
+                                               double (&px3)[DIM + 1][3], double (&xw)[DIM + 1], double (&vel)[DIM + 1][DIM],
+                                               double (&vw)[DIM + 1], ElemGeo<DIM>& G) {
+    constexpr int NPE = DIM + 1;
+    const uint2 w = *reinterpret_cast<const uint2*>(lc);  // 4 x 16-bit local node indices
+    const unsigned li[4] = {w.x & 0xffffu, w.x >> 16, w.y & 0xffffu, w.y >> 16};
+    double px[NPE][DIM];
+#pragma unroll
+    for (int m = 0; m < NPE; ++m) {
+        const double* r = nodeS + (size_t)li[m] * TILE_NSTRIDE;
+        const double2 x01 = *reinterpret_cast<const double2*>(r), x23 = *reinterpret_cast<const double2*>(r + 2);
+        const double2 v01 = *reinterpret_cast<const double2*>(r + 4), v23 = *reinterpret_cast<const double2*>(r + 6);
+        px[m][0] = x01.x, px[m][1] = x01.y;
+        px3[m][0] = x01.x, px3[m][1] = x01.y, px3[m][2] = x23.x;
+        vel[m][0] = v01.x, vel[m][1] = v01.y;
+        if constexpr (DIM == 3) {
+            px[m][2] = x23.x;
+            vel[m][2] = v23.x;
+        }
+        xw[m] = x23.y;
+        vw[m] = v23.y;
+    }
+    buildGeo<DIM>(px, G);
 }
 
 // ---- continuity, CDS_dpdt: element phase into shared memory, then the ordered nodal sum + epilogue -----------------------
@@ -201,23 +333,19 @@ __global__ void __launch_bounds__(256, 2) k_wc_cont_tile(const TileArgs ta, cons
                                                          double* __restrict__ hminOut) {
     constexpr int NPE = DIM + 1;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
-    extern __shared__ __align__(32) double recS[];  // cnt x (alpha, beta, V/NPE, he)
+    extern __shared__ __align__(32) double smemT[];
+    double* nodeS = smemT;                                        // nodeCap x TILE_NSTRIDE
+    double* recS = smemT + (size_t)ta.nodeCap * TILE_NSTRIDE;     // slotCap x (F0 contribution, V/NPE, he, -)
     const int t = ta.tile0 + blockIdx.x, tid = threadIdx.x;
-    const int start = ta.nePrefix[(size_t)t * ta.T], cnt = ta.tileCnt[t];
+    const int k0 = t * ta.T;
+    const int start = ta.nePrefix[k0], cnt = ta.tileCnt[t];
     const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
+    stageTileNodes(ta, t, X4, V4, nodeS);
+    __syncthreads();
     for (int j = tid; j < cnt; j += 256) {
-        const int e = __ldg(ta.tileElems + start + j);
-        int nd[NPE];
-        if constexpr (DIM == 3) {
-            const int4 q = __ldg(reinterpret_cast<const int4*>(a.conn + (size_t)e * 4));
-            nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
-        } else {
-#pragma unroll
-            for (int m = 0; m < NPE; ++m) nd[m] = __ldg(a.conn + (size_t)e * NPE + m);
-        }
-        double P[NPE], vel[NPE][DIM], rho[NPE];
+        double P[NPE], vel[NPE][DIM], rho[NPE], px[NPE][3];
         ElemGeo<DIM> G;
-        loadElem<DIM>(X4, V4, nd, P, vel, rho, G);
+        loadElemStaged<DIM>(nodeS, ta.lconn + ((size_t)start + j) * 4, px, P, vel, rho, G);
         double sumP = 0, divv = 0;
 #pragma unroll
         for (int q = 0; q < NPE; ++q) {
@@ -229,32 +357,31 @@ __global__ void __launch_bounds__(256, 2) k_wc_cont_tile(const TileArgs ta, cons
         const double adv = -dtStep * G.V * divv;
         const double alpha = adv * (a.K0 / NPE + a.K0p * PHI * sumP) + (a.meduri ? G.V * PHI * sumP : 0.0);
         const double beta = adv * (a.K0p * PHI) + (a.meduri ? G.V * PHI : G.V / NPE);
-        double px[NPE][3];
+        const double he = elemHe<DIM>(px), mq = G.V / NPE;
+        const uint2 dw = *reinterpret_cast<const uint2*>(ta.dst16 + ((size_t)start + j) * 4);
+        const unsigned dst[4] = {dw.x & 0xffffu, dw.x >> 16, dw.y & 0xffffu, dw.y >> 16};
 #pragma unroll
-        for (int m = 0; m < NPE; ++m) {
-            const double* xp = X4 + (size_t)nd[m] * 4;  // L1 hits: loadElem just read these records
-            px[m][0] = xp[0], px[m][1] = xp[1], px[m][2] = xp[2];
-        }
-        double* r = recS + (size_t)j * 4;
-        *reinterpret_cast<double2*>(r) = make_double2(alpha, beta);
-        *reinterpret_cast<double2*>(r + 2) = make_double2(G.V / NPE, elemHe<DIM>(px));
+        for (int q = 0; q < NPE; ++q)
+            if (dst[q] != 0xffffu) {
+                double* r = recS + (size_t)dst[q] * 4;
+                *reinterpret_cast<double2*>(r) = make_double2(alpha + beta * P[q], mq);
+                r[2] = he;
+            }
     }
     __syncthreads();
     const int s = tid >> 2, sub = tid & 3;
-    const int k = t * ta.T + s;
+    const int k = k0 + s;
     const bool valid = s < ta.T && k < ta.nRows;
     const int i = valid ? __ldg(ta.perm + k) : 0;
     double m = 0, F0 = 0, hmin = 1.7976931348623157e308;
     if (valid) {
-        const int eb = a.n2ePtr[i], end = a.n2ePtr[i + 1];
-        const double pi = X4[(size_t)i * 4 + 3];
-        for (int pos = eb + sub; pos < end; pos += 4) {
-            const unsigned w = __ldg(ta.idx16 + pos);
-            const double* r = recS + (size_t)(w & 0x3fffu) * 4;
-            const double2 r01 = *reinterpret_cast<const double2*>(r), r23 = *reinterpret_cast<const double2*>(r + 2);
-            F0 += r01.x + r01.y * pi;
-            m += r23.x;
-            hmin = nanMin(r23.y, hmin);
+        const int off = ta.nePrefix[k] - start, ne = ta.nePrefix[k + 1] - ta.nePrefix[k];
+        for (int kk = sub; kk < ne; kk += 4) {
+            const double* r = recS + (size_t)(off + kk) * 4;
+            const double2 r01 = *reinterpret_cast<const double2*>(r);
+            F0 += r01.x;
+            m += r01.y;
+            hmin = nanMin(r[2], hmin);
         }
     }
     m = groupSum<4>(m);
@@ -279,28 +406,24 @@ __global__ void __launch_bounds__(256, 2) k_wc_cont_tile(const TileArgs ta, cons
 
 // ---- momentum: per-(element, local node) records (F, lumped rho-mass) in shared memory, plane per local node ------------------
 template <int DIM>
-__global__ void __launch_bounds__(256, 2) k_wc_mom_tile(const TileArgs ta, const WcArgs a, int cap, const double* __restrict__ X4,
+__global__ void __launch_bounds__(256, 2) k_wc_mom_tile(const TileArgs ta, const WcArgs a, const double* __restrict__ X4,
                                                         const double* __restrict__ V4, double* __restrict__ V4out,
                                                         double* __restrict__ A4out, double* __restrict__ X4out, double* __restrict__ cfl2) {
     constexpr int NPE = DIM + 1;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
-    extern __shared__ __align__(32) double recS[];  // NPE planes of cap records (Fx, Fy, Fz, mass)
+    extern __shared__ __align__(32) double smemT[];
+    double* nodeS = smemT;                                        // nodeCap x TILE_NSTRIDE
+    double* recS = smemT + (size_t)ta.nodeCap * TILE_NSTRIDE;     // slotCap x (Fx, Fy, Fz, lumped mass)
     const int t = ta.tile0 + blockIdx.x, tid = threadIdx.x;
-    const int start = ta.nePrefix[(size_t)t * ta.T], cnt = ta.tileCnt[t];
+    const int k0 = t * ta.T;
+    const int start = ta.nePrefix[k0], cnt = ta.tileCnt[t];
     const double dtStep = a.dtPtr ? *a.dtPtr : a.dt;
+    stageTileNodes(ta, t, X4, V4, nodeS);
+    __syncthreads();
     for (int j = tid; j < cnt; j += 256) {
-        const int e = __ldg(ta.tileElems + start + j);
-        int nd[NPE];
-        if constexpr (DIM == 3) {
-            const int4 q = __ldg(reinterpret_cast<const int4*>(a.conn + (size_t)e * 4));
-            nd[0] = q.x, nd[1] = q.y, nd[2] = q.z, nd[3] = q.w;
-        } else {
-#pragma unroll
-            for (int m = 0; m < NPE; ++m) nd[m] = __ldg(a.conn + (size_t)e * NPE + m);
-        }
-        double P[NPE], vel[NPE][DIM], rho[NPE];
+        double P[NPE], vel[NPE][DIM], rho[NPE], px[NPE][3];
         ElemGeo<DIM> G;
-        loadElem<DIM>(X4, V4, nd, P, vel, rho, G);
+        loadElemStaged<DIM>(nodeS, ta.lconn + ((size_t)start + j) * 4, px, P, vel, rho, G);
         double sumP = 0, sumR = 0;
         double Gm[DIM][DIM];  // G_ac = sum_j v_{j,a} g[c][j]
 #pragma unroll
@@ -329,8 +452,11 @@ __global__ void __launch_bounds__(256, 2) k_wc_mom_tile(const TileArgs ta, const
                 if (c == aa) sv -= (2.0 / 3.0) * tr;
                 sig[aa][c] = a.mu * sv;
             }
+        const uint2 dw = *reinterpret_cast<const uint2*>(ta.dst16 + ((size_t)start + j) * 4);
+        const unsigned dst[4] = {dw.x & 0xffffu, dw.x >> 16, dw.y & 0xffffu, dw.y >> 16};
 #pragma unroll
         for (int q = 0; q < NPE; ++q) {
+            if (dst[q] == 0xffffu) continue;  // node q belongs to another tile (which computes this element too)
             const double li_mass = G.V * PHI * (rho[q] + sumR);  // lumped rho-mass == sum_g w (N.rho) N_q
             double F[3] = {0.0, 0.0, 0.0};
 #pragma unroll
@@ -340,24 +466,23 @@ __global__ void __launch_bounds__(256, 2) k_wc_mom_tile(const TileArgs ta, const
                 for (int c = 0; c < DIM; ++c) sg += sig[aa][c] * G.g[c][q];
                 F[aa] = -G.V * sg + G.V * pbar * G.g[aa][q] + a.body[aa] * li_mass;
             }
-            double* r = recS + ((size_t)q * cap + j) * 4;
+            double* r = recS + (size_t)dst[q] * 4;
             *reinterpret_cast<double2*>(r) = make_double2(F[0], F[1]);
             *reinterpret_cast<double2*>(r + 2) = make_double2(F[2], li_mass);
         }
     }
     __syncthreads();
     const int s = tid >> 2, sub = tid & 3;
-    const int k = t * ta.T + s;
+    const int k = k0 + s;
     const bool valid = s < ta.T && k < ta.nRows;
     const int i = valid ? __ldg(ta.perm + k) : 0;
     double M = 0, F[DIM];
 #pragma unroll
     for (int c = 0; c < DIM; ++c) F[c] = 0;
     if (valid) {
-        const int eb = a.n2ePtr[i], end = a.n2ePtr[i + 1];
-        for (int pos = eb + sub; pos < end; pos += 4) {
-            const unsigned w = __ldg(ta.idx16 + pos);
-            const double* r = recS + ((size_t)(w >> 14) * cap + (w & 0x3fffu)) * 4;
+        const int off = ta.nePrefix[k] - start, ne = ta.nePrefix[k + 1] - ta.nePrefix[k];
+        for (int kk = sub; kk < ne; kk += 4) {
+            const double* r = recS + (size_t)(off + kk) * 4;
             const double2 r01 = *reinterpret_cast<const double2*>(r), r23 = *reinterpret_cast<const double2*>(r + 2);
             F[0] += r01.x;
             F[1] += r01.y;

@@ -46,7 +46,8 @@ def run_ranks(mesh, n_ranks, fn, devices=None, native_partition=True):
         t.join()
     handle.close()
     group.close()
-    for e in errors:
-        if e is not None:
-            raise e
+    # report the root cause, not the "aborted by another rank" it caused on the other ranks
+    real = [e for e in errors if e is not None and "aborted by another rank" not in str(e)]
+    for e in real + [e for e in errors if e is not None]:
+        raise e
     return results

