@@ -62,9 +62,28 @@ struct MgLevel {
     int ncLocal = 0, rowOff = 0;
     std::vector<int64_t> rowCounts, rowDispls;  // per rank, coarse rows
     std::vector<int64_t> blkCounts, blkDispls;  // per rank, coarse blocks
+    void resetLogical() {  // a recycled level object keeps its buffers, nothing else
+        n = nVec = maxNb = nc = ncLocal = rowOff = 0;
+        nBlocks = 0;
+        nbrPtr = nbr = diagSlot = nullptr;
+        Aval = X = nullptr;
+        distributed = nextReplicated = false;
+        plan = nullptr;
+        omega = 0.5;
+    }
 };
 struct MgHierarchy {
-    std::vector<std::unique_ptr<MgLevel>> lev;
+    // The level objects (and every device buffer they own) persist across symbolic rebuilds: an incompressible run remeshes
+    // every time step, and freeing / re-allocating ~100 device buffers per step costs tens of milliseconds of cudaFree /
+    // cudaMalloc (measured: 60-360 ms per rebuild, growing).  `lev` lists the levels of the current hierarchy.
+    std::vector<std::unique_ptr<MgLevel>> pool;
+    std::vector<MgLevel*> lev;
+    DevBuf<double> sBox, sXc, sTmp, sPart;  // scratch of the symbolic phase (grow-only)
+    DevBuf<int> sKey, sCell;
+    MgLevel& levelObject(size_t l) {
+        while (pool.size() <= l) pool.push_back(std::make_unique<MgLevel>());
+        return *pool[l];
+    }
     DevBuf<double> dense;  // coarsest level: A^-1, nD x nD
     DevBuf<int> flag;
     int nD = 0;
@@ -732,13 +751,15 @@ int mgReplicateNodes() { return getenv("PFEM_MG_REPL_NODES") ? atoi(getenv("PFEM
 // lists in ascending order, coarse coordinates written to Xc (4 doubles per aggregate).  Returns false when this rank's
 // share cannot be coarsened; nc = local aggregate count.
 bool localAggregate(pfem_ctx* c, MgHierarchy& H, MgLevel& L, double& cellSize, int& ncOut, DevBuf<double>& XcLocal) {
+    DevBuf<double>& box = H.sBox;
+    DevBuf<int>& key = H.sKey;
+    DevBuf<int>& cell = H.sCell;
     const int dim = c->dim, n = L.n;
     ncOut = 0;
     if (n < 1) return false;
     const double target = dim == 3 ? 8.0 : 4.0;
     c->scratchI.reserve((size_t)std::max(L.nVec, c->nNodes) + 64);
     H.flag.reserve(16);
-    DevBuf<double> box;
     box.reserve(8);
     k_bbox<<<1, 1024, 0, c->stream>>>(L.X, n, dim, box.p);
     LAUNCH_CHECK(c);
@@ -756,7 +777,6 @@ bool localAggregate(pfem_ctx* c, MgHierarchy& H, MgLevel& L, double& cellSize, i
     double Hc = cellSize > 0.0 ? cellSize : 2.0 * std::pow(vol / n, 1.0 / dim);
     const double slack = cellSize > 0.0 ? 3.0 : 1.7;  // a suggested size is only overridden when it is far off
     L.agg.reserve((size_t)L.nVec + 4);
-    DevBuf<int> key, cell;
     key.reserve(n);
     int nc = 0;
     for (int attempt = 0; attempt < 6; ++attempt) {
@@ -811,7 +831,7 @@ bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSi
     const int dim = c->dim, n = L.n, BS = dim + 1;
     const bool multi = L.distributed && c->nRanks > 1;
     int nc = 0;
-    DevBuf<double> XcLocal;
+    DevBuf<double>& XcLocal = H.sXc;
     bool ok = localAggregate(c, H, L, cellSize, nc, XcLocal);
     const int R = c->nRanks, me = c->rank;
     std::vector<double> all(2 * (size_t)R, 0.0);
@@ -833,7 +853,7 @@ bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSi
     L.rowOff = 0;
     H.flag.reserve(16);
     int* misc = H.flag.p;
-    DevBuf<double> tmp;  // aggregate ids of the fine vector entries as doubles (halo exchange payload)
+    DevBuf<double>& tmp = H.sTmp;  // aggregate ids of the fine vector entries as doubles (halo exchange payload)
 
     if (!multi) {
         // ---- single rank, or a replicated level: the whole level is here ------------------------------------------------
@@ -944,9 +964,12 @@ bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSi
         std::vector<double> aggAll((size_t)L.nVec);
         CUDA_CHECK(cudaMemcpyAsync(aggAll.data(), tmp.p, (size_t)L.nVec * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
-        C.ownPlan.reset(new HaloPlan());
-        C.ownPlan->sendIdx.accounting = C.ownPlan->sendBuf.accounting = &c->deviceBytes;
+        if (!C.ownPlan) {
+            C.ownPlan.reset(new HaloPlan());
+            C.ownPlan->sendIdx.accounting = C.ownPlan->sendBuf.accounting = &c->deviceBytes;
+        }
         HaloPlan& CP = *C.ownPlan;
+        CP.clear();
         std::vector<int> ghostAgg((size_t)(L.nVec - n), 0);
         int nGhostC = 0;
         for (const auto& p : L.plan->peers) {
@@ -1031,16 +1054,17 @@ void buildSymbolic(pfem_ctx* c, MgHierarchy& H) {
     H.dropGraphs();
     H.lev.clear();
     H.symbolicFailed = false;
-    auto L0 = std::make_unique<MgLevel>();
+    MgLevel* L0 = &H.levelObject(0);
+    L0->resetLogical();
     L0->n = c->nRows, L0->nVec = c->nNodes, L0->maxNb = c->maxNb, L0->nBlocks = c->nBlocks;
     L0->distributed = c->nRanks > 1;
     L0->plan = &c->plan;
-    H.lev.push_back(std::move(L0));
+    H.lev.push_back(L0);
     // node spacing of level 0 from the mean element size: h0 = (mean |detJ|)^(1/dim)
     double cellSize = 0.0;
     if (c->nElems > 0) {
         const int nb = 256;
-        DevBuf<double> part;
+        DevBuf<double>& part = H.sPart;
         part.reserve(nb + 8);
         k_vol_partial<<<nb, 256, 0, c->stream>>>(c->conn.p, c->nElems, c->dim, c->X4.p, part.p);
         LAUNCH_CHECK(c);
@@ -1058,10 +1082,11 @@ void buildSymbolic(pfem_ctx* c, MgHierarchy& H) {
         }
         allocVectors(c, L, BS);
         if (!L.distributed && L.n <= COARSEST_NODES) break;  // (a distributed level's size is a per-rank number: coarsen() decides)
-        auto C = std::make_unique<MgLevel>();
+        MgLevel* C = &H.levelObject((size_t)l + 1);
+        C->resetLogical();
         if (!coarsen(c, H, L, *C, cellSize)) break;
         cellSize *= 2.0;
-        H.lev.push_back(std::move(C));
+        H.lev.push_back(C);
     }
     H.symbolicValid = true;
     H.numericValid = false;
