@@ -1278,7 +1278,12 @@ void mgApply(pfem_ctx* c, double* out) {
     PhaseScope ph(c, "Preconditioner apply");
     MgHierarchy& H = *c->mg;
     static const bool noGraph = getenv("PFEM_MG_NOGRAPH") != nullptr;
-    if (noGraph || H.graphBroken || c->profileDetail || c->nRanks > 1) {  // no NCCL calls inside a capture
+    // partitioned mesh: the cycle runs un-graphed.  Capturing the NCCL point-to-point exchanges of the cycle into the graph
+    // (PFEM_MG_GRAPH_NCCL=1) was tried on 2 and 4 B200s and DEADLOCKED in the first replay (round 2, profiles/README.md): the
+    // ranks capture two graphs each (one per output vector) whose grouped send/recv lists differ per rank; kept opt-in only.
+    static const bool graphNccl = getenv("PFEM_MG_GRAPH_NCCL") && atoi(getenv("PFEM_MG_GRAPH_NCCL")) == 1;
+    const bool multiNoGraph = c->nRanks > 1 && (c->local || !graphNccl);
+    if (noGraph || H.graphBroken || c->profileDetail || multiNoGraph) {
         cycle(c, H, 0, H.lev[0]->b.p, out);
         return;
     }
@@ -1288,7 +1293,13 @@ void mgApply(pfem_ctx* c, double* out) {
     mix((unsigned long long)(uintptr_t)H.lev[0]->Aval), mix((unsigned long long)(uintptr_t)H.lev[0]->nbr);
     mix((unsigned long long)(uintptr_t)H.lev[0]->b.p), mix((unsigned long long)H.lev.size()), mix((unsigned long long)H.nu), mix((unsigned long long)H.nuCoarse);
     mix((unsigned long long)__double_as_longlong_host(H.over)), mix(H.denseOk ? 1ull : 0ull), mix((unsigned long long)H.nD);
-    for (auto& L : H.lev) mix((unsigned long long)(uintptr_t)L->Dw.p), mix((unsigned long long)(uintptr_t)L->Af.p), mix((unsigned long long)L->n);
+    for (auto& L : H.lev) {
+        mix((unsigned long long)(uintptr_t)L->Dw.p), mix((unsigned long long)(uintptr_t)L->Af.p), mix((unsigned long long)L->n);
+        if (L->distributed && L->plan) {  // a captured exchange bakes in the pack buffer and the send list
+            L->plan->sendBuf.reserve((size_t)L->plan->nSendTotal * (c->dim + 1) + 8);
+            mix((unsigned long long)(uintptr_t)L->plan->sendBuf.p), mix((unsigned long long)(uintptr_t)L->plan->sendIdx.p);
+        }
+    }
     for (auto& g : H.graphs)
         if (g.out == out && g.sig == sig) {
             CUDA_CHECK(cudaGraphLaunch(g.exec, c->stream));

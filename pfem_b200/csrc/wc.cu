@@ -1308,7 +1308,8 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
     // tile passes of a partitioned mesh: the tiles holding interface nodes run first; the exchange of their results
     // (commStream) overlaps the interior tiles; the main stream joins before the next pass reads the ghosts
     auto splitPass = [&](int nFirst, int nTotal, auto launchRange, auto exchange) {
-        const bool split = c->nRanks > 1 && c->commStream && !c->local && wcOverlap();
+        // (with phase timers on, the pass runs serialised so that every phase is timed on one stream)
+        const bool split = c->nRanks > 1 && c->commStream && !c->local && wcOverlap() && !c->profiling;
         const int nI = split ? nFirst : 0;
         if (nI > 0) launchRange(0, nI);
         if (split) CUDA_CHECK(cudaEventRecord(c->evTile, c->stream));
