@@ -74,6 +74,11 @@ typedef struct pfem_wc_params {
     int32_t eqType;
 } pfem_wc_params;
 
+/* Boussinesq constants (Material.k, cv, alpha, Tr: IncompNewton/MomContEquation.inl:32-38, WCompNewton/HeatEquation.inl:24-27) */
+typedef struct pfem_thermal_params {
+    double k, cv, alpha, Tr;
+} pfem_thermal_params;
+
 typedef struct pfem_info {
     int32_t dim, device, nRanks, rank;
     int64_t nNodes, nElems, nDof;
@@ -126,6 +131,30 @@ int pfem_set_facets(pfem_ctx* ctx, int64_t nFacets, const uint64_t* facetNodes, 
  * explicit step adds it to F for facets entirely on the free surface (WCompNewton/MomEquation.inl:312-336).  Default 0
  * (the reference's `if(m_gamma < 1e-15) continue`). */
 int pfem_set_surface_tension(pfem_ctx* ctx, double gamma);
+
+/* ---- temperature / shear-rate dependent factors and the heat equations ---- */
+/* Problem ids "Boussinesq" / "BoussinesqWC": with thermal parameters set, pfem_pspg_assemble uses the F factor
+ * rho (1 - alpha (T - Tr)) and the H factor (1 - alpha (T - Tr)) (MomContEquation.inl:166-199), pfem_wc_step runs
+ * m_solveBoussinesqWC (WCompNewton/Solver.cpp:278-320: explicit heat equation HeatEquation.inl:154-298, then continuity,
+ * then momentum with the buoyancy factor MomEquation.inl:105-112) and pfem_wc_next_dt takes the thermal diffusivity
+ * k/(cv rho) into account (Solver.cpp:214-216).  NULL switches the factors off. */
+int pfem_set_thermal(pfem_ctx* ctx, const pfem_thermal_params* t);
+/* Problem id "Bingham": K factor mu + tau0 (1 - exp(-mReg gammaDot))/gammaDot (MomContEquation.inl:102-119). */
+int pfem_set_bingham(pfem_ctx* ctx, int on, double tau0, double mReg);
+/* nodal temperature (the extra node state of the Boussinesq problems), T[nNodes] */
+int pfem_set_temperature(pfem_ctx* ctx, const double* T);
+int pfem_get_temperature(pfem_ctx* ctx, double* T);
+/* mask[n] != 0 <=> getBcTagFlags(node tag, flag 1): a "<type>T" Lua function exists; values[n] = its value
+ * (WCompNewton/HeatEquation.inl:203-216, IncompNewton/HeatEquation.inl:383-408) */
+int pfem_set_temperature_bc(pfem_ctx* ctx, const uint8_t* mask, const double* values);
+/* HeatEqIncompNewton::m_buildAb + m_applyBC (IncompNewton/HeatEquation.inl:227-412, no flux facet terms): scalar system
+ * A = M(cv rho) + dt L(k), b = M thetaPrev on the current positions.  Single-GPU contexts. */
+int pfem_heat_assemble(pfem_ctx* ctx, double rho, double cv, double k, double dt, const double* thetaPrev);
+/* Eigen::ConjugateGradient::solveWithGuess of that system (HeatEquation.inl:129-135): Jacobi-preconditioned CG started
+ * from the temperature on the device (zero if none); the solution becomes the device temperature; T may be NULL. */
+int pfem_heat_solve(pfem_ctx* ctx, double relTol, int maxIter, double* T, int* iters, double* relRes);
+/* the heat system in the reference's format (column-major compressed, masked rows reduced to their diagonal); parity only */
+int pfem_heat_export_csc(pfem_ctx* ctx, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b);
 
 /* ---- incompressible PSPG (MomContEqIncompNewton<dim>) ------------------------------- */
 /* m_buildAbPSPG + m_applyBCPSPG (PSPG.inl:7-146, 149-235; facet terms: pfem_set_surface_tension).  qPrev: (dim+1)*nNodes. */

@@ -32,6 +32,10 @@ class WcParams(C.Structure):
                 ("bodyForce", C.c_double * 3), ("meduri", C.c_int32), ("eqType", C.c_int32)]
 
 
+class ThermalParams(C.Structure):
+    _fields_ = [("k", C.c_double), ("cv", C.c_double), ("alpha", C.c_double), ("Tr", C.c_double)]
+
+
 class Info(C.Structure):
     _fields_ = [("dim", C.c_int32), ("device", C.c_int32), ("nRanks", C.c_int32), ("rank", C.c_int32),
                 ("nNodes", C.c_int64), ("nElems", C.c_int64), ("nDof", C.c_int64), ("nnzBlocks", C.c_int64),
@@ -59,6 +63,14 @@ SYMBOLS = {
     "pfem_set_dirichlet": (C.c_int, [_VP, _U8P, _DP]),
     "pfem_set_facets": (C.c_int, [_VP, C.c_int64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "pfem_set_surface_tension": (C.c_int, [_VP, C.c_double]),
+    "pfem_set_thermal": (C.c_int, [_VP, C.POINTER(ThermalParams)]),
+    "pfem_set_bingham": (C.c_int, [_VP, C.c_int, C.c_double, C.c_double]),
+    "pfem_set_temperature": (C.c_int, [_VP, _DP]),
+    "pfem_get_temperature": (C.c_int, [_VP, _DP]),
+    "pfem_set_temperature_bc": (C.c_int, [_VP, _U8P, _DP]),
+    "pfem_heat_assemble": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double, _DP]),
+    "pfem_heat_solve": (C.c_int, [_VP, C.c_double, C.c_int, _DP, C.POINTER(C.c_int), _DP]),
+    "pfem_heat_export_csc": (C.c_int, [_VP, _I64P, _I32P, _I32P, _DP, _DP]),
     "pfem_pspg_set_qprev": (C.c_int, [_VP, _DP]),
     "pfem_pspg_assemble": (C.c_int, [_VP, C.POINTER(PspgParams), _DP]),
     "pfem_pspg_assemble_resident": (C.c_int, [_VP, C.POINTER(PspgParams)]),
@@ -309,6 +321,56 @@ class PfemContext:
 
     def set_surface_tension(self, gamma):
         self._chk(self._L.pfem_set_surface_tension(self._h, float(gamma)))
+
+    # -- Boussinesq / Bingham / heat ---------------------------------------------------
+    def set_thermal(self, k=None, cv=1.0, alpha=0.0, Tr=0.0):
+        """Boussinesq constants; k=None switches the factors off."""
+        if k is None:
+            self._chk(self._L.pfem_set_thermal(self._h, None))
+        else:
+            t = ThermalParams(k, cv, alpha, Tr)
+            self._chk(self._L.pfem_set_thermal(self._h, C.byref(t)))
+
+    def set_bingham(self, tau0=None, m_reg=0.0):
+        self._chk(self._L.pfem_set_bingham(self._h, 0 if tau0 is None else 1, float(tau0 or 0.0), float(m_reg)))
+
+    def set_temperature(self, T):
+        T = _f64(T, self.n_nodes)
+        self._chk(self._L.pfem_set_temperature(self._h, _dptr(T)))
+
+    def get_temperature(self):
+        T = np.empty(self.n_nodes)
+        self._chk(self._L.pfem_get_temperature(self._h, _dptr(T)))
+        return T
+
+    def set_temperature_bc(self, mask, values):
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        values = _f64(values, self.n_nodes)
+        self._chk(self._L.pfem_set_temperature_bc(self._h, mask.ctypes.data_as(_U8P), _dptr(values)))
+
+    def heat_assemble(self, rho, cv, k, dt, theta_prev):
+        th = _f64(theta_prev, self.n_nodes)
+        self._chk(self._L.pfem_heat_assemble(self._h, rho, cv, k, dt, _dptr(th)))
+
+    def heat_solve(self, rel_tol=1e-14, max_iter=10000, fetch=True):
+        T = np.empty(self.n_nodes) if fetch else None
+        it, rr = C.c_int(0), C.c_double(0)
+        rc = self._chk(self._L.pfem_heat_solve(self._h, rel_tol, max_iter, _dptr(T) if fetch else None, C.byref(it), C.byref(rr)),
+                       allow=(PFEM_NOT_CONVERGED, PFEM_NAN))
+        return dict(status=rc, T=T, iters=it.value, rel_res=rr.value)
+
+    def heat_export_csc(self):
+        import scipy.sparse as sp
+        nnz = C.c_int64(0)
+        self._chk(self._L.pfem_heat_export_csc(self._h, C.byref(nnz), None, None, None, None))
+        n = self.n_nodes
+        col_ptr = np.empty(n + 1, dtype=np.int32)
+        row_idx = np.empty(nnz.value, dtype=np.int32)
+        val = np.empty(nnz.value)
+        b = np.empty(n)
+        self._chk(self._L.pfem_heat_export_csc(self._h, C.byref(nnz), col_ptr.ctypes.data_as(_I32P), row_idx.ctypes.data_as(_I32P),
+                                               _dptr(val), _dptr(b)))
+        return sp.csc_matrix((val, row_idx, col_ptr), shape=(n, n)), b
 
     # -- PSPG ---------------------------------------------------------------------
     @staticmethod

@@ -202,6 +202,58 @@ int pfem_set_surface_tension(pfem_ctx* c, double gamma) {
     API_END(c)
 }
 
+int pfem_set_thermal(pfem_ctx* c, const pfem_thermal_params* t) {
+    API_BEGIN(c)
+    if (!t) {
+        c->thermalOn = false;
+    } else {
+        PFEM_REQUIRE(t->cv > 0 && t->k >= 0, PFEM_ERR_INVALID, "set_thermal: cv must be positive, k non-negative");
+        c->thermalOn = true;
+        c->thK = t->k, c->thCv = t->cv, c->thAlpha = t->alpha, c->thTr = t->Tr;
+    }
+    API_END(c)
+}
+int pfem_set_bingham(pfem_ctx* c, int on, double tau0, double mReg) {
+    API_BEGIN(c)
+    PFEM_REQUIRE(!on || (tau0 >= 0 && mReg >= 0), PFEM_ERR_INVALID, "set_bingham: tau0 and mReg must be non-negative");
+    c->binghamOn = on != 0;
+    c->binghamTau0 = tau0, c->binghamM = mReg;
+    API_END(c)
+}
+int pfem_set_temperature(pfem_ctx* c, const double* T) {
+    API_BEGIN(c)
+    thermalSetTemperature(c, T);
+    API_END(c)
+}
+int pfem_get_temperature(pfem_ctx* c, double* T) {
+    API_BEGIN(c)
+    thermalGetTemperature(c, T);
+    API_END(c)
+}
+int pfem_set_temperature_bc(pfem_ctx* c, const uint8_t* mask, const double* values) {
+    API_BEGIN(c)
+    thermalSetBc(c, mask, values);
+    API_END(c)
+}
+int pfem_heat_assemble(pfem_ctx* c, double rho, double cv, double k, double dt, const double* thetaPrev) {
+    API_BEGIN(c)
+    heatAssemble(c, rho, cv, k, dt, thetaPrev);
+    API_END(c)
+}
+int pfem_heat_solve(pfem_ctx* c, double relTol, int maxIter, double* T, int* iters, double* relRes) {
+    if (!c) return PFEM_ERR_INVALID;
+    try {
+        cudaSetDevice(c->device);
+        c->cflFresh = false;
+        return heatSolve(c, relTol, maxIter, T, iters, relRes);
+    } API_CATCH(c)
+}
+int pfem_heat_export_csc(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b) {
+    API_BEGIN(c)
+    heatExport(c, nnz, colPtr, rowIdx, val, b);
+    API_END(c)
+}
+
 int pfem_pspg_set_qprev(pfem_ctx* c, const double* qPrev) {
     API_BEGIN(c)
     fieldsSetQprev(c, qPrev);

@@ -186,6 +186,18 @@ struct pfem_ctx {
     cudaEvent_t evTile = nullptr, evHalo = nullptr;
     double cflMu = 0, cflK0 = 0, cflK0p = 0;
 
+    // ---- temperature-dependent / shear-rate-dependent factors and the heat equations (thermal.cu) ----
+    bool thermalOn = false;    // Boussinesq factors (pfem_set_thermal)
+    double thK = 0, thCv = 1, thAlpha = 0, thTr = 0;
+    bool binghamOn = false;    // Bingham regularised viscosity (pfem_set_bingham)
+    double binghamTau0 = 0, binghamM = 0;
+    bool haveTemperature = false, haveTemperatureBc = false, haveHeatSystem = false;
+    DevBuf<double> Tn, Tnb;    // nodal temperature (+ ping-pong partner of the explicit heat step)
+    DevBuf<uint8_t> tMask;     // node carries a temperature Dirichlet condition ("<type>T" Lua function)
+    DevBuf<double> tVal;
+    DevBuf<double> hA, hb, hTheta;            // implicit heat system on the node pattern
+    DevBuf<double> cgR, cgZ, cgP, cgAp, cgD;  // conjugate-gradient vectors
+
     // ---- free-surface facets / surface tension (facets.cu) ----
     int nFacets = 0, nFstNodes = 0;
     double gammaST = 0.0;      // MomContEqIncompNewton::m_gamma / MomEqWCompNewton::m_gamma
@@ -226,6 +238,8 @@ struct pfem_ctx {
         blkMask.accounting = &deviceBytes;
         rowDir.accounting = &deviceBytes;
         nodeHdr.accounting = &deviceBytes;
+        for (auto* b : {&Tn, &Tnb, &tVal, &hA, &hb, &hTheta, &cgR, &cgZ, &cgP, &cgAp, &cgD}) b->accounting = &deviceBytes;
+        tMask.accounting = &deviceBytes;
         for (auto* b : {&tilePerm, &tileNePrefix, &tileElems, &tileCnt, &tileKey, &tileNodes}) b->accounting = &deviceBytes;
         tileDst16.accounting = &deviceBytes;
         tileLconn.accounting = &deviceBytes;
@@ -306,6 +320,17 @@ void mgApply(pfem_ctx* c, double* out);
 void wcStep(pfem_ctx* c, const pfem_wc_params& p, double dt);
 int wcNextDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, double maxDT, double* dt);
 int wcRun(pfem_ctx* c, const pfem_wc_params& p, int nSteps, double securityCoeff, double maxDT, double* dtInOut, double* elapsed);
+// thermal.cu
+bool pspgNeedsGeneralPath(const pfem_ctx* c);
+void pspgAssembleGeneral(pfem_ctx* c, const pfem_pspg_params& p, const double* fst4);
+void thermalSetTemperature(pfem_ctx* c, const double* T);
+void thermalGetTemperature(pfem_ctx* c, double* T);
+void thermalSetBc(pfem_ctx* c, const uint8_t* mask, const double* values);
+void thermalWcHeat(pfem_ctx* c, double dt, const double* dtPtr);
+void thermalPrepare(pfem_ctx* c);
+void heatAssemble(pfem_ctx* c, double rho, double cv, double k, double dt, const double* thetaPrevHost);
+int heatSolve(pfem_ctx* c, double relTol, int maxIter, double* Tout, int* itersOut, double* relResOut);
+void heatExport(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b);
 // facets.cu
 void facetsSet(pfem_ctx* c, int64_t nFacets, const uint64_t* facetNodes, const uint64_t* outNode, const uint64_t* elemIndex);
 const double* facetsForces(pfem_ctx* c, const double* X4, bool allNodesRule);  // null when the facet terms are off

@@ -1111,6 +1111,14 @@ void pspgAssemble(pfem_ctx* c, const pfem_pspg_params& p) {
     a.nbcap = std::max(c->maxNb, 8);  // >= 640 B per warp: the area doubles as the diagonal-reduction scratch
     a.rho = p.rho, a.mu = p.mu, a.dt = p.dt;
     for (int d = 0; d < 3; ++d) a.body[d] = p.bodyForce[d];
+    if (pspgNeedsGeneralPath(c)) {  // per-element factors (Bingham viscosity, Boussinesq buoyancy): general kernels, thermal.cu
+        pspgAssembleGeneral(c, p, a.fst4);
+        c->haveSystem = true;
+        mgInvalidate(c, false);
+        c->asmStamp = p.dt;
+        c->haveSolution = false;
+        return;
+    }
     {
         PhaseScope ph(c, "Assemble system");  // = Compute triplets + Push back + Assemble matrix/vector + Apply BC
         static const int cfg = getenv("PFEM_ASM_CFG") ? atoi(getenv("PFEM_ASM_CFG")) : 0;

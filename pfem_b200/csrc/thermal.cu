@@ -1,0 +1,787 @@
+// thermal.cu -- the SURVEY 8(f) rank-3 rows on the device: temperature-dependent and shear-rate-dependent factors and the
+// heat equations.
+//   * Bingham regularised viscosity      (IncompNewton/MomContEquation.inl:102-119): K factor mu + tau0 (1 - exp(-m gd))/gd,
+//     gd = sqrt(V^T B^T ddev B V) of the element's CURRENT velocities;
+//   * incompressible Boussinesq          (MomContEquation.inl:166-199): F factor rho (1 - alpha (T - Tr)), H factor
+//     (1 - alpha (T - Tr)), T = N.T_e at the Gauss points;
+//   * implicit heat equation + CG        (IncompNewton/HeatEquation.inl:227-419, solveWithGuess :129-135): scalar system
+//     A = M(cv rho) + dt L(k), b = M theta_prev, Dirichlet / free-node rows, Jacobi-preconditioned conjugate gradients;
+//   * explicit heat equation (BoussinesqWC, WCompNewton/HeatEquation.inl:154-298), the buoyancy factor of the explicit
+//     momentum equation (WCompNewton/MomEquation.inl:105-112) and the thermal diffusivity in the CFL step
+//     (WCompNewton/Solver.cpp:214-216) live in wc.cu next to the kernels they extend; the nodal pass is here.
+// These are the GENERAL assembly kernels: one thread per node block (i, j) gathers the elements around edge (i, j) in
+// ascending element index and evaluates the closed forms of SURVEY appendix A with per-element factors; a second pass per
+// node sums the right-hand side and applies the boundary conditions.  Simple and deterministic, not tuned: the tuned
+// kernel (pspg.cu) covers the constant-factor problem of the named configurations; problems with these factors take
+// this path (about 10x slower at C4).
+#include "common.cuh"
+
+namespace {
+
+__device__ __forceinline__ double2 ld2(const double* p) { return *reinterpret_cast<const double2*>(p); }
+
+template <int DIM> struct GElem {
+    double g[DIM + 1][DIM];  // grad N_m
+    double V;
+};
+// geometry of element e from the nodal records (Element.cpp:15-135, MatricesBuilder.inl:93-127)
+template <int DIM>
+__device__ __forceinline__ void elemGeo(const double* __restrict__ X4, const int (&nd)[DIM + 1], GElem<DIM>& G) {
+    constexpr int NPE = DIM + 1;
+    constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
+    double px[NPE][DIM];
+#pragma unroll
+    for (int m = 0; m < NPE; ++m)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) px[m][d] = X4[(size_t)nd[m] * 4 + d];
+    double J[DIM][DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d)
+#pragma unroll
+        for (int m = 0; m < DIM; ++m) J[d][m] = px[m + 1][d] - px[0][d];
+    double det, inv[DIM][DIM];
+    if constexpr (DIM == 2) {
+        det = J[0][0] * J[1][1] - J[1][0] * J[0][1];
+        const double rd = 1.0 / det;
+        inv[0][0] = J[1][1] * rd, inv[0][1] = -J[0][1] * rd, inv[1][0] = -J[1][0] * rd, inv[1][1] = J[0][0] * rd;
+    } else {
+        det = J[0][0] * J[1][1] * J[2][2] + J[0][1] * J[1][2] * J[2][0] + J[0][2] * J[1][0] * J[2][1] -
+              J[2][0] * J[1][1] * J[0][2] - J[2][1] * J[1][2] * J[0][0] - J[2][2] * J[1][0] * J[0][1];
+        const double rd = 1.0 / det;
+        inv[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * rd;
+        inv[0][1] = (J[2][1] * J[0][2] - J[2][2] * J[0][1]) * rd;
+        inv[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * rd;
+        inv[1][0] = (J[2][0] * J[1][2] - J[1][0] * J[2][2]) * rd;
+        inv[1][1] = (J[0][0] * J[2][2] - J[2][0] * J[0][2]) * rd;
+        inv[1][2] = (J[1][0] * J[0][2] - J[0][0] * J[1][2]) * rd;
+        inv[2][0] = (J[1][0] * J[2][1] - J[2][0] * J[1][1]) * rd;
+        inv[2][1] = (J[2][0] * J[0][1] - J[0][0] * J[2][1]) * rd;
+        inv[2][2] = (J[0][0] * J[1][1] - J[1][0] * J[0][1]) * rd;
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) {
+        double s = -inv[0][d];
+#pragma unroll
+        for (int m = 1; m < DIM; ++m) s -= inv[m][d];
+        G.g[0][d] = s;
+#pragma unroll
+        for (int m = 0; m < DIM; ++m) G.g[m + 1][d] = inv[m][d];
+    }
+    G.V = det * REF;
+}
+template <int DIM> __device__ __forceinline__ void loadConn(const int* __restrict__ conn, int e, int (&nd)[DIM + 1]) {
+#pragma unroll
+    for (int m = 0; m < DIM + 1; ++m) nd[m] = conn[(size_t)e * (DIM + 1) + m];
+}
+// Gauss rule of the element integrals (Mesh.cpp:375-399, 443-459): at point g the shape functions are GA for node g and GB
+// for the others, weight 1/(dim+1)
+template <int DIM> struct Gauss {
+    static constexpr double GA = (DIM == 3) ? 0.585410196624968 : 0.66666666666666666667;
+    static constexpr double GB = (DIM == 3) ? 0.138196601125011 : 0.16666666666666666667;
+    static constexpr double W = 1.0 / (DIM + 1);
+};
+
+struct GenArgs {
+    const int* conn;
+    const int* n2ePtr;
+    const int* n2e;
+    const unsigned* blkMask;
+    const int* nbrPtr;
+    const int* nbr;
+    const int* diagSlot;
+    const uint8_t* flags;
+    const uint8_t* dirMask;
+    const double* dirVal4;
+    const double* X4;
+    const double* V4;    // current velocities (tau, Bingham shear rate)
+    const double* VP4;   // previous velocities
+    const double* T;     // nodal temperature or null
+    const double* fst4;
+    double* Aval;
+    double* b;
+    double* dinv;
+    int nRows, CH;
+    double rho, mu, dt, body[3];
+    double tau0, mReg;   // Bingham (bingham != 0)
+    double alpha, Tr;    // Boussinesq (T != null)
+    int bingham;
+};
+
+// tau (PSPG.inl:238-259) and the element viscosity
+template <int DIM>
+__device__ __forceinline__ void elemTauMu(const GenArgs& a, const int (&nd)[DIM + 1], const GElem<DIM>& G, double& tau, double& muE) {
+    constexpr int NPE = DIM + 1;
+    constexpr double REF = (DIM == 2) ? 0.5 : 0.16666666666666666666666666666667;
+    double usum = 0, L[DIM][DIM];  // L[a][c] = d v_a / d x_c
+#pragma unroll
+    for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) L[aa][c] = 0;
+#pragma unroll
+    for (int m = 0; m < NPE; ++m) {
+        double v[DIM], s = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            v[d] = a.V4[(size_t)nd[m] * 4 + d];
+            s += v[d] * v[d];
+        }
+        usum += sqrt(s);
+#pragma unroll
+        for (int aa = 0; aa < DIM; ++aa)
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) L[aa][c] += v[aa] * G.g[m][c];
+    }
+    const double det = G.V / REF;
+    const double h2 = REF * det / 3.14159265358979323846;  // reference hazard 7: the 2-D formula also in 3-D
+    const double U = usum / NPE;
+    const double t1 = 2.0 / a.dt, t3 = 4.0 * a.mu / (h2 * a.rho);
+    tau = 1.0 / sqrt(t1 * t1 + 4.0 * U * U / h2 + 9.0 * t3 * t3);
+    muE = a.mu;
+    if (a.bingham) {
+        double gd2 = 0;  // V^T B^T ddev B V with ddev = diag(2,..,1,..): 2 sum eps_dd^2 + sum engineering shear^2
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gd2 += 2.0 * L[d][d] * L[d][d];
+#pragma unroll
+        for (int p = 0; p < DIM; ++p)
+#pragma unroll
+            for (int q = p + 1; q < DIM; ++q) {
+                const double sh = L[p][q] + L[q][p];
+                gd2 += sh * sh;
+            }
+        const double gd = sqrt(gd2);
+        muE += (gd < 1e-15) ? a.tau0 * a.mReg : a.tau0 * (1.0 - exp(-a.mReg * gd)) / gd;
+    }
+}
+
+// block (i, slot) of the PSPG matrix: every element around edge (i, j), ascending element index, row masks applied
+template <int DIM>
+__global__ void __launch_bounds__(128) k_gen_blocks(const GenArgs a) {
+    constexpr int NPE = DIM + 1, BS = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // thread -> (node, slot) by a search in nbrPtr restricted to the owned rows
+    const int64_t nBlk = a.nbrPtr[a.nRows];
+    if (t >= nBlk) return;
+    int lo = 0, hi = a.nRows - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.nbrPtr[mid] <= t) lo = mid;
+        else hi = mid - 1;
+    }
+    const int i = lo, nb0 = a.nbrPtr[i], s = (int)(t - nb0);
+    const int j = a.nbr[nb0 + s], eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+    const uint8_t fl = a.flags[i];
+    const bool isBound = fl & PFEM_NODE_BOUND, isFree = fl & PFEM_NODE_FREE;
+    const bool maskV = isBound || isFree, maskP = isFree;
+    double acc[BS][BS];
+#pragma unroll
+    for (int r = 0; r < BS; ++r)
+#pragma unroll
+        for (int c = 0; c < BS; ++c) acc[r][c] = 0;
+    for (int k = 0; k < ne; ++k) {
+        if (!((a.blkMask[(size_t)(nb0 + s) * a.CH + (k >> 5)] >> (k & 31)) & 1u)) continue;
+        const int e = a.n2e[eb + k];
+        int nd[NPE];
+        loadConn<DIM>(a.conn, e, nd);
+        int li = 0, lj = 0;
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) {
+            li = (nd[m] == i) ? m : li;
+            lj = (nd[m] == j) ? m : lj;
+        }
+        GElem<DIM> G;
+        elemGeo<DIM>(a.X4, nd, G);
+        double tau, muE;
+        elemTauMu<DIM>(a, nd, G, tau, muE);
+        double gi[DIM], gj[DIM], dot = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            gi[d] = G.g[0][d], gj[d] = G.g[0][d];
+#pragma unroll
+            for (int m = 1; m < NPE; ++m) {
+                gi[d] = (li == m) ? G.g[m][d] : gi[d];
+                gj[d] = (lj == m) ? G.g[m][d] : gj[d];
+            }
+            dot += gi[d] * gj[d];
+        }
+        const double V = G.V;
+        const double cm = a.rho * V * PHI * (i == j ? 2.0 : 1.0) / a.dt;
+#pragma unroll
+        for (int aa = 0; aa < DIM; ++aa) {
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) acc[aa][c] += muE * V * gi[c] * gj[aa];
+            acc[aa][aa] += cm + muE * V * dot;
+            acc[aa][DIM] -= (V / NPE) * gi[aa];
+            acc[DIM][aa] += (V / NPE) * ((tau / a.dt) * gi[aa] + gj[aa]);
+        }
+        acc[DIM][DIM] += tau * (V / a.rho) * dot;
+    }
+    const bool diag = (s == a.diagSlot[i]);
+#pragma unroll
+    for (int r = 0; r < BS; ++r) {
+        const bool rowMasked = (r < DIM) ? maskV : maskP;
+#pragma unroll
+        for (int c = 0; c < BS; ++c) {
+            double v = acc[r][c];
+            if (rowMasked) v = (diag && r == c) ? 1.0 : 0.0;
+            a.Aval[((size_t)nb0 + s) * BS * BS + r * BS + c] = v;
+        }
+    }
+}
+
+// right-hand side rows of node i + m_applyBCPSPG (PSPG.inl:140-144, 149-235) on the blocks k_gen_blocks wrote
+template <int DIM>
+__global__ void __launch_bounds__(128) k_gen_rhs_bc(const GenArgs a) {
+    constexpr int NPE = DIM + 1, BS = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nRows) return;
+    const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+    double bi[BS];
+#pragma unroll
+    for (int r = 0; r < BS; ++r) bi[r] = 0;
+    for (int k = 0; k < ne; ++k) {
+        const int e = a.n2e[eb + k];
+        int nd[NPE];
+        loadConn<DIM>(a.conn, e, nd);
+        int li = 0;
+#pragma unroll
+        for (int m = 1; m < NPE; ++m) li = (nd[m] == i) ? m : li;
+        GElem<DIM> G;
+        elemGeo<DIM>(a.X4, nd, G);
+        double tau, muE;
+        elemTauMu<DIM>(a, nd, G, tau, muE);
+        double gi[DIM], sv[DIM], vpi[DIM];
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            gi[d] = G.g[0][d];
+#pragma unroll
+            for (int m = 1; m < NPE; ++m) gi[d] = (li == m) ? G.g[m][d] : gi[d];
+            sv[d] = 0;
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) sv[d] += a.VP4[(size_t)nd[m] * 4 + d];
+            vpi[d] = a.VP4[(size_t)i * 4 + d];
+        }
+        // Gauss sums of the F and H factors (MomContEquation.inl:166-207, 218-222)
+        double fF = a.rho / NPE, fH = 1.0;  // sum_g w f N_g[i]  |  sum_g w f
+        if (a.T) {
+            double Te[NPE], sT = 0;
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) {
+                Te[m] = a.T[nd[m]];
+                sT += Te[m];
+            }
+            fF = 0, fH = 0;
+#pragma unroll
+            for (int g = 0; g < NPE; ++g) {
+                const double Tg = Gauss<DIM>::GB * sT + (Gauss<DIM>::GA - Gauss<DIM>::GB) * Te[g];
+                const double f = 1.0 - a.alpha * (Tg - a.Tr);
+                fF += Gauss<DIM>::W * (a.rho * f) * (g == li ? Gauss<DIM>::GA : Gauss<DIM>::GB);
+                fH += Gauss<DIM>::W * f;
+            }
+        }
+        const double V = G.V, cmass = a.rho * V * PHI / a.dt;
+        double gb = 0, gs = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            gb += gi[d] * a.body[d];
+            gs += gi[d] * sv[d];
+            bi[d] += V * a.body[d] * fF + cmass * (vpi[d] + sv[d]);
+        }
+        bi[DIM] += tau * V * gb * fH + (tau / a.dt) * (V / NPE) * gs;
+    }
+    const uint8_t fl = a.flags[i];
+    const bool isBound = fl & PFEM_NODE_BOUND, isFree = fl & PFEM_NODE_FREE;
+    if (a.fst4)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) bi[d] += a.fst4[(size_t)i * 4 + d];
+    // Dirichlet column elimination (PSPG.inl:216-228): b_row -= A(row, col) g_D ; A(row, col) = 0 for row != col
+    const int nb0 = a.nbrPtr[i], nb = a.nbrPtr[i + 1] - nb0, si = a.diagSlot[i];
+    for (int s = 0; s < nb; ++s) {
+        const int j = a.nbr[nb0 + s];
+        if (!(a.dirMask[j] && (a.flags[j] & PFEM_NODE_BOUND))) continue;
+        double* blk = a.Aval + ((size_t)nb0 + s) * BS * BS;
+#pragma unroll
+        for (int cc = 0; cc < DIM; ++cc) {
+            const double gv = a.dirVal4[(size_t)j * 4 + cc];
+#pragma unroll
+            for (int r = 0; r < BS; ++r) {
+                if (s == si && r == cc) continue;
+                bi[r] -= blk[r * BS + cc] * gv;
+                blk[r * BS + cc] = 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < BS; ++r) {
+        double bv = bi[r];
+        if (isFree) {
+            if (r == DIM) bv = 0.0;
+            else if (!isBound) bv = a.VP4[(size_t)i * 4 + r] + a.dt * a.body[r];
+        }
+        if (isBound && a.dirMask[i] && r < DIM) bv = a.dirVal4[(size_t)i * 4 + r];
+        a.b[(size_t)i * BS + r] = bv;
+        const double d = a.Aval[((size_t)nb0 + si) * BS * BS + r * BS + r];
+        a.dinv[(size_t)i * BS + r] = (d != 0.0) ? rsqrt(fabs(d)) : 1.0;
+    }
+}
+
+// ---- implicit heat equation (scalar system on the node pattern) -------------------------------------------------------------
+struct HeatArgs {
+    const int* conn;
+    const int* n2ePtr;
+    const int* n2e;
+    const unsigned* blkMask;
+    const int* nbrPtr;
+    const int* nbr;
+    const int* diagSlot;
+    const uint8_t* flags;
+    const uint8_t* tMask;
+    const double* tVal;
+    const double* X4;
+    const double* thetaPrev;
+    double* A;     // one value per node block
+    double* b;
+    int nRows, CH;
+    double rhoCv, k, dt;
+};
+template <int DIM> __global__ void __launch_bounds__(128) k_heat_blocks(const HeatArgs a) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t nBlk = a.nbrPtr[a.nRows];
+    if (t >= nBlk) return;
+    int lo = 0, hi = a.nRows - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (a.nbrPtr[mid] <= t) lo = mid;
+        else hi = mid - 1;
+    }
+    const int i = lo, nb0 = a.nbrPtr[i], s = (int)(t - nb0);
+    const int j = a.nbr[nb0 + s], eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+    const bool masked = a.tMask[i] || (a.flags[i] & PFEM_NODE_FREE);  // HeatEquation.inl:268-280, 300-308
+    double acc = 0;
+    if (!masked)
+        for (int k = 0; k < ne; ++k) {
+            if (!((a.blkMask[(size_t)(nb0 + s) * a.CH + (k >> 5)] >> (k & 31)) & 1u)) continue;
+            const int e = a.n2e[eb + k];
+            int nd[NPE];
+            loadConn<DIM>(a.conn, e, nd);
+            int li = 0, lj = 0;
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) {
+                li = (nd[m] == i) ? m : li;
+                lj = (nd[m] == j) ? m : lj;
+            }
+            GElem<DIM> G;
+            elemGeo<DIM>(a.X4, nd, G);
+            double dot = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                double gi = G.g[0][d], gj = G.g[0][d];
+#pragma unroll
+                for (int m = 1; m < NPE; ++m) {
+                    gi = (li == m) ? G.g[m][d] : gi;
+                    gj = (lj == m) ? G.g[m][d] : gj;
+                }
+                dot += gi * gj;
+            }
+            acc += a.rhoCv * G.V * PHI * (i == j ? 2.0 : 1.0) + a.dt * (a.k * G.V * dot);  // M + dt L
+        }
+    else
+        acc = (s == a.diagSlot[i]) ? 1.0 : 0.0;
+    a.A[(size_t)nb0 + s] = acc;
+}
+template <int DIM> __global__ void __launch_bounds__(128) k_heat_rhs_bc(const HeatArgs a) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.nRows) return;
+    const int eb = a.n2ePtr[i], ne = a.n2ePtr[i + 1] - eb;
+    double bi = 0;
+    for (int k = 0; k < ne; ++k) {  // b = M theta_prev: all rows, masked or not (HeatEquation.inl:283-288, 313-317)
+        const int e = a.n2e[eb + k];
+        int nd[NPE];
+        loadConn<DIM>(a.conn, e, nd);
+        GElem<DIM> G;
+        elemGeo<DIM>(a.X4, nd, G);
+        double st = 0;
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) st += a.thetaPrev[nd[m]];
+        bi += a.rhoCv * G.V * PHI * (a.thetaPrev[i] + st);
+    }
+    const bool free_ = a.flags[i] & PFEM_NODE_FREE, tbc = a.tMask[i] != 0;
+    const int nb0 = a.nbrPtr[i], nb = a.nbrPtr[i + 1] - nb0, si = a.diagSlot[i];
+    for (int s = 0; s < nb; ++s) {  // Dirichlet columns (HeatEquation.inl:396-408)
+        const int j = a.nbr[nb0 + s];
+        if (s == si || !a.tMask[j]) continue;
+        bi -= a.A[(size_t)nb0 + s] * a.tVal[j];
+        a.A[(size_t)nb0 + s] = 0.0;
+    }
+    if (free_ && !tbc) bi = a.thetaPrev[i];
+    else if (tbc) bi = a.tVal[i];
+    a.b[i] = bi;
+}
+
+// ---- Jacobi-preconditioned conjugate gradients on the scalar node-pattern matrix ------------------------------------------------
+__global__ void k_s_spmv(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ A,
+                         const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0;
+    for (int k = ptr[i]; k < ptr[i + 1]; ++k) s += A[k] * x[col[k]];
+    y[i] = s;
+}
+// partial[blockIdx] = sum_i a_i b_i (fixed grid, fixed order)
+__global__ void __launch_bounds__(256) k_s_dot(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ partial) {
+    __shared__ double sh[8];
+    double s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += a[i] * b[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0;
+        for (int k = 0; k < 8; ++k) t += sh[k];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void k_s_dot_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0;
+        for (int k = 0; k < nb; ++k) t += partial[k];
+        *out = t;
+    }
+}
+// scal: [0] rho = r.z, [1] p.Ap, [2] rho_new, [3] ||r||^2, [4] ||b||^2
+__global__ void k_cg_init(int n, const int* __restrict__ ptr, const int* __restrict__ diag, const double* __restrict__ A,
+                          const double* __restrict__ b, const double* __restrict__ Ax, double* __restrict__ r, double* __restrict__ z,
+                          double* __restrict__ p, double* __restrict__ dinv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = A[ptr[i] + diag[i]];
+    const double di = d != 0.0 ? 1.0 / d : 1.0;  // Eigen::DiagonalPreconditioner
+    dinv[i] = di;
+    const double ri = b[i] - Ax[i];
+    r[i] = ri;
+    z[i] = di * ri;
+    p[i] = di * ri;
+}
+__global__ void k_cg_update_xr(int n, const double* __restrict__ scal, const double* __restrict__ p, const double* __restrict__ Ap,
+                               const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double alpha = scal[0] / scal[1];
+    x[i] += alpha * p[i];
+    const double ri = r[i] - alpha * Ap[i];
+    r[i] = ri;
+    z[i] = dinv[i] * ri;
+}
+__global__ void k_cg_update_p(int n, double* __restrict__ scal, const double* __restrict__ z, double* __restrict__ p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double beta = scal[2] / scal[0];
+    if (i < n) p[i] = z[i] + beta * p[i];
+}
+__global__ void k_cg_shift(double* scal) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) scal[0] = scal[2];
+}
+__global__ void k_nodal_copy(int n, const double* __restrict__ src, double* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// explicit heat equation of BoussinesqWC, nodal gather (WCompNewton/HeatEquation.inl:154-298): lumped M with f = cv (N.rho),
+// L with f = k, F = -dt L T + M T; free nodes keep T, Dirichlet nodes take g_T
+template <int DIM>
+__global__ void __launch_bounds__(128) k_wc_heat(int nRows, const int* __restrict__ conn, const int* __restrict__ n2ePtr,
+                                                 const int* __restrict__ n2e, const uint8_t* __restrict__ flags,
+                                                 const uint8_t* __restrict__ tMask, const double* __restrict__ tVal,
+                                                 const double* __restrict__ X4, const double* __restrict__ V4, const double* __restrict__ T,
+                                                 double* __restrict__ Tnew, double k, double cv, double dtVal, const double* __restrict__ dtPtr) {
+    constexpr int NPE = DIM + 1;
+    constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRows) return;
+    const double dt = dtPtr ? *dtPtr : dtVal;
+    double M = 0, F = 0;
+    for (int kk = n2ePtr[i]; kk < n2ePtr[i + 1]; ++kk) {
+        const int e = n2e[kk];
+        int nd[NPE];
+        loadConn<DIM>(conn, e, nd);
+        int li = 0;
+#pragma unroll
+        for (int m = 1; m < NPE; ++m) li = (nd[m] == i) ? m : li;
+        GElem<DIM> G;
+        elemGeo<DIM>(X4, nd, G);
+        double sumR = 0, gT[DIM], gi[DIM], lt = 0;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) gT[d] = 0;
+#pragma unroll
+        for (int m = 0; m < NPE; ++m) {
+            sumR += V4[(size_t)nd[m] * 4 + 3];
+            const double Tm = T[nd[m]];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) gT[d] += G.g[m][d] * Tm;
+        }
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) {
+            gi[d] = G.g[0][d];
+#pragma unroll
+            for (int m = 1; m < NPE; ++m) gi[d] = (li == m) ? G.g[m][d] : gi[d];
+            lt += gi[d] * gT[d];
+        }
+        const double lump = cv * G.V * PHI * (V4[(size_t)i * 4 + 3] + sumR);  // lumped cv (N.rho) mass
+        F += -dt * (k * G.V * lt) + lump * T[i];
+        M += lump;
+    }
+    const bool free_ = flags[i] & PFEM_NODE_FREE, tbc = tMask[i] != 0;
+    double inv = 1.0 / M;
+    if (free_ && !tbc) {
+        F = T[i];
+        inv = 1.0;
+    } else if (tbc) {
+        F = tVal[i];
+        inv = 1.0;
+    }
+    Tnew[i] = inv * F;
+}
+
+GenArgs makeGenArgs(pfem_ctx* c, const pfem_pspg_params& p) {
+    GenArgs a;
+    a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.blkMask = c->blkMask.p, a.nbrPtr = c->nbrPtr.p, a.nbr = c->nbr.p;
+    a.diagSlot = c->diagSlot.p, a.flags = c->flags.p, a.dirMask = c->dirMask.p, a.dirVal4 = c->dirVal4.p;
+    a.X4 = c->X4.p, a.V4 = c->V4.p, a.VP4 = c->VP4.p, a.T = c->thermalOn ? c->Tn.p : nullptr;
+    a.Aval = c->Aval.p, a.b = c->bvec.p, a.dinv = c->dinv.p, a.nRows = c->nRows, a.CH = c->maskWords;
+    a.rho = p.rho, a.mu = p.mu, a.dt = p.dt;
+    for (int d = 0; d < 3; ++d) a.body[d] = p.bodyForce[d];
+    a.bingham = c->binghamOn ? 1 : 0, a.tau0 = c->binghamTau0, a.mReg = c->binghamM;
+    a.alpha = c->thAlpha, a.Tr = c->thTr;
+    a.fst4 = nullptr;
+    return a;
+}
+
+}  // namespace
+
+bool pspgNeedsGeneralPath(const pfem_ctx* c) { return c->binghamOn || c->thermalOn; }
+
+// m_buildAbPSPG + m_applyBCPSPG with per-element factors (called by pspgAssemble when Bingham / Boussinesq are on)
+void pspgAssembleGeneral(pfem_ctx* c, const pfem_pspg_params& p, const double* fst4) {
+    PFEM_REQUIRE(!c->thermalOn || c->haveTemperature, PFEM_ERR_STATE, "pspg_assemble: Boussinesq factors need pfem_set_temperature");
+    GenArgs a = makeGenArgs(c, p);
+    a.fst4 = fst4;
+    PhaseScope ph(c, "Assemble system");
+    const int64_t nBlkRows = c->nBlocks;  // (partitioned mesh: blocks of the owned rows come first; the kernel bounds itself)
+    if (c->dim == 2) {
+        k_gen_blocks<2><<<divUp(nBlkRows, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_gen_rhs_bc<2><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(a);
+    } else {
+        k_gen_blocks<3><<<divUp(nBlkRows, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_gen_rhs_bc<3><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(a);
+    }
+    LAUNCH_CHECK(c);
+}
+
+void thermalSetTemperature(pfem_ctx* c, const double* T) {
+    PFEM_REQUIRE(c->haveTopology && T, PFEM_ERR_STATE, "set_temperature: topology missing or null");
+    c->Tn.reserve((size_t)c->nNodes + 4);
+    c->Tnb.reserve((size_t)c->nNodes + 4);
+    CUDA_CHECK(cudaMemcpyAsync(c->Tn.p, T, (size_t)c->nNodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->haveTemperature = true;
+}
+void thermalGetTemperature(pfem_ctx* c, double* T) {
+    PFEM_REQUIRE(c->haveTemperature && T, PFEM_ERR_STATE, "get_temperature: no temperature on the device");
+    CUDA_CHECK(cudaMemcpyAsync(T, c->Tn.p, (size_t)c->nNodes * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+void thermalSetBc(pfem_ctx* c, const uint8_t* mask, const double* values) {
+    PFEM_REQUIRE(c->haveTopology && mask && values, PFEM_ERR_STATE, "set_temperature_bc: topology missing or null");
+    c->tMask.reserve((size_t)c->nNodes + 4);
+    c->tVal.reserve((size_t)c->nNodes + 4);
+    CUDA_CHECK(cudaMemcpyAsync(c->tMask.p, mask, (size_t)c->nNodes, cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->tVal.p, values, (size_t)c->nNodes * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->haveTemperatureBc = true;
+}
+static void needThermalBc(pfem_ctx* c) {
+    if (c->haveTemperatureBc) return;  // no temperature BC given: none anywhere
+    c->tMask.reserve((size_t)c->nNodes + 4);
+    c->tVal.reserve((size_t)c->nNodes + 4);
+    CUDA_CHECK(cudaMemsetAsync(c->tMask.p, 0, (size_t)c->nNodes, c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->tVal.p, 0, (size_t)c->nNodes * sizeof(double), c->stream));
+    c->haveTemperatureBc = true;
+}
+
+void thermalPrepare(pfem_ctx* c) {  // allocations / defaults outside any graph capture
+    PFEM_REQUIRE(c->haveTemperature, PFEM_ERR_STATE, "wc_step (Boussinesq): call pfem_set_temperature first");
+    needThermalBc(c);
+    c->Tnb.reserve((size_t)c->nNodes + 4);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+
+// explicit heat step of m_solveBoussinesqWC (Solver.cpp:301-303): on the moved mesh, with the density of the previous step
+void thermalWcHeat(pfem_ctx* c, double dt, const double* dtPtr) {
+    PFEM_REQUIRE(c->haveTemperature, PFEM_ERR_STATE, "wc_step (Boussinesq): call pfem_set_temperature first");
+    needThermalBc(c);
+    PhaseScope ph(c, "Solving heat eq");
+    if (c->dim == 2)
+        k_wc_heat<2><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(c->nRows, c->conn.p, c->n2ePtr.p, c->n2e.p, c->flags.p, c->tMask.p,
+                                                                c->tVal.p, c->X4.p, c->V4.p, c->Tn.p, c->Tnb.p, c->thK, c->thCv, dt, dtPtr);
+    else
+        k_wc_heat<3><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(c->nRows, c->conn.p, c->n2ePtr.p, c->n2e.p, c->flags.p, c->tMask.p,
+                                                                c->tVal.p, c->X4.p, c->V4.p, c->Tn.p, c->Tnb.p, c->thK, c->thCv, dt, dtPtr);
+    LAUNCH_CHECK(c);
+    if (c->nRanks > 1) commHalo(c, c->Tnb.p, nullptr, 1);
+    k_nodal_copy<<<divUp(c->nNodes, 256), 256, 0, c->stream>>>(c->nNodes, c->Tnb.p, c->Tn.p);
+    LAUNCH_CHECK(c);
+}
+
+// HeatEqIncompNewton::m_buildAb + m_applyBC (IncompNewton/HeatEquation.inl:227-412, no flux facet terms)
+void heatAssemble(pfem_ctx* c, double rho, double cv, double k, double dt, const double* thetaPrevHost) {
+    PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, "heat_assemble: topology/positions missing");
+    PFEM_REQUIRE(c->nRanks == 1, PFEM_ERR_STATE, "heat_assemble: single-GPU contexts");
+    PFEM_REQUIRE(thetaPrevHost && dt > 0 && rho > 0 && cv > 0, PFEM_ERR_INVALID, "heat_assemble: bad arguments");
+    needThermalBc(c);
+    const int n = c->nNodes;
+    c->hA.reserve((size_t)c->nBlocks + 4);
+    c->hb.reserve((size_t)n + 4);
+    c->hTheta.reserve((size_t)n + 4);
+    CUDA_CHECK(cudaMemcpyAsync(c->hTheta.p, thetaPrevHost, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    HeatArgs a;
+    a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.blkMask = c->blkMask.p, a.nbrPtr = c->nbrPtr.p, a.nbr = c->nbr.p;
+    a.diagSlot = c->diagSlot.p, a.flags = c->flags.p, a.tMask = c->tMask.p, a.tVal = c->tVal.p, a.X4 = c->X4.p;
+    a.thetaPrev = c->hTheta.p, a.A = c->hA.p, a.b = c->hb.p, a.nRows = n, a.CH = c->maskWords;
+    a.rhoCv = cv * rho, a.k = k, a.dt = dt;
+    PhaseScope ph(c, "Assemble heat system");
+    if (c->dim == 2) {
+        k_heat_blocks<2><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_heat_rhs_bc<2><<<divUp(n, 128), 128, 0, c->stream>>>(a);
+    } else {
+        k_heat_blocks<3><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_heat_rhs_bc<3><<<divUp(n, 128), 128, 0, c->stream>>>(a);
+    }
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->haveHeatSystem = true;
+}
+
+// Eigen::ConjugateGradient<..., Lower|Upper, DiagonalPreconditioner>::solveWithGuess (IncompNewton/HeatEquation.inl:129-135):
+// x0 = the temperature on the device (pfem_set_temperature) or zero; stops at ||r|| <= relTol ||b||
+int heatSolve(pfem_ctx* c, double relTol, int maxIter, double* Tout, int* itersOut, double* relResOut) {
+    PFEM_REQUIRE(c->haveHeatSystem, PFEM_ERR_STATE, "heat_solve: no assembled heat system (pfem_heat_assemble)");
+    PFEM_REQUIRE(relTol > 0 && maxIter > 0, PFEM_ERR_INVALID, "heat_solve: relTol and maxIter must be positive");
+    PhaseScope ph(c, "Solve heat system");
+    const int n = c->nNodes, g = divUp(n, 256), nb = std::max(1, std::min(c->smCount * 4, g));
+    for (auto* v : {&c->cgR, &c->cgZ, &c->cgP, &c->cgAp, &c->cgD}) v->reserve((size_t)n + 4);
+    c->Tn.reserve((size_t)n + 4);
+    c->Tnb.reserve((size_t)n + 4);
+    c->partial.reserve((size_t)nb + 16);
+    c->scal.reserve(SC_COUNT);
+    if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
+    if (!c->haveTemperature) {
+        CUDA_CHECK(cudaMemsetAsync(c->Tn.p, 0, (size_t)n * sizeof(double), c->stream));
+        c->haveTemperature = true;
+    }
+    double* x = c->Tn.p;
+    double* S = c->scal.p;
+    auto dot = [&](const double* a, const double* b, int slot) {
+        k_s_dot<<<nb, 256, 0, c->stream>>>(n, a, b, c->partial.p);
+        LAUNCH_CHECK(c);
+        k_s_dot_final<<<1, 32, 0, c->stream>>>(c->partial.p, nb, S + slot);
+        LAUNCH_CHECK(c);
+    };
+    k_s_spmv<<<g, 256, 0, c->stream>>>(n, c->nbrPtr.p, c->nbr.p, c->hA.p, x, c->cgAp.p);
+    LAUNCH_CHECK(c);
+    k_cg_init<<<g, 256, 0, c->stream>>>(n, c->nbrPtr.p, c->diagSlot.p, c->hA.p, c->hb.p, c->cgAp.p, c->cgR.p, c->cgZ.p, c->cgP.p, c->cgD.p);
+    LAUNCH_CHECK(c);
+    dot(c->cgR.p, c->cgZ.p, 0);
+    dot(c->cgR.p, c->cgR.p, 3);
+    dot(c->hb.p, c->hb.p, 4);
+    CUDA_CHECK(cudaMemcpyAsync(c->hScal, S, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    const double bb = c->hScal[4];
+    double rr = c->hScal[3];
+    int it = 0, status = PFEM_OK;
+    if (bb == 0.0) {  // Eigen: x = 0 for b = 0
+        CUDA_CHECK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), c->stream));
+        rr = 0;
+    } else {
+        const double thr = relTol * relTol * bb;
+        while (rr > thr && it < maxIter) {
+            k_s_spmv<<<g, 256, 0, c->stream>>>(n, c->nbrPtr.p, c->nbr.p, c->hA.p, c->cgP.p, c->cgAp.p);
+            LAUNCH_CHECK(c);
+            dot(c->cgP.p, c->cgAp.p, 1);
+            k_cg_update_xr<<<g, 256, 0, c->stream>>>(n, S, c->cgP.p, c->cgAp.p, c->cgD.p, x, c->cgR.p, c->cgZ.p);
+            LAUNCH_CHECK(c);
+            dot(c->cgR.p, c->cgZ.p, 2);
+            dot(c->cgR.p, c->cgR.p, 3);
+            k_cg_update_p<<<g, 256, 0, c->stream>>>(n, S, c->cgZ.p, c->cgP.p);
+            LAUNCH_CHECK(c);
+            k_cg_shift<<<1, 32, 0, c->stream>>>(S);
+            LAUNCH_CHECK(c);
+            ++it;
+            CUDA_CHECK(cudaMemcpyAsync(c->hScal, S, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            rr = c->hScal[3];
+            if (!(rr == rr)) {
+                status = PFEM_NAN;
+                break;
+            }
+        }
+        if (status == PFEM_OK && rr > thr) status = PFEM_NOT_CONVERGED;
+    }
+    if (itersOut) *itersOut = it;
+    if (relResOut) *relResOut = bb > 0 ? sqrt(rr / bb) : 0.0;
+    if (Tout) {
+        CUDA_CHECK(cudaMemcpyAsync(Tout, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return status;
+}
+
+// the heat system in the reference's format: column-major compressed, rows of masked nodes reduced to their diagonal
+void heatExport(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b) {
+    PFEM_REQUIRE(c->haveHeatSystem && nnz, PFEM_ERR_STATE, "heat_export: no assembled heat system");
+    const int n = c->nNodes;
+    std::vector<int> ptr((size_t)n + 1), nbr((size_t)c->nBlocks), diag((size_t)n);
+    std::vector<double> A((size_t)c->nBlocks), bb((size_t)n);
+    std::vector<uint8_t> fl((size_t)n), tm((size_t)n);
+    CUDA_CHECK(cudaMemcpyAsync(ptr.data(), c->nbrPtr.p, ((size_t)n + 1) * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(nbr.data(), c->nbr.p, (size_t)c->nBlocks * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(A.data(), c->hA.p, (size_t)c->nBlocks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(bb.data(), c->hb.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(fl.data(), c->flags.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(tm.data(), c->tMask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    // entry (i, j) exists when row i is unmasked, or i == j; the pattern is symmetric in (i, j), so column j lists the
+    // neighbours i of j that qualify (ascending: nbr lists are sorted)
+    auto masked = [&](int i) { return tm[i] || (fl[i] & PFEM_NODE_FREE); };
+    int64_t count = 0;
+    for (int j = 0; j < n; ++j)
+        for (int k = ptr[j]; k < ptr[j + 1]; ++k) {
+            const int i = nbr[k];
+            if (!masked(i) || i == j) ++count;
+        }
+    *nnz = count;
+    if (!colPtr) return;
+    PFEM_REQUIRE(rowIdx && val && b, PFEM_ERR_INVALID, "heat_export: null output array");
+    int64_t o = 0;
+    for (int j = 0; j < n; ++j) {
+        colPtr[j] = (int32_t)o;
+        for (int k = ptr[j]; k < ptr[j + 1]; ++k) {
+            const int i = nbr[k];
+            if (!(!masked(i) || i == j)) continue;
+            // value A(i, j): slot of j in row i
+            const int* lo = std::lower_bound(nbr.data() + ptr[i], nbr.data() + ptr[i + 1], j);
+            rowIdx[o] = i;
+            val[o] = A[(size_t)(lo - nbr.data())];
+            ++o;
+        }
+    }
+    colPtr[n] = (int32_t)o;
+    for (int i = 0; i < n; ++i) b[i] = bb[i];
+}

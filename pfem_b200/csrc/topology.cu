@@ -255,6 +255,7 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
     c->haveSystem = c->haveSolution = c->haveQprev = c->haveSnapshot = c->havePositions = c->haveDirichlet = false;
     c->nnzReference = -1;
     c->rowDirDirty = true;
+    c->haveTemperature = c->haveTemperatureBc = c->haveHeatSystem = false;
     mgInvalidate(c, true);
 
     c->conn.reserve(nConn + 4);

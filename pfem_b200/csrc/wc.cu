@@ -232,6 +232,9 @@ struct WcArgs {
     // their halo exchange overlaps the rest): node = order[k0 + k], k < nNodes; order == null: node = k0 + k
     const int* order = nullptr;
     int k0 = 0;
+    // BoussinesqWC: nodal temperature (null: off) and the buoyancy constants (WCompNewton/MomEquation.inl:105-112)
+    const double* T = nullptr;
+    double thAlpha = 0, thTr = 0;
 };
 __device__ __forceinline__ int wcNodeOf(const WcArgs& a, int k) { return a.order ? __ldg(a.order + a.k0 + k) : a.k0 + k; }
 
@@ -401,6 +404,24 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const doub
             for (int c = 0; c < DIM; ++c) gi[c] = pick<NPE>(G.g[c], li);
             const double pbar = sumP / NPE;
             const double li_mass = G.V * PHI * (pick<NPE>(rho, li) + sumR);  // lumped rho-mass == sum_g w (N.rho) N_i
+            double bodyMass = li_mass;
+            if (a.T) {  // F factor (N.rho)(1 - alpha (N.T - Tr)): Gauss sum, shape functions GA at "their" point, GB elsewhere
+                constexpr double GA = (DIM == 3) ? 0.585410196624968 : 0.66666666666666666667;
+                constexpr double GB = (DIM == 3) ? 0.138196601125011 : 0.16666666666666666667;
+                double sumT = 0, Te[NPE];
+#pragma unroll
+                for (int q = 0; q < NPE; ++q) {
+                    Te[q] = a.T[nd[q]];
+                    sumT += Te[q];
+                }
+                double fs = 0;
+#pragma unroll
+                for (int g = 0; g < NPE; ++g) {
+                    const double rg = GB * sumR + (GA - GB) * rho[g], Tg = GB * sumT + (GA - GB) * Te[g];
+                    fs += (1.0 / NPE) * (rg * (1.0 - a.thAlpha * (Tg - a.thTr))) * (g == li ? GA : GB);
+                }
+                bodyMass = G.V * fs;
+            }
 #pragma unroll
             for (int aa = 0; aa < DIM; ++aa) {
                 double sg = 0;  // sum_c sigma_ac g[c][i],  sigma = mu (G + G^T - 2/3 tr I)
@@ -410,7 +431,7 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom(const WcArgs a, const doub
                     if (c == aa) sig -= (2.0 / 3.0) * tr;
                     sg += a.mu * sig * gi[c];
                 }
-                F[aa] += -G.V * sg + G.V * pbar * gi[aa] + a.body[aa] * li_mass;
+                F[aa] += -G.V * sg + G.V * pbar * gi[aa] + a.body[aa] * bodyMass;
             }
             M += li_mass;
         }
@@ -926,7 +947,7 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom_s(const WcArgsS a, const d
 template <int DIM>
 __global__ void __launch_bounds__(256) k_wc_dt(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
                                                const double* __restrict__ V4, double mu, double K0, double K0p, double sc2,
-                                               double* __restrict__ partial) {
+                                               double* __restrict__ partial, double thKoverCv = 0.0) {
     constexpr int NPE = DIM + 1;
     double best = 1.7976931348623157e308;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nElems; e += gridDim.x * blockDim.x) {
@@ -943,7 +964,8 @@ __global__ void __launch_bounds__(256) k_wc_dt(int nElems, const int* __restrict
             double u2 = v01.x * v01.x + v01.y * v01.y;
             if (DIM == 3) u2 += v23.x * v23.x;
             const double c2 = (K0 + K0p * x23.y) / v23.y;
-            const double alpha = mu / v23.y;
+            double alpha = mu / v23.y;
+            if (thKoverCv > 0.0) alpha = nanMax(thKoverCv / v23.y, alpha);  // thermal diffusivity k/(cv rho), Solver.cpp:214-216
             mx = nanMax(nanMax(u2, c2), mx);
             alphaMax = nanMax(alpha * alpha, alphaMax);
         }
@@ -1221,6 +1243,7 @@ int wcCfgRaw() {
     return cfg;
 }
 bool wcTwoPass(const pfem_ctx* c) {
+    if (c->thermalOn) return false;  // BoussinesqWC: the buoyancy factor lives in the gather momentum kernel
     const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();  // pfem_wc_set_variant overrides the environment
     if (raw == 11 || raw == 12 || raw == 13) return true;
     if (raw != 10) return false;
@@ -1229,7 +1252,7 @@ bool wcTwoPass(const pfem_ctx* c) {
 // tiles (element records in shared memory) instead of element records in HBM: the default at size, CDS_dpdt only
 bool wcTiles(const pfem_ctx* c, const pfem_wc_params& p) {
     const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();
-    if (p.eqType != PFEM_WC_CDS_DPDT || c->maxE > 255) return false;
+    if (p.eqType != PFEM_WC_CDS_DPDT || c->maxE > 255 || c->thermalOn) return false;
     return raw == 13;  // opt-in: measured slower than the two-pass kernels on B200
 }
 // overlap of the halo exchanges with the interior node pass (PFEM_WC_OVERLAP=0 serialises them: A/B switch)
@@ -1240,6 +1263,7 @@ bool wcOverlap() {
 bool wcTwoPassMom(const pfem_ctx* c) { return (c->wcVariant ? c->wcVariant : wcCfgRaw()) != 12; }
 int wcCfg(const pfem_ctx* c) {
     const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();
+    if (c->thermalOn) return 6;
     return wcTwoPass(c) ? 10 : (raw >= 10 ? 6 : raw);
 }
 
@@ -1275,6 +1299,10 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         LAUNCH_CHECK(c);
     }
     a.fst4 = as.fst4 = facetsForces(c, c->X4.p, true);  // on the moved mesh; Facet::isOnFreeSurface = all nodes (Facet.cpp:249-255)
+    if (c->thermalOn) {  // m_solveBoussinesqWC: heat -> continuity -> momentum (Solver.cpp:278-320)
+        thermalWcHeat(c, dt, dtPtr);
+        a.T = c->Tn.p, a.thAlpha = c->thAlpha, a.thTr = c->thTr;
+    }
 #define PFEM_WC_LAUNCH_S(KERNEL, LPN_, ...)                                                                         \
     do {                                                                                                            \
         const int grid_ = divUp((int64_t)c->nRows * LPN_, 256);                                                     \
@@ -1445,10 +1473,11 @@ void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int gr
         return;
     }
     PhaseScope ph(c, "CFL element pass");
+    const double thKoverCv = c->thermalOn ? c->thK / c->thCv : 0.0;
     if (c->dim == 2)
-        k_wc_dt<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
+        k_wc_dt<2><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p, thKoverCv);
     else
-        k_wc_dt<3><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p);
+        k_wc_dt<3><<<grid, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4.p, c->V4.p, p.mu, p.K0, p.K0p, sc2, c->dtPartial.p, thKoverCv);
     LAUNCH_CHECK(c);
 }
 
@@ -1461,6 +1490,7 @@ void checkStepArgs(pfem_ctx* c, const pfem_wc_params& p, double dt) {
     c->X4b.reserve(n4);
     c->V4b.reserve(n4);
     if (p.eqType == PFEM_WC_CDS_RHO) c->wcF0.reserve((size_t)c->nNodes);
+    if (c->thermalOn) thermalPrepare(c);
     if (wcTiles(c, p) && !c->tilesValid) buildTiles(c);
     if (c->nRanks > 1 && !c->local && wcCfg(c) == 10 && !c->orderValid && wcOverlap()) buildNodeOrder(c);
     if (wcCfg(c) == 10) {  // before any graph capture
