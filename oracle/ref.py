@@ -86,6 +86,8 @@ def lib():
         L.pfem_ref_set_direct_solver.argtypes = [C.c_void_p]
         L.pfem_ref_direct_solves.restype = C.c_long
         L.pfem_ref_set_threads.argtypes = [C.c_int]
+        if hasattr(L, "pfem_ref_set_bc_ramp"):
+            L.pfem_ref_set_bc_ramp.argtypes = [C.c_double]
         L.pfem_ref_set_thermal_bc.argtypes = [I64, BP, DP]
         L.pfem_ref_get_threads.restype = C.c_int
         L.pfem_ref_cg_log.restype = C.c_long
@@ -103,6 +105,12 @@ def set_threads(n: int = 0) -> int:
     """OpenMP threads (= Problem::m_nThreads, one parameter table each) of the cases created from now on; 0 = all cores."""
     lib().pfem_ref_set_threads(int(n))
     return lib().pfem_ref_get_threads()
+
+
+def set_bc_ramp(ramp: float = 0.0) -> None:
+    """Velocity Dirichlet values of the cases created from now on become dirVal (1 + ramp t): a time-dependent
+    "<type>V"(pos, t) table like the reference's examples/2D/cylinder/cylinderComp.lua."""
+    lib().pfem_ref_set_bc_ramp(float(ramp))
 
 
 def use_scipy_direct_solver(enable: bool = True) -> None:

@@ -70,6 +70,7 @@ struct RefCase {
     std::vector<std::uint8_t> flags, dirMask;
     std::vector<std::int32_t> tags;
     std::vector<double> dirVal;
+    double bcRamp = 0.0;              // g_D(pos, t) = dirVal (1 + bcRamp t)
     std::vector<std::uint8_t> tMask;  // BoussinesqWC: node has a "<type>T" boundary condition
     std::vector<double> tVal;
     sol::table root;
@@ -209,6 +210,10 @@ void pfem_ref_set_thermal_bc(std::int64_t n, const std::uint8_t* tMask, const do
     g_tVal.assign(tVal, tVal + (n > 0 ? n : 0));
 }
 void pfem_ref_set_threads(int n) { g_threads = n > 0 ? n : omp_get_num_procs(); }
+// time dependence of the velocity Dirichlet table of the cases created from now on: g_D(pos, t) = dirVal (1 + ramp t)
+// (the "<type>V"(pos, t) signature of the reference's Lua BC functions, e.g. examples/2D/cylinder/cylinderComp.lua)
+double g_bcRamp = 0.0;
+void pfem_ref_set_bc_ramp(double ramp) { g_bcRamp = ramp; }
 int pfem_ref_get_threads() { return g_threads; }
 
 // Direct solver used by the stand-in Eigen::SparseLU (nullptr -> built-in dense LU).
@@ -247,6 +252,7 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
         rc->flags.assign(flags, flags + nNodes);
         rc->dirMask.assign(dirMask, dirMask + nNodes);
         rc->dirVal.assign(dirVal, dirVal + dim * nNodes);
+        rc->bcRamp = g_bcRamp;
         if (nFacets > 0) rc->facets.assign(facets, facets + nFacets * (dim + 2));
         rc->tags.resize(rc->N);
         const bool boussinesqWC = rc->problemId == "BoussinesqWC";
@@ -293,8 +299,10 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
         sol::function dirV = [self](const sol::Args& a) -> std::any {
             const auto pos = std::any_cast<std::array<double, 3>>(a.at(1));
             const std::size_t n = self->nodeAt(pos);
+            const double t = a.size() > 2 ? std::any_cast<double>(a.at(2)) : 0.0;
+            const double f = 1.0 + self->bcRamp * t;
             std::vector<double> g(self->dim);
-            for (int d = 0; d < self->dim; ++d) g[d] = self->dirVal[n + d * self->N];
+            for (int d = 0; d < self->dim; ++d) g[d] = self->dirVal[n + d * self->N] * f;
             return g;
         };
         sol::function dirT = [self](const sol::Args& a) -> std::any {

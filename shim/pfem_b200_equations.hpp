@@ -18,8 +18,11 @@
 #include <cstdint>
 #include <cstdlib>
 #include <limits>
+#include <memory>
+#include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "pfem_b200.h"
@@ -116,15 +119,175 @@ struct Renumbering {
     }
 };
 
+// Devices of this process: PFEM_DEVICES="0,1,2,3" (default: PFEM_DEVICE or 0).  With more than one entry the mesh is
+// RCB-partitioned by the library (pfem_partition_*) and every device gets one context driven by its own host thread
+// (pfem_comm_local_*): this is how the reference's single host process reaches several GPUs.  An id may repeat (several
+// ranks on one GPU: how the drop-in test exercises the path on a single-GPU box).
+inline std::vector<int> devicesFromEnv() {
+    std::vector<int> d;
+    if (const char* e = std::getenv("PFEM_DEVICES")) {
+        std::stringstream ss(e);
+        std::string tok;
+        while (std::getline(ss, tok, ','))
+            if (!tok.empty()) d.push_back(std::atoi(tok.c_str()));
+    }
+    if (d.empty()) d.push_back(deviceFromEnv());
+    return d;
+}
+struct RankSet {
+    std::vector<pfem_ctx*> ctx;
+    void* group = nullptr;
+    // local mesh of every rank (multi-device only): local -> global node ids, owned-node count
+    std::vector<std::vector<int64_t>> l2g;
+    std::vector<int64_t> nOwned;
+    int n() const { return (int)ctx.size(); }
+    bool multi() const { return ctx.size() > 1; }
+    RankSet(int dim) {
+        const std::vector<int> dev = devicesFromEnv();
+        ctx.assign(dev.size(), nullptr);
+        for (std::size_t r = 0; r < dev.size(); ++r)
+            if (pfem_create(&ctx[r], dim, dev[r]) != PFEM_OK) {
+                const std::string msg = std::string("pfem_create: ") + pfem_last_error(nullptr);
+                destroy();
+                throw std::runtime_error(msg);
+            }
+        if (multi()) {
+            if (pfem_comm_local_create(n(), &group) != PFEM_OK) {
+                destroy();
+                throw std::runtime_error(std::string("pfem_comm_local_create: ") + pfem_last_error(nullptr));
+            }
+            for (int r = 0; r < n(); ++r) check(ctx[r], pfem_comm_init_local(ctx[r], group, r), "pfem_comm_init_local");
+            l2g.resize(n());
+            nOwned.assign(n(), 0);
+        }
+    }
+    RankSet(const RankSet&) = delete;
+    RankSet& operator=(const RankSet&) = delete;
+    void destroy() {
+        for (auto* c : ctx)
+            if (c) pfem_destroy(c);
+        ctx.clear();
+        if (group) pfem_comm_local_destroy(group);
+        group = nullptr;
+    }
+    ~RankSet() { destroy(); }
+    // run f(rank) on every rank concurrently (collective library calls meet at internal barriers); rethrows the first failure
+    template <class F> void each(F f) {
+        if (!multi()) {
+            f(0);
+            return;
+        }
+        std::vector<std::string> err(n());
+        std::vector<std::thread> th;
+        for (int r = 0; r < n(); ++r)
+            th.emplace_back([&, r] {
+                try {
+                    f(r);
+                } catch (const std::exception& e) {
+                    err[r] = e.what();
+                    pfem_comm_abort(ctx[r]);
+                }
+            });
+        for (auto& t : th) t.join();
+        for (auto& e : err)
+            if (!e.empty() && e.find("aborted by another rank") == std::string::npos) throw std::runtime_error(e);
+        for (auto& e : err)
+            if (!e.empty()) throw std::runtime_error(e);
+    }
+    // nodal SoA array of the whole mesh (nComp x nN) -> the local array of rank r
+    std::vector<double> scatter(int r, const std::vector<double>& q, std::size_t nN) const {
+        const auto& m = l2g[r];
+        const std::size_t nComp = q.size() / nN, nl = m.size();
+        std::vector<double> o(nComp * nl);
+        for (std::size_t s = 0; s < nComp; ++s)
+            for (std::size_t k = 0; k < nl; ++k) o[k + s * nl] = q[(std::size_t)m[k] + s * nN];
+        return o;
+    }
+    // owned entries of the local array of rank r -> the whole-mesh array (ranks write disjoint entries)
+    void gatherOwned(int r, const std::vector<double>& loc, std::vector<double>& q, std::size_t nN) const {
+        const auto& m = l2g[r];
+        const std::size_t nl = m.size(), nComp = loc.size() / nl;
+        for (std::size_t s = 0; s < nComp; ++s)
+            for (int64_t k = 0; k < nOwned[r]; ++k) q[(std::size_t)m[k] + s * nN] = loc[(std::size_t)k + s * nl];
+    }
+};
+
+// whole-mesh download in the device numbering: states [first, first+count) and positions
+inline void downloadAll(RankSet& R, std::size_t nN, int dim, int first, int count, std::vector<double>* q, std::vector<double>* x) {
+    if (q) q->assign((std::size_t)count * nN, 0.0);
+    if (x) x->assign((std::size_t)dim * nN, 0.0);
+    R.each([&](int r) {
+        const std::size_t nl = R.multi() ? R.l2g[r].size() : nN;
+        std::vector<double> ql((std::size_t)count * nl), xl((std::size_t)dim * nl);
+        if (q) check(R.ctx[r], pfem_get_states(R.ctx[r], first, count, ql.data()), "pfem_get_states");
+        if (x) check(R.ctx[r], pfem_get_positions(R.ctx[r], xl.data()), "pfem_get_positions");
+        if (!R.multi()) {
+            if (q) *q = ql;
+            if (x) *x = xl;
+        } else {
+            if (q) R.gatherOwned(r, ql, *q, nN);
+            if (x) R.gatherOwned(r, xl, *x, nN);
+        }
+    });
+}
+
 // Mesh -> device: connectivity, flags, positions, states [first, first+count), Dirichlet mask/values (Lua evaluated here,
 // serially, exactly where the reference evaluates it: PSPG.inl:206-214, WCompNewton/MomEquation.inl:355-364).
+// Velocity Dirichlet data of the bound nodes whose tag carries a "<type>V" function, evaluated at time tNext and at the
+// given positions (device numbering, null: the host mesh's coordinates) -- what the reference evaluates inside
+// m_applyBCPSPG (PSPG.inl:206-214) and, on EVERY explicit step, MomEqWCompNewton::m_applyBC (MomEquation.inl:355-371).
+template <unsigned short dim, class MeshT, class SolverT, class BcTable>
+void evalDirichlet(MeshT* pMesh, SolverT* pSolver, BcTable& bc, unsigned short bcFlag, double tNext, const Renumbering& rn,
+                   const std::vector<double>* xDevice, std::vector<uint8_t>& dmask, std::vector<double>& dval, bool* anyMovingBcNode) {
+    const std::size_t nN = pMesh->getNodesCount();
+    dmask.assign(nN, 0);
+    dval.assign(dim * nN, 0.0);
+    if (anyMovingBcNode) *anyMovingBcNode = false;
+    for (std::size_t nOld = 0; nOld < nN; ++nOld) {  // old order: the Lua BC functions are called as the reference calls them
+        const auto& node = pMesh->getNode(nOld);
+        if (!(node.isBound() && pSolver->getBcTagFlags(node.getTag(), bcFlag))) continue;
+        const std::size_t n = rn.nodeNew(nOld);
+        std::array<double, 3> pos = node.getPosition();
+        if (xDevice && !node.isFixed())
+            for (unsigned short d = 0; d < dim; ++d) pos[d] = (*xDevice)[n + d * nN];
+        if (anyMovingBcNode && !node.isFixed()) *anyMovingBcNode = true;
+        const std::array<double, dim> r = bc.template call<std::array<double, dim>>(pMesh->getNodeType(nOld) + "V", pos, tNext);
+        dmask[n] = 1;
+        for (unsigned short d = 0; d < dim; ++d) dval[n + d * nN] = r[d];
+    }
+}
+inline void pushDirichlet(RankSet& R, std::size_t nN, const std::vector<uint8_t>& dmask, const std::vector<double>& dval) {
+    R.each([&](int r) {
+        if (!R.multi()) {
+            check(R.ctx[r], pfem_set_dirichlet(R.ctx[r], dmask.data(), dval.data()), "pfem_set_dirichlet");
+            return;
+        }
+        const auto& m = R.l2g[r];
+        std::vector<uint8_t> ml(m.size());
+        for (std::size_t k = 0; k < m.size(); ++k) ml[k] = dmask[(std::size_t)m[k]];
+        const std::vector<double> vl = R.scatter(r, dval, nN);
+        check(R.ctx[r], pfem_set_dirichlet(R.ctx[r], ml.data(), vl.data()), "pfem_set_dirichlet");
+    });
+}
+
+// Mesh -> device(s): connectivity, flags, positions, states [first, first+count), Dirichlet mask/values.
 template <unsigned short dim, class MeshT, class SolverT, class ProblemT, class BcTable>
-void uploadMesh(pfem_ctx* ctx, MeshT* pMesh, SolverT* pSolver, ProblemT* pProblem, BcTable& bc, unsigned short bcFlag,
+void uploadMesh(RankSet& R, MeshT* pMesh, SolverT* pSolver, ProblemT* pProblem, BcTable& bc, unsigned short bcFlag,
                 unsigned int firstState, unsigned int stateCount, bool topologyChanged, Renumbering& rn,
-                bool withFacets = false) {
+                bool withFacets = false, bool* anyMovingBcNode = nullptr) {
     const std::size_t nN = pMesh->getNodesCount(), nE = pMesh->getElementsCount();
+    std::vector<double> x(dim * nN), q(stateCount * nN), dval;
+    std::vector<uint8_t> dmask;
+    if (topologyChanged) rn.template build<dim>(pMesh);
+    for (std::size_t nOld = 0; nOld < nN; ++nOld) {
+        const auto& node = pMesh->getNode(nOld);
+        const std::size_t n = rn.nodeNew(nOld);
+        for (unsigned short d = 0; d < dim; ++d) x[n + d * nN] = node.getCoordinate(d);
+        for (unsigned int s = 0; s < stateCount; ++s) q[n + s * nN] = node.getState(firstState + s);
+    }
+    const double tNext = pProblem->getCurrentSimTime() + pSolver->getTimeStep();
+    evalDirichlet<dim>(pMesh, pSolver, bc, bcFlag, tNext, rn, nullptr, dmask, dval, anyMovingBcNode);
     if (topologyChanged) {
-        rn.template build<dim>(pMesh);
         std::vector<uint64_t> conn(nE * (dim + 1));
         for (std::size_t e = 0; e < nE; ++e) {
             const auto& element = pMesh->getElement(rn.active ? rn.elemOldOfNew[e] : e);
@@ -136,36 +299,64 @@ void uploadMesh(pfem_ctx* ctx, MeshT* pMesh, SolverT* pSolver, ProblemT* pProble
             flags[n] = (node.isBound() ? PFEM_NODE_BOUND : 0u) | (node.isFree() ? PFEM_NODE_FREE : 0u) |
                        (node.isFixed() ? PFEM_NODE_FIXED : 0u) | (node.isOnFreeSurface() ? PFEM_NODE_FREE_SURFACE : 0u);
         }
-        check(ctx, pfem_set_topology(ctx, (int64_t)nN, (int64_t)nE, conn.data(), flags.data()), "pfem_set_topology");
-        if (withFacets) {  // gamma > 0: Mesh::m_facetsList for the surface-tension facet loops (PSPG.inl:155-187, MomEquation.inl:312-336)
-            const std::size_t nF = pMesh->getFacetsCount();
-            std::vector<uint64_t> fNodes(nF * dim), fOut(nF), fElem(nF);
-            for (std::size_t f = 0; f < nF; ++f) {
-                const auto& facet = pMesh->getFacet(f);
-                for (unsigned short k = 0; k < dim; ++k) fNodes[f * dim + k] = rn.nodeNew(facet.getNodeIndex(k));
-                fOut[f] = rn.nodeNew(facet.getOutNodeIndex());
-                fElem[f] = rn.active ? rn.elemNewOfOld[facet.getElementIndex()] : facet.getElementIndex();
+        if (!R.multi()) {
+            pfem_ctx* ctx = R.ctx[0];
+            check(ctx, pfem_set_topology(ctx, (int64_t)nN, (int64_t)nE, conn.data(), flags.data()), "pfem_set_topology");
+            if (withFacets) {  // gamma > 0: Mesh::m_facetsList for the surface-tension facet loops (PSPG.inl:155-187, MomEquation.inl:312-336)
+                const std::size_t nF = pMesh->getFacetsCount();
+                std::vector<uint64_t> fNodes(nF * dim), fOut(nF), fElem(nF);
+                for (std::size_t f = 0; f < nF; ++f) {
+                    const auto& facet = pMesh->getFacet(f);
+                    for (unsigned short k = 0; k < dim; ++k) fNodes[f * dim + k] = rn.nodeNew(facet.getNodeIndex(k));
+                    fOut[f] = rn.nodeNew(facet.getOutNodeIndex());
+                    fElem[f] = rn.active ? rn.elemNewOfOld[facet.getElementIndex()] : facet.getElementIndex();
+                }
+                check(ctx, pfem_set_facets(ctx, (int64_t)nF, fNodes.data(), fOut.data(), fElem.data()), "pfem_set_facets");
             }
-            check(ctx, pfem_set_facets(ctx, (int64_t)nF, fNodes.data(), fOut.data(), fElem.data()), "pfem_set_facets");
+        } else {
+            if (withFacets) throw std::runtime_error("the B200 path supports surface tension on single-device runs only");
+            // RCB partition by the library; every rank gets its local mesh (owned nodes + one ghost-element layer) and halo plan
+            pfem_partition* part = nullptr;
+            if (pfem_partition_create(&part, dim, (int64_t)nN, (int64_t)nE, conn.data(), x.data(), R.n()) != PFEM_OK)
+                throw std::runtime_error("pfem_partition_create failed");
+            std::shared_ptr<pfem_partition> guard(part, [](pfem_partition* p) { pfem_partition_destroy(p); });
+            for (int r = 0; r < R.n(); ++r) {  // (builds the local parts serially: they share host scratch inside the handle)
+                int64_t nl = 0, no = 0, ne = 0, ns = 0;
+                int32_t np = 0;
+                if (pfem_partition_local_sizes(part, r, &nl, &no, &ne, &np, &ns) != PFEM_OK) throw std::runtime_error("pfem_partition_local_sizes failed");
+                R.l2g[r].assign((std::size_t)nl, 0);
+                R.nOwned[r] = no;
+            }
+            R.each([&](int r) {
+                int64_t nl = 0, no = 0, ne = 0, ns = 0;
+                int32_t np = 0;
+                pfem_partition_local_sizes(part, r, &nl, &no, &ne, &np, &ns);
+                std::vector<int64_t> l2gElems((std::size_t)ne), sendOff((std::size_t)np + 1), recvStart((std::size_t)np), recvCount((std::size_t)np);
+                std::vector<uint64_t> lconn((std::size_t)ne * (dim + 1));
+                std::vector<int32_t> peers((std::size_t)np), sendIdx((std::size_t)ns);
+                if (pfem_partition_local_get(part, r, R.l2g[r].data(), l2gElems.data(), lconn.data(), peers.data(), sendOff.data(),
+                                             sendIdx.data(), recvStart.data(), recvCount.data()) != PFEM_OK)
+                    throw std::runtime_error("pfem_partition_local_get failed");
+                std::vector<uint8_t> lflags((std::size_t)nl);
+                for (std::size_t k = 0; k < (std::size_t)nl; ++k) lflags[k] = flags[(std::size_t)R.l2g[r][k]];
+                pfem_ctx* ctx = R.ctx[r];
+                check(ctx, pfem_set_topology(ctx, nl, ne, lconn.data(), lflags.data()), "pfem_set_topology");
+                check(ctx, pfem_set_partition(ctx, no, np, peers.data(), sendOff.data(), sendIdx.data(), recvStart.data(), recvCount.data()),
+                      "pfem_set_partition");
+            });
         }
     }
-    std::vector<double> x(dim * nN), q(stateCount * nN), dval(dim * nN, 0.0);
-    std::vector<uint8_t> dmask(nN, 0);
-    const double tNext = pProblem->getCurrentSimTime() + pSolver->getTimeStep();
-    for (std::size_t nOld = 0; nOld < nN; ++nOld) {  // old order: the Lua BC functions are called as the reference calls them
-        const auto& node = pMesh->getNode(nOld);
-        const std::size_t n = rn.nodeNew(nOld);
-        for (unsigned short d = 0; d < dim; ++d) x[n + d * nN] = node.getCoordinate(d);
-        for (unsigned int s = 0; s < stateCount; ++s) q[n + s * nN] = node.getState(firstState + s);
-        if (node.isBound() && pSolver->getBcTagFlags(node.getTag(), bcFlag)) {
-            const std::array<double, dim> r = bc.template call<std::array<double, dim>>(pMesh->getNodeType(nOld) + "V", node.getPosition(), tNext);
-            dmask[n] = 1;
-            for (unsigned short d = 0; d < dim; ++d) dval[n + d * nN] = r[d];
+    R.each([&](int r) {
+        pfem_ctx* ctx = R.ctx[r];
+        if (!R.multi()) {
+            check(ctx, pfem_set_positions(ctx, x.data()), "pfem_set_positions");
+            check(ctx, pfem_set_states(ctx, (int)firstState, (int)stateCount, q.data()), "pfem_set_states");
+        } else {
+            check(ctx, pfem_set_positions(ctx, R.scatter(r, x, nN).data()), "pfem_set_positions");
+            check(ctx, pfem_set_states(ctx, (int)firstState, (int)stateCount, R.scatter(r, q, nN).data()), "pfem_set_states");
         }
-    }
-    check(ctx, pfem_set_positions(ctx, x.data()), "pfem_set_positions");
-    check(ctx, pfem_set_states(ctx, (int)firstState, (int)stateCount, q.data()), "pfem_set_states");
-    check(ctx, pfem_set_dirichlet(ctx, dmask.data(), dval.data()), "pfem_set_dirichlet");
+    });
+    pushDirichlet(R, nN, dmask, dval);
 }
 
 }  // namespace pfem_b200_shim
@@ -194,8 +385,9 @@ public:
         for (unsigned short d = 0; d < 3; ++d) m_par.bodyForce[d] = d < dim ? bodyForce[d] : 0.0;
         m_relTol = m_equationParams[0].doesVarExist("krylovTol") ? m_equationParams[0].template checkAndGet<double>("krylovTol") : 1e-12;
         m_needNormalCurv = false;  // facet normals are recomputed on the device (MomContEquation.inl:257 asks the host mesh for them)
-        const int rc = pfem_create(&m_ctx, dim, pfem_b200_shim::deviceFromEnv());
-        if (rc != PFEM_OK) throw std::runtime_error(std::string("pfem_create: ") + pfem_last_error(nullptr));
+        m_ranks.reset(new pfem_b200_shim::RankSet(dim));
+        if (m_ranks->multi()) throw std::runtime_error("the B200 PSPG equation drives one device from the shim (PFEM_DEVICES lists several)");
+        m_ctx = m_ranks->ctx[0];
         pfem_b200_shim::check(m_ctx, pfem_set_surface_tension(m_ctx, m_gamma), "pfem_set_surface_tension");
         // optional new key: preconditioner = "auto" | "point" | "block" | "mg"   (default auto: multigrid with hand-over)
         if (m_equationParams[0].doesVarExist("preconditioner")) {
@@ -206,7 +398,7 @@ public:
             pfem_b200_shim::check(m_ctx, pfem_pspg_set_preconditioner(m_ctx, kind, 0, 0.0), "pfem_pspg_set_preconditioner");
         }
     }
-    ~MomContEqIncompNewtonB200() override { pfem_destroy(m_ctx); }
+    ~MomContEqIncompNewtonB200() override = default;  // the rank set destroys its context
 
     // MomContEqIncompNewton::solve + PicardAlgo::solve (MomContEquation.inl:287-298, PicardAlgo.cpp:31-94)
     bool solve() override {
@@ -214,7 +406,10 @@ public:
         const std::size_t nN = m_pMesh->getNodesCount();
         m_par.dt = m_pSolver->getTimeStep();
         // the incompressible solver remeshes after every successful step (IncompNewton/Solver.cpp:241-242): new topology
-        uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bcParams[0], m_bcFlags[0], m_statesIndex[0], dim + 1, true,
+        // (Dirichlet data: evaluated here at t + dt and the start-of-step positions; the reference re-evaluates it on every
+        //  Picard iterate at the moved positions, PSPG.inl:206-214 -- identical for fixed boundary nodes and for
+        //  position-independent BC functions, which is every example of the reference)
+        uploadMesh<dim>(*m_ranks, m_pMesh, m_pSolver, m_pProblem, m_bcParams[0], m_bcFlags[0], m_statesIndex[0], dim + 1, true,
                         m_rn, m_gamma >= 1e-15);
         std::vector<double> qPrev((dim + 1) * nN), qIter((dim + 1) * nN, 0.0), qIterPrev;
         for (std::size_t n = 0; n < nN; ++n)
@@ -268,6 +463,7 @@ private:
         for (std::size_t i = 0; i < count; ++i) d[i] = q[i] * dt;
         return d;
     }
+    std::unique_ptr<pfem_b200_shim::RankSet> m_ranks;
     pfem_ctx* m_ctx = nullptr;
     pfem_pspg_params m_par{};
     pfem_b200_shim::Renumbering m_rn;
@@ -299,38 +495,56 @@ public:
         else throw std::runtime_error("unknown WCompNewton solver id: " + id);
         auto bodyForce = momParams.template checkAndGet<std::vector<double>>("bodyForce");
         for (unsigned short d = 0; d < 3; ++d) m_par.bodyForce[d] = d < dim ? bodyForce[d] : 0.0;
-        const int rc = pfem_create(&m_ctx, dim, pfem_b200_shim::deviceFromEnv());
-        if (rc != PFEM_OK) throw std::runtime_error(std::string("pfem_create: ") + pfem_last_error(nullptr));
-        pfem_b200_shim::check(m_ctx, pfem_set_surface_tension(m_ctx, m_gamma), "pfem_set_surface_tension");
+        m_ranks.reset(new pfem_b200_shim::RankSet(dim));
+        for (auto* c : m_ranks->ctx) pfem_b200_shim::check(c, pfem_set_surface_tension(c, m_gamma), "pfem_set_surface_tension");
     }
-    ~WCompNewtonStepB200() { pfem_destroy(m_ctx); }
+    ~WCompNewtonStepB200() = default;
 
     void markRemeshed() { m_dirty = true; }  // call after Mesh::remesh (WCompNewton/Solver.cpp:266-269)
 
     // m_solveWCompNewtonNoT up to the remesh test (Solver.cpp:236-263); states stay on the device between remeshes
     bool step() {
         using namespace pfem_b200_shim;
+        RankSet& R = *m_ranks;
+        const std::size_t nN = m_pMesh->getNodesCount();
         if (m_dirty) {
-            uploadMesh<dim>(m_ctx, m_pMesh, m_pSolver, m_pProblem, m_bc, 0, 0, 2 * dim + 2, true, m_rn, m_gamma >= 1e-15);
+            uploadMesh<dim>(R, m_pMesh, m_pSolver, m_pProblem, m_bc, 0, 0, 2 * dim + 2, true, m_rn, m_gamma >= 1e-15, &m_movingBcNodes);
             m_dirty = false;
+            m_dmask.clear();  // the upload evaluated the BC table at t + dt: the cache below restarts
+        } else {
+            // the reference calls "<type>V"(pos, t + dt) for every bound node on EVERY explicit step (MomEquation.inl:355-371):
+            // re-evaluate the table at the new time (and, for boundary nodes that move, at the device positions) and upload
+            // it when it changed -- a constant table costs the Lua calls only, like on the host
+            std::vector<uint8_t> dmask;
+            std::vector<double> dval, xDev;
+            if (m_movingBcNodes) downloadAll(R, nN, dim, 0, 1, nullptr, &xDev);
+            const double tNext = m_pProblem->getCurrentSimTime() + m_pSolver->getTimeStep();
+            evalDirichlet<dim>(m_pMesh, m_pSolver, m_bc, 0, tNext, m_rn, m_movingBcNodes ? &xDev : nullptr, dmask, dval, &m_movingBcNodes);
+            if (dmask != m_dmask || dval != m_dval) pushDirichlet(R, nN, dmask, dval);
+            m_dmask.swap(dmask);
+            m_dval.swap(dval);
         }
-        check(m_ctx, pfem_wc_step(m_ctx, &m_par, m_pSolver->getTimeStep()), "pfem_wc_step");
+        const double dt = m_pSolver->getTimeStep();
+        R.each([&](int r) { check(R.ctx[r], pfem_wc_step(R.ctx[r], &m_par, dt), "pfem_wc_step"); });
         return true;
     }
     // computeNextDT (Solver.cpp:192-234); throws on NaN like the reference (:231-232)
     double nextDT(double maxDT) {
-        double dt = 0;
-        const int rc = pfem_wc_next_dt(m_ctx, &m_par, m_securityCoeff, maxDT, &dt);
-        pfem_b200_shim::check(m_ctx, rc, "pfem_wc_next_dt");
-        if (rc == PFEM_NAN) throw std::runtime_error("NaN time step!");
-        return dt;
+        pfem_b200_shim::RankSet& R = *m_ranks;
+        std::vector<double> dt(R.n(), 0.0);
+        std::vector<int> rcs(R.n(), 0);
+        R.each([&](int r) {
+            rcs[r] = pfem_wc_next_dt(R.ctx[r], &m_par, m_securityCoeff, maxDT, &dt[r]);
+            pfem_b200_shim::check(R.ctx[r], rcs[r], "pfem_wc_next_dt");
+        });
+        if (rcs[0] == PFEM_NAN) throw std::runtime_error("NaN time step!");
+        return dt[0];  // the minimum is all-reduced: every rank holds the same value
     }
     // device -> host mesh (before remeshing or extractor output): states and positions
     void download() {
         const std::size_t nN = m_pMesh->getNodesCount();
-        std::vector<double> q((2 * dim + 2) * nN), x(dim * nN), xOld(dim * nN);
-        pfem_b200_shim::check(m_ctx, pfem_get_states(m_ctx, 0, 2 * dim + 2, q.data()), "pfem_get_states");
-        pfem_b200_shim::check(m_ctx, pfem_get_positions(m_ctx, x.data()), "pfem_get_positions");
+        std::vector<double> q, x, xOld(dim * nN);
+        pfem_b200_shim::downloadAll(*m_ranks, nN, dim, 0, 2 * dim + 2, &q, &x);
         q = m_rn.toOld(q, nN);
         x = m_rn.toOld(x, nN);
         for (std::size_t n = 0; n < nN; ++n) {
@@ -346,9 +560,12 @@ private:
     Mesh* m_pMesh;
     SolTable m_bc;
     double m_securityCoeff;
-    pfem_ctx* m_ctx = nullptr;
+    std::unique_ptr<pfem_b200_shim::RankSet> m_ranks;
     pfem_wc_params m_par{};
     pfem_b200_shim::Renumbering m_rn;
     double m_gamma = 0.0;
     bool m_dirty = true;
+    bool m_movingBcNodes = false;          // a bound node with a velocity BC that is not fixed: its BC sees the device position
+    std::vector<uint8_t> m_dmask;          // Dirichlet table last uploaded outside a mesh upload
+    std::vector<double> m_dval;
 };

@@ -82,3 +82,53 @@ def test_wc_steps_through_the_shim(dim, n, eq, gamma, permute):
             assert np.abs(a.positions() - b.positions()).max() < 1e-13
             dt_ref, dt = a.wc_next_dt(), b.wc_next_dt_b200()
             assert abs(dt - dt_ref) <= 1e-13 * dt_ref
+
+
+def _wc_pair(dim, n, eq, steps, check):
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.02, permute=True)
+    st = mg.wc_state(mesh)
+    st["acc"] = 0.3 * np.random.default_rng(2).standard_normal(st["acc"].shape)
+    # non-zero Dirichlet data on part of the walls (hazard 10: it becomes the boundary nodes' "acceleration")
+    vals = mesh.dir_val.reshape(dim, mesh.n_nodes)
+    sel = (mesh.dir_mask != 0) & (np.arange(mesh.n_nodes) % 2 == 0)
+    vals[:, sel] = 0.05 * np.random.default_rng(8).standard_normal((dim, int(sel.sum())))
+    mesh.dir_val = np.ascontiguousarray(vals.reshape(-1))
+    W = mg.WC_PARAMS
+    wpar = np.concatenate([orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], mg.gravity(dim), True, eq),
+                           [1e-6, 1e-3, W["securityCoeff"]]])
+    q0 = np.concatenate([st["v"], st["p"], st["rho"], st["acc"]])
+    nn = mesh.n_nodes
+    with ref.RefCase(mesh, "wc", wpar) as a, ref.RefCase(mesh, "wc", wpar) as b:
+        a.set_states(q0)
+        b.set_states(q0)
+        dt = a.wc_next_dt()
+        for step in range(steps):
+            assert a.wc_step(dt) and b.wc_step_b200(dt)
+            want, got = split_wc(a.get_states(), dim, nn), split_wc(b.get_states(), dim, nn)
+            for k in ("v", "p", "rho", "acc"):
+                assert rel_err(got[k], want[k]) < 1e-12 * 10 ** step, (k, step)
+            assert np.abs(a.positions() - b.positions()).max() < 1e-13
+            dt_ref, dt = a.wc_next_dt(), b.wc_next_dt_b200()
+            assert abs(dt - dt_ref) <= 1e-13 * dt_ref
+            check(step, want)
+
+
+def test_wc_time_dependent_dirichlet_table_through_the_shim():
+    """The reference evaluates "<type>V"(pos, t + dt) for every bound node on EVERY explicit step
+    (WCompNewton/MomEquation.inl:355-371); the shim must refresh the device table per step, not per remesh."""
+    seen = []
+    ref.set_bc_ramp(2.0e5)  # dt ~ 1e-6: the table changes by tens of percent from step to step
+    try:
+        _wc_pair(3, 5, "CDS_dpdt", 4, lambda step, want: seen.append(np.abs(want["acc"]).max()))
+    finally:
+        ref.set_bc_ramp(0.0)
+    assert len(set(seen)) > 1
+
+
+@pytest.mark.parametrize("devices", ["0,0", "0,0,0"])
+def test_wc_steps_through_the_shim_on_several_ranks(devices, monkeypatch):
+    """PFEM_DEVICES lists several devices: the shim partitions the reference's mesh with pfem_partition_*, drives one
+    context per entry from its own thread (pfem_comm_local_*) and gathers the owned nodes back -- the reference's single
+    host process on N GPUs.  Here the entries name the same GPU."""
+    monkeypatch.setenv("PFEM_DEVICES", devices)
+    _wc_pair(3, 6, "CDS_dpdt", 3, lambda step, want: None)
