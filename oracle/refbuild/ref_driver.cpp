@@ -299,7 +299,11 @@ void* pfem_ref_create(int dim, std::int64_t nNodes, std::int64_t nElems, const s
         sol::function dirV = [self](const sol::Args& a) -> std::any {
             const auto pos = std::any_cast<std::array<double, 3>>(a.at(1));
             const std::size_t n = self->nodeAt(pos);
-            const double t = a.size() > 2 ? std::any_cast<double>(a.at(2)) : 0.0;
+            double t = 0.0;
+            if (a.size() > 2) {
+                if (const double* pt = std::any_cast<double>(&a.at(2))) t = *pt;
+                else if (self->bcRamp != 0.0) throw std::runtime_error(std::string("BC time argument of type ") + a.at(2).type().name());
+            }
             const double f = 1.0 + self->bcRamp * t;
             std::vector<double> g(self->dim);
             for (int d = 0; d < self->dim; ++d) g[d] = self->dirVal[n + d * self->N] * f;
