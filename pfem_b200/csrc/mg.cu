@@ -51,6 +51,7 @@ struct MgLevel {
     DevBuf<double> sc;            // 1/sqrt|a_dd| per dof (l1 damping works in the equilibrated variables)
     double omega = 0.5;           // damping of this level's smoother (tuned or fixed)
     DevBuf<double> b, xa, xb, t, xo;
+    DevBuf<double> w, xo2;        // W-cycle: right-hand side and result of the second coarse visit
     // partitioned mesh: a DISTRIBUTED level holds this rank's rows; its vectors carry a ghost tail that
     // `plan` refreshes from the owners before every sweep.  Below a size threshold the next level is REPLICATED: every rank
     // holds all of its rows (this rank contributed rows [rowOff, rowOff + ncLocal)) and works on it redundantly, so the
@@ -90,6 +91,7 @@ struct MgHierarchy {
     bool denseOk = false;
     bool symbolicValid = false, numericValid = false, symbolicFailed = false;
     int nu = 2, nuCoarse = 2;
+    int wFrom = -1;  // W-cycle: the coarse correction of every level >= wFrom is computed twice (-1: V-cycle)
     double fixedOmega = 0.0;  // > 0: the caller's damping on every level; 0: tuned per level (tuneDamping)
     double over = 1.5;
     bool tuned = false;
@@ -622,6 +624,10 @@ __global__ void __launch_bounds__(1024) k_mg_norm2(int nDof, const double* __res
     }
 }
 
+__global__ void k_mg_add(int n, const double* __restrict__ a, double* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += a[i];
+}
 __global__ void k_to_float(size_t n, const double* __restrict__ a, float* __restrict__ f) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f[i] = (float)a[i];
 }
@@ -734,6 +740,16 @@ void cycle(pfem_ctx* c, MgHierarchy& H, int l, const double* b, double* out) {
         }
     }
     cycle(c, H, l + 1, C.b.p, C.xo.p);
+    // W-cycle: a second visit of the coarse level on the residual of the first (unsmoothed aggregation loses its mesh
+    // independence with V-cycles; the coarse levels cost a few percent of the cycle).  Not when that level is solved exactly.
+    const bool coarseExact = (l + 2 == (int)H.lev.size()) && H.denseOk;
+    if (H.wFrom >= 0 && l >= H.wFrom && !coarseExact) {
+        launchSpmv<EPI_RESID>(c, C, BS, C.xo.p, C.w.p, C.b.p);
+        cycle(c, H, l + 1, C.w.p, C.xo2.p);
+        const int nc = C.n * BS;
+        k_mg_add<<<divUp(nc, 256), 256, 0, c->stream>>>(nc, C.xo2.p, C.xo.p);
+        LAUNCH_CHECK(c);
+    }
     if (BS == 4) k_mg_prolong<4><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, C.xo.p, H.over, cur);
     else k_mg_prolong<3><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, C.xo.p, H.over, cur);
     LAUNCH_CHECK(c);
@@ -1040,7 +1056,7 @@ bool coarsen(pfem_ctx* c, MgHierarchy& H, MgLevel& L, MgLevel& C, double& cellSi
 
 void allocVectors(pfem_ctx* c, MgLevel& L, int BS) {
     const size_t nv = (size_t)L.nVec * BS + 8;
-    for (auto* v : {&L.b, &L.xa, &L.xb, &L.t, &L.xo}) {
+    for (auto* v : {&L.b, &L.xa, &L.xb, &L.t, &L.xo, &L.w, &L.xo2}) {
         const bool fresh = nv > v->cap;
         v->reserve(nv);
         if (fresh) CUDA_CHECK(cudaMemsetAsync(v->p, 0, v->cap * sizeof(double), c->stream));  // ghost entries stay zero
@@ -1263,6 +1279,8 @@ bool mgSetup(pfem_ctx* c) {
     if (c->asmStamp != H.stamp) H.tuned = false;                          // another dt: the spectrum moved
     static const int envNuC = getenv("PFEM_MG_NUC") ? atoi(getenv("PFEM_MG_NUC")) : 0;
     H.nu = nu, H.nuCoarse = envNuC > 0 ? envNuC : nu + 1, H.fixedOmega = omega, H.over = over, H.stamp = c->asmStamp;
+    static const int envW = getenv("PFEM_MG_W") ? atoi(getenv("PFEM_MG_W")) : -1;
+    H.wFrom = envW;
     if (!H.symbolicValid) {
         buildSymbolic(c, H);
         H.tuned = false;
@@ -1292,6 +1310,7 @@ void mgApply(pfem_ctx* c, double* out) {
     auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
     mix((unsigned long long)(uintptr_t)H.lev[0]->Aval), mix((unsigned long long)(uintptr_t)H.lev[0]->nbr);
     mix((unsigned long long)(uintptr_t)H.lev[0]->b.p), mix((unsigned long long)H.lev.size()), mix((unsigned long long)H.nu), mix((unsigned long long)H.nuCoarse);
+    mix((unsigned long long)(H.wFrom + 7));
     mix((unsigned long long)__double_as_longlong_host(H.over)), mix(H.denseOk ? 1ull : 0ull), mix((unsigned long long)H.nD);
     for (auto& L : H.lev) {
         mix((unsigned long long)(uintptr_t)L->Dw.p), mix((unsigned long long)(uintptr_t)L->Af.p), mix((unsigned long long)L->n);
