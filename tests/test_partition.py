@@ -110,3 +110,25 @@ def test_halo_exchange_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok in res), res
+
+
+@pytest.mark.parametrize("dim,n,n_ranks", [(3, 10, 2), (3, 12, 4), (3, 9, 8), (2, 40, 3), (3, 11, 5)])
+def test_native_partitioner_equals_the_numpy_statement(dim, n, n_ranks):
+    """csrc/partition.cu (pfem_partition_*, what the shim and the bench call) against partition.py: same owners, same
+    local meshes, same halo plans -- both order points along the widest axis by (coordinate, node index)."""
+    from pfem_b200.capi import NativePartition
+    from pfem_b200.partition import partition_mesh_native
+
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.002, permute=True)
+    h = NativePartition(dim, mesh.conn, mesh.x, n_ranks)
+    try:
+        assert (h.owner() == rcb_owner(mesh.coords(), n_ranks)).all()
+        for r in range(n_ranks):
+            a = partition_mesh(mesh, n_ranks, r)
+            b = partition_mesh_native(mesh, n_ranks, r, handle=h)
+            assert a.n_owned == b.n_owned and (a.l2g_nodes == b.l2g_nodes).all() and (a.l2g_elems == b.l2g_elems).all()
+            assert (a.mesh.conn == b.mesh.conn).all() and a.peers == b.peers
+            assert a.recv_start == b.recv_start and a.recv_count == b.recv_count
+            assert all((x == y).all() for x, y in zip(a.send_idx, b.send_idx))
+    finally:
+        h.close()
