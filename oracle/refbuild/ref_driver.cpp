@@ -634,6 +634,12 @@ template <unsigned short dim> int wcStepB200(RefCase& rc, double dt, int downloa
         SolTable material("Material", rc.problem->m_problemParams[0]);
         SolTable cont("ContEq", s->m_solverParams[0]), mom("MomEq", s->m_solverParams[0]);
         SolTable bc("BC", mom);
+        if (rc.problemId == "BoussinesqWC") {  // the heat equation's BC table: m_pEquations[2]->getBCParam(0)
+            SolTable heat("HeatEq", s->m_solverParams[0]);
+            SolTable heatBc("BC", heat);
+            rc.wcShim = std::make_shared<Shim>(rc.problem.get(), s, rc.mesh, material, cont, mom, bc,
+                                               static_cast<SolverWCompNewton*>(s)->m_securityCoeff, &heatBc);
+        } else
         rc.wcShim = std::make_shared<Shim>(rc.problem.get(), s, rc.mesh, material, cont, mom, bc, static_cast<SolverWCompNewton*>(s)->m_securityCoeff);
     }
     auto* shim = static_cast<Shim*>(rc.wcShim.get());

@@ -370,7 +370,9 @@ public:
                               const std::vector<unsigned int>& statesIndex)
         : Equation(pProblem, pSolver, pMesh, solverParams, materialParams, bcFlags, statesIndex, "MomContEq") {
         if (m_pSolver->getID() != "PSPG") throw std::runtime_error("the B200 path implements the PSPG solver only");
-        if (m_pProblem->getID() != "IncompNewtonNoT") throw std::runtime_error("the B200 path implements IncompNewtonNoT only");
+        const std::string problemId = m_pProblem->getID();
+        if (problemId != "IncompNewtonNoT" && problemId != "Bingham")
+            throw std::runtime_error("the B200 PSPG equation implements the IncompNewtonNoT and Bingham problems (Boussinesq: library only)");
         if (bcFlags.size() != 1 || statesIndex.size() != 1)
             throw std::runtime_error("the " + getID() + " equation requires one BC flag and one statesIndex");  // MomContEquation.inl:64-69
         m_par.rho = m_materialParams[0].template checkAndGet<double>("rho");
@@ -389,6 +391,11 @@ public:
         if (m_ranks->multi()) throw std::runtime_error("the B200 PSPG equation drives one device from the shim (PFEM_DEVICES lists several)");
         m_ctx = m_ranks->ctx[0];
         pfem_b200_shim::check(m_ctx, pfem_set_surface_tension(m_ctx, m_gamma), "pfem_set_surface_tension");
+        if (problemId == "Bingham") {  // MomContEquation.inl:54-58, 102-119: regularised yield-stress viscosity
+            const double tau0 = m_materialParams[0].template checkAndGet<double>("tau0");
+            const double mReg = m_materialParams[0].template checkAndGet<double>("mReg");
+            pfem_b200_shim::check(m_ctx, pfem_set_bingham(m_ctx, 1, tau0, mReg), "pfem_set_bingham");
+        }
         // optional new key: preconditioner = "auto" | "point" | "block" | "mg"   (default auto: multigrid with hand-over)
         if (m_equationParams[0].doesVarExist("preconditioner")) {
             const std::string pre = m_equationParams[0].template checkAndGet<std::string>("preconditioner");
@@ -477,9 +484,19 @@ private:
 template <unsigned short dim>
 class WCompNewtonStepB200 {
 public:
+    // heatBc: the BC table of the heat equation (m_pEquations[2]->getBCParam(0)), required for problem id "BoussinesqWC"
     WCompNewtonStepB200(Problem* pProblem, Solver* pSolver, Mesh* pMesh, SolTable& material, SolTable& contParams,
-                        SolTable& momParams, SolTable bcParams, double securityCoeff)
+                        SolTable& momParams, SolTable bcParams, double securityCoeff, const SolTable* heatBc = nullptr)
         : m_pProblem(pProblem), m_pSolver(pSolver), m_pMesh(pMesh), m_bc(bcParams), m_securityCoeff(securityCoeff) {
+        if (m_pProblem->getID() == "BoussinesqWC") {  // WCompNewton/Solver.cpp:72-130, HeatEquation.inl:26-31, MomEquation.inl:35-40
+            if (!heatBc) throw std::runtime_error("BoussinesqWC needs the heat equation's BC table");
+            m_heatBc.reset(new SolTable(*heatBc));
+            m_thermal.k = material.template checkAndGet<double>("k");
+            m_thermal.cv = material.template checkAndGet<double>("cv");
+            m_thermal.alpha = material.template checkAndGet<double>("alpha");
+            m_thermal.Tr = material.template checkAndGet<double>("Tr");
+            m_isThermal = true;
+        }
         m_par.mu = material.template checkAndGet<double>("mu");
         m_par.K0 = material.template checkAndGet<double>("K0");
         m_par.K0p = material.template checkAndGet<double>("K0p");
@@ -496,7 +513,10 @@ public:
         auto bodyForce = momParams.template checkAndGet<std::vector<double>>("bodyForce");
         for (unsigned short d = 0; d < 3; ++d) m_par.bodyForce[d] = d < dim ? bodyForce[d] : 0.0;
         m_ranks.reset(new pfem_b200_shim::RankSet(dim));
-        for (auto* c : m_ranks->ctx) pfem_b200_shim::check(c, pfem_set_surface_tension(c, m_gamma), "pfem_set_surface_tension");
+        for (auto* c : m_ranks->ctx) {
+            pfem_b200_shim::check(c, pfem_set_surface_tension(c, m_gamma), "pfem_set_surface_tension");
+            if (m_isThermal) pfem_b200_shim::check(c, pfem_set_thermal(c, &m_thermal), "pfem_set_thermal");
+        }
     }
     ~WCompNewtonStepB200() = default;
 
@@ -511,6 +531,15 @@ public:
             uploadMesh<dim>(R, m_pMesh, m_pSolver, m_pProblem, m_bc, 0, 0, 2 * dim + 2, true, m_rn, m_gamma >= 1e-15, &m_movingBcNodes);
             m_dirty = false;
             m_dmask.clear();  // the upload evaluated the BC table at t + dt: the cache below restarts
+            if (m_isThermal) {  // the temperature is the extra node state 2 dim + 2 (WCompNewton/Solver.cpp:91-92)
+                std::vector<double> T(nN);
+                for (std::size_t nOld = 0; nOld < nN; ++nOld) T[m_rn.nodeNew(nOld)] = m_pMesh->getNode(nOld).getState(2 * dim + 2);
+                R.each([&](int r) {
+                    const std::vector<double> Tl = R.multi() ? R.scatter(r, T, nN) : T;
+                    check(R.ctx[r], pfem_set_temperature(R.ctx[r], Tl.data()), "pfem_set_temperature");
+                });
+                m_tmask.clear();
+            }
         } else {
             // the reference calls "<type>V"(pos, t + dt) for every bound node on EVERY explicit step (MomEquation.inl:355-371):
             // re-evaluate the table at the new time (and, for boundary nodes that move, at the device positions) and upload
@@ -523,6 +552,33 @@ public:
             if (dmask != m_dmask || dval != m_dval) pushDirichlet(R, nN, dmask, dval);
             m_dmask.swap(dmask);
             m_dval.swap(dval);
+        }
+        if (m_isThermal) {  // "<type>T"(pos, t + dt) of the nodes whose tag carries flag 1 (HeatEquation.inl:226-244), every step
+            std::vector<uint8_t> tmask(nN, 0);
+            std::vector<double> tval(nN, 0.0);
+            const double tNext = m_pProblem->getCurrentSimTime() + m_pSolver->getTimeStep();
+            for (std::size_t nOld = 0; nOld < nN; ++nOld) {
+                const auto& node = m_pMesh->getNode(nOld);
+                if (!m_pSolver->getBcTagFlags(node.getTag(), 1)) continue;
+                const std::array<double, 1> res = m_heatBc->template call<std::array<double, 1>>(m_pMesh->getNodeType(nOld) + "T", node.getPosition(), tNext);
+                tmask[m_rn.nodeNew(nOld)] = 1;
+                tval[m_rn.nodeNew(nOld)] = res[0];
+            }
+            if (tmask != m_tmask || tval != m_tval) {
+                R.each([&](int r) {
+                    if (!R.multi()) {
+                        check(R.ctx[r], pfem_set_temperature_bc(R.ctx[r], tmask.data(), tval.data()), "pfem_set_temperature_bc");
+                        return;
+                    }
+                    const auto& m = R.l2g[r];
+                    std::vector<uint8_t> ml(m.size());
+                    for (std::size_t k = 0; k < m.size(); ++k) ml[k] = tmask[(std::size_t)m[k]];
+                    const std::vector<double> vl = R.scatter(r, tval, nN);
+                    check(R.ctx[r], pfem_set_temperature_bc(R.ctx[r], ml.data(), vl.data()), "pfem_set_temperature_bc");
+                });
+                m_tmask.swap(tmask);
+                m_tval.swap(tval);
+            }
         }
         const double dt = m_pSolver->getTimeStep();
         R.each([&](int r) { check(R.ctx[r], pfem_wc_step(R.ctx[r], &m_par, dt), "pfem_wc_step"); });
@@ -552,6 +608,18 @@ public:
             for (unsigned short d = 0; d < dim; ++d) xOld[n + d * nN] = x[n + d * nN] - m_pMesh->getNode(n).getCoordinate(d);
         }
         m_pMesh->updateNodesPosition(xOld);  // delta to the device positions (fixed nodes have delta 0)
+        if (m_isThermal) {
+            pfem_b200_shim::RankSet& R = *m_ranks;
+            std::vector<double> T(nN, 0.0);
+            R.each([&](int r) {
+                const std::size_t nl = R.multi() ? R.l2g[r].size() : nN;
+                std::vector<double> Tl(nl);
+                pfem_b200_shim::check(R.ctx[r], pfem_get_temperature(R.ctx[r], Tl.data()), "pfem_get_temperature");
+                if (R.multi()) R.gatherOwned(r, Tl, T, nN);
+                else T = Tl;
+            });
+            for (std::size_t nOld = 0; nOld < nN; ++nOld) m_pMesh->setNodeState(nOld, 2 * dim + 2, T[m_rn.nodeNew(nOld)]);
+        }
     }
 
 private:
@@ -565,6 +633,11 @@ private:
     pfem_b200_shim::Renumbering m_rn;
     double m_gamma = 0.0;
     bool m_dirty = true;
+    bool m_isThermal = false;              // problem id "BoussinesqWC"
+    pfem_thermal_params m_thermal{};
+    std::unique_ptr<SolTable> m_heatBc;
+    std::vector<uint8_t> m_tmask;
+    std::vector<double> m_tval;
     bool m_movingBcNodes = false;          // a bound node with a velocity BC that is not fixed: its BC sees the device position
     std::vector<uint8_t> m_dmask;          // Dirichlet table last uploaded outside a mesh upload
     std::vector<double> m_dval;

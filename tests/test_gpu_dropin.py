@@ -132,3 +132,64 @@ def test_wc_steps_through_the_shim_on_several_ranks(devices, monkeypatch):
     host process on N GPUs.  Here the entries name the same GPU."""
     monkeypatch.setenv("PFEM_DEVICES", devices)
     _wc_pair(3, 6, "CDS_dpdt", 3, lambda step, want: None)
+
+
+@pytest.mark.parametrize("dim,n", [(2, 8), (3, 4)])
+def test_bingham_time_step_through_the_shim(dim, n):
+    """Problem id "Bingham" (SURVEY 8f rank 3): the shim reads tau0 / mReg from the Material table (MomContEquation.inl:54-58)
+    and the library assembles with the shear-rate dependent viscosity; one PicardAlgo time step on both sides."""
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.02, permute=True)
+    _, q_prev = mg.pspg_state(mesh)
+    P = mg.PSPG_PARAMS
+    par = np.concatenate([orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim)), [10, 1e-6]])
+    nn = mesh.n_nodes
+    out = {}
+    for which, bingham in (("newtonian", None), ("reference", (50.0, 100.0)), ("b200", (50.0, 100.0))):
+        with ref.RefCase(mesh, "pspg", par, bingham=bingham) as rc:
+            if which == "b200":
+                rc.use_b200_equation()
+            rc.set_states(q_prev)
+            ok, _ = rc.pspg_solve()
+            assert ok
+            out[which] = rc.get_states()
+    assert rel_err(out["b200"][: dim * nn], out["reference"][: dim * nn]) < 1e-8
+    assert rel_err(out["b200"][dim * nn:], out["reference"][dim * nn:]) < 1e-8
+    assert rel_err(out["reference"][: dim * nn], out["newtonian"][: dim * nn]) > 1e-4  # the yield stress is live
+
+
+@pytest.mark.parametrize("dim,n", [(2, 8), (3, 4)])
+def test_boussinesq_wc_steps_through_the_shim(dim, n):
+    """Problem id "BoussinesqWC": the shim sets the thermal factors from the Material table, uploads the temperature
+    state 2 dim + 2 and evaluates the heat equation's "<type>T" table (HeatEquation.inl:226-244); the reference runs
+    m_solveBoussinesqWC (WCompNewton/Solver.cpp:278-320)."""
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.02, permute=True)
+    nn = mesh.n_nodes
+    st = mg.wc_state(mesh)
+    st["acc"] = 0.3 * np.random.default_rng(3).standard_normal(st["acc"].shape)
+    c = mesh.coords()
+    T0 = 300.0 + 10.0 * c[:, 0] + 2.0 * np.random.default_rng(5).standard_normal(nn)
+    bound = (mesh.flags & mg.F_BOUND) != 0
+    t_mask = (bound & ((np.abs(c[:, 0]) < 1e-12) | (np.abs(c[:, 0] - 1.0) < 1e-12))).astype(np.uint8)
+    t_val = np.where(c[:, 0] < 0.5, 310.0, 290.0)
+    th = dict(k=6.0e3, cv=4.186, alpha=6.9e-3, Tr=300.0, t_mask=t_mask, t_val=t_val)
+    W = mg.WC_PARAMS
+    wpar = np.concatenate([orc.wc_param_array(W["mu"], W["K0"], W["K0p"], W["rhoStar"], mg.gravity(dim), True, "CDS_dpdt"),
+                           [1e-6, 1e-3, W["securityCoeff"]]])
+    q0 = np.concatenate([st["v"], st["p"], st["rho"], st["acc"], T0])
+    with ref.RefCase(mesh, "wc", wpar, thermal=th) as a, ref.RefCase(mesh, "wc", wpar, thermal=th) as b:
+        a.set_states(q0)
+        b.set_states(q0)
+        dt = a.wc_next_dt()
+        for step in range(3):
+            assert a.wc_step(dt) and b.wc_step_b200(dt)
+            qa, qb = a.get_states(), b.get_states()
+            want, got = split_wc(qa[: (2 * dim + 2) * nn], dim, nn), split_wc(qb[: (2 * dim + 2) * nn], dim, nn)
+            for k in ("v", "p", "rho", "acc"):
+                assert rel_err(got[k], want[k]) < 1e-12 * 10 ** step, (k, step)
+            Ta, Tb = qa[(2 * dim + 2) * nn:], qb[(2 * dim + 2) * nn:]
+            assert rel_err(Tb, Ta) < 1e-13
+            assert np.array_equal(Ta[t_mask != 0], t_val[t_mask != 0])
+            assert np.abs(a.positions() - b.positions()).max() < 1e-13
+            dt_ref, dt = a.wc_next_dt(), b.wc_next_dt_b200()
+            assert abs(dt - dt_ref) <= 1e-13 * dt_ref
+        assert np.abs(Ta - T0).max() > 1e-3  # conduction moved the temperature
