@@ -82,8 +82,8 @@ static NcclApi* loadNccl() {
 
 namespace {
 // buf[(e*width + c)] = arr[idx[e]*width + c]
-__global__ void k_pack(const int* __restrict__ idx, int nSend, int width, const double* __restrict__ arr,
-                       double* __restrict__ buf) {
+template <typename T>
+__global__ void k_pack(const int* __restrict__ idx, int nSend, int width, const T* __restrict__ arr, T* __restrict__ buf) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nSend * width) return;
     const int e = t / width, cidx = t % width;
@@ -255,19 +255,21 @@ void commFinishPlan(pfem_ctx* c, HaloPlan& P) {
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
 }
 
-// owners -> ghosts for up to two nodal arrays of `width` doubles per node
-void commHaloPlan(pfem_ctx* c, HaloPlan& P, double* arr0, double* arr1, int width) {
+// owners -> ghosts for up to two nodal arrays of `width` values of type T per node
+template <typename T> void commHaloPlanT(pfem_ctx* c, HaloPlan& P, T* arr0, T* arr1, int width) {
     if (c->nRanks <= 1) return;
     PFEM_REQUIRE(c->comm || c->local, PFEM_ERR_COMM, "halo exchange without a communicator");
     if (!c->local && P.peers.empty()) return;  // the local transport meets at barriers: every rank takes part
     PhaseScope ph(c, "Halo exchange");
     const int nArr = arr1 ? 2 : 1;
-    double* arrs[2] = {arr0, arr1};
-    P.sendBuf.reserve((size_t)P.nSendTotal * width * nArr + 8);
+    T* arrs[2] = {arr0, arr1};
+    P.sendBuf.reserve((size_t)P.nSendTotal * width * nArr + 8);  // sized in doubles: enough for either type
+    T* sendBuf = reinterpret_cast<T*>(P.sendBuf.p);
+    const ncclDataType_t ncclT = sizeof(T) == 8 ? ncclFloat64 : ncclFloat32;
     for (int k = 0; k < nArr; ++k) {
         if (P.nSendTotal > 0) {
-            k_pack<<<divUp((int64_t)P.nSendTotal * width, 256), 256, 0, c->stream>>>(
-                P.sendIdx.p, P.nSendTotal, width, arrs[k], P.sendBuf.p + (size_t)k * P.nSendTotal * width);
+            k_pack<T><<<divUp((int64_t)P.nSendTotal * width, 256), 256, 0, c->stream>>>(
+                P.sendIdx.p, P.nSendTotal, width, arrs[k], sendBuf + (size_t)k * P.nSendTotal * width);
             LAUNCH_CHECK(c);
         }
     }
@@ -288,8 +290,8 @@ void commHaloPlan(pfem_ctx* c, HaloPlan& P, double* arr0, double* arr1, int widt
             CUDA_CHECK(cudaStreamWaitEvent(c->stream, o.ctx->evPacked, 0));
             for (int k = 0; k < nArr; ++k)
                 CUDA_CHECK(cudaMemcpyAsync(arrs[k] + (size_t)p.recvStart * width,
-                                           o.src + ((size_t)k * o.plan->nSendTotal + q->sendOff) * width,
-                                           (size_t)p.recvCount * width * sizeof(double), cudaMemcpyDefault, c->stream));
+                                           reinterpret_cast<const T*>(o.src) + ((size_t)k * o.plan->nSendTotal + q->sendOff) * width,
+                                           (size_t)p.recvCount * width * sizeof(T), cudaMemcpyDefault, c->stream));
         }
         CUDA_CHECK(cudaEventRecord(c->evCopied, c->stream));
         g->barrier();
@@ -302,15 +304,18 @@ void commHaloPlan(pfem_ctx* c, HaloPlan& P, double* arr0, double* arr1, int widt
     for (int k = 0; k < nArr; ++k) {
         for (const auto& p : P.peers) {
             if (p.sendCount > 0)
-                NCCL_CHECK(api, api->Send(P.sendBuf.p + ((size_t)k * P.nSendTotal + p.sendOff) * width,
-                                          (size_t)p.sendCount * width, ncclFloat64, p.rank, (ncclComm_t)c->comm, c->stream));
+                NCCL_CHECK(api, api->Send(sendBuf + ((size_t)k * P.nSendTotal + p.sendOff) * width,
+                                          (size_t)p.sendCount * width, ncclT, p.rank, (ncclComm_t)c->comm, c->stream));
             if (p.recvCount > 0)
-                NCCL_CHECK(api, api->Recv(arrs[k] + (size_t)p.recvStart * width, (size_t)p.recvCount * width, ncclFloat64,
+                NCCL_CHECK(api, api->Recv(arrs[k] + (size_t)p.recvStart * width, (size_t)p.recvCount * width, ncclT,
                                           p.rank, (ncclComm_t)c->comm, c->stream));
         }
     }
     NCCL_CHECK(api, api->GroupEnd());
 }
+template void commHaloPlanT<double>(pfem_ctx*, HaloPlan&, double*, double*, int);
+template void commHaloPlanT<float>(pfem_ctx*, HaloPlan&, float*, float*, int);
+void commHaloPlan(pfem_ctx* c, HaloPlan& P, double* arr0, double* arr1, int width) { commHaloPlanT<double>(c, P, arr0, arr1, width); }
 void commHalo(pfem_ctx* c, double* arr0, double* arr1, int width) { commHaloPlan(c, c->plan, arr0, arr1, width); }
 
 static void localAllReduce(pfem_ctx* c, double* buf, int count, bool isMin) {

@@ -153,6 +153,10 @@ struct pfem_ctx {
     double asmStamp = 0.0;     // dt of the assembled system (the multigrid dampings are re-tuned when it changes)
     DevBuf<double> kx, kr, kr0, kp, kp2, kv, ks, kt, kph, ksh;  // Krylov vectors (internal dof order)
     DevBuf<double> partial;    // PS_COUNT * reduceBlocks
+    bool mgFlexible = false;   // the Krylov method tolerates a slightly non-linear preconditioner (FGMRES): fp32 cycle vectors
+    DevBuf<double> gmV, gmZ;   // FGMRES: orthonormal basis (owned dofs) and preconditioned directions (owned + ghost dofs)
+    DevBuf<double> gmBank;     // (restart + 2) * reduceBlocks partial dot products
+    DevBuf<double> gmS;        // Hessenberg column, rotations, g, y (GmLayout in krylov.cu)
     DevBuf<double> scal;       // SC_COUNT
     double* hScal = nullptr;   // pinned mirror
     int reduceBlocks = 0;
@@ -342,6 +346,7 @@ void commSetPartition(pfem_ctx* c, int64_t nOwned, int nPeers, const int32_t* pe
                       const int32_t* sendIdx, const int64_t* recvStart, const int64_t* recvCount);
 void commHalo(pfem_ctx* c, double* arr0, double* arr1, int width);  // owners -> ghosts, up to two nodal arrays (level-0 plan)
 void commHaloPlan(pfem_ctx* c, HaloPlan& plan, double* arr0, double* arr1, int width);
+template <typename T> void commHaloPlanT(pfem_ctx* c, HaloPlan& plan, T* arr0, T* arr1, int width);  // T = double | float
 void commAllReduceSum(pfem_ctx* c, double* buf, int count);
 void commAllReduceMin(pfem_ctx* c, double* devScalar);
 // every rank contributes counts[rank] doubles from `src`; all of them land in `dst` at displs[r] on every rank (device buffers;

@@ -363,6 +363,179 @@ __global__ void __launch_bounds__(RB_THREADS) k_update_xr(int n, double* __restr
     const int slots[2] = {PS_RHO, PS_RR};
     blockSumStore<2>(vv, partial, stride, slots);
 }
+// ---- flexible GMRES(m) for the multigrid-preconditioned solve -------------------------------------------------------------
+// BiCGSTAB spends two multigrid cycles and two SpMV per iteration; right-preconditioned GMRES minimises the residual over the
+// same Krylov space with ONE cycle and ONE SpMV per basis vector and needs ~0.68x the cycles (prototype:
+// tests/research/krylov_proto.py).  The cycle dominates (0.73 of 0.9 ms per basis vector at C4), the orthogonalisation is
+// classical Gram-Schmidt as two passes: all dots against the same w (chunks of 8 basis vectors per launch, w stays in
+// registers), then w -= sum h_i v_i with its norm fused.  Flexible form: the preconditioned directions z_k are kept, the
+// solution update is x += sum y_k z_k, consistent with the recurrence whatever the (fp32, fixed) cycle does.
+// Every reduction goes through the ordered partial-sum bank: bit-reproducible like the BiCGSTAB path.
+struct GmLayout {  // offsets into gmS for restart length m
+    int m;
+    __host__ __device__ int h() const { return 0; }                  // m + 2 reduced dots of the current column
+    __host__ __device__ int H() const { return m + 2; }              // (m + 1) x m Hessenberg, column-major, rotated in place
+    __host__ __device__ int cs() const { return H() + (m + 1) * m; }
+    __host__ __device__ int sn() const { return cs() + m; }
+    __host__ __device__ int g() const { return sn() + m; }           // m + 1
+    __host__ __device__ int y() const { return g() + m + 1; }        // m
+    __host__ __device__ int scale() const { return y() + m; }        // 1 / h_{k+1,k} of the last column
+    __host__ __device__ int count() const { return scale() + 1; }
+};
+// v_0 = r / ||r|| ; rhs of the first cycle = S^-1 v_0 ; g = (||r||, 0, ...)
+__global__ void __launch_bounds__(RB_THREADS) k_gm_first(int n, const double* __restrict__ r, const double* __restrict__ dinv,
+                                                         double* __restrict__ v0, double* __restrict__ mgRhs, double* scal,
+                                                         double* gs, GmLayout L, const double* partial, int stride, int nPart) {
+    const double rr = bankSum(partial, stride, PS_RR, nPart);
+    const bool conv = rr <= scal[SC_TOL2], bad = !(rr == rr);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[SC_RES2] = rr;
+        scal[SC_ITERS] = 0.0;
+        if (conv || bad) scal[SC_DONE] = 1.0;
+        if (bad) scal[SC_BAD] = 1.0;
+        gs[L.g()] = sqrt(rr);
+    }
+    if (conv || bad) return;
+    const double inv = 1.0 / sqrt(rr);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double vi = r[i] * inv;
+        v0[i] = vi;
+        mgRhs[i] = vi / dinv[i];
+    }
+}
+// partial dots (v_{i0+j}, w), j < nv <= 8, into bank slots i0 + j; the last chunk also stores (w, w) in slot `slotWW`
+__global__ void __launch_bounds__(RB_THREADS) k_gm_dots(int n, const double* __restrict__ V, size_t ldv, int i0, int nv,
+                                                        const double* __restrict__ w, double* bank, int stride, int slotWW) {
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double ww = 0;
+    const double* Vb = V + (size_t)i0 * ldv;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double wi = w[i];
+        ww += wi * wi;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nv) acc[j] += Vb[(size_t)j * ldv + i] * wi;
+    }
+    __shared__ double sh[9][RB_THREADS / 32];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double t = warpSum(acc[j]);
+        if (lane == 0) sh[j][wp] = t;
+    }
+    {
+        const double t = warpSum(ww);
+        if (lane == 0) sh[8][wp] = t;
+    }
+    __syncthreads();
+    if (wp == 0) {
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            double t = lane < nw ? sh[j][lane] : 0.0;
+            t = warpSum(t);
+            if (lane == 0) {
+                if (j < 8 && j < nv) bank[(size_t)(i0 + j) * stride + blockIdx.x] = t;
+                if (j == 8 && slotWW >= 0) bank[(size_t)slotWW * stride + blockIdx.x] = t;
+            }
+        }
+    }
+}
+// h_i = sum of bank slot i (fixed order), i < count
+__global__ void __launch_bounds__(RB_THREADS) k_gm_reduce(const double* bank, int stride, int nPart, int slot0, int count, double* out) {
+    for (int i = 0; i < count; ++i) {
+        const double t = bankSum(bank, stride, slot0 + i, nPart);
+        if (threadIdx.x == 0) out[i] = t;
+    }
+}
+// w -= sum_{i<=k} h_i v_i ; partial ||w||^2 into bank slot `slotN`
+__global__ void __launch_bounds__(RB_THREADS) k_gm_update(int n, const double* __restrict__ V, size_t ldv, int nv,
+                                                          const double* __restrict__ h, double* __restrict__ w, double* bank,
+                                                          int stride, int slotN) {
+    __shared__ double hs[64];
+    if (threadIdx.x < nv) hs[threadIdx.x] = h[threadIdx.x];
+    __syncthreads();
+    double nn = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double a = w[i];
+#pragma unroll 4
+        for (int j = 0; j < nv; ++j) a -= hs[j] * V[(size_t)j * ldv + i];
+        w[i] = a;
+        nn += a * a;
+    }
+    double vv[1] = {nn};
+    const int slots[1] = {slotN};
+    blockSumStore<1>(vv, bank, stride, slots);
+}
+// column k of the Hessenberg matrix: previous rotations, new rotation, residual estimate |g_{k+1}|, convergence flag
+__global__ void __launch_bounds__(RB_THREADS) k_gm_givens(int k, double* gs, GmLayout L, const double* bank, int stride,
+                                                          int nPart, int slotN, double* scal) {
+    const double nn = bankSum(bank, stride, slotN, nPart);
+    if (threadIdx.x != 0) return;
+    double* Hc = gs + L.H() + (size_t)k * (L.m + 1);
+    const double* h = gs + L.h();
+    double* cs = gs + L.cs();
+    double* sn = gs + L.sn();
+    double* g = gs + L.g();
+    for (int i = 0; i <= k; ++i) Hc[i] = h[i];
+    const double hk1 = sqrt(nn);
+    for (int i = 0; i < k; ++i) {
+        const double t = cs[i] * Hc[i] + sn[i] * Hc[i + 1];
+        Hc[i + 1] = -sn[i] * Hc[i] + cs[i] * Hc[i + 1];
+        Hc[i] = t;
+    }
+    const double d = hypot(Hc[k], hk1);
+    const bool bad = !(d == d) || !(fabs(d) < 1e300) || d == 0.0;
+    const double c = bad ? 1.0 : Hc[k] / d, s = bad ? 0.0 : hk1 / d;
+    cs[k] = c;
+    sn[k] = s;
+    Hc[k] = bad ? 1.0 : d;
+    Hc[k + 1] = 0.0;
+    g[k + 1] = -s * g[k];
+    g[k] = c * g[k];
+    const double res2 = g[k + 1] * g[k + 1];
+    gs[L.scale()] = hk1 > 0.0 ? 1.0 / hk1 : 0.0;
+    scal[SC_RES2] = res2;
+    scal[SC_ITERS] = (double)(k + 1);
+    if (bad) scal[SC_DONE] = 1.0, scal[SC_BAD] = 1.0;
+    else if (res2 <= scal[SC_TOL2] || hk1 == 0.0) scal[SC_DONE] = 1.0;
+}
+// v_{k+1} = w / h_{k+1,k} ; rhs of the next cycle = S^-1 v_{k+1}
+__global__ void __launch_bounds__(RB_THREADS) k_gm_next(int n, const double* __restrict__ w, const double* __restrict__ dinv,
+                                                        double* __restrict__ vNext, double* __restrict__ mgRhs,
+                                                        const double* __restrict__ gs, GmLayout L, const double* scal) {
+    if (scal[SC_DONE] != 0.0) return;
+    const double inv = gs[L.scale()];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double vi = w[i] * inv;
+        vNext[i] = vi;
+        mgRhs[i] = vi / dinv[i];
+    }
+}
+// y = R^-1 g (k x k upper triangle left by the rotations)
+__global__ void k_gm_backsolve(int k, double* gs, GmLayout L) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double* H = gs + L.H();
+    const double* g = gs + L.g();
+    double* y = gs + L.y();
+    for (int i = k - 1; i >= 0; --i) {
+        double t = g[i];
+        for (int j = i + 1; j < k; ++j) t -= H[(size_t)j * (L.m + 1) + i] * y[j];
+        y[i] = t / H[(size_t)i * (L.m + 1) + i];
+    }
+}
+// x += sum_{j<k} y_j z_j
+__global__ void __launch_bounds__(RB_THREADS) k_gm_xupdate(int n, const double* __restrict__ Z, size_t ldz, int k,
+                                                           const double* __restrict__ y, double* __restrict__ x) {
+    __shared__ double ys[64];
+    if (threadIdx.x < k) ys[threadIdx.x] = y[threadIdx.x];
+    __syncthreads();
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        double a = x[i];
+#pragma unroll 4
+        for (int j = 0; j < k; ++j) a += ys[j] * Z[(size_t)j * ldz + i];
+        x[i] = a;
+    }
+}
 // d = b - y ; partial ||d||^2 (true residual)
 __global__ void __launch_bounds__(RB_THREADS) k_resid(int n, const double* __restrict__ b, const double* __restrict__ y,
                                                       const double* __restrict__ sc, double* partial, int stride) {
@@ -527,6 +700,129 @@ static double residualNorm(pfem_ctx* c, double* xInternal, const double* scale) 
 }
 double krylovResidualNorm(pfem_ctx* c, double* xInternal) { return residualNorm(c, xInternal, nullptr); }
 
+namespace {
+// restart length of the flexible GMRES (PFEM_GMRES_M, <= 62); 0 selects BiCGSTAB for the multigrid-preconditioned solve too
+int gmresRestart() {
+    static const int v = getenv("PFEM_GMRES_M") ? std::max(0, std::min(62, atoi(getenv("PFEM_GMRES_M")))) : 40;
+    return v;
+}
+struct GmresOutcome {
+    int status = PFEM_OK;
+    int iters = 0;
+    double relRes = 0;
+    bool giveUp = false, diverged = false;
+};
+// FGMRES(m) cycles on the equilibrated system with the multigrid cycle as right preconditioner; x (physical variables) in kx
+GmresOutcome gmresSolve(pfem_ctx* c, const KrylovDims& k, double relTol, int maxIter, bool warmStart, bool mgAuto, double* mgB) {
+    GmresOutcome out;
+    const int m = gmresRestart();
+    GmLayout L{m};
+    const size_t ldv = ((size_t)k.n + 7) & ~(size_t)7, ldz = ((size_t)k.nAll + 7) & ~(size_t)7;
+    c->gmV.reserve(ldv * (m + 1) + 8);
+    c->gmZ.reserve(ldz * m + 8);
+    c->gmBank.reserve((size_t)(m + 3) * k.stride);
+    c->gmS.reserve(L.count() + 8);
+    const int slotWW = m + 1, slotN = m + 2;
+    double* gs = c->gmS.p;
+    double* w = c->kt.p;
+    double rrFirst = -1.0;
+    const int maxRestarts = 12;
+    for (int restart = 0; restart <= maxRestarts; ++restart) {
+        const bool zeroGuess = !warmStart && restart == 0;
+        if (!zeroGuess) spmv(c, k, c->kx.p, c->kt.p, nullptr, -1, -1, false, c->dinv.p);
+        k_init<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->bvec.p, zeroGuess ? nullptr : c->kt.p, c->dinv.p, c->kr.p,
+                                                        c->kr0.p, c->kp.p, c->kv.p, c->partial.p, k.stride);
+        LAUNCH_CHECK(c);
+        const int npVec = globalise(c, k, PS_RHO, PS_RR, k.vecGrid);
+        globalise(c, k, PS_AUX, -1, k.vecGrid);
+        k_init_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, c->partial.p, k.stride, npVec, relTol, 1, restart == 0);
+        LAUNCH_CHECK(c);
+        k_gm_first<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->dinv.p, c->gmV.p, mgB, c->scal.p, gs, L, c->partial.p,
+                                                            k.stride, npVec);
+        LAUNCH_CHECK(c);
+        int j = 0;  // basis vectors built in this cycle
+        bool done = false;
+        while (!done && j < m && out.iters + j < maxIter) {
+            mgApply(c, c->kph.p);
+            spmv(c, k, c->kph.p, w, nullptr, -1, -1, false, c->dinv.p);  // w = S A z (ghost entries of z refreshed first)
+            CUDA_CHECK(cudaMemcpyAsync(c->gmZ.p + (size_t)j * ldz, c->kph.p, (size_t)k.nAll * sizeof(double), cudaMemcpyDeviceToDevice,
+                                       c->stream));
+            {
+                PhaseScope ph(c, "GMRES orthogonalisation");
+                for (int i0 = 0; i0 <= j; i0 += 8) {
+                    const int nv = std::min(8, j + 1 - i0);
+                    k_gm_dots<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->gmV.p, ldv, i0, nv, w, c->gmBank.p, k.stride,
+                                                                     i0 + 8 > j ? slotWW : -1);
+                    LAUNCH_CHECK(c);
+                }
+                k_gm_reduce<<<1, RB_THREADS, 0, c->stream>>>(c->gmBank.p, k.stride, k.vecGrid, 0, j + 1, gs + L.h());
+                LAUNCH_CHECK(c);
+                if (k.multi) commAllReduceSum(c, gs + L.h(), j + 1);
+                k_gm_update<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->gmV.p, ldv, j + 1, gs + L.h(), w, c->gmBank.p, k.stride,
+                                                                   slotN);
+                LAUNCH_CHECK(c);
+                int npN = k.vecGrid;
+                if (k.multi) {
+                    k_bank_collapse<<<1, RB_THREADS, 0, c->stream>>>(c->gmBank.p, k.stride, slotN, -1, npN);
+                    LAUNCH_CHECK(c);
+                    commAllReduceSum(c, c->gmBank.p + (size_t)slotN * k.stride, 1);
+                    npN = 1;
+                }
+                k_gm_givens<<<1, RB_THREADS, 0, c->stream>>>(j, gs, L, c->gmBank.p, k.stride, npN, slotN, c->scal.p);
+                LAUNCH_CHECK(c);
+                k_gm_next<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, w, c->dinv.p, c->gmV.p + (size_t)(j + 1) * ldv, mgB, gs, L,
+                                                                 c->scal.p);
+                LAUNCH_CHECK(c);
+            }
+            ++j;
+            CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+            const double rr = c->hScal[SC_RES2];
+            if (c->hScal[SC_DONE] != 0.0 || !(rr == rr)) done = true;
+            else if (mgAuto) {  // GMRES cannot diverge; a cycle that is no preconditioner shows as stagnation
+                if (rrFirst < 0.0) rrFirst = rr;
+                if (out.iters + j >= 50 && rr > 1e-3 * rrFirst) out.giveUp = done = true;
+            }
+        }
+        if (j > 0) {  // x += Z y
+            k_gm_backsolve<<<1, 32, 0, c->stream>>>(j, gs, L);
+            LAUNCH_CHECK(c);
+            k_gm_xupdate<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->gmZ.p, ldz, j, gs + L.y(), c->kx.p);
+            LAUNCH_CHECK(c);
+        } else {
+            CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        }
+        out.iters += j;
+        if (out.giveUp) {
+            out.status = PFEM_NOT_CONVERGED;
+            break;
+        }
+        const double bnorm = sqrt(c->hScal[SC_BNORM2]);
+        if (bnorm == 0.0) {
+            k_zero<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(c->kx.p, k.nAll);
+            LAUNCH_CHECK(c);
+            out.relRes = 0;
+            out.status = PFEM_OK;
+            break;
+        }
+        const double trueRes = residualNorm(c, c->kx.p, c->dinv.p);
+        out.relRes = trueRes / bnorm;
+        if (!(out.relRes == out.relRes)) {
+            out.status = PFEM_NAN;
+            break;
+        }
+        if (out.relRes <= relTol * 1.0000001) {
+            out.status = PFEM_OK;
+            break;
+        }
+        out.status = PFEM_NOT_CONVERGED;
+        if (out.iters >= maxIter) break;
+    }
+    return out;
+}
+}  // namespace
+
 int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* relResOut, bool warmStart) {
     PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "solve: no assembled system (pfem_pspg_assemble)");
     PFEM_REQUIRE(relTol > 0 && maxIter > 0, PFEM_ERR_INVALID, "solve: relTol and maxIter must be positive");
@@ -549,6 +845,7 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
         else if (envPre == "block") kind = PFEM_PRECOND_BLOCK;
         else kind = PFEM_PRECOND_MG;
     }
+    c->mgFlexible = kind == PFEM_PRECOND_MG && gmresRestart() > 0;
     if (kind == PFEM_PRECOND_MG && !mgSetup(c)) kind = PFEM_PRECOND_BLOCK;  // mesh too small for a second level
     c->lastPrecond = kind;
     double* mgB = kind == PFEM_PRECOND_MG ? mgRhs(c) : nullptr;
@@ -574,7 +871,12 @@ int krylovSolve(pfem_ctx* c, double relTol, int maxIter, int* itersOut, double* 
         W = c->Wblk.p;
     }
     const int maxRestarts = 12;
-    for (int restart = 0; restart <= maxRestarts; ++restart) {
+    const bool useGmres = kind == PFEM_PRECOND_MG && gmresRestart() > 0;
+    if (useGmres) {
+        const GmresOutcome g = gmresSolve(c, k, relTol, maxIter, warmStart, mgAuto, mgB);
+        status = g.status, totalIters = g.iters, relRes = g.relRes, mgGiveUp = g.giveUp, mgDiverged = g.diverged;
+    }
+    for (int restart = 0; !useGmres && restart <= maxRestarts; ++restart) {
         // r = b - A x
         const bool zeroGuess = !warmStart && restart == 0;
         if (!zeroGuess) spmv(c, k, c->kx.p, c->kt.p, nullptr, -1, -1, false, c->dinv.p);

@@ -48,6 +48,7 @@ struct MgLevel {
     DevBuf<int> agg, aggPtr, aggNodes, cslot;
     // numeric
     DevBuf<double> Dw;            // omega * A_ii^-1
+    DevBuf<float> DwF;            // fp32 copy for the fp32-vector cycle
     DevBuf<double> sc;            // 1/sqrt|a_dd| per dof (l1 damping works in the equilibrated variables)
     double omega = 0.5;           // damping of this level's smoother (tuned or fixed)
     DevBuf<double> b, xa, xb, t, xo;
@@ -91,6 +92,9 @@ struct MgHierarchy {
     bool denseOk = false;
     bool symbolicValid = false, numericValid = false, symbolicFailed = false;
     int nu = 2, nuCoarse = 2;
+    int preFine = -1, postFine = -1, preCoarse = -1, postCoarse = -1;  // -1: nu / nuCoarse (PFEM_MG_PRE|POST|PREC|POSTC)
+    bool f32v = false;         // the cycle runs on fp32 vectors (flexible GMRES outside); level buffers are reinterpreted
+    DevBuf<float> inF, outF;   // fp32 copies of the cycle's right-hand side and result
     int wFrom = -1;  // W-cycle: the coarse correction of every level >= wFrom is computed twice (-1: V-cycle)
     double fixedOmega = 0.0;  // > 0: the caller's damping on every level; 0: tuned per level (tuneDamping)
     double over = 1.5;
@@ -559,45 +563,47 @@ __global__ void __launch_bounds__(1024) k_dense_invert(int n, int BS, const int*
     for (int t = tid; t < nD * nD; t += nt) Dinv[t] = a[t];
 }
 // x = A^-1 b: warp per row
-__global__ void __launch_bounds__(1024) k_dense_apply(int nD, const double* __restrict__ Dinv, const double* __restrict__ b,
-                                                      double* __restrict__ x) {
+template <typename VT>
+__global__ void __launch_bounds__(1024) k_dense_apply(int nD, const double* __restrict__ Dinv, const VT* __restrict__ b,
+                                                      VT* __restrict__ x) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (int r = w; r < nD; r += nw) {
         double s = 0;
-        for (int c = lane; c < nD; c += 32) s += Dinv[(size_t)r * nD + c] * b[c];
+        for (int c = lane; c < nD; c += 32) s += Dinv[(size_t)r * nD + c] * (double)b[c];
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) x[r] = s;
+        if (lane == 0) x[r] = (VT)s;
     }
 }
 
 // ---- cycle ------------------------------------------------------------------------------------------------------------
 // first sweep from a zero guess: x = Dw b
-template <int BS>
-__global__ void k_mg_jacobi0(int nDof, const double* __restrict__ Dw, const double* __restrict__ b, double* __restrict__ x) {
+template <int BS, typename VT>
+__global__ void k_mg_jacobi0(int nDof, const VT* __restrict__ Dw, const VT* __restrict__ b, VT* __restrict__ x) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nDof) return;
     const int base = (i / BS) * BS;
-    double a = 0;
+    VT a = 0;
 #pragma unroll
     for (int c = 0; c < BS; ++c) a += Dw[(size_t)i * BS + c] * b[base + c];
     x[i] = a;
 }
-template <int BS>
+template <int BS, typename VT>
 __global__ void k_mg_restrict(int nc, const int* __restrict__ aggPtr, const int* __restrict__ aggNodes,
-                              const double* __restrict__ r, double* __restrict__ bc) {
+                              const VT* __restrict__ r, VT* __restrict__ bc) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nc * BS) return;
     const int I = t / BS, d = t % BS;
-    double s = 0;
+    VT s = 0;
     for (int m = aggPtr[I]; m < aggPtr[I + 1]; ++m) s += r[(size_t)aggNodes[m] * BS + d];
     bc[t] = s;
 }
-template <int BS>
-__global__ void k_mg_prolong(int nDof, const int* __restrict__ agg, const double* __restrict__ xc, double over,
-                             double* __restrict__ x) {
+template <int BS, typename VT>
+__global__ void k_mg_prolong(int nDof, const int* __restrict__ agg, const VT* __restrict__ xc, double over,
+                             VT* __restrict__ x, bool set) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nDof) return;
-    x[i] += over * xc[(size_t)agg[i / BS] * BS + (i % BS)];
+    const VT e = (VT)over * xc[(size_t)agg[i / BS] * BS + (i % BS)];
+    x[i] = set ? e : x[i] + e;
 }
 
 // deterministic start vector of the power iteration (all frequencies present) and ordered 2-norm, single CTA
@@ -624,9 +630,12 @@ __global__ void __launch_bounds__(1024) k_mg_norm2(int nDof, const double* __res
     }
 }
 
-__global__ void k_mg_add(int n, const double* __restrict__ a, double* __restrict__ x) {
+template <typename VT> __global__ void k_mg_add(int n, const VT* __restrict__ a, VT* __restrict__ x) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] += a[i];
+}
+__global__ void k_to_double(size_t n, const float* __restrict__ f, double* __restrict__ a) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] = (double)f[i];
 }
 __global__ void k_to_float(size_t n, const double* __restrict__ a, float* __restrict__ f) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f[i] = (float)a[i];
@@ -636,17 +645,36 @@ bool mgFp32() {
     return v;
 }
 
-template <int EPI>
-void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const double* x, double* y, const double* b) {
+template <typename VT> inline const VT* levelDw(const MgLevel& L);
+template <> inline const double* levelDw<double>(const MgLevel& L) { return L.Dw.p; }
+template <> inline const float* levelDw<float>(const MgLevel& L) { return L.DwF.p; }
+template <typename VT> inline VT* vecOf(DevBuf<double>& b) { return reinterpret_cast<VT*>(b.p); }
+
+template <int EPI, typename VT>
+void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const VT* x, VT* y, const VT* b) {
     // partitioned mesh: the sweeps of a distributed level act on the GLOBAL matrix of that level (ghost entries of the
     // iterate follow their owners); replicated levels need no exchange
-    if (L.distributed && c->nRanks > 1) commHaloPlan(c, *L.plan, const_cast<double*>(x), nullptr, BS);
-    SpmvEpi e;
+    if (L.distributed && c->nRanks > 1) commHaloPlanT<VT>(c, *L.plan, const_cast<VT*>(x), nullptr, BS);
+    SpmvEpiT<VT> e;
     e.b = b;
-    e.Dw = L.Dw.p;
+    e.Dw = levelDw<VT>(L);
     const int grid = std::max(1, std::min(c->smCount * 8, divUp(L.n, 8)));
     std::unique_ptr<PhaseScope> ph;
     if (c->profileDetail && L.Aval == c->Aval.p) ph.reset(new PhaseScope(c, EPI == EPI_SMOOTH ? "MG smooth L0" : "MG resid L0"));
+    if constexpr (sizeof(VT) == 4) {  // fp32 vectors: always with the fp32 matrix copy
+        PFEM_REQUIRE(L.Af.p && L.DwF.p, PFEM_ERR_STATE, "multigrid: fp32 level data missing");
+        if (BS == 4 && L.maxNb > 16)
+            k_spmv<4, 2, EPI, float, 4, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1,
+                                                                          -1, nullptr, nullptr, e);
+        else if (BS == 4)
+            k_spmv<4, 4, EPI, float, 2, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1,
+                                                                          -1, nullptr, nullptr, e);
+        else
+            k_spmv<3, 3, EPI, float, 2, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1,
+                                                                          -1, nullptr, nullptr, e);
+        LAUNCH_CHECK(c);
+        return;
+    } else {
     static const bool minb4 = !(getenv("PFEM_MG_MINB4") && atoi(getenv("PFEM_MG_MINB4")) == 0);  // 64 registers, 32 warps/SM
     // cp.async ring variant: measured equal to the 64-register kernel (126 vs 118 us smoothing sweep at 2 M tets): the sweep is
     // bound by instruction issue and gather latency (ncu: 47 % issue active, 67 M instructions, DRAM 3.1 TB/s), not by the
@@ -689,75 +717,108 @@ void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const double* x, double* 
         k_spmv<3, 3, EPI><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, x, y, nullptr, nullptr, 0, -1, -1, nullptr,
                                                      nullptr, e);
     LAUNCH_CHECK(c);
+    }
 }
 
-void cycle(pfem_ctx* c, MgHierarchy& H, int l, const double* b, double* out) {
+template <typename VT>
+void cycle(pfem_ctx* c, MgHierarchy& H, int l, const VT* b, VT* out) {
     const int BS = c->dim + 1;
     MgLevel& L = *H.lev[l];
     const int nDof = L.n * BS;
     const bool last = l + 1 == (int)H.lev.size();
     if (last && H.denseOk) {
-        k_dense_apply<<<1, 1024, 0, c->stream>>>(H.nD, H.dense.p, b, out);
+        k_dense_apply<VT><<<1, 1024, 0, c->stream>>>(H.nD, H.dense.p, b, out);
         LAUNCH_CHECK(c);
         return;
     }
-    double* cur = L.xa.p;
-    double* oth = L.xb.p;
-    auto jac0 = [&](double* dst) {
-        if (BS == 4) k_mg_jacobi0<4><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.Dw.p, b, dst);
-        else k_mg_jacobi0<3><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.Dw.p, b, dst);
+    VT* cur = vecOf<VT>(L.xa);
+    VT* oth = vecOf<VT>(L.xb);
+    auto jac0 = [&](VT* dst) {
+        if (BS == 4) k_mg_jacobi0<4, VT><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, levelDw<VT>(L), b, dst);
+        else k_mg_jacobi0<3, VT><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, levelDw<VT>(L), b, dst);
         LAUNCH_CHECK(c);
     };
     const int nu = l == 0 ? H.nu : H.nuCoarse;  // coarse sweeps are cheap: the fine level may run fewer than the rest
-    const int nPre = last ? 4 * nu : nu, nPost = last ? 0 : nu;
-    jac0(cur);
+    int nPre = last ? 4 * nu : nu, nPost = last ? 0 : nu;
+    if (!last) {  // asymmetric cycles: without pre-smoothing the residual is b itself (no matrix pass before the restriction)
+        const int pre = l == 0 ? H.preFine : H.preCoarse, post = l == 0 ? H.postFine : H.postCoarse;
+        if (pre >= 0) nPre = pre;
+        if (post >= 0) nPost = post;
+        if (nPre + nPost == 0) nPost = 1;
+    }
+    if (nPre > 0) jac0(cur);
     for (int k = 1; k < nPre; ++k) {
-        double* dst = (last && k == nPre - 1) ? out : oth;
-        launchSpmv<EPI_SMOOTH>(c, L, BS, cur, dst, b);
+        VT* dst = (last && k == nPre - 1) ? out : oth;
+        launchSpmv<EPI_SMOOTH, VT>(c, L, BS, cur, dst, b);
         std::swap(cur, oth);
         if (dst == out) cur = out;
     }
     if (last) {  // coarsest level without a dense inverse: smoothing only
-        if (cur != out) CUDA_CHECK(cudaMemcpyAsync(out, cur, (size_t)nDof * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        if (cur != out) CUDA_CHECK(cudaMemcpyAsync(out, cur, (size_t)nDof * sizeof(VT), cudaMemcpyDeviceToDevice, c->stream));
         return;
     }
     MgLevel& C = *H.lev[l + 1];
-    launchSpmv<EPI_RESID>(c, L, BS, cur, L.t.p, b);
+    const VT* resid = b;
+    if (nPre > 0) {
+        launchSpmv<EPI_RESID, VT>(c, L, BS, cur, vecOf<VT>(L.t), b);
+        resid = vecOf<VT>(L.t);
+    }
     {
         // my aggregates: all coarse rows, or rows [rowOff, rowOff + ncLocal) of a replicated next level (then all-gathered)
         const int ncL = L.ncLocal;
-        double* dstB = C.b.p + (size_t)L.rowOff * BS;
+        VT* Cb = vecOf<VT>(C.b);
+        VT* dstB = Cb + (size_t)L.rowOff * BS;
         if (ncL > 0) {
-            if (BS == 4) k_mg_restrict<4><<<divUp(ncL * BS, 256), 256, 0, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, L.t.p, dstB);
-            else k_mg_restrict<3><<<divUp(ncL * BS, 256), 256, 0, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, L.t.p, dstB);
+            if (BS == 4) k_mg_restrict<4, VT><<<divUp(ncL * BS, 256), 256, 0, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, resid, dstB);
+            else k_mg_restrict<3, VT><<<divUp(ncL * BS, 256), 256, 0, c->stream>>>(ncL, L.aggPtr.p, L.aggNodes.p, resid, dstB);
             LAUNCH_CHECK(c);
         }
         if (L.nextReplicated) {
             std::vector<int64_t> cnt(L.rowCounts), dsp(L.rowDispls);
-            for (auto& v : cnt) v *= BS;
-            for (auto& v : dsp) v *= BS;
-            commAllGatherV(c, dstB, C.b.p, cnt, dsp);
+            for (auto& v : cnt) v *= BS * (int64_t)sizeof(VT);
+            for (auto& v : dsp) v *= BS * (int64_t)sizeof(VT);
+            commAllGatherBytes(c, dstB, Cb, cnt, dsp);
         }
     }
-    cycle(c, H, l + 1, C.b.p, C.xo.p);
+    cycle<VT>(c, H, l + 1, vecOf<VT>(C.b), vecOf<VT>(C.xo));
     // W-cycle: a second visit of the coarse level on the residual of the first (unsmoothed aggregation loses its mesh
     // independence with V-cycles; the coarse levels cost a few percent of the cycle).  Not when that level is solved exactly.
     const bool coarseExact = (l + 2 == (int)H.lev.size()) && H.denseOk;
     if (H.wFrom >= 0 && l >= H.wFrom && !coarseExact) {
-        launchSpmv<EPI_RESID>(c, C, BS, C.xo.p, C.w.p, C.b.p);
-        cycle(c, H, l + 1, C.w.p, C.xo2.p);
+        launchSpmv<EPI_RESID, VT>(c, C, BS, vecOf<VT>(C.xo), vecOf<VT>(C.w), vecOf<VT>(C.b));
+        cycle<VT>(c, H, l + 1, vecOf<VT>(C.w), vecOf<VT>(C.xo2));
         const int nc = C.n * BS;
-        k_mg_add<<<divUp(nc, 256), 256, 0, c->stream>>>(nc, C.xo2.p, C.xo.p);
+        k_mg_add<VT><<<divUp(nc, 256), 256, 0, c->stream>>>(nc, vecOf<VT>(C.xo2), vecOf<VT>(C.xo));
         LAUNCH_CHECK(c);
     }
-    if (BS == 4) k_mg_prolong<4><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, C.xo.p, H.over, cur);
-    else k_mg_prolong<3><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, C.xo.p, H.over, cur);
+    VT* corrected = nPost == 0 ? out : cur;  // no post-smoothing: the corrected iterate is the result
+    if (nPost == 0 && nPre > 0) CUDA_CHECK(cudaMemcpyAsync(out, cur, (size_t)nDof * sizeof(VT), cudaMemcpyDeviceToDevice, c->stream));
+    if (BS == 4) k_mg_prolong<4, VT><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, vecOf<VT>(C.xo), H.over, corrected, nPre == 0);
+    else k_mg_prolong<3, VT><<<divUp(nDof, 256), 256, 0, c->stream>>>(nDof, L.agg.p, vecOf<VT>(C.xo), H.over, corrected, nPre == 0);
     LAUNCH_CHECK(c);
     for (int k = 1; k <= nPost; ++k) {
-        double* dst = (k == nPost) ? out : oth;
-        launchSpmv<EPI_SMOOTH>(c, L, BS, cur, dst, b);
+        VT* dst = (k == nPost) ? out : oth;
+        launchSpmv<EPI_SMOOTH, VT>(c, L, BS, cur, dst, b);
         std::swap(cur, oth);
     }
+}
+
+// one cycle from the fp64 right-hand side in lev[0]->b to the fp64 vector `out`
+void runCycle(pfem_ctx* c, MgHierarchy& H, double* out) {
+    MgLevel& L0 = *H.lev[0];
+    if (!H.f32v) {
+        cycle<double>(c, H, 0, L0.b.p, out);
+        return;
+    }
+    const size_t nDof = (size_t)L0.n * (c->dim + 1), nAll = (size_t)L0.nVec * (c->dim + 1);
+    H.inF.reserve(nAll + 8);
+    H.outF.reserve(nAll + 8);
+    const int grid = std::max(1, std::min(c->smCount * 8, divUp((int64_t)nDof, 256)));
+    k_to_float<<<grid, 256, 0, c->stream>>>(nDof, L0.b.p, H.inF.p);
+    LAUNCH_CHECK(c);
+    cycle<float>(c, H, 0, H.inF.p, H.outF.p);
+    k_to_double<<<grid, 256, 0, c->stream>>>(nDof, H.outF.p, out);
+    LAUNCH_CHECK(c);
 }
 
 // total size below which the next level is replicated on every rank (read at every symbolic build: tests change it)
@@ -1156,7 +1217,7 @@ void tuneDamping(pfem_ctx* c, MgHierarchy& H, MgLevel& L, int BS) {
         double nrm[32];
         for (int it = 0; it <= nIt; ++it) {
             if (it > 0) {
-                launchSpmv<EPI_SMOOTH>(c, L, BS, cur, oth, L.t.p);
+                launchSpmv<EPI_SMOOTH, double>(c, L, BS, cur, oth, L.t.p);
                 std::swap(cur, oth);
             }
             k_mg_norm2<<<1, 1024, 0, c->stream>>>(nDof, cur, dNorm);
@@ -1198,6 +1259,12 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
             tuneDamping(c, H, L, BS);  // leaves Dw for the accepted damping
         else
             blockInverse(c, L, BS);
+        if (mgFp32()) {  // fp32 copy of the damped block inverses for the fp32-vector cycle
+            const size_t nd = (size_t)L.n * BB;
+            L.DwF.reserve(nd + 8);
+            k_to_float<<<std::max(1, std::min(c->smCount * 8, divUp((int64_t)nd, 1024))), 256, 0, c->stream>>>(nd, L.Dw.p, L.DwF.p);
+            LAUNCH_CHECK(c);
+        }
         sub.reset();
         if (l + 1 == H.lev.size()) break;
         PhaseScope sub2(c, l == 0 ? "MG Galerkin L0" : "MG Galerkin coarse");
@@ -1272,15 +1339,25 @@ bool mgSetup(pfem_ctx* c) {
     static const int envNu = getenv("PFEM_MG_NU") ? atoi(getenv("PFEM_MG_NU")) : 0;
     static const double envOmega = getenv("PFEM_MG_OMEGA") ? atof(getenv("PFEM_MG_OMEGA")) : 0.0;
     static const double envOver = getenv("PFEM_MG_OVER") ? atof(getenv("PFEM_MG_OVER")) : 0.0;
-    const int nu = c->mgSweeps > 0 ? c->mgSweeps : (envNu > 0 ? envNu : 2);
+    // default sweeps: V(3,3) in 3-D, V(2,2) in 2-D, 3 on the coarse levels (measured under FGMRES at C4 / Delaunay cloud / 2-D
+    // n=700: 3-D 33 -> 23 cycles and 33.9 -> 27.9 ms with the third sweep, 2-D 39 -> 42 cycles and slower)
+    const bool explicitNu = c->mgSweeps > 0 || envNu > 0;
+    const int nu = c->mgSweeps > 0 ? c->mgSweeps : (envNu > 0 ? envNu : (c->dim == 3 ? 3 : 2));
     const double omega = c->mgDamping > 0 ? c->mgDamping : (envOmega > 0 ? envOmega : 0.0);  // 0: tuned per level
     const double over = envOver > 0 ? envOver : 1.5;
     if (omega != H.fixedOmega) H.numericValid = false, H.tuned = false;  // Dw carries the damping
     if (c->asmStamp != H.stamp) H.tuned = false;                          // another dt: the spectrum moved
     static const int envNuC = getenv("PFEM_MG_NUC") ? atoi(getenv("PFEM_MG_NUC")) : 0;
-    H.nu = nu, H.nuCoarse = envNuC > 0 ? envNuC : nu + 1, H.fixedOmega = omega, H.over = over, H.stamp = c->asmStamp;
+    H.nu = nu, H.nuCoarse = envNuC > 0 ? envNuC : (explicitNu ? nu + 1 : 3), H.fixedOmega = omega, H.over = over, H.stamp = c->asmStamp;
     static const int envW = getenv("PFEM_MG_W") ? atoi(getenv("PFEM_MG_W")) : -1;
     H.wFrom = envW;
+    auto envInt = [](const char* name) { return getenv(name) ? atoi(getenv(name)) : -1; };
+    static const int envPre = envInt("PFEM_MG_PRE"), envPost = envInt("PFEM_MG_POST"), envPreC = envInt("PFEM_MG_PREC"),
+                     envPostC = envInt("PFEM_MG_POSTC");
+    H.preFine = envPre, H.postFine = envPost, H.preCoarse = envPreC, H.postCoarse = envPostC;
+    // fp32 vectors inside the cycle: only under the flexible GMRES (the caller says so) and with the fp32 matrix copies
+    static const bool envF32V = !(getenv("PFEM_MG_FP32V") && atoi(getenv("PFEM_MG_FP32V")) == 0);
+    H.f32v = c->mgFlexible && envF32V && mgFp32();
     if (!H.symbolicValid) {
         buildSymbolic(c, H);
         H.tuned = false;
@@ -1302,7 +1379,7 @@ void mgApply(pfem_ctx* c, double* out) {
     static const bool graphNccl = getenv("PFEM_MG_GRAPH_NCCL") && atoi(getenv("PFEM_MG_GRAPH_NCCL")) == 1;
     const bool multiNoGraph = c->nRanks > 1 && (c->local || !graphNccl);
     if (noGraph || H.graphBroken || c->profileDetail || multiNoGraph) {
-        cycle(c, H, 0, H.lev[0]->b.p, out);
+        runCycle(c, H, out);
         return;
     }
     // everything a captured cycle bakes in: buffers that can be reallocated, and the cycle parameters
@@ -1310,10 +1387,13 @@ void mgApply(pfem_ctx* c, double* out) {
     auto mix = [&](unsigned long long v) { sig = (sig ^ v) * 1099511628211ull; };
     mix((unsigned long long)(uintptr_t)H.lev[0]->Aval), mix((unsigned long long)(uintptr_t)H.lev[0]->nbr);
     mix((unsigned long long)(uintptr_t)H.lev[0]->b.p), mix((unsigned long long)H.lev.size()), mix((unsigned long long)H.nu), mix((unsigned long long)H.nuCoarse);
-    mix((unsigned long long)(H.wFrom + 7));
+    mix((unsigned long long)(H.preFine + 1)), mix((unsigned long long)(H.postFine + 1)), mix((unsigned long long)(H.preCoarse + 1)), mix((unsigned long long)(H.postCoarse + 1));
+    mix((unsigned long long)(H.wFrom + 7)), mix(H.f32v ? 2ull : 1ull);
+    if (H.f32v) mix((unsigned long long)(uintptr_t)H.inF.p), mix((unsigned long long)(uintptr_t)H.outF.p);
     mix((unsigned long long)__double_as_longlong_host(H.over)), mix(H.denseOk ? 1ull : 0ull), mix((unsigned long long)H.nD);
     for (auto& L : H.lev) {
         mix((unsigned long long)(uintptr_t)L->Dw.p), mix((unsigned long long)(uintptr_t)L->Af.p), mix((unsigned long long)L->n);
+        mix((unsigned long long)(uintptr_t)L->DwF.p);
         if (L->distributed && L->plan) {  // a captured exchange bakes in the pack buffer and the send list
             L->plan->sendBuf.reserve((size_t)L->plan->nSendTotal * (c->dim + 1) + 8);
             mix((unsigned long long)(uintptr_t)L->plan->sendBuf.p), mix((unsigned long long)(uintptr_t)L->plan->sendIdx.p);
@@ -1339,7 +1419,7 @@ void mgApply(pfem_ctx* c, double* out) {
     bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
     if (ok) {
         try {
-            cycle(c, H, 0, H.lev[0]->b.p, out);
+            runCycle(c, H, out);
         } catch (...) {
             ok = false;
         }
@@ -1353,7 +1433,7 @@ void mgApply(pfem_ctx* c, double* out) {
     if (!ok) {
         cudaGetLastError();
         H.graphBroken = true;
-        cycle(c, H, 0, H.lev[0]->b.p, out);
+        runCycle(c, H, out);
         return;
     }
     MgHierarchy::GraphSlot g;

@@ -98,11 +98,35 @@ __device__ __forceinline__ void loadSlot(const float* __restrict__ Aval, const d
 template <int BS> __device__ __forceinline__ double dotSlot(const RowLoadF<BS>& L) {
     return (double)L.a.x * L.x01.x + (double)L.a.y * L.x01.y + (double)L.a.z * L.x23.x + (double)L.a.w * L.x23.y;
 }
-template <int BS, typename AT> struct RowLoadOf {
+// fp32 matrix AND fp32 vectors (multigrid cycle under the flexible GMRES): one 16-byte load each for the block row and for
+// the node's x, four FFMA, no conversions
+template <int BS> struct RowLoadFF {
+    float4 a, x;
+};
+template <int BS>
+__device__ __forceinline__ void loadSlot(const float* __restrict__ Aval, const float* __restrict__ x, int blk, int col, int r,
+                                         RowLoadFF<BS>& L) {
+    const float* ap = Aval + ((size_t)blk * BS + r) * BS;
+    const float* xp = x + (size_t)col * BS;
+    if constexpr (BS == 4) {
+        L.a = __ldcs(reinterpret_cast<const float4*>(ap));
+        L.x = __ldg(reinterpret_cast<const float4*>(xp));
+    } else {
+        L.a = make_float4(__ldcs(ap), __ldcs(ap + 1), __ldcs(ap + 2), 0.f);
+        L.x = make_float4(__ldg(xp), __ldg(xp + 1), __ldg(xp + 2), 0.f);
+    }
+}
+template <int BS> __device__ __forceinline__ float dotSlot(const RowLoadFF<BS>& L) {
+    return L.a.x * L.x.x + L.a.y * L.x.y + L.a.z * L.x.z + L.a.w * L.x.w;
+}
+template <int BS, typename AT, typename VT = double> struct RowLoadOf {
     using type = RowLoad<BS>;
 };
-template <int BS> struct RowLoadOf<BS, float> {
+template <int BS> struct RowLoadOf<BS, float, double> {
     using type = RowLoadF<BS>;
+};
+template <int BS> struct RowLoadOf<BS, float, float> {
+    using type = RowLoadFF<BS>;
 };
 template <int BS> __device__ __forceinline__ double dotSlot(const RowLoad<BS>& L) {
     return L.a01.x * L.x01.x + L.a01.y * L.x01.y + L.a23.x * L.x23.x + L.a23.y * L.x23.y;
@@ -111,19 +135,21 @@ template <int BS> __device__ __forceinline__ double dotSlot(const RowLoad<BS>& L
 // Epilogue of a block row.  EPI_PLAIN: y = rowScale .* (A x) with the fused dots (BiCGSTAB).  EPI_RESID: y = b - A x.
 // EPI_SMOOTH: damped node-block Jacobi sweep y = x + Dw_i (b_i - (A x)_i), Dw_i = omega A_ii^-1 (multigrid smoother).
 enum { EPI_PLAIN = 0, EPI_RESID = 1, EPI_SMOOTH = 2 };
-struct SpmvEpi {
-    const double* b = nullptr;
-    const double* Dw = nullptr;
+template <typename VT> struct SpmvEpiT {
+    const VT* b = nullptr;
+    const VT* Dw = nullptr;
 };
+using SpmvEpi = SpmvEpiT<double>;
 
 // SL: block slots per lane group held in registers (8 groups x SL blocks per row on the pipelined path; 2 covers the
 // <= 16 blocks of a tetrahedral mesh row, 4 the ~27 of an aggregated level)
-template <int BS, int MINB, int EPI = EPI_PLAIN, typename AT = double, int SL = 2>
+template <int BS, int MINB, int EPI = EPI_PLAIN, typename AT = double, int SL = 2, typename VT = double>
 __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __restrict__ nbrPtr, const int* __restrict__ nbr,
-                                              const AT* __restrict__ Aval, const double* __restrict__ x,
-                                              double* __restrict__ y, const double* __restrict__ w1, double* partial,
+                                              const AT* __restrict__ Aval, const VT* __restrict__ x,
+                                              VT* __restrict__ y, const double* __restrict__ w1, double* partial,
                                               int stride, int slotYW, int slotYY, const double* __restrict__ scal,
-                                              const double* __restrict__ rowScale, const SpmvEpi epi = SpmvEpi()) {
+                                              const double* __restrict__ rowScale, const SpmvEpiT<VT> epi = SpmvEpiT<VT>()) {
+    static_assert(EPI != EPI_PLAIN || sizeof(VT) == 8, "the Krylov SpMV (fused dots, row scale) is fp64");
     const int lane = threadIdx.x & 31, grp = lane >> 2, r = lane & 3;
     const int warpsPerBlock = blockDim.x >> 5;
     const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nw = gridDim.x * warpsPerBlock;
@@ -158,11 +184,11 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             constexpr bool HOIST = MINB <= 3;
             const bool epiLane = grp == 0 && r < BS;
             const size_t oe = (size_t)i * BS + (r < BS ? r : 0);
-            double e0 = 0, e1 = 0;
+            VT e0 = 0, e1 = 0;
             if (HOIST && epiLane) {
                 if constexpr (EPI == EPI_PLAIN) {
-                    if (rowScale) e0 = rowScale[oe];
-                    if (slotYW >= 0) e1 = w1[oe];
+                    if (rowScale) e0 = (VT)rowScale[oe];
+                    if (slotYW >= 0) e1 = (VT)w1[oe];
                 } else if constexpr (EPI == EPI_RESID) {
                     e0 = epi.b[oe];
                 } else {
@@ -171,9 +197,9 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
                     asm volatile("prefetch.global.L1 [%0];" ::"l"(epi.Dw + oe * BS));  // the row of Dw: no registers held
                 }
             }
-            double acc = 0;
+            VT acc = 0;
             if (r < BS) {
-                typename RowLoadOf<BS, AT>::type Ls[SL];
+                typename RowLoadOf<BS, AT, VT>::type Ls[SL];
 #pragma unroll
                 for (int k = 0; k < SL; ++k)
                     if (cs[k] >= 0) loadSlot<BS>(Aval, x, pb0 + grp + 8 * k, cs[k], r, Ls[k]);
@@ -181,7 +207,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
                 for (int k = 0; k < SL; ++k)
                     if (cs[k] >= 0) acc += dotSlot<BS>(Ls[k]);
                 for (int s = grp + 8 * SL; s < nb; s += 8) {  // rows with more than 8*SL blocks (rare)
-                    typename RowLoadOf<BS, AT>::type L;
+                    typename RowLoadOf<BS, AT, VT>::type L;
                     loadSlot<BS>(Aval, x, pb0 + s, __ldg(nbr + pb0 + s), r, L);
                     acc += dotSlot<BS>(L);
                 }
@@ -191,8 +217,8 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
             if (!HOIST && epiLane) {
                 if constexpr (EPI == EPI_PLAIN) {
-                    if (rowScale) e0 = rowScale[oe];
-                    if (slotYW >= 0) e1 = w1[oe];
+                    if (rowScale) e0 = (VT)rowScale[oe];
+                    if (slotYW >= 0) e1 = (VT)w1[oe];
                 } else {
                     e0 = epi.b[oe];
                     if constexpr (EPI == EPI_SMOOTH) e1 = x[oe];
@@ -208,11 +234,11 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             } else if constexpr (EPI == EPI_RESID) {
                 if (epiLane) y[oe] = e0 - acc;
             } else {
-                const double res = epiLane ? e0 - acc : 0.0;
-                double upd = 0;
+                const VT res = epiLane ? e0 - acc : (VT)0;
+                VT upd = 0;
 #pragma unroll
                 for (int cc = 0; cc < BS; ++cc) {
-                    const double rc = __shfl_sync(0xffffffffu, res, cc);
+                    const VT rc = __shfl_sync(0xffffffffu, res, cc);
                     if (epiLane) upd += epi.Dw[oe * BS + cc] * rc;
                 }
                 if (epiLane) y[oe] = e1 + upd;
