@@ -6,7 +6,7 @@
 
 N = 1 -- BASELINE.json configs[3] ("C4"): synthetic Kuhn box n=69 -> 1 971 054 tets, 343 000 nodes, 1 372 000 dof.
   One STEP = one body of the PSPG Picard loop: m_buildAbPSPG + m_applyBCPSPG (assembly) followed by the linear solve
-  (multigrid-preconditioned BiCGSTAB to ||r||/||b|| <= 1e-12, the tolerance the parity tests solve at), inputs resident.
+  (multigrid-preconditioned flexible GMRES to ||r||/||b|| <= 1e-12, the tolerance the parity tests solve at), inputs resident.
   `value`    = assembly Melem/s (device events); `krylov` = the solve of the same steps; `ms_per_step` = both.
   `e2e`      = the WHOLE step through the host-buffer C ABI, per step: pfem_set_topology (pattern build of the remeshed
                connectivity: the incompressible solver remeshes every step, IncompNewton/Solver.cpp:242) + positions,
@@ -611,7 +611,7 @@ def run_single(env, args):
     log(f"  -> assembly {r['asm_ms']:.3f} ms, solve {r['solve_ms']:.1f} ms ({r['iters']} iterations); C5 explicit step")
     n_elems, n_nodes, nnz = r["n_elems"], r["n_nodes"], r["nnz"]
     b_asm, b_spmv = algorithmic_bytes(n_nodes, n_elems, nnz, 3)
-    b_smooth = r["n_blocks"] * (16 * 4 + 4) + 4 * n_nodes * (4 * 8 + 3 * 8)
+    b_smooth = r["n_blocks"] * (16 * 4 + 4) + 4 * n_nodes * (4 * 4 + 3 * 4)   # fp32 A blocks + index; per dof: fp32 Dw row, x, b, y
     smooth_us, spmv_us = 1e3 * r["smooth_ms"], 1e3 * r["spmv_ms"]
     value = n_elems / (r["asm_ms"] * 1e-3) / 1e6
 
@@ -635,20 +635,21 @@ def run_single(env, args):
         "ms_per_step": r["step_ms"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"C4 synthetic 3D Kuhn box n={r['cells']} ({n_elems} tets), incompressible PSPG: assembly+BC then "
-                               f"multigrid-preconditioned BiCGSTAB (rel tol {REL_TOL:g}) per step",
+                               f"multigrid-preconditioned FGMRES(40) (rel tol {REL_TOL:g}) per step",
                    "n_elems": n_elems, "n_nodes": n_nodes, "n_dof": 4 * n_nodes, "nnz": nnz,
                    "l2_policy": "inputs larger than L2 (A = %.0f MB vs 126 MB L2)" % (nnz * 8 / 1e6),
                    "value_definition": "n_elems / mean device time of (assembly prologue + assembly kernel) in the timed steps"},
         "assembly_ms": r["asm_ms"], "step_melem_s": n_elems / (r["step_ms"] * 1e-3) / 1e6,
         "pattern_build_ms": 1e3 * r["topo_s"],
         "krylov": {"solve_ms": r["solve_ms"], "iters": r["iters"], "rel_res": r["rel_res"], "status": r["status"], "rel_tol": REL_TOL,
+                   "solver": "FGMRES(40), one multigrid V(3,3) cycle + one fp64 SpMV per iteration (r1/early r2: BiCGSTAB, two of each)",
                    "ms_per_iter": r["solve_ms"] / max(r["iters"], 1), "spmv_us": spmv_us, "spmv_launches_per_step": r["spmv_calls"],
                    "preconditioner": r["precond"], "mg_levels": r["levels"], "precond_setup_ms": r["pre_setup_ms"],
                    "precond_apply_us": 1e3 * r["pre_apply_ms"], "precond_applies_per_step": r["pre_apply_calls"],
                    "mg_smooth_l0_us": smooth_us, "mg_smooth_l0_launches_per_step": r["smooth_calls"],
                    "mg_smooth_share_of_step": (smooth_us * 1e-3 * r["smooth_calls"]) / r["step_ms"] if r["step_ms"] else None},
-        "roofline": roof("k_spmv<4,float,EPI_SMOOTH> (fine-level multigrid smoothing sweep)", b_smooth, smooth_us * 1e-6, "mg_smooth_c4"),
-        "roofline_spmv": roof("k_spmv<4> (fp64 BiCGSTAB SpMV)", b_spmv, spmv_us * 1e-6, "spmv_c4"),
+        "roofline": roof("k_spmv<4,float,EPI_SMOOTH,float> (fine-level multigrid smoothing sweep, fp32 matrix copy and vectors)", b_smooth, smooth_us * 1e-6, "mg_smooth_c4"),
+        "roofline_spmv": roof("k_spmv<4> (fp64 Krylov SpMV)", b_spmv, spmv_us * 1e-6, "spmv_c4"),
         "roofline_assembly": roof("k_pspg_assemble2<3>", b_asm, r["asm_ms"] * 1e-3, "pspg_assemble_c4",
                                   {"fp64_gflops": FLOPS_PER_ELEM_ASM * n_elems / (r["asm_ms"] * 1e-3) / 1e9,
                                    "fp64_flops_per_element": FLOPS_PER_ELEM_ASM,
@@ -797,7 +798,7 @@ def run_multi(env, args):
                                "pspg_iters_sharded": parity_pspg["iters_sharded"], "pspg_iters_1gpu": parity_pspg["iters_1gpu"],
                                "pspg_workload": f"C4 n={args.cells} sharded over {world} GPUs vs one GPU, rel tol {REL_TOL:g}"},
             "pspg_weak": {"workload": f"Kuhn box n={cells_weak} ({pw['n_elems']} tets, {pw['n_elems'] / world / 1e6:.2f} M per GPU), assembly + "
-                                      f"multigrid-BiCGSTAB (rel tol {REL_TOL:g})",
+                                      f"multigrid-FGMRES (rel tol {REL_TOL:g})",
                           "assembly_melem_s": pw["n_elems"] / (pw["asm_ms"] * 1e-3) / 1e6, "assembly_ms": pw["asm_ms"],
                           "step_ms": pw["step_ms"], "solve_ms": pw["solve_ms"], "iters": pw["iters"], "status": pw["status"],
                           "rel_res": pw["rel_res"], "mg_levels": pw["levels"], "halo_us": 1e3 * pw["halo_ms"],

@@ -403,49 +403,48 @@ __global__ void __launch_bounds__(RB_THREADS) k_gm_first(int n, const double* __
         mgRhs[i] = vi / dinv[i];
     }
 }
-// partial dots (v_{i0+j}, w), j < nv <= 8, into bank slots i0 + j; the last chunk also stores (w, w) in slot `slotWW`
+// partial dots (v_{i0+j}, w), j < nv <= 8, into bank slots i0 + j (two consecutive entries per thread: 16-byte loads; the
+// vectors are padded to a multiple of 8 entries and the pad of w is never read: n2 = n / 2 pairs + a scalar tail)
 __global__ void __launch_bounds__(RB_THREADS) k_gm_dots(int n, const double* __restrict__ V, size_t ldv, int i0, int nv,
-                                                        const double* __restrict__ w, double* bank, int stride, int slotWW) {
+                                                        const double* __restrict__ w, double* bank, int stride) {
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double ww = 0;
     const double* Vb = V + (size_t)i0 * ldv;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const double wi = w[i];
-        ww += wi * wi;
+    const int n2 = n >> 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        const double2 wi = reinterpret_cast<const double2*>(w)[i];
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-            if (j < nv) acc[j] += Vb[(size_t)j * ldv + i] * wi;
+            if (j < nv) {
+                const double2 vj = reinterpret_cast<const double2*>(Vb + (size_t)j * ldv)[i];
+                acc[j] += vj.x * wi.x + vj.y * wi.y;
+            }
     }
-    __shared__ double sh[9][RB_THREADS / 32];
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (j < nv) acc[j] += Vb[(size_t)j * ldv + n - 1] * w[n - 1];
+    }
+    __shared__ double sh[8][RB_THREADS / 32];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const double t = warpSum(acc[j]);
         if (lane == 0) sh[j][wp] = t;
     }
-    {
-        const double t = warpSum(ww);
-        if (lane == 0) sh[8][wp] = t;
-    }
     __syncthreads();
     if (wp == 0) {
 #pragma unroll
-        for (int j = 0; j < 9; ++j) {
+        for (int j = 0; j < 8; ++j) {
             double t = lane < nw ? sh[j][lane] : 0.0;
             t = warpSum(t);
-            if (lane == 0) {
-                if (j < 8 && j < nv) bank[(size_t)(i0 + j) * stride + blockIdx.x] = t;
-                if (j == 8 && slotWW >= 0) bank[(size_t)slotWW * stride + blockIdx.x] = t;
-            }
+            if (lane == 0 && j < nv) bank[(size_t)(i0 + j) * stride + blockIdx.x] = t;
         }
     }
 }
-// h_i = sum of bank slot i (fixed order), i < count
-__global__ void __launch_bounds__(RB_THREADS) k_gm_reduce(const double* bank, int stride, int nPart, int slot0, int count, double* out) {
-    for (int i = 0; i < count; ++i) {
-        const double t = bankSum(bank, stride, slot0 + i, nPart);
-        if (threadIdx.x == 0) out[i] = t;
-    }
+// h_i = sum of bank slot i (fixed order): one block per slot
+__global__ void __launch_bounds__(RB_THREADS) k_gm_reduce(const double* bank, int stride, int nPart, int slot0, double* out) {
+    const double t = bankSum(bank, stride, slot0 + blockIdx.x, nPart);
+    if (threadIdx.x == 0) out[blockIdx.x] = t;
 }
 // w -= sum_{i<=k} h_i v_i ; partial ||w||^2 into bank slot `slotN`
 __global__ void __launch_bounds__(RB_THREADS) k_gm_update(int n, const double* __restrict__ V, size_t ldv, int nv,
@@ -455,11 +454,22 @@ __global__ void __launch_bounds__(RB_THREADS) k_gm_update(int n, const double* _
     if (threadIdx.x < nv) hs[threadIdx.x] = h[threadIdx.x];
     __syncthreads();
     double nn = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        double a = w[i];
-#pragma unroll 4
-        for (int j = 0; j < nv; ++j) a -= hs[j] * V[(size_t)j * ldv + i];
-        w[i] = a;
+    const int n2 = n >> 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += gridDim.x * blockDim.x) {
+        double2 a = reinterpret_cast<double2*>(w)[i];
+#pragma unroll 8
+        for (int j = 0; j < nv; ++j) {
+            const double2 vj = reinterpret_cast<const double2*>(V + (size_t)j * ldv)[i];
+            a.x -= hs[j] * vj.x;
+            a.y -= hs[j] * vj.y;
+        }
+        reinterpret_cast<double2*>(w)[i] = a;
+        nn += a.x * a.x + a.y * a.y;
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        double a = w[n - 1];
+        for (int j = 0; j < nv; ++j) a -= hs[j] * V[(size_t)j * ldv + n - 1];
+        w[n - 1] = a;
         nn += a * a;
     }
     double vv[1] = {nn};
@@ -720,9 +730,9 @@ GmresOutcome gmresSolve(pfem_ctx* c, const KrylovDims& k, double relTol, int max
     const size_t ldv = ((size_t)k.n + 7) & ~(size_t)7, ldz = ((size_t)k.nAll + 7) & ~(size_t)7;
     c->gmV.reserve(ldv * (m + 1) + 8);
     c->gmZ.reserve(ldz * m + 8);
-    c->gmBank.reserve((size_t)(m + 3) * k.stride);
+    c->gmBank.reserve((size_t)(m + 2) * k.stride);
     c->gmS.reserve(L.count() + 8);
-    const int slotWW = m + 1, slotN = m + 2;
+    const int slotN = m + 1;
     double* gs = c->gmS.p;
     double* w = c->kt.p;
     double rrFirst = -1.0;
@@ -743,19 +753,17 @@ GmresOutcome gmresSolve(pfem_ctx* c, const KrylovDims& k, double relTol, int max
         int j = 0;  // basis vectors built in this cycle
         bool done = false;
         while (!done && j < m && out.iters + j < maxIter) {
-            mgApply(c, c->kph.p);
-            spmv(c, k, c->kph.p, w, nullptr, -1, -1, false, c->dinv.p);  // w = S A z (ghost entries of z refreshed first)
-            CUDA_CHECK(cudaMemcpyAsync(c->gmZ.p + (size_t)j * ldz, c->kph.p, (size_t)k.nAll * sizeof(double), cudaMemcpyDeviceToDevice,
-                                       c->stream));
+            double* zj = c->gmZ.p + (size_t)j * ldz;
+            mgApply(c, zj);                                             // the cycle's result lands in z_j (converted from fp32)
+            spmv(c, k, zj, w, nullptr, -1, -1, false, c->dinv.p);       // w = S A z (ghost entries of z refreshed first)
             {
                 PhaseScope ph(c, "GMRES orthogonalisation");
                 for (int i0 = 0; i0 <= j; i0 += 8) {
                     const int nv = std::min(8, j + 1 - i0);
-                    k_gm_dots<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->gmV.p, ldv, i0, nv, w, c->gmBank.p, k.stride,
-                                                                     i0 + 8 > j ? slotWW : -1);
+                    k_gm_dots<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->gmV.p, ldv, i0, nv, w, c->gmBank.p, k.stride);
                     LAUNCH_CHECK(c);
                 }
-                k_gm_reduce<<<1, RB_THREADS, 0, c->stream>>>(c->gmBank.p, k.stride, k.vecGrid, 0, j + 1, gs + L.h());
+                k_gm_reduce<<<j + 1, RB_THREADS, 0, c->stream>>>(c->gmBank.p, k.stride, k.vecGrid, 0, gs + L.h());
                 LAUNCH_CHECK(c);
                 if (k.multi) commAllReduceSum(c, gs + L.h(), j + 1);
                 k_gm_update<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->gmV.p, ldv, j + 1, gs + L.h(), w, c->gmBank.p, k.stride,

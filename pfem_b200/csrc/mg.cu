@@ -803,20 +803,25 @@ void cycle(pfem_ctx* c, MgHierarchy& H, int l, const VT* b, VT* out) {
     }
 }
 
-// one cycle from the fp64 right-hand side in lev[0]->b to the fp64 vector `out`
+// one cycle from the fp64 right-hand side in lev[0]->b.  fp64 vectors: the result is written to `out`.  fp32 vectors: the
+// result stays in H.outF and mgApply converts it into the caller's vector OUTSIDE the captured graph, so that one graph serves
+// every output vector (FGMRES hands a different z_j per iteration).
 void runCycle(pfem_ctx* c, MgHierarchy& H, double* out) {
     MgLevel& L0 = *H.lev[0];
     if (!H.f32v) {
         cycle<double>(c, H, 0, L0.b.p, out);
         return;
     }
-    const size_t nDof = (size_t)L0.n * (c->dim + 1), nAll = (size_t)L0.nVec * (c->dim + 1);
-    H.inF.reserve(nAll + 8);
-    H.outF.reserve(nAll + 8);
+    const size_t nDof = (size_t)L0.n * (c->dim + 1);
     const int grid = std::max(1, std::min(c->smCount * 8, divUp((int64_t)nDof, 256)));
     k_to_float<<<grid, 256, 0, c->stream>>>(nDof, L0.b.p, H.inF.p);
     LAUNCH_CHECK(c);
     cycle<float>(c, H, 0, H.inF.p, H.outF.p);
+}
+void convertResult(pfem_ctx* c, MgHierarchy& H, double* out) {
+    if (!H.f32v) return;
+    const size_t nDof = (size_t)H.lev[0]->n * (c->dim + 1);
+    const int grid = std::max(1, std::min(c->smCount * 8, divUp((int64_t)nDof, 256)));
     k_to_double<<<grid, 256, 0, c->stream>>>(nDof, H.outF.p, out);
     LAUNCH_CHECK(c);
 }
@@ -1378,8 +1383,16 @@ void mgApply(pfem_ctx* c, double* out) {
     // ranks capture two graphs each (one per output vector) whose grouped send/recv lists differ per rank; kept opt-in only.
     static const bool graphNccl = getenv("PFEM_MG_GRAPH_NCCL") && atoi(getenv("PFEM_MG_GRAPH_NCCL")) == 1;
     const bool multiNoGraph = c->nRanks > 1 && (c->local || !graphNccl);
+    if (H.f32v) {  // reserved here, not inside a capture
+        const size_t nAll = (size_t)H.lev[0]->nVec * (c->dim + 1);
+        H.inF.reserve(nAll + 8);
+        H.outF.reserve(nAll + 8);
+    }
+    double* const userOut = out;
+    if (H.f32v) out = nullptr;  // the captured part ends in H.outF: one graph for every output vector
     if (noGraph || H.graphBroken || c->profileDetail || multiNoGraph) {
         runCycle(c, H, out);
+        convertResult(c, H, userOut);
         return;
     }
     // everything a captured cycle bakes in: buffers that can be reallocated, and the cycle parameters
@@ -1403,6 +1416,7 @@ void mgApply(pfem_ctx* c, double* out) {
         if (g.out == out && g.sig == sig) {
             CUDA_CHECK(cudaGraphLaunch(g.exec, c->stream));
             c->launches += g.launches;
+            convertResult(c, H, userOut);
             return;
         }
     for (size_t k = 0; k < H.graphs.size();)  // stale capture for this output vector
@@ -1434,6 +1448,7 @@ void mgApply(pfem_ctx* c, double* out) {
         cudaGetLastError();
         H.graphBroken = true;
         runCycle(c, H, out);
+        convertResult(c, H, userOut);
         return;
     }
     MgHierarchy::GraphSlot g;
@@ -1441,4 +1456,5 @@ void mgApply(pfem_ctx* c, double* out) {
     H.graphs.push_back(g);
     CUDA_CHECK(cudaGraphLaunch(exec, c->stream));
     c->launches += per;
+    convertResult(c, H, userOut);
 }

@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             const int nb = pb1 - pb0;
             // epilogue operands are fetched with the row, not after its reduction (one more exposed latency per row otherwise)
             // (only where the register budget allows it: at 64 registers the hoisted operands spill and cost more than they save)
-            constexpr bool HOIST = MINB <= 3;
+            constexpr bool HOIST = MINB <= 3 || sizeof(VT) == 4;  // fp32 vectors: 56 registers, room for the hoisted operands
             const bool epiLane = grp == 0 && r < BS;
             const size_t oe = (size_t)i * BS + (r < BS ? r : 0);
             VT e0 = 0, e1 = 0;
