@@ -150,42 +150,53 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
                                               int stride, int slotYW, int slotYY, const double* __restrict__ scal,
                                               const double* __restrict__ rowScale, const SpmvEpiT<VT> epi = SpmvEpiT<VT>()) {
     static_assert(EPI != EPI_PLAIN || sizeof(VT) == 8, "the Krylov SpMV (fused dots, row scale) is fp64");
+    // Pipeline (round 2): the loads of row i+1 (A rows, x gathers) are issued right after the products of row i, BEFORE its
+    // shuffle reduction and epilogue, into the registers row i has just released -- the reduction / epilogue latency
+    // (ncu: 14 % of the stall samples on the late Dw loads, 7 dependent shuffles) hides under the next row's memory latency.
+    // For that the column indices run two rows ahead and the row pointers three.
+    using Row = typename RowLoadOf<BS, AT, VT>::type;
     const int lane = threadIdx.x & 31, grp = lane >> 2, r = lane & 3;
     const int warpsPerBlock = blockDim.x >> 5;
     const int gw = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5), nw = gridDim.x * warpsPerBlock;
     double accYW = 0, accYY = 0;
     const bool frozen = scal && scal[SC_DONE] != 0.0;
-    if (!frozen) {
+    if (!frozen && gw < nNodes) {
         int i = gw;
-        int pb0 = 0, pb1 = 0, qb0 = 0, qb1 = 0;  // row i / row i+nw block ranges
-        if (i < nNodes) {
-            pb0 = __ldg(nbrPtr + i);
-            pb1 = __ldg(nbrPtr + i + 1);
-        }
+        int pb0, pb1, qb0 = 0, qb1 = 0, rb0 = 0, rb1 = 0;  // block ranges of rows i, i+nw, i+2nw
+        pb0 = __ldg(nbrPtr + i);
+        pb1 = __ldg(nbrPtr + i + 1);
         if (i + nw < nNodes) {
             qb0 = __ldg(nbrPtr + i + nw);
             qb1 = __ldg(nbrPtr + i + nw + 1);
         }
-        int cs[SL];
+        if (i + 2 * nw < nNodes) {
+            rb0 = __ldg(nbrPtr + i + 2 * nw);
+            rb1 = __ldg(nbrPtr + i + 2 * nw + 1);
+        }
+        Row Ls[SL];
+        if (r < BS) {
 #pragma unroll
-        for (int k = 0; k < SL; ++k) cs[k] = (grp + 8 * k < pb1 - pb0) ? __ldg(nbr + pb0 + grp + 8 * k) : -1;
+            for (int k = 0; k < SL; ++k)
+                if (grp + 8 * k < pb1 - pb0) loadSlot<BS>(Aval, x, pb0 + grp + 8 * k, __ldg(nbr + pb0 + grp + 8 * k), r, Ls[k]);
+        }
+        int cs[SL];  // column indices of row i+nw
+#pragma unroll
+        for (int k = 0; k < SL; ++k) cs[k] = (grp + 8 * k < qb1 - qb0) ? __ldg(nbr + qb0 + grp + 8 * k) : -1;
         for (; i < nNodes; i += nw) {
             int fb0 = 0, fb1 = 0;
-            if (i + 2 * nw < nNodes) {
-                fb0 = __ldg(nbrPtr + i + 2 * nw);
-                fb1 = __ldg(nbrPtr + i + 2 * nw + 1);
+            if (i + 3 * nw < nNodes) {
+                fb0 = __ldg(nbrPtr + i + 3 * nw);
+                fb1 = __ldg(nbrPtr + i + 3 * nw + 1);
             }
-            int ds[SL];
+            int ds[SL];  // column indices of row i+2nw
 #pragma unroll
-            for (int k = 0; k < SL; ++k) ds[k] = (grp + 8 * k < qb1 - qb0) ? __ldg(nbr + qb0 + grp + 8 * k) : -1;
+            for (int k = 0; k < SL; ++k) ds[k] = (grp + 8 * k < rb1 - rb0) ? __ldg(nbr + rb0 + grp + 8 * k) : -1;
             const int nb = pb1 - pb0;
-            // epilogue operands are fetched with the row, not after its reduction (one more exposed latency per row otherwise)
-            // (only where the register budget allows it: at 64 registers the hoisted operands spill and cost more than they save)
-            constexpr bool HOIST = MINB <= 3 || sizeof(VT) == 4;  // fp32 vectors: 56 registers, room for the hoisted operands
+            // epilogue operands are fetched with the row, not after its reduction
             const bool epiLane = grp == 0 && r < BS;
             const size_t oe = (size_t)i * BS + (r < BS ? r : 0);
             VT e0 = 0, e1 = 0;
-            if (HOIST && epiLane) {
+            if (epiLane) {
                 if constexpr (EPI == EPI_PLAIN) {
                     if (rowScale) e0 = (VT)rowScale[oe];
                     if (slotYW >= 0) e1 = (VT)w1[oe];
@@ -199,31 +210,22 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
             }
             VT acc = 0;
             if (r < BS) {
-                typename RowLoadOf<BS, AT, VT>::type Ls[SL];
 #pragma unroll
                 for (int k = 0; k < SL; ++k)
-                    if (cs[k] >= 0) loadSlot<BS>(Aval, x, pb0 + grp + 8 * k, cs[k], r, Ls[k]);
-#pragma unroll
-                for (int k = 0; k < SL; ++k)
-                    if (cs[k] >= 0) acc += dotSlot<BS>(Ls[k]);
+                    if (grp + 8 * k < nb) acc += dotSlot<BS>(Ls[k]);
                 for (int s = grp + 8 * SL; s < nb; s += 8) {  // rows with more than 8*SL blocks (rare)
-                    typename RowLoadOf<BS, AT, VT>::type L;
+                    Row L;
                     loadSlot<BS>(Aval, x, pb0 + s, __ldg(nbr + pb0 + s), r, L);
                     acc += dotSlot<BS>(L);
                 }
+                // next row's operands, into the registers this row has released
+#pragma unroll
+                for (int k = 0; k < SL; ++k)
+                    if (cs[k] >= 0) loadSlot<BS>(Aval, x, qb0 + grp + 8 * k, cs[k], r, Ls[k]);
             }
             acc += __shfl_xor_sync(0xffffffffu, acc, 4);
             acc += __shfl_xor_sync(0xffffffffu, acc, 8);
             acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-            if (!HOIST && epiLane) {
-                if constexpr (EPI == EPI_PLAIN) {
-                    if (rowScale) e0 = (VT)rowScale[oe];
-                    if (slotYW >= 0) e1 = (VT)w1[oe];
-                } else {
-                    e0 = epi.b[oe];
-                    if constexpr (EPI == EPI_SMOOTH) e1 = x[oe];
-                }
-            }
             if constexpr (EPI == EPI_PLAIN) {
                 if (epiLane) {
                     if (rowScale) acc *= e0;  // symmetric Jacobi scaling: y = S A x
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(256, MINB) k_spmv(int nNodes, const int* __res
                 }
                 if (epiLane) y[oe] = e1 + upd;
             }
-            pb0 = qb0, pb1 = qb1, qb0 = fb0, qb1 = fb1;
+            pb0 = qb0, pb1 = qb1, qb0 = rb0, qb1 = rb1, rb0 = fb0, rb1 = fb1;
 #pragma unroll
             for (int k = 0; k < SL; ++k) cs[k] = ds[k];
         }
