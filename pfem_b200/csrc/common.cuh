@@ -318,6 +318,7 @@ void mgInvalidate(pfem_ctx* c, bool symbolic);
 void mgDestroy(pfem_ctx* c);
 bool mgSetup(pfem_ctx* c);
 double* mgRhs(pfem_ctx* c);
+float* mgRhsF(pfem_ctx* c);  // non-null when the cycle runs on fp32 vectors: the caller writes the right-hand side there instead
 int mgLevelCount(pfem_ctx* c);
 void mgApply(pfem_ctx* c, double* out);
 // wc.cu

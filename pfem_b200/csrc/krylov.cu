@@ -12,6 +12,7 @@
 //   * 5 kernels per iteration, the loop runs `checkEvery` iterations between convergence polls; a device-side DONE
 //     flag freezes the state once ||r|| <= tol ||b||.
 // Vectors use the internal dof order node*BS + d.
+#include <cmath>
 #include <cstdlib>
 #include <string>
 
@@ -384,8 +385,9 @@ struct GmLayout {  // offsets into gmS for restart length m
 };
 // v_0 = r / ||r|| ; rhs of the first cycle = S^-1 v_0 ; g = (||r||, 0, ...)
 __global__ void __launch_bounds__(RB_THREADS) k_gm_first(int n, const double* __restrict__ r, const double* __restrict__ dinv,
-                                                         double* __restrict__ v0, double* __restrict__ mgRhs, double* scal,
-                                                         double* gs, GmLayout L, const double* partial, int stride, int nPart) {
+                                                         double* __restrict__ v0, double* __restrict__ mgRhs,
+                                                         float* __restrict__ mgRhsF, double* scal, double* gs, GmLayout L,
+                                                         const double* partial, int stride, int nPart) {
     const double rr = bankSum(partial, stride, PS_RR, nPart);
     const bool conv = rr <= scal[SC_TOL2], bad = !(rr == rr);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -400,7 +402,8 @@ __global__ void __launch_bounds__(RB_THREADS) k_gm_first(int n, const double* __
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double vi = r[i] * inv;
         v0[i] = vi;
-        mgRhs[i] = vi / dinv[i];
+        if (mgRhsF) mgRhsF[i] = (float)(vi / dinv[i]);  // the fp32-vector cycle reads its right-hand side directly
+        else mgRhs[i] = vi / dinv[i];
     }
 }
 // partial dots (v_{i0+j}, w), j < nv <= 8, into bank slots i0 + j (two consecutive entries per thread: 16-byte loads; the
@@ -481,6 +484,7 @@ __global__ void __launch_bounds__(RB_THREADS) k_gm_givens(int k, double* gs, GmL
                                                           int nPart, int slotN, double* scal) {
     const double nn = bankSum(bank, stride, slotN, nPart);
     if (threadIdx.x != 0) return;
+    if (scal[SC_DONE] != 0.0) return;  // iterations launched ahead of a poll: the state of the converged iteration stays
     double* Hc = gs + L.H() + (size_t)k * (L.m + 1);
     const double* h = gs + L.h();
     double* cs = gs + L.cs();
@@ -512,13 +516,15 @@ __global__ void __launch_bounds__(RB_THREADS) k_gm_givens(int k, double* gs, GmL
 // v_{k+1} = w / h_{k+1,k} ; rhs of the next cycle = S^-1 v_{k+1}
 __global__ void __launch_bounds__(RB_THREADS) k_gm_next(int n, const double* __restrict__ w, const double* __restrict__ dinv,
                                                         double* __restrict__ vNext, double* __restrict__ mgRhs,
-                                                        const double* __restrict__ gs, GmLayout L, const double* scal) {
+                                                        float* __restrict__ mgRhsF, const double* __restrict__ gs, GmLayout L,
+                                                        const double* scal) {
     if (scal[SC_DONE] != 0.0) return;
     const double inv = gs[L.scale()];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const double vi = w[i] * inv;
         vNext[i] = vi;
-        mgRhs[i] = vi / dinv[i];
+        if (mgRhsF) mgRhsF[i] = (float)(vi / dinv[i]);
+        else mgRhs[i] = vi / dinv[i];
     }
 }
 // y = R^-1 g (k x k upper triangle left by the rotations)
@@ -716,6 +722,10 @@ int gmresRestart() {
     static const int v = getenv("PFEM_GMRES_M") ? std::max(0, std::min(62, atoi(getenv("PFEM_GMRES_M")))) : 40;
     return v;
 }
+bool gmresPollAhead() {
+    static const bool v = !(getenv("PFEM_GMRES_POLL_EVERY") && atoi(getenv("PFEM_GMRES_POLL_EVERY")) == 1);
+    return v;
+}
 struct GmresOutcome {
     int status = PFEM_OK;
     int iters = 0;
@@ -747,11 +757,17 @@ GmresOutcome gmresSolve(pfem_ctx* c, const KrylovDims& k, double relTol, int max
         globalise(c, k, PS_AUX, -1, k.vecGrid);
         k_init_scal<<<1, RB_THREADS, 0, c->stream>>>(c->scal.p, c->partial.p, k.stride, npVec, relTol, 1, restart == 0);
         LAUNCH_CHECK(c);
-        k_gm_first<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->dinv.p, c->gmV.p, mgB, c->scal.p, gs, L, c->partial.p,
-                                                            k.stride, npVec);
+        float* mgBF = mgRhsF(c);  // non-null: the cycle runs on fp32 vectors and takes its right-hand side in fp32
+        k_gm_first<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, c->kr.p, c->dinv.p, c->gmV.p, mgB, mgBF, c->scal.p, gs, L,
+                                                            c->partial.p, k.stride, npVec);
         LAUNCH_CHECK(c);
         int j = 0;  // basis vectors built in this cycle
         bool done = false;
+        // Polling: the residual estimate after every iteration needs a stream synchronisation (~20 us bubble).  The cycle is
+        // a contraction of at best one order of magnitude per iteration on every mesh measured (typically 0.5), so after a
+        // poll that leaves `orders` orders to go, floor(orders) - 1 iterations are launched without polling; k_gm_givens
+        // freezes the state should the test fire earlier, and k_gm_next stops producing basis vectors.
+        int unpolled = 0;
         while (!done && j < m && out.iters + j < maxIter) {
             double* zj = c->gmZ.p + (size_t)j * ldz;
             mgApply(c, zj);                                             // the cycle's result lands in z_j (converted from fp32)
@@ -778,18 +794,33 @@ GmresOutcome gmresSolve(pfem_ctx* c, const KrylovDims& k, double relTol, int max
                 }
                 k_gm_givens<<<1, RB_THREADS, 0, c->stream>>>(j, gs, L, c->gmBank.p, k.stride, npN, slotN, c->scal.p);
                 LAUNCH_CHECK(c);
-                k_gm_next<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, w, c->dinv.p, c->gmV.p + (size_t)(j + 1) * ldv, mgB, gs, L,
-                                                                 c->scal.p);
+                k_gm_next<<<k.vecGrid, RB_THREADS, 0, c->stream>>>(k.n, w, c->dinv.p, c->gmV.p + (size_t)(j + 1) * ldv, mgB, mgBF, gs,
+                                                                 L, c->scal.p);
                 LAUNCH_CHECK(c);
             }
             ++j;
+            if (unpolled > 0 && j < m && out.iters + j < maxIter) {
+                --unpolled;
+                continue;
+            }
             CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
             CUDA_CHECK(cudaStreamSynchronize(c->stream));
             const double rr = c->hScal[SC_RES2];
-            if (c->hScal[SC_DONE] != 0.0 || !(rr == rr)) done = true;
-            else if (mgAuto) {  // GMRES cannot diverge; a cycle that is no preconditioner shows as stagnation
-                if (rrFirst < 0.0) rrFirst = rr;
-                if (out.iters + j >= 50 && rr > 1e-3 * rrFirst) out.giveUp = done = true;
+            if (c->hScal[SC_DONE] != 0.0 || !(rr == rr)) {
+                done = true;
+                if (c->hScal[SC_DONE] != 0.0) j = std::min(j, std::max(1, (int)c->hScal[SC_ITERS]));  // where the test fired
+            } else {
+                if (mgAuto) {  // GMRES cannot diverge; a cycle that is no preconditioner shows as stagnation
+                    if (rrFirst < 0.0) rrFirst = rr;
+                    if (out.iters + j >= 50 && rr > 1e-3 * rrFirst) {
+                        out.giveUp = done = true;
+                        // less than one order in 50 iterations: the iterate is no better a start for the Jacobi fallback than
+                        // the caller's (measured on the 2-D large-dt regime: 5917 iterations from it, 4552 from scratch)
+                        out.diverged = rr > 1e-2 * rrFirst;
+                    }
+                }
+                const double tol2 = c->hScal[SC_TOL2];
+                if (gmresPollAhead() && tol2 > 0.0 && rr > tol2) unpolled = std::max(0, (int)std::floor(0.5 * std::log10(rr / tol2)) - 1);
             }
         }
         if (j > 0) {  // x += Z y

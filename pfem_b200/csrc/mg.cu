@@ -95,6 +95,7 @@ struct MgHierarchy {
     int preFine = -1, postFine = -1, preCoarse = -1, postCoarse = -1;  // -1: nu / nuCoarse (PFEM_MG_PRE|POST|PREC|POSTC)
     bool f32v = false;         // the cycle runs on fp32 vectors (flexible GMRES outside); level buffers are reinterpreted
     DevBuf<float> inF, outF;   // fp32 copies of the cycle's right-hand side and result
+    bool rhsIsF32 = false;     // the caller writes inF itself (mgRhsF): no conversion pass at the head of the cycle
     int wFrom = -1;  // W-cycle: the coarse correction of every level >= wFrom is computed twice (-1: V-cycle)
     double fixedOmega = 0.0;  // > 0: the caller's damping on every level; 0: tuned per level (tuneDamping)
     double over = 1.5;
@@ -664,7 +665,7 @@ void launchSpmv(pfem_ctx* c, const MgLevel& L, int BS, const VT* x, VT* y, const
     if constexpr (sizeof(VT) == 4) {  // fp32 vectors: always with the fp32 matrix copy
         PFEM_REQUIRE(L.Af.p && L.DwF.p, PFEM_ERR_STATE, "multigrid: fp32 level data missing");
         if (BS == 4 && L.maxNb > 16)
-            k_spmv<4, 2, EPI, float, 4, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1,
+            k_spmv<4, 3, EPI, float, 4, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1,
                                                                           -1, nullptr, nullptr, e);
         else if (BS == 4)
             k_spmv<4, 4, EPI, float, 2, float><<<grid, 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Af.p, x, y, nullptr, nullptr, 0, -1,
@@ -814,8 +815,10 @@ void runCycle(pfem_ctx* c, MgHierarchy& H, double* out) {
     }
     const size_t nDof = (size_t)L0.n * (c->dim + 1);
     const int grid = std::max(1, std::min(c->smCount * 8, divUp((int64_t)nDof, 256)));
-    k_to_float<<<grid, 256, 0, c->stream>>>(nDof, L0.b.p, H.inF.p);
-    LAUNCH_CHECK(c);
+    if (!H.rhsIsF32) {
+        k_to_float<<<grid, 256, 0, c->stream>>>(nDof, L0.b.p, H.inF.p);
+        LAUNCH_CHECK(c);
+    }
     cycle<float>(c, H, 0, H.inF.p, H.outF.p);
 }
 void convertResult(pfem_ctx* c, MgHierarchy& H, double* out) {
@@ -1363,6 +1366,7 @@ bool mgSetup(pfem_ctx* c) {
     // fp32 vectors inside the cycle: only under the flexible GMRES (the caller says so) and with the fp32 matrix copies
     static const bool envF32V = !(getenv("PFEM_MG_FP32V") && atoi(getenv("PFEM_MG_FP32V")) == 0);
     H.f32v = c->mgFlexible && envF32V && mgFp32();
+    H.rhsIsF32 = false;  // until the Krylov method asks for the fp32 right-hand side (mgRhsF)
     if (!H.symbolicValid) {
         buildSymbolic(c, H);
         H.tuned = false;
@@ -1372,6 +1376,15 @@ bool mgSetup(pfem_ctx* c) {
     return true;
 }
 double* mgRhs(pfem_ctx* c) { return c->mg->lev[0]->b.p; }
+float* mgRhsF(pfem_ctx* c) {
+    MgHierarchy& H = *c->mg;
+    if (!H.f32v) return nullptr;
+    const size_t nAll = (size_t)H.lev[0]->nVec * (c->dim + 1);
+    H.inF.reserve(nAll + 8);
+    H.outF.reserve(nAll + 8);
+    H.rhsIsF32 = true;
+    return H.inF.p;
+}
 int mgLevelCount(pfem_ctx* c) { return c->mg ? (int)c->mg->lev.size() : 0; }
 // out = V-cycle(rhs held in mgRhs()): an approximation of A^-1 rhs in the physical variables
 void mgApply(pfem_ctx* c, double* out) {
@@ -1401,7 +1414,7 @@ void mgApply(pfem_ctx* c, double* out) {
     mix((unsigned long long)(uintptr_t)H.lev[0]->Aval), mix((unsigned long long)(uintptr_t)H.lev[0]->nbr);
     mix((unsigned long long)(uintptr_t)H.lev[0]->b.p), mix((unsigned long long)H.lev.size()), mix((unsigned long long)H.nu), mix((unsigned long long)H.nuCoarse);
     mix((unsigned long long)(H.preFine + 1)), mix((unsigned long long)(H.postFine + 1)), mix((unsigned long long)(H.preCoarse + 1)), mix((unsigned long long)(H.postCoarse + 1));
-    mix((unsigned long long)(H.wFrom + 7)), mix(H.f32v ? 2ull : 1ull);
+    mix((unsigned long long)(H.wFrom + 7)), mix(H.f32v ? (H.rhsIsF32 ? 3ull : 2ull) : 1ull);
     if (H.f32v) mix((unsigned long long)(uintptr_t)H.inF.p), mix((unsigned long long)(uintptr_t)H.outF.p);
     mix((unsigned long long)__double_as_longlong_host(H.over)), mix(H.denseOk ? 1ull : 0ull), mix((unsigned long long)H.nD);
     for (auto& L : H.lev) {
