@@ -357,11 +357,23 @@ __global__ void k_galerkin(int nc, const int* __restrict__ aggPtr, const int* __
     if (I >= nc || l >= BB) return;
     const int c0 = cPtr[I], cn = cPtr[I + 1] - c0;
     for (int k = 0; k < cn; ++k) acc[k * BB + l] = 0.0;
+    // four fine blocks per step with their loads issued together (the walk is latency-bound: one dependent global load per
+    // block otherwise); the sums keep the ascending order
     for (int m = aggPtr[I]; m < aggPtr[I + 1]; ++m) {
         const int i = aggNodes[m];
-        for (int k = fPtr[i]; k < fPtr[i + 1]; ++k) {
-            const int cs = cslot[k];
-            if (cs >= 0) acc[cs * BB + l] += fA[(size_t)k * BB + l];
+        const int k1 = fPtr[i + 1];
+        for (int k = fPtr[i]; k < k1; k += 4) {
+            int cs[4];
+            double a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const bool in = k + u < k1;
+                cs[u] = in ? cslot[k + u] : -1;
+                a[u] = in ? fA[(size_t)(k + u) * BB + l] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (cs[u] >= 0) acc[cs[u] * BB + l] += a[u];
         }
     }
     for (int k = 0; k < cn; ++k) cA[(size_t)(c0 + k) * BB + l] = acc[k * BB + l];
@@ -440,7 +452,8 @@ __global__ void k_mg_diag_scale(int n, const int* __restrict__ nbrPtr, const int
 }
 template <int BS>
 __global__ void k_mg_l1_scale(int n, const int* __restrict__ nbrPtr, const int* __restrict__ nbr, const double* __restrict__ Aval,
-                              const double* __restrict__ sc, double theta, double wcap, double* __restrict__ Dw, double* __restrict__ rmax) {
+                              const double* __restrict__ sc, double theta, double wcap, double* __restrict__ Dw, double* __restrict__ rmax,
+                              float* __restrict__ Af) {
     constexpr int BB = BS * BS;
     const int l = threadIdx.x & 15;
     const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
@@ -453,17 +466,29 @@ __global__ void k_mg_l1_scale(int n, const int* __restrict__ nbrPtr, const int* 
     double ri = 0;
     const int b0 = act ? nbrPtr[i] : 0, b1 = act ? nbrPtr[i + 1] : 0;
     const unsigned hm = 0xffffu << (threadIdx.x & 16);  // this half-warp
+    const double scMine = ent ? sc[(size_t)i * BS + r] : 1.0;
+    // the block entry, the neighbour index and its scale are fetched one block ahead (two for the index): the walk is
+    // latency-bound otherwise (round 2: 603 -> ~300 us at C4)
+    int nb1 = (ent && b0 < b1) ? nbr[b0] : 0;
+    int nb2 = (ent && b0 + 1 < b1) ? nbr[b0 + 1] : 0;
+    double a1 = (ent && b0 < b1) ? Aval[(size_t)b0 * BB + l] : 0.0;
+    double s1 = (ent && b0 < b1) ? sc[(size_t)nb1 * BS + cc] : 0.0;
     for (int k = b0; k < b1; ++k) {
-        // every lane fetches its own entry of the block once (one coalesced 128-byte row per half-warp); the 4x4 product
-        // takes the column entries from the owning lanes
-        const double aMine = ent ? Aval[(size_t)k * BB + l] : 0.0;
+        const bool more = ent && k + 1 < b1;
+        const double a2 = more ? Aval[(size_t)(k + 1) * BB + l] : 0.0;
+        const double s2 = more ? sc[(size_t)nb2 * BS + cc] : 0.0;
+        const int nb3 = (ent && k + 2 < b1) ? nbr[k + 2] : 0;
+        // every lane holds its own entry of the block (one coalesced 128-byte row per half-warp); the 4x4 product takes the
+        // column entries from the owning lanes
+        const double aMine = a1;
+        if (Af && ent) Af[(size_t)k * BB + l] = (float)aMine;  // the cycle's fp32 copy of A, written in the same pass
         double p = 0;
 #pragma unroll
         for (int q = 0; q < BS; ++q) {
             const double aq = __shfl_sync(hm, aMine, (threadIdx.x & 16) + min(q * BS + cc, 15));
             p += dinvRow[q] * aq;
         }
-        if (ent) p *= sc[(size_t)nbr[k] * BS + cc] / sc[(size_t)i * BS + r];  // S_i^-1 (D^-1 A)_ij S_j
+        if (ent) p *= s1 / scMine;  // S_i^-1 (D^-1 A)_ij S_j
         p = ent ? fabs(p) : 0.0;
         // row sums over cc (lanes of the same r), then max over r
         double rs = 0;
@@ -476,6 +501,7 @@ __global__ void k_mg_l1_scale(int n, const int* __restrict__ nbrPtr, const int* 
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(hm, mx, o));
         ri += mx;
+        a1 = a2, s1 = s2, nb2 = nb3;
     }
     ri = fmax(ri, 1.0);
     if (ent) Dw[(size_t)i * BB + l] *= fmin(theta / ri, wcap);
@@ -1178,7 +1204,7 @@ void buildSymbolic(pfem_ctx* c, MgHierarchy& H) {
 }
 
 // Dw = damping * A_ii^-1: uniform damping L.omega, or (l1 = true) theta / r_i per node
-void blockInverse(pfem_ctx* c, MgLevel& L, int BS, bool l1 = false, double theta = 1.0) {
+void blockInverse(pfem_ctx* c, MgLevel& L, int BS, bool l1 = false, double theta = 1.0, float* Af = nullptr) {
     const double w = l1 ? 1.0 : L.omega;
     if (BS == 4) k_mg_block_inv<4><<<divUp(L.n, 128), 128, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, w, L.Dw.p);
     else k_mg_block_inv<3><<<divUp(L.n, 128), 128, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, w, L.Dw.p);
@@ -1196,12 +1222,12 @@ void blockInverse(pfem_ctx* c, MgLevel& L, int BS, bool l1 = false, double theta
         k_mg_diag_scale<4><<<divUp(L.n * BS, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, L.sc.p);
         LAUNCH_CHECK(c);
         if (L.distributed && c->nRanks > 1) commHaloPlan(c, *L.plan, L.sc.p, nullptr, BS);  // scales of the ghost columns
-        k_mg_l1_scale<4><<<divUp((int64_t)L.n * 16, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, L.sc.p, theta, wcap, L.Dw.p, nullptr);
+        k_mg_l1_scale<4><<<divUp((int64_t)L.n * 16, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, L.sc.p, theta, wcap, L.Dw.p, nullptr, Af);
     } else {
         k_mg_diag_scale<3><<<divUp(L.n * BS, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.diagSlot, L.Aval, L.sc.p);
         LAUNCH_CHECK(c);
         if (L.distributed && c->nRanks > 1) commHaloPlan(c, *L.plan, L.sc.p, nullptr, BS);
-        k_mg_l1_scale<3><<<divUp((int64_t)L.n * 16, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, L.sc.p, theta, wcap, L.Dw.p, nullptr);
+        k_mg_l1_scale<3><<<divUp((int64_t)L.n * 16, 256), 256, 0, c->stream>>>(L.n, L.nbrPtr, L.nbr, L.Aval, L.sc.p, theta, wcap, L.Dw.p, nullptr, Af);
     }
     LAUNCH_CHECK(c);
 }
@@ -1251,15 +1277,18 @@ void buildNumeric(pfem_ctx* c, MgHierarchy& H) {
         MgLevel& L = *H.lev[l];
         static const int dampMode = getenv("PFEM_MG_DAMP") ? atoi(getenv("PFEM_MG_DAMP")) : 0;  // 0 l1 | 1 uniform | 2 tuned
         std::unique_ptr<PhaseScope> sub(new PhaseScope(c, l == 0 ? "MG smoother setup L0" : "MG smoother setup coarse"));
+        const bool l1Path = dampMode == 0 || c->nRanks > 1;  // (the tuned ladder takes per-rank decisions: not on a partitioned mesh)
         if (mgFp32()) {
             const size_t nv = (size_t)L.nBlocks * BB;
             L.Af.reserve(nv + 8);
-            k_to_float<<<std::max(1, std::min(c->smCount * 8, divUp((int64_t)nv, 1024))), 256, 0, c->stream>>>(nv, L.Aval, L.Af.p);
-            LAUNCH_CHECK(c);
+            if (!l1Path) {  // the l1 pass reads every entry of A anyway and writes the fp32 copy itself
+                k_to_float<<<std::max(1, std::min(c->smCount * 8, divUp((int64_t)nv, 1024))), 256, 0, c->stream>>>(nv, L.Aval, L.Af.p);
+                LAUNCH_CHECK(c);
+            }
         }
-        if (dampMode == 0 || c->nRanks > 1) {  // (the tuned ladder takes per-rank decisions: not on a partitioned mesh)
+        if (l1Path) {
             L.omega = H.fixedOmega > 0.0 ? H.fixedOmega : 2.0;  // theta: 2.0 measured best-robust (2.5 turns unstable in 2-D)
-            blockInverse(c, L, BS, true, L.omega);
+            blockInverse(c, L, BS, true, L.omega, mgFp32() ? L.Af.p : nullptr);
         } else if (H.fixedOmega > 0.0 || dampMode == 1) {
             L.omega = H.fixedOmega > 0.0 ? H.fixedOmega : 0.45;
             blockInverse(c, L, BS);
