@@ -133,7 +133,7 @@ constexpr int NBR_CAP = 512;  // distinct coarse neighbours a warp can collect
 __global__ void __launch_bounds__(1024) k_bbox(const double* __restrict__ X, int n, int dim, double* __restrict__ out) {
     __shared__ double slo[3][32], shi[3][32];
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-    for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
         for (int d = 0; d < dim; ++d) {
             const double v = X[(size_t)i * 4 + d];
             lo[d] = fmin(lo[d], v);
@@ -153,9 +153,18 @@ __global__ void __launch_bounds__(1024) k_bbox(const double* __restrict__ X, int
         double a = 1e300, b = -1e300;
         for (int k = 0; k < (int)(blockDim.x >> 5); ++k) a = fmin(a, slo[d][k]), b = fmax(b, shi[d][k]);
         if (d >= dim) a = b = 0.0;
-        out[d] = a;
-        out[3 + d] = b;
+        out[(size_t)blockIdx.x * 6 + d] = a;
+        out[(size_t)blockIdx.x * 6 + 3 + d] = b;
     }
+}
+// box of the per-block boxes (minimum / maximum: order-independent, so the result is the same bits as one block's)
+__global__ void k_bbox_final(const double* __restrict__ part, int nPart, double* __restrict__ out) {
+    const int d = threadIdx.x;
+    if (d >= 3) return;
+    double a = 1e300, b = -1e300;
+    for (int k = 0; k < nPart; ++k) a = fmin(a, part[(size_t)k * 6 + d]), b = fmax(b, part[(size_t)k * 6 + 3 + d]);
+    out[d] = a;
+    out[3 + d] = b;
 }
 
 // mean element size -> node spacing h0 of level 0 (two-stage ordered sum: deterministic)
@@ -872,7 +881,17 @@ bool localAggregate(pfem_ctx* c, MgHierarchy& H, MgLevel& L, double& cellSize, i
     c->scratchI.reserve((size_t)std::max(L.nVec, c->nNodes) + 64);
     H.flag.reserve(16);
     box.reserve(8);
-    k_bbox<<<1, 1024, 0, c->stream>>>(L.X, n, dim, box.p);
+    {
+        const int nb = std::max(1, std::min(64, n / 4096));
+        box.reserve(8 + (size_t)nb * 6);
+        if (nb == 1)
+            k_bbox<<<1, 1024, 0, c->stream>>>(L.X, n, dim, box.p);
+        else {
+            k_bbox<<<nb, 1024, 0, c->stream>>>(L.X, n, dim, box.p + 8);
+            LAUNCH_CHECK(c);
+            k_bbox_final<<<1, 32, 0, c->stream>>>(box.p + 8, nb, box.p);
+        }
+    }
     LAUNCH_CHECK(c);
     double hb[6];
     CUDA_CHECK(cudaMemcpyAsync(hb, box.p, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
