@@ -77,6 +77,7 @@ def lib():
         L.pfem_ref_pspg_build.argtypes = [C.c_void_p, DP, C.c_int]
         L.pfem_ref_csc_copy.argtypes = [C.c_void_p, IP, C.POINTER(C.c_int32), DP, DP]
         L.pfem_ref_pspg_solve.argtypes = [C.c_void_p]
+        L.pfem_ref_heat_solve.argtypes = [C.c_void_p]
         L.pfem_ref_in_heat_build.restype = I64
         L.pfem_ref_in_heat_build.argtypes = [C.c_void_p, DP, C.c_int]
         L.pfem_ref_in_heat_copy.argtypes = [C.c_void_p, IP, C.POINTER(C.c_int32), DP, DP]
@@ -268,6 +269,10 @@ class RefCase:
         ok = self._chk(lib().pfem_ref_pspg_solve(self._h), "pspg_solve")
         return bool(ok), lib().pfem_ref_direct_solves() - n0
 
+    def heat_solve(self):
+        """m_pEquations[1]->solve(): the heat equation of the incompressible Boussinesq problem (IN/Solver.cpp:249-258)."""
+        return bool(self._chk(lib().pfem_ref_heat_solve(self._h), "heat_solve"))
+
     @staticmethod
     def cg_log(max_rows=256):
         """(n, iterations, relative residual, info) of the stand-in ConjugateGradient solves since the last call."""
@@ -277,7 +282,8 @@ class RefCase:
 
     # ---- drop-in build only (libpfem_ref_dropin.so) ----
     def use_b200_equation(self):
-        """Swap the reference's MomContEqIncompNewton<dim> for the shim's MomContEqIncompNewtonB200<dim> (= the REGISTER_EQ edit)."""
+        """Swap the reference's MomContEqIncompNewton<dim> for the shim's MomContEqIncompNewtonB200<dim> (= the REGISTER_EQ edit);
+        problem id "Boussinesq": HeatEqIncompNewton<dim> becomes HeatEqIncompNewtonB200<dim> as well."""
         self._chk(lib().pfem_ref_use_b200_equation(self._h), "use_b200_equation")
 
     def wc_step_b200(self, dt, download=True):

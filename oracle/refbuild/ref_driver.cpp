@@ -577,6 +577,19 @@ int pfem_ref_pspg_solve(void* h) {
     }
 }
 
+// The heat equation of the Boussinesq problem: m_pEquations[1]->solve() (IN/Solver.cpp:249-258).  Returns 1 ok / 0 failed.
+int pfem_ref_heat_solve(void* h) {
+    auto& rc = *static_cast<RefCase*>(h);
+    try {
+        rc.rebuildPositions();
+        if (rc.solver->m_pEquations.size() < 2) return -1;
+        return rc.solver->m_pEquations[1]->solve() ? 1 : 0;
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return -1;
+    }
+}
+
 // One explicit step: SolverWCompNewton::m_solveWCompNewtonNoT with the given dt (WC/Solver.cpp:236-276)
 int pfem_ref_wc_step(void* h, double dt) {
     auto& rc = *static_cast<RefCase*>(h);
@@ -613,12 +626,22 @@ int pfem_ref_use_b200_equation(void* h) {
         Solver* s = rc.solver;
         std::vector<SolTable> materialParams(rc.problem->m_problemParams.size());
         for (std::size_t i = 0; i < materialParams.size(); ++i) materialParams[i] = SolTable("Material", rc.problem->m_problemParams[i]);
+        const bool boussinesq = rc.problemId == "Boussinesq";
         const std::vector<unsigned short> bcFlags = {0};
-        const std::vector<unsigned int> statesIndex = {0};
+        std::vector<unsigned int> statesIndex = {0};
+        if (boussinesq) statesIndex.push_back(static_cast<unsigned int>(rc.dim) + 1);  // IN/Solver.cpp:63-64
         if (rc.dim == 2)
             s->m_pEquations[0] = std::make_unique<MomContEqIncompNewtonB200<2>>(rc.problem.get(), s, rc.mesh, s->m_solverParams, materialParams, bcFlags, statesIndex);
         else
             s->m_pEquations[0] = std::make_unique<MomContEqIncompNewtonB200<3>>(rc.problem.get(), s, rc.mesh, s->m_solverParams, materialParams, bcFlags, statesIndex);
+        if (boussinesq) {  // IN/Solver.cpp:70-75: the heat equation, flags {1,2,3,4}, state dim + 1
+            const std::vector<unsigned short> hFlags = {1, 2, 3, 4};
+            const std::vector<unsigned int> hStates = {static_cast<unsigned int>(rc.dim) + 1};
+            if (rc.dim == 2)
+                s->m_pEquations[1] = std::make_unique<HeatEqIncompNewtonB200<2>>(rc.problem.get(), s, rc.mesh, s->m_solverParams, materialParams, hFlags, hStates);
+            else
+                s->m_pEquations[1] = std::make_unique<HeatEqIncompNewtonB200<3>>(rc.problem.get(), s, rc.mesh, s->m_solverParams, materialParams, hFlags, hStates);
+        }
         return 0;
     } catch (const std::exception& e) {
         g_lastError = e.what();

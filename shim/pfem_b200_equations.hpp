@@ -270,6 +270,23 @@ inline void pushDirichlet(RankSet& R, std::size_t nN, const std::vector<uint8_t>
     });
 }
 
+// "<type>T"(pos, t + dt) of the nodes whose tag carries flag `bcFlag` (IncompNewton/HeatEquation.inl:383-408,
+// WCompNewton/HeatEquation.inl:226-244), device numbering
+template <class MeshT, class SolverT, class BcTable>
+void evalTemperatureBc(MeshT* pMesh, SolverT* pSolver, BcTable& bc, unsigned short bcFlag, double tNext, const Renumbering& rn,
+                       std::vector<uint8_t>& tmask, std::vector<double>& tval) {
+    const std::size_t nN = pMesh->getNodesCount();
+    tmask.assign(nN, 0);
+    tval.assign(nN, 0.0);
+    for (std::size_t nOld = 0; nOld < nN; ++nOld) {
+        const auto& node = pMesh->getNode(nOld);
+        if (!pSolver->getBcTagFlags(node.getTag(), bcFlag)) continue;
+        const std::array<double, 1> res = bc.template call<std::array<double, 1>>(pMesh->getNodeType(nOld) + "T", node.getPosition(), tNext);
+        tmask[rn.nodeNew(nOld)] = 1;
+        tval[rn.nodeNew(nOld)] = res[0];
+    }
+}
+constexpr unsigned short kNoVelocityBc = 0xffff;  // bcFlag value: do not evaluate / upload velocity Dirichlet data
 // Mesh -> device(s): connectivity, flags, positions, states [first, first+count), Dirichlet mask/values.
 template <unsigned short dim, class MeshT, class SolverT, class ProblemT, class BcTable>
 void uploadMesh(RankSet& R, MeshT* pMesh, SolverT* pSolver, ProblemT* pProblem, BcTable& bc, unsigned short bcFlag,
@@ -286,7 +303,8 @@ void uploadMesh(RankSet& R, MeshT* pMesh, SolverT* pSolver, ProblemT* pProblem, 
         for (unsigned int s = 0; s < stateCount; ++s) q[n + s * nN] = node.getState(firstState + s);
     }
     const double tNext = pProblem->getCurrentSimTime() + pSolver->getTimeStep();
-    evalDirichlet<dim>(pMesh, pSolver, bc, bcFlag, tNext, rn, nullptr, dmask, dval, anyMovingBcNode);
+    const bool withVelocityBc = bcFlag != kNoVelocityBc;  // the heat equation's context carries no velocity data
+    if (withVelocityBc) evalDirichlet<dim>(pMesh, pSolver, bc, bcFlag, tNext, rn, nullptr, dmask, dval, anyMovingBcNode);
     if (topologyChanged) {
         std::vector<uint64_t> conn(nE * (dim + 1));
         for (std::size_t e = 0; e < nE; ++e) {
@@ -350,13 +368,14 @@ void uploadMesh(RankSet& R, MeshT* pMesh, SolverT* pSolver, ProblemT* pProblem, 
         pfem_ctx* ctx = R.ctx[r];
         if (!R.multi()) {
             check(ctx, pfem_set_positions(ctx, x.data()), "pfem_set_positions");
-            check(ctx, pfem_set_states(ctx, (int)firstState, (int)stateCount, q.data()), "pfem_set_states");
+            if (stateCount > 0) check(ctx, pfem_set_states(ctx, (int)firstState, (int)stateCount, q.data()), "pfem_set_states");
         } else {
             check(ctx, pfem_set_positions(ctx, R.scatter(r, x, nN).data()), "pfem_set_positions");
-            check(ctx, pfem_set_states(ctx, (int)firstState, (int)stateCount, R.scatter(r, q, nN).data()), "pfem_set_states");
+            if (stateCount > 0)
+                check(ctx, pfem_set_states(ctx, (int)firstState, (int)stateCount, R.scatter(r, q, nN).data()), "pfem_set_states");
         }
     });
-    pushDirichlet(R, nN, dmask, dval);
+    if (withVelocityBc) pushDirichlet(R, nN, dmask, dval);
 }
 
 }  // namespace pfem_b200_shim
@@ -371,10 +390,11 @@ public:
         : Equation(pProblem, pSolver, pMesh, solverParams, materialParams, bcFlags, statesIndex, "MomContEq") {
         if (m_pSolver->getID() != "PSPG") throw std::runtime_error("the B200 path implements the PSPG solver only");
         const std::string problemId = m_pProblem->getID();
-        if (problemId != "IncompNewtonNoT" && problemId != "Bingham")
-            throw std::runtime_error("the B200 PSPG equation implements the IncompNewtonNoT and Bingham problems (Boussinesq: library only)");
-        if (bcFlags.size() != 1 || statesIndex.size() != 1)
-            throw std::runtime_error("the " + getID() + " equation requires one BC flag and one statesIndex");  // MomContEquation.inl:64-69
+        if (problemId != "IncompNewtonNoT" && problemId != "Bingham" && problemId != "Boussinesq")
+            throw std::runtime_error("the B200 PSPG equation implements the IncompNewtonNoT, Bingham and Boussinesq problems");
+        m_isBoussinesq = problemId == "Boussinesq";
+        if (bcFlags.size() != 1 || statesIndex.size() != (m_isBoussinesq ? 2u : 1u))  // MomContEquation.inl:64-69; IN/Solver.cpp:63-64
+            throw std::runtime_error("the " + getID() + " equation requires one BC flag and one statesIndex (two for Boussinesq)");
         m_par.rho = m_materialParams[0].template checkAndGet<double>("rho");
         m_par.mu = m_materialParams[0].template checkAndGet<double>("mu");
         m_gamma = m_materialParams[0].template checkAndGet<double>("gamma");
@@ -391,6 +411,14 @@ public:
         if (m_ranks->multi()) throw std::runtime_error("the B200 PSPG equation drives one device from the shim (PFEM_DEVICES lists several)");
         m_ctx = m_ranks->ctx[0];
         pfem_b200_shim::check(m_ctx, pfem_set_surface_tension(m_ctx, m_gamma), "pfem_set_surface_tension");
+        if (m_isBoussinesq) {  // MomContEquation.inl:32-38, 166-199: F and H carry (1 - alpha (T - Tr)); T is state statesIndex[1]
+            pfem_thermal_params th{};
+            th.alpha = m_materialParams[0].template checkAndGet<double>("alpha");
+            th.Tr = m_materialParams[0].template checkAndGet<double>("Tr");
+            th.k = m_materialParams[0].template checkAndGet<double>("k");
+            th.cv = m_materialParams[0].template checkAndGet<double>("cv");
+            pfem_b200_shim::check(m_ctx, pfem_set_thermal(m_ctx, &th), "pfem_set_thermal");
+        }
         if (problemId == "Bingham") {  // MomContEquation.inl:54-58, 102-119: regularised yield-stress viscosity
             const double tau0 = m_materialParams[0].template checkAndGet<double>("tau0");
             const double mReg = m_materialParams[0].template checkAndGet<double>("mReg");
@@ -418,6 +446,11 @@ public:
         //  position-independent BC functions, which is every example of the reference)
         uploadMesh<dim>(*m_ranks, m_pMesh, m_pSolver, m_pProblem, m_bcParams[0], m_bcFlags[0], m_statesIndex[0], dim + 1, true,
                         m_rn, m_gamma >= 1e-15);
+        if (m_isBoussinesq) {  // the temperature the buoyancy factors read: the host mesh's current T state
+            std::vector<double> T(nN);
+            for (std::size_t nOld = 0; nOld < nN; ++nOld) T[m_rn.nodeNew(nOld)] = m_pMesh->getNode(nOld).getState(m_statesIndex[1]);
+            check(m_ctx, pfem_set_temperature(m_ctx, T.data()), "pfem_set_temperature");
+        }
         std::vector<double> qPrev((dim + 1) * nN), qIter((dim + 1) * nN, 0.0), qIterPrev;
         for (std::size_t n = 0; n < nN; ++n)
             for (unsigned int s = 0; s <= dim; ++s) qPrev[n + s * nN] = m_pMesh->getNode(n).getState(m_statesIndex[0] + s);
@@ -475,9 +508,83 @@ private:
     pfem_pspg_params m_par{};
     pfem_b200_shim::Renumbering m_rn;
     double m_gamma = 0.0;
+    bool m_isBoussinesq = false;
     unsigned int m_maxIter = 10;
     double m_minRes = 1e-6, m_relTol = 1e-12;
     std::string m_residual;
+};
+
+// ======================================================================================================================
+// HeatEqIncompNewton (IncompNewton/HeatEquation.inl) without phase change and without flux facet terms: the implicit heat
+// system M(cv rho) + dt L(k), b = M theta_prev with Dirichlet / free-node rows, solved by Jacobi-CG started from the current
+// temperature (the reference: Eigen::ConjugateGradient::solveWithGuess, :129-135; the Picard loop runs once, :206-207).
+// Registered where IN/Solver.cpp:71-74 registers HeatEqIncompNewton (problem ids "Boussinesq" and "Conduction").
+// Its device context is its own (the momentum-continuity equation of the same solver keeps another one): the two
+// equations solve on different meshes anyway when solveHeatFirst is false (the momentum solve moves the nodes).
+template <unsigned short dim>
+class HeatEqIncompNewtonB200 : public Equation {
+public:
+    HeatEqIncompNewtonB200(Problem* pProblem, Solver* pSolver, Mesh* pMesh, std::vector<SolTable> solverParams,
+                           std::vector<SolTable> materialParams, const std::vector<unsigned short>& bcFlags,
+                           const std::vector<unsigned int>& statesIndex)
+        : Equation(pProblem, pSolver, pMesh, solverParams, materialParams, bcFlags, statesIndex, "HeatEq") {
+        m_k = m_materialParams[0].template checkAndGet<double>("k");
+        m_rho = m_materialParams[0].template checkAndGet<double>("rho");
+        m_cv = m_materialParams[0].template checkAndGet<double>("cv");
+        const double h = m_materialParams[0].template checkAndGet<double>("h");
+        m_materialParams[0].template checkAndGet<double>("Tinf");
+        const double epsRad = m_materialParams[0].template checkAndGet<double>("epsRad");
+        if (h != 0.0 || epsRad != 0.0) throw std::runtime_error("the B200 heat equation has no convection / radiation facet terms (h, epsRad must be 0)");
+        for (const char* key : {"Tm", "C", "eps", "DT", "Lm"})
+            if (m_materialParams[0].doesVarExist(key)) throw std::runtime_error("the B200 heat equation has no phase change");
+        if (bcFlags.size() != 4) throw std::runtime_error("the " + getID() + " equation require two flags for four possible boundary conditions!");
+        if (statesIndex.size() != 1) throw std::runtime_error("the " + getID() + " equation require one state index describing the T state !");
+        m_equationParams[0].template checkAndGet<unsigned int>("maxIter");
+        m_equationParams[0].template checkAndGet<double>("minRes");
+        const std::string residual = m_equationParams[0].template checkAndGet<std::string>("residual");
+        if (residual != "T" && residual != "Ax_f") throw std::runtime_error("unknown residual type: " + residual);
+        m_relTol = m_equationParams[0].doesVarExist("krylovTol") ? m_equationParams[0].template checkAndGet<double>("krylovTol") : 1e-12;
+        m_needNormalCurv = false;
+        m_ranks.reset(new pfem_b200_shim::RankSet(dim));
+        if (m_ranks->multi()) throw std::runtime_error("the B200 heat equation drives one device from the shim (PFEM_DEVICES lists several)");
+        m_ctx = m_ranks->ctx[0];
+    }
+    ~HeatEqIncompNewtonB200() override = default;
+
+    bool solve() override {
+        using namespace pfem_b200_shim;
+        const std::size_t nN = m_pMesh->getNodesCount();
+        const double dt = m_pSolver->getTimeStep();
+        // flux BCs (flags 2-4) are not taken over: refuse them instead of dropping them silently
+        for (std::size_t n = 0; n < nN; ++n) {
+            const auto& node = m_pMesh->getNode(n);
+            for (unsigned short f = 1; f < 4; ++f)
+                if (m_pSolver->getBcTagFlags(node.getTag(), m_bcFlags[f])) throw std::runtime_error("the B200 heat equation has no flux boundary conditions (Q, Qh, Qr)");
+        }
+        uploadMesh<dim>(*m_ranks, m_pMesh, m_pSolver, m_pProblem, m_bcParams[0], kNoVelocityBc, 0, 0, true, m_rn, false);
+        std::vector<double> T(nN);
+        for (std::size_t nOld = 0; nOld < nN; ++nOld) T[m_rn.nodeNew(nOld)] = m_pMesh->getNode(nOld).getState(m_statesIndex[0]);
+        std::vector<uint8_t> tmask;
+        std::vector<double> tval;
+        evalTemperatureBc(m_pMesh, m_pSolver, m_bcParams[0], m_bcFlags[0], m_pProblem->getCurrentSimTime() + dt, m_rn, tmask, tval);
+        check(m_ctx, pfem_set_temperature(m_ctx, T.data()), "pfem_set_temperature");           // solveWithGuess: start from theta_prev
+        check(m_ctx, pfem_set_temperature_bc(m_ctx, tmask.data(), tval.data()), "pfem_set_temperature_bc");
+        check(m_ctx, pfem_heat_assemble(m_ctx, m_rho, m_cv, m_k, dt, T.data()), "pfem_heat_assemble");
+        std::vector<double> Tn(nN);
+        int iters = 0;
+        double relRes = 0;
+        const int rc = pfem_heat_solve(m_ctx, m_relTol, 100000, Tn.data(), &iters, &relRes);
+        check(m_ctx, rc, "pfem_heat_solve");
+        if (rc == PFEM_NOT_CONVERGED || rc == PFEM_NAN) return false;
+        for (std::size_t nOld = 0; nOld < nN; ++nOld) m_pMesh->setNodeState(nOld, m_statesIndex[0], Tn[m_rn.nodeNew(nOld)]);
+        return true;
+    }
+
+private:
+    std::unique_ptr<pfem_b200_shim::RankSet> m_ranks;
+    pfem_ctx* m_ctx = nullptr;
+    pfem_b200_shim::Renumbering m_rn;
+    double m_k = 0, m_rho = 0, m_cv = 0, m_relTol = 1e-12;
 };
 
 // ======================================================================================================================

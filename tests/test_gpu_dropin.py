@@ -193,3 +193,41 @@ def test_boussinesq_wc_steps_through_the_shim(dim, n):
             dt_ref, dt = a.wc_next_dt(), b.wc_next_dt_b200()
             assert abs(dt - dt_ref) <= 1e-13 * dt_ref
         assert np.abs(Ta - T0).max() > 1e-3  # conduction moved the temperature
+
+
+@pytest.mark.parametrize("dim,n", [(2, 8), (3, 4)])
+def test_boussinesq_time_step_through_the_shim(dim, n):
+    """Problem id "Boussinesq" (incompressible): SolverIncompNewton::m_solveBoussinesq with solveHeatFirst = the heat
+    equation's solve() then the momentum-continuity solve() (IN/Solver.cpp:249-264), once with the reference's
+    HeatEqIncompNewton + MomContEqIncompNewton and once with HeatEqIncompNewtonB200 + MomContEqIncompNewtonB200."""
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.02, permute=True)
+    nn = mesh.n_nodes
+    _, q_prev = mg.pspg_state(mesh)
+    c = mesh.coords()
+    T0 = 300.0 + 10.0 * c[:, 0] + 2.0 * np.random.default_rng(5).standard_normal(nn)
+    bound = (mesh.flags & mg.F_BOUND) != 0
+    t_mask = (bound & ((np.abs(c[:, 0]) < 1e-12) | (np.abs(c[:, 0] - 1.0) < 1e-12))).astype(np.uint8)
+    t_val = np.where(c[:, 0] < 0.5, 310.0, 290.0)
+    P = mg.PSPG_PARAMS
+    par = np.concatenate([orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim)), [10, 1e-6]])
+    out = {}
+    for which, alpha in (("no_buoyancy", 0.0), ("reference", 6.9e-3), ("b200", 6.9e-3)):
+        th = dict(alpha=alpha, Tr=300.0, k=6.0e4, cv=4.186, t_mask=t_mask, t_val=t_val)  # conduction exaggerated: one step shows it
+        with ref.RefCase(mesh, "pspg", par, thermal=th) as rc:
+            if which == "b200":
+                rc.use_b200_equation()
+            rc.set_states(np.concatenate([q_prev, T0]))
+            assert rc.heat_solve()
+            ok, _ = rc.pspg_solve()
+            assert ok
+            out[which] = (rc.get_states(0, dim + 2), rc.positions())
+    (q_ref, x_ref), (q, x) = out["reference"], out["b200"]
+    assert rel_err(q[: dim * nn], q_ref[: dim * nn]) < 1e-8
+    assert rel_err(q[dim * nn: (dim + 1) * nn], q_ref[dim * nn: (dim + 1) * nn]) < 1e-8
+    T_ref, T = q_ref[(dim + 1) * nn:], q[(dim + 1) * nn:]
+    assert rel_err(T, T_ref) < 1e-9
+    assert np.allclose(T[t_mask != 0], t_val[t_mask != 0], rtol=1e-12, atol=0)   # rows reduced to their diagonal, CG to 1e-12
+    assert np.abs(T_ref - T0).max() > 1e-2                       # the heat equation moved the temperature
+    assert np.abs(x - x_ref).max() < 1e-9
+    q_nob = out["no_buoyancy"][0]
+    assert rel_err(q_ref[: dim * nn], q_nob[: dim * nn]) > 1e-6  # the buoyancy factor is live
