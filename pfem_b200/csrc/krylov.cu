@@ -718,13 +718,11 @@ double krylovResidualNorm(pfem_ctx* c, double* xInternal) { return residualNorm(
 
 namespace {
 // restart length of the flexible GMRES (PFEM_GMRES_M, <= 62); 0 selects BiCGSTAB for the multigrid-preconditioned solve too
-int gmresRestart() {
-    static const int v = getenv("PFEM_GMRES_M") ? std::max(0, std::min(62, atoi(getenv("PFEM_GMRES_M")))) : 40;
-    return v;
+int gmresRestart() {  // read at every solve: the tests switch it
+    return getenv("PFEM_GMRES_M") ? std::max(0, std::min(62, atoi(getenv("PFEM_GMRES_M")))) : 40;
 }
 bool gmresPollAhead() {
-    static const bool v = !(getenv("PFEM_GMRES_POLL_EVERY") && atoi(getenv("PFEM_GMRES_POLL_EVERY")) == 1);
-    return v;
+    return !(getenv("PFEM_GMRES_POLL_EVERY") && atoi(getenv("PFEM_GMRES_POLL_EVERY")) == 1);
 }
 struct GmresOutcome {
     int status = PFEM_OK;

@@ -1412,7 +1412,7 @@ bool mgSetup(pfem_ctx* c) {
                      envPostC = envInt("PFEM_MG_POSTC");
     H.preFine = envPre, H.postFine = envPost, H.preCoarse = envPreC, H.postCoarse = envPostC;
     // fp32 vectors inside the cycle: only under the flexible GMRES (the caller says so) and with the fp32 matrix copies
-    static const bool envF32V = !(getenv("PFEM_MG_FP32V") && atoi(getenv("PFEM_MG_FP32V")) == 0);
+    const bool envF32V = !(getenv("PFEM_MG_FP32V") && atoi(getenv("PFEM_MG_FP32V")) == 0);  // read per solve: tests switch it
     H.f32v = c->mgFlexible && envF32V && mgFp32();
     H.rhsIsF32 = false;  // until the Krylov method asks for the fp32 right-hand side (mgRhsF)
     if (!H.symbolicValid) {

@@ -88,3 +88,30 @@ def test_auto_hands_over_when_the_cycle_is_not_a_contraction():
     assert aut["used"] == "block"
     assert aut["iters"] < 2 * blk["iters"] + 100
     assert rel_err(aut["q"], blk["q"]) < TOL_Q
+
+
+@pytest.mark.parametrize("dim,n", [(2, 48), (3, 16)])
+def test_krylov_variants_agree(dim, n, monkeypatch):
+    """Flexible GMRES (default under multigrid) against BiCGSTAB with the same cycle (PFEM_GMRES_M=0), a restart length that
+    forces several restarts (PFEM_GMRES_M=4), polling after every iteration, and the fp64-vector cycle (PFEM_MG_FP32V=0):
+    same fields; GMRES spends at most as many cycles as BiCGSTAB (which runs two per iteration)."""
+    mesh = mg.kuhn_box(dim, n, free_fraction=0.01, permute=True)
+    q, q_prev = mg.pspg_state(mesh)
+    P = mg.PSPG_PARAMS
+    par = orc.pspg_param_array(P["rho"], P["mu"], P["dt"], mg.gravity(dim))
+    out = {}
+    for name, env in (("gmres", {}), ("bicgstab", {"PFEM_GMRES_M": "0"}), ("restarts", {"PFEM_GMRES_M": "4"}),
+                      ("poll_every", {"PFEM_GMRES_POLL_EVERY": "1"}), ("fp64_vectors", {"PFEM_MG_FP32V": "0"})):
+        for k in ("PFEM_GMRES_M", "PFEM_GMRES_POLL_EVERY", "PFEM_MG_FP32V"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out[name] = _solve(mesh, q, q_prev, par, "mg", tol=1e-12)
+        assert out[name]["status"] == 0 and out[name]["used"] == "mg" and out[name]["rel_res"] <= 1e-12 * 1.01, (name, out[name])
+    ref_q = out["gmres"]["q"]
+    for name in ("bicgstab", "restarts", "poll_every", "fp64_vectors"):
+        assert rel_err(out[name]["q"], ref_q) < TOL_Q, name
+    assert out["gmres"]["iters"] <= 2 * out["bicgstab"]["iters"]
+    assert out["restarts"]["iters"] >= out["gmres"]["iters"]
+    assert out["poll_every"]["iters"] == out["gmres"]["iters"] and (out["poll_every"]["q"] == ref_q).all()
+    assert abs(out["fp64_vectors"]["iters"] - out["gmres"]["iters"]) <= 1
