@@ -148,51 +148,53 @@ __global__ void k_neighbours(const int* __restrict__ conn, int npe, const int* _
         }
         return;
     }
-    for (int c = lane; c < C; c += 32) cand[c] = (unsigned)conn[(size_t)n2e[eb + c / npe] * npe + (c % npe)];
+    // candidates = the nodes of the incident elements; warp-wide bitonic sort in shared memory (padded with 0xffffffff to a
+    // power of two), then the distinct values are the entries that differ from their left neighbour.  Round 2: replaces an
+    // O(C^2) duplicate sweep + rank count (1.65 -> ~0.7 ms for the two passes at 2 M tets).
+    int P = 32;
+    while (P < C) P <<= 1;
+    for (int c = lane; c < P; c += 32) cand[c] = c < C ? (unsigned)conn[(size_t)n2e[eb + c / npe] * npe + (c % npe)] : 0xffffffffu;
     __syncwarp();
-    // sweep 1: mark later duplicates (bit 31)
-    for (int c = lane; c < C; c += 32) {
-        const unsigned v = cand[c] & 0x7fffffffu;
-        bool first = true;
-        for (int q = 0; q < c; ++q)
-            if ((cand[q] & 0x7fffffffu) == v) {
-                first = false;
-                break;
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = lane; t < (P >> 1); t += 32) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int q = i | j;
+                const unsigned x = cand[i], y = cand[q];
+                const bool up = (i & k) == 0;
+                if ((x > y) == up) cand[i] = y, cand[q] = x;
             }
-        if (!first) cand[c] = v | 0x80000000u;
-    }
-    __syncwarp();
+            __syncwarp();
+        }
     int nDistinct = 0;
-    for (int c = lane; c < C; c += 32) {
+    for (int c0 = 0; c0 < P; c0 += 32) {  // (uniform trip count: the ballot needs the whole warp)
+        const int c = c0 + lane;
         const unsigned v = cand[c];
-        if (v & 0x80000000u) continue;
-        ++nDistinct;
-        if (FILL) {
-            int rank = 0;
-            for (int q = 0; q < C; ++q) {
-                const unsigned u = cand[q];
-                rank += (!(u & 0x80000000u) && u < v) ? 1 : 0;
-            }
+        const bool first = v != 0xffffffffu && (c == 0 || cand[c - 1] != v);
+        const unsigned bal = __ballot_sync(0xffffffffu, first);
+        if (FILL && first) {
+            const int rank = nDistinct + __popc(bal & ((1u << lane) - 1u));
             nbr[nbrCntOrPtr[node] + rank] = (int)v;
             sorted[rank] = v;
             if ((int)v == node) diagSlot[node] = rank;
         }
+        nDistinct += __popc(bal);
     }
     if (!FILL) {
-        for (int o = 16; o > 0; o >>= 1) nDistinct += __shfl_xor_sync(0xffffffffu, nDistinct, o);
         if (lane == 0) {
             nbrCntOrPtr[node] = nDistinct;
             atomicMax(maxNb, nDistinct);
         }
         return;
     }
+    __syncwarp();
     const int nb0 = nbrCntOrPtr[node], nb = nbrCntOrPtr[node + 1] - nb0;
     for (int t = lane; t < nb * CH; t += 32) masks[t] = 0u;
     __syncwarp();
     // slot of every candidate = lower_bound in the sorted distinct list; one byte per (element, local node)
     unsigned char* slotBytes = reinterpret_cast<unsigned char*>(n2eSlots + eb);
     for (int c = lane; c < C; c += 32) {
-        const unsigned v = cand[c] & 0x7fffffffu;
+        const unsigned v = (unsigned)conn[(size_t)n2e[eb + c / npe] * npe + (c % npe)];  // original (element, local node) order
         int lo = 0, hi = nb - 1;
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
@@ -294,7 +296,8 @@ void topoBuild(pfem_ctx* c, int64_t nNodes64, int64_t nElems64, const uint64_t* 
 
     // neighbour lists
     const int warps = 8;
-    const int candCap = max(c->maxE, 1) * npe;
+    int candCap = 32;  // power of two >= the largest candidate count (bitonic sort in k_neighbours)
+    while (candCap < max(c->maxE, 1) * npe) candCap <<= 1;
     const int CH = (max(c->maxE, 1) + 31) / 32;
     c->maskWords = CH;
     size_t smem = (size_t)warps * candCap * sizeof(int);
