@@ -156,6 +156,28 @@ int pfem_heat_solve(pfem_ctx* ctx, double relTol, int maxIter, double* T, int* i
 /* the heat system in the reference's format (column-major compressed, masked rows reduced to their diagonal); parity only */
 int pfem_heat_export_csc(pfem_ctx* ctx, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b);
 
+/* ---- fractional-step solver id "FracStep" (SURVEY 8f rank 1): the three linear systems of one Picard body
+ * (MomContEquationFracStep.inl:464-548), each assembled on the device from given inputs, and Eigen's Jacobi-preconditioned
+ * conjugate gradients (m_solverIt) for them.  Single-GPU contexts, gamma = 0.
+ * 1 velocity prediction: m_buildMatFracStep + m_applyBCVAppStep (:8-298): (M/dt + K) vTilde = F + M/dt v_prev + gammaFS D^T p_prev,
+ *   rows of bound / free nodes reduced to the identity, Dirichlet columns eliminated; qPrev = (v_prev, p_prev), (dim+1) nNodes.
+ *   Held in the node-block storage of the PSPG system with identity pressure rows: pfem_pspg_export_csc / pfem_pspg_matvec see it.
+ * 2 pressure: m_buildMatPcorrStep + m_applyBCPCorrStep (:124-130, 158-166, 300-376): L p = -(rho/dt) D vTilde + gammaFS L p_prev,
+ *   rows of free nodes reduced to the identity, zero right-hand side on free-surface nodes; vTilde dim nNodes, pPrev nNodes.
+ *   Scalar storage of the heat system: pfem_heat_export_csc sees the matrix, pfem_fs_get_rhs the right-hand side.
+ *   (The reference leaves this system singular -- DESIGN.md section 7; it is assembled for parity, pfem_fs_solve on it
+ *   returns PFEM_NOT_CONVERGED at the iteration cap like the reference's own solve.)
+ * 3 velocity correction: m_buildMatVStep + m_applyBCVStep (:76-83, 167-176, 378-452): M deltaV = dt D^T deltaP, identity rows
+ *   for bound / free nodes; the same scalar mass matrix for every component, right-hand side [d][nNodes]. */
+int pfem_fs_assemble_vapp(pfem_ctx* ctx, const pfem_pspg_params* p, double gammaFS, const double* qPrev);
+int pfem_fs_assemble_pcorr(pfem_ctx* ctx, double rho, double dt, double gammaFS, const double* vTilde, const double* pPrev);
+int pfem_fs_assemble_vcorr(pfem_ctx* ctx, double rho, double dt, const double* deltaP);
+int pfem_fs_get_rhs(pfem_ctx* ctx, double* b);
+/* x = m_solverIt.solve(b) on the system assembled last (:472-478, 491-497, 516-522): zero initial guess, diagonal
+ * preconditioner, stop at ||r||^2 < relTol^2 ||b||^2 (Eigen's default relTol is machine epsilon, its iteration cap 2 n);
+ * `iters` counts as Eigen's iterations() does.  x: dim nNodes (systems 1, 3: [d][nNodes]) or nNodes (system 2); may be NULL. */
+int pfem_fs_solve(pfem_ctx* ctx, double relTol, int maxIter, double* x, int* iters, double* relRes);
+
 /* ---- incompressible PSPG (MomContEqIncompNewton<dim>) ------------------------------- */
 /* m_buildAbPSPG + m_applyBCPSPG (PSPG.inl:7-146, 149-235; facet terms: pfem_set_surface_tension).  qPrev: (dim+1)*nNodes. */
 int pfem_pspg_assemble(pfem_ctx* ctx, const pfem_pspg_params* p, const double* qPrev);

@@ -78,6 +78,10 @@ def lib():
         L.pfem_ref_csc_copy.argtypes = [C.c_void_p, IP, C.POINTER(C.c_int32), DP, DP]
         L.pfem_ref_pspg_solve.argtypes = [C.c_void_p]
         L.pfem_ref_heat_solve.argtypes = [C.c_void_p]
+        L.pfem_ref_fs_build.restype = I64
+        L.pfem_ref_fs_build.argtypes = [C.c_void_p, C.c_int, DP, DP]
+        L.pfem_ref_fs_copy.argtypes = [C.c_void_p, C.c_int, IP, C.POINTER(C.c_int32), DP, DP]
+        L.pfem_ref_fs_solve.argtypes = [C.c_void_p, C.c_int, DP, DP]
         L.pfem_ref_in_heat_build.restype = I64
         L.pfem_ref_in_heat_build.argtypes = [C.c_void_p, DP, C.c_int]
         L.pfem_ref_in_heat_copy.argtypes = [C.c_void_p, IP, C.POINTER(C.c_int32), DP, DP]
@@ -268,6 +272,32 @@ class RefCase:
         n0 = lib().pfem_ref_direct_solves()
         ok = self._chk(lib().pfem_ref_pspg_solve(self._h), "pspg_solve")
         return bool(ok), lib().pfem_ref_direct_solves() - n0
+
+    def fs_build(self, which, a, b=None):
+        """FracStep sub-system `which` (0 velocity prediction: a = v_prev, b = p_prev; 1 pressure: a = vTilde, b = p_prev;
+        2 velocity correction: a = deltaP) built by the reference's own m_buildMat* + m_applyBC* (MomContEquationFracStep.inl).
+        Returns (A csc, rhs)."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        nnz = lib().pfem_ref_fs_build(self._h, int(which), _d(a), None if bb is None else _d(bb))
+        if nnz < 0:
+            raise RuntimeError(f"fs_build: {lib().pfem_ref_last_error().decode()}")
+        n = self.N if which == 1 else self.dim * self.N
+        col_ptr = np.zeros(n + 1, dtype=np.int64)
+        row_idx = np.zeros(nnz, dtype=np.int32)
+        val = np.zeros(nnz)
+        rhs = np.zeros(n)
+        lib().pfem_ref_fs_copy(self._h, int(which), col_ptr.ctypes.data_as(IP), row_idx.ctypes.data_as(C.POINTER(C.c_int32)), _d(val), _d(rhs))
+        return sp.csc_matrix((val, row_idx, col_ptr), shape=(n, n)), rhs
+
+    def fs_solve(self, which):
+        """m_solverIt.compute(A); x = m_solverIt.solve(b) on the sub-system last built (stand-in ConjugateGradient: Jacobi,
+        tolerance eps, 2n iterations).  Returns (x, iterations, error, info)."""
+        n = self.N if which == 1 else self.dim * self.N
+        x = np.zeros(n)
+        out = np.zeros(3)
+        self._chk(lib().pfem_ref_fs_solve(self._h, int(which), _d(x), _d(out)), "fs_solve")
+        return x, int(out[0]), float(out[1]), int(out[2])
 
     def heat_solve(self):
         """m_pEquations[1]->solve(): the heat equation of the incompressible Boussinesq problem (IN/Solver.cpp:249-258)."""

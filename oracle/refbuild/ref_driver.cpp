@@ -174,6 +174,65 @@ template <unsigned short dim> const Eigen::SparseMatrix<double>* heatBuildIN(Ref
     return &eq->m_A;
 }
 
+// FracStep sub-systems of MomContEquationFracStep.inl on the current mesh, run one at a time with given inputs:
+//   which 0: m_buildMatFracStep({a = v_prev (dim N), b = p_prev (N)}) + m_applyBCVAppStep(v_prev)  -> m_MK_dt, m_bVAppStep
+//   which 1: m_buildMatPcorrStep(a = vTilde, b = p_prev) + m_applyBCPCorrStep()                      -> m_L, m_bPcorrStep
+//            (uses m_DTelm / m_Lelm / m_L of the last which-0 build, as the Picard body does: :487-507)
+//   which 2: m_buildMatVStep(a = deltaP) + m_applyBCVStep()                                         -> m_M, m_bVStep
+template <unsigned short dim> struct FsView {
+    const Eigen::SparseMatrix<double>* A = nullptr;
+    const Eigen::VectorXd* b = nullptr;
+};
+template <unsigned short dim> FsView<dim> fsSystem(RefCase& rc, int which) {
+    FsView<dim> v;
+    auto* eq = dynamic_cast<MomContEqIncompNewton<dim>*>(rc.solver->m_pEquations[0].get());
+    if (!eq) return v;
+    if (which == 0) v.A = &eq->m_MK_dt, v.b = &eq->m_bVAppStep;
+    else if (which == 1) v.A = &eq->m_L, v.b = &eq->m_bPcorrStep;
+    else v.A = &eq->m_M, v.b = &eq->m_bVStep;
+    return v;
+}
+template <unsigned short dim> std::int64_t fsBuild(RefCase& rc, int which, const double* a, const double* b) {
+    auto* eq = dynamic_cast<MomContEqIncompNewton<dim>*>(rc.solver->m_pEquations[0].get());
+    if (!eq) return -1;
+    const Eigen::Index nV = static_cast<Eigen::Index>(dim * rc.N), nP = static_cast<Eigen::Index>(rc.N);
+    auto vec = [](const double* src, Eigen::Index n) {
+        Eigen::VectorXd q(n);
+        for (Eigen::Index i = 0; i < n; ++i) q[i] = src[i];
+        return q;
+    };
+    if (which == 0) {  // the "prepare" lambda of m_setupPicardFracStep (:454-462), then the head of its body (:468-470)
+        eq->m_M.resize(nV, nV);
+        eq->m_MK_dt.resize(nV, nV);
+        eq->m_L.resize(nP, nP);
+        eq->m_bVAppStep.resize(nV); eq->m_bVAppStep.setZero();
+        eq->m_bPcorrStep.resize(nP); eq->m_bPcorrStep.setZero();
+        eq->m_bVStep.resize(nV); eq->m_bVStep.setZero();
+        std::vector<Eigen::VectorXd> qPrev = {vec(a, nV), vec(b, nP)};
+        eq->m_buildMatFracStep(qPrev);
+        eq->m_applyBCVAppStep(qPrev[0]);
+    } else if (which == 1) {
+        eq->m_buildMatPcorrStep(vec(a, nV), vec(b, nP));
+        eq->m_applyBCPCorrStep();
+    } else {
+        eq->m_buildMatVStep(vec(a, nP));
+        eq->m_applyBCVStep();
+    }
+    return fsSystem<dim>(rc, which).A->nonZeros();
+}
+template <unsigned short dim> int fsSolve(RefCase& rc, int which, double* x, double* itersErrInfo) {
+    auto* eq = dynamic_cast<MomContEqIncompNewton<dim>*>(rc.solver->m_pEquations[0].get());
+    if (!eq) return -1;
+    const FsView<dim> v = fsSystem<dim>(rc, which);
+    eq->m_solverIt.compute(*v.A);                       // :472, :491, :516
+    const Eigen::VectorXd sol = eq->m_solverIt.solve(*v.b);
+    for (Eigen::Index i = 0; i < sol.rows(); ++i) x[i] = sol[i];
+    itersErrInfo[0] = static_cast<double>(eq->m_solverIt.iterations());
+    itersErrInfo[1] = static_cast<double>(eq->m_solverIt.error());
+    itersErrInfo[2] = static_cast<double>(eq->m_solverIt.info());
+    return 0;
+}
+
 template <unsigned short dim> int elementMatrices(RefCase& rc, double* M, double* K, double* D, double* L, double* C, double* F, double* H) {
     auto* eq = dynamic_cast<MomContEqIncompNewton<dim>*>(rc.solver->m_pEquations[0].get());
     if (!eq) return -1;
@@ -563,6 +622,48 @@ int pfem_ref_in_heat_copy(void* h, std::int64_t* colPtr, std::int32_t* rowIdx, d
     }
     for (Eigen::Index i = 0; i < b->rows(); ++i) bOut[i] = (*b)[i];
     return 0;
+}
+
+// FracStep sub-systems (see fsBuild): returns nnz or < 0; copy out with pfem_ref_fs_copy; solve with the equation's own
+// ConjugateGradient object (m_solverIt) through pfem_ref_fs_solve: out = (iterations, error, info)
+std::int64_t pfem_ref_fs_build(void* h, int which, const double* a, const double* b) {
+    auto& rc = *static_cast<RefCase*>(h);
+    try {
+        if (which == 0) rc.rebuildPositions();
+        return rc.dim == 2 ? fsBuild<2>(rc, which, a, b) : fsBuild<3>(rc, which, a, b);
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return -1;
+    }
+}
+int pfem_ref_fs_copy(void* h, int which, std::int64_t* colPtr, std::int32_t* rowIdx, double* val, double* bOut) {
+    auto& rc = *static_cast<RefCase*>(h);
+    const Eigen::SparseMatrix<double>* A;
+    const Eigen::VectorXd* b;
+    if (rc.dim == 2) {
+        const auto v = fsSystem<2>(rc, which);
+        A = v.A, b = v.b;
+    } else {
+        const auto v = fsSystem<3>(rc, which);
+        A = v.A, b = v.b;
+    }
+    if (!A) return -1;
+    for (Eigen::Index j = 0; j <= A->cols(); ++j) colPtr[j] = A->outerIndexPtr()[j];
+    for (Eigen::Index k = 0; k < A->nonZeros(); ++k) {
+        rowIdx[k] = A->innerIndexPtr()[k];
+        val[k] = A->valuePtr()[k];
+    }
+    for (Eigen::Index i = 0; i < b->rows(); ++i) bOut[i] = (*b)[i];
+    return 0;
+}
+int pfem_ref_fs_solve(void* h, int which, double* x, double* itersErrInfo) {
+    auto& rc = *static_cast<RefCase*>(h);
+    try {
+        return rc.dim == 2 ? fsSolve<2>(rc, which, x, itersErrInfo) : fsSolve<3>(rc, which, x, itersErrInfo);
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return -1;
+    }
 }
 
 // One PSPG time step of the equation: MomContEqIncompNewton::solve() = the Picard loop.  Returns 1 ok / 0 failed.

@@ -71,6 +71,11 @@ SYMBOLS = {
     "pfem_heat_assemble": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, C.c_double, _DP]),
     "pfem_heat_solve": (C.c_int, [_VP, C.c_double, C.c_int, _DP, C.POINTER(C.c_int), _DP]),
     "pfem_heat_export_csc": (C.c_int, [_VP, _I64P, _I32P, _I32P, _DP, _DP]),
+    "pfem_fs_assemble_vapp": (C.c_int, [_VP, C.POINTER(PspgParams), C.c_double, _DP]),
+    "pfem_fs_assemble_pcorr": (C.c_int, [_VP, C.c_double, C.c_double, C.c_double, _DP, _DP]),
+    "pfem_fs_assemble_vcorr": (C.c_int, [_VP, C.c_double, C.c_double, _DP]),
+    "pfem_fs_get_rhs": (C.c_int, [_VP, _DP]),
+    "pfem_fs_solve": (C.c_int, [_VP, C.c_double, C.c_int, _DP, C.POINTER(C.c_int), _DP]),
     "pfem_pspg_set_qprev": (C.c_int, [_VP, _DP]),
     "pfem_pspg_assemble": (C.c_int, [_VP, C.POINTER(PspgParams), _DP]),
     "pfem_pspg_assemble_resident": (C.c_int, [_VP, C.POINTER(PspgParams)]),
@@ -371,6 +376,34 @@ class PfemContext:
         self._chk(self._L.pfem_heat_export_csc(self._h, C.byref(nnz), col_ptr.ctypes.data_as(_I32P), row_idx.ctypes.data_as(_I32P),
                                                _dptr(val), _dptr(b)))
         return sp.csc_matrix((val, row_idx, col_ptr), shape=(n, n)), b
+
+    # -- fractional-step solver (FracStep): the three systems of one Picard body -------
+    def fs_assemble_vapp(self, params, gamma_fs, q_prev):
+        q = _f64(q_prev, self.n_dof)
+        self._chk(self._L.pfem_fs_assemble_vapp(self._h, C.byref(params), float(gamma_fs), _dptr(q)))
+
+    def fs_assemble_pcorr(self, rho, dt, gamma_fs, v_tilde, p_prev):
+        v = _f64(v_tilde, self.dim * self.n_nodes)
+        pp = _f64(p_prev, self.n_nodes)
+        self._chk(self._L.pfem_fs_assemble_pcorr(self._h, rho, dt, float(gamma_fs), _dptr(v), _dptr(pp)))
+
+    def fs_assemble_vcorr(self, rho, dt, delta_p):
+        dp = _f64(delta_p, self.n_nodes)
+        self._chk(self._L.pfem_fs_assemble_vcorr(self._h, rho, dt, _dptr(dp)))
+
+    def fs_get_rhs(self, which):
+        b = np.empty((self.dim if which == 2 else 1) * self.n_nodes)
+        self._chk(self._L.pfem_fs_get_rhs(self._h, _dptr(b)))
+        return b
+
+    def fs_solve(self, which, rel_tol=np.finfo(float).eps, max_iter=None):
+        """Eigen-style Jacobi-CG on the system assembled last; which = 0 | 1 | 2 only sizes the result."""
+        n = (1 if which == 1 else self.dim) * self.n_nodes
+        x = np.empty(n)
+        it, rr = C.c_int(0), C.c_double(0)
+        rc = self._chk(self._L.pfem_fs_solve(self._h, float(rel_tol), int(max_iter or 2 * n), _dptr(x), C.byref(it), C.byref(rr)),
+                       allow=(PFEM_NOT_CONVERGED, PFEM_NAN))
+        return dict(status=rc, x=x, iters=it.value, rel_res=rr.value)
 
     # -- PSPG ---------------------------------------------------------------------
     @staticmethod

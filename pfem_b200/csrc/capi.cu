@@ -254,6 +254,36 @@ int pfem_heat_export_csc(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* ro
     API_END(c)
 }
 
+int pfem_fs_assemble_vapp(pfem_ctx* c, const pfem_pspg_params* p, double gammaFS, const double* qPrev) {
+    API_BEGIN(c)
+    PFEM_REQUIRE(p, PFEM_ERR_INVALID, "fs_assemble_vapp: params is null");
+    fsAssembleVapp(c, *p, gammaFS, qPrev);
+    API_END(c)
+}
+int pfem_fs_assemble_pcorr(pfem_ctx* c, double rho, double dt, double gammaFS, const double* vTilde, const double* pPrev) {
+    API_BEGIN(c)
+    fsAssemblePcorr(c, rho, dt, gammaFS, vTilde, pPrev);
+    API_END(c)
+}
+int pfem_fs_assemble_vcorr(pfem_ctx* c, double rho, double dt, const double* deltaP) {
+    API_BEGIN(c)
+    fsAssembleVcorr(c, rho, dt, deltaP);
+    API_END(c)
+}
+int pfem_fs_get_rhs(pfem_ctx* c, double* b) {
+    API_BEGIN(c)
+    fsGetRhs(c, b);
+    API_END(c)
+}
+int pfem_fs_solve(pfem_ctx* c, double relTol, int maxIter, double* x, int* iters, double* relRes) {
+    if (!c) return PFEM_ERR_INVALID;
+    try {
+        cudaSetDevice(c->device);
+        c->cflFresh = false;
+        return fsSolve(c, relTol, maxIter, x, iters, relRes);
+    } API_CATCH(c)
+}
+
 int pfem_pspg_set_qprev(pfem_ctx* c, const double* qPrev) {
     API_BEGIN(c)
     fieldsSetQprev(c, qPrev);

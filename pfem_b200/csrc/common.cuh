@@ -153,6 +153,10 @@ struct pfem_ctx {
     double asmStamp = 0.0;     // dt of the assembled system (the multigrid dampings are re-tuned when it changes)
     DevBuf<double> kx, kr, kr0, kp, kp2, kv, ks, kt, kph, ksh;  // Krylov vectors (internal dof order)
     DevBuf<double> partial;    // PS_COUNT * reduceBlocks
+    DevBuf<double> fsVec;      // fractional-step systems: vTilde input / scalar-system solution, [d][nNodes]
+    DevBuf<uint8_t> fsMask;    // row mask of the scalar systems (zero: pressure; bound nodes: velocity correction)
+    const uint8_t* heatMask = nullptr;  // the Dirichlet-row mask the scalar system in hA was assembled with
+    int fsWhich = -1;          // fractional-step system assembled last (0 velocity prediction, 1 pressure, 2 velocity correction)
     bool mgFlexible = false;   // the Krylov method tolerates a slightly non-linear preconditioner (FGMRES): fp32 cycle vectors
     DevBuf<double> gmV, gmZ;   // FGMRES: orthonormal basis (owned dofs) and preconditioned directions (owned + ghost dofs)
     DevBuf<double> gmBank;     // (restart + 2) * reduceBlocks partial dot products
@@ -336,6 +340,11 @@ void thermalPrepare(pfem_ctx* c);
 void heatAssemble(pfem_ctx* c, double rho, double cv, double k, double dt, const double* thetaPrevHost);
 int heatSolve(pfem_ctx* c, double relTol, int maxIter, double* Tout, int* itersOut, double* relResOut);
 void heatExport(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, double* val, double* b);
+void fsAssembleVapp(pfem_ctx* c, const pfem_pspg_params& p, double gammaFS, const double* qPrevHost);
+void fsAssemblePcorr(pfem_ctx* c, double rho, double dt, double gammaFS, const double* vTildeHost, const double* pPrevHost);
+void fsAssembleVcorr(pfem_ctx* c, double rho, double dt, const double* deltaPHost);
+void fsGetRhs(pfem_ctx* c, double* b);
+int fsSolve(pfem_ctx* c, double relTol, int maxIter, double* xHost, int* itersOut, double* relResOut);
 // facets.cu
 void facetsSet(pfem_ctx* c, int64_t nFacets, const uint64_t* facetNodes, const uint64_t* outNode, const uint64_t* elemIndex);
 const double* facetsForces(pfem_ctx* c, const double* X4, bool allNodesRule);  // null when the facet terms are off

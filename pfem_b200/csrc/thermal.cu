@@ -105,6 +105,11 @@ struct GenArgs {
     double tau0, mReg;   // Bingham (bingham != 0)
     double alpha, Tr;    // Boussinesq (T != null)
     int bingham;
+    // mode 1: velocity-prediction system of the fractional-step solver (MomContEquationFracStep.inl:8-217): M/dt + K on the
+    // velocity rows, identity pressure rows, b = F + M/dt v_prev + gammaFS D^T p_prev
+    int mode = 0;
+    double gammaFS = 0.0;
+    const double* pPrev = nullptr;
 };
 
 // tau (PSPG.inl:238-259) and the element viscosity
@@ -211,15 +216,17 @@ __global__ void __launch_bounds__(128) k_gen_blocks(const GenArgs a) {
 #pragma unroll
             for (int c = 0; c < DIM; ++c) acc[aa][c] += muE * V * gi[c] * gj[aa];
             acc[aa][aa] += cm + muE * V * dot;
-            acc[aa][DIM] -= (V / NPE) * gi[aa];
-            acc[DIM][aa] += (V / NPE) * ((tau / a.dt) * gi[aa] + gj[aa]);
+            if (a.mode == 0) {
+                acc[aa][DIM] -= (V / NPE) * gi[aa];
+                acc[DIM][aa] += (V / NPE) * ((tau / a.dt) * gi[aa] + gj[aa]);
+            }
         }
-        acc[DIM][DIM] += tau * (V / a.rho) * dot;
+        if (a.mode == 0) acc[DIM][DIM] += tau * (V / a.rho) * dot;
     }
     const bool diag = (s == a.diagSlot[i]);
 #pragma unroll
     for (int r = 0; r < BS; ++r) {
-        const bool rowMasked = (r < DIM) ? maskV : maskP;
+        const bool rowMasked = (r < DIM) ? maskV : (maskP || a.mode == 1);
 #pragma unroll
         for (int c = 0; c < BS; ++c) {
             double v = acc[r][c];
@@ -282,16 +289,26 @@ __global__ void __launch_bounds__(128) k_gen_rhs_bc(const GenArgs a) {
         }
         const double V = G.V, cmass = a.rho * V * PHI / a.dt;
         double gb = 0, gs = 0;
+        double sumP = 0;
+        if (a.mode == 1) {
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) sumP += a.pPrev[nd[m]];
+        }
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
             gb += gi[d] * a.body[d];
             gs += gi[d] * sv[d];
             bi[d] += V * a.body[d] * fF + cmass * (vpi[d] + sv[d]);
+            if (a.mode == 1) bi[d] += a.gammaFS * (V / NPE) * gi[d] * sumP;  // gammaFS D^T p_prev (FracStep.inl:61, 146-147)
         }
-        bi[DIM] += tau * V * gb * fH + (tau / a.dt) * (V / NPE) * gs;
+        if (a.mode == 0) bi[DIM] += tau * V * gb * fH + (tau / a.dt) * (V / NPE) * gs;
     }
     const uint8_t fl = a.flags[i];
     const bool isBound = fl & PFEM_NODE_BOUND, isFree = fl & PFEM_NODE_FREE;
+    if (a.mode == 1 && (isBound || isFree)) {  // FracStep.inl:138-150: nothing is assembled into the rows of bound / free nodes
+#pragma unroll
+        for (int r = 0; r < BS; ++r) bi[r] = 0;
+    }
     if (a.fst4)
 #pragma unroll
         for (int d = 0; d < DIM; ++d) bi[d] += a.fst4[(size_t)i * 4 + d];
@@ -319,6 +336,7 @@ __global__ void __launch_bounds__(128) k_gen_rhs_bc(const GenArgs a) {
             if (r == DIM) bv = 0.0;
             else if (!isBound) bv = a.VP4[(size_t)i * 4 + r] + a.dt * a.body[r];
         }
+        if (a.mode == 1 && r == DIM) bv = 0.0;
         if (isBound && a.dirMask[i] && r < DIM) bv = a.dirVal4[(size_t)i * 4 + r];
         a.b[(size_t)i * BS + r] = bv;
         const double d = a.Aval[((size_t)nb0 + si) * BS * BS + r * BS + r];
@@ -546,6 +564,136 @@ __global__ void __launch_bounds__(128) k_wc_heat(int nRows, const int* __restric
     Tnew[i] = inv * F;
 }
 
+// ---- fractional-step solver: pressure and velocity-correction right-hand sides ----------------------------------------------
+// b_p (MomContEquationFracStep.inl:300-347 + m_applyBCPCorrStep :349-376): rows of nodes that are neither free nor on the free
+// surface get -(rho/dt) (D vTilde)_i + gammaFS (L p_prev)_i summed over their elements in ascending order, the others 0.
+// vT: vTilde as [d][nNodes]
+template <int DIM>
+__global__ void __launch_bounds__(128) k_fs_pcorr_rhs(int nRows, int nNodes, const int* __restrict__ conn, const int* __restrict__ n2ePtr,
+                                                       const int* __restrict__ n2e, const uint8_t* __restrict__ flags,
+                                                       const double* __restrict__ X4, const double* __restrict__ vT,
+                                                       const double* __restrict__ pPrev, double rhoOverDt, double gammaFS,
+                                                       double* __restrict__ b) {
+    constexpr int NPE = DIM + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRows) return;
+    const uint8_t fl = flags[i];
+    double bi = 0;
+    if (!(fl & (PFEM_NODE_FREE | PFEM_NODE_FREE_SURFACE))) {
+        const int eb = n2ePtr[i], ne = n2ePtr[i + 1] - eb;
+        for (int k = 0; k < ne; ++k) {
+            const int e = n2e[eb + k];
+            int nd[NPE];
+            loadConn<DIM>(conn, e, nd);
+            int li = 0;
+#pragma unroll
+            for (int m = 1; m < NPE; ++m) li = (nd[m] == i) ? m : li;
+            GElem<DIM> G;
+            elemGeo<DIM>(X4, nd, G);
+            double gi[DIM], div = 0, lp = 0;
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                gi[d] = G.g[0][d];
+#pragma unroll
+                for (int m = 1; m < NPE; ++m) gi[d] = (li == m) ? G.g[m][d] : gi[d];
+            }
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) {
+                double dot = 0;
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) {
+                    div += G.g[m][d] * vT[(size_t)d * nNodes + nd[m]];
+                    dot += gi[d] * G.g[m][d];
+                }
+                lp += dot * pPrev[nd[m]];
+            }
+            bi += -rhoOverDt * (G.V / NPE) * div + gammaFS * G.V * lp;
+        }
+    }
+    b[i] = bi;
+}
+// b_v (FracStep.inl:378-452): rows of nodes that are neither free nor bound get dt (D^T deltaP)_(i,d), the others 0; b as [d][nNodes]
+template <int DIM>
+__global__ void __launch_bounds__(128) k_fs_vcorr_rhs(int nRows, int nNodes, const int* __restrict__ conn, const int* __restrict__ n2ePtr,
+                                                       const int* __restrict__ n2e, const uint8_t* __restrict__ flags,
+                                                       const double* __restrict__ X4, const double* __restrict__ dP, double dt,
+                                                       double* __restrict__ b) {
+    constexpr int NPE = DIM + 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRows) return;
+    double bi[DIM];
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) bi[d] = 0;
+    if (!(flags[i] & (PFEM_NODE_FREE | PFEM_NODE_BOUND))) {
+        const int eb = n2ePtr[i], ne = n2ePtr[i + 1] - eb;
+        for (int k = 0; k < ne; ++k) {
+            const int e = n2e[eb + k];
+            int nd[NPE];
+            loadConn<DIM>(conn, e, nd);
+            int li = 0;
+#pragma unroll
+            for (int m = 1; m < NPE; ++m) li = (nd[m] == i) ? m : li;
+            GElem<DIM> G;
+            elemGeo<DIM>(X4, nd, G);
+            double sp = 0;
+#pragma unroll
+            for (int m = 0; m < NPE; ++m) sp += dP[nd[m]];
+#pragma unroll
+            for (int d = 0; d < DIM; ++d) {
+                double gi = G.g[0][d];
+#pragma unroll
+                for (int m = 1; m < NPE; ++m) gi = (li == m) ? G.g[m][d] : gi;
+                bi[d] += dt * (G.V / NPE) * gi * sp;
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; ++d) b[(size_t)d * nNodes + i] = bi[d];
+}
+// m_applyBCPCorrStep / m_applyBCVStep walk the COLUMN of every masked node (Eigen's InnerIterator on a column-major matrix):
+// diagonal 1, the other entries of the column 0 (FracStep.inl:359-371, 436-447); the rows were never assembled (identity)
+__global__ void k_fs_zero_cols(int nRows, const int* __restrict__ nbrPtr, const int* __restrict__ nbr, const int* __restrict__ diagSlot,
+                               const uint8_t* __restrict__ mask, const uint8_t* __restrict__ flags, double* __restrict__ A) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nRows) return;
+    const int nb0 = nbrPtr[i], nb = nbrPtr[i + 1] - nb0, si = diagSlot[i];
+    for (int s = 0; s < nb; ++s) {
+        if (s == si) continue;
+        const int j = nbr[nb0 + s];
+        if (mask[j] || (flags[j] & PFEM_NODE_FREE)) A[(size_t)nb0 + s] = 0.0;
+    }
+}
+__global__ void k_fs_bound_mask(int n, const uint8_t* __restrict__ flags, uint8_t* __restrict__ mask) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mask[i] = (flags[i] & PFEM_NODE_BOUND) ? 1 : 0;
+}
+// 1 / diagonal of the node-block system (Eigen::DiagonalPreconditioner), internal dof order node*BS + r
+__global__ void k_fs_block_dinv(int nNodes, int BS, const int* __restrict__ nbrPtr, const int* __restrict__ diagSlot,
+                                const double* __restrict__ Aval, double* __restrict__ dinv) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nNodes * BS) return;
+    const int i = t / BS, r = t % BS;
+    const double d = Aval[((size_t)nbrPtr[i] + diagSlot[i]) * BS * BS + r * BS + r];
+    dinv[t] = d != 0.0 ? 1.0 / d : 1.0;
+}
+__global__ void k_fs_scalar_dinv(int n, int comps, const int* __restrict__ ptr, const int* __restrict__ diag, const double* __restrict__ A,
+                                 double* __restrict__ dinv) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double d = A[ptr[i] + diag[i]];
+    const double v = d != 0.0 ? 1.0 / d : 1.0;
+    for (int cc = 0; cc < comps; ++cc) dinv[(size_t)cc * n + i] = v;
+}
+// r = b - Ax ; p = dinv r   (start of Eigen's conjugate_gradient)
+__global__ void k_cgg_init(int n, const double* __restrict__ b, const double* __restrict__ Ax, const double* __restrict__ dinv,
+                           double* __restrict__ r, double* __restrict__ p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ri = b[i] - Ax[i];
+    r[i] = ri;
+    p[i] = dinv[i] * ri;
+}
+
 GenArgs makeGenArgs(pfem_ctx* c, const pfem_pspg_params& p) {
     GenArgs a;
     a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.blkMask = c->blkMask.p, a.nbrPtr = c->nbrPtr.p, a.nbr = c->nbr.p;
@@ -654,6 +802,7 @@ void heatAssemble(pfem_ctx* c, double rho, double cv, double k, double dt, const
     a.diagSlot = c->diagSlot.p, a.flags = c->flags.p, a.tMask = c->tMask.p, a.tVal = c->tVal.p, a.X4 = c->X4.p;
     a.thetaPrev = c->hTheta.p, a.A = c->hA.p, a.b = c->hb.p, a.nRows = n, a.CH = c->maskWords;
     a.rhoCv = cv * rho, a.k = k, a.dt = dt;
+    c->heatMask = c->tMask.p;
     PhaseScope ph(c, "Assemble heat system");
     if (c->dim == 2) {
         k_heat_blocks<2><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
@@ -755,7 +904,7 @@ void heatExport(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, dou
     CUDA_CHECK(cudaMemcpyAsync(A.data(), c->hA.p, (size_t)c->nBlocks * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(bb.data(), c->hb.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaMemcpyAsync(fl.data(), c->flags.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaMemcpyAsync(tm.data(), c->tMask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(tm.data(), c->heatMask ? c->heatMask : c->tMask.p, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CUDA_CHECK(cudaStreamSynchronize(c->stream));
     // entry (i, j) exists when row i is unmasked, or i == j; the pattern is symmetric in (i, j), so column j lists the
     // neighbours i of j that qualify (ascending: nbr lists are sorted)
@@ -784,4 +933,244 @@ void heatExport(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, dou
     }
     colPtr[n] = (int32_t)o;
     for (int i = 0; i < n; ++i) b[i] = bb[i];
+}
+
+// ---- fractional-step solver id "FracStep" (MomContEquationFracStep.inl) ---------------------------------------
+// The three linear systems of one Picard body (:464-548), each assembled on the device from given inputs, and Eigen's
+// Jacobi-preconditioned conjugate gradients for them.  Single-GPU contexts, gamma = 0 (no surface-tension facet term).
+namespace {
+// Eigen::ConjugateGradient (ConjugateGradient.h, conjugate_gradient()): zero initial guess, diagonal preconditioner, stops when
+// ||r||^2 < max(tol^2 ||b||^2, DBL_MIN); `iterations` as Eigen counts them: the pass that reaches the threshold is not counted.
+template <class Spmv>
+int cgEigen(pfem_ctx* c, int n, Spmv spmv, const double* dinv, const double* b, double* x, double relTol, int maxIter, int* itersOut,
+            double* relResOut) {
+    const int g = divUp(n, 256), nb = std::max(1, std::min(c->smCount * 4, g));
+    for (auto* v : {&c->cgR, &c->cgZ, &c->cgP, &c->cgAp}) v->reserve((size_t)n + 8);
+    c->partial.reserve((size_t)nb + 16);
+    c->scal.reserve(SC_COUNT);
+    if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
+    double* S = c->scal.p;
+    auto dot = [&](const double* a, const double* bb, int slot) {
+        k_s_dot<<<nb, 256, 0, c->stream>>>(n, a, bb, c->partial.p);
+        LAUNCH_CHECK(c);
+        k_s_dot_final<<<1, 32, 0, c->stream>>>(c->partial.p, nb, S + slot);
+        LAUNCH_CHECK(c);
+    };
+    auto fetch = [&]() {
+        CUDA_CHECK(cudaMemcpyAsync(c->hScal, S, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    };
+    CUDA_CHECK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), c->stream));
+    CUDA_CHECK(cudaMemsetAsync(c->cgAp.p, 0, (size_t)n * sizeof(double), c->stream));
+    k_cgg_init<<<g, 256, 0, c->stream>>>(n, b, c->cgAp.p, dinv, c->cgR.p, c->cgP.p);
+    LAUNCH_CHECK(c);
+    dot(c->cgR.p, c->cgP.p, 0);  // absNew = r . p
+    dot(c->cgR.p, c->cgR.p, 3);
+    dot(b, b, 4);
+    fetch();
+    const double bb = c->hScal[4];
+    double rr = c->hScal[3];
+    int it = 0, status = PFEM_OK;
+    if (bb == 0.0) rr = 0;  // x = 0
+    else {
+        const double thr = std::max(relTol * relTol * bb, 2.2250738585072014e-308);
+        if (!(rr < thr)) {
+            while (it < maxIter) {
+                spmv(c->cgP.p, c->cgAp.p);
+                dot(c->cgP.p, c->cgAp.p, 1);
+                k_cg_update_xr<<<g, 256, 0, c->stream>>>(n, S, c->cgP.p, c->cgAp.p, dinv, x, c->cgR.p, c->cgZ.p);
+                LAUNCH_CHECK(c);
+                dot(c->cgR.p, c->cgR.p, 3);
+                dot(c->cgR.p, c->cgZ.p, 2);
+                fetch();
+                rr = c->hScal[3];
+                if (!(rr == rr)) {
+                    status = PFEM_NAN;
+                    break;
+                }
+                if (rr < thr) break;
+                k_cg_update_p<<<g, 256, 0, c->stream>>>(n, S, c->cgZ.p, c->cgP.p);
+                LAUNCH_CHECK(c);
+                k_cg_shift<<<1, 32, 0, c->stream>>>(S);
+                LAUNCH_CHECK(c);
+                ++it;
+            }
+            if (status == PFEM_OK && !(rr < thr)) status = PFEM_NOT_CONVERGED;
+        }
+    }
+    if (itersOut) *itersOut = it;
+    if (relResOut) *relResOut = bb > 0 ? sqrt(rr / bb) : 0.0;
+    return status;
+}
+void fsRequire(pfem_ctx* c, const char* what) {
+    PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, std::string(what) + ": topology/positions missing");
+    PFEM_REQUIRE(c->nRanks == 1, PFEM_ERR_STATE, std::string(what) + ": single-GPU contexts");
+    PFEM_REQUIRE(c->gammaST < 1e-15, PFEM_ERR_STATE, std::string(what) + ": the fractional-step systems carry no surface-tension term (gamma must be 0)");
+}
+HeatArgs fsHeatArgs(pfem_ctx* c, const uint8_t* mask) {
+    HeatArgs a;
+    a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.blkMask = c->blkMask.p, a.nbrPtr = c->nbrPtr.p, a.nbr = c->nbr.p;
+    a.diagSlot = c->diagSlot.p, a.flags = c->flags.p, a.tMask = mask, a.tVal = nullptr, a.X4 = c->X4.p;
+    a.thetaPrev = nullptr, a.A = c->hA.p, a.b = nullptr, a.nRows = c->nNodes, a.CH = c->maskWords;
+    a.rhoCv = 0, a.k = 0, a.dt = 1;
+    return a;
+}
+}  // namespace
+
+// system 1: (M/dt + K) vTilde = F + M/dt v_prev + gammaFS D^T p_prev with m_applyBCVAppStep (FracStep.inl:8-298), held in the
+// node-block storage of the PSPG system with identity pressure rows: pfem_pspg_export_csc / pfem_pspg_matvec see it
+void fsAssembleVapp(pfem_ctx* c, const pfem_pspg_params& p, double gammaFS, const double* qPrevHost) {
+    fsRequire(c, "fs_assemble_vapp");
+    PFEM_REQUIRE(qPrevHost && p.dt > 0 && p.rho > 0, PFEM_ERR_INVALID, "fs_assemble_vapp: bad arguments");
+    PFEM_REQUIRE(!c->thermalOn, PFEM_ERR_STATE, "fs_assemble_vapp: Boussinesq factors are not taken over for FracStep");
+    const int BS = c->dim + 1, n = c->nNodes;
+    c->Aval.reserve((size_t)c->nBlocks * BS * BS);
+    c->bvec.reserve((size_t)n * BS);
+    c->dinv.reserve((size_t)n * BS);
+    c->hTheta.reserve((size_t)n + 4);
+    fieldsSetQprev(c, qPrevHost);  // velocity part -> VP4
+    CUDA_CHECK(cudaMemcpyAsync(c->hTheta.p, qPrevHost + (size_t)c->dim * n, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    GenArgs a = makeGenArgs(c, p);
+    a.T = nullptr;
+    a.mode = 1, a.gammaFS = gammaFS, a.pPrev = c->hTheta.p;
+    PhaseScope ph(c, "Assemble system");
+    if (c->dim == 2) {
+        k_gen_blocks<2><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_gen_rhs_bc<2><<<divUp(n, 128), 128, 0, c->stream>>>(a);
+    } else {
+        k_gen_blocks<3><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_gen_rhs_bc<3><<<divUp(n, 128), 128, 0, c->stream>>>(a);
+    }
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->haveSystem = true;
+    c->haveSolution = false;
+    mgInvalidate(c, false);
+    c->asmStamp = p.dt;
+    c->fsWhich = 0;
+}
+// system 2: L p = -(rho/dt) D vTilde + gammaFS L p_prev with m_applyBCPCorrStep (FracStep.inl:124-130, 158-166, 300-376), scalar
+// system in the storage of the heat equation: pfem_heat_export_csc sees it
+void fsAssemblePcorr(pfem_ctx* c, double rho, double dt, double gammaFS, const double* vTildeHost, const double* pPrevHost) {
+    fsRequire(c, "fs_assemble_pcorr");
+    PFEM_REQUIRE(vTildeHost && pPrevHost && dt > 0 && rho > 0, PFEM_ERR_INVALID, "fs_assemble_pcorr: bad arguments");
+    const int n = c->nNodes, dim = c->dim;
+    c->hA.reserve((size_t)c->nBlocks + 4);
+    c->hb.reserve((size_t)dim * n + 4);
+    c->hTheta.reserve((size_t)n + 4);
+    c->fsVec.reserve((size_t)dim * n + 4);
+    c->fsMask.reserve((size_t)n + 4);
+    CUDA_CHECK(cudaMemsetAsync(c->fsMask.p, 0, (size_t)n, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->fsVec.p, vTildeHost, (size_t)dim * n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CUDA_CHECK(cudaMemcpyAsync(c->hTheta.p, pPrevHost, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    HeatArgs a = fsHeatArgs(c, c->fsMask.p);
+    a.k = 1.0;  // L with factor 1 (MomContEquation.inl:154-158)
+    PhaseScope ph(c, "Assemble system");
+    if (dim == 2) {
+        k_heat_blocks<2><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_fs_zero_cols<<<divUp(n, 128), 128, 0, c->stream>>>(n, c->nbrPtr.p, c->nbr.p, c->diagSlot.p, c->fsMask.p, c->flags.p, c->hA.p);
+        LAUNCH_CHECK(c);
+        k_fs_pcorr_rhs<2><<<divUp(n, 128), 128, 0, c->stream>>>(n, n, c->conn.p, c->n2ePtr.p, c->n2e.p, c->flags.p, c->X4.p, c->fsVec.p,
+                                                               c->hTheta.p, rho / dt, gammaFS, c->hb.p);
+    } else {
+        k_heat_blocks<3><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_fs_zero_cols<<<divUp(n, 128), 128, 0, c->stream>>>(n, c->nbrPtr.p, c->nbr.p, c->diagSlot.p, c->fsMask.p, c->flags.p, c->hA.p);
+        LAUNCH_CHECK(c);
+        k_fs_pcorr_rhs<3><<<divUp(n, 128), 128, 0, c->stream>>>(n, n, c->conn.p, c->n2ePtr.p, c->n2e.p, c->flags.p, c->X4.p, c->fsVec.p,
+                                                               c->hTheta.p, rho / dt, gammaFS, c->hb.p);
+    }
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->heatMask = c->fsMask.p;
+    c->haveHeatSystem = true;
+    c->fsWhich = 1;
+}
+// system 3: M deltaV = dt D^T deltaP with m_applyBCVStep (FracStep.inl:76-83, 167-176, 378-452): the scalar consistent mass
+// matrix (factor rho, identity rows for bound / free nodes) for every velocity component, right-hand side [d][nNodes]
+void fsAssembleVcorr(pfem_ctx* c, double rho, double dt, const double* deltaPHost) {
+    fsRequire(c, "fs_assemble_vcorr");
+    PFEM_REQUIRE(deltaPHost && dt > 0 && rho > 0, PFEM_ERR_INVALID, "fs_assemble_vcorr: bad arguments");
+    const int n = c->nNodes, dim = c->dim;
+    c->hA.reserve((size_t)c->nBlocks + 4);
+    c->hb.reserve((size_t)dim * n + 4);
+    c->hTheta.reserve((size_t)n + 4);
+    c->fsMask.reserve((size_t)n + 4);
+    k_fs_bound_mask<<<divUp(n, 256), 256, 0, c->stream>>>(n, c->flags.p, c->fsMask.p);
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaMemcpyAsync(c->hTheta.p, deltaPHost, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    HeatArgs a = fsHeatArgs(c, c->fsMask.p);
+    a.rhoCv = rho;  // M with factor rho (MomContEquation.inl:96-99)
+    PhaseScope ph(c, "Assemble system");
+    if (dim == 2) {
+        k_heat_blocks<2><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_fs_zero_cols<<<divUp(n, 128), 128, 0, c->stream>>>(n, c->nbrPtr.p, c->nbr.p, c->diagSlot.p, c->fsMask.p, c->flags.p, c->hA.p);
+        LAUNCH_CHECK(c);
+        k_fs_vcorr_rhs<2><<<divUp(n, 128), 128, 0, c->stream>>>(n, n, c->conn.p, c->n2ePtr.p, c->n2e.p, c->flags.p, c->X4.p, c->hTheta.p, dt, c->hb.p);
+    } else {
+        k_heat_blocks<3><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
+        k_fs_zero_cols<<<divUp(n, 128), 128, 0, c->stream>>>(n, c->nbrPtr.p, c->nbr.p, c->diagSlot.p, c->fsMask.p, c->flags.p, c->hA.p);
+        LAUNCH_CHECK(c);
+        k_fs_vcorr_rhs<3><<<divUp(n, 128), 128, 0, c->stream>>>(n, n, c->conn.p, c->n2ePtr.p, c->n2e.p, c->flags.p, c->X4.p, c->hTheta.p, dt, c->hb.p);
+    }
+    LAUNCH_CHECK(c);
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    c->heatMask = c->fsMask.p;
+    c->haveHeatSystem = true;
+    c->fsWhich = 2;
+}
+// right-hand side of the scalar-storage systems (2: nNodes values, 3: dim * nNodes as [d][nNodes])
+void fsGetRhs(pfem_ctx* c, double* b) {
+    PFEM_REQUIRE(b && (c->fsWhich == 1 || c->fsWhich == 2) && c->haveHeatSystem, PFEM_ERR_STATE, "fs_get_rhs: assemble system 2 or 3 first");
+    const size_t n = (size_t)(c->fsWhich == 2 ? c->dim : 1) * c->nNodes;
+    CUDA_CHECK(cudaMemcpyAsync(b, c->hb.p, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_CHECK(cudaStreamSynchronize(c->stream));
+}
+// m_solverIt.compute(A); x = m_solverIt.solve(b) on the system assembled last (FracStep.inl:472-478, 491-497, 516-522)
+int fsSolve(pfem_ctx* c, double relTol, int maxIter, double* xHost, int* itersOut, double* relResOut) {
+    PFEM_REQUIRE(c->fsWhich >= 0, PFEM_ERR_STATE, "fs_solve: no fractional-step system assembled");
+    PFEM_REQUIRE(relTol > 0 && maxIter > 0, PFEM_ERR_INVALID, "fs_solve: relTol and maxIter must be positive");
+    PhaseScope ph(c, "Solve system");
+    const int N = c->nNodes, dim = c->dim;
+    int status;
+    if (c->fsWhich == 0) {  // node-block system, internal dof order node*BS + d (pressure entries stay 0: identity rows, b = 0)
+        PFEM_REQUIRE(c->haveSystem, PFEM_ERR_STATE, "fs_solve: system 1 is gone (another assembly ran)");
+        const int BS = dim + 1, n = N * BS;
+        c->cgD.reserve((size_t)n + 8);
+        c->kx.reserve((size_t)n + 8);
+        k_fs_block_dinv<<<divUp(n, 256), 256, 0, c->stream>>>(N, BS, c->nbrPtr.p, c->diagSlot.p, c->Aval.p, c->cgD.p);
+        LAUNCH_CHECK(c);
+        status = cgEigen(c, n, [&](double* x, double* y) { krylovMatvec(c, x, y); }, c->cgD.p, c->bvec.p, c->kx.p, relTol, maxIter,
+                         itersOut, relResOut);
+        c->haveSolution = true;
+        if (xHost) {  // velocity part, [d][nNodes]
+            std::vector<double> q((size_t)n);
+            krylovStoreVector(c, c->kx.p, q.data());
+            std::copy(q.begin(), q.begin() + (size_t)dim * N, xHost);
+        }
+        return status;
+    }
+    PFEM_REQUIRE(c->haveHeatSystem, PFEM_ERR_STATE, "fs_solve: the scalar system is gone");
+    const int comps = c->fsWhich == 2 ? dim : 1, n = N * comps;
+    c->cgD.reserve((size_t)n + 8);
+    c->fsVec.reserve((size_t)dim * N + 4);
+    k_fs_scalar_dinv<<<divUp(N, 256), 256, 0, c->stream>>>(N, comps, c->nbrPtr.p, c->diagSlot.p, c->hA.p, c->cgD.p);
+    LAUNCH_CHECK(c);
+    auto spmv = [&](double* x, double* y) {
+        for (int cc = 0; cc < comps; ++cc) {
+            k_s_spmv<<<divUp(N, 256), 256, 0, c->stream>>>(N, c->nbrPtr.p, c->nbr.p, c->hA.p, x + (size_t)cc * N, y + (size_t)cc * N);
+            LAUNCH_CHECK(c);
+        }
+    };
+    status = cgEigen(c, n, spmv, c->cgD.p, c->hb.p, c->fsVec.p, relTol, maxIter, itersOut, relResOut);
+    if (xHost) {
+        CUDA_CHECK(cudaMemcpyAsync(xHost, c->fsVec.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+    }
+    return status;
 }
