@@ -15,6 +15,7 @@
 // kernel (pspg.cu) covers the constant-factor problem of the named configurations; problems with these factors take
 // this path (about 10x slower at C4).
 #include "common.cuh"
+#include "spmv.cuh"
 
 namespace {
 
@@ -441,71 +442,120 @@ template <int DIM> __global__ void __launch_bounds__(128) k_heat_rhs_bc(const He
     a.b[i] = bi;
 }
 
-// ---- Jacobi-preconditioned conjugate gradients on the scalar node-pattern matrix ------------------------------------------------
-__global__ void k_s_spmv(int n, const int* __restrict__ ptr, const int* __restrict__ col, const double* __restrict__ A,
-                         const double* __restrict__ x, double* __restrict__ y) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    double s = 0;
-    for (int k = ptr[i]; k < ptr[i + 1]; ++k) s += A[k] * x[col[k]];
-    y[i] = s;
-}
-// partial[blockIdx] = sum_i a_i b_i (fixed grid, fixed order)
-__global__ void __launch_bounds__(256) k_s_dot(int n, const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ partial) {
-    __shared__ double sh[8];
-    double s = 0;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += a[i] * b[i];
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0;
-        for (int k = 0; k < 8; ++k) t += sh[k];
-        partial[blockIdx.x] = t;
-    }
-}
-__global__ void k_s_dot_final(const double* __restrict__ partial, int nb, double* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double t = 0;
-        for (int k = 0; k < nb; ++k) t += partial[k];
-        *out = t;
-    }
-}
-// scal: [0] rho = r.z, [1] p.Ap, [2] rho_new, [3] ||r||^2, [4] ||b||^2
-__global__ void k_cg_init(int n, const int* __restrict__ ptr, const int* __restrict__ diag, const double* __restrict__ A,
-                          const double* __restrict__ b, const double* __restrict__ Ax, double* __restrict__ r, double* __restrict__ z,
-                          double* __restrict__ p, double* __restrict__ dinv) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double d = A[ptr[i] + diag[i]];
-    const double di = d != 0.0 ? 1.0 / d : 1.0;  // Eigen::DiagonalPreconditioner
-    dinv[i] = di;
-    const double ri = b[i] - Ax[i];
-    r[i] = ri;
-    z[i] = di * ri;
-    p[i] = di * ri;
-}
-__global__ void k_cg_update_xr(int n, const double* __restrict__ scal, const double* __restrict__ p, const double* __restrict__ Ap,
-                               const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r, double* __restrict__ z) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double alpha = scal[0] / scal[1];
-    x[i] += alpha * p[i];
-    const double ri = r[i] - alpha * Ap[i];
-    r[i] = ri;
-    z[i] = dinv[i] * ri;
-}
-__global__ void k_cg_update_p(int n, double* __restrict__ scal, const double* __restrict__ z, double* __restrict__ p) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const double beta = scal[2] / scal[0];
-    if (i < n) p[i] = z[i] + beta * p[i];
-}
-__global__ void k_cg_shift(double* scal) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) scal[0] = scal[2];
-}
 __global__ void k_nodal_copy(int n, const double* __restrict__ src, double* __restrict__ dst) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) dst[i] = src[i];
+}
+
+// ---- device-driven conjugate gradients (round 2) ---------------------------------------------------------------------------------
+// Jacobi-preconditioned CG for the scalar node-pattern systems (heat equation, fractional-step pressure / velocity correction)
+// and the node-block velocity-prediction system.  The first version launched 11 kernels and synchronised the host once per
+// iteration (121 us per iteration on a 343 k-row scalar system whose SpMV takes 15 us).  Here an iteration is 3 launches (4 for the node-block system), every dot product
+// goes through the ordered partial-sum bank (each consumer block re-reduces it: same bits everywhere, no atomics), the
+// convergence test and the iteration count live on the device (Eigen's semantics: the pass that reaches the threshold is not
+// counted) and the host polls every 8 iterations.
+enum { CGD_RZ0 = 0, CGD_RZ1, CGD_RR, CGD_BB, CGD_THR, CGD_DONE, CGD_ITERS, CGD_BAD, CGD_COUNT = 8 };
+enum { CGB_PAP = 0, CGB_RR, CGB_RZ, CGB_COUNT };
+// y = A x on the scalar node-pattern matrix + partial dot (x, y) into bank slot CGB_PAP at [blockOffset + blockIdx]
+__global__ void __launch_bounds__(RB_THREADS) k_cgd_spmv(int n, const int* __restrict__ ptr, const int* __restrict__ col,
+                                                         const double* __restrict__ A, const double* __restrict__ x,
+                                                         double* __restrict__ y, double* bank, int stride, int blockOffset,
+                                                         const double* __restrict__ scal) {
+    if (scal[CGD_DONE] != 0.0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double d = 0;
+    if (i < n) {
+        double s = 0;
+        for (int k = ptr[i]; k < ptr[i + 1]; ++k) s += A[k] * x[col[k]];
+        y[i] = s;
+        d = s * x[i];
+    }
+    double v[1] = {d};
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const double t = warpSum(v[0]);
+    if (lane == 0) sh[w] = t;
+    __syncthreads();
+    if (w == 0) {
+        double u = lane < nw ? sh[lane] : 0.0;
+        u = warpSum(u);
+        if (lane == 0) bank[(size_t)CGB_PAP * stride + blockOffset + blockIdx.x] = u;
+    }
+}
+// partial dot (a, b) into bank slot CGB_PAP (node-block system: the SpMV is the Krylov kernel, the dot follows)
+__global__ void __launch_bounds__(RB_THREADS) k_cgd_dot(int n, const double* __restrict__ a, const double* __restrict__ b, double* bank,
+                                                        int stride, const double* __restrict__ scal) {
+    if (scal[CGD_DONE] != 0.0) return;
+    double s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += a[i] * b[i];
+    double v[1] = {s};
+    const int slots[1] = {CGB_PAP};
+    blockSumStore<1>(v, bank, stride, slots);
+}
+// r = b - Ax (Ax may be null: x = 0) ; z = dinv r ; p = z ; partials (r, r), (r, z), and (b, b) into CGB_PAP
+__global__ void __launch_bounds__(RB_THREADS) k_cgd_init(int n, const double* __restrict__ b, const double* __restrict__ Ax,
+                                                         const double* __restrict__ dinv, double* __restrict__ r,
+                                                         double* __restrict__ z, double* __restrict__ p, double* bank, int stride) {
+    double rr = 0, rz = 0, bb = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double bi = b[i], ri = Ax ? bi - Ax[i] : bi, zi = dinv[i] * ri;
+        r[i] = ri, z[i] = zi, p[i] = zi;
+        rr += ri * ri, rz += ri * zi, bb += bi * bi;
+    }
+    double v[3] = {bb, rr, rz};
+    const int slots[3] = {CGB_PAP, CGB_RR, CGB_RZ};
+    blockSumStore<3>(v, bank, stride, slots);
+}
+__global__ void __launch_bounds__(RB_THREADS) k_cgd_init_scal(double* scal, const double* bank, int stride, int nPart, double relTol) {
+    const double bb = bankSum(bank, stride, CGB_PAP, nPart);
+    const double rr = bankSum(bank, stride, CGB_RR, nPart);
+    const double rz = bankSum(bank, stride, CGB_RZ, nPart);
+    if (threadIdx.x == 0) {
+        const double thr = fmax(relTol * relTol * bb, 2.2250738585072014e-308);
+        scal[CGD_RZ0] = rz, scal[CGD_RZ1] = rz, scal[CGD_RR] = rr, scal[CGD_BB] = bb, scal[CGD_THR] = thr;
+        scal[CGD_ITERS] = 0.0, scal[CGD_BAD] = (rr == rr) ? 0.0 : 1.0;
+        scal[CGD_DONE] = (bb == 0.0 || rr < thr || !(rr == rr)) ? 1.0 : 0.0;
+    }
+}
+// alpha = (r, z) / (p, Ap) ; x += alpha p ; r -= alpha Ap ; z = dinv r ; partials (r, r), (r, z)
+__global__ void __launch_bounds__(RB_THREADS) k_cgd_xr(int n, int nPartPAp, const double* __restrict__ scal, int parity,
+                                                       const double* __restrict__ p, const double* __restrict__ Ap,
+                                                       const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
+                                                       double* __restrict__ z, double* bank, int stride) {
+    if (scal[CGD_DONE] != 0.0) return;
+    const double pAp = bankSum(bank, stride, CGB_PAP, nPartPAp);
+    const double alpha = scal[CGD_RZ0 + parity] / pAp;
+    double rr = 0, rz = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * Ap[i], zi = dinv[i] * ri;
+        r[i] = ri, z[i] = zi;
+        rr += ri * ri, rz += ri * zi;
+    }
+    double v[2] = {rr, rz};
+    const int slots[2] = {CGB_RR, CGB_RZ};
+    blockSumStore<2>(v, bank, stride, slots);
+}
+// convergence test (Eigen: stop BEFORE counting the pass), beta = (r, z)_new / (r, z) ; p = z + beta p
+__global__ void __launch_bounds__(RB_THREADS) k_cgd_p(int n, int nPart, double* scal, int parity, const double* __restrict__ z,
+                                                      double* __restrict__ p, const double* bank, int stride) {
+    if (scal[CGD_DONE] != 0.0) return;
+    const double rr = bankSum(bank, stride, CGB_RR, nPart);
+    const double rzNew = bankSum(bank, stride, CGB_RZ, nPart);
+    const double rzOld = scal[CGD_RZ0 + parity];
+    const bool bad = !(rr == rr), conv = rr < scal[CGD_THR];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        scal[CGD_RR] = rr;
+        if (bad) scal[CGD_BAD] = 1.0;
+        if (bad || conv) scal[CGD_DONE] = 1.0;
+        else {
+            scal[CGD_RZ0 + (parity ^ 1)] = rzNew;
+            scal[CGD_ITERS] += 1.0;
+        }
+    }
+    if (bad || conv) return;
+    const double beta = rzNew / rzOld;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = z[i] + beta * p[i];
 }
 
 // explicit heat equation of BoussinesqWC, nodal gather (WCompNewton/HeatEquation.inl:154-298): lumped M with f = cv (N.rho),
@@ -684,16 +734,6 @@ __global__ void k_fs_scalar_dinv(int n, int comps, const int* __restrict__ ptr, 
     const double v = d != 0.0 ? 1.0 / d : 1.0;
     for (int cc = 0; cc < comps; ++cc) dinv[(size_t)cc * n + i] = v;
 }
-// r = b - Ax ; p = dinv r   (start of Eigen's conjugate_gradient)
-__global__ void k_cgg_init(int n, const double* __restrict__ b, const double* __restrict__ Ax, const double* __restrict__ dinv,
-                           double* __restrict__ r, double* __restrict__ p) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double ri = b[i] - Ax[i];
-    r[i] = ri;
-    p[i] = dinv[i] * ri;
-}
-
 GenArgs makeGenArgs(pfem_ctx* c, const pfem_pspg_params& p) {
     GenArgs a;
     a.conn = c->conn.p, a.n2ePtr = c->n2ePtr.p, a.n2e = c->n2e.p, a.blkMask = c->blkMask.p, a.nbrPtr = c->nbrPtr.p, a.nbr = c->nbr.p;
@@ -786,6 +826,79 @@ void thermalWcHeat(pfem_ctx* c, double dt, const double* dtPtr) {
     LAUNCH_CHECK(c);
 }
 
+namespace {
+// bank row length: the vector kernels write <= smCount * 4 partials, a scalar SpMV over `comps` components comps * ceil(N / 256)
+int cgdStride(pfem_ctx* c, int n) { return divUp(n, RB_THREADS) + c->smCount * 4 + 16; }
+// Jacobi-preconditioned CG driven from the device (kernels k_cgd_*).  spmvDot(p, Ap) must compute Ap = A p AND leave the
+// partial sums of (p, Ap) in bank slot CGB_PAP, returning how many partials it wrote; x holds the initial guess on entry when
+// withGuess (then Ax0 is computed through spmvDot first).  Returns the status; iterations as Eigen counts them.
+template <class SpmvDot>
+int cgDevice(pfem_ctx* c, int n, SpmvDot spmvDot, const double* dinv, const double* b, double* x, bool withGuess, double relTol,
+             int maxIter, int* itersOut, double* relResOut) {
+    const int grid = std::max(1, std::min(c->smCount * 4, divUp(n, RB_THREADS)));
+    for (auto* v : {&c->cgR, &c->cgZ, &c->cgP, &c->cgAp}) v->reserve((size_t)n + 8);
+    const int stride = cgdStride(c, n);
+    c->gmBank.reserve((size_t)CGB_COUNT * stride);
+    c->gmS.reserve(CGD_COUNT + 8);
+    if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
+    double* S = c->gmS.p;
+    double* bank = c->gmBank.p;
+    CUDA_CHECK(cudaMemsetAsync(S, 0, CGD_COUNT * sizeof(double), c->stream));
+    const double* Ax = nullptr;
+    if (withGuess) {
+        spmvDot(x, c->cgAp.p);
+        Ax = c->cgAp.p;
+    } else
+        CUDA_CHECK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), c->stream));
+    k_cgd_init<<<grid, RB_THREADS, 0, c->stream>>>(n, b, Ax, dinv, c->cgR.p, c->cgZ.p, c->cgP.p, bank, stride);
+    LAUNCH_CHECK(c);
+    k_cgd_init_scal<<<1, RB_THREADS, 0, c->stream>>>(S, bank, stride, grid, relTol);
+    LAUNCH_CHECK(c);
+    auto poll = [&]() {
+        CUDA_CHECK(cudaMemcpyAsync(c->hScal, S, CGD_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        return c->hScal[CGD_DONE] != 0.0;
+    };
+    bool done = poll();
+    int launched = 0;
+    while (!done && launched < maxIter) {
+        const int batch = std::min(8, maxIter - launched);
+        for (int k = 0; k < batch; ++k, ++launched) {
+            const int parity = launched & 1;
+            const int nPartPAp = spmvDot(c->cgP.p, c->cgAp.p);
+            k_cgd_xr<<<grid, RB_THREADS, 0, c->stream>>>(n, nPartPAp, S, parity, c->cgP.p, c->cgAp.p, dinv, x, c->cgR.p, c->cgZ.p, bank, stride);
+            LAUNCH_CHECK(c);
+            k_cgd_p<<<grid, RB_THREADS, 0, c->stream>>>(n, grid, S, parity, c->cgZ.p, c->cgP.p, bank, stride);
+            LAUNCH_CHECK(c);
+        }
+        done = poll();
+    }
+    const double bb = c->hScal[CGD_BB], rr = c->hScal[CGD_RR];
+    if (itersOut) *itersOut = (int)c->hScal[CGD_ITERS];
+    if (relResOut) *relResOut = bb > 0 ? sqrt(rr / bb) : 0.0;
+    if (c->hScal[CGD_BAD] != 0.0) return PFEM_NAN;
+    if (bb == 0.0) {  // Eigen: x = 0 for b = 0
+        CUDA_CHECK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), c->stream));
+        return PFEM_OK;
+    }
+    return rr < c->hScal[CGD_THR] ? PFEM_OK : PFEM_NOT_CONVERGED;
+}
+// scalar node-pattern matrix applied to `comps` components stored one after the other
+struct ScalarSpmvDot {
+    pfem_ctx* c;
+    int N, comps, stride;
+    int operator()(const double* x, double* y) const {
+        const int g = divUp(N, RB_THREADS);
+        for (int cc = 0; cc < comps; ++cc) {
+            k_cgd_spmv<<<g, RB_THREADS, 0, c->stream>>>(N, c->nbrPtr.p, c->nbr.p, c->hA.p, x + (size_t)cc * N, y + (size_t)cc * N,
+                                                      c->gmBank.p, stride, cc * g, c->gmS.p);
+            LAUNCH_CHECK(c);
+        }
+        return comps * g;
+    }
+};
+}  // namespace
+
 // HeatEqIncompNewton::m_buildAb + m_applyBC (IncompNewton/HeatEquation.inl:227-412, no flux facet terms)
 void heatAssemble(pfem_ctx* c, double rho, double cv, double k, double dt, const double* thetaPrevHost) {
     PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, "heat_assemble: topology/positions missing");
@@ -824,69 +937,20 @@ int heatSolve(pfem_ctx* c, double relTol, int maxIter, double* Tout, int* itersO
     PFEM_REQUIRE(c->haveHeatSystem, PFEM_ERR_STATE, "heat_solve: no assembled heat system (pfem_heat_assemble)");
     PFEM_REQUIRE(relTol > 0 && maxIter > 0, PFEM_ERR_INVALID, "heat_solve: relTol and maxIter must be positive");
     PhaseScope ph(c, "Solve heat system");
-    const int n = c->nNodes, g = divUp(n, 256), nb = std::max(1, std::min(c->smCount * 4, g));
-    for (auto* v : {&c->cgR, &c->cgZ, &c->cgP, &c->cgAp, &c->cgD}) v->reserve((size_t)n + 4);
+    const int n = c->nNodes;
+    c->cgD.reserve((size_t)n + 4);
     c->Tn.reserve((size_t)n + 4);
     c->Tnb.reserve((size_t)n + 4);
-    c->partial.reserve((size_t)nb + 16);
-    c->scal.reserve(SC_COUNT);
-    if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
-    if (!c->haveTemperature) {
-        CUDA_CHECK(cudaMemsetAsync(c->Tn.p, 0, (size_t)n * sizeof(double), c->stream));
-        c->haveTemperature = true;
-    }
-    double* x = c->Tn.p;
-    double* S = c->scal.p;
-    auto dot = [&](const double* a, const double* b, int slot) {
-        k_s_dot<<<nb, 256, 0, c->stream>>>(n, a, b, c->partial.p);
-        LAUNCH_CHECK(c);
-        k_s_dot_final<<<1, 32, 0, c->stream>>>(c->partial.p, nb, S + slot);
-        LAUNCH_CHECK(c);
-    };
-    k_s_spmv<<<g, 256, 0, c->stream>>>(n, c->nbrPtr.p, c->nbr.p, c->hA.p, x, c->cgAp.p);
+    const bool guess = c->haveTemperature;
+    c->haveTemperature = true;
+    k_fs_scalar_dinv<<<divUp(n, 256), 256, 0, c->stream>>>(n, 1, c->nbrPtr.p, c->diagSlot.p, c->hA.p, c->cgD.p);  // Eigen::DiagonalPreconditioner
     LAUNCH_CHECK(c);
-    k_cg_init<<<g, 256, 0, c->stream>>>(n, c->nbrPtr.p, c->diagSlot.p, c->hA.p, c->hb.p, c->cgAp.p, c->cgR.p, c->cgZ.p, c->cgP.p, c->cgD.p);
-    LAUNCH_CHECK(c);
-    dot(c->cgR.p, c->cgZ.p, 0);
-    dot(c->cgR.p, c->cgR.p, 3);
-    dot(c->hb.p, c->hb.p, 4);
-    CUDA_CHECK(cudaMemcpyAsync(c->hScal, S, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    const double bb = c->hScal[4];
-    double rr = c->hScal[3];
-    int it = 0, status = PFEM_OK;
-    if (bb == 0.0) {  // Eigen: x = 0 for b = 0
-        CUDA_CHECK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), c->stream));
-        rr = 0;
-    } else {
-        const double thr = relTol * relTol * bb;
-        while (rr > thr && it < maxIter) {
-            k_s_spmv<<<g, 256, 0, c->stream>>>(n, c->nbrPtr.p, c->nbr.p, c->hA.p, c->cgP.p, c->cgAp.p);
-            LAUNCH_CHECK(c);
-            dot(c->cgP.p, c->cgAp.p, 1);
-            k_cg_update_xr<<<g, 256, 0, c->stream>>>(n, S, c->cgP.p, c->cgAp.p, c->cgD.p, x, c->cgR.p, c->cgZ.p);
-            LAUNCH_CHECK(c);
-            dot(c->cgR.p, c->cgZ.p, 2);
-            dot(c->cgR.p, c->cgR.p, 3);
-            k_cg_update_p<<<g, 256, 0, c->stream>>>(n, S, c->cgZ.p, c->cgP.p);
-            LAUNCH_CHECK(c);
-            k_cg_shift<<<1, 32, 0, c->stream>>>(S);
-            LAUNCH_CHECK(c);
-            ++it;
-            CUDA_CHECK(cudaMemcpyAsync(c->hScal, S, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_CHECK(cudaStreamSynchronize(c->stream));
-            rr = c->hScal[3];
-            if (!(rr == rr)) {
-                status = PFEM_NAN;
-                break;
-            }
-        }
-        if (status == PFEM_OK && rr > thr) status = PFEM_NOT_CONVERGED;
-    }
-    if (itersOut) *itersOut = it;
-    if (relResOut) *relResOut = bb > 0 ? sqrt(rr / bb) : 0.0;
+    c->gmBank.reserve((size_t)CGB_COUNT * cgdStride(c, n));
+    c->gmS.reserve(CGD_COUNT + 8);
+    const ScalarSpmvDot spmv{c, n, 1, cgdStride(c, n)};
+    const int status = cgDevice(c, n, spmv, c->cgD.p, c->hb.p, c->Tn.p, guess, relTol, maxIter, itersOut, relResOut);
     if (Tout) {
-        CUDA_CHECK(cudaMemcpyAsync(Tout, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaMemcpyAsync(Tout, c->Tn.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
     }
     return status;
@@ -939,69 +1003,6 @@ void heatExport(pfem_ctx* c, int64_t* nnz, int32_t* colPtr, int32_t* rowIdx, dou
 // The three linear systems of one Picard body (:464-548), each assembled on the device from given inputs, and Eigen's
 // Jacobi-preconditioned conjugate gradients for them.  Single-GPU contexts, gamma = 0 (no surface-tension facet term).
 namespace {
-// Eigen::ConjugateGradient (ConjugateGradient.h, conjugate_gradient()): zero initial guess, diagonal preconditioner, stops when
-// ||r||^2 < max(tol^2 ||b||^2, DBL_MIN); `iterations` as Eigen counts them: the pass that reaches the threshold is not counted.
-template <class Spmv>
-int cgEigen(pfem_ctx* c, int n, Spmv spmv, const double* dinv, const double* b, double* x, double relTol, int maxIter, int* itersOut,
-            double* relResOut) {
-    const int g = divUp(n, 256), nb = std::max(1, std::min(c->smCount * 4, g));
-    for (auto* v : {&c->cgR, &c->cgZ, &c->cgP, &c->cgAp}) v->reserve((size_t)n + 8);
-    c->partial.reserve((size_t)nb + 16);
-    c->scal.reserve(SC_COUNT);
-    if (!c->hScal) CUDA_CHECK(cudaMallocHost(&c->hScal, SC_COUNT * sizeof(double)));
-    double* S = c->scal.p;
-    auto dot = [&](const double* a, const double* bb, int slot) {
-        k_s_dot<<<nb, 256, 0, c->stream>>>(n, a, bb, c->partial.p);
-        LAUNCH_CHECK(c);
-        k_s_dot_final<<<1, 32, 0, c->stream>>>(c->partial.p, nb, S + slot);
-        LAUNCH_CHECK(c);
-    };
-    auto fetch = [&]() {
-        CUDA_CHECK(cudaMemcpyAsync(c->hScal, S, 5 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_CHECK(cudaStreamSynchronize(c->stream));
-    };
-    CUDA_CHECK(cudaMemsetAsync(x, 0, (size_t)n * sizeof(double), c->stream));
-    CUDA_CHECK(cudaMemsetAsync(c->cgAp.p, 0, (size_t)n * sizeof(double), c->stream));
-    k_cgg_init<<<g, 256, 0, c->stream>>>(n, b, c->cgAp.p, dinv, c->cgR.p, c->cgP.p);
-    LAUNCH_CHECK(c);
-    dot(c->cgR.p, c->cgP.p, 0);  // absNew = r . p
-    dot(c->cgR.p, c->cgR.p, 3);
-    dot(b, b, 4);
-    fetch();
-    const double bb = c->hScal[4];
-    double rr = c->hScal[3];
-    int it = 0, status = PFEM_OK;
-    if (bb == 0.0) rr = 0;  // x = 0
-    else {
-        const double thr = std::max(relTol * relTol * bb, 2.2250738585072014e-308);
-        if (!(rr < thr)) {
-            while (it < maxIter) {
-                spmv(c->cgP.p, c->cgAp.p);
-                dot(c->cgP.p, c->cgAp.p, 1);
-                k_cg_update_xr<<<g, 256, 0, c->stream>>>(n, S, c->cgP.p, c->cgAp.p, dinv, x, c->cgR.p, c->cgZ.p);
-                LAUNCH_CHECK(c);
-                dot(c->cgR.p, c->cgR.p, 3);
-                dot(c->cgR.p, c->cgZ.p, 2);
-                fetch();
-                rr = c->hScal[3];
-                if (!(rr == rr)) {
-                    status = PFEM_NAN;
-                    break;
-                }
-                if (rr < thr) break;
-                k_cg_update_p<<<g, 256, 0, c->stream>>>(n, S, c->cgZ.p, c->cgP.p);
-                LAUNCH_CHECK(c);
-                k_cg_shift<<<1, 32, 0, c->stream>>>(S);
-                LAUNCH_CHECK(c);
-                ++it;
-            }
-            if (status == PFEM_OK && !(rr < thr)) status = PFEM_NOT_CONVERGED;
-        }
-    }
-    if (itersOut) *itersOut = it;
-    if (relResOut) *relResOut = bb > 0 ? sqrt(rr / bb) : 0.0;
-    return status;
-}
 void fsRequire(pfem_ctx* c, const char* what) {
     PFEM_REQUIRE(c->haveTopology && c->havePositions, PFEM_ERR_STATE, std::string(what) + ": topology/positions missing");
     PFEM_REQUIRE(c->nRanks == 1, PFEM_ERR_STATE, std::string(what) + ": single-GPU contexts");
@@ -1145,8 +1146,16 @@ int fsSolve(pfem_ctx* c, double relTol, int maxIter, double* xHost, int* itersOu
         c->kx.reserve((size_t)n + 8);
         k_fs_block_dinv<<<divUp(n, 256), 256, 0, c->stream>>>(N, BS, c->nbrPtr.p, c->diagSlot.p, c->Aval.p, c->cgD.p);
         LAUNCH_CHECK(c);
-        status = cgEigen(c, n, [&](double* x, double* y) { krylovMatvec(c, x, y); }, c->cgD.p, c->bvec.p, c->kx.p, relTol, maxIter,
-                         itersOut, relResOut);
+        c->gmBank.reserve((size_t)CGB_COUNT * cgdStride(c, n));
+        c->gmS.reserve(CGD_COUNT + 8);
+        const int stride = cgdStride(c, n), dotGrid = std::max(1, std::min(c->smCount * 4, divUp(n, RB_THREADS)));
+        auto spmvDot = [&](const double* x, double* y) {
+            krylovMatvec(c, const_cast<double*>(x), y);
+            k_cgd_dot<<<dotGrid, RB_THREADS, 0, c->stream>>>(n, x, y, c->gmBank.p, stride, c->gmS.p);
+            LAUNCH_CHECK(c);
+            return dotGrid;
+        };
+        status = cgDevice(c, n, spmvDot, c->cgD.p, c->bvec.p, c->kx.p, false, relTol, maxIter, itersOut, relResOut);
         c->haveSolution = true;
         if (xHost) {  // velocity part, [d][nNodes]
             std::vector<double> q((size_t)n);
@@ -1161,13 +1170,10 @@ int fsSolve(pfem_ctx* c, double relTol, int maxIter, double* xHost, int* itersOu
     c->fsVec.reserve((size_t)dim * N + 4);
     k_fs_scalar_dinv<<<divUp(N, 256), 256, 0, c->stream>>>(N, comps, c->nbrPtr.p, c->diagSlot.p, c->hA.p, c->cgD.p);
     LAUNCH_CHECK(c);
-    auto spmv = [&](double* x, double* y) {
-        for (int cc = 0; cc < comps; ++cc) {
-            k_s_spmv<<<divUp(N, 256), 256, 0, c->stream>>>(N, c->nbrPtr.p, c->nbr.p, c->hA.p, x + (size_t)cc * N, y + (size_t)cc * N);
-            LAUNCH_CHECK(c);
-        }
-    };
-    status = cgEigen(c, n, spmv, c->cgD.p, c->hb.p, c->fsVec.p, relTol, maxIter, itersOut, relResOut);
+    c->gmBank.reserve((size_t)CGB_COUNT * cgdStride(c, n));
+    c->gmS.reserve(CGD_COUNT + 8);
+    const ScalarSpmvDot spmv{c, N, comps, cgdStride(c, n)};
+    status = cgDevice(c, n, spmv, c->cgD.p, c->hb.p, c->fsVec.p, false, relTol, maxIter, itersOut, relResOut);
     if (xHost) {
         CUDA_CHECK(cudaMemcpyAsync(xHost, c->fsVec.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CUDA_CHECK(cudaStreamSynchronize(c->stream));
