@@ -153,6 +153,7 @@ struct pfem_ctx {
     double asmStamp = 0.0;     // dt of the assembled system (the multigrid dampings are re-tuned when it changes)
     DevBuf<double> kx, kr, kr0, kp, kp2, kv, ks, kt, kph, ksh;  // Krylov vectors (internal dof order)
     DevBuf<double> partial;    // PS_COUNT * reduceBlocks
+    DevBuf<double> genRec;     // general assembly kernels: per-element record (grad N, V, tau, viscosity), 16 doubles
     DevBuf<double> fsVec;      // fractional-step systems: vTilde input / scalar-system solution, [d][nNodes]
     DevBuf<uint8_t> fsMask;    // row mask of the scalar systems (zero: pressure; bound nodes: velocity correction)
     const uint8_t* heatMask = nullptr;  // the Dirichlet-row mask the scalar system in hA was assembled with

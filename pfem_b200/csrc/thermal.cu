@@ -9,11 +9,12 @@
 //   * explicit heat equation (BoussinesqWC, WCompNewton/HeatEquation.inl:154-298), the buoyancy factor of the explicit
 //     momentum equation (WCompNewton/MomEquation.inl:105-112) and the thermal diffusivity in the CFL step
 //     (WCompNewton/Solver.cpp:214-216) live in wc.cu next to the kernels they extend; the nodal pass is here.
-// These are the GENERAL assembly kernels: one thread per node block (i, j) gathers the elements around edge (i, j) in
-// ascending element index and evaluates the closed forms of SURVEY appendix A with per-element factors; a second pass per
-// node sums the right-hand side and applies the boundary conditions.  Simple and deterministic, not tuned: the tuned
+// These are the GENERAL assembly kernels: an element pass writes one record per element (grad N, V, tau, viscosity), one
+// thread per node block (i, j) gathers the elements around edge (i, j) in ascending element index and evaluates the closed
+// forms of SURVEY appendix A with the per-element factors; a last pass per node sums the right-hand side and applies the
+// boundary conditions.  The fractional-step systems and the device-driven CG are at the end of the file.  Simple and deterministic, not tuned: the tuned
 // kernel (pspg.cu) covers the constant-factor problem of the named configurations; problems with these factors take
-// this path (about 10x slower at C4).
+// this path (about 4x slower at C4).
 #include "common.cuh"
 #include "spmv.cuh"
 
@@ -111,7 +112,29 @@ struct GenArgs {
     int mode = 0;
     double gammaFS = 0.0;
     const double* pPrev = nullptr;
+    // per-element record written once by k_gen_elem (grad N, V, tau, viscosity): the block / right-hand-side passes read it
+    // instead of re-evaluating the element for every node block it touches (16x at C4)
+    double* rec = nullptr;
+    int nElems = 0;
 };
+template <int DIM> struct GenRec {
+    static constexpr int STRIDE = (DIM == 3) ? 16 : 10;  // doubles: (DIM+1) DIM gradients, V, tau, mu (+ pad: 16-byte multiples)
+};
+template <int DIM>
+__device__ __forceinline__ void loadRec(const double* __restrict__ rec, int e, GElem<DIM>& G, double& tau, double& muE) {
+    const double2* r = reinterpret_cast<const double2*>(rec + (size_t)e * GenRec<DIM>::STRIDE);
+    double v[GenRec<DIM>::STRIDE];
+#pragma unroll
+    for (int k = 0; k < GenRec<DIM>::STRIDE / 2; ++k) {
+        const double2 t = __ldg(r + k);
+        v[2 * k] = t.x, v[2 * k + 1] = t.y;
+    }
+#pragma unroll
+    for (int m = 0; m < DIM + 1; ++m)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) G.g[m][d] = v[m * DIM + d];
+    G.V = v[(DIM + 1) * DIM], tau = v[(DIM + 1) * DIM + 1], muE = v[(DIM + 1) * DIM + 2];
+}
 
 // tau (PSPG.inl:238-259) and the element viscosity
 template <int DIM>
@@ -159,6 +182,30 @@ __device__ __forceinline__ void elemTauMu(const GenArgs& a, const int (&nd)[DIM 
     }
 }
 
+// element pass: geometry, tau and the element viscosity once per element
+template <int DIM>
+__global__ void __launch_bounds__(128) k_gen_elem(const GenArgs a) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= a.nElems) return;
+    int nd[DIM + 1];
+    loadConn<DIM>(a.conn, e, nd);
+    GElem<DIM> G;
+    elemGeo<DIM>(a.X4, nd, G);
+    double tau, muE;
+    elemTauMu<DIM>(a, nd, G, tau, muE);
+    double v[GenRec<DIM>::STRIDE];
+#pragma unroll
+    for (int k = 0; k < GenRec<DIM>::STRIDE; ++k) v[k] = 0.0;
+#pragma unroll
+    for (int m = 0; m < DIM + 1; ++m)
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) v[m * DIM + d] = G.g[m][d];
+    v[(DIM + 1) * DIM] = G.V, v[(DIM + 1) * DIM + 1] = tau, v[(DIM + 1) * DIM + 2] = muE;
+    double2* r = reinterpret_cast<double2*>(a.rec + (size_t)e * GenRec<DIM>::STRIDE);
+#pragma unroll
+    for (int k = 0; k < GenRec<DIM>::STRIDE / 2; ++k) r[k] = make_double2(v[2 * k], v[2 * k + 1]);
+}
+
 // block (i, slot) of the PSPG matrix: every element around edge (i, j), ascending element index, row masks applied
 template <int DIM>
 __global__ void __launch_bounds__(128) k_gen_blocks(const GenArgs a) {
@@ -196,9 +243,8 @@ __global__ void __launch_bounds__(128) k_gen_blocks(const GenArgs a) {
             lj = (nd[m] == j) ? m : lj;
         }
         GElem<DIM> G;
-        elemGeo<DIM>(a.X4, nd, G);
         double tau, muE;
-        elemTauMu<DIM>(a, nd, G, tau, muE);
+        loadRec<DIM>(a.rec, e, G, tau, muE);
         double gi[DIM], gj[DIM], dot = 0;
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
@@ -256,9 +302,8 @@ __global__ void __launch_bounds__(128) k_gen_rhs_bc(const GenArgs a) {
 #pragma unroll
         for (int m = 1; m < NPE; ++m) li = (nd[m] == i) ? m : li;
         GElem<DIM> G;
-        elemGeo<DIM>(a.X4, nd, G);
         double tau, muE;
-        elemTauMu<DIM>(a, nd, G, tau, muE);
+        loadRec<DIM>(a.rec, e, G, tau, muE);
         double gi[DIM], sv[DIM], vpi[DIM];
 #pragma unroll
         for (int d = 0; d < DIM; ++d) {
@@ -745,6 +790,8 @@ GenArgs makeGenArgs(pfem_ctx* c, const pfem_pspg_params& p) {
     a.bingham = c->binghamOn ? 1 : 0, a.tau0 = c->binghamTau0, a.mReg = c->binghamM;
     a.alpha = c->thAlpha, a.Tr = c->thTr;
     a.fst4 = nullptr;
+    c->genRec.reserve((size_t)std::max(c->nElems, 1) * 16 + 8);
+    a.rec = c->genRec.p, a.nElems = c->nElems;
     return a;
 }
 
@@ -760,10 +807,14 @@ void pspgAssembleGeneral(pfem_ctx* c, const pfem_pspg_params& p, const double* f
     PhaseScope ph(c, "Assemble system");
     const int64_t nBlkRows = c->nBlocks;  // (partitioned mesh: blocks of the owned rows come first; the kernel bounds itself)
     if (c->dim == 2) {
+        k_gen_elem<2><<<divUp(std::max(c->nElems, 1), 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
         k_gen_blocks<2><<<divUp(nBlkRows, 128), 128, 0, c->stream>>>(a);
         LAUNCH_CHECK(c);
         k_gen_rhs_bc<2><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(a);
     } else {
+        k_gen_elem<3><<<divUp(std::max(c->nElems, 1), 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
         k_gen_blocks<3><<<divUp(nBlkRows, 128), 128, 0, c->stream>>>(a);
         LAUNCH_CHECK(c);
         k_gen_rhs_bc<3><<<divUp(c->nRows, 128), 128, 0, c->stream>>>(a);
@@ -1036,10 +1087,14 @@ void fsAssembleVapp(pfem_ctx* c, const pfem_pspg_params& p, double gammaFS, cons
     a.mode = 1, a.gammaFS = gammaFS, a.pPrev = c->hTheta.p;
     PhaseScope ph(c, "Assemble system");
     if (c->dim == 2) {
+        k_gen_elem<2><<<divUp(std::max(c->nElems, 1), 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
         k_gen_blocks<2><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
         LAUNCH_CHECK(c);
         k_gen_rhs_bc<2><<<divUp(n, 128), 128, 0, c->stream>>>(a);
     } else {
+        k_gen_elem<3><<<divUp(std::max(c->nElems, 1), 128), 128, 0, c->stream>>>(a);
+        LAUNCH_CHECK(c);
         k_gen_blocks<3><<<divUp(c->nBlocks, 128), 128, 0, c->stream>>>(a);
         LAUNCH_CHECK(c);
         k_gen_rhs_bc<3><<<divUp(n, 128), 128, 0, c->stream>>>(a);
