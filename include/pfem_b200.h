@@ -185,15 +185,18 @@ int pfem_pspg_assemble(pfem_ctx* ctx, const pfem_pspg_params* p, const double* q
  * qPrevVec[0]) uploads it once: set_qprev copies it to the device, assemble_resident assembles from device-resident data. */
 int pfem_pspg_set_qprev(pfem_ctx* ctx, const double* qPrev);
 int pfem_pspg_assemble_resident(pfem_ctx* ctx, const pfem_pspg_params* p);
-/* Replaces m_solver.analyzePattern/factorize/solve (PSPG.inl:281-290) by preconditioned BiCGSTAB on the device.
+/* Replaces m_solver.analyzePattern/factorize/solve (PSPG.inl:281-290) by a preconditioned Krylov solve on the device:
+ * flexible GMRES(40) under the multigrid preconditioner, BiCGSTAB under the Jacobi ones (`iters` counts preconditioner
+ * applications for the former, iterations of two applications each for the latter).
  * q (out, (dim+1)*nNodes) may be NULL to leave the solution on the device.  relTol is on ||b - A q|| / ||b||.
  * Returns PFEM_NOT_CONVERGED / PFEM_NAN like a failed factorisation would (PSPG.inl:304-312). */
 int pfem_pspg_solve(pfem_ctx* ctx, double relTol, int maxIter, double* q, int* iters, double* relRes);
-/* Preconditioner of that BiCGSTAB.  kind: PFEM_PRECOND_AUTO (multigrid when the mesh has more than 32 nodes, else node-block
+/* Preconditioner of that solve.  kind: PFEM_PRECOND_AUTO (multigrid when the mesh has more than 32 nodes, else node-block
  * Jacobi), _POINT (diagonal, what Eigen's iterative solvers default to, MomContEquation.hpp:49), _BLOCK (node-block Jacobi),
  * _MG (aggregation multigrid, V(sweeps,sweeps), node-block Jacobi smoothing with the local damping `damping`/r_i, r_i the
- * inf-norm of block row i of D^-1 A).  sweeps <= 0 / damping <= 0 keep the defaults (2, 2.0).  Under _AUTO a multigrid solve
- * that has not converged after 300 iterations continues with node-block Jacobi.  get_preconditioner reports what the last
+ * inf-norm of block row i of D^-1 A).  sweeps <= 0 / damping <= 0 keep the defaults (3 in 3-D, 2 in 2-D; 2.0).  Under _AUTO a multigrid
+ * solve that stagnates (less than 1.5 orders of magnitude in 50 iterations) or has not converged after 300 iterations
+ * continues with node-block Jacobi.  get_preconditioner reports what the last
  * solve used and its number of multigrid levels (1: none). */
 #define PFEM_PRECOND_AUTO 0
 #define PFEM_PRECOND_POINT 1

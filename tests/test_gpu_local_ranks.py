@@ -3,7 +3,7 @@
 transport underneath commHalo / commAllReduce / commAllGather.
 
 Bars: explicit weakly-compressible steps bit-identical to the 1-GPU run (same per-node summation order); PSPG fields
-within 1e-8 (north_star) with the multigrid-preconditioned BiCGSTAB taking at most 1.5x (+2) the single-GPU iterations.
+within 1e-8 (north_star) with the multigrid-preconditioned Krylov solve taking at most 1.5x (+2) the single-GPU iterations.
 """
 import os
 

@@ -1,4 +1,4 @@
-"""Aggregation-multigrid preconditioner of the device BiCGSTAB (csrc/mg.cu): same solution as node-block Jacobi and as a
+"""Aggregation-multigrid preconditioner of the device Krylov solve (csrc/mg.cu, csrc/krylov.cu): same solution as node-block Jacobi and as a
 direct solve of the oracle's matrix, far fewer iterations, bit-reproducible."""
 import numpy as np
 import pytest

@@ -1,4 +1,4 @@
-"""CUDA path (through the C ABI) vs the CPU oracle: PSPG assembly, BC, export, SpMV, BiCGSTAB, Picard."""
+"""CUDA path (through the C ABI) vs the CPU oracle: PSPG assembly, BC, export, SpMV, Krylov solve, Picard."""
 import numpy as np
 import pytest
 import scipy.sparse.linalg as spla
