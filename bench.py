@@ -787,7 +787,7 @@ def run_multi(env, args):
             "config": {"workload": f"C5 synthetic 3D Kuhn box n={w['cells']} ({n_elems} tets, {n_nodes} nodes), explicit weakly-compressible "
                                    "step (CDS_dpdt + Meduri): kick/move + continuity + momentum + CFL dt per step, dt chained on the device",
                        "partition": f"RCB nodes + ghost-element layer over {world} GPUs (csrc/partition.cu), 2 halo exchanges + 1 min-all-reduce "
-                                    "per step over NCCL, interface nodes first with the exchange overlapping the interior node pass",
+                                    "per step over NCCL (serialised with the node passes; PFEM_WC_OVERLAP=1 overlaps them: measured slower at 4 GPUs)",
                        "n_elems": n_elems, "n_nodes": n_nodes,
                        "l2_policy": "inputs larger than L2 (element records %.0f MB per GPU vs 126 MB L2)" % (n_elems * 160 / 1e6 / world),
                        "value_definition": "n_elems / max-over-ranks device time per step of pfem_wc_run"},

@@ -1255,9 +1255,12 @@ bool wcTiles(const pfem_ctx* c, const pfem_wc_params& p) {
     if (p.eqType != PFEM_WC_CDS_DPDT || c->maxE > 255 || c->thermalOn) return false;
     return raw == 13;  // opt-in: measured slower than the two-pass kernels on B200
 }
-// overlap of the halo exchanges with the interior node pass (PFEM_WC_OVERLAP=0 serialises them: A/B switch)
+// Overlap of the halo exchanges with the interior node pass (interface nodes first, second stream): opt-in with
+// PFEM_WC_OVERLAP=1.  A/B on 4 B200s at C5 (tools/wc_overlap_ab.py, 20 steps, twice each): 0.780 / 0.780 ms per step
+// serialised against 0.887 / 0.827 ms overlapped -- the interface-first node order costs the node passes 0.05 ms of
+// coalescing and the split passes two more launches each, which is what the two hidden exchanges (0.055 ms each) are worth.
 bool wcOverlap() {
-    static const bool v = !(getenv("PFEM_WC_OVERLAP") && atoi(getenv("PFEM_WC_OVERLAP")) == 0);
+    static const bool v = getenv("PFEM_WC_OVERLAP") && atoi(getenv("PFEM_WC_OVERLAP")) == 1;
     return v;
 }
 bool wcTwoPassMom(const pfem_ctx* c) { return (c->wcVariant ? c->wcVariant : wcCfgRaw()) != 12; }
