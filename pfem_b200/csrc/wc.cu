@@ -562,10 +562,13 @@ __global__ void __launch_bounds__(256) k_wc_cont_node(const WcArgs a, const doub
     }
 }
 
-template <int DIM, int MINB>
+// TH: BoussinesqWC -- the body-force term takes the buoyancy-weighted mass sum_g w (N.rho)(1 - alpha (N.T - Tr)) N_q
+// (WCompNewton/MomEquation.inl:105-112), the same Gauss sum as in the gather kernel k_wc_mom
+template <int DIM, int MINB, bool TH = false>
 __global__ void __launch_bounds__(256, MINB) k_wc_mom_elem(int nElems, const int* __restrict__ conn, const double* __restrict__ X4,
                                                      const double* __restrict__ V4, double mu, double bx, double by, double bz,
-                                                     double* __restrict__ rec) {
+                                                     double* __restrict__ rec, const double* __restrict__ T = nullptr,
+                                                     double thAlpha = 0.0, double thTr = 0.0) {
     constexpr int NPE = DIM + 1;
     constexpr double PHI = 1.0 / ((DIM + 1) * (DIM + 2));
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -610,16 +613,36 @@ __global__ void __launch_bounds__(256, MINB) k_wc_mom_elem(int nElems, const int
             if (c == aa) sv -= (2.0 / 3.0) * tr;
             sig[aa][c] = mu * sv;
         }
+    double Te[NPE], sumT = 0;
+    if constexpr (TH) {
+#pragma unroll
+        for (int q = 0; q < NPE; ++q) {
+            Te[q] = T[nd[q]];
+            sumT += Te[q];
+        }
+    }
 #pragma unroll
     for (int q = 0; q < NPE; ++q) {
         const double li_mass = G.V * PHI * (rho[q] + sumR);  // lumped rho-mass == sum_g w (N.rho) N_q
+        double bodyMass = li_mass;
+        if constexpr (TH) {
+            constexpr double GA = (DIM == 3) ? 0.585410196624968 : 0.66666666666666666667;
+            constexpr double GB = (DIM == 3) ? 0.138196601125011 : 0.16666666666666666667;
+            double fs = 0;
+#pragma unroll
+            for (int g = 0; g < NPE; ++g) {
+                const double rg = GB * sumR + (GA - GB) * rho[g], Tg = GB * sumT + (GA - GB) * Te[g];
+                fs += (1.0 / NPE) * (rg * (1.0 - thAlpha * (Tg - thTr))) * (g == q ? GA : GB);
+            }
+            bodyMass = G.V * fs;
+        }
         double F[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int aa = 0; aa < DIM; ++aa) {
             double sg = 0;
 #pragma unroll
             for (int c = 0; c < DIM; ++c) sg += sig[aa][c] * G.g[c][q];
-            F[aa] = -G.V * sg + G.V * pbar * G.g[aa][q] + body[aa] * li_mass;
+            F[aa] = -G.V * sg + G.V * pbar * G.g[aa][q] + body[aa] * bodyMass;
         }
         st4(rec + ((size_t)q * nElems + e) * 4, F[0], F[1], F[2], li_mass);  // plane q: consecutive lanes, consecutive sectors
     }
@@ -1243,8 +1266,10 @@ int wcCfgRaw() {
     return cfg;
 }
 bool wcTwoPass(const pfem_ctx* c) {
-    if (c->thermalOn) return false;  // BoussinesqWC: the buoyancy factor lives in the gather momentum kernel
     const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();  // pfem_wc_set_variant overrides the environment
+    // BoussinesqWC: the two-pass kernels carry the buoyancy factor too (round 2); the mixed variant 12 (gather momentum)
+    // and the tiles do not
+    if (c->thermalOn && (raw == 12 || raw == 13)) return raw == 12;
     if (raw == 11 || raw == 12 || raw == 13) return true;
     if (raw != 10) return false;
     return c->nElems >= 200000;
@@ -1266,7 +1291,7 @@ bool wcOverlap() {
 bool wcTwoPassMom(const pfem_ctx* c) { return (c->wcVariant ? c->wcVariant : wcCfgRaw()) != 12; }
 int wcCfg(const pfem_ctx* c) {
     const int raw = c->wcVariant ? c->wcVariant : wcCfgRaw();
-    if (c->thermalOn) return 6;
+    if (c->thermalOn && !wcTwoPass(c)) return 6;  // BoussinesqWC below the two-pass size: the gather kernels with the buoyancy factor
     return wcTwoPass(c) ? 10 : (raw >= 10 ? 6 : raw);
 }
 
@@ -1434,7 +1459,10 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
         if (cfg == 10 && !wcTwoPassMom(c)) PFEM_WC_LAUNCH(k_wc_mom, 4, c->X4b.p, c->V4b.p, c->V4.p, c->A4.p, c->X4.p, c->wcCfl2.p);
         else if (cfg == 10) {
             const int ge = divUp(c->nElems, 256);
-            if (c->dim == 2) k_wc_mom_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
+            if (c->thermalOn) {  // BoussinesqWC: buoyancy-weighted body mass
+                if (c->dim == 2) k_wc_mom_elem<2, 3, true><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p, c->Tn.p, c->thAlpha, c->thTr);
+                else k_wc_mom_elem<3, 3, true><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p, c->Tn.p, c->thAlpha, c->thTr);
+            } else if (c->dim == 2) k_wc_mom_elem<2, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
             else if (wcElemBlocks() == 4) k_wc_mom_elem<3, 4><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
             else if (wcElemBlocks() == 2) k_wc_mom_elem<3, 2><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
             else k_wc_mom_elem<3, 3><<<ge, 256, 0, c->stream>>>(c->nElems, c->conn.p, c->X4b.p, c->V4b.p, p.mu, p.bodyForce[0], p.bodyForce[1], p.bodyForce[2], c->wcElemRec.p);
@@ -1469,7 +1497,7 @@ void launchStep(pfem_ctx* c, const pfem_wc_params& p, double dt, const double* d
 void launchDt(pfem_ctx* c, const pfem_wc_params& p, double securityCoeff, int grid, bool afterTwoPassStep = false) {
     const double sc2 = securityCoeff * securityCoeff;
     // the stored he / nodal CFL values belong to the two-pass step that has just run with the same material constants
-    if (afterTwoPassStep && p.eqType == PFEM_WC_CDS_DPDT && p.mu == c->cflMu && p.K0 == c->cflK0 && p.K0p == c->cflK0p) {
+    if (afterTwoPassStep && !c->thermalOn && p.eqType == PFEM_WC_CDS_DPDT && p.mu == c->cflMu && p.K0 == c->cflK0 && p.K0p == c->cflK0p) {
         PhaseScope ph(c, "CFL nodal pass");
         k_wc_dt_nodal<<<grid, 256, 0, c->stream>>>(c->nRows, c->wcHmin.p, c->wcCfl2.p, sc2, c->dtPartial.p);
         LAUNCH_CHECK(c);

@@ -81,14 +81,19 @@ def test_boussinesq_pspg_and_heat_system_match_reference_fixture(gpu_ctx_factory
         assert again["status"] == 0 and again["iters"] <= 1
 
 
+@pytest.mark.parametrize("variant", [0, 6, 11, 12])
 @pytest.mark.parametrize("name", golden_names("wcb_"))
-def test_boussinesq_wc_steps_match_reference_fixture(gpu_ctx_factory, name):
+def test_boussinesq_wc_steps_match_reference_fixture(gpu_ctx_factory, name, variant):
+    """variant: 0 default by size (gather kernels on these small meshes), 6 gather, 11 two-pass element records (what a C5-size
+    BoussinesqWC mesh takes: k_wc_mom_elem<.., TH>), 12 two-pass continuity + gather momentum."""
     mesh, z = load_golden(name)
     dim, nn = mesh.dim, mesh.n_nodes
     k, cv, alpha, Tr = [float(v) for v in z["thermal"]]
     nst = 2 * dim + 2
     with gpu_ctx_factory(dim) as ctx:
         ctx.set_mesh(mesh)
+        if variant:
+            ctx.wc_set_variant(variant)
         ctx.set_states(0, z["q0"][: nst * nn])
         ctx.set_thermal(k, cv, alpha, Tr)
         ctx.set_temperature(z["q0"][nst * nn:])
@@ -112,3 +117,34 @@ def test_boussinesq_wc_steps_match_reference_fixture(gpu_ctx_factory, name):
         ctx.set_positions(mesh.x)
         ctx.wc_step(wp, float(z["dts"][0]))
         assert np.abs(ctx.get_states(0, dim) - z["states"][0][: dim * nn]).max() > 0
+
+
+@pytest.mark.parametrize("name", golden_names("wcb_"))
+def test_boussinesq_wc_kernel_variants_agree_through_the_chained_run(gpu_ctx_factory, name):
+    """Gather kernels against the two-pass kernels with the buoyancy factor (k_wc_mom_elem<.., TH>), through pfem_wc_run
+    (chained CFL steps with the thermal diffusivity term): same per-node summation order, fields within rounding of each
+    other (the two kernels contract their multiply-adds differently, so not bit for bit)."""
+    mesh, z = load_golden(name)
+    dim, nn = mesh.dim, mesh.n_nodes
+    k, cv, alpha, Tr = [float(v) for v in z["thermal"]]
+    nst = 2 * dim + 2
+    out = {}
+    for variant in (6, 11):
+        with gpu_ctx_factory(dim) as ctx:
+            ctx.set_mesh(mesh)
+            ctx.wc_set_variant(variant)
+            ctx.set_states(0, z["q0"][: nst * nn])
+            ctx.set_thermal(k, cv, alpha, Tr)
+            ctx.set_temperature(z["q0"][nst * nn:])
+            ctx.set_temperature_bc(z["t_mask"], z["t_val"])
+            w = z["wpar"]
+            wp = ctx.wc_params(w[0], w[1], w[2], w[3], w[4:7], bool(w[7]), "CDS_dpdt")
+            dt0 = ctx.wc_next_dt(wp, float(z["security_coeff"]), float(z["max_dt"]))
+            dt, el = ctx.wc_run(wp, 5, float(z["security_coeff"]), float(z["max_dt"]), dt0)
+            out[variant] = (dt0, dt, el, ctx.get_states(0, nst), ctx.get_temperature(), ctx.get_positions())
+    a, b = out[6], out[11]
+    assert a[0] == b[0] and abs(a[1] - b[1]) <= 1e-12 * a[1] and abs(a[2] - b[2]) <= 1e-12 * a[2]
+    for s in range(nst):
+        u, v = a[3][s * nn:(s + 1) * nn], b[3][s * nn:(s + 1) * nn]
+        assert np.abs(u - v).max() <= 1e-11 * max(np.abs(u).max(), 1e-300), s
+    assert np.abs(a[4] - b[4]).max() <= 1e-12 * np.abs(a[4]).max() and np.abs(a[5] - b[5]).max() < 1e-13

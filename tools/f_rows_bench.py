@@ -92,4 +92,4 @@ for thermal in (False, True):
         t0 = time.perf_counter()
         dt, _ = ctx.wc_run(wp, 20, W["securityCoeff"], 1e-3, dt)
         t = 1e3 * (time.perf_counter() - t0) / 20
-        print(f"explicit step n={wc_cells} ({ne} tets) {'BoussinesqWC (gather kernels + heat pass)' if thermal else 'WCompNewtonNoT (two-pass kernels)      '}: {t:6.3f} ms/step  {ne / t / 1e3:7.0f} Melem/s")
+        print(f"explicit step n={wc_cells} ({ne} tets) {'BoussinesqWC (two-pass + heat pass)     ' if thermal else 'WCompNewtonNoT (two-pass kernels)      '}: {t:6.3f} ms/step  {ne / t / 1e3:7.0f} Melem/s")
