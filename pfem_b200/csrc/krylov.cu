@@ -760,7 +760,11 @@ GmresOutcome gmresSolve(pfem_ctx* c, const KrylovDims& k, double relTol, int max
                                                             c->partial.p, k.stride, npVec);
         LAUNCH_CHECK(c);
         int j = 0;  // basis vectors built in this cycle
-        bool done = false;
+        // the start residual may already pass the test (warm start from a converged iterate, b = 0): k_gm_first has set DONE and
+        // written neither v_0 nor the cycle's right-hand side -- no iteration may run on them
+        CUDA_CHECK(cudaMemcpyAsync(c->hScal, c->scal.p, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_CHECK(cudaStreamSynchronize(c->stream));
+        bool done = c->hScal[SC_DONE] != 0.0;
         // Polling: the residual estimate after every iteration needs a stream synchronisation (~20 us bubble).  The cycle is
         // a contraction of at best one order of magnitude per iteration on every mesh measured (typically 0.5), so after a
         // poll that leaves `orders` orders to go, floor(orders) - 1 iterations are launched without polling; k_gm_givens
