@@ -1,5 +1,5 @@
 """CPU prototype: preconditioner applications needed by BiCGSTAB vs right-preconditioned GMRES / GCR with the same
-aggregation-multigrid cycle (research tooling, see precond_proto.py).  Usage: python tests/research/krylov_proto.py [n] [nu]"""
+aggregation-multigrid cycle (research tooling, see precond_proto.py).  Usage: python tests/research/krylov_proto.py [n] [nu] [gs]"""
 import sys
 
 import numpy as np
@@ -74,8 +74,9 @@ def main():
     coords = mesh.coords()
     vol = np.abs(mg.det_j(mesh)).mean() / 6
     h = (6 * vol) ** (1.0 / 3)
-    for over in (1.5,):
-        mgp = pp.MG(A_phys, coords, h, bs, nu=nu, w=0.7, factor=2.0, cycle="V", over=over)
+    gs = "gs" in sys.argv   # node-block Gauss-Seidel smoothing instead of damped Jacobi
+    for over in ((1.0, 1.5) if gs else (1.5,)):
+        mgp = pp.MG(A_phys, coords, h, bs, nu=nu, w=0.7, factor=2.0, cycle="V", over=over, gs=gs)
         M = lambda r, mgp=mgp: mgp(r / s) / s     # noqa: E731
         x, it, res = pp.bicgstab(A, b, M, tol=tol)
         print(f"bicgstab  over={over}: {it} iterations = {2 * it} cycles + {2 * it} spmv, res {res:.1e}")

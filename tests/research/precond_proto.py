@@ -113,14 +113,24 @@ def prolong(agg, bs):
 class MG:
     """aggregation multigrid, block-Jacobi smoothing (nu pre + nu post, damping w), V- or W(K)-cycle."""
 
-    def __init__(self, A, coords, h, bs, nu=1, w=0.7, min_size=None, factor=2.0, cycle="V", over=1.0, smooth_p=False):
+    def __init__(self, A, coords, h, bs, nu=1, w=0.7, min_size=None, factor=2.0, cycle="V", over=1.0, smooth_p=False, gs=False):
         import os
         min_size = int(os.environ.get("MG_MIN", "400")) if min_size is None else min_size
         self.levels = []
         self.bs, self.nu, self.w, self.cycle, self.over = bs, nu, w, cycle, over
+        self.gs = gs   # node-block Gauss-Seidel (forward before, backward after the coarse correction) instead of damped Jacobi
         while True:
             Dinv = block_diag_inv(A, bs)
             lev = dict(A=A, Dinv=Dinv)
+            if gs:
+                B = A.tobsr(blocksize=(bs, bs))
+                B.sort_indices()
+                n = B.shape[0] // bs
+                rows = np.repeat(np.arange(n), np.diff(B.indptr))
+                for name, keep in (("fwd", B.indices <= rows), ("bwd", B.indices >= rows)):
+                    ptr = np.concatenate([[0], np.cumsum(np.bincount(rows[keep], minlength=n))])
+                    T = sp.bsr_matrix((B.data[keep], B.indices[keep], ptr), shape=B.shape)
+                    lev[name] = spl.splu(T.tocsc(), permc_spec="NATURAL")      # block triangle (D + L) / (D + U): no fill
             self.levels.append(lev)
             if A.shape[0] // bs <= min_size or len(self.levels) > 8:
                 lev["lu"] = spl.splu(A.tocsc())
@@ -136,24 +146,30 @@ class MG:
             coords = coarse_coords(coords, agg)
         print("   MG levels:", [l["A"].shape[0] // bs for l in self.levels], "nnz", [l["A"].nnz for l in self.levels])
 
-    def smooth(self, lev, x, b, n):
+    def smooth(self, lev, x, b, n, backward=False):
         for _ in range(n):
-            x = x + self.w * apply_bdinv(lev["Dinv"], b - lev["A"] @ x)
+            if self.gs:
+                x = x + lev["bwd" if backward else "fwd"].solve(b - lev["A"] @ x)
+            else:
+                x = x + self.w * apply_bdinv(lev["Dinv"], b - lev["A"] @ x)
         return x
 
     def cyc(self, k, b):
         lev = self.levels[k]
         if "lu" in lev:
             return lev["lu"].solve(b)
-        x = self.w * apply_bdinv(lev["Dinv"], b)
-        x = self.smooth(lev, x, b, self.nu - 1)
+        if self.gs:
+            x = self.smooth(lev, np.zeros_like(b), b, self.nu)
+        else:
+            x = self.w * apply_bdinv(lev["Dinv"], b)
+            x = self.smooth(lev, x, b, self.nu - 1)
         r = b - lev["A"] @ x
         rc = lev["P"].T @ r
         ec = self.cyc(k + 1, rc)
         if self.cycle == "W":
             ec = ec + self.cyc(k + 1, rc - self.levels[k + 1]["A"] @ ec)
         x = x + self.over * (lev["P"] @ ec)
-        x = self.smooth(lev, x, b, self.nu)
+        x = self.smooth(lev, x, b, self.nu, backward=True)
         return x
 
     def __call__(self, r):
